@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py -- primary+adjoint Mrays/s of the differentiable SDF rendering hot path.
+
+Step = one optimisation-loop view as python/shape_opt.py:78-83 drives it: primal render at
+spp*primal_spp_mult (256) + adjoint re-render/backprop at spp_grad (64), 256^3 SDF + 256^3x3 reflectance
+grid, 512x512 film (BASELINE.json configs[2], the configuration the metric is quoted on).
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU oracle (the restated reference) instead.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (sdf kind, sdf res, albedo res, W, H, adjoint spp, primal mult, n_sensors)
+    'c3_blobs256_tex_512x512_64spp': ('blobs', 256, 256, 512, 512, 64, 4, 12),
+    'c2_blobs128_256x256_16spp': ('blobs', 128, None, 256, 256, 16, 4, 12),
+    'c1_sphere64_128x128_4spp': ('sphere', 64, None, 128, 128, 4, 4, 6),
+    'c4_blobs512_512x512_64spp': ('blobs', 512, None, 512, 512, 64, 4, 12),
+}
+METRIC = "primary+adjoint Mrays/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='sdfrt', choices=['sdfrt', 'reference'])
+    ap.add_argument('--workload', default='c3_blobs256_tex_512x512_64spp', choices=list(WORKLOADS))
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cpu-sample-lanes', type=int, default=0, help='lanes per pass of the CPU sample (0 = auto)')
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index=0):
+        self.samples, self.stop, self.index = [], False, index
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits'],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([s.strip() for s in out.split(',')])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.t.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        mx = max(int(s[1]) for s in self.samples if s[1].isdigit())
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for k, n in enumerate(names) if any(s[2 + k].lower().startswith('active') for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (restated reference) on a bounded sample of the same workload
+# ------------------------------------------------------------------------------------------------
+def build_oracle_scene(wl, dtype):
+    import numpy as np
+    import torch
+    from oracle import sdf_oracle as O
+    kind, R, AR, W, H, spp, mult, nsens = WORKLOADS[wl]
+    origins = O.regular_camera_origins(nsens)
+    sensor = O.Sensor(to_world=O.look_at(origins[0], [0.5, 0.5, 0.5], [0, 1, 0]), width=W, height=H)
+    sys.path.insert(0, ROOT)
+    import sdfrt.synthetic as syn
+    sdf = O.Grid3d(syn.make_sdf_device(kind, R, 'cpu').to(dtype))
+    alb = None if AR is None else torch.from_numpy(syn.make_albedo_grid(AR)).to(dtype)
+    sc = O.Scene(sdf=sdf, sensor=sensor, albedo_grid=alb)
+    wf = O.WarpField2D(sdf, weight_strategy=6, edge_eps=0.01)
+    wf.clamping_thresh = 0.05
+    return O, sc, wf
+
+
+def cpu_sample_pass(O, sc, wf, wl, lanes, seed):
+    """One bounded sample: `lanes` primal lanes + `lanes//mult` adjoint lanes (same 4:1 ratio as the workload),
+    taken from the middle of the wavefront (object-covering rows).  Returns (rays, seconds)."""
+    import torch
+    kind, R, AR, W, H, spp, mult, nsens = WORKLOADS[wl]
+    b = sc.sensor.border
+    wf_p = (W + 2 * b) * (H + 2 * b) * spp * mult
+    wf_a = (W + 2 * b) * (H + 2 * b) * spp
+    n_a = max(spp, lanes // mult)
+    t0 = time.perf_counter()
+    lo = wf_p // 2 - lanes // 2
+    with torch.no_grad():
+        O.render(sc, wf, 'sdf_direct_reparam', seed, spp * mult, lane_range=(lo, lo + lanes), develop=False)
+    lo = wf_a // 2 - n_a // 2
+    sdf = sc.sdf
+    d0, a0 = sdf.data, sc.albedo_grid
+    sdf.data = d0.detach().clone().requires_grad_(True)
+    if a0 is not None:
+        sc.albedo_grid = a0.detach().clone().requires_grad_(True)
+    try:
+        acc = O.render(sc, wf, 'sdf_direct_reparam', seed + 13, spp, mode_backward=True, lane_range=(lo, lo + n_a), develop=False)
+        loss = (acc[..., :3] / acc[..., 3:4].clamp_min(1e-3)).sum()
+        loss.backward()
+    finally:
+        sdf.data, sc.albedo_grid = d0, a0
+    return lanes + n_a, time.perf_counter() - t0
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation = the oracle port (Mitsuba/Dr.Jit cannot be installed)."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    import torch
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    O, sc, wf = build_oracle_scene(args.workload, torch.float32)
+    lanes = args.cpu_sample_lanes or 65536
+    for w in range(args.warmup):
+        cpu_sample_pass(O, sc, wf, args.workload, max(4096, lanes // 8), w)
+    rays = secs = 0.0
+    for s in range(args.steps):
+        r, t = cpu_sample_pass(O, sc, wf, args.workload, lanes, 100 + s)
+        rays += r
+        secs += t
+    val = rays / secs / 1e6
+    sample = f"{lanes} primal + {lanes // WORKLOADS[args.workload][6]} adjoint lanes per step from the wavefront centre"
+    line = {"metric": METRIC, "value": val, "unit": "Mrays/s", "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "note": "oracle port of the reference (Mitsuba llvm_ad_rgb unavailable offline)"},
+            "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import sdfrt
+    from sdfrt import synthetic as syn
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run for --gpus > 1")
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    kind, R, AR, W, H, spp, mult, nsens = WORKLOADS[args.workload]
+    ctx = sdfrt.Context(local)
+    sdf = syn.make_sdf_device(kind, R, dev)
+    alb = None if AR is None else torch.from_numpy(syn.make_albedo_grid(AR)).to(dev)
+    sensor = sdfrt.get_regular_cameras(nsens, resx=W, resy=H)[0]
+    ctx.set_sdf(sdf)
+    ctx.set_albedo(alb)
+    ctx.set_sensor(sensor.to_world, W, H)
+    ctx.set_shading()
+    ctx.set_integrator('sdf_direct_reparam')
+    ctx.set_warp()
+    ctx.set_partition(rank, world)
+    Hb, Wb, b = ctx.film_dims()
+    n_primal, n_adj = Hb * Wb * spp * mult, Hb * Wb * spp
+    film_p, film_a = ctx.new_film(), ctx.new_film()
+    image = torch.empty((H, W, 3), device=dev)
+    grad_image = torch.ones((H, W, 3), device=dev)  # loss = dr.sum(img), figures/benchmark/benchmark.py:44
+    grad_sdf = torch.zeros_like(sdf)
+    grad_alb = None if alb is None else torch.zeros_like(alb)
+    stream = torch.cuda.current_stream(dev)
+
+    ev = {k: [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)] for k in ('p0', 'p1', 'a0', 'a1', 'b1')}
+
+    def step(i, seed, timed):
+        if timed:
+            ev['p0'][i].record(stream)
+        ctx.render_primal(seed, spp * mult, film_p)
+        if world > 1:
+            dist.all_reduce(film_p)
+        ctx.develop(film_p, image)
+        if timed:
+            ev['p1'][i].record(stream)
+        grad_sdf.zero_()
+        if grad_alb is not None:
+            grad_alb.zero_()
+        if timed:
+            ev['a0'][i].record(stream)
+        ctx.adjoint_accumulate(seed + 1 + nsens, spp, film_a)
+        if world > 1:
+            dist.all_reduce(film_a)
+        if timed:
+            ev['a1'][i].record(stream)
+        ctx.adjoint_backprop(film_a, grad_image, grad_sdf, grad_alb)
+        if world > 1:
+            dist.all_reduce(grad_sdf)
+            if grad_alb is not None:
+                dist.all_reduce(grad_alb)
+        if timed:
+            ev['b1'][i].record(stream)
+
+    for w in range(args.warmup):
+        step(0, w * (1 + nsens), False)
+    torch.cuda.synchronize(dev)
+    ctx.stats(reset=True)
+    if world > 1:
+        dist.barrier()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        torch.cuda.synchronize(dev)
+        t0.record(stream)
+        for s in range(args.steps):
+            step(s, 1000 + s * (1 + nsens), True)
+        t1.record(stream)
+        torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    ms = t0.elapsed_time(t1)
+    tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms = tt.item()
+    stats = ctx.stats(reset=True)
+    rays_per_step = n_primal + n_adj
+    value = rays_per_step * args.steps / (ms * 1e-3) / 1e6
+
+    # per-kernel timings (this rank) and the roofline of the dominant kernel
+    t_primal = sum(ev['p0'][i].elapsed_time(ev['p1'][i]) for i in range(args.steps)) / args.steps
+    t_accum = sum(ev['a0'][i].elapsed_time(ev['a1'][i]) for i in range(args.steps)) / args.steps
+    t_back = sum(ev['a1'][i].elapsed_time(ev['b1'][i]) for i in range(args.steps)) / args.steps
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    peak = float(peaks.get('hbm_gbs', 6650.0))
+    peak_src = 'measured' if 'hbm_gbs' in peaks else 'fallback'
+    # algorithmic bytes: 256 B per 64-tap evaluation (+ 2x256 B per adjoint scatter site), this rank, per step
+    ev_bytes = 256.0 * (stats['n_evals_value'] + stats['n_evals_grad'] + stats['n_evals_hess']) / args.steps
+    sc_bytes = 512.0 * stats['n_scatter_sites'] / args.steps
+    kernels = {'k_forward<primal>': t_primal, 'k_forward<diff>': t_accum, 'k_backward': t_back}
+    dom = max(kernels, key=kernels.get)
+    alg_bytes = ev_bytes + sc_bytes
+    achieved = alg_bytes / ((t_primal + t_accum + t_back) * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "dominant_kernel": dom,
+                "kernel_ms": kernels, "algorithmic_bytes_per_step": alg_bytes,
+                "note": "fetch-level bytes (256 B per B-spline evaluation); the 256^3 grid is L2-resident, see DESIGN.md"}
+
+    # e2e through the host-buffer C-ABI entry point (single GPU): H2D sdf + D2H image + grad every step
+    e2e = None
+    if world == 1:
+        sdf_h = sdf.cpu().pin_memory()
+        img_h = torch.empty((H, W, 3)).pin_memory()
+        g_h = torch.empty((R, R, R)).pin_memory()
+        for w in range(2):
+            ctx.render_view_host(sdf_h, w, spp * mult, w + 1 + nsens, spp, None, img_h, g_h)
+        torch.cuda.synchronize(dev)
+        e_steps = max(1, min(args.steps, 5))
+        tw = time.perf_counter()
+        for s in range(e_steps):
+            ctx.render_view_host(sdf_h, 1000 + s, spp * mult, 1001 + s + nsens, spp, None, img_h, g_h)
+        tw = time.perf_counter() - tw
+        e2e = {"value": rays_per_step * e_steps / tw / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": sdf_h.numel() * 4,
+               "d2h_bytes_per_step": img_h.numel() * 4 + g_h.numel() * 4, "steps": e_steps}
+        ctx.set_sdf(sdf)
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = len(os.sched_getaffinity(0))
+        torch.set_num_threads(cores)
+        O, osc, owf = build_oracle_scene(args.workload, torch.float32)
+        lanes = args.cpu_sample_lanes or 65536
+        cpu_sample_pass(O, osc, owf, args.workload, 8192, 0)
+        r, t = cpu_sample_pass(O, osc, owf, args.workload, lanes, 100)
+        cpu_baseline = {"value": r / t / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
+                        "sample": f"{lanes} primal + {lanes // mult} adjoint lanes from the wavefront centre, {t:.1f} s"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": args.workload, "sdf_res": R, "albedo_res": AR, "film": [W, H], "spp_primal": spp * mult,
+                           "spp_adjoint": spp, "rays_per_step": rays_per_step, "partition": f"film rows x{world}",
+                           "l2": "inputs (sdf+albedo+grads+lane records > 1 GB) exceed L2; no explicit flush"},
+                "clocks": clk.summary(), "e2e": e2e, "gpu_launches": 5 * args.steps,
+                "roofline": roofline, "cpu_baseline": cpu_baseline, "stats_per_step": {k: v / args.steps for k, v in stats.items()}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    a = parse()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_gpu(a)

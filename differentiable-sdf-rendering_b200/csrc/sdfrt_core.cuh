@@ -1,0 +1,667 @@
+// sdfrt_core.cuh -- per-ray math of the differentiable SDF rendering hot path (fp32).
+//
+// Everything here is straight-line per-lane arithmetic shared by the CUDA kernels in
+// sdfrt_kernels.cu.  The functions are `__host__ __device__` so that a developer harness
+// (tests/host_harness.cpp, CPU-only unit tests of the *math*) can call them; the shipped
+// library only ever calls them from device code.
+//
+// Reference semantics (paths relative to the upstream repository):
+//   python/shapes.py      SDFBase.ray_intersect & friends, Grid3d cubic B-spline lookups
+//   python/warp.py        WarpField2D
+//   python/math_util.py   normalize_sqr, bbox_distance_inside_d
+//   python/integrators/   reparam.py, sdf_direct_reparam.py, sdf_silhouette_reparam.py,
+//                         sdf_simple_shading_reparam.py
+// Third-party behaviour (cubic texture, PCG32/TEA, perspective sensor, gaussian film,
+// constant emitter, diffuse BSDF) is restated in oracle/ref_semantics.md.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define SDFRT_HD __host__ __device__ __forceinline__
+#else
+#define SDFRT_HD inline
+#endif
+
+namespace sdfrt {
+
+// ------------------------------------------------------------------------------------
+// vectors
+// ------------------------------------------------------------------------------------
+struct V3 {
+    float x, y, z;
+};
+SDFRT_HD V3 v3(float x, float y, float z) { return V3{x, y, z}; }
+SDFRT_HD V3 v3(float s) { return V3{s, s, s}; }
+SDFRT_HD V3 operator+(V3 a, V3 b) { return V3{a.x + b.x, a.y + b.y, a.z + b.z}; }
+SDFRT_HD V3 operator-(V3 a, V3 b) { return V3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+SDFRT_HD V3 operator-(V3 a) { return V3{-a.x, -a.y, -a.z}; }
+SDFRT_HD V3 operator*(V3 a, float s) { return V3{a.x * s, a.y * s, a.z * s}; }
+SDFRT_HD V3 operator*(float s, V3 a) { return V3{a.x * s, a.y * s, a.z * s}; }
+SDFRT_HD V3 operator*(V3 a, V3 b) { return V3{a.x * b.x, a.y * b.y, a.z * b.z}; }
+SDFRT_HD V3 operator/(V3 a, float s) { return V3{a.x / s, a.y / s, a.z / s}; }
+SDFRT_HD V3& operator+=(V3& a, V3 b) { a.x += b.x; a.y += b.y; a.z += b.z; return a; }
+SDFRT_HD float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+SDFRT_HD V3 normalize(V3 a) { return a / sqrtf(dot(a, a)); }
+SDFRT_HD float sign1(float x) { return x >= 0.f ? 1.f : -1.f; }  // dr.sign
+SDFRT_HD float fminf3(V3 a) { return fminf(a.x, fminf(a.y, a.z)); }
+SDFRT_HD float comp(V3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
+
+// symmetric 3x3 (Hessian): xx yy zz xy xz yz
+struct S3 {
+    float xx, yy, zz, xy, xz, yz;
+};
+SDFRT_HD V3 mul(const S3& H, V3 v) {
+    return V3{H.xx * v.x + H.xy * v.y + H.xz * v.z, H.xy * v.x + H.yy * v.y + H.yz * v.z,
+              H.xz * v.x + H.yz * v.y + H.zz * v.z};
+}
+// general 3x3, row major
+struct M3 {
+    float m[3][3];
+};
+SDFRT_HD V3 mul(const M3& A, V3 v) {
+    return V3{A.m[0][0] * v.x + A.m[0][1] * v.y + A.m[0][2] * v.z, A.m[1][0] * v.x + A.m[1][1] * v.y + A.m[1][2] * v.z,
+              A.m[2][0] * v.x + A.m[2][1] * v.y + A.m[2][2] * v.z};
+}
+SDFRT_HD V3 mulT(const M3& A, V3 v) {
+    return V3{A.m[0][0] * v.x + A.m[1][0] * v.y + A.m[2][0] * v.z, A.m[0][1] * v.x + A.m[1][1] * v.y + A.m[2][1] * v.z,
+              A.m[0][2] * v.x + A.m[1][2] * v.y + A.m[2][2] * v.z};
+}
+
+// ------------------------------------------------------------------------------------
+// parameters (plain data; mirrors include/sdfrt.h)
+// ------------------------------------------------------------------------------------
+struct GridView {
+    const float* data;  // (rz, ry, rx), x fastest
+    int rx, ry, rz;
+    float px, py, pz;  // sdf.p: lookups use x - p (python/shapes.py:408-414)
+};
+struct AlbedoView {
+    const float* data;  // (rz, ry, rx, 3) or nullptr
+    int rx, ry, rz;
+    float cr, cg, cb;  // constant reflectance when data == nullptr
+};
+struct TracerParams {
+    float step_scale, trace_eps;
+    int refine_intersection, use_extra_weight;
+    float extra_thresh, sil_weight_offset, sil_weight_epsilon;
+    int weight_power, use_weight_sum_weight, max_steps;
+};
+struct WarpParams {
+    int kind;
+    float edge_eps;
+    int weight_strategy;
+    float clamping_thresh;
+    int normalize_warp_field, max_reparam_depth;
+};
+struct SensorParams {
+    float R[3][3];  // camera -> world rotation (columns left, up, dir)
+    float c[3];     // camera origin
+    float tan_half_fov, aspect, near_clip, far_clip;
+    int W, H, border;
+    float filter_radius, filter_alpha, filter_bias;  // gaussian: exp(alpha x^2) - bias
+};
+struct ShadingParams {
+    float Le[3];
+    float env_dist;
+    int hide_emitters;
+};
+struct Counters {  // device work counters (unsigned long long for atomicAdd)
+    unsigned long long n_rays, n_evals_value, n_evals_grad, n_evals_hess, n_scatter_sites, n_albedo_lookups,
+        n_steps_max, n_hits;
+};
+
+constexpr float kBBoxDelta = 0.05f;     // python/shapes.py:416-418
+constexpr float kRayEpsilon = 1500.f * 5.9604644775390625e-08f;  // mitsuba math::RayEpsilon<float>
+constexpr float kShadowEpsilon = 10.f * kRayEpsilon;
+constexpr float kPi = 3.14159265358979323846f;
+
+// ------------------------------------------------------------------------------------
+// Sampler: PCG32 seeded through TEA (mitsuba `independent`), oracle/ref_semantics.md S2
+// ------------------------------------------------------------------------------------
+struct Pcg32 {
+    uint64_t state, inc;
+};
+SDFRT_HD uint32_t pcg_next_u32(Pcg32& r) {
+    uint64_t old = r.state;
+    r.state = old * 0x5851F42D4C957F2DULL + r.inc;
+    uint32_t xs = (uint32_t)(((old >> 18u) ^ old) >> 27u);
+    uint32_t rot = (uint32_t)(old >> 59u);
+    return (xs >> rot) | (xs << ((32u - rot) & 31u));
+}
+SDFRT_HD float pcg_next_f32(Pcg32& r) {
+    uint32_t bits = (pcg_next_u32(r) >> 9) | 0x3f800000u;
+    float f;
+#if defined(__CUDA_ARCH__)
+    f = __uint_as_float(bits);
+#else
+    union { uint32_t u; float f; } cv; cv.u = bits; f = cv.f;
+#endif
+    return f - 1.f;
+}
+SDFRT_HD Pcg32 sampler_seed(uint32_t seed, uint32_t lane) {
+    uint32_t v0 = seed, v1 = lane, sum = 0;
+    for (int i = 0; i < 4; ++i) {
+        sum += 0x9e3779b9u;
+        v0 += ((v1 << 4) + 0xa341316cu) ^ (v1 + sum) ^ ((v1 >> 5) + 0xc8013ea4u);
+        v1 += ((v0 << 4) + 0xad90777du) ^ (v0 + sum) ^ ((v0 >> 5) + 0x7e95761eu);
+    }
+    Pcg32 r;
+    r.state = 0;
+    r.inc = ((uint64_t)v1 << 1) | 1ull;
+    pcg_next_u32(r);
+    r.state += (uint64_t)v0;
+    pcg_next_u32(r);
+    return r;
+}
+
+// ------------------------------------------------------------------------------------
+// Tricubic B-spline lookups (drjit Texture3f.eval_cubic*, python/shapes.py:420-450)
+// ------------------------------------------------------------------------------------
+SDFRT_HD void bspline_w(float a, float w[4]) {
+    float a2 = a * a, a3 = a2 * a;
+    w[0] = (-a3 + 3.f * a2 - 3.f * a + 1.f) * (1.f / 6.f);
+    w[1] = (3.f * a3 - 6.f * a2 + 4.f) * (1.f / 6.f);
+    w[2] = (-3.f * a3 + 3.f * a2 + 3.f * a + 1.f) * (1.f / 6.f);
+    w[3] = a3 * (1.f / 6.f);
+}
+SDFRT_HD void bspline_dw(float a, float w[4]) {
+    float a2 = a * a;
+    w[0] = -0.5f * a2 + a - 0.5f;
+    w[1] = 1.5f * a2 - 2.f * a;
+    w[2] = -1.5f * a2 + a + 0.5f;
+    w[3] = 0.5f * a2;
+}
+SDFRT_HD void bspline_ddw(float a, float w[4]) {
+    w[0] = 1.f - a;
+    w[1] = 3.f * a - 2.f;
+    w[2] = -3.f * a + 1.f;
+    w[3] = a;
+}
+
+struct CellCoord {  // base tap index (may be out of range -> clamped per tap) and fractional offsets
+    int ix, iy, iz;
+    float ax, ay, az;
+    bool interior;
+};
+SDFRT_HD CellCoord cell_coord(const GridView& G, V3 x) {
+    CellCoord c;
+    float ux = (x.x - G.px) * (float)G.rx - 0.5f;
+    float uy = (x.y - G.py) * (float)G.ry - 0.5f;
+    float uz = (x.z - G.pz) * (float)G.rz - 0.5f;
+    float fx = floorf(ux), fy = floorf(uy), fz = floorf(uz);
+    c.ax = ux - fx; c.ay = uy - fy; c.az = uz - fz;
+    // keep the int conversion defined for far-away points (texels clamp anyway)
+    fx = fminf(fmaxf(fx, -4.f), (float)G.rx + 4.f);
+    fy = fminf(fmaxf(fy, -4.f), (float)G.ry + 4.f);
+    fz = fminf(fmaxf(fz, -4.f), (float)G.rz + 4.f);
+    c.ix = (int)fx - 1; c.iy = (int)fy - 1; c.iz = (int)fz - 1;
+    c.interior = (c.ix >= 0) & (c.iy >= 0) & (c.iz >= 0) & (c.ix + 3 < G.rx) & (c.iy + 3 < G.ry) & (c.iz + 3 < G.rz);
+    return c;
+}
+SDFRT_HD int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// ORDER 0: value; 1: + gradient; 2: + Hessian.  Separable evaluation: x-reduction per row,
+// then y, then z (~1/2 the FMAs of the naive 64 x 10 form).
+template <int ORDER>
+SDFRT_HD void eval_sdf(const GridView& G, V3 x, float& v, V3& g, S3& H) {
+    const CellCoord c = cell_coord(G, x);
+    float wx[4], wy[4], wz[4], dx[4], dy[4], dz[4], ex[4], ey[4], ez[4];
+    bspline_w(c.ax, wx); bspline_w(c.ay, wy); bspline_w(c.az, wz);
+    if (ORDER >= 1) { bspline_dw(c.ax, dx); bspline_dw(c.ay, dy); bspline_dw(c.az, dz); }
+    if (ORDER >= 2) { bspline_ddw(c.ax, ex); bspline_ddw(c.ay, ey); bspline_ddw(c.az, ez); }
+    int xo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) xo[i] = c.interior ? (c.ix + i) : clampi(c.ix + i, 0, G.rx - 1);
+    float r_v = 0, r_gx = 0, r_gy = 0, r_gz = 0, r_xx = 0, r_yy = 0, r_zz = 0, r_xy = 0, r_xz = 0, r_yz = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int zz = c.interior ? (c.iz + k) : clampi(c.iz + k, 0, G.rz - 1);
+        float A0 = 0, A1 = 0, A2 = 0, B0 = 0, B1 = 0, C0 = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int yy = c.interior ? (c.iy + j) : clampi(c.iy + j, 0, G.ry - 1);
+            const float* row = G.data + ((size_t)zz * G.ry + yy) * (size_t)G.rx;
+            const float f0 = row[xo[0]], f1 = row[xo[1]], f2 = row[xo[2]], f3 = row[xo[3]];
+            const float a = wx[0] * f0 + wx[1] * f1 + wx[2] * f2 + wx[3] * f3;
+            A0 += wy[j] * a;
+            if (ORDER >= 1) {
+                const float b = dx[0] * f0 + dx[1] * f1 + dx[2] * f2 + dx[3] * f3;
+                A1 += dy[j] * a;
+                B0 += wy[j] * b;
+                if (ORDER >= 2) {
+                    const float cc = ex[0] * f0 + ex[1] * f1 + ex[2] * f2 + ex[3] * f3;
+                    A2 += ey[j] * a;
+                    B1 += dy[j] * b;
+                    C0 += wy[j] * cc;
+                }
+            }
+        }
+        r_v += wz[k] * A0;
+        if (ORDER >= 1) {
+            r_gz += dz[k] * A0;
+            r_gy += wz[k] * A1;
+            r_gx += wz[k] * B0;
+            if (ORDER >= 2) {
+                r_zz += ez[k] * A0;
+                r_yz += dz[k] * A1;
+                r_yy += wz[k] * A2;
+                r_xz += dz[k] * B0;
+                r_xy += wz[k] * B1;
+                r_xx += wz[k] * C0;
+            }
+        }
+    }
+    v = r_v;
+    if (ORDER >= 1) {
+        const float sx = (float)G.rx, sy = (float)G.ry, sz = (float)G.rz;
+        g = V3{r_gx * sx, r_gy * sy, r_gz * sz};
+        if (ORDER >= 2) {
+            H.xx = r_xx * sx * sx; H.yy = r_yy * sy * sy; H.zz = r_zz * sz * sz;
+            H.xy = r_xy * sx * sy; H.xz = r_xz * sx * sz; H.yz = r_yz * sy * sz;
+        }
+    }
+}
+SDFRT_HD float eval_value(const GridView& G, V3 x) {
+    float v; V3 g; S3 H;
+    eval_sdf<0>(G, x, v, g, H);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------
+// math_util.bbox_distance_inside_d (python/math_util.py:31-41); bbox = unit cube +- 0.05
+// ------------------------------------------------------------------------------------
+SDFRT_HD float bbox_distance_inside_d(V3 x, V3& dist_d) {
+    const float lo = -kBBoxDelta, hi = 1.f + kBBoxDelta;
+    const V3 dmin = V3{x.x - lo, x.y - lo, x.z - lo};
+    const V3 dmax = V3{hi - x.x, hi - x.y, hi - x.z};
+    const float dist = fmaxf(0.f, fminf(fminf3(dmin), fminf3(dmax)));
+    const V3 amax = V3{fabsf(dmax.x), fabsf(dmax.y), fabsf(dmax.z)};
+    const V3 amin = V3{fabsf(dmin.x), fabsf(dmin.y), fabsf(dmin.z)};
+    const V3 md = V3{fminf(amin.x, amax.x), fminf(amin.y, amax.y), fminf(amin.z, amax.z)};
+    V3 n = v3(0.f);
+    if ((md.x < md.y) & (md.x < md.z)) n = v3(1, 0, 0);
+    if ((md.y < md.z) & (md.y < md.x)) n = v3(0, 1, 0);
+    if ((md.z < md.x) & (md.z < md.y)) n = v3(0, 0, 1);
+    dist_d = v3(0.f);
+    if (dist > 0.f) dist_d = V3{n.x * sign1(amax.x - amin.x), n.y * sign1(amax.y - amin.y), n.z * sign1(amax.z - amin.z)};
+    return dist;
+}
+
+// ------------------------------------------------------------------------------------
+// Ray / AABB (mitsuba BoundingBox3f::ray_intersect + contains), python/shapes.py:129-141
+// ------------------------------------------------------------------------------------
+struct BoxHit {
+    bool intersects, inside;
+    float mint, maxt;
+};
+SDFRT_HD BoxHit ray_box(V3 o, V3 d) {
+    const float lo = -kBBoxDelta, hi = 1.f + kBBoxDelta;
+    BoxHit b;
+    const V3 r = V3{1.f / d.x, 1.f / d.y, 1.f / d.z};
+    const V3 t1 = V3{(lo - o.x) * r.x, (lo - o.y) * r.y, (lo - o.z) * r.z};
+    const V3 t2 = V3{(hi - o.x) * r.x, (hi - o.y) * r.y, (hi - o.z) * r.z};
+    b.mint = fmaxf(fminf(t1.x, t2.x), fmaxf(fminf(t1.y, t2.y), fminf(t1.z, t2.z)));
+    b.maxt = fminf(fmaxf(t1.x, t2.x), fminf(fmaxf(t1.y, t2.y), fmaxf(t1.z, t2.z)));
+    const bool inx = (o.x >= lo) & (o.x <= hi), iny = (o.y >= lo) & (o.y <= hi), inz = (o.z >= lo) & (o.z <= hi);
+    b.inside = inx & iny & inz;
+    const bool act = ((d.x != 0.f) | inx) & ((d.y != 0.f) | iny) & ((d.z != 0.f) | inz);
+    b.intersects = act & (b.maxt >= b.mint);
+    b.intersects = b.intersects & ((b.mint > 0.f) | b.inside);  // python/shapes.py:132
+    return b;
+}
+
+// ------------------------------------------------------------------------------------
+// SDFBase.eval_trace_weight (python/shapes.py:68-113, use_weight_ad == False)
+// ------------------------------------------------------------------------------------
+SDFRT_HD float ipow(float b, int e) {
+    float r = 1.f;
+    for (int i = 0; i < e; ++i) r *= b;
+    return r;
+}
+SDFRT_HD float eval_trace_weight(const TracerParams& P, V3 d, int i, V3 x, float sdf_value, V3 g, const S3& H, V3& weight_d) {
+    const float n_dot_d = dot(g, d);
+    const float n_dot_n = dot(g, g);
+    const float dot_ratio = n_dot_d / n_dot_n;
+    const float denom = P.sil_weight_epsilon + fabsf(sdf_value) + P.sil_weight_offset * n_dot_d * dot_ratio;
+    const float dist_weight = 1.f / ipow(denom, P.weight_power);
+    V3 bbox_dist_d;
+    const float bbox_dist = bbox_distance_inside_d(x, bbox_dist_d);
+    const float bbox_eps = 0.01f;
+    const float bbox_weight = (i > 0) ? fminf(bbox_dist, bbox_eps) / bbox_eps : 1.f;
+    const float weight = dist_weight * bbox_weight;
+    const V3 bbox_weight_d = ((i > 0) & (bbox_dist < bbox_eps)) ? bbox_dist_d / bbox_eps : v3(0.f);
+    const V3 gradient = (2.f * dot_ratio) * (d - dot_ratio * g);
+    const V3 denom_d = sign1(sdf_value) * g + P.sil_weight_offset * mul(H, gradient);  // gradient @ H (H symmetric)
+    const V3 dist_weight_d = (-(float)P.weight_power * dist_weight / denom) * denom_d;
+    weight_d = dist_weight * bbox_weight_d + bbox_weight * dist_weight_d;
+    return weight;
+}
+
+// ------------------------------------------------------------------------------------
+// Tracer outputs (python/shapes.py:288)
+// ------------------------------------------------------------------------------------
+struct TraceOut {
+    float its_t, warp_t, warp_weight;
+    V3 warp_t_d, warp_weight_d;
+    int n_steps;
+};
+
+// refine loop, python/shapes.py:245-257 / :323-334
+SDFRT_HD float refine_hit(const GridView& G, const TracerParams& P, V3 o, V3 d, float its_t, float trace_eps, int& n_evals) {
+    if (!P.refine_intersection || !isfinite(its_t)) return its_t;
+    for (int i = 0; i < 10; ++i) {
+        const float md = eval_value(G, o + its_t * d);
+        ++n_evals;
+        its_t += md * (10.f / (10.f + (float)i));
+        if (!((md <= 0.f) | (md > trace_eps))) break;
+    }
+    return its_t;
+}
+
+// SDFBase.ray_intersect_non_diff, python/shapes.py:290-339
+SDFRT_HD float trace_non_diff(const GridView& G, const TracerParams& P, V3 o, V3 d, float ray_maxt, bool do_refine,
+                              int& n_steps, int& n_evals) {
+    d = normalize(d);
+    const BoxHit b = ray_box(o, d);
+    const float maxt = fminf(b.maxt, ray_maxt);
+    const float trace_eps = P.trace_eps * fmaxf(maxt, 1.f);
+    float its_t = INFINITY;
+    float t = b.inside ? 0.f : b.mint + 1e-5f;
+    bool active = b.intersects;
+    int i = 0;
+    while (active && i < P.max_steps) {
+        float v = eval_value(G, o + t * d);
+        if (P.step_scale != 1.f) v *= P.step_scale;
+        const bool hit = v < trace_eps;
+        if (hit) its_t = t;
+        active = (t <= maxt) & !hit;
+        t += hit ? 0.f : fabsf(v);
+        active = active & (t <= maxt);
+        ++i;
+    }
+    n_steps = i;
+    n_evals += i;
+    if (do_refine) its_t = refine_hit(G, P, o, d, its_t, trace_eps, n_evals);
+    return its_t;
+}
+
+// SDFBase.ray_intersect (differentiable tracer), python/shapes.py:115-288
+SDFRT_HD void trace_diff(const GridView& G, const TracerParams& P, V3 o, V3 d, float ray_maxt, bool do_refine, TraceOut& out,
+                         int& n_evals_hess, int& n_evals_value) {
+    d = normalize(d);
+    const BoxHit b = ray_box(o, d);
+    const float maxt = fminf(b.maxt, ray_maxt);
+    const float trace_eps = P.trace_eps * fmaxf(maxt, 1.f);
+    float its_t = INFINITY;
+    float t = b.inside ? 0.f : b.mint + 1e-5f;
+    float warp_t = 0.f, prev_surf_dist = 0.f, weight_sum = 0.f, extra_weight_sum = 0.f;
+    V3 prev_sdf_grad_c = v3(0.f), mixed_sum_d = v3(0.f), weight_d_sum = v3(0.f), extra_weight_sum_d = v3(0.f);
+    // entry face of the bounding box and initial dt/dx (python/shapes.py:155-164)
+    V3 t_d = v3(0.f);
+    {
+        const float lo = -kBBoxDelta, hi = 1.f + kBBoxDelta;
+        const V3 q = o + t * d;
+        const V3 md = V3{fminf(fabsf(lo - q.x), fabsf(hi - q.x)), fminf(fabsf(lo - q.y), fabsf(hi - q.y)),
+                         fminf(fabsf(lo - q.z), fabsf(hi - q.z))};
+        V3 n = v3(0.f);
+        if ((md.x < md.y) & (md.x < md.z)) n = v3(1, 0, 0);
+        if ((md.y < md.z) & (md.y < md.x)) n = v3(0, 1, 0);
+        if ((md.z < md.x) & (md.z < md.y)) n = v3(0, 0, 1);
+        const float d_dot_n = dot(d, n);
+        if (!b.inside && fabsf(d_dot_n) > 0.f) t_d = (-1.f / d_dot_n * t) * n;
+    }
+    bool active = b.intersects;
+    int i = 0;
+    while (active && i < P.max_steps) {
+        const V3 x = o + t * d;
+        float sdf_value; V3 g; S3 H;
+        eval_sdf<2>(G, x, sdf_value, g, H);
+        if (P.step_scale != 1.f) {
+            const float s = P.step_scale;
+            sdf_value *= s; g = g * s;
+            H.xx *= s; H.yy *= s; H.zz *= s; H.xy *= s; H.xz *= s; H.yz *= s;
+        }
+        const bool hit = sdf_value < trace_eps;
+        if (hit) its_t = t;
+        const float surf_dist = fabsf(sdf_value);
+        V3 weight_d;
+        float weight = eval_trace_weight(P, d, i, x, sdf_value, g, H, weight_d);
+        float inv_extra_w_den = 0.f, dist_difference = 0.f;
+        if (P.use_extra_weight) {
+            inv_extra_w_den = 1.f / fminf(P.extra_thresh, surf_dist);
+            dist_difference = prev_surf_dist - surf_dist;
+            extra_weight_sum += (dist_difference >= 0.f) ? dist_difference * inv_extra_w_den : 0.f;
+            extra_weight_sum = fminf(extra_weight_sum, 1.f);
+        }
+        const float curr_segment_value = hit ? 0.f : surf_dist;
+        const float segment_length = 0.5f * (curr_segment_value + prev_surf_dist);
+        float weight_increment = segment_length * weight;
+        if (P.use_extra_weight) weight_increment *= extra_weight_sum;
+        weight_sum += weight_increment;
+        warp_t += weight_increment * t;
+        // convert_deriv(in_d, t, t_d) = t * in_d + dot(d, in_d) * t_d   (python/shapes.py:126-127)
+        weight_d = t * weight_d + dot(d, weight_d) * t_d;
+        const V3 sdf_grad_c = t * g + dot(d, g) * t_d;
+        const V3 segment_d = 0.5f * (sdf_grad_c + prev_sdf_grad_c);
+        if (P.use_extra_weight) {
+            const V3 surf_dist_d = sign1(sdf_value) * sdf_grad_c;
+            V3 extra_w_d = (prev_sdf_grad_c - surf_dist_d) * inv_extra_w_den;
+            if (sdf_value < P.extra_thresh) extra_w_d = extra_w_d - (dist_difference * inv_extra_w_den * inv_extra_w_den) * surf_dist_d;
+            if (dist_difference > 0.f) extra_weight_sum_d += extra_w_d;
+            if ((extra_weight_sum >= 1.f) | (extra_weight_sum <= 0.f)) extra_weight_sum_d = v3(0.f);
+            weight_d = weight * extra_weight_sum_d + weight_d * extra_weight_sum;
+            weight *= extra_weight_sum;
+        }
+        const V3 weight_increment_d = weight * segment_d + weight_d * segment_length;
+        mixed_sum_d += weight_increment_d * t + (weight * segment_length) * t_d;
+        t_d += sdf_grad_c;
+        weight_d_sum += weight_increment_d;
+        ++i;
+        t += curr_segment_value;
+        prev_surf_dist = surf_dist;
+        prev_sdf_grad_c = sdf_grad_c;
+        active = (t <= maxt) & !hit;
+    }
+    n_evals_hess += i;
+    out.n_steps = i;
+    if (do_refine) its_t = refine_hit(G, P, o, d, its_t, trace_eps, n_evals_value);
+    out.its_t = its_t;
+    const float inv_weight_sum = 1.f / weight_sum;
+    warp_t = warp_t * inv_weight_sum;
+    V3 warp_t_d = (-warp_t * weight_d_sum + mixed_sum_d) * inv_weight_sum;
+    float warp_weight = 1.f;
+    V3 warp_weight_d = v3(0.f);
+    if (P.use_weight_sum_weight) {
+        warp_weight = fminf(fmaxf(weight_sum, 0.f), 1.f);
+        warp_weight_d = ((weight_sum > 0.f) & (weight_sum < 1.f)) ? weight_d_sum : v3(0.f);
+    }
+    const bool invalid = (weight_sum < 1e-7f) | !b.intersects | !isfinite(warp_t);
+    if (invalid) {
+        warp_t = INFINITY;
+        warp_t_d = v3(0.f);
+        warp_weight = 0.f;
+        warp_weight_d = v3(0.f);
+    }
+    out.warp_t = warp_t; out.warp_t_d = warp_t_d; out.warp_weight = warp_weight; out.warp_weight_d = warp_weight_d;
+}
+
+// ------------------------------------------------------------------------------------
+// WarpField2D.weight / weight_epsilon (python/warp.py:25-45)
+// ------------------------------------------------------------------------------------
+SDFRT_HD float warp_weight_fn(V3 x, float sdf_value, V3 g, float edge_eps, V3& w_d, float& edge_eps_d_out) {
+    V3 bbox_dist_d;
+    const float bbox_dist = bbox_distance_inside_d(x, bbox_dist_d);
+    const bool use_edge_eps = edge_eps <= bbox_dist;
+    const V3 edge_eps_d = use_edge_eps ? v3(0.f) : bbox_dist_d;
+    edge_eps = fminf(edge_eps, bbox_dist);
+    const float inv_edge_eps = 1.f / edge_eps;
+    const float surf_dist = fabsf(sdf_value);
+    const float fac = 1.f - surf_dist * inv_edge_eps;
+    const float w = fmaxf(fac, 0.f);
+    w_d = (-sign1(sdf_value) * inv_edge_eps) * g + (surf_dist * inv_edge_eps * inv_edge_eps) * edge_eps_d;
+    if (!(fac >= 0.f)) w_d = v3(0.f);
+    edge_eps_d_out = (use_edge_eps & (fac >= 0.f)) ? surf_dist * inv_edge_eps * inv_edge_eps : 0.f;
+    return w;
+}
+
+// The warp site: everything WarpField2D.eval (python/warp.py:47-96) contributes to the adjoint.
+// With outputs d = d0 <- dir and div = 1 <- tr(P J M), the derivative is linear in
+// (dphi, dg) at x = o + warp_t d0:
+//    d(div) = cphi_div * dphi + cg_div . dg          d(dir) = cphi_dir * dphi   (vector)
+// (derivation in DESIGN.md, "closed-form adjoint").
+struct WarpSite {
+    bool active;
+    float cphi_div;  // d div / d phi
+    V3 cg_div;       // d div / d g
+    V3 cphi_dir;     // d dir / d phi
+    float phi; V3 g; S3 H;  // evaluation at the site (for the chain rule through an attached origin)
+};
+SDFRT_HD WarpSite warp_site(const GridView& G, const WarpParams& W, const TracerParams& T, V3 o, V3 d0, float tau, V3 tau_d,
+                            float omega, V3 omega_d) {
+    WarpSite s;
+    s.active = false;
+    s.cphi_div = 0.f; s.cg_div = v3(0.f); s.cphi_dir = v3(0.f);
+    s.phi = 0.f; s.g = v3(0.f); s.H = S3{0, 0, 0, 0, 0, 0};
+    if (!isfinite(tau)) return s;
+    const V3 x = o + tau * d0;
+    float phi; V3 g; S3 H;
+    eval_sdf<2>(G, x, phi, g, H);
+    s.phi = phi; s.g = g; s.H = H;
+    // n' and J_n (python/warp.py:56-63)
+    V3 np;
+    M3 JnH;  // J_n @ H
+    if (W.normalize_warp_field) {
+        const float g2 = dot(g, g);
+        np = g / g2;
+        const float c2 = 2.f / (g2 * g2);
+        const V3 Hg = mul(H, g);  // (g g^T H)_ij = g_i (H g)_j   (H symmetric)
+        const float Hm[3][3] = {{H.xx, H.xy, H.xz}, {H.xy, H.yy, H.yz}, {H.xz, H.yz, H.zz}};
+        const float gv[3] = {g.x, g.y, g.z}, Hgv[3] = {Hg.x, Hg.y, Hg.z};
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) JnH.m[i][j] = Hm[i][j] / g2 - c2 * gv[i] * Hgv[j];
+    } else {
+        np = g;
+        JnH.m[0][0] = H.xx; JnH.m[0][1] = H.xy; JnH.m[0][2] = H.xz;
+        JnH.m[1][0] = H.xy; JnH.m[1][1] = H.yy; JnH.m[1][2] = H.yz;
+        JnH.m[2][0] = H.xz; JnH.m[2][1] = H.yz; JnH.m[2][2] = H.zz;
+    }
+    // weight of the warp field (python/warp.py:66-76)
+    const float eps = (W.weight_strategy == 6) ? W.edge_eps * tau : W.edge_eps;
+    V3 w_g; float eps_d;
+    float w = warp_weight_fn(x, phi, g, eps, w_g, eps_d);
+    w_g = w_g + (eps_d * W.edge_eps) * d0;
+    if (T.use_weight_sum_weight) {
+        w_g = w_g * omega + w * omega_d;
+        w *= omega;
+    }
+    if (!(w > 0.f)) return s;
+    // A = M P,  M = I + d0 (x) (tau_d / tau),  P = I - d0 d0^T   (python/warp.py:84-88)
+    const V3 q = tau_d / tau;
+    const float dv[3] = {d0.x, d0.y, d0.z}, qv[3] = {q.x, q.y, q.z};
+    float Pm[3][3], Mm[3][3];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            Pm[i][j] = (i == j ? 1.f : 0.f) - dv[i] * dv[j];
+            Mm[i][j] = (i == j ? 1.f : 0.f) + dv[i] * qv[j];
+        }
+    M3 A;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) A.m[i][j] = Mm[i][0] * Pm[0][j] + Mm[i][1] * Pm[1][j] + Mm[i][2] * Pm[2][j];
+    const V3 Anp = mul(A, np);
+    float trJHA = 0.f;  // tr(J_n H A)
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) trJHA += JnH.m[i][j] * A.m[j][i];
+    s.cphi_div = -dot(w_g, Anp) - w * trJHA;
+    s.cg_div = (-w) * Anp;
+    const float tc = fmaxf(W.clamping_thresh, tau);
+    const V3 Pnp = V3{Pm[0][0] * np.x + Pm[0][1] * np.y + Pm[0][2] * np.z, Pm[1][0] * np.x + Pm[1][1] * np.y + Pm[1][2] * np.z,
+                      Pm[2][0] * np.x + Pm[2][1] * np.y + Pm[2][2] * np.z};
+    s.cphi_dir = (-w / tc) * Pnp;
+    s.active = isfinite(s.cphi_div) & isfinite(s.cg_div.x + s.cg_div.y + s.cg_div.z) &
+               isfinite(s.cphi_dir.x + s.cphi_dir.y + s.cphi_dir.z);
+    return s;
+}
+
+// ------------------------------------------------------------------------------------
+// Sensor (mitsuba PerspectiveCamera) and film filter, oracle/ref_semantics.md S3-S4
+// ------------------------------------------------------------------------------------
+SDFRT_HD void sensor_sample_ray(const SensorParams& S, float px, float py, V3& o, V3& d, float& maxt) {
+    const float sx = px / (float)S.W, sy = py / (float)S.H;
+    V3 np = V3{(1.f - 2.f * sx) * S.tan_half_fov * S.near_clip, (1.f - 2.f * sy) * S.tan_half_fov / S.aspect * S.near_clip, S.near_clip};
+    const V3 dl = normalize(np);
+    d = V3{S.R[0][0] * dl.x + S.R[0][1] * dl.y + S.R[0][2] * dl.z, S.R[1][0] * dl.x + S.R[1][1] * dl.y + S.R[1][2] * dl.z,
+           S.R[2][0] * dl.x + S.R[2][1] * dl.y + S.R[2][2] * dl.z};
+    const float inv_z = 1.f / dl.z;
+    const float nt = S.near_clip * inv_z;
+    o = V3{S.c[0] + d.x * nt, S.c[1] + d.y * nt, S.c[2] + d.z * nt};
+    maxt = (S.far_clip - S.near_clip) * inv_z;
+}
+// sample_direction(it.p = o + d): uv (pixels); `inside` = importance > 0; ref = camera-space point
+SDFRT_HD void sensor_project(const SensorParams& S, V3 p, float& u, float& v, bool& inside, V3& ref) {
+    const V3 q = V3{p.x - S.c[0], p.y - S.c[1], p.z - S.c[2]};
+    ref = V3{S.R[0][0] * q.x + S.R[1][0] * q.y + S.R[2][0] * q.z, S.R[0][1] * q.x + S.R[1][1] * q.y + S.R[2][1] * q.z,
+             S.R[0][2] * q.x + S.R[1][2] * q.y + S.R[2][2] * q.z};
+    const float sx = 0.5f - 0.5f * ref.x / (ref.z * S.tan_half_fov);
+    const float sy = 0.5f - 0.5f * S.aspect * ref.y / (ref.z * S.tan_half_fov);
+    u = sx * (float)S.W;
+    v = sy * (float)S.H;
+    inside = (sx >= 0.f) & (sx <= 1.f) & (sy >= 0.f) & (sy <= 1.f) & (ref.z >= S.near_clip) & (ref.z <= S.far_clip);
+}
+SDFRT_HD float filter_eval(const SensorParams& S, float x) { return fmaxf(0.f, expf(S.filter_alpha * x * x) - S.filter_bias); }
+SDFRT_HD float filter_deriv(const SensorParams& S, float x) {
+    const float e = expf(S.filter_alpha * x * x);
+    return (e - S.filter_bias > 0.f) ? 2.f * S.filter_alpha * x * e : 0.f;
+}
+
+SDFRT_HD V3 square_to_uniform_sphere(float u0, float u1) {
+    const float z = 1.f - 2.f * u1;
+    const float r = sqrtf(fmaxf(0.f, 1.f - z * z));
+    const float phi = 2.f * kPi * u0;
+    return V3{r * cosf(phi), r * sinf(phi), z};
+}
+
+// diffuse reflectance: constant or trilinear gridvolume on [0,1]^3 (clamp); optional gradient wrt p
+struct AlbedoTaps {
+    int idx[8];
+    float w[8];
+};
+SDFRT_HD V3 eval_albedo(const AlbedoView& A, V3 p, AlbedoTaps* taps, V3 dwd[3] /* d rho_c / d p */) {
+    if (A.data == nullptr) {
+        if (dwd) { dwd[0] = dwd[1] = dwd[2] = v3(0.f); }
+        return V3{A.cr, A.cg, A.cb};
+    }
+    const float ux = p.x * (float)A.rx - 0.5f, uy = p.y * (float)A.ry - 0.5f, uz = p.z * (float)A.rz - 0.5f;
+    float fx = floorf(ux), fy = floorf(uy), fz = floorf(uz);
+    const float ax = ux - fx, ay = uy - fy, az = uz - fz;
+    fx = fminf(fmaxf(fx, -2.f), (float)A.rx + 2.f);
+    fy = fminf(fmaxf(fy, -2.f), (float)A.ry + 2.f);
+    fz = fminf(fmaxf(fz, -2.f), (float)A.rz + 2.f);
+    const int ix = (int)fx, iy = (int)fy, iz = (int)fz;
+    V3 rho = v3(0.f);
+    V3 gx = v3(0.f), gy = v3(0.f), gz = v3(0.f);  // per-channel derivative wrt (x, y, z)
+    for (int k = 0; k < 8; ++k) {
+        const int bx = k & 1, by = (k >> 1) & 1, bz = (k >> 2) & 1;
+        const int xx = clampi(ix + bx, 0, A.rx - 1), yy = clampi(iy + by, 0, A.ry - 1), zz = clampi(iz + bz, 0, A.rz - 1);
+        const float wx = bx ? ax : 1.f - ax, wy = by ? ay : 1.f - ay, wz = bz ? az : 1.f - az;
+        const int lin = ((zz * A.ry + yy) * A.rx + xx);
+        const float* t = A.data + (size_t)lin * 3;
+        const V3 c = V3{t[0], t[1], t[2]};
+        const float w = wx * wy * wz;
+        rho += w * c;
+        if (taps) { taps->idx[k] = lin; taps->w[k] = w; }
+        if (dwd) {
+            gx += ((bx ? 1.f : -1.f) * wy * wz * (float)A.rx) * c;
+            gy += ((by ? 1.f : -1.f) * wx * wz * (float)A.ry) * c;
+            gz += ((bz ? 1.f : -1.f) * wx * wy * (float)A.rz) * c;
+        }
+    }
+    if (dwd) {  // dwd[c] = gradient of channel c wrt p
+        dwd[0] = V3{gx.x, gy.x, gz.x};
+        dwd[1] = V3{gx.y, gy.y, gz.y};
+        dwd[2] = V3{gx.z, gy.z, gz.z};
+    }
+    return rho;
+}
+
+}  // namespace sdfrt

@@ -1,0 +1,542 @@
+// sdfrt_kernels.cu -- CUDA kernels (sm_100a) and the C ABI of libsdfrt.so (include/sdfrt.h).
+//
+// Kernels
+//   k_forward<DIFF>   one wavefront lane per thread: camera sample -> sphere trace through the
+//                     tricubic SDF grid -> shading -> gaussian film splat.  DIFF=true runs the
+//                     differentiable tracer (python/shapes.py:115-288) and stores its outputs per lane.
+//   k_film_adjoint    per film pixel: (dL/dV, dL/dWt) of I = V / Wt (HDRFilm::develop).
+//   k_backward        one lane per thread: closed-form adjoint + 64-tap atomic scatter into dL/d(sdf).
+//   k_develop, k_trace_rays, k_eval_sdf  small helpers / test hooks.
+// No CPU fallback exists: every entry point launches device work or fails.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "sdfrt_params.h"
+
+using namespace sdfrt;
+
+namespace {
+
+constexpr int kBlock = 128;
+
+struct DeviceStats {
+    Counters c;
+};
+
+__device__ __forceinline__ unsigned warp_sum(unsigned v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ unsigned warp_max(unsigned v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ void flush_stats(const LaneStats& st, unsigned n_rays, Counters* c) {
+    const unsigned a = warp_sum(st.n_value), b = warp_sum(st.n_grad), h = warp_sum(st.n_hess), s = warp_sum(st.n_sites),
+                   al = warp_sum(st.n_albedo), m = warp_max(st.n_steps_max), hi = warp_sum(st.n_hit), nr = warp_sum(n_rays);
+    if ((threadIdx.x & 31) == 0) {
+        if (nr) atomicAdd(&c->n_rays, (unsigned long long)nr);
+        if (a) atomicAdd(&c->n_evals_value, (unsigned long long)a);
+        if (b) atomicAdd(&c->n_evals_grad, (unsigned long long)b);
+        if (h) atomicAdd(&c->n_evals_hess, (unsigned long long)h);
+        if (s) atomicAdd(&c->n_scatter_sites, (unsigned long long)s);
+        if (al) atomicAdd(&c->n_albedo_lookups, (unsigned long long)al);
+        if (hi) atomicAdd(&c->n_hits, (unsigned long long)hi);
+        atomicMax(&c->n_steps_max, (unsigned long long)m);
+    }
+}
+
+template <bool DIFF>
+__global__ void __launch_bounds__(kBlock) k_forward(const __grid_constant__ SceneParams sc, const __grid_constant__ PassParams ps,
+                                                     float* __restrict__ film, float* __restrict__ rec,
+                                                     unsigned long long rec_stride, Counters* counters) {
+    const unsigned long long lane = ps.lane_begin + (unsigned long long)blockIdx.x * kBlock + threadIdx.x;
+    LaneStats st = {0, 0, 0, 0, 0, 0, 0};
+    const bool live = lane < ps.lane_end;
+    if (live) lane_forward<DIFF>(sc, ps, lane, film, rec, rec_stride, st);
+    flush_stats(st, live ? 1u : 0u, counters);
+}
+
+__global__ void __launch_bounds__(kBlock) k_backward(const __grid_constant__ SceneParams sc, const __grid_constant__ PassParams ps,
+                                                      const float* __restrict__ film_adj, const float* __restrict__ rec,
+                                                      unsigned long long rec_stride, BackwardTargets tg, float* grad_p,
+                                                      Counters* counters) {
+    const unsigned long long lane = ps.lane_begin + (unsigned long long)blockIdx.x * kBlock + threadIdx.x;
+    LaneStats st = {0, 0, 0, 0, 0, 0, 0};
+    V3 gp = v3(0.f);
+    if (lane < ps.lane_end) lane_backward(sc, ps, lane, film_adj, rec, rec_stride, tg, gp, st);
+    flush_stats(st, 0u, counters);
+    if (grad_p != nullptr) {
+        const float gx = warp_sum_f(gp.x), gy = warp_sum_f(gp.y), gz = warp_sum_f(gp.z);
+        if ((threadIdx.x & 31) == 0) {
+            if (gx != 0.f) atomicAdd(grad_p + 0, gx);
+            if (gy != 0.f) atomicAdd(grad_p + 1, gy);
+            if (gz != 0.f) atomicAdd(grad_p + 2, gz);
+        }
+    }
+}
+
+// I = V / Wt on the crop window  =>  dL/dV = G / Wt,  dL/dWt = -(G . I) / Wt   (zero on the border)
+__global__ void k_film_adjoint(const float* __restrict__ film, const float* __restrict__ grad_image, float* __restrict__ film_adj,
+                               int W, int H, int border) {
+    const int Wb = W + 2 * border, Hb = H + 2 * border;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Wb * Hb) return;
+    const int by = i / Wb, bx = i - by * Wb;
+    const int qx = bx - border, qy = by - border;
+    float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (qx >= 0 && qx < W && qy >= 0 && qy < H) {
+        const float4 a = reinterpret_cast<const float4*>(film)[i];
+        const float* g = grad_image + ((size_t)qy * W + qx) * 3;
+        if (a.w != 0.f) {
+            const float iw = 1.f / a.w;
+            out.x = g[0] * iw; out.y = g[1] * iw; out.z = g[2] * iw;
+            out.w = -(g[0] * a.x + g[1] * a.y + g[2] * a.z) * iw * iw;
+        }
+    }
+    reinterpret_cast<float4*>(film_adj)[i] = out;
+}
+
+__global__ void k_develop(const float* __restrict__ film, float* __restrict__ image, int W, int H, int border) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= W * H) return;
+    const int qy = i / W, qx = i - qy * W;
+    const float4 a = reinterpret_cast<const float4*>(film)[(size_t)(qy + border) * (W + 2 * border) + (qx + border)];
+    const float iw = a.w == 0.f ? 1.f : 1.f / a.w;
+    image[(size_t)i * 3 + 0] = a.x * iw;
+    image[(size_t)i * 3 + 1] = a.y * iw;
+    image[(size_t)i * 3 + 2] = a.z * iw;
+}
+
+__global__ void k_ones(float* p, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = 1.f;
+}
+
+__global__ void k_trace_rays(GridView G, TracerParams T, const float* __restrict__ o, const float* __restrict__ d,
+                             const float* __restrict__ maxt, int n, int differentiable, sdfrt_ray_out out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const V3 ro = V3{o[3 * i], o[3 * i + 1], o[3 * i + 2]}, rd = V3{d[3 * i], d[3 * i + 1], d[3 * i + 2]};
+    const float mt = maxt ? maxt[i] : INFINITY;
+    TraceOut tr;
+    tr.warp_t = 0.f; tr.warp_t_d = v3(0.f); tr.warp_weight = 0.f; tr.warp_weight_d = v3(0.f); tr.n_steps = 0;
+    int nh = 0, nv = 0;
+    if (differentiable) {
+        trace_diff(G, T, ro, rd, mt, true, tr, nh, nv);
+    } else {
+        tr.its_t = trace_non_diff(G, T, ro, rd, mt, true, tr.n_steps, nv);
+    }
+    out.its_t[i] = tr.its_t;
+    if (out.warp_t) out.warp_t[i] = tr.warp_t;
+    if (out.warp_weight) out.warp_weight[i] = tr.warp_weight;
+    if (out.warp_t_d) { out.warp_t_d[3 * i] = tr.warp_t_d.x; out.warp_t_d[3 * i + 1] = tr.warp_t_d.y; out.warp_t_d[3 * i + 2] = tr.warp_t_d.z; }
+    if (out.warp_weight_d) { out.warp_weight_d[3 * i] = tr.warp_weight_d.x; out.warp_weight_d[3 * i + 1] = tr.warp_weight_d.y; out.warp_weight_d[3 * i + 2] = tr.warp_weight_d.z; }
+    if (out.n_steps) out.n_steps[i] = tr.n_steps;
+}
+
+__global__ void k_eval_sdf(GridView G, const float* __restrict__ x, int n, int order, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const V3 p = V3{x[3 * i], x[3 * i + 1], x[3 * i + 2]};
+    float v; V3 g; S3 H;
+    if (order == 0) {
+        eval_sdf<0>(G, p, v, g, H);
+        out[i] = v;
+    } else if (order == 1) {
+        eval_sdf<1>(G, p, v, g, H);
+        float* q = out + (size_t)i * 4;
+        q[0] = v; q[1] = g.x; q[2] = g.y; q[3] = g.z;
+    } else {
+        eval_sdf<2>(G, p, v, g, H);
+        float* q = out + (size_t)i * 10;
+        q[0] = v; q[1] = g.x; q[2] = g.y; q[3] = g.z;
+        q[4] = H.xx; q[5] = H.yy; q[6] = H.zz; q[7] = H.xy; q[8] = H.xz; q[9] = H.yz;
+    }
+}
+
+}  // namespace
+
+// ----------------------------------------------------------------------------------------------------
+// context
+// ----------------------------------------------------------------------------------------------------
+struct sdfrt_ctx {
+    int device = 0;
+    std::string err;
+    SceneParams sc;
+    sdfrt_tracer_params tracer_pub;
+    sdfrt_warp_params warp_pub;
+    sdfrt_sensor sensor_pub;
+    sdfrt_shading shading_pub;
+    int rank = 0, world = 1;
+    bool have_sdf = false;
+    // adjoint state
+    float* rec = nullptr;
+    size_t rec_capacity = 0;  // floats
+    unsigned long long rec_stride = 0;
+    PassParams adj_pass;
+    bool adj_ready = false;
+    float* film_adj = nullptr;
+    size_t film_adj_capacity = 0;
+    Counters* counters = nullptr;
+    // buffers of the host entry point
+    float *h_sdf = nullptr, *h_film = nullptr, *h_image = nullptr, *h_gimg = nullptr, *h_grad = nullptr;
+    size_t h_sdf_n = 0, h_film_n = 0, h_image_n = 0, h_grad_n = 0;
+};
+
+namespace {
+
+int fail(sdfrt_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}
+#define SDFRT_CUDA(ctx, expr)                                                                                \
+    do {                                                                                                     \
+        cudaError_t e__ = (expr);                                                                            \
+        if (e__ != cudaSuccess)                                                                              \
+            return fail(ctx, SDFRT_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));           \
+    } while (0)
+
+int ensure(sdfrt_ctx* ctx, float** buf, size_t* cap, size_t need) {
+    if (*cap >= need) return SDFRT_OK;
+    if (*buf) cudaFree(*buf);
+    *buf = nullptr;
+    *cap = 0;
+    SDFRT_CUDA(ctx, cudaMalloc((void**)buf, need * sizeof(float)));
+    *cap = need;
+    return SDFRT_OK;
+}
+
+size_t film_floats(const sdfrt_ctx* ctx) {
+    const SensorParams& S = ctx->sc.S;
+    return (size_t)(S.W + 2 * S.border) * (size_t)(S.H + 2 * S.border) * 4;
+}
+
+int check_ready(sdfrt_ctx* ctx, int spp) {
+    if (!ctx) return SDFRT_ERR_INVALID;
+    if (!ctx->have_sdf) return fail(ctx, SDFRT_ERR_STATE, "no SDF bound (sdfrt_set_sdf)");
+    if (spp <= 0) return fail(ctx, SDFRT_ERR_INVALID, "spp must be positive");
+    const SensorParams& S = ctx->sc.S;
+    const unsigned long long wf = (unsigned long long)(S.W + 2 * S.border) * (S.H + 2 * S.border) * (unsigned long long)spp;
+    // the sampler is seeded per 32-bit lane index (python/integrators/reparam.py:47-50: 2^30 on CUDA, 2^32 on LLVM)
+    if (wf > 0xffffffffull) return fail(ctx, SDFRT_ERR_INVALID, "wavefront exceeds 2^32 lanes");
+    return SDFRT_OK;
+}
+
+template <bool DIFF>
+int launch_forward(sdfrt_ctx* ctx, const PassParams& ps, float* film, cudaStream_t st) {
+    SDFRT_CUDA(ctx, cudaSetDevice(ctx->device));
+    SDFRT_CUDA(ctx, cudaMemsetAsync(film, 0, film_floats(ctx) * sizeof(float), st));
+    const unsigned long long n = ps.lane_end - ps.lane_begin;
+    if (n == 0) return SDFRT_OK;
+    const unsigned long long blocks = (n + kBlock - 1) / kBlock;
+    if (blocks > 0x7fffffffull) return fail(ctx, SDFRT_ERR_INVALID, "too many lanes for one launch");
+    k_forward<DIFF><<<(unsigned)blocks, kBlock, 0, st>>>(ctx->sc, ps, film, ctx->rec, ctx->rec_stride, ctx->counters);
+    SDFRT_CUDA(ctx, cudaGetLastError());
+    return SDFRT_OK;
+}
+
+}  // namespace
+
+// ----------------------------------------------------------------------------------------------------
+// C ABI
+// ----------------------------------------------------------------------------------------------------
+extern "C" {
+
+int sdfrt_version(void) { return 100; }
+
+void sdfrt_tracer_defaults(sdfrt_tracer_params* p) { tracer_defaults(p); }
+void sdfrt_warp_defaults(sdfrt_warp_params* p) { warp_defaults(p); }
+void sdfrt_sensor_defaults(sdfrt_sensor* s) { sensor_defaults(s); }
+void sdfrt_shading_defaults(sdfrt_shading* s) { shading_defaults(s); }
+
+sdfrt_ctx* sdfrt_create(int device, int* status) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || device < 0 || device >= n) {
+        if (status) *status = SDFRT_ERR_CUDA;
+        return nullptr;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10) {
+        if (status) *status = SDFRT_ERR_CUDA;  // built for sm_100a only; there is no fallback path
+        return nullptr;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) {
+        if (status) *status = SDFRT_ERR_CUDA;
+        return nullptr;
+    }
+    sdfrt_ctx* ctx = new sdfrt_ctx();
+    ctx->device = device;
+    std::memset(&ctx->sc, 0, sizeof(ctx->sc));
+    tracer_defaults(&ctx->tracer_pub);
+    warp_defaults(&ctx->warp_pub);
+    sensor_defaults(&ctx->sensor_pub);
+    shading_defaults(&ctx->shading_pub);
+    ctx->sc.T = make_tracer(ctx->tracer_pub);
+    ctx->sc.W = make_warp(ctx->warp_pub);
+    ctx->sc.S = make_sensor(ctx->sensor_pub);
+    ctx->sc.Sh = make_shading(ctx->shading_pub);
+    ctx->sc.A.data = nullptr;
+    ctx->sc.A.cr = ctx->shading_pub.albedo[0]; ctx->sc.A.cg = ctx->shading_pub.albedo[1]; ctx->sc.A.cb = ctx->shading_pub.albedo[2];
+    ctx->sc.integrator = INTEGRATOR_DIRECT;
+    if (cudaMalloc((void**)&ctx->counters, sizeof(Counters)) != cudaSuccess || cudaMemset(ctx->counters, 0, sizeof(Counters)) != cudaSuccess) {
+        delete ctx;
+        if (status) *status = SDFRT_ERR_CUDA;
+        return nullptr;
+    }
+    if (status) *status = SDFRT_OK;
+    return ctx;
+}
+
+void sdfrt_destroy(sdfrt_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaFree(ctx->rec);
+    cudaFree(ctx->film_adj);
+    cudaFree(ctx->counters);
+    cudaFree(ctx->h_sdf); cudaFree(ctx->h_film); cudaFree(ctx->h_image); cudaFree(ctx->h_gimg); cudaFree(ctx->h_grad);
+    delete ctx;
+}
+
+const char* sdfrt_last_error(const sdfrt_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int sdfrt_set_sdf(sdfrt_ctx* ctx, const float* sdf, int rx, int ry, int rz, const float p[3]) {
+    if (!ctx) return SDFRT_ERR_INVALID;
+    if (!sdf || rx < 1 || ry < 1 || rz < 1) return fail(ctx, SDFRT_ERR_INVALID, "bad SDF grid");
+    ctx->sc.G.data = sdf;
+    ctx->sc.G.rx = rx; ctx->sc.G.ry = ry; ctx->sc.G.rz = rz;
+    ctx->sc.G.px = p ? p[0] : 0.f; ctx->sc.G.py = p ? p[1] : 0.f; ctx->sc.G.pz = p ? p[2] : 0.f;
+    ctx->have_sdf = true;
+    ctx->adj_ready = false;
+    return SDFRT_OK;
+}
+
+int sdfrt_set_albedo(sdfrt_ctx* ctx, const float* rgb_grid, int rx, int ry, int rz) {
+    if (!ctx) return SDFRT_ERR_INVALID;
+    if (rgb_grid && (rx < 1 || ry < 1 || rz < 1)) return fail(ctx, SDFRT_ERR_INVALID, "bad albedo grid");
+    ctx->sc.A.data = rgb_grid;
+    ctx->sc.A.rx = rx; ctx->sc.A.ry = ry; ctx->sc.A.rz = rz;
+    ctx->adj_ready = false;
+    return SDFRT_OK;
+}
+
+int sdfrt_set_tracer(sdfrt_ctx* ctx, const sdfrt_tracer_params* p) {
+    if (!ctx || !p) return SDFRT_ERR_INVALID;
+    if (p->weight_power < 1 || p->weight_power > 8) return fail(ctx, SDFRT_ERR_INVALID, "weight_power out of range");
+    ctx->tracer_pub = *p;
+    ctx->sc.T = make_tracer(*p);
+    ctx->adj_ready = false;
+    return SDFRT_OK;
+}
+
+int sdfrt_set_warp(sdfrt_ctx* ctx, const sdfrt_warp_params* p) {
+    if (!ctx || !p) return SDFRT_ERR_INVALID;
+    if (p->kind < SDFRT_WARP_NONE || p->kind > SDFRT_WARP_2D) return fail(ctx, SDFRT_ERR_INVALID, "unknown warp kind");
+    ctx->warp_pub = *p;
+    ctx->sc.W = make_warp(*p);
+    ctx->adj_ready = false;
+    return SDFRT_OK;
+}
+
+int sdfrt_set_sensor(sdfrt_ctx* ctx, const sdfrt_sensor* s) {
+    if (!ctx || !s) return SDFRT_ERR_INVALID;
+    if (s->width < 1 || s->height < 1 || !(s->filter_radius > 0.f) || !(s->filter_stddev > 0.f) || s->filter_radius > 2.5f)
+        return fail(ctx, SDFRT_ERR_INVALID, "bad sensor");
+    ctx->sensor_pub = *s;
+    ctx->sc.S = make_sensor(*s);
+    ctx->adj_ready = false;
+    return SDFRT_OK;
+}
+
+int sdfrt_set_shading(sdfrt_ctx* ctx, const sdfrt_shading* s) {
+    if (!ctx || !s) return SDFRT_ERR_INVALID;
+    ctx->shading_pub = *s;
+    ctx->sc.Sh = make_shading(*s);
+    ctx->sc.A.cr = s->albedo[0]; ctx->sc.A.cg = s->albedo[1]; ctx->sc.A.cb = s->albedo[2];
+    ctx->adj_ready = false;
+    return SDFRT_OK;
+}
+
+int sdfrt_set_integrator(sdfrt_ctx* ctx, int integrator) {
+    if (!ctx) return SDFRT_ERR_INVALID;
+    if (integrator < SDFRT_INTEGRATOR_SILHOUETTE || integrator > SDFRT_INTEGRATOR_DIRECT)
+        return fail(ctx, SDFRT_ERR_INVALID, "unknown integrator");
+    ctx->sc.integrator = integrator;
+    ctx->adj_ready = false;
+    return SDFRT_OK;
+}
+
+int sdfrt_set_partition(sdfrt_ctx* ctx, int rank, int world) {
+    if (!ctx) return SDFRT_ERR_INVALID;
+    if (world < 1 || rank < 0 || rank >= world) return fail(ctx, SDFRT_ERR_INVALID, "bad partition");
+    ctx->rank = rank;
+    ctx->world = world;
+    ctx->adj_ready = false;
+    return SDFRT_OK;
+}
+
+int sdfrt_film_dims(const sdfrt_ctx* ctx, int* height_b, int* width_b, int* border) {
+    if (!ctx) return SDFRT_ERR_INVALID;
+    const SensorParams& S = ctx->sc.S;
+    if (height_b) *height_b = S.H + 2 * S.border;
+    if (width_b) *width_b = S.W + 2 * S.border;
+    if (border) *border = S.border;
+    return SDFRT_OK;
+}
+
+uint64_t sdfrt_wavefront_size(const sdfrt_ctx* ctx, int spp) {
+    if (!ctx || spp <= 0) return 0;
+    const SensorParams& S = ctx->sc.S;
+    return (uint64_t)(S.W + 2 * S.border) * (uint64_t)(S.H + 2 * S.border) * (uint64_t)spp;
+}
+
+int sdfrt_render_primal(sdfrt_ctx* ctx, uint32_t seed, int spp, float* film_accum, void* stream) {
+    int rc = check_ready(ctx, spp);
+    if (rc) return rc;
+    if (!film_accum) return fail(ctx, SDFRT_ERR_INVALID, "film_accum is null");
+    const PassParams ps = make_pass(ctx->sc.S, seed, spp, ctx->rank, ctx->world);
+    return launch_forward<false>(ctx, ps, film_accum, (cudaStream_t)stream);
+}
+
+int sdfrt_develop(sdfrt_ctx* ctx, const float* film_accum, float* image, void* stream) {
+    if (!ctx || !film_accum || !image) return SDFRT_ERR_INVALID;
+    SDFRT_CUDA(ctx, cudaSetDevice(ctx->device));
+    const SensorParams& S = ctx->sc.S;
+    const int n = S.W * S.H;
+    k_develop<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(film_accum, image, S.W, S.H, S.border);
+    SDFRT_CUDA(ctx, cudaGetLastError());
+    return SDFRT_OK;
+}
+
+int sdfrt_adjoint_accumulate(sdfrt_ctx* ctx, uint32_t seed_grad, int spp_grad, float* film_accum, void* stream) {
+    int rc = check_ready(ctx, spp_grad);
+    if (rc) return rc;
+    if (!film_accum) return fail(ctx, SDFRT_ERR_INVALID, "film_accum is null");
+    SDFRT_CUDA(ctx, cudaSetDevice(ctx->device));
+    const PassParams ps = make_pass(ctx->sc.S, seed_grad, spp_grad, ctx->rank, ctx->world);
+    const unsigned long long n = ps.lane_end - ps.lane_begin;
+    rc = ensure(ctx, &ctx->rec, &ctx->rec_capacity, (size_t)n * REC_COUNT + 1);
+    if (rc) return rc;
+    ctx->rec_stride = n;
+    rc = launch_forward<true>(ctx, ps, film_accum, (cudaStream_t)stream);
+    if (rc) return rc;
+    ctx->adj_pass = ps;
+    ctx->adj_ready = true;
+    return SDFRT_OK;
+}
+
+int sdfrt_adjoint_backprop(sdfrt_ctx* ctx, const float* film_accum, const float* grad_image, float* grad_sdf,
+                           float* grad_albedo, float* grad_p, void* stream) {
+    if (!ctx) return SDFRT_ERR_INVALID;
+    if (!ctx->adj_ready) return fail(ctx, SDFRT_ERR_STATE, "sdfrt_adjoint_accumulate must run first (and no set_* in between)");
+    if (!film_accum || !grad_image || !grad_sdf) return fail(ctx, SDFRT_ERR_INVALID, "null buffer");
+    SDFRT_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const SensorParams& S = ctx->sc.S;
+    int rc = ensure(ctx, &ctx->film_adj, &ctx->film_adj_capacity, film_floats(ctx));
+    if (rc) return rc;
+    const int npix = (S.W + 2 * S.border) * (S.H + 2 * S.border);
+    k_film_adjoint<<<(npix + 255) / 256, 256, 0, st>>>(film_accum, grad_image, ctx->film_adj, S.W, S.H, S.border);
+    SDFRT_CUDA(ctx, cudaGetLastError());
+    const PassParams& ps = ctx->adj_pass;
+    const unsigned long long n = ps.lane_end - ps.lane_begin;
+    if (n == 0) return SDFRT_OK;
+    BackwardTargets tg;
+    tg.grad_sdf = grad_sdf;
+    tg.grad_albedo = grad_albedo;
+    const unsigned long long blocks = (n + kBlock - 1) / kBlock;
+    k_backward<<<(unsigned)blocks, kBlock, 0, st>>>(ctx->sc, ps, ctx->film_adj, ctx->rec, ctx->rec_stride, tg, grad_p, ctx->counters);
+    SDFRT_CUDA(ctx, cudaGetLastError());
+    return SDFRT_OK;
+}
+
+int sdfrt_get_stats(sdfrt_ctx* ctx, sdfrt_stats* out, int reset, void* stream) {
+    if (!ctx || !out) return SDFRT_ERR_INVALID;
+    SDFRT_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    Counters c;
+    SDFRT_CUDA(ctx, cudaMemcpyAsync(&c, ctx->counters, sizeof(c), cudaMemcpyDeviceToHost, st));
+    SDFRT_CUDA(ctx, cudaStreamSynchronize(st));
+    out->n_rays = c.n_rays; out->n_evals_value = c.n_evals_value; out->n_evals_grad = c.n_evals_grad;
+    out->n_evals_hess = c.n_evals_hess; out->n_scatter_sites = c.n_scatter_sites; out->n_albedo_lookups = c.n_albedo_lookups;
+    out->n_steps_max = c.n_steps_max; out->n_hits = c.n_hits;
+    if (reset) SDFRT_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, sizeof(Counters), st));
+    return SDFRT_OK;
+}
+
+int sdfrt_trace_rays(sdfrt_ctx* ctx, const float* o, const float* d, const float* maxt, int n, int differentiable,
+                     const sdfrt_ray_out* out, void* stream) {
+    if (!ctx || !o || !d || !out || !out->its_t || n < 0) return SDFRT_ERR_INVALID;
+    if (!ctx->have_sdf) return fail(ctx, SDFRT_ERR_STATE, "no SDF bound (sdfrt_set_sdf)");
+    if (n == 0) return SDFRT_OK;
+    SDFRT_CUDA(ctx, cudaSetDevice(ctx->device));
+    k_trace_rays<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(ctx->sc.G, ctx->sc.T, o, d, maxt, n, differentiable, *out);
+    SDFRT_CUDA(ctx, cudaGetLastError());
+    return SDFRT_OK;
+}
+
+int sdfrt_eval_sdf(sdfrt_ctx* ctx, const float* x, int n, int order, float* out, void* stream) {
+    if (!ctx || !x || !out || n < 0 || order < 0 || order > 2) return SDFRT_ERR_INVALID;
+    if (!ctx->have_sdf) return fail(ctx, SDFRT_ERR_STATE, "no SDF bound (sdfrt_set_sdf)");
+    if (n == 0) return SDFRT_OK;
+    SDFRT_CUDA(ctx, cudaSetDevice(ctx->device));
+    k_eval_sdf<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(ctx->sc.G, x, n, order, out);
+    SDFRT_CUDA(ctx, cudaGetLastError());
+    return SDFRT_OK;
+}
+
+int sdfrt_render_view_host(sdfrt_ctx* ctx, const float* sdf_host, int rx, int ry, int rz, uint32_t seed, int spp,
+                           uint32_t seed_grad, int spp_grad, const float* grad_image_host, float* image_host,
+                           float* grad_sdf_host) {
+    if (!ctx || !sdf_host || !image_host || !grad_sdf_host) return SDFRT_ERR_INVALID;
+    if (ctx->world != 1) return fail(ctx, SDFRT_ERR_STATE, "host entry point is single-GPU; use the device API with a partition");
+    SDFRT_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t nvox = (size_t)rx * ry * rz;
+    const SensorParams& S = ctx->sc.S;
+    const size_t nimg = (size_t)S.W * S.H * 3;
+    int rc;
+    if ((rc = ensure(ctx, &ctx->h_sdf, &ctx->h_sdf_n, nvox))) return rc;
+    if ((rc = ensure(ctx, &ctx->h_grad, &ctx->h_grad_n, nvox))) return rc;
+    if ((rc = ensure(ctx, &ctx->h_film, &ctx->h_film_n, film_floats(ctx)))) return rc;
+    if (ctx->h_image_n < nimg) {
+        size_t cap = ctx->h_image_n;
+        if ((rc = ensure(ctx, &ctx->h_image, &cap, nimg))) return rc;
+        cap = ctx->h_image_n;
+        if ((rc = ensure(ctx, &ctx->h_gimg, &cap, nimg))) return rc;
+        ctx->h_image_n = nimg;
+    }
+    cudaStream_t st = 0;
+    SDFRT_CUDA(ctx, cudaMemcpyAsync(ctx->h_sdf, sdf_host, nvox * sizeof(float), cudaMemcpyHostToDevice, st));
+    const float p0[3] = {ctx->sc.G.px, ctx->sc.G.py, ctx->sc.G.pz};
+    if ((rc = sdfrt_set_sdf(ctx, ctx->h_sdf, rx, ry, rz, ctx->have_sdf ? p0 : nullptr))) return rc;
+    if ((rc = sdfrt_render_primal(ctx, seed, spp, ctx->h_film, st))) return rc;
+    if ((rc = sdfrt_develop(ctx, ctx->h_film, ctx->h_image, st))) return rc;
+    SDFRT_CUDA(ctx, cudaMemcpyAsync(image_host, ctx->h_image, nimg * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (grad_image_host) {
+        SDFRT_CUDA(ctx, cudaMemcpyAsync(ctx->h_gimg, grad_image_host, nimg * sizeof(float), cudaMemcpyHostToDevice, st));
+    } else {
+        k_ones<<<(unsigned)((nimg + 255) / 256), 256, 0, st>>>(ctx->h_gimg, nimg);
+        SDFRT_CUDA(ctx, cudaGetLastError());
+    }
+    SDFRT_CUDA(ctx, cudaMemsetAsync(ctx->h_grad, 0, nvox * sizeof(float), st));
+    if ((rc = sdfrt_adjoint_accumulate(ctx, seed_grad, spp_grad, ctx->h_film, st))) return rc;
+    if ((rc = sdfrt_adjoint_backprop(ctx, ctx->h_film, ctx->h_gimg, ctx->h_grad, nullptr, nullptr, st))) return rc;
+    SDFRT_CUDA(ctx, cudaMemcpyAsync(grad_sdf_host, ctx->h_grad, nvox * sizeof(float), cudaMemcpyDeviceToHost, st));
+    SDFRT_CUDA(ctx, cudaStreamSynchronize(st));
+    return SDFRT_OK;
+}
+
+}  // extern "C"

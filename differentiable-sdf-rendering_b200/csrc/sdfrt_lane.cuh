@@ -1,0 +1,428 @@
+// sdfrt_lane.cuh -- one wavefront lane (= one camera sample) of the reparameterised integrators.
+//
+//   lane_forward<DIFF>   ReparamIntegrator.render / eval_sample (python/integrators/reparam.py:82-185)
+//                        + <integrator>.sample; DIFF selects the differentiable tracer and writes the
+//                        per-lane tracer record that the adjoint consumes.
+//   lane_backward        closed-form adjoint of the same lane (what dr.backward_from(image * grad_in)
+//                        produces through Dr.Jit's AD in python/integrators/reparam.py:187-190),
+//                        scattering dL/d(sdf.data) with 64-tap B-spline weights.
+// See DESIGN.md for the derivation.
+#pragma once
+#include "sdfrt_core.cuh"
+
+namespace sdfrt {
+
+enum { INTEGRATOR_SILHOUETTE = 0, INTEGRATOR_SIMPLE_SHADING = 1, INTEGRATOR_DIRECT = 2 };
+enum { WARP_NONE = 0, WARP_DUMMY = 1, WARP_2D = 2 };
+
+struct SceneParams {
+    GridView G;
+    AlbedoView A;
+    TracerParams T;
+    WarpParams W;
+    SensorParams S;
+    ShadingParams Sh;
+    int integrator;
+};
+
+struct PassParams {
+    uint32_t seed;
+    int spp;
+    int log2_spp;               // >= 0 if spp is a power of two (python/integrators/reparam.py:144-148)
+    unsigned long long lane_begin, lane_end;  // this rank's slice of the wavefront
+};
+
+// per-lane record written by lane_forward<true>, SoA with stride = number of local lanes
+enum {
+    REC_ITS_T = 0, REC_TAU, REC_TAU_DX, REC_TAU_DY, REC_TAU_DZ, REC_OMEGA, REC_OMEGA_DX, REC_OMEGA_DY, REC_OMEGA_DZ,
+    REC_S_STATE,  // shadow ray: 0 = no NEE contribution, 1 = unoccluded and gates passed
+    REC_S_TAU, REC_S_TAU_DX, REC_S_TAU_DY, REC_S_TAU_DZ, REC_S_OMEGA, REC_S_OMEGA_DX, REC_S_OMEGA_DY, REC_S_OMEGA_DZ,
+    REC_COUNT
+};
+
+struct LaneStats {
+    unsigned n_value, n_grad, n_hess, n_sites, n_albedo, n_steps_max, n_hit;
+};
+
+#if defined(__CUDA_ARCH__)
+#define SDFRT_ATOMIC_ADD(ptr, val) atomicAdd((ptr), (val))
+#else
+#define SDFRT_ATOMIC_ADD(ptr, val) (*(ptr) += (val))
+#endif
+
+SDFRT_HD bool reparam_at_depth(const WarpParams& W, int depth) {
+    return W.kind == WARP_2D && (W.max_reparam_depth < 0 || depth <= W.max_reparam_depth);
+}
+
+struct CameraSample {
+    V3 o, d;
+    float maxt;
+    Pcg32 rng;
+};
+SDFRT_HD CameraSample camera_sample(const SceneParams& sc, const PassParams& ps, unsigned long long lane) {
+    const int b = sc.S.border;
+    const int Wb = sc.S.W + 2 * b;
+    const unsigned long long pix = ps.log2_spp >= 0 ? (lane >> ps.log2_spp) : (lane / (unsigned long long)ps.spp);
+    const int py = (int)(pix / (unsigned long long)Wb);
+    const int px = (int)(pix - (unsigned long long)py * Wb);
+    CameraSample cs;
+    cs.rng = sampler_seed(ps.seed, (uint32_t)lane);
+    const float r0 = pcg_next_f32(cs.rng), r1 = pcg_next_f32(cs.rng);
+    (void)pcg_next_f32(cs.rng);  // wavelength sample, consumed even in RGB (python/integrators/reparam.py:90)
+    sensor_sample_ray(sc.S, (float)(px - b) + r0, (float)(py - b) + r1, cs.o, cs.d, cs.maxt);
+    return cs;
+}
+
+// shadow ray of the emitter sample (python/integrators/sdf_direct_reparam.py:38-51 + spawn_ray_to)
+struct ShadowRay {
+    V3 o, d;
+    float maxt;
+};
+SDFRT_HD ShadowRay make_shadow_ray(const ShadingParams& Sh, V3 p, V3 n, float u0, float u1) {
+    const V3 d_e = square_to_uniform_sphere(u0, u1);
+    const V3 ds_p = p + Sh.env_dist * d_e;
+    const float mag = (1.f + fmaxf(fabsf(p.x), fmaxf(fabsf(p.y), fabsf(p.z)))) * kRayEpsilon;
+    const float sgn = sign1(dot(n, ds_p - p));
+    ShadowRay s;
+    s.o = p + (mag * sgn) * n;
+    const V3 dv = ds_p - s.o;
+    const float dist = sqrtf(dot(dv, dv));
+    s.d = dv / dist;
+    s.maxt = dist * (1.f - kShadowEpsilon);
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward lane
+// ------------------------------------------------------------------------------------------------
+template <bool DIFF>
+SDFRT_HD void lane_forward(const SceneParams& sc, const PassParams& ps, unsigned long long lane, float* film, float* rec,
+                           unsigned long long rec_stride, LaneStats& st) {
+    CameraSample cs = camera_sample(sc, ps, lane);
+    const V3 o = cs.o, d0 = cs.d;
+    int nv = 0, nh = 0, nsteps = 0;
+    TraceOut tr;
+    tr.warp_t = INFINITY; tr.warp_t_d = v3(0.f); tr.warp_weight = 0.f; tr.warp_weight_d = v3(0.f);
+    if (DIFF && reparam_at_depth(sc.W, 0)) {
+        trace_diff(sc.G, sc.T, o, d0, cs.maxt, true, tr, nh, nv);
+        nsteps = tr.n_steps;
+    } else {
+        tr.its_t = trace_non_diff(sc.G, sc.T, o, d0, cs.maxt, true, nsteps, nv);
+    }
+    const bool hit = isfinite(tr.its_t);
+    V3 rgb = v3(0.f);
+    float s_state = 0.f;
+    TraceOut ts;
+    ts.warp_t = INFINITY; ts.warp_t_d = v3(0.f); ts.warp_weight = 0.f; ts.warp_weight_d = v3(0.f);
+    if (sc.integrator == INTEGRATOR_SILHOUETTE) {
+        rgb = v3(hit ? 1.f : 0.f);
+    } else if (sc.integrator == INTEGRATOR_SIMPLE_SHADING) {
+        if (hit) {
+            float phi; V3 g; S3 H;
+            eval_sdf<1>(sc.G, o + tr.its_t * d0, phi, g, H);
+            st.n_grad += 1;
+            const V3 n = normalize(g);
+            rgb = v3(fmaxf(0.f, (n.x + n.y + n.z) * 0.57735026918962576f));
+        }
+    } else {
+        if (!hit) {
+            if (!sc.Sh.hide_emitters) rgb = V3{sc.Sh.Le[0], sc.Sh.Le[1], sc.Sh.Le[2]};
+        } else {
+            const V3 p = o + tr.its_t * d0;
+            float phi; V3 g; S3 H;
+            eval_sdf<1>(sc.G, p, phi, g, H);
+            st.n_grad += 1;
+            const V3 n = normalize(g);
+            const float cos_i = -dot(n, d0);
+            const float u0 = pcg_next_f32(cs.rng), u1 = pcg_next_f32(cs.rng);
+            const ShadowRay sr = make_shadow_ray(sc.Sh, p, n, u0, u1);
+            const float cos_o = dot(n, sr.d);
+            // the reference marches every shadow ray; a lane whose BSDF gate is closed contributes
+            // exactly zero whatever the march returns, so it is skipped here.
+            if ((cos_i > 0.f) & (cos_o > 0.f)) {
+                float its_s;
+                int ns = 0;
+                if (DIFF && reparam_at_depth(sc.W, 1)) {
+                    trace_diff(sc.G, sc.T, sr.o, sr.d, sr.maxt, false, ts, nh, nv);
+                    its_s = ts.its_t;
+                    ns = ts.n_steps;
+                } else {
+                    its_s = trace_non_diff(sc.G, sc.T, sr.o, sr.d, sr.maxt, false, ns, nv);
+                }
+                nsteps = nsteps > ns ? nsteps : ns;
+                if (!isfinite(its_s)) {
+                    s_state = 1.f;
+                    const V3 rho = eval_albedo(sc.A, p, nullptr, nullptr);
+                    st.n_albedo += (sc.A.data != nullptr);
+                    const float k = cos_o * 4.f;  // (rho / pi) * cos_o * Le / (1 / (4 pi))
+                    rgb = V3{rho.x * k * sc.Sh.Le[0], rho.y * k * sc.Sh.Le[1], rho.z * k * sc.Sh.Le[2]};
+                }
+            }
+        }
+    }
+    st.n_value += nv;
+    st.n_hess += nh;
+    st.n_hit += hit;
+    st.n_steps_max = st.n_steps_max > (unsigned)nsteps ? st.n_steps_max : (unsigned)nsteps;
+
+    if (DIFF) {
+        const unsigned long long l = lane - ps.lane_begin;
+        float* r = rec + l;
+        r[REC_ITS_T * rec_stride] = tr.its_t;
+        r[REC_TAU * rec_stride] = tr.warp_t;
+        r[REC_TAU_DX * rec_stride] = tr.warp_t_d.x; r[REC_TAU_DY * rec_stride] = tr.warp_t_d.y; r[REC_TAU_DZ * rec_stride] = tr.warp_t_d.z;
+        r[REC_OMEGA * rec_stride] = tr.warp_weight;
+        r[REC_OMEGA_DX * rec_stride] = tr.warp_weight_d.x; r[REC_OMEGA_DY * rec_stride] = tr.warp_weight_d.y; r[REC_OMEGA_DZ * rec_stride] = tr.warp_weight_d.z;
+        r[REC_S_STATE * rec_stride] = s_state;
+        r[REC_S_TAU * rec_stride] = ts.warp_t;
+        r[REC_S_TAU_DX * rec_stride] = ts.warp_t_d.x; r[REC_S_TAU_DY * rec_stride] = ts.warp_t_d.y; r[REC_S_TAU_DZ * rec_stride] = ts.warp_t_d.z;
+        r[REC_S_OMEGA * rec_stride] = ts.warp_weight;
+        r[REC_S_OMEGA_DX * rec_stride] = ts.warp_weight_d.x; r[REC_S_OMEGA_DY * rec_stride] = ts.warp_weight_d.y; r[REC_S_OMEGA_DZ * rec_stride] = ts.warp_weight_d.z;
+    }
+
+    // re-projection + splat (python/integrators/reparam.py:100-118; ImageBlock::put)
+    float u, v; bool inside; V3 ref;
+    sensor_project(sc.S, o + d0, u, v, inside, ref);
+    const int b = sc.S.border;
+    const int Wb = sc.S.W + 2 * b, Hb = sc.S.H + 2 * b;
+    const float pfx = u + ((float)b - 0.5f), pfy = v + ((float)b - 0.5f);
+    const float rad = sc.S.filter_radius;
+    const int x0 = (int)ceilf(pfx - rad), y0 = (int)ceilf(pfy - rad);
+    const int x1 = (int)floorf(pfx + rad), y1 = (int)floorf(pfy + rad);
+    for (int by = y0; by <= y1; ++by) {
+        if (by < 0 || by >= Hb) continue;
+        const float wy = filter_eval(sc.S, (float)by - pfy);
+        if (wy == 0.f) continue;
+        for (int bx = x0; bx <= x1; ++bx) {
+            if (bx < 0 || bx >= Wb) continue;
+            const float w = wy * filter_eval(sc.S, (float)bx - pfx);
+            if (w == 0.f) continue;
+            float* px = film + ((size_t)by * Wb + bx) * 4;
+            if (rgb.x != 0.f) SDFRT_ATOMIC_ADD(px + 0, rgb.x * w);
+            if (rgb.y != 0.f) SDFRT_ATOMIC_ADD(px + 1, rgb.y * w);
+            if (rgb.z != 0.f) SDFRT_ATOMIC_ADD(px + 2, rgb.z * w);
+            SDFRT_ATOMIC_ADD(px + 3, w);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// adjoint scatter of one B-spline site: grad[k] += phi_hat * B_k(x) + g_hat . grad B_k(x)
+// ------------------------------------------------------------------------------------------------
+SDFRT_HD void scatter_site(float* grad, const GridView& G, V3 x, float phi_hat, V3 g_hat) {
+    const CellCoord c = cell_coord(G, x);
+    float wx[4], wy[4], wz[4], dx[4], dy[4], dz[4];
+    bspline_w(c.ax, wx); bspline_w(c.ay, wy); bspline_w(c.az, wz);
+    bspline_dw(c.ax, dx); bspline_dw(c.ay, dy); bspline_dw(c.az, dz);
+    const float gx = g_hat.x * (float)G.rx, gy = g_hat.y * (float)G.ry, gz = g_hat.z * (float)G.rz;
+    float ex[4];  // phi_hat * wx + gx * dx  (x-direction factor shared by all rows)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ex[i] = phi_hat * wx[i] + gx * dx[i];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int zz = clampi(c.iz + k, 0, G.rz - 1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int yy = clampi(c.iy + j, 0, G.ry - 1);
+            float* row = grad + ((size_t)zz * G.ry + yy) * (size_t)G.rx;
+            const float a = wy[j] * wz[k];                               // multiplies ex[i]
+            const float bq = gy * dy[j] * wz[k] + gz * wy[j] * dz[k];    // multiplies wx[i]
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int xx = clampi(c.ix + i, 0, G.rx - 1);
+                SDFRT_ATOMIC_ADD(row + xx, a * ex[i] + bq * wx[i]);
+            }
+        }
+    }
+}
+
+struct BackwardTargets {
+    float* grad_sdf;     // (rz, ry, rx), accumulated
+    float* grad_albedo;  // (rz, ry, rx, 3) or nullptr
+};
+
+// ------------------------------------------------------------------------------------------------
+// backward lane.  film_adj: (Hb, Wb, 4) = (dL/dV_rgb, dL/dWt) per film pixel (see k_film_adjoint).
+// Returns this lane's contribution to dL/d(sdf.p) in grad_p.
+// ------------------------------------------------------------------------------------------------
+SDFRT_HD void lane_backward(const SceneParams& sc, const PassParams& ps, unsigned long long lane, const float* film_adj,
+                            const float* rec, unsigned long long rec_stride, const BackwardTargets& tg, V3& grad_p,
+                            LaneStats& st) {
+    CameraSample cs = camera_sample(sc, ps, lane);
+    const V3 o = cs.o, d0 = cs.d;
+    const float* r = rec + (lane - ps.lane_begin);
+    const float its_t = r[REC_ITS_T * rec_stride];
+    const bool hit = isfinite(its_t);
+
+    // ---- recompute the forward values that the adjoint needs -----------------------------------
+    V3 rgb = v3(0.f);
+    V3 p = v3(0.f), n = v3(0.f), g_p = v3(0.f);
+    S3 H_p = S3{0, 0, 0, 0, 0, 0};
+    float cos_o = 0.f;
+    ShadowRay sr; sr.o = v3(0.f); sr.d = v3(0.f); sr.maxt = 0.f;
+    V3 rho = v3(0.f);
+    V3 drho[3];
+    AlbedoTaps taps;
+    bool nee = false;
+    float shade = 0.f;
+    if (hit && sc.integrator != INTEGRATOR_SILHOUETTE) {
+        p = o + its_t * d0;
+        float phi;
+        eval_sdf<2>(sc.G, p, phi, g_p, H_p);
+        st.n_hess += 1;
+        n = normalize(g_p);
+    }
+    if (sc.integrator == INTEGRATOR_SILHOUETTE) {
+        rgb = v3(hit ? 1.f : 0.f);
+    } else if (sc.integrator == INTEGRATOR_SIMPLE_SHADING) {
+        if (hit) {
+            shade = (n.x + n.y + n.z) * 0.57735026918962576f;
+            rgb = v3(fmaxf(0.f, shade));
+        }
+    } else {
+        if (!hit) {
+            if (!sc.Sh.hide_emitters) rgb = V3{sc.Sh.Le[0], sc.Sh.Le[1], sc.Sh.Le[2]};
+        } else if (r[REC_S_STATE * rec_stride] != 0.f) {
+            nee = true;
+            const float u0 = pcg_next_f32(cs.rng), u1 = pcg_next_f32(cs.rng);
+            sr = make_shadow_ray(sc.Sh, p, n, u0, u1);
+            cos_o = dot(n, sr.d);
+            rho = eval_albedo(sc.A, p, &taps, drho);
+            const float k = cos_o * 4.f;
+            rgb = V3{rho.x * k * sc.Sh.Le[0], rho.y * k * sc.Sh.Le[1], rho.z * k * sc.Sh.Le[2]};
+        }
+    }
+
+    // ---- film adjoint: gather over the filter footprint ------------------------------------------
+    float u, v; bool inside; V3 ref;
+    sensor_project(sc.S, o + d0, u, v, inside, ref);
+    const int b = sc.S.border;
+    const int Wb = sc.S.W + 2 * b, Hb = sc.S.H + 2 * b;
+    const float pfx = u + ((float)b - 0.5f), pfy = v + ((float)b - 0.5f);
+    const float rad = sc.S.filter_radius;
+    const int x0 = (int)ceilf(pfx - rad), y0 = (int)ceilf(pfy - rad);
+    const int x1 = (int)floorf(pfx + rad), y1 = (int)floorf(pfy + rad);
+    V3 c_hat = v3(0.f);
+    float wch_hat = 0.f, u_hat = 0.f, v_hat = 0.f;
+    for (int by = y0; by <= y1; ++by) {
+        if (by < 0 || by >= Hb) continue;
+        const float fy = filter_eval(sc.S, (float)by - pfy);
+        const float dfy = filter_deriv(sc.S, (float)by - pfy);
+        for (int bx = x0; bx <= x1; ++bx) {
+            if (bx < 0 || bx >= Wb) continue;
+            const float fx = filter_eval(sc.S, (float)bx - pfx);
+            const float dfx = filter_deriv(sc.S, (float)bx - pfx);
+            const float* a = film_adj + ((size_t)by * Wb + bx) * 4;
+            const float a0 = a[0], a1 = a[1], a2 = a[2], a3 = a[3];
+            const float w = fx * fy;
+            c_hat += w * V3{a0, a1, a2};
+            wch_hat += w * a3;
+            const float s = a0 * rgb.x + a1 * rgb.y + a2 * rgb.z + a3;  // d L / d f_q  (c = rgb, wch = 1)
+            u_hat += -dfx * fy * s;  // d f_q / d u = -fx'(bx - pfx) fy
+            v_hat += -fx * dfy * s;
+        }
+    }
+    // c = rw * rgb, wch = div * rw  (values rw = div = 1)
+    const float crgb = dot(c_hat, rgb);
+    const float rw_hat = crgb + wch_hat;
+    float div_hat = wch_hat + crgb;  // rgb is proportional to the primary det in every integrator
+
+    // ---- re-projection: it.p = o + d  ->  (uv, rw) ------------------------------------------------
+    V3 ref_hat = v3(0.f);
+    {
+        const float iz = 1.f / ref.z, it = 1.f / sc.S.tan_half_fov;
+        const float Wf = (float)sc.S.W, Hf = (float)sc.S.H;
+        // u = W (0.5 - 0.5 x / (z tan)),  v = H (0.5 - 0.5 aspect y / (z tan))
+        ref_hat.x += u_hat * (-0.5f * Wf * iz * it);
+        ref_hat.z += u_hat * (0.5f * Wf * ref.x * iz * iz * it);
+        ref_hat.y += v_hat * (-0.5f * Hf * sc.S.aspect * iz * it);
+        ref_hat.z += v_hat * (0.5f * Hf * sc.S.aspect * ref.y * iz * iz * it);
+        if (inside) {  // rw = W_e / detach(W_e), W_e ~ dist / z^3
+            const float inv_d2 = 1.f / dot(ref, ref);
+            ref_hat += rw_hat * V3{ref.x * inv_d2, ref.y * inv_d2, ref.z * inv_d2 - 3.f * iz};
+        }
+    }
+    V3 d_hat = V3{sc.S.R[0][0] * ref_hat.x + sc.S.R[0][1] * ref_hat.y + sc.S.R[0][2] * ref_hat.z,
+                  sc.S.R[1][0] * ref_hat.x + sc.S.R[1][1] * ref_hat.y + sc.S.R[1][2] * ref_hat.z,
+                  sc.S.R[2][0] * ref_hat.x + sc.S.R[2][1] * ref_hat.y + sc.S.R[2][2] * ref_hat.z};
+
+    // ---- shading -> surface interaction -------------------------------------------------------------
+    if (hit && sc.integrator != INTEGRATOR_SILHOUETTE) {
+        V3 n_hat = v3(0.f), p_hat = v3(0.f);
+        if (sc.integrator == INTEGRATOR_SIMPLE_SHADING) {
+            if (shade > 0.f) n_hat = v3((c_hat.x + c_hat.y + c_hat.z) * 0.57735026918962576f);
+        } else if (nee) {
+            // rgb_c = div * div_s * rho_c * cos_o * 4 Le_c
+            const V3 K = V3{4.f * sc.Sh.Le[0], 4.f * sc.Sh.Le[1], 4.f * sc.Sh.Le[2]};
+            const float cos_hat = c_hat.x * rho.x * K.x + c_hat.y * rho.y * K.y + c_hat.z * rho.z * K.z;
+            n_hat = cos_hat * sr.d;
+            const V3 ds_hat = cos_hat * n;
+            const float div_s_hat = crgb;
+            // albedo
+            const V3 rho_hat = V3{c_hat.x * K.x * cos_o, c_hat.y * K.y * cos_o, c_hat.z * K.z * cos_o};
+            if (sc.A.data != nullptr) {
+                st.n_albedo += 1;
+                p_hat += rho_hat.x * drho[0] + rho_hat.y * drho[1] + rho_hat.z * drho[2];
+                if (tg.grad_albedo != nullptr) {
+                    for (int k = 0; k < 8; ++k) {
+                        float* t = tg.grad_albedo + (size_t)taps.idx[k] * 3;
+                        SDFRT_ATOMIC_ADD(t + 0, taps.w[k] * rho_hat.x);
+                        SDFRT_ATOMIC_ADD(t + 1, taps.w[k] * rho_hat.y);
+                        SDFRT_ATOMIC_ADD(t + 2, taps.w[k] * rho_hat.z);
+                    }
+                }
+            }
+            // shadow-ray warp site (attached through its origin o_s = p + const)
+            if (reparam_at_depth(sc.W, 1)) {
+                const V3 tau_d = V3{r[REC_S_TAU_DX * rec_stride], r[REC_S_TAU_DY * rec_stride], r[REC_S_TAU_DZ * rec_stride]};
+                const V3 om_d = V3{r[REC_S_OMEGA_DX * rec_stride], r[REC_S_OMEGA_DY * rec_stride], r[REC_S_OMEGA_DZ * rec_stride]};
+                const float tau = r[REC_S_TAU * rec_stride];
+                const WarpSite ws = warp_site(sc.G, sc.W, sc.T, sr.o, sr.d, tau, tau_d, r[REC_S_OMEGA * rec_stride], om_d);
+                st.n_hess += isfinite(tau);
+                if (ws.active) {
+                    const float phi_hat = div_s_hat * ws.cphi_div + dot(ds_hat, ws.cphi_dir);
+                    const V3 g_hat = div_s_hat * ws.cg_div;
+                    scatter_site(tg.grad_sdf, sc.G, sr.o + tau * sr.d, phi_hat, g_hat);
+                    st.n_sites += 1;
+                    const V3 os_hat = phi_hat * ws.g + mul(ws.H, g_hat);
+                    p_hat += os_hat;
+                    grad_p = grad_p - os_hat;
+                }
+            }
+        }
+        // compute_surface_interaction (python/shapes.py:347-366): n = normalize(g(p)), p = o + t d,
+        // t = t* <- phi(p0) / detach(g . -d)
+        const float inv_gn = 1.f / sqrtf(dot(g_p, g_p));
+        const V3 gp_hat = (n_hat - dot(n, n_hat) * n) * inv_gn;
+        p_hat += mul(H_p, gp_hat);
+        const float t_hat = dot(p_hat, d0);
+        const float phi2_hat = t_hat / (-dot(g_p, d0));
+        const V3 dd = its_t * p_hat + (its_t * phi2_hat) * g_p;
+        if (isfinite(phi2_hat) & isfinite(gp_hat.x + gp_hat.y + gp_hat.z) & isfinite(dd.x + dd.y + dd.z)) {
+            d_hat += dd;
+            scatter_site(tg.grad_sdf, sc.G, p, phi2_hat, gp_hat);
+            st.n_sites += 1;
+            grad_p = grad_p - (phi2_hat * g_p + mul(H_p, gp_hat));
+        }
+    }
+
+    // ---- primary warp site ---------------------------------------------------------------------------
+    if (reparam_at_depth(sc.W, 0)) {
+        const V3 tau_d = V3{r[REC_TAU_DX * rec_stride], r[REC_TAU_DY * rec_stride], r[REC_TAU_DZ * rec_stride]};
+        const V3 om_d = V3{r[REC_OMEGA_DX * rec_stride], r[REC_OMEGA_DY * rec_stride], r[REC_OMEGA_DZ * rec_stride]};
+        const float tau = r[REC_TAU * rec_stride];
+        const WarpSite ws = warp_site(sc.G, sc.W, sc.T, o, d0, tau, tau_d, r[REC_OMEGA * rec_stride], om_d);
+        st.n_hess += isfinite(tau);
+        if (ws.active) {
+            const float phi_hat = div_hat * ws.cphi_div + dot(d_hat, ws.cphi_dir);
+            const V3 g_hat = div_hat * ws.cg_div;
+            if (isfinite(phi_hat) & isfinite(g_hat.x + g_hat.y + g_hat.z)) {
+                scatter_site(tg.grad_sdf, sc.G, o + tau * d0, phi_hat, g_hat);
+                st.n_sites += 1;
+                grad_p = grad_p - (phi_hat * ws.g + mul(ws.H, g_hat));
+            }
+        }
+    }
+}
+
+}  // namespace sdfrt

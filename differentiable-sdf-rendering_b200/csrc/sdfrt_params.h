@@ -1,0 +1,107 @@
+// sdfrt_params.h -- host-side translation of the public C structs (include/sdfrt.h) into the
+// plain parameter blocks consumed by the per-lane code (sdfrt_core.cuh / sdfrt_lane.cuh).
+#pragma once
+#include <cmath>
+#include <cstring>
+
+#include "../../include/sdfrt.h"
+#include "sdfrt_lane.cuh"
+
+namespace sdfrt {
+
+inline void tracer_defaults(sdfrt_tracer_params* p) {  // python/shapes.py:28-41
+    p->step_scale = 1.0f;
+    p->trace_eps = 1e-6f;
+    p->refine_intersection = 1;
+    p->use_extra_weight = 1;
+    p->extra_thresh = 0.05f;
+    p->sil_weight_offset = 0.05f;
+    p->sil_weight_epsilon = 1e-6f;
+    p->weight_power = 3;
+    p->use_weight_sum_weight = 1;
+    p->max_steps = 1 << 16;
+}
+inline void warp_defaults(sdfrt_warp_params* p) {  // python/configs.py:12-40 ("Warp")
+    p->kind = SDFRT_WARP_2D;
+    p->edge_eps = 0.01f;
+    p->weight_strategy = 6;
+    p->clamping_thresh = 0.05f;
+    p->normalize_warp_field = 1;
+    p->max_reparam_depth = -1;
+}
+inline void sensor_defaults(sdfrt_sensor* s) {  // python/util.py:115-138, sensor 0 of a 6-camera rig is set by the caller
+    std::memset(s, 0, sizeof(*s));
+    for (int i = 0; i < 4; ++i) s->to_world[i * 4 + i] = 1.f;
+    s->fov_x_deg = 39.f;
+    s->near_clip = 1e-2f;
+    s->far_clip = 1e4f;
+    s->width = 128;
+    s->height = 128;
+    s->filter_radius = 2.f;
+    s->filter_stddev = 0.5f;
+    s->sample_border = 1;
+}
+inline void shading_defaults(sdfrt_shading* s) {
+    s->env_radiance[0] = s->env_radiance[1] = s->env_radiance[2] = 1.f;
+    s->env_dist = 2.f * std::sqrt(3.f);
+    s->albedo[0] = s->albedo[1] = s->albedo[2] = 0.5f;
+    s->hide_emitters = 0;
+}
+
+inline TracerParams make_tracer(const sdfrt_tracer_params& p) {
+    TracerParams t;
+    t.step_scale = p.step_scale; t.trace_eps = p.trace_eps;
+    t.refine_intersection = p.refine_intersection; t.use_extra_weight = p.use_extra_weight;
+    t.extra_thresh = p.extra_thresh; t.sil_weight_offset = p.sil_weight_offset; t.sil_weight_epsilon = p.sil_weight_epsilon;
+    t.weight_power = p.weight_power; t.use_weight_sum_weight = p.use_weight_sum_weight;
+    t.max_steps = p.max_steps > 0 ? p.max_steps : (1 << 16);
+    return t;
+}
+inline WarpParams make_warp(const sdfrt_warp_params& p) {
+    WarpParams w;
+    w.kind = p.kind; w.edge_eps = p.edge_eps; w.weight_strategy = p.weight_strategy;
+    w.clamping_thresh = p.clamping_thresh; w.normalize_warp_field = p.normalize_warp_field;
+    w.max_reparam_depth = p.max_reparam_depth;
+    return w;
+}
+inline SensorParams make_sensor(const sdfrt_sensor& s) {
+    SensorParams o;
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) o.R[i][j] = s.to_world[i * 4 + j];
+        o.c[i] = s.to_world[i * 4 + 3];
+    }
+    o.tan_half_fov = (float)std::tan(0.5 * (double)s.fov_x_deg * 3.14159265358979323846 / 180.0);
+    o.aspect = (float)s.width / (float)s.height;
+    o.near_clip = s.near_clip; o.far_clip = s.far_clip;
+    o.W = s.width; o.H = s.height;
+    // border_size = ceil(radius - 0.5) (mitsuba ReconstructionFilter), only sampled if sample_border
+    o.border = s.sample_border ? (int)std::ceil(s.filter_radius - 0.5f) : 0;
+    o.filter_radius = s.filter_radius;
+    o.filter_alpha = -1.f / (2.f * s.filter_stddev * s.filter_stddev);
+    o.filter_bias = (float)std::exp((double)o.filter_alpha * s.filter_radius * s.filter_radius);
+    return o;
+}
+inline ShadingParams make_shading(const sdfrt_shading& s) {
+    ShadingParams o;
+    for (int i = 0; i < 3; ++i) o.Le[i] = s.env_radiance[i];
+    o.env_dist = s.env_dist;
+    o.hide_emitters = s.hide_emitters;
+    return o;
+}
+inline PassParams make_pass(const SensorParams& S, uint32_t seed, int spp, int rank, int world) {
+    PassParams p;
+    p.seed = seed;
+    p.spp = spp;
+    p.log2_spp = -1;
+    for (int k = 0; k < 31; ++k)
+        if ((1 << k) == spp) p.log2_spp = k;
+    const unsigned long long npix = (unsigned long long)(S.W + 2 * S.border) * (unsigned long long)(S.H + 2 * S.border);
+    // contiguous pixel ranges per rank (rows of the film first), spp lanes per pixel
+    const unsigned long long p0 = npix * (unsigned long long)rank / (unsigned long long)world;
+    const unsigned long long p1 = npix * (unsigned long long)(rank + 1) / (unsigned long long)world;
+    p.lane_begin = p0 * (unsigned long long)spp;
+    p.lane_end = p1 * (unsigned long long)spp;
+    return p;
+}
+
+}  // namespace sdfrt

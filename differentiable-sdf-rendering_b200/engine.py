@@ -1,0 +1,191 @@
+"""Thin object wrapper over the C ABI (libsdfrt.so).  PyTorch is used for device memory and
+streams only; all rendering work happens in the hand-written CUDA kernels behind the C ABI."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _capi
+from ._capi import (INTEGRATOR_DIRECT, INTEGRATOR_SILHOUETTE, INTEGRATOR_SIMPLE_SHADING, WARP_2D, WARP_DUMMY, WARP_NONE,
+                    SdfrtError, check)
+
+INTEGRATOR_IDS = {'sdf_silhouette_reparam': INTEGRATOR_SILHOUETTE,
+                  'sdf_simple_shading_reparam': INTEGRATOR_SIMPLE_SHADING,
+                  'sdf_direct_reparam': INTEGRATOR_DIRECT}
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _f32c(t, device):
+    if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.device == device):
+        raise SdfrtError("expected a contiguous float32 CUDA tensor on " + str(device))
+    return t
+
+
+class Context:
+    """One sdfrt_ctx per (process, device)."""
+
+    def __init__(self, device=0):
+        self.lib = _capi.load()
+        if not torch.cuda.is_available():
+            raise SdfrtError("no CUDA device: libsdfrt has no CPU fallback")
+        self.device = torch.device('cuda', device if isinstance(device, int) else device.index or 0)
+        st = C.c_int(0)
+        self.ctx = self.lib.sdfrt_create(self.device.index, C.byref(st))
+        if not self.ctx:
+            raise SdfrtError(f"sdfrt_create failed ({st.value}): need an sm_100 GPU")
+        self._keep = {}
+        self.sensor = _capi.SensorParams()
+        self.lib.sdfrt_sensor_defaults(C.byref(self.sensor))
+
+    def __del__(self):
+        try:
+            if getattr(self, 'ctx', None):
+                self.lib.sdfrt_destroy(self.ctx)
+                self.ctx = None
+        except Exception:
+            pass
+
+    # ---- scene state ------------------------------------------------------------------------
+    def set_sdf(self, data, p=(0.0, 0.0, 0.0)):
+        """data: (Z, Y, X[, 1]) float32 CUDA tensor (borrowed)."""
+        _f32c(data, self.device)
+        rz, ry, rx = data.shape[:3]
+        pv = (C.c_float * 3)(*[float(v) for v in p])
+        check(self.ctx, self.lib.sdfrt_set_sdf(self.ctx, _ptr(data), rx, ry, rz, pv))
+        self._keep['sdf'] = data
+        self.sdf_shape = (rz, ry, rx)
+
+    def set_albedo(self, grid):
+        if grid is None:
+            check(self.ctx, self.lib.sdfrt_set_albedo(self.ctx, None, 0, 0, 0))
+        else:
+            _f32c(grid, self.device)
+            rz, ry, rx, ch = grid.shape
+            if ch != 3:
+                raise SdfrtError("albedo grid must be (Z, Y, X, 3)")
+            check(self.ctx, self.lib.sdfrt_set_albedo(self.ctx, _ptr(grid), rx, ry, rz))
+        self._keep['albedo'] = grid
+
+    def set_tracer(self, **kw):
+        p = _capi.TracerParams()
+        self.lib.sdfrt_tracer_defaults(C.byref(p))
+        for k, v in kw.items():
+            if not hasattr(p, k):
+                raise SdfrtError(f"unknown tracer attribute {k}")
+            setattr(p, k, v)
+        check(self.ctx, self.lib.sdfrt_set_tracer(self.ctx, C.byref(p)))
+
+    def set_warp(self, kind=WARP_2D, edge_eps=0.01, weight_strategy=6, clamping_thresh=0.05, normalize_warp_field=True,
+                 max_reparam_depth=-1):
+        p = _capi.WarpParams(kind, edge_eps, weight_strategy, clamping_thresh, int(normalize_warp_field), max_reparam_depth)
+        check(self.ctx, self.lib.sdfrt_set_warp(self.ctx, C.byref(p)))
+
+    def set_sensor(self, to_world, width, height, fov=39.0, near_clip=1e-2, far_clip=1e4, filter_radius=2.0,
+                   filter_stddev=0.5, sample_border=True):
+        s = self.sensor
+        s.to_world[:] = [float(v) for v in np.asarray(to_world, dtype=np.float64).reshape(-1)]
+        s.fov_x_deg, s.near_clip, s.far_clip = fov, near_clip, far_clip
+        s.width, s.height = int(width), int(height)
+        s.filter_radius, s.filter_stddev, s.sample_border = filter_radius, filter_stddev, int(sample_border)
+        check(self.ctx, self.lib.sdfrt_set_sensor(self.ctx, C.byref(s)))
+
+    def set_shading(self, env_radiance=(1.0, 1.0, 1.0), env_dist=2.0 * 3.0 ** 0.5, albedo=(0.5, 0.5, 0.5), hide_emitters=False):
+        p = _capi.ShadingParams()
+        p.env_radiance[:] = list(env_radiance)
+        p.env_dist = env_dist
+        p.albedo[:] = list(albedo)
+        p.hide_emitters = int(hide_emitters)
+        check(self.ctx, self.lib.sdfrt_set_shading(self.ctx, C.byref(p)))
+
+    def set_integrator(self, name_or_id):
+        i = INTEGRATOR_IDS[name_or_id] if isinstance(name_or_id, str) else int(name_or_id)
+        check(self.ctx, self.lib.sdfrt_set_integrator(self.ctx, i))
+
+    def set_partition(self, rank, world):
+        check(self.ctx, self.lib.sdfrt_set_partition(self.ctx, rank, world))
+
+    # ---- rendering ----------------------------------------------------------------------------
+    def film_dims(self):
+        h, w, b = C.c_int(), C.c_int(), C.c_int()
+        check(self.ctx, self.lib.sdfrt_film_dims(self.ctx, C.byref(h), C.byref(w), C.byref(b)))
+        return h.value, w.value, b.value
+
+    def wavefront_size(self, spp):
+        return int(self.lib.sdfrt_wavefront_size(self.ctx, spp))
+
+    def new_film(self):
+        h, w, _ = self.film_dims()
+        return torch.empty((h, w, 4), dtype=torch.float32, device=self.device)
+
+    def render_primal(self, seed, spp, film=None):
+        film = self.new_film() if film is None else film
+        check(self.ctx, self.lib.sdfrt_render_primal(self.ctx, seed & 0xFFFFFFFF, spp, _ptr(film), _stream(self.device)))
+        return film
+
+    def develop(self, film, image=None):
+        if image is None:
+            image = torch.empty((self.sensor.height, self.sensor.width, 3), dtype=torch.float32, device=self.device)
+        check(self.ctx, self.lib.sdfrt_develop(self.ctx, _ptr(film), _ptr(image), _stream(self.device)))
+        return image
+
+    def adjoint_accumulate(self, seed_grad, spp_grad, film=None):
+        film = self.new_film() if film is None else film
+        check(self.ctx, self.lib.sdfrt_adjoint_accumulate(self.ctx, seed_grad & 0xFFFFFFFF, spp_grad, _ptr(film),
+                                                          _stream(self.device)))
+        return film
+
+    def adjoint_backprop(self, film, grad_image, grad_sdf, grad_albedo=None, grad_p=None):
+        _f32c(grad_image, self.device)
+        _f32c(grad_sdf, self.device)
+        check(self.ctx, self.lib.sdfrt_adjoint_backprop(self.ctx, _ptr(film), _ptr(grad_image), _ptr(grad_sdf),
+                                                        _ptr(grad_albedo), _ptr(grad_p), _stream(self.device)))
+
+    def stats(self, reset=True):
+        s = _capi.Stats()
+        check(self.ctx, self.lib.sdfrt_get_stats(self.ctx, C.byref(s), int(reset), _stream(self.device)))
+        return s.as_dict()
+
+    # ---- test hooks -----------------------------------------------------------------------------
+    def trace_rays(self, o, d, maxt=None, differentiable=True):
+        _f32c(o, self.device)
+        _f32c(d, self.device)
+        n = o.shape[0]
+        f = dict(dtype=torch.float32, device=self.device)
+        out = dict(its_t=torch.empty(n, **f), warp_t=torch.empty(n, **f), warp_t_d=torch.empty(n, 3, **f),
+                   warp_weight=torch.empty(n, **f), warp_weight_d=torch.empty(n, 3, **f),
+                   n_steps=torch.empty(n, dtype=torch.int32, device=self.device))
+        ro = _capi.RayOut(*[out[k].data_ptr() for k in ('its_t', 'warp_t', 'warp_t_d', 'warp_weight', 'warp_weight_d', 'n_steps')])
+        check(self.ctx, self.lib.sdfrt_trace_rays(self.ctx, _ptr(o), _ptr(d), _ptr(maxt), n, int(differentiable),
+                                                  C.byref(ro), _stream(self.device)))
+        return out
+
+    def eval_sdf(self, x, order=0):
+        _f32c(x, self.device)
+        n = x.shape[0]
+        out = torch.empty((n, {0: 1, 1: 4, 2: 10}[order]), dtype=torch.float32, device=self.device)
+        check(self.ctx, self.lib.sdfrt_eval_sdf(self.ctx, _ptr(x), n, order, _ptr(out), _stream(self.device)))
+        return out
+
+    def render_view_host(self, sdf_host, seed, spp, seed_grad, spp_grad, grad_image_host=None, image_host=None,
+                         grad_sdf_host=None):
+        """End-to-end call with HOST (numpy / pinned torch CPU) buffers."""
+        def hp(a):
+            if a is None:
+                return None
+            return C.c_void_p(a.data_ptr() if torch.is_tensor(a) else a.ctypes.data)
+        rz, ry, rx = sdf_host.shape[:3]
+        if image_host is None:
+            image_host = torch.empty((self.sensor.height, self.sensor.width, 3), dtype=torch.float32).pin_memory()
+        if grad_sdf_host is None:
+            grad_sdf_host = torch.empty((rz, ry, rx), dtype=torch.float32).pin_memory()
+        check(self.ctx, self.lib.sdfrt_render_view_host(self.ctx, hp(sdf_host), rx, ry, rz, seed & 0xFFFFFFFF, spp,
+                                                        seed_grad & 0xFFFFFFFF, spp_grad, hp(grad_image_host),
+                                                        hp(image_host), hp(grad_sdf_host)))
+        return image_host, grad_sdf_host

@@ -1,0 +1,92 @@
+"""Host-side mirror of python/integrators/reparam.py: same attributes and method names; `render`
+and `render_backward` launch the CUDA passes through the C ABI."""
+import torch
+
+from .. import engine
+from ..shapes import Grid3d
+from ..warp import warp_params_of
+
+
+class Properties(dict):
+    """Stand-in for mi.Properties: a dict with .get / .has_property."""
+
+    def has_property(self, k):
+        return k in self
+
+
+class ReparamIntegrator:
+    integrator_name = None
+
+    def __init__(self, props=None, sdf=None):
+        props = Properties(props or {})
+        self.max_depth = props.get('max_depth', 4)
+        self.weight_by_spp = props.get('weight_by_spp', False)
+        assert not self.weight_by_spp, "Not supported"  # python/integrators/reparam.py:16
+        self.use_mis = props.get('use_mis', False)
+        if self.use_mis:
+            raise NotImplementedError("the BSDF-sampling MIS branch (sdf_direct_reparam.py:87-107) is not on the hot path")
+        self.antithetic_sampling = props.get('antithetic_sampling', False)
+        if self.antithetic_sampling:
+            raise NotImplementedError("antithetic_sampling is evaluation-only in the reference and not provided")
+        self.use_aovs = props.get('use_aovs', False)
+        self.hide_emitters = props.get('hide_emitters', False)
+        self.sdf = sdf
+        self.warp_field = None
+        self.last_film = None
+
+    # ---- parameter plumbing (python/integrators/reparam.py:269-277) ----
+    def traverse(self, cb):
+        if self.sdf is not None:
+            self.sdf.traverse(cb)
+
+    def parameters_changed(self, keys=None):
+        if self.sdf is not None:
+            self.sdf.parameters_changed(keys)
+
+    # ---- rendering ----
+    def _bind(self, scene, sensor):
+        if self.sdf is None:
+            raise ValueError("integrator has no SDF")
+        if isinstance(sensor, int):
+            sensor = scene.sensors()[sensor]
+        ctx = self.sdf.ctx
+        film = sensor.film()
+        ctx.set_sensor(sensor.to_world, film.width, film.height, sensor.fov, sensor.near_clip, sensor.far_clip,
+                       film.filter_radius, film.filter_stddev, film.sample_border)
+        ctx.set_shading(scene.env_radiance, scene.env_dist, scene.albedo, self.hide_emitters)
+        ctx.set_albedo(scene.albedo_grid)
+        ctx.set_integrator(self.integrator_name)
+        ctx.set_warp(**warp_params_of(self.warp_field))
+        ctx.set_tracer(**self.sdf.tracer_params())
+        return ctx
+
+    def _check_wavefront(self, ctx, spp):
+        n = ctx.wavefront_size(spp)
+        if n > 0xffffffff:  # python/integrators/reparam.py:48-50
+            raise Exception(f"Wavefront {n} exceeds {0xffffffff}")
+
+    def render(self, scene, sensor=0, seed=0, spp=0, develop=True, evaluate=True):
+        if not develop:
+            raise Exception("Must use develop=True for this AD integrator")  # python/integrators/reparam.py:122-123
+        ctx = self._bind(scene, sensor)
+        self._check_wavefront(ctx, spp)
+        film = ctx.render_primal(seed, spp)
+        return ctx.develop(film)
+
+    def render_backward(self, scene, params, grad_in, sensor=0, seed=0, spp=0):
+        """Accumulates dLoss/d(sdf.data) into `sdf.data.grad` (and the reflectance grid's .grad)."""
+        ctx = self._bind(scene, sensor)
+        self._check_wavefront(ctx, spp)
+        film = ctx.adjoint_accumulate(seed, spp)
+        data = self.sdf.data
+        if data.grad is None:
+            data.grad = torch.zeros_like(data)
+        galb = None
+        if scene.albedo_grid is not None and scene.albedo_grid.requires_grad:
+            if scene.albedo_grid.grad is None:
+                scene.albedo_grid.grad = torch.zeros_like(scene.albedo_grid)
+            galb = scene.albedo_grid.grad
+        if not hasattr(self.sdf, 'p_grad') or self.sdf.p_grad is None:
+            self.sdf.p_grad = torch.zeros(3, dtype=torch.float32, device=ctx.device)
+        ctx.adjoint_backprop(film, grad_in.contiguous(), data.grad, galb, self.sdf.p_grad)
+        self.last_film = film

@@ -1,0 +1,171 @@
+/* libsdfrt -- C ABI of the B200-native differentiable SDF rendering hot path.
+ *
+ * Drop-in boundary for rgl-epfl/differentiable-sdf-rendering (reference paths are relative to
+ * /root/reference).  The reference has no FFI of its own -- its device code is JIT-traced
+ * from Python by Dr.Jit -- so every entry point cites the Python interface it replaces.
+ *
+ * Conventions: plain pointers and sizes only (no torch / Dr.Jit types).  Unless a function
+ * name ends in `_host`, every data pointer is a DEVICE pointer owned by the caller and
+ * every call is asynchronous on `stream` (a cudaStream_t passed as void*).  Functions
+ * return 0 on success, <0 on error; sdfrt_last_error() describes the last failure of the
+ * context.  One context per (process, device); a context is not thread-safe.
+ * There is no CPU fallback: creation fails if no sm_100 device is usable.
+ */
+#ifndef SDFRT_H
+#define SDFRT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sdfrt_ctx sdfrt_ctx;
+
+enum { SDFRT_OK = 0, SDFRT_ERR_INVALID = -1, SDFRT_ERR_CUDA = -2, SDFRT_ERR_STATE = -3 };
+
+/* integrator plugins, python/integrators/{sdf_silhouette,sdf_simple_shading,sdf_direct}_reparam.py */
+enum { SDFRT_INTEGRATOR_SILHOUETTE = 0, SDFRT_INTEGRATOR_SIMPLE_SHADING = 1, SDFRT_INTEGRATOR_DIRECT = 2 };
+/* warp field kinds, python/warp.py: None / DummyWarpField(:179) / WarpField2D(:7) */
+enum { SDFRT_WARP_NONE = 0, SDFRT_WARP_DUMMY = 1, SDFRT_WARP_2D = 2 };
+
+/* SDFBase tracer knobs, python/shapes.py:28-41 (same defaults via sdfrt_tracer_defaults) */
+typedef struct sdfrt_tracer_params {
+    float step_scale;            /* :30 */
+    float trace_eps;             /* :31 */
+    int32_t refine_intersection; /* :33 */
+    int32_t use_extra_weight;    /* :34 */
+    float extra_thresh;          /* :35 */
+    float sil_weight_offset;     /* :36 */
+    float sil_weight_epsilon;    /* :37 */
+    int32_t weight_power;        /* :38 */
+    int32_t use_weight_sum_weight; /* :39 */
+    int32_t max_steps;           /* safety cap on the march (reference: unbounded, :170) */
+} sdfrt_tracer_params;
+
+/* WarpField2D attributes, python/warp.py:10-23 and python/configs.py:36-40 */
+typedef struct sdfrt_warp_params {
+    int32_t kind;               /* SDFRT_WARP_* */
+    float edge_eps;             /* :13 (already divided by 4 for strategy 2, :22-23) */
+    int32_t weight_strategy;    /* :14 */
+    float clamping_thresh;      /* :16 */
+    int32_t normalize_warp_field; /* :20 */
+    int32_t max_reparam_depth;  /* :11 */
+} sdfrt_warp_params;
+
+/* perspective sensor + hdrfilm + gaussian rfilter as built by python/util.py:115-138 */
+typedef struct sdfrt_sensor {
+    float to_world[16];   /* row-major 4x4, mitsuba look_at convention (columns left, up, dir, origin) */
+    float fov_x_deg;      /* 39 */
+    float near_clip, far_clip;
+    int32_t width, height;
+    float filter_radius;  /* gaussian: 4*stddev = 2 */
+    float filter_stddev;  /* 0.5 */
+    int32_t sample_border;
+} sdfrt_sensor;
+
+/* `constant` environment emitter + diffuse BSDF of the dummy SDF shape */
+typedef struct sdfrt_shading {
+    float env_radiance[3];
+    float env_dist;        /* 2 * scene bounding-sphere radius (shadow-ray target distance) */
+    float albedo[3];       /* used when no albedo grid is bound */
+    int32_t hide_emitters; /* python/integrators/sdf_direct_reparam.py:12 */
+} sdfrt_shading;
+
+/* device-counted work, for the roofline byte count */
+typedef struct sdfrt_stats {
+    uint64_t n_rays;          /* camera lanes processed */
+    uint64_t n_evals_value;   /* 64-tap value-only evaluations */
+    uint64_t n_evals_grad;    /* value+gradient evaluations */
+    uint64_t n_evals_hess;    /* value+gradient+Hessian evaluations */
+    uint64_t n_scatter_sites; /* 64-tap adjoint scatter sites */
+    uint64_t n_albedo_lookups;
+    uint64_t n_steps_max;     /* longest march */
+    uint64_t n_hits;
+} sdfrt_stats;
+
+/* per-ray tracer outputs of SDFBase.ray_intersect, python/shapes.py:288 (test hook) */
+typedef struct sdfrt_ray_out {
+    float* its_t;          /* [n] */
+    float* warp_t;         /* [n] */
+    float* warp_t_d;       /* [n*3] */
+    float* warp_weight;    /* [n] */
+    float* warp_weight_d;  /* [n*3] */
+    int32_t* n_steps;      /* [n] or NULL */
+} sdfrt_ray_out;
+
+/* ---- lifetime ---------------------------------------------------------------------- */
+sdfrt_ctx* sdfrt_create(int device, int* status);
+void sdfrt_destroy(sdfrt_ctx* ctx);
+const char* sdfrt_last_error(const sdfrt_ctx* ctx);
+int sdfrt_version(void);
+
+void sdfrt_tracer_defaults(sdfrt_tracer_params* p);  /* python/shapes.py:28-41 */
+void sdfrt_warp_defaults(sdfrt_warp_params* p);      /* python/configs.py:12-40 ("Warp" config) */
+void sdfrt_sensor_defaults(sdfrt_sensor* s);         /* python/util.py:115-138 */
+void sdfrt_shading_defaults(sdfrt_shading* s);
+
+/* ---- scene state (borrowed pointers; valid until the next set_* of the same kind) ------ */
+/* Grid3d(data) + traverse()'s `sdf.data` / `sdf.p`: python/shapes.py:378-392,469-479.
+ * sdf is (rz, ry, rx) C-order, x fastest; identity to_world (has_transform == False). */
+int sdfrt_set_sdf(sdfrt_ctx* ctx, const float* sdf, int rx, int ry, int rz, const float p[3]);
+/* `main-bsdf.reflectance.volume.data`: (rz, ry, rx, 3) trilinear grid on [0,1]^3, or NULL */
+int sdfrt_set_albedo(sdfrt_ctx* ctx, const float* rgb_grid, int rx, int ry, int rz);
+int sdfrt_set_tracer(sdfrt_ctx* ctx, const sdfrt_tracer_params* p);
+int sdfrt_set_warp(sdfrt_ctx* ctx, const sdfrt_warp_params* p);   /* integrator.warp_field = ... (python/shape_opt.py:47) */
+int sdfrt_set_sensor(sdfrt_ctx* ctx, const sdfrt_sensor* s);
+int sdfrt_set_shading(sdfrt_ctx* ctx, const sdfrt_shading* s);
+int sdfrt_set_integrator(sdfrt_ctx* ctx, int integrator);         /* SDFRT_INTEGRATOR_* */
+/* multi-GPU ray partition: this context renders wavefront lanes [lane_begin, lane_end) of the
+ * (W+2b)(H+2b)*spp wavefront; expressed as fractions rank/world so it is spp-independent.
+ * RNG streams stay keyed by the global lane index (python/integrators/reparam.py:51). */
+int sdfrt_set_partition(sdfrt_ctx* ctx, int rank, int world);
+
+/* ---- rendering ---------------------------------------------------------------------- */
+/* film accumulator geometry: (H+2b, W+2b, 4) floats, b = border of the reconstruction filter */
+int sdfrt_film_dims(const sdfrt_ctx* ctx, int* height_b, int* width_b, int* border);
+uint64_t sdfrt_wavefront_size(const sdfrt_ctx* ctx, int spp);
+
+/* mi.render(...) primal: ReparamIntegrator.render(mode=Primal), python/integrators/reparam.py:120-185.
+ * Zeroes and fills film_accum (this rank's lanes only); no develop. */
+int sdfrt_render_primal(sdfrt_ctx* ctx, uint32_t seed, int spp, float* film_accum, void* stream);
+/* film.develop(): image (H, W, 3) = rgb / weight, border cropped */
+int sdfrt_develop(sdfrt_ctx* ctx, const float* film_accum, float* image, void* stream);
+
+/* render_backward, python/integrators/reparam.py:187-190, split in two phases so that a
+ * multi-GPU caller can all-reduce the film between them:
+ *  accumulate: re-render at (seed_grad, spp_grad) with the differentiable tracer; fills
+ *              film_accum and keeps per-lane tracer records inside the context.
+ *  backprop:   given the (all-reduced) film_accum of that re-render and grad_image =
+ *              dLoss/dImage (H, W, 3), ADDS dLoss/d(sdf.data) into grad_sdf (rz, ry, rx),
+ *              dLoss/d(albedo) into grad_albedo (or NULL) and dLoss/d(sdf.p) into grad_p[3]
+ *              (device pointer, or NULL). */
+int sdfrt_adjoint_accumulate(sdfrt_ctx* ctx, uint32_t seed_grad, int spp_grad, float* film_accum, void* stream);
+int sdfrt_adjoint_backprop(sdfrt_ctx* ctx, const float* film_accum, const float* grad_image,
+                           float* grad_sdf, float* grad_albedo, float* grad_p, void* stream);
+
+/* device work counters accumulated since the last reset (synchronises `stream`) */
+int sdfrt_get_stats(sdfrt_ctx* ctx, sdfrt_stats* out, int reset, void* stream);
+
+/* ---- test hooks / helpers used by the reference's callers ------------------------------ */
+/* SDFBase.ray_intersect / ray_intersect_non_diff, python/shapes.py:115-339; o, d: [n*3], maxt: [n] or NULL */
+int sdfrt_trace_rays(sdfrt_ctx* ctx, const float* o, const float* d, const float* maxt, int n,
+                     int differentiable, const sdfrt_ray_out* out, void* stream);
+/* Grid3d.eval / eval_and_grad / eval_all, python/shapes.py:420-450; x: [n*3];
+ * out: order 0 -> [n], 1 -> [n*4] (v, g), 2 -> [n*10] (v, g, Hxx Hyy Hzz Hxy Hxz Hyz).
+ * Also serves variables.upsample_sdf (python/variables.py:18-23). */
+int sdfrt_eval_sdf(sdfrt_ctx* ctx, const float* x, int n, int order, float* out, void* stream);
+
+/* ---- end-to-end entry point with HOST buffers (what a plugin without device memory calls) --
+ * One optimisation-loop view: upload sdf (host, rz*ry*rx floats), render primal at (seed, spp),
+ * re-render + backprop at (seed_grad, spp_grad) against grad_image_host (H*W*3; if NULL the
+ * reference benchmark's loss dr.sum(img) is used, figures/benchmark/benchmark.py:44), download
+ * image_host (H*W*3) and grad_sdf_host (rz*ry*rx).  Synchronous. */
+int sdfrt_render_view_host(sdfrt_ctx* ctx, const float* sdf_host, int rx, int ry, int rz,
+                           uint32_t seed, int spp, uint32_t seed_grad, int spp_grad,
+                           const float* grad_image_host, float* image_host, float* grad_sdf_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDFRT_H */

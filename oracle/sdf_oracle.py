@@ -1,0 +1,991 @@
+"""CPU oracle for the differentiable-SDF-rendering hot path.  TEST INFRASTRUCTURE ONLY.
+
+PARITY UNPINNED: the reference (rgl-epfl/differentiable-sdf-rendering) ships no tests,
+golden vectors or scenes, and its runtime (mitsuba 3.0-3.5 / drjit <= 0.4, unpinned,
+`README.md:48-50`) is not installable offline.  This file is therefore a *restatement*:
+every function follows the cited reference lines, with Dr.Jit's AD replaced by
+torch.autograd on the CPU (`replace_grad(a, b)` == `a.detach() + (b - b.detach())`,
+`dr.detach` == `.detach()`, `dr.suspend_grad` == `torch.no_grad`).  The third-party
+pieces (cubic texture, PCG32/TEA sampler, perspective sensor, gaussian film, constant
+emitter, diffuse BSDF, spawn_ray_to) are restated from the published Mitsuba 3 /
+Dr.Jit algorithms as listed in SURVEY.md App. B and oracle/ref_semantics.md.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this module.  The product path (libsdfrt.so) never does.
+
+All ray data are torch tensors of shape (N,) or (N,3); dtype is selectable (float64 is
+the gold used for parity, float32 mirrors the arithmetic type of the CUDA path).
+"""
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+INF = float('inf')
+
+# --------------------------------------------------------------------------------------
+# small AD helpers (Dr.Jit semantics)
+# --------------------------------------------------------------------------------------
+
+
+def replace_grad(a, b):
+    """dr.replace_grad: value of `a`, derivative of `b`."""
+    a = a.detach() if torch.is_tensor(a) else torch.as_tensor(a, dtype=b.dtype)
+    return a + (b - b.detach())
+
+
+def dr_sign(x):
+    """dr.sign: +1 for x >= 0, -1 otherwise."""
+    return torch.where(x >= 0, torch.ones_like(x), -torch.ones_like(x))
+
+
+def dot(a, b):
+    return (a * b).sum(-1)
+
+
+def normalize(v):
+    return v / torch.linalg.norm(v, dim=-1, keepdim=True)
+
+
+def outer(v, w):
+    """math_util.outer_product (python/math_util.py:21-25)."""
+    return v[..., :, None] * w[..., None, :]
+
+
+def eye3(like):
+    return torch.eye(3, dtype=like.dtype).expand(like.shape[:-1] + (3, 3))
+
+
+def normalize_sqr(x):
+    """math_util.normalize_sqr (python/math_util.py:13-18): x/|x|^2 and its Jacobian."""
+    x2 = dot(x, x)
+    jac = eye3(x) / x2[..., None, None] - (2 / (x2 * x2))[..., None, None] * outer(x, x)
+    return x / x2[..., None], jac
+
+
+def bbox_distance_inside_d(x, bmin, bmax):
+    """math_util.bbox_distance_inside_d (python/math_util.py:31-41)."""
+    d = torch.minimum((x - bmin).min(-1).values, (bmax - x).min(-1).values).clamp_min(0.0)
+    bbox_max_dist = (bmax - x).abs()
+    bbox_min_dist = (bmin - x).abs()
+    md = torch.minimum(bbox_min_dist, bbox_max_dist)
+    n = torch.zeros_like(x)
+    mx, my, mz = md[..., 0], md[..., 1], md[..., 2]
+    n[(mx < my) & (mx < mz)] = torch.tensor([1.0, 0.0, 0.0], dtype=x.dtype)
+    n[(my < mz) & (my < mx)] = torch.tensor([0.0, 1.0, 0.0], dtype=x.dtype)
+    n[(mz < mx) & (mz < my)] = torch.tensor([0.0, 0.0, 1.0], dtype=x.dtype)
+    d_d = torch.where((d > 0)[..., None], n * dr_sign(bbox_max_dist - bbox_min_dist), torch.zeros_like(x))
+    return d, d_d
+
+
+# --------------------------------------------------------------------------------------
+# Sampler: Mitsuba `independent` = PCG32 seeded through TEA
+# --------------------------------------------------------------------------------------
+
+_M32 = np.uint64(0xFFFFFFFF)
+PCG32_MULT = np.uint64(0x5851F42D4C957F2D)
+
+
+def sample_tea_32(v0, v1, rounds=4):
+    """Tiny Encryption Algorithm, 4 rounds, as mitsuba `sample_tea_32`."""
+    v0 = np.asarray(v0, dtype=np.uint64) & _M32
+    v1 = np.asarray(v1, dtype=np.uint64) & _M32
+    s = np.uint64(0)
+    for _ in range(rounds):
+        s = (s + np.uint64(0x9E3779B9)) & _M32
+        v0 = (v0 + ((((v1 << np.uint64(4)) & _M32) + np.uint64(0xA341316C)) ^ (v1 + s) ^ ((v1 >> np.uint64(5)) + np.uint64(0xC8013EA4)))) & _M32
+        v1 = (v1 + ((((v0 << np.uint64(4)) & _M32) + np.uint64(0xAD90777D)) ^ (v0 + s) ^ ((v0 >> np.uint64(5)) + np.uint64(0x7E95761E)))) & _M32
+    return v0, v1
+
+
+class PCG32:
+    """drjit PCG32 (XSH-RR 64/32) vectorised over lanes."""
+
+    def __init__(self, initstate, initseq):
+        with np.errstate(over='ignore'):
+            self.state = np.zeros_like(initstate, dtype=np.uint64)
+            self.inc = ((initseq.astype(np.uint64) << np.uint64(1)) | np.uint64(1))
+            self.next_u32()
+            self.state = self.state + initstate.astype(np.uint64)
+            self.next_u32()
+
+    def next_u32(self):
+        with np.errstate(over='ignore'):
+            old = self.state
+            self.state = old * PCG32_MULT + self.inc
+            xorshifted = (((old >> np.uint64(18)) ^ old) >> np.uint64(27)) & _M32
+            rot = (old >> np.uint64(59)) & _M32
+            res = ((xorshifted >> rot) | (xorshifted << ((np.uint64(32) - rot) & np.uint64(31)))) & _M32
+        return res.astype(np.uint32)
+
+    def next_f32(self):
+        u = self.next_u32()
+        bits = (u >> np.uint32(9)) | np.uint32(0x3F800000)
+        return bits.view(np.float32) - np.float32(1.0)
+
+
+class IndependentSampler:
+    """`sampler.seed(seed, wavefront)` + next_1d/next_2d (python/integrators/reparam.py:39-51)."""
+
+    def __init__(self, seed, wavefront, dtype, lane_offset=0, lane_count=None):
+        idx = np.arange(lane_offset, lane_offset + (wavefront if lane_count is None else lane_count), dtype=np.uint64)
+        v0, v1 = sample_tea_32(np.full_like(idx, np.uint64(seed & 0xFFFFFFFF)), idx)
+        self.rng = PCG32(v0, v1)
+        self.dtype = dtype
+
+    def next_1d(self):
+        return torch.from_numpy(self.rng.next_f32().copy()).to(self.dtype)
+
+    def next_2d(self):
+        a = self.next_1d()
+        b = self.next_1d()
+        return torch.stack([a, b], -1)
+
+
+# --------------------------------------------------------------------------------------
+# Tricubic B-spline texture (drjit Texture3f.eval_cubic / _grad / _hessian), SURVEY App. B
+# --------------------------------------------------------------------------------------
+
+
+def _bspline_w(a):
+    a2 = a * a
+    a3 = a2 * a
+    w = torch.stack([(-a3 + 3 * a2 - 3 * a + 1) / 6, (3 * a3 - 6 * a2 + 4) / 6,
+                     (-3 * a3 + 3 * a2 + 3 * a + 1) / 6, a3 / 6], -1)
+    dw = torch.stack([-0.5 * a2 + a - 0.5, 1.5 * a2 - 2 * a, -1.5 * a2 + a + 0.5, 0.5 * a2], -1)
+    ddw = torch.stack([1 - a, 3 * a - 2, -3 * a + 1, a], -1)
+    return w, dw, ddw
+
+
+class Grid3d:
+    """python/shapes.py:375-483 (identity `to_world` only) + SDFBase knobs `:28-41`."""
+
+    def __init__(self, data, p=None):
+        data = torch.as_tensor(data)
+        if data.dim() == 4:
+            data = data[..., 0]
+        self.data = data  # (Z, Y, X), x fastest; may require grad
+        self.dtype = data.dtype
+        self.p = torch.zeros(3, dtype=self.dtype) if p is None else torch.as_tensor(p, dtype=self.dtype)
+        # SDFBase.__init__ defaults (python/shapes.py:28-41)
+        self.step_scale = 1.0
+        self.trace_eps = 1e-6
+        self.refine_intersection = True
+        self.use_extra_weight = True
+        self.extra_thresh = 0.05
+        self.sil_weight_offset = 0.05
+        self.sil_weight_epsilon = 1e-6
+        self.weight_power = 3
+        self.use_weight_sum_weight = True
+        self.max_steps = 1 << 16  # safety cap (reference has none, python/shapes.py:170)
+        self.n_evals = 0          # 64-tap evaluation sites (for the roofline byte count)
+
+    @property
+    def shape(self):
+        return tuple(self.data.shape)
+
+    def bbox(self):
+        """python/shapes.py:416-418: unit cube +-0.05; ignores self.p (Appendix C #13)."""
+        lo = torch.full((3,), -0.05, dtype=self.dtype)
+        hi = torch.full((3,), 1.05, dtype=self.dtype)
+        return lo, hi
+
+    def _taps(self, x, order):
+        """Direct 64-tap evaluation; order 0: value, 1: +gradient, 2: +Hessian."""
+        self.n_evals += x.shape[0]
+        Z, Y, X = self.data.shape
+        res = torch.tensor([X, Y, Z], dtype=self.dtype)
+        xl = x - self.p  # call_wrap: to_local @ (x - p) (python/shapes.py:408-414)
+        u = xl * res - 0.5
+        uf = torch.floor(u.detach())
+        a = u - uf
+        i0 = uf.to(torch.int64) - 1
+        wx, dwx, ddwx = _bspline_w(a[:, 0])
+        wy, dwy, ddwy = _bspline_w(a[:, 1])
+        wz, dwz, ddwz = _bspline_w(a[:, 2])
+        o = torch.arange(4)
+        ix = (i0[:, 0:1] + o).clamp(0, X - 1)
+        iy = (i0[:, 1:2] + o).clamp(0, Y - 1)
+        iz = (i0[:, 2:3] + o).clamp(0, Z - 1)
+        lin = (iz[:, :, None, None] * Y + iy[:, None, :, None]) * X + ix[:, None, None, :]
+        f = self.data.reshape(-1)[lin.reshape(-1)].reshape(-1, 4, 4, 4)  # [n, z, y, x]
+
+        def red(az, ay, ax):
+            return torch.einsum('nzyx,nz,ny,nx->n', f, az, ay, ax)
+
+        v = red(wz, wy, wx)
+        if order == 0:
+            return v
+        g = torch.stack([red(wz, wy, dwx) * res[0], red(wz, dwy, wx) * res[1], red(dwz, wy, wx) * res[2]], -1)
+        if order == 1:
+            return v, g
+        hxx = red(wz, wy, ddwx) * res[0] * res[0]
+        hyy = red(wz, ddwy, wx) * res[1] * res[1]
+        hzz = red(ddwz, wy, wx) * res[2] * res[2]
+        hxy = red(wz, dwy, dwx) * res[0] * res[1]
+        hxz = red(dwz, wy, dwx) * res[0] * res[2]
+        hyz = red(dwz, dwy, wx) * res[1] * res[2]
+        H = torch.stack([torch.stack([hxx, hxy, hxz], -1), torch.stack([hxy, hyy, hyz], -1),
+                         torch.stack([hxz, hyz, hzz], -1)], -2)
+        return v, g, H
+
+    def eval(self, x):
+        """python/shapes.py:420-421 (value only)."""
+        return self._taps(x, 0)
+
+    def eval_and_grad(self, x):
+        """python/shapes.py:430-436."""
+        return self._taps(x, 1)
+
+    def eval_grad(self, x):
+        """python/shapes.py:423-428."""
+        return self._taps(x, 1)[1]
+
+    def eval_all(self, x):
+        """python/shapes.py:438-450: (v, detach v, g, detach g, H)."""
+        v, g, H = self._taps(x, 2)
+        return v, v.detach(), g, g.detach(), H
+
+    # ---- python/shapes.py:68-113 -----------------------------------------------------
+    def eval_trace_weight(self, d, i, bmin, bmax, x, sdf_value, sdf_grad, hessian):
+        n_dot_d = dot(sdf_grad, d)
+        n_dot_n = dot(sdf_grad, sdf_grad)
+        dot_ratio = n_dot_d / n_dot_n
+        denom = self.sil_weight_epsilon + sdf_value.abs() + self.sil_weight_offset * n_dot_d * dot_ratio
+        dist_weight = 1 / denom ** self.weight_power
+        bbox_dist, bbox_dist_d = bbox_distance_inside_d(x, bmin, bmax)
+        bbox_eps = 0.01
+        bbox_weight = torch.where(i > 0, torch.minimum(bbox_dist, torch.full_like(bbox_dist, bbox_eps)) / bbox_eps,
+                                  torch.ones_like(bbox_dist))
+        weight = dist_weight * bbox_weight
+        bbox_weight_d = torch.where(((i > 0) & (bbox_dist < bbox_eps))[:, None], bbox_dist_d / bbox_eps,
+                                    torch.zeros_like(bbox_dist_d))
+        gradient = 2 * dot_ratio[:, None] * (d - dot_ratio[:, None] * sdf_grad)
+        denom_d = dr_sign(sdf_value)[:, None] * sdf_grad + self.sil_weight_offset * torch.einsum('ni,nij->nj', gradient, hessian)
+        dist_weight_d = (-self.weight_power * dist_weight / denom)[:, None] * denom_d
+        weight_d = dist_weight[:, None] * bbox_weight_d + bbox_weight[:, None] * dist_weight_d
+        return weight, weight_d
+
+    # ---- AABB slab test (mitsuba BoundingBox3f::ray_intersect), SURVEY App. B --------
+    @staticmethod
+    def _aabb(o, d, bmin, bmax):
+        d_rcp = 1.0 / d
+        t1 = (bmin - o) * d_rcp
+        t2 = (bmax - o) * d_rcp
+        t1p = torch.minimum(t1, t2)
+        t2p = torch.maximum(t1, t2)
+        mint = t1p.max(-1).values
+        maxt = t2p.min(-1).values
+        active = ((d != 0) | ((o >= bmin) & (o <= bmax))).all(-1) & (maxt >= mint)
+        inside = ((o >= bmin) & (o <= bmax)).all(-1)
+        return active, mint, maxt, inside
+
+    # ---- python/shapes.py:115-288: the differentiable tracer --------------------------
+    @torch.no_grad()
+    def ray_intersect(self, o, d, ray_maxt, active, extra_outputs=None):
+        N = o.shape[0]
+        dt = self.dtype
+        d = normalize(d)
+        bmin, bmax = self.bbox()
+        intersects_bbox, mint, maxt, inside_bbox = self._aabb(o, d, bmin, bmax)
+        intersects_bbox = intersects_bbox & ((mint > 0) | inside_bbox)
+        active = active & intersects_bbox
+        maxt = torch.minimum(maxt, ray_maxt)
+        trace_eps = self.trace_eps * maxt.clamp_min(1.0)
+        its_t = torch.full((N,), INF, dtype=dt)
+        t = torch.where(inside_bbox, torch.zeros_like(mint), mint + 1e-5)
+        warp_t = torch.zeros(N, dtype=dt)
+        prev_surf_dist = torch.zeros(N, dtype=dt)
+        prev_sdf_grad_c = torch.zeros(N, 3, dtype=dt)
+        weight_sum = torch.zeros(N, dtype=dt)
+        mixed_sum_d = torch.zeros(N, 3, dtype=dt)
+        weight_d_sum = torch.zeros(N, 3, dtype=dt)
+        it = torch.zeros(N, dtype=torch.int64)
+        extra_weight_sum = torch.zeros(N, dtype=dt)
+        extra_weight_sum_d = torch.zeros(N, 3, dtype=dt)
+
+        # entry face normal + initial t_d (python/shapes.py:155-164)
+        bbox_its_p = o + t[:, None] * d
+        md = torch.minimum((bmin - bbox_its_p).abs(), (bmax - bbox_its_p).abs())
+        n = torch.zeros(N, 3, dtype=dt)
+        n[(md[:, 0] < md[:, 1]) & (md[:, 0] < md[:, 2])] = torch.tensor([1.0, 0.0, 0.0], dtype=dt)
+        n[(md[:, 1] < md[:, 2]) & (md[:, 1] < md[:, 0])] = torch.tensor([0.0, 1.0, 0.0], dtype=dt)
+        n[(md[:, 2] < md[:, 0]) & (md[:, 2] < md[:, 1])] = torch.tensor([0.0, 0.0, 1.0], dtype=dt)
+        d_dot_n = dot(d, n)
+        t_d = torch.zeros(N, 3, dtype=dt)
+        m0 = (~inside_bbox) & (d_dot_n.abs() > 0)
+        t_d[m0] = (-n[m0] / d_dot_n[m0, None]) * t[m0, None]
+
+        act = torch.nonzero(active).squeeze(-1)
+        step = 0
+        while act.numel() > 0 and step < self.max_steps:
+            step += 1
+            a = act
+            da = d[a]
+            ta = t[a]
+            x = o[a] + ta[:, None] * da
+            sdf_value, sdf_grad, hessian = self._taps(x, 2)
+            if self.step_scale != 1.0:
+                sdf_value = sdf_value * self.step_scale
+                sdf_grad = sdf_grad * self.step_scale
+                hessian = hessian * self.step_scale
+            intersected = sdf_value < trace_eps[a]
+            its_t[a] = torch.where(intersected, ta, its_t[a])
+            surf_dist = sdf_value.abs()
+            weight, weight_d = self.eval_trace_weight(da, it[a], bmin, bmax, x, sdf_value, sdf_grad, hessian)
+
+            ews = extra_weight_sum[a]
+            psd = prev_surf_dist[a]
+            if self.use_extra_weight:
+                inv_extra_w_den = 1 / torch.minimum(torch.full_like(surf_dist, self.extra_thresh), surf_dist)
+                dist_difference = psd - surf_dist
+                ews = ews + torch.where(dist_difference >= 0, dist_difference * inv_extra_w_den, torch.zeros_like(ews))
+                ews = torch.minimum(ews, torch.ones_like(ews))
+            curr_segment_value = torch.where(intersected, torch.zeros_like(surf_dist), surf_dist)
+            segment_length = 0.5 * (curr_segment_value + psd)
+            weight_increment = segment_length * weight
+            if self.use_extra_weight:
+                weight_increment = weight_increment * ews
+            weight_sum[a] = weight_sum[a] + weight_increment
+            warp_t[a] = warp_t[a] + weight_increment * ta
+
+            tda = t_d[a]
+
+            def convert_deriv(in_d):
+                return ta[:, None] * in_d + dot(da, in_d)[:, None] * tda
+
+            weight_d = convert_deriv(weight_d)
+            sdf_grad_c = convert_deriv(sdf_grad)
+            pg = prev_sdf_grad_c[a]
+            segment_d = 0.5 * (sdf_grad_c + pg)
+            if self.use_extra_weight:
+                sdf_sign = dr_sign(sdf_value)
+                surf_dist_d = sdf_sign[:, None] * sdf_grad_c
+                extra_w_d = (pg - surf_dist_d) * inv_extra_w_den[:, None]
+                extra_w_d = extra_w_d - (dist_difference * inv_extra_w_den ** 2)[:, None] * torch.where(
+                    (sdf_value < self.extra_thresh)[:, None], surf_dist_d, torch.zeros_like(surf_dist_d))
+                ewd = extra_weight_sum_d[a] + torch.where((dist_difference > 0.0)[:, None], extra_w_d, torch.zeros_like(extra_w_d))
+                ewd = torch.where(((ews >= 1.0) | (ews <= 0.0))[:, None], torch.zeros_like(ewd), ewd)
+                extra_weight_sum_d[a] = ewd
+                extra_weight_sum[a] = ews
+                weight_d = weight[:, None] * ewd + weight_d * ews[:, None]
+                weight = weight * ews
+            weight_increment_d = weight[:, None] * segment_d + weight_d * segment_length[:, None]
+            mixed_sum_d[a] = mixed_sum_d[a] + weight_increment_d * ta[:, None] + (weight * segment_length)[:, None] * tda
+            t_d[a] = tda + sdf_grad_c
+            weight_d_sum[a] = weight_d_sum[a] + weight_increment_d
+            it[a] = it[a] + 1
+            ta = ta + curr_segment_value
+            t[a] = ta
+            prev_surf_dist[a] = surf_dist
+            prev_sdf_grad_c[a] = sdf_grad_c
+            keep = (ta <= maxt[a]) & (~intersected)
+            act = a[keep]
+
+        if extra_outputs is not None:
+            extra_outputs['i'] = it
+            extra_outputs['weight_sum'] = weight_sum.clone()
+
+        if self.refine_intersection:
+            its_t = self._refine(o, d, its_t, trace_eps)
+
+        inv_weight_sum = 1 / weight_sum
+        warp_t = warp_t * inv_weight_sum
+        warp_t_d = (-warp_t[:, None] * weight_d_sum + mixed_sum_d) * inv_weight_sum[:, None]
+        warp_weight = weight_sum.clamp(0.0, 1.0)
+        warp_weight_d = torch.where(((weight_sum > 0.0) & (weight_sum < 1.0))[:, None], weight_d_sum,
+                                    torch.zeros_like(weight_d_sum))
+        invalid = (weight_sum < 1e-7) | ~intersects_bbox
+        invalid = invalid | ~torch.isfinite(warp_t)  # 0/0 when weight_sum == 0 (reference: same branch via <1e-7)
+        warp_t = torch.where(invalid, torch.full_like(warp_t, INF), warp_t)
+        z3 = torch.zeros_like(warp_t_d)
+        warp_t_d = torch.where(invalid[:, None], z3, warp_t_d)
+        warp_weight = torch.where(invalid, torch.zeros_like(warp_weight), warp_weight)
+        warp_weight_d = torch.where(invalid[:, None], z3, warp_weight_d)
+        return its_t, warp_t, warp_t_d, warp_weight, warp_weight_d
+
+    @torch.no_grad()
+    def _refine(self, o, d, its_t, trace_eps):
+        """python/shapes.py:245-257 / :323-334."""
+        its_t = its_t.clone()
+        ref = torch.nonzero(torch.isfinite(its_t)).squeeze(-1)
+        i = 0
+        while ref.numel() > 0 and i < 10:
+            tt = its_t[ref]
+            min_dist = self._taps(o[ref] + tt[:, None] * d[ref], 0)
+            its_t[ref] = tt + min_dist * (10.0 / (10.0 + i))
+            keep = (min_dist <= 0) | (min_dist > trace_eps[ref])
+            i += 1
+            ref = ref[keep]
+        return its_t
+
+    # ---- python/shapes.py:290-339: value-only tracer -----------------------------------
+    @torch.no_grad()
+    def ray_intersect_non_diff(self, o, d, ray_maxt, active, refine=None):
+        N = o.shape[0]
+        dt = self.dtype
+        d = normalize(d)
+        bmin, bmax = self.bbox()
+        intersects_bbox, mint, maxt, inside_bbox = self._aabb(o, d, bmin, bmax)
+        intersects_bbox = intersects_bbox & ((mint > 0) | inside_bbox)
+        active = active & intersects_bbox
+        maxt = torch.minimum(maxt, ray_maxt)
+        its_t = torch.full((N,), INF, dtype=dt)
+        t = torch.where(inside_bbox, torch.zeros_like(mint), mint + 1e-5)
+        trace_eps = self.trace_eps * maxt.clamp_min(1.0)
+        act = torch.nonzero(active).squeeze(-1)
+        step = 0
+        while act.numel() > 0 and step < self.max_steps:
+            step += 1
+            a = act
+            ta = t[a]
+            sdf_value = self._taps(o[a] + ta[:, None] * d[a], 0)
+            if self.step_scale != 1.0:
+                sdf_value = sdf_value * self.step_scale
+            intersected = sdf_value < trace_eps[a]
+            its_t[a] = torch.where(intersected, ta, its_t[a])
+            curr = torch.where(intersected, torch.zeros_like(sdf_value), sdf_value.abs())
+            keep = (ta <= maxt[a]) & (~intersected)
+            ta = ta + curr
+            t[a] = ta
+            keep = keep & (ta <= maxt[a])
+            act = a[keep]
+        if self.refine_intersection if refine is None else refine:
+            its_t = self._refine(o, d, its_t, trace_eps)
+        return its_t
+
+    # ---- python/shapes.py:347-366 ----------------------------------------------------
+    def compute_surface_interaction(self, o, d, t):
+        """Valid (finite t) lanes only.  Returns dict(t, p, n, wi_z); d may carry grad."""
+        p = o + t[:, None] * d
+        sdf_value, sdf_grad = self.eval_and_grad(p)
+        t_diff = sdf_value / dot(sdf_grad, -d).detach()
+        t2 = replace_grad(t, t_diff)
+        p2 = o + t2[:, None] * d
+        n = normalize(self.eval_grad(p2))
+        wi_z = dot(n, -d)  # si.to_local(-ray.d).z
+        return dict(t=t2, p=p2, n=n, wi_z=wi_z)
+
+
+# --------------------------------------------------------------------------------------
+# Warp field (python/warp.py:7-128)
+# --------------------------------------------------------------------------------------
+
+
+class WarpField2D:
+    def __init__(self, sdf, weight_strategy=4, edge_eps=0.05):
+        self.max_reparam_depth = -1
+        self.sdf = sdf
+        self.edge_eps = edge_eps / 4 if weight_strategy == 2 else edge_eps  # python/warp.py:22-23
+        self.weight_strategy = weight_strategy
+        self.clamping_thresh = 0.0
+        self.normalize_warp_field = True
+
+    def weight(self, x, d, sdf_value, sdf_grad, edge_eps):
+        """python/warp.py:25-39."""
+        bmin, bmax = self.sdf.bbox()
+        bbox_dist, bbox_dist_d = bbox_distance_inside_d(x, bmin, bmax)
+        use_edge_eps = edge_eps <= bbox_dist
+        edge_eps_d = torch.where(use_edge_eps[:, None], torch.zeros_like(bbox_dist_d), bbox_dist_d)
+        edge_eps = torch.minimum(edge_eps, bbox_dist)
+        inv_edge_eps = 1 / edge_eps
+        surf_dist = sdf_value.abs()
+        fac = 1 - surf_dist * inv_edge_eps
+        w = fac.clamp_min(0.0)
+        w_d = -dr_sign(sdf_value)[:, None] * sdf_grad * inv_edge_eps[:, None] + (surf_dist * inv_edge_eps ** 2)[:, None] * edge_eps_d
+        w_d = torch.where((fac >= 0.0)[:, None], w_d, torch.zeros_like(w_d))
+        edge_eps_d = torch.where(use_edge_eps & (fac >= 0), surf_dist * inv_edge_eps ** 2, torch.zeros_like(surf_dist))
+        return w, w_d, edge_eps_d
+
+    def weight_epsilon(self, t):
+        """python/warp.py:41-45."""
+        if self.weight_strategy == 6:
+            return self.edge_eps * t.detach()
+        return torch.full_like(t, self.edge_eps)
+
+    def eval(self, x, ray_d, t, dt_dx, active, warp_weight, warp_weight_d, return_active=False):
+        """python/warp.py:47-96.  Inputs must be finite on every lane (caller sanitises)."""
+        sdf_value, _, sdf_normal, sdf_normal_d, h_mat = self.sdf.eval_all(x)
+        h_mat = h_mat.detach()
+        if self.normalize_warp_field:
+            sdf_normal_d_n, norm_jac = normalize_sqr(sdf_normal_d)
+            warp = -sdf_normal_d_n * sdf_value[:, None]
+            jac = -(norm_jac @ h_mat) * sdf_value[:, None, None] - outer(sdf_normal_d_n, sdf_normal)
+        else:
+            sdf_normal_d_n = sdf_normal_d
+            warp = -sdf_normal_d_n * sdf_value[:, None]
+            jac = -h_mat * sdf_value[:, None, None] - outer(sdf_normal_d_n, sdf_normal)
+        xd = x.detach()
+        d = ray_d.detach()
+        weight, weight_grad, edge_eps_grad = self.weight(xd, d, sdf_value.detach(), sdf_normal.detach(),
+                                                         self.weight_epsilon(t))
+        weight_grad = weight_grad + edge_eps_grad[:, None] * ray_d * self.edge_eps
+        weight_grad = weight_grad * warp_weight[:, None] + weight[:, None] * warp_weight_d
+        weight = weight * warp_weight
+        weight = weight.detach()
+        jac = outer(warp, weight_grad) + weight[:, None, None] * jac
+        warp = warp * weight[:, None]
+        warp = replace_grad(torch.zeros_like(warp), warp)
+        warp = ray_d * torch.clamp_min(t, self.clamping_thresh)[:, None] + warp
+        warp = normalize(warp)
+        proj_jac = (eye3(ray_d) - outer(ray_d, ray_d)) @ jac
+        jac = proj_jac + proj_jac @ outer(ray_d, dt_dx / t[:, None])
+        div = jac[:, 0, 0] + jac[:, 1, 1] + jac[:, 2, 2]
+        active = active & (weight > 0)
+        if return_active:
+            return None, active & torch.isfinite(div) & torch.isfinite(warp).all(-1)
+        div = torch.where(active, div, torch.zeros_like(div))
+        warp = torch.where(active[:, None], warp, ray_d)
+        warp = replace_grad(ray_d, warp)
+        return warp, div
+
+    def ray_intersect(self, o, d, ray_maxt, depth=0, ray_test=False, reparam=True, active=None):
+        """python/warp.py:99-123.  Returns (its_t, d_attached, div, tracer outputs)."""
+        N = o.shape[0]
+        if active is None:
+            active = torch.ones(N, dtype=torch.bool)
+        reparam = reparam and ((self.max_reparam_depth < 0) or (depth <= self.max_reparam_depth))
+        its_t, warp_t, warp_t_d, warp_weight, warp_weight_d = self.sdf.ray_intersect(
+            o.detach(), d.detach(), ray_maxt, active)
+        div = torch.ones(N, dtype=o.dtype)
+        d_out = d
+        if reparam:
+            ok = active & torch.isfinite(warp_t)
+            sel = torch.nonzero(ok).squeeze(-1)
+            if sel.numel() > 0:
+                # pass 1 (no grad): which lanes end with weight > 0 (python/warp.py:91); only those carry
+                # a derivative, and restricting pass 2 to them keeps 0*inf out of the reverse sweep.
+                with torch.no_grad():
+                    _, dv0 = self.eval(o[sel] + warp_t[sel, None] * d[sel], d[sel], warp_t[sel], warp_t_d[sel],
+                                       torch.ones_like(sel, dtype=torch.bool), warp_weight[sel], warp_weight_d[sel],
+                                       return_active=True)
+                sel = sel[dv0]
+            if sel.numel() > 0:
+                ds = d[sel]
+                warp, dv = self.eval(o[sel] + warp_t[sel, None] * ds, ds, warp_t[sel], warp_t_d[sel],
+                                     torch.ones_like(sel, dtype=torch.bool), warp_weight[sel], warp_weight_d[sel])
+                # ray.d = replace_grad(ray.d, warp); div = replace_grad(1, div)  (python/warp.py:114-115)
+                d_out = d.index_add(0, sel, warp - warp.detach())
+                div = div.index_add(0, sel, dv - dv.detach())
+        return its_t, d_out, div, dict(warp_t=warp_t, warp_t_d=warp_t_d, warp_weight=warp_weight,
+                                       warp_weight_d=warp_weight_d)
+
+
+class DummyWarpField:
+    """python/warp.py:179-196: value-only trace, no reparameterisation."""
+
+    def __init__(self, sdf):
+        self.sdf = sdf
+
+    def ray_intersect(self, o, d, ray_maxt, depth=0, ray_test=False, reparam=True, active=None):
+        N = o.shape[0]
+        if active is None:
+            active = torch.ones(N, dtype=torch.bool)
+        its_t = self.sdf.ray_intersect_non_diff(o.detach(), d.detach(), ray_maxt, active)
+        return its_t, d, torch.ones(N, dtype=o.dtype), {}
+
+
+# --------------------------------------------------------------------------------------
+# Sensor / film / emitter / BSDF restatements
+# --------------------------------------------------------------------------------------
+
+
+def look_at(origin, target, up):
+    """mitsuba ScalarTransform4f.look_at: columns (left, new_up, dir, origin)."""
+    origin, target, up = (np.asarray(v, dtype=np.float64) for v in (origin, target, up))
+    dir_ = target - origin
+    dir_ /= np.linalg.norm(dir_)
+    left = np.cross(up, dir_)
+    left /= np.linalg.norm(left)
+    new_up = np.cross(dir_, left)
+    m = np.eye(4)
+    m[:3, 0], m[:3, 1], m[:3, 2], m[:3, 3] = left, new_up, dir_, origin
+    return m
+
+
+def regular_camera_origins(n_sensors, radius=2.0, angle_shift=0.0, height_scale=1.0):
+    """python/util.py:84-112 with height_steps = int(n_sensors > 1), hemisphere, vary_height."""
+    if n_sensors > 1:
+        angles = (np.arange(n_sensors) / n_sensors + angle_shift / n_sensors) * 2 * np.pi
+        elevation = 1.15 / height_scale + np.sin(angles * n_sensors / 4) * 0.5
+        elevation = np.clip(elevation, 0.0, np.pi / 2 + 0.05)
+    else:
+        # height_steps == 0 -> falls in the `else` branch as well (python/util.py:101-111)
+        angles = (np.arange(1) / 1 + angle_shift) * 2 * np.pi
+        elevation = 1.15 / height_scale + np.sin(angles * 1 / 4) * 0.5
+        elevation = np.clip(elevation, 0.0, np.pi / 2 + 0.05)
+    origins = np.stack([np.cos(angles) * np.sin(elevation) * radius, np.cos(elevation) * radius,
+                        np.sin(angles) * np.sin(elevation) * radius], -1)
+    return origins + np.array([0.5, 0.0, 0.5])
+
+
+@dataclass
+class Sensor:
+    """Perspective sensor + hdrfilm(gaussian) as built by python/util.py:115-138."""
+    to_world: np.ndarray
+    width: int = 128
+    height: int = 128
+    fov: float = 39.0           # degrees, x axis
+    near: float = 1e-2
+    far: float = 1e4
+    filter_radius: float = 2.0  # gaussian stddev 0.5 -> radius 4*stddev
+    filter_stddev: float = 0.5
+    sample_border: bool = True
+
+    @property
+    def border(self):
+        return int(math.ceil(self.filter_radius - 0.5)) if self.sample_border else 0
+
+    def sample_ray(self, pos_px, dtype):
+        """PerspectiveCamera::sample_ray_differential; pos in pixel units."""
+        W, H = self.width, self.height
+        tan = math.tan(math.radians(self.fov) * 0.5)
+        aspect = W / H
+        sx = pos_px[:, 0] / W
+        sy = pos_px[:, 1] / H
+        near_p = torch.stack([(1 - 2 * sx) * tan * self.near, (1 - 2 * sy) * tan / aspect * self.near,
+                              torch.full_like(sx, self.near)], -1)
+        d_l = normalize(near_p)
+        R = torch.as_tensor(self.to_world[:3, :3], dtype=dtype)
+        c = torch.as_tensor(self.to_world[:3, 3], dtype=dtype)
+        d = d_l @ R.T
+        inv_z = 1 / d_l[:, 2]
+        o = c + d * (self.near * inv_z)[:, None]
+        maxt = (self.far - self.near) * inv_z
+        return o, d, maxt
+
+    def sample_direction(self, p):
+        """PerspectiveCamera::sample_direction: uv (pixels) and importance*inv_dist^2."""
+        W, H = self.width, self.height
+        dtype = p.dtype
+        tan = math.tan(math.radians(self.fov) * 0.5)
+        aspect = W / H
+        R = torch.as_tensor(self.to_world[:3, :3], dtype=dtype)
+        c = torch.as_tensor(self.to_world[:3, 3], dtype=dtype)
+        ref = (p - c) @ R
+        sx = 0.5 - 0.5 * ref[:, 0] / (ref[:, 2] * tan)
+        sy = 0.5 - 0.5 * aspect * ref[:, 1] / (ref[:, 2] * tan)
+        uv = torch.stack([sx * W, sy * H], -1)
+        dist = torch.linalg.norm(ref, dim=-1)
+        inside = (sx >= 0) & (sx <= 1) & (sy >= 0) & (sy <= 1) & (ref[:, 2] >= self.near) & (ref[:, 2] <= self.far)
+        # importance(local_d) * inv_dist^2 = norm * inv_ct^3 / dist^2 = norm * dist / z^3
+        norm = 1.0 / ((2 * tan) * (2 * tan / aspect))
+        w = norm * dist / ref[:, 2] ** 3
+        return uv, torch.where(inside, w, torch.zeros_like(w))
+
+
+def gaussian_filter(x, stddev, radius):
+    """mitsuba GaussianFilter::eval: max(0, exp(alpha x^2) - exp(alpha r^2)), alpha=-1/(2 sigma^2)."""
+    alpha = -1.0 / (2.0 * stddev * stddev)
+    bias = math.exp(alpha * radius * radius)
+    return (torch.exp(alpha * x * x) - bias).clamp_min(0.0)
+
+
+def film_put(sensor, uv, channels):
+    """ImageBlock::put (no normalisation) onto a (H+2b, W+2b, C) accumulator."""
+    b = sensor.border
+    Wb, Hb = sensor.width + 2 * b, sensor.height + 2 * b
+    C = channels.shape[1]
+    r = sensor.filter_radius
+    pos_f = uv + (b - 0.5)
+    lo = torch.ceil(pos_f.detach() - r).to(torch.int64)
+    acc = torch.zeros(Hb * Wb, C, dtype=uv.dtype)
+    n = int(math.ceil(2 * r)) + 1
+    for yi in range(n):
+        by = lo[:, 1] + yi
+        wy = gaussian_filter(by.to(uv.dtype) - pos_f[:, 1], sensor.filter_stddev, r)
+        for xi in range(n):
+            bx = lo[:, 0] + xi
+            wx = gaussian_filter(bx.to(uv.dtype) - pos_f[:, 0], sensor.filter_stddev, r)
+            ok = (bx >= 0) & (bx < Wb) & (by >= 0) & (by < Hb) & (bx.to(uv.dtype) <= pos_f[:, 0].detach() + r) & (
+                by.to(uv.dtype) <= pos_f[:, 1].detach() + r)
+            idx = torch.where(ok, by * Wb + bx, torch.zeros_like(bx))
+            val = channels * torch.where(ok, wx * wy, torch.zeros_like(wx))[:, None]
+            acc = acc.index_add(0, idx, val)
+    return acc.reshape(Hb, Wb, C)
+
+
+def film_develop(sensor, acc):
+    """HDRFilm::develop: rgb / (W == 0 ? 1 : W), crop the border."""
+    b = sensor.border
+    core = acc[b:b + sensor.height, b:b + sensor.width]
+    w = core[..., 3:4]
+    w = torch.where(w == 0, torch.ones_like(w), w)
+    return core[..., :3] / w
+
+
+RAY_EPSILON = 2.0 ** -24 * 1500.0
+SHADOW_EPSILON = RAY_EPSILON * 10.0
+
+
+def square_to_uniform_sphere(u):
+    z = 1 - 2 * u[:, 1]
+    r = torch.sqrt((1 - z * z).clamp_min(0.0))
+    phi = 2 * math.pi * u[:, 0]
+    return torch.stack([r * torch.cos(phi), r * torch.sin(phi), z], -1)
+
+
+@dataclass
+class Scene:
+    """Minimal stand-in for the Mitsuba scene the integrators query."""
+    sdf: Grid3d
+    sensor: Sensor
+    env_radiance: tuple = (1.0, 1.0, 1.0)     # `constant` emitter
+    albedo: tuple = (0.5, 0.5, 0.5)           # diffuse reflectance (constant)
+    albedo_grid: torch.Tensor = None          # optional (Z,Y,X,3) trilinear gridvolume on [0,1]^3
+    env_dist: float = 2.0 * math.sqrt(3.0)    # constant emitter: 2 * scene bsphere radius (unit cube + margin)
+    hide_emitters: bool = False
+
+
+def eval_albedo(scene, p):
+    """diffuse BSDF reflectance: constant or trilinear gridvolume lookup (clamp)."""
+    if scene.albedo_grid is None:
+        return torch.as_tensor(scene.albedo, dtype=p.dtype).expand(p.shape[0], 3)
+    g = scene.albedo_grid
+    Z, Y, X, _ = g.shape
+    res = torch.tensor([X, Y, Z], dtype=p.dtype)
+    u = p * res - 0.5
+    uf = torch.floor(u.detach())
+    a = u - uf
+    i0 = uf.to(torch.int64)
+    out = 0
+    flat = g.reshape(-1, 3)
+    for dz in (0, 1):
+        iz = (i0[:, 2] + dz).clamp(0, Z - 1)
+        wz = a[:, 2] if dz else 1 - a[:, 2]
+        for dy in (0, 1):
+            iy = (i0[:, 1] + dy).clamp(0, Y - 1)
+            wy = a[:, 1] if dy else 1 - a[:, 1]
+            for dx in (0, 1):
+                ix = (i0[:, 0] + dx).clamp(0, X - 1)
+                wx = a[:, 0] if dx else 1 - a[:, 0]
+                out = out + flat[(iz * Y + iy) * X + ix] * (wx * wy * wz)[:, None]
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# Integrators (python/integrators/*.py)
+# --------------------------------------------------------------------------------------
+
+
+def _ray_intersect(scene, warp_field, o, d, maxt, depth, reparam, active=None):
+    """ReparamIntegrator.ray_intersect without OptiX (python/integrators/reparam.py:201-232).
+
+    With reparam=False only `its_t` is consumed; the reference still runs the differentiable
+    tracer when a WarpField2D is attached (python/shapes.py:116) but its `its_t` follows the same
+    stepping rule (:235,238 vs :317-320), so the value-only tracer is used here.
+    """
+    wf = warp_field if warp_field is not None else DummyWarpField(scene.sdf)
+    if isinstance(wf, WarpField2D) and not (reparam and (wf.max_reparam_depth < 0 or depth <= wf.max_reparam_depth)):
+        wf = DummyWarpField(scene.sdf)
+    return wf.ray_intersect(o, d, maxt, depth=depth, reparam=reparam, active=active)
+
+
+def sample_silhouette(scene, warp_field, sampler, o, d, maxt, reparam_mode):
+    """python/integrators/sdf_silhouette_reparam.py:16-29 (always reparameterises)."""
+    its_t, d_att, det, _ = _ray_intersect(scene, warp_field, o, d, maxt, 0, True)
+    valid = torch.isfinite(its_t)
+    # (the reference also builds `si` here; its gradient does not reach `result`)
+    result = torch.where(valid, torch.ones_like(det), torch.zeros_like(det)) * det
+    return result[:, None].expand(-1, 3), d_att, det
+
+
+def sample_simple_shading(scene, warp_field, sampler, o, d, maxt, reparam_mode):
+    """python/integrators/sdf_simple_shading_reparam.py:16-28."""
+    its_t, d_att, det, _ = _ray_intersect(scene, warp_field, o, d, maxt, 0, True)
+    h = torch.nonzero(torch.isfinite(its_t)).squeeze(-1)
+    result = torch.zeros(o.shape[0], dtype=o.dtype)
+    if h.numel() > 0:
+        si = scene.sdf.compute_surface_interaction(o[h], d_att[h], its_t[h])
+        l = torch.full((3,), 1.0 / math.sqrt(3.0), dtype=o.dtype)
+        shade = (si['n'] @ l).clamp_min(0.0)
+        result = result.index_add(0, h, shade * det[h])
+    return result[:, None].expand(-1, 3), d_att, det
+
+
+def sample_direct(scene, warp_field, sampler, o, d, maxt, reparam_mode):
+    """python/integrators/sdf_direct_reparam.py:16-84,109-111 (NEE branch, use_mis=False)."""
+    sdf = scene.sdf
+    dtype = o.dtype
+    N = o.shape[0]
+    reparametrize = reparam_mode
+    its_t, d_att, det, _ = _ray_intersect(scene, warp_field, o, d, maxt, 0, reparametrize)
+    valid = torch.isfinite(its_t)
+    Le = torch.as_tensor(scene.env_radiance, dtype=dtype)
+    # result += throughput * si.emitter(scene).eval(si): environment for misses (:24-31)
+    miss_vis = (~valid) & (not scene.hide_emitters)
+    result = det[:, None] * torch.where(miss_vis[:, None], Le.expand(N, 3), torch.zeros(N, 3, dtype=dtype))
+
+    # ---- emitter sampling (:36-84), on the lanes with a valid si ----
+    u = sampler.next_2d()
+    h = torch.nonzero(valid).squeeze(-1)
+    if h.numel() == 0:
+        return result, d_att, det
+    si = sdf.compute_surface_interaction(o[h], d_att[h], its_t[h])
+    # si_d = compute_surface_interaction(detach(ray), detach(its_t)) has the same values (python/warp.py:121)
+    p, n = si['p'], si['n']
+    with torch.no_grad():
+        d_e = square_to_uniform_sphere(u[h])
+        ds_p = p.detach() + d_e * scene.env_dist
+        ds_pdf = 1.0 / (4 * math.pi)
+        # si.spawn_ray_to(ds.p): offset along detached n, maxt shortened
+        mag = (1 + p.detach().abs().max(-1).values) * RAY_EPSILON
+        sgn = dr_sign(dot(n.detach(), ds_p - p.detach()))
+        off = (mag * sgn)[:, None] * n.detach()
+    o_s = p + off
+    dvec = ds_p - o_s
+    dist = torch.linalg.norm(dvec, dim=-1)
+    d_s = (dvec / dist[:, None]).detach()  # shadow_ray.d = detach(shadow_ray.d) (:51)
+    maxt_s = (dist * (1 - SHADOW_EPSILON)).detach()
+    its_s, d_s_att, det_e, _ = _ray_intersect(scene, warp_field, o_s, d_s, maxt_s, 1, reparametrize)
+    occluded = torch.isfinite(its_s)
+    cos_o = dot(n, d_s_att)           # wo = si.to_local(shadow_ray.d); only z enters the diffuse BSDF
+    cos_i = si['wi_z']
+    emitter_val = Le / ds_pdf         # constant emitter eval / pdf (:68-74)
+    rho = eval_albedo(scene, p)
+    gate = (~occluded) & (cos_i > 0) & (cos_o > 0)
+    bsdf_val = rho / math.pi * cos_o[:, None]
+    nee = bsdf_val * emitter_val
+    contrib = det[h, None] * nee * det_e[:, None]
+    contrib = torch.where(gate[:, None], contrib, torch.zeros_like(contrib))
+    result = result.index_add(0, h, contrib)
+    return result, d_att, det
+
+
+INTEGRATORS = {'sdf_silhouette_reparam': sample_silhouette,
+               'sdf_simple_shading_reparam': sample_simple_shading,
+               'sdf_direct_reparam': sample_direct}
+
+
+def render(scene, warp_field, integrator, seed, spp, mode_backward=False, lane_range=None, develop=True):
+    """ReparamIntegrator.render (python/integrators/reparam.py:120-185) + eval_sample (:82-118).
+
+    mode_backward=False == dr.ADMode.Primal (no reparameterisation in the direct integrator).
+    lane_range=(lo, hi) restricts the wavefront to global lanes [lo, hi) (multi-GPU partition
+    emulation; RNG streams stay keyed by the global lane index).  Returns the developed image
+    (H, W, 3) or, with develop=False, the raw accumulator (H+2b, W+2b, 4).
+    """
+    sensor = scene.sensor
+    dtype = scene.sdf.dtype
+    b = sensor.border
+    Wb, Hb = sensor.width + 2 * b, sensor.height + 2 * b
+    wavefront = Wb * Hb * spp
+    lo, hi = (0, wavefront) if lane_range is None else lane_range
+    idx = torch.arange(lo, hi, dtype=torch.int64)
+    pix = idx // spp
+    py = pix // Wb
+    px = pix - py * Wb
+    pos = torch.stack([px - b, py - b], -1).to(dtype)
+    sampler = IndependentSampler(seed, wavefront, dtype, lane_offset=lo, lane_count=hi - lo)
+    r = sampler.next_2d()
+    position_sample = pos + r
+    _wavelength = sampler.next_1d()  # consumed even in RGB (python/integrators/reparam.py:90)
+    o, d, maxt = sensor.sample_ray(position_sample, dtype)
+    rgb, d_att, det = INTEGRATORS[integrator](scene, warp_field, sampler, o, d, maxt, mode_backward)
+    # re-projection (python/integrators/reparam.py:100-106)
+    it_p = o + d_att
+    uv, rw = sensor.sample_direction(it_p)
+    rw_safe = torch.where(rw > 0, rw, torch.ones_like(rw))
+    rw1 = torch.where(rw > 0, rw_safe / rw_safe.detach(), torch.ones_like(rw))
+    rw1 = replace_grad(torch.ones_like(rw1), rw1)
+    rgb = rw1[:, None] * rgb
+    wch = replace_grad(torch.ones_like(det), det * rw1)
+    acc = film_put(sensor, uv, torch.cat([rgb, wch[:, None]], -1))
+    if not develop:
+        return acc
+    return film_develop(sensor, acc)
+
+
+def render_backward(scene, warp_field, integrator, grad_in, seed, spp):
+    """ReparamIntegrator.render_backward (python/integrators/reparam.py:187-190).
+
+    Returns (image, grad wrt sdf.data (Z,Y,X), grad wrt sdf.p (3,), grad wrt albedo grid or None).
+    """
+    sdf = scene.sdf
+    data0, p0, alb0 = sdf.data, sdf.p, scene.albedo_grid
+    sdf.data = data0.detach().clone().requires_grad_(True)
+    sdf.p = p0.detach().clone().requires_grad_(True)
+    if alb0 is not None:
+        scene.albedo_grid = alb0.detach().clone().requires_grad_(True)
+    try:
+        image = render(scene, warp_field, integrator, seed, spp, mode_backward=True)
+        loss = (image * grad_in).sum()
+        wrt = [sdf.data, sdf.p] + ([scene.albedo_grid] if alb0 is not None else [])
+        grads = torch.autograd.grad(loss, wrt, allow_unused=True)
+        g_data = grads[0] if grads[0] is not None else torch.zeros_like(sdf.data)
+        g_p = grads[1] if grads[1] is not None else torch.zeros_like(sdf.p)
+        g_alb = None
+        if alb0 is not None:
+            g_alb = grads[2] if grads[2] is not None else torch.zeros_like(scene.albedo_grid)
+        return image.detach(), g_data, g_p, g_alb
+    finally:
+        sdf.data, sdf.p, scene.albedo_grid = data0, p0, alb0
+
+
+# --------------------------------------------------------------------------------------
+# Synthetic stand-in SDFs -- scenes of the reference are a separate download
+# --------------------------------------------------------------------------------------
+
+
+def _grid_points(res):
+    """Nodes at linspace(0,1,R) like create_sphere_sdf (python/shapes.py:557-560)."""
+    lin = np.linspace(0, 1, res)
+    z, y, x = np.meshgrid(lin, lin, lin, indexing='ij')
+    return x, y, z
+
+
+def box_sdf_grid(res, extents=0.49, smoothing=0.01):
+    """variables.update_box_sdf (python/variables.py:161-166) with BoxSDF (python/shapes.py:548-550)."""
+    lin = np.linspace(-0.5, 0.5, res)
+    z, y, x = np.meshgrid(lin, lin, lin, indexing='ij')
+    q = np.stack([np.abs(x), np.abs(y), np.abs(z)], -1) - extents
+    return np.linalg.norm(np.maximum(q, 0.0), axis=-1) + np.minimum(q.max(-1), 0.0) - smoothing
+
+
+def make_sdf(kind, res):
+    """'sphere' (python/shapes.py:557: c=.5, r=.3), 'knot' (torus-knot tube), 'blobs' (smooth union)."""
+    x, y, z = _grid_points(res)
+    if kind == 'sphere':
+        sdf = np.sqrt((x - 0.5) ** 2 + (y - 0.5) ** 2 + (z - 0.5) ** 2) - 0.3
+    elif kind == 'knot':
+        # (2,3) torus knot sampled as a polyline; tube radius 0.045; conservative distance
+        s = np.linspace(0, 2 * np.pi, 400, endpoint=False)
+        R, r = 0.24, 0.10
+        cx = 0.5 + (R + r * np.cos(3 * s)) * np.cos(2 * s)
+        cy = 0.5 + r * np.sin(3 * s) * 1.3
+        cz = 0.5 + (R + r * np.cos(3 * s)) * np.sin(2 * s)
+        P = np.stack([cx, cy, cz], -1)
+        pts = np.stack([x.ravel(), y.ravel(), z.ravel()], -1)
+        best = np.full(pts.shape[0], np.inf)
+        for k in range(0, P.shape[0], 8):
+            dd = np.linalg.norm(pts[:, None, :] - P[None, k:k + 8, :], axis=-1).min(1)
+            best = np.minimum(best, dd)
+        sdf = (best - 0.045).reshape(x.shape)
+    elif kind == 'blobs':
+        rng = np.random.default_rng(0)
+        c = rng.uniform(0.25, 0.75, size=(24, 3))
+        rad = rng.uniform(0.05, 0.13, size=24)
+        k = 0.03
+        acc = np.zeros_like(x)
+        for ci, ri in zip(c, rad):
+            dd = np.sqrt((x - ci[0]) ** 2 + (y - ci[1]) ** 2 + (z - ci[2]) ** 2) - ri
+            acc += np.exp(-dd / k)
+        sdf = -k * np.log(acc)
+    else:
+        raise ValueError(kind)
+    sdf = np.maximum(sdf, box_sdf_grid(res))  # bbox constraint, python/variables.py:185-187
+    return sdf.astype(np.float32)
+
+
+def make_scene(kind='sphere', res=32, width=32, height=32, n_sensors=6, sensor_idx=0, dtype=torch.float64,
+               albedo_grid_res=None):
+    origins = regular_camera_origins(n_sensors)
+    tw = look_at(origins[sensor_idx], [0.5, 0.5, 0.5], [0, 1, 0])
+    sensor = Sensor(to_world=tw, width=width, height=height)
+    sdf = Grid3d(torch.from_numpy(make_sdf(kind, res)).to(dtype))
+    alb = None
+    if albedo_grid_res is not None:
+        rng = np.random.default_rng(1)
+        alb = torch.from_numpy(rng.uniform(0.2, 0.8, size=(albedo_grid_res,) * 3 + (3,)).astype(np.float32)).to(dtype)
+    return Scene(sdf=sdf, sensor=sensor, albedo_grid=alb)

@@ -1,0 +1,140 @@
+"""ctypes binding of tests/host_harness (the per-lane kernel math compiled for the host).
+
+Test infrastructure only: lets `-m "not gpu"` tests compare the CUDA path's arithmetic with the
+oracle on a machine without a GPU.  The product (libsdfrt.so) never uses it.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, 'host_harness', 'harness.cpp')
+LIB = os.path.join(HERE, 'host_harness', 'libsdfrt_hostmath.so')
+
+
+class TracerParams(C.Structure):
+    _fields_ = [('step_scale', C.c_float), ('trace_eps', C.c_float), ('refine_intersection', C.c_int32),
+                ('use_extra_weight', C.c_int32), ('extra_thresh', C.c_float), ('sil_weight_offset', C.c_float),
+                ('sil_weight_epsilon', C.c_float), ('weight_power', C.c_int32), ('use_weight_sum_weight', C.c_int32),
+                ('max_steps', C.c_int32)]
+
+
+class WarpParams(C.Structure):
+    _fields_ = [('kind', C.c_int32), ('edge_eps', C.c_float), ('weight_strategy', C.c_int32),
+                ('clamping_thresh', C.c_float), ('normalize_warp_field', C.c_int32), ('max_reparam_depth', C.c_int32)]
+
+
+class SensorParams(C.Structure):
+    _fields_ = [('to_world', C.c_float * 16), ('fov_x_deg', C.c_float), ('near_clip', C.c_float), ('far_clip', C.c_float),
+                ('width', C.c_int32), ('height', C.c_int32), ('filter_radius', C.c_float), ('filter_stddev', C.c_float),
+                ('sample_border', C.c_int32)]
+
+
+class ShadingParams(C.Structure):
+    _fields_ = [('env_radiance', C.c_float * 3), ('env_dist', C.c_float), ('albedo', C.c_float * 3),
+                ('hide_emitters', C.c_int32)]
+
+
+class HHScene(C.Structure):
+    _fields_ = [('sdf', C.c_void_p), ('rx', C.c_int), ('ry', C.c_int), ('rz', C.c_int), ('p', C.c_float * 3),
+                ('albedo', C.c_void_p), ('ax', C.c_int), ('ay', C.c_int), ('az', C.c_int),
+                ('tracer', TracerParams), ('warp', WarpParams), ('sensor', SensorParams), ('shading', ShadingParams),
+                ('integrator', C.c_int)]
+
+
+def build():
+    srcs = [SRC] + [os.path.join(HERE, '..', 'differentiable-sdf-rendering_b200', 'csrc', f)
+                    for f in ('sdfrt_core.cuh', 'sdfrt_lane.cuh', 'sdfrt_params.h')]
+    if os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(s) for s in srcs):
+        return LIB
+    subprocess.check_call(['g++', '-O2', '-std=c++17', '-fPIC', '-shared', '-x', 'c++', SRC, '-o', LIB])
+    return LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+    return _lib
+
+
+def fptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class HostScene:
+    """Owns the numpy buffers referenced by an HHScene."""
+
+    def __init__(self, sdf, sensor_to_world, width, height, integrator=2, albedo_grid=None, p=(0, 0, 0)):
+        self.h = HHScene()
+        lib().hh_defaults(C.byref(self.h))
+        self.sdf = np.ascontiguousarray(sdf, dtype=np.float32)
+        rz, ry, rx = self.sdf.shape
+        self.h.sdf = self.sdf.ctypes.data
+        self.h.rx, self.h.ry, self.h.rz = rx, ry, rz
+        self.h.p[:] = list(p)
+        self.albedo = None
+        if albedo_grid is not None:
+            self.albedo = np.ascontiguousarray(albedo_grid, dtype=np.float32)
+            self.h.albedo = self.albedo.ctypes.data
+            self.h.az, self.h.ay, self.h.ax = self.albedo.shape[:3]
+        tw = np.asarray(sensor_to_world, dtype=np.float32).reshape(-1)
+        self.h.sensor.to_world[:] = list(tw)
+        self.h.sensor.width, self.h.sensor.height = width, height
+        self.h.integrator = integrator
+        self.border = 2
+
+    @property
+    def film_shape(self):
+        b = self.border if self.h.sensor.sample_border else 0
+        return (self.h.sensor.height + 2 * b, self.h.sensor.width + 2 * b, 4)
+
+    def wavefront(self, spp):
+        fs = self.film_shape
+        return fs[0] * fs[1] * spp
+
+    def eval_sdf(self, x, order):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        n = x.shape[0]
+        out = np.zeros((n, {0: 1, 1: 4, 2: 10}[order]), dtype=np.float32)
+        lib().hh_eval_sdf(C.byref(self.h), fptr(x), n, order, fptr(out))
+        return out
+
+    def trace(self, o, d, maxt=None, differentiable=True):
+        o = np.ascontiguousarray(o, dtype=np.float32)
+        d = np.ascontiguousarray(d, dtype=np.float32)
+        n = o.shape[0]
+        its_t = np.zeros(n, np.float32); warp_t = np.zeros(n, np.float32); ww = np.zeros(n, np.float32)
+        wtd = np.zeros((n, 3), np.float32); wwd = np.zeros((n, 3), np.float32); ns = np.zeros(n, np.int32)
+        mt = None if maxt is None else np.ascontiguousarray(maxt, dtype=np.float32)
+        lib().hh_trace(C.byref(self.h), fptr(o), fptr(d), None if mt is None else fptr(mt), n, int(differentiable),
+                       fptr(its_t), fptr(warp_t), fptr(wtd), fptr(ww), fptr(wwd), fptr(ns))
+        return dict(its_t=its_t, warp_t=warp_t, warp_t_d=wtd, warp_weight=ww, warp_weight_d=wwd, n_steps=ns)
+
+    def forward(self, seed, spp, diff):
+        film = np.zeros(self.film_shape, np.float32)
+        n = self.wavefront(spp)
+        rec = np.zeros((lib().hh_rec_count(), n), np.float32) if diff else np.zeros((1, 1), np.float32)
+        stats = np.zeros(8, np.uint64)
+        lib().hh_forward(C.byref(self.h), C.c_uint(seed), spp, int(diff), fptr(film), fptr(rec), fptr(stats))
+        return film, rec, stats
+
+    def develop(self, film):
+        img = np.zeros((self.h.sensor.height, self.h.sensor.width, 3), np.float32)
+        lib().hh_develop(C.byref(self.h), fptr(film), fptr(img))
+        return img
+
+    def backward(self, seed, spp, film, rec, grad_image):
+        grad_image = np.ascontiguousarray(grad_image, dtype=np.float32)
+        g = np.zeros_like(self.sdf)
+        ga = None if self.albedo is None else np.zeros_like(self.albedo)
+        gp = np.zeros(3, np.float32)
+        stats = np.zeros(8, np.uint64)
+        lib().hh_backward(C.byref(self.h), C.c_uint(seed), spp, fptr(film), fptr(rec), fptr(grad_image), fptr(g),
+                          None if ga is None else fptr(ga), fptr(gp), fptr(stats))
+        return g, ga, gp, stats
