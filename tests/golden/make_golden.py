@@ -1,0 +1,58 @@
+"""Generates the golden fixtures in this directory with the CPU oracle (fp64).
+
+The reference ships no golden data and cannot be imported offline (PARITY UNPINNED, see
+oracle/sdf_oracle.py), so these vectors pin *our restatement*: they detect drift of the oracle and
+give the GPU tests something to compare against that does not require running the oracle.
+Run:  python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from oracle import sdf_oracle as O  # noqa: E402
+
+CASES = {
+    # name: (sdf kind, R, W, spp, integrator, albedo_res)
+    'sphere_direct': ('sphere', 32, 24, 8, 'sdf_direct_reparam', None),
+    'knot_direct': ('knot', 32, 24, 8, 'sdf_direct_reparam', None),
+    'blobs_tex_direct': ('blobs', 32, 24, 8, 'sdf_direct_reparam', 8),
+    'knot_silhouette': ('knot', 32, 24, 8, 'sdf_silhouette_reparam', None),
+    'sphere_simple': ('sphere', 32, 24, 8, 'sdf_simple_shading_reparam', None),
+}
+SEED, SEED_GRAD = 3, 11
+
+
+def grad_image(W):
+    return np.random.default_rng(5).uniform(-1, 1, size=(W, W, 3))
+
+
+def run_case(name):
+    kind, R, W, spp, integ, ar = CASES[name]
+    sc = O.make_scene(kind, res=R, width=W, height=W, albedo_grid_res=ar)
+    wf = O.WarpField2D(sc.sdf, weight_strategy=6, edge_eps=0.01)
+    wf.clamping_thresh = 0.05
+    with torch.no_grad():
+        img = O.render(sc, wf, integ, seed=SEED, spp=spp)
+    img_adj, g, gp, ga = O.render_backward(sc, wf, integ, torch.from_numpy(grad_image(W)), seed=SEED_GRAD, spp=spp)
+    # per-ray tracer outputs for the first 256 lanes of the central film rows (fixed rays)
+    pos = torch.from_numpy(np.random.default_rng(9).uniform(0, W, size=(256, 2)))
+    o, d, maxt = sc.sensor.sample_ray(pos, torch.float64)
+    its_t, warp_t, warp_t_d, ww, wwd = sc.sdf.ray_intersect(o, d, maxt, torch.ones(256, dtype=torch.bool))
+    out = dict(image=img.numpy().astype(np.float32), image_adj=img_adj.numpy().astype(np.float32),
+               grad_sdf=g.numpy().astype(np.float32), grad_p=gp.numpy().astype(np.float32),
+               ray_o=o.numpy().astype(np.float32), ray_d=d.numpy().astype(np.float32), ray_maxt=maxt.numpy().astype(np.float32),
+               its_t=its_t.numpy().astype(np.float32), warp_t=warp_t.numpy().astype(np.float32),
+               warp_t_d=warp_t_d.numpy().astype(np.float32), warp_weight=ww.numpy().astype(np.float32))
+    if ga is not None:
+        out['grad_albedo'] = ga.numpy().astype(np.float32)
+    return out
+
+
+if __name__ == '__main__':
+    for name in CASES:
+        np.savez_compressed(os.path.join(HERE, name + '.npz'), **run_case(name))
+        print('wrote', name)

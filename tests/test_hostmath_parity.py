@@ -1,0 +1,140 @@
+"""The per-lane math of the CUDA kernels (csrc/sdfrt_core.cuh, sdfrt_lane.cuh) compiled for the host and
+compared with the oracle.  CPU only; the same comparisons run through the C ABI on the GPU in
+test_gpu_parity.py.  Tolerances: the kernels compute in fp32, the oracle in fp64."""
+import numpy as np
+import pytest
+import torch
+
+import hostmath as HM
+from oracle import sdf_oracle as O
+
+INTEG = {'sdf_silhouette_reparam': 0, 'sdf_simple_shading_reparam': 1, 'sdf_direct_reparam': 2}
+
+
+def make_pair(kind='sphere', R=32, W=24, integ='sdf_direct_reparam', albedo_res=None, warp=None, p=(0, 0, 0)):
+    sc = O.make_scene(kind, res=R, width=W, height=W, albedo_grid_res=albedo_res)
+    sc.sdf.p = torch.tensor(p, dtype=torch.float64)
+    hs = HM.HostScene(sc.sdf.data.numpy(), sc.sensor.to_world, W, W, integrator=INTEG[integ],
+                      albedo_grid=None if albedo_res is None else sc.albedo_grid.numpy(), p=p)
+    warp = dict(weight_strategy=6, edge_eps=0.01, clamping_thresh=0.05, normalize=True, max_depth=-1, kind=2) | (warp or {})
+    if warp['kind'] == 2:
+        wf = O.WarpField2D(sc.sdf, weight_strategy=warp['weight_strategy'], edge_eps=warp['edge_eps'])
+        wf.clamping_thresh = warp['clamping_thresh']
+        wf.normalize_warp_field = warp['normalize']
+        wf.max_reparam_depth = warp['max_depth']
+    elif warp['kind'] == 1:
+        wf = O.DummyWarpField(sc.sdf)
+    else:
+        wf = None
+    hs.h.warp.kind = warp['kind']
+    hs.h.warp.edge_eps = wf.edge_eps if warp['kind'] == 2 else 0.0
+    hs.h.warp.weight_strategy = warp['weight_strategy']
+    hs.h.warp.clamping_thresh = warp['clamping_thresh']
+    hs.h.warp.normalize_warp_field = int(warp['normalize'])
+    hs.h.warp.max_reparam_depth = warp['max_depth']
+    return sc, wf, hs
+
+
+def test_eval_value_grad_hessian():
+    sc, _, hs = make_pair('blobs')
+    x = np.random.default_rng(0).uniform(-0.1, 1.1, size=(2000, 3))
+    v, g, H = sc.sdf._taps(torch.from_numpy(x), 2)
+    out = hs.eval_sdf(x, 2)
+    hs_scale = H.abs().max().item()
+    assert np.abs(out[:, 0] - v.numpy()).max() < 2e-6
+    assert np.abs(out[:, 1:4] - g.numpy()).max() < 2e-5
+    Hh = np.stack([out[:, 4], out[:, 7], out[:, 8], out[:, 7], out[:, 5], out[:, 9], out[:, 8], out[:, 9], out[:, 6]], -1).reshape(-1, 3, 3)
+    assert np.abs(Hh - H.numpy()).max() < 1e-5 * max(1.0, hs_scale)
+    assert np.abs(hs.eval_sdf(x, 0)[:, 0] - v.numpy()).max() < 2e-6
+    assert np.abs(hs.eval_sdf(x, 1)[:, 1:4] - g.numpy()).max() < 2e-5
+
+
+def _camera_rays(sc, n, seed):
+    rng = np.random.default_rng(seed)
+    pos = torch.from_numpy(rng.uniform(-2, sc.sensor.width + 2, size=(n, 2)))
+    return sc.sensor.sample_ray(pos, torch.float64)
+
+
+@pytest.mark.parametrize('kind', ['sphere', 'knot'])
+def test_tracer_outputs_per_ray(kind):
+    sc, _, hs = make_pair(kind)
+    o, d, maxt = _camera_rays(sc, 600, 1)
+    act = torch.ones(600, dtype=torch.bool)
+    its_t, warp_t, warp_t_d, ww, wwd = sc.sdf.ray_intersect(o, d, maxt, act)
+    h = hs.trace(o.numpy(), d.numpy(), maxt.numpy(), differentiable=True)
+    fin = torch.isfinite(its_t).numpy()
+    assert (np.isfinite(h['its_t']) == fin).mean() > 0.995          # borderline rays may flip in fp32
+    both = fin & np.isfinite(h['its_t'])
+    assert np.abs(h['its_t'][both] - its_t.numpy()[both]).max() < 5e-5
+    wfin = torch.isfinite(warp_t).numpy() & np.isfinite(h['warp_t'])
+    assert (np.isfinite(h['warp_t']) == torch.isfinite(warp_t).numpy()).mean() > 0.99
+    # warp_t etc. are ratios of sums of 1/denom^3 weights: compare where well conditioned, relative to scale
+    rel = np.abs(h['warp_t'][wfin] - warp_t.numpy()[wfin]) / np.maximum(1.0, np.abs(warp_t.numpy()[wfin]))
+    assert np.quantile(rel, 0.99) < 1e-3
+    dsc = np.maximum(1.0, np.abs(warp_t_d.numpy()[wfin]).max(-1))
+    reld = np.abs(h['warp_t_d'][wfin] - warp_t_d.numpy()[wfin]).max(-1) / dsc
+    assert np.quantile(reld, 0.98) < 2e-2
+    assert np.quantile(np.abs(h['warp_weight'][wfin] - ww.numpy()[wfin]), 0.99) < 1e-3
+    # value-only tracer agrees with the differentiable one on its_t
+    h0 = hs.trace(o.numpy(), d.numpy(), maxt.numpy(), differentiable=False)
+    assert np.abs(h0['its_t'][both] - h['its_t'][both]).max() < 2e-5
+
+
+CASES = [
+    ('sphere', 'sdf_silhouette_reparam', None, None),
+    ('sphere', 'sdf_simple_shading_reparam', None, None),
+    ('sphere', 'sdf_direct_reparam', None, None),
+    ('knot', 'sdf_direct_reparam', None, None),
+    ('blobs', 'sdf_direct_reparam', 8, None),                                   # reflectance grid
+    ('knot', 'sdf_direct_reparam', None, dict(max_depth=0)),                     # configs.WarpPrimary
+    ('knot', 'sdf_direct_reparam', None, dict(normalize=False)),                 # configs.WarpNotNormalized
+    ('sphere', 'sdf_direct_reparam', None, dict(kind=1)),                        # DummyWarpField: shading gradients only
+    ('knot', 'sdf_silhouette_reparam', None, dict(weight_strategy=4, edge_eps=0.05, clamping_thresh=0.0)),  # WarpField2D ctor defaults
+]
+
+
+@pytest.mark.parametrize('kind,integ,albedo_res,warp', CASES)
+def test_image_and_gradient_parity(kind, integ, albedo_res, warp):
+    W, spp = 24, 8
+    sc, wf, hs = make_pair(kind, 32, W, integ, albedo_res, warp)
+    with torch.no_grad():
+        img_o = O.render(sc, wf, integ, seed=3, spp=spp).numpy()
+    film, _, _ = hs.forward(3, spp, False)
+    assert np.abs(hs.develop(film) - img_o).max() < 2e-5
+    g_in = np.random.default_rng(5).uniform(-1, 1, size=(W, W, 3))
+    img2, g_o, gp_o, ga_o = O.render_backward(sc, wf, integ, torch.from_numpy(g_in), seed=11, spp=spp)
+    film, rec, _ = hs.forward(11, spp, True)
+    assert np.abs(hs.develop(film) - img2.numpy()).max() < 2e-5
+    g_h, ga_h, gp_h, st = hs.backward(11, spp, film, rec, g_in)
+    g_o = g_o.numpy()
+    scale = np.abs(g_o).max()
+    assert scale > 0
+    # fp32 kernels vs fp64 oracle.  With clamping_thresh=0 the 1/warp_t factor makes single rays ill-conditioned
+    # (the fp32 oracle itself is then 8e-3 away from the fp64 one), hence the looser bound for that case.
+    assert np.abs(g_h - g_o).max() < 2e-2 * scale
+    assert np.linalg.norm(g_h - g_o) < 5e-3 * np.linalg.norm(g_o)
+    cos = (g_h * g_o).sum() / np.linalg.norm(g_h) / np.linalg.norm(g_o)
+    assert cos > 0.9999
+    assert np.abs(gp_h - gp_o.numpy()).max() < 1e-2 * max(1.0, np.abs(gp_o.numpy()).max())
+    if albedo_res is not None:
+        ga_o = ga_o.numpy()
+        assert np.abs(ga_h - ga_o).max() < 1e-3 * np.abs(ga_o).max()
+
+
+def test_translated_sdf_p():
+    sc, wf, hs = make_pair('sphere', 32, 16, 'sdf_direct_reparam', p=(0.03, -0.02, 0.01))
+    with torch.no_grad():
+        img_o = O.render(sc, wf, 'sdf_direct_reparam', seed=3, spp=4).numpy()
+    film, _, _ = hs.forward(3, 4, False)
+    assert np.abs(hs.develop(film) - img_o).max() < 2e-5
+
+
+def test_adjoint_is_linear_in_grad_image():
+    _, _, hs = make_pair('knot', 32, 16, 'sdf_direct_reparam')
+    film, rec, _ = hs.forward(5, 4, True)
+    rng = np.random.default_rng(0)
+    a, b = rng.normal(size=(16, 16, 3)), rng.normal(size=(16, 16, 3))
+    ga = hs.backward(5, 4, film, rec, a)[0]
+    gb = hs.backward(5, 4, film, rec, b)[0]
+    gab = hs.backward(5, 4, film, rec, 2 * a - 3 * b)[0]
+    assert np.abs(gab - (2 * ga - 3 * gb)).max() < 1e-4 * max(np.abs(ga).max(), np.abs(gb).max())
