@@ -347,136 +347,141 @@ struct TraceOut {
     int n_steps;
 };
 
-// refine loop, python/shapes.py:245-257 / :323-334
-SDFRT_HD float refine_hit(const GridView& G, const TracerParams& P, V3 o, V3 d, float its_t, float trace_eps, int& n_evals) {
-    if (!P.refine_intersection || !isfinite(its_t)) return its_t;
-    for (int i = 0; i < 10; ++i) {
-        const float md = eval_value(G, o + its_t * d);
-        ++n_evals;
-        its_t += md * (10.f / (10.f + (float)i));
-        if (!((md <= 0.f) | (md > trace_eps))) break;
-    }
-    return its_t;
+// ------------------------------------------------------------------------------------
+// The tracers as resumable state machines: one ray *segment* (primary or shadow ray) is
+//   segment_begin -> {value_step | diff_step}* -> refine_step* -> diff_finalize
+// with exactly one SDF evaluation between two steps.  trace_non_diff / trace_diff below run a segment
+// to completion (per-lane form used by the test hooks and the host harness); the persistent wavefront
+// kernel (sdfrt_march.cuh) interleaves the steps of 32 segments per warp and refills finished slots.
+// ------------------------------------------------------------------------------------
+struct Segment {
+    V3 o, d;       // d normalised (python/shapes.py:124)
+    float t, maxt, trace_eps, its_t;
+    int i;         // march step counter, then refine iteration counter
+    bool intersects, inside;
+};
+
+// python/shapes.py:124-141.  Returns whether the march is active.
+SDFRT_HD bool segment_begin(Segment& s, const TracerParams& P, V3 o, V3 d, float ray_maxt) {
+    s.o = o;
+    s.d = normalize(d);
+    const BoxHit b = ray_box(o, s.d);
+    s.maxt = fminf(b.maxt, ray_maxt);
+    s.trace_eps = P.trace_eps * fmaxf(s.maxt, 1.f);
+    s.its_t = INFINITY;
+    s.t = b.inside ? 0.f : b.mint + 1e-5f;
+    s.i = 0;
+    s.intersects = b.intersects;
+    s.inside = b.inside;
+    return b.intersects;
 }
 
-// SDFBase.ray_intersect_non_diff, python/shapes.py:290-339
-SDFRT_HD float trace_non_diff(const GridView& G, const TracerParams& P, V3 o, V3 d, float ray_maxt, bool do_refine,
-                              int& n_steps, int& n_evals) {
-    d = normalize(d);
-    const BoxHit b = ray_box(o, d);
-    const float maxt = fminf(b.maxt, ray_maxt);
-    const float trace_eps = P.trace_eps * fmaxf(maxt, 1.f);
-    float its_t = INFINITY;
-    float t = b.inside ? 0.f : b.mint + 1e-5f;
-    bool active = b.intersects;
-    int i = 0;
-    while (active && i < P.max_steps) {
-        float v = eval_value(G, o + t * d);
-        if (P.step_scale != 1.f) v *= P.step_scale;
-        const bool hit = v < trace_eps;
-        if (hit) its_t = t;
-        active = (t <= maxt) & !hit;
-        t += hit ? 0.f : fabsf(v);
-        active = active & (t <= maxt);
-        ++i;
-    }
-    n_steps = i;
-    n_evals += i;
-    if (do_refine) its_t = refine_hit(G, P, o, d, its_t, trace_eps, n_evals);
-    return its_t;
+// one iteration of SDFBase.ray_intersect_non_diff's loop (python/shapes.py:309-320); v = sdf(o + t d)
+SDFRT_HD bool value_step(Segment& s, const TracerParams& P, float v) {
+    if (P.step_scale != 1.f) v *= P.step_scale;
+    const bool hit = v < s.trace_eps;
+    if (hit) s.its_t = s.t;
+    bool active = (s.t <= s.maxt) & !hit;
+    s.t += hit ? 0.f : fabsf(v);
+    active = active & (s.t <= s.maxt);
+    ++s.i;
+    return active & (s.i < P.max_steps);
 }
 
-// SDFBase.ray_intersect (differentiable tracer), python/shapes.py:115-288
-SDFRT_HD void trace_diff(const GridView& G, const TracerParams& P, V3 o, V3 d, float ray_maxt, bool do_refine, TraceOut& out,
-                         int& n_evals_hess, int& n_evals_value) {
-    d = normalize(d);
-    const BoxHit b = ray_box(o, d);
-    const float maxt = fminf(b.maxt, ray_maxt);
-    const float trace_eps = P.trace_eps * fmaxf(maxt, 1.f);
-    float its_t = INFINITY;
-    float t = b.inside ? 0.f : b.mint + 1e-5f;
-    float warp_t = 0.f, prev_surf_dist = 0.f, weight_sum = 0.f, extra_weight_sum = 0.f;
-    V3 prev_sdf_grad_c = v3(0.f), mixed_sum_d = v3(0.f), weight_d_sum = v3(0.f), extra_weight_sum_d = v3(0.f);
-    // entry face of the bounding box and initial dt/dx (python/shapes.py:155-164)
-    V3 t_d = v3(0.f);
-    {
-        const float lo = -kBBoxDelta, hi = 1.f + kBBoxDelta;
-        const V3 q = o + t * d;
-        const V3 md = V3{fminf(fabsf(lo - q.x), fabsf(hi - q.x)), fminf(fabsf(lo - q.y), fabsf(hi - q.y)),
-                         fminf(fabsf(lo - q.z), fabsf(hi - q.z))};
-        V3 n = v3(0.f);
-        if ((md.x < md.y) & (md.x < md.z)) n = v3(1, 0, 0);
-        if ((md.y < md.z) & (md.y < md.x)) n = v3(0, 1, 0);
-        if ((md.z < md.x) & (md.z < md.y)) n = v3(0, 0, 1);
-        const float d_dot_n = dot(d, n);
-        if (!b.inside && fabsf(d_dot_n) > 0.f) t_d = (-1.f / d_dot_n * t) * n;
+// refine loop body, python/shapes.py:245-257 / :323-334; md = sdf(o + its_t d); s.i counts iterations
+SDFRT_HD bool refine_step(Segment& s, float md) {
+    s.its_t += md * (10.f / (10.f + (float)s.i));
+    ++s.i;
+    return ((md <= 0.f) | (md > s.trace_eps)) & (s.i < 10);
+}
+
+struct DiffAcc {
+    float warp_t, prev_surf_dist, weight_sum, extra_weight_sum;
+    V3 prev_sdf_grad_c, mixed_sum_d, weight_d_sum, extra_weight_sum_d, t_d;
+};
+
+// entry face of the bounding box and initial dt/dx (python/shapes.py:142-164)
+SDFRT_HD void diff_begin(DiffAcc& a, const Segment& s) {
+    a.warp_t = 0.f; a.prev_surf_dist = 0.f; a.weight_sum = 0.f; a.extra_weight_sum = 0.f;
+    a.prev_sdf_grad_c = v3(0.f); a.mixed_sum_d = v3(0.f); a.weight_d_sum = v3(0.f); a.extra_weight_sum_d = v3(0.f);
+    a.t_d = v3(0.f);
+    const float lo = -kBBoxDelta, hi = 1.f + kBBoxDelta;
+    const V3 q = s.o + s.t * s.d;
+    const V3 md = V3{fminf(fabsf(lo - q.x), fabsf(hi - q.x)), fminf(fabsf(lo - q.y), fabsf(hi - q.y)),
+                     fminf(fabsf(lo - q.z), fabsf(hi - q.z))};
+    V3 n = v3(0.f);
+    if ((md.x < md.y) & (md.x < md.z)) n = v3(1, 0, 0);
+    if ((md.y < md.z) & (md.y < md.x)) n = v3(0, 1, 0);
+    if ((md.z < md.x) & (md.z < md.y)) n = v3(0, 0, 1);
+    const float d_dot_n = dot(s.d, n);
+    if (!s.inside && fabsf(d_dot_n) > 0.f) a.t_d = (-1.f / d_dot_n * s.t) * n;
+}
+
+// one iteration of SDFBase.ray_intersect's loop (python/shapes.py:170-238); (sdf_value, g, H) at o + t d
+SDFRT_HD bool diff_step(Segment& s, DiffAcc& a, const TracerParams& P, float sdf_value, V3 g, S3 H) {
+    const V3 d = s.d;
+    const float t = s.t;
+    const V3 x = s.o + t * d;
+    if (P.step_scale != 1.f) {
+        const float sc = P.step_scale;
+        sdf_value *= sc; g = g * sc;
+        H.xx *= sc; H.yy *= sc; H.zz *= sc; H.xy *= sc; H.xz *= sc; H.yz *= sc;
     }
-    bool active = b.intersects;
-    int i = 0;
-    while (active && i < P.max_steps) {
-        const V3 x = o + t * d;
-        float sdf_value; V3 g; S3 H;
-        eval_sdf<2>(G, x, sdf_value, g, H);
-        if (P.step_scale != 1.f) {
-            const float s = P.step_scale;
-            sdf_value *= s; g = g * s;
-            H.xx *= s; H.yy *= s; H.zz *= s; H.xy *= s; H.xz *= s; H.yz *= s;
-        }
-        const bool hit = sdf_value < trace_eps;
-        if (hit) its_t = t;
-        const float surf_dist = fabsf(sdf_value);
-        V3 weight_d;
-        float weight = eval_trace_weight(P, d, i, x, sdf_value, g, H, weight_d);
-        float inv_extra_w_den = 0.f, dist_difference = 0.f;
-        if (P.use_extra_weight) {
-            inv_extra_w_den = 1.f / fminf(P.extra_thresh, surf_dist);
-            dist_difference = prev_surf_dist - surf_dist;
-            extra_weight_sum += (dist_difference >= 0.f) ? dist_difference * inv_extra_w_den : 0.f;
-            extra_weight_sum = fminf(extra_weight_sum, 1.f);
-        }
-        const float curr_segment_value = hit ? 0.f : surf_dist;
-        const float segment_length = 0.5f * (curr_segment_value + prev_surf_dist);
-        float weight_increment = segment_length * weight;
-        if (P.use_extra_weight) weight_increment *= extra_weight_sum;
-        weight_sum += weight_increment;
-        warp_t += weight_increment * t;
-        // convert_deriv(in_d, t, t_d) = t * in_d + dot(d, in_d) * t_d   (python/shapes.py:126-127)
-        weight_d = t * weight_d + dot(d, weight_d) * t_d;
-        const V3 sdf_grad_c = t * g + dot(d, g) * t_d;
-        const V3 segment_d = 0.5f * (sdf_grad_c + prev_sdf_grad_c);
-        if (P.use_extra_weight) {
-            const V3 surf_dist_d = sign1(sdf_value) * sdf_grad_c;
-            V3 extra_w_d = (prev_sdf_grad_c - surf_dist_d) * inv_extra_w_den;
-            if (sdf_value < P.extra_thresh) extra_w_d = extra_w_d - (dist_difference * inv_extra_w_den * inv_extra_w_den) * surf_dist_d;
-            if (dist_difference > 0.f) extra_weight_sum_d += extra_w_d;
-            if ((extra_weight_sum >= 1.f) | (extra_weight_sum <= 0.f)) extra_weight_sum_d = v3(0.f);
-            weight_d = weight * extra_weight_sum_d + weight_d * extra_weight_sum;
-            weight *= extra_weight_sum;
-        }
-        const V3 weight_increment_d = weight * segment_d + weight_d * segment_length;
-        mixed_sum_d += weight_increment_d * t + (weight * segment_length) * t_d;
-        t_d += sdf_grad_c;
-        weight_d_sum += weight_increment_d;
-        ++i;
-        t += curr_segment_value;
-        prev_surf_dist = surf_dist;
-        prev_sdf_grad_c = sdf_grad_c;
-        active = (t <= maxt) & !hit;
+    const bool hit = sdf_value < s.trace_eps;
+    if (hit) s.its_t = t;
+    const float surf_dist = fabsf(sdf_value);
+    V3 weight_d;
+    float weight = eval_trace_weight(P, d, s.i, x, sdf_value, g, H, weight_d);
+    float inv_extra_w_den = 0.f, dist_difference = 0.f;
+    if (P.use_extra_weight) {
+        inv_extra_w_den = 1.f / fminf(P.extra_thresh, surf_dist);
+        dist_difference = a.prev_surf_dist - surf_dist;
+        a.extra_weight_sum += (dist_difference >= 0.f) ? dist_difference * inv_extra_w_den : 0.f;
+        a.extra_weight_sum = fminf(a.extra_weight_sum, 1.f);
     }
-    n_evals_hess += i;
-    out.n_steps = i;
-    if (do_refine) its_t = refine_hit(G, P, o, d, its_t, trace_eps, n_evals_value);
-    out.its_t = its_t;
-    const float inv_weight_sum = 1.f / weight_sum;
-    warp_t = warp_t * inv_weight_sum;
-    V3 warp_t_d = (-warp_t * weight_d_sum + mixed_sum_d) * inv_weight_sum;
+    const float curr_segment_value = hit ? 0.f : surf_dist;
+    const float segment_length = 0.5f * (curr_segment_value + a.prev_surf_dist);
+    float weight_increment = segment_length * weight;
+    if (P.use_extra_weight) weight_increment *= a.extra_weight_sum;
+    a.weight_sum += weight_increment;
+    a.warp_t += weight_increment * t;
+    // convert_deriv(in_d, t, t_d) = t * in_d + dot(d, in_d) * t_d   (python/shapes.py:126-127)
+    weight_d = t * weight_d + dot(d, weight_d) * a.t_d;
+    const V3 sdf_grad_c = t * g + dot(d, g) * a.t_d;
+    const V3 segment_d = 0.5f * (sdf_grad_c + a.prev_sdf_grad_c);
+    if (P.use_extra_weight) {
+        const V3 surf_dist_d = sign1(sdf_value) * sdf_grad_c;
+        V3 extra_w_d = (a.prev_sdf_grad_c - surf_dist_d) * inv_extra_w_den;
+        if (sdf_value < P.extra_thresh) extra_w_d = extra_w_d - (dist_difference * inv_extra_w_den * inv_extra_w_den) * surf_dist_d;
+        if (dist_difference > 0.f) a.extra_weight_sum_d += extra_w_d;
+        if ((a.extra_weight_sum >= 1.f) | (a.extra_weight_sum <= 0.f)) a.extra_weight_sum_d = v3(0.f);
+        weight_d = weight * a.extra_weight_sum_d + weight_d * a.extra_weight_sum;
+        weight *= a.extra_weight_sum;
+    }
+    const V3 weight_increment_d = weight * segment_d + weight_d * segment_length;
+    a.mixed_sum_d += weight_increment_d * t + (weight * segment_length) * a.t_d;
+    a.t_d += sdf_grad_c;
+    a.weight_d_sum += weight_increment_d;
+    ++s.i;
+    s.t = t + curr_segment_value;
+    a.prev_surf_dist = surf_dist;
+    a.prev_sdf_grad_c = sdf_grad_c;
+    return (s.t <= s.maxt) & !hit & (s.i < P.max_steps);
+}
+
+// python/shapes.py:259-283 (its_t is taken from the segment after the refine loop)
+SDFRT_HD void diff_finalize(const Segment& s, const DiffAcc& a, const TracerParams& P, TraceOut& out) {
+    out.its_t = s.its_t;
+    const float inv_weight_sum = 1.f / a.weight_sum;
+    float warp_t = a.warp_t * inv_weight_sum;
+    V3 warp_t_d = (-warp_t * a.weight_d_sum + a.mixed_sum_d) * inv_weight_sum;
     float warp_weight = 1.f;
     V3 warp_weight_d = v3(0.f);
     if (P.use_weight_sum_weight) {
-        warp_weight = fminf(fmaxf(weight_sum, 0.f), 1.f);
-        warp_weight_d = ((weight_sum > 0.f) & (weight_sum < 1.f)) ? weight_d_sum : v3(0.f);
+        warp_weight = fminf(fmaxf(a.weight_sum, 0.f), 1.f);
+        warp_weight_d = ((a.weight_sum > 0.f) & (a.weight_sum < 1.f)) ? a.weight_d_sum : v3(0.f);
     }
-    const bool invalid = (weight_sum < 1e-7f) | !b.intersects | !isfinite(warp_t);
+    const bool invalid = (a.weight_sum < 1e-7f) | !s.intersects | !isfinite(warp_t);
     if (invalid) {
         warp_t = INFINITY;
         warp_t_d = v3(0.f);
@@ -484,6 +489,46 @@ SDFRT_HD void trace_diff(const GridView& G, const TracerParams& P, V3 o, V3 d, f
         warp_weight_d = v3(0.f);
     }
     out.warp_t = warp_t; out.warp_t_d = warp_t_d; out.warp_weight = warp_weight; out.warp_weight_d = warp_weight_d;
+}
+
+// SDFBase.ray_intersect_non_diff, python/shapes.py:290-339
+SDFRT_HD float trace_non_diff(const GridView& G, const TracerParams& P, V3 o, V3 d, float ray_maxt, bool do_refine,
+                              int& n_steps, int& n_evals) {
+    Segment s;
+    bool active = segment_begin(s, P, o, d, ray_maxt);
+    while (active) active = value_step(s, P, eval_value(G, s.o + s.t * s.d));
+    n_steps = s.i;
+    n_evals += s.i;
+    if (do_refine && P.refine_intersection && isfinite(s.its_t)) {
+        s.i = 0;
+        bool refining = true;
+        while (refining) refining = refine_step(s, eval_value(G, s.o + s.its_t * s.d));
+        n_evals += s.i;
+    }
+    return s.its_t;
+}
+
+// SDFBase.ray_intersect (differentiable tracer), python/shapes.py:115-288
+SDFRT_HD void trace_diff(const GridView& G, const TracerParams& P, V3 o, V3 d, float ray_maxt, bool do_refine, TraceOut& out,
+                         int& n_evals_hess, int& n_evals_value) {
+    Segment s;
+    DiffAcc a;
+    bool active = segment_begin(s, P, o, d, ray_maxt);
+    diff_begin(a, s);
+    while (active) {
+        float v; V3 g; S3 H;
+        eval_sdf<2>(G, s.o + s.t * s.d, v, g, H);
+        active = diff_step(s, a, P, v, g, H);
+    }
+    n_evals_hess += s.i;
+    out.n_steps = s.i;
+    if (do_refine && P.refine_intersection && isfinite(s.its_t)) {
+        s.i = 0;
+        bool refining = true;
+        while (refining) refining = refine_step(s, eval_value(G, s.o + s.its_t * s.d));
+        n_evals_value += s.i;
+    }
+    diff_finalize(s, a, P, out);
 }
 
 // ------------------------------------------------------------------------------------

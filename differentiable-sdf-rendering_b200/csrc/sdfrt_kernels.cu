@@ -1,8 +1,8 @@
 // sdfrt_kernels.cu -- CUDA kernels (sm_100a) and the C ABI of libsdfrt.so (include/sdfrt.h).
 //
 // Kernels
-//   k_forward<DIFF>   one wavefront lane per thread: camera sample -> sphere trace through the
-//                     tricubic SDF grid -> shading -> gaussian film splat.  DIFF=true runs the
+//   k_march<DIFF>     (sdfrt_march.cuh) persistent-threads wavefront marcher: camera sample -> sphere trace
+//                     through the tricubic SDF grid -> shading -> gaussian film splat.  DIFF=true runs the
 //                     differentiable tracer (python/shapes.py:115-288) and stores its outputs per lane.
 //   k_film_adjoint    per film pixel: (dL/dV, dL/dWt) of I = V / Wt (HDRFilm::develop).
 //   k_backward        one lane per thread: closed-form adjoint + 64-tap atomic scatter into dL/d(sdf).
@@ -16,6 +16,7 @@
 #include <string>
 
 #include "sdfrt_params.h"
+#include "sdfrt_march.cuh"
 
 using namespace sdfrt;
 
@@ -56,17 +57,6 @@ __device__ __forceinline__ void flush_stats(const LaneStats& st, unsigned n_rays
         if (hi) atomicAdd(&c->n_hits, (unsigned long long)hi);
         atomicMax(&c->n_steps_max, (unsigned long long)m);
     }
-}
-
-template <bool DIFF>
-__global__ void __launch_bounds__(kBlock) k_forward(const __grid_constant__ SceneParams sc, const __grid_constant__ PassParams ps,
-                                                     float* __restrict__ film, float* __restrict__ rec,
-                                                     unsigned long long rec_stride, Counters* counters) {
-    const unsigned long long lane = ps.lane_begin + (unsigned long long)blockIdx.x * kBlock + threadIdx.x;
-    LaneStats st = {0, 0, 0, 0, 0, 0, 0};
-    const bool live = lane < ps.lane_end;
-    if (live) lane_forward<DIFF>(sc, ps, lane, film, rec, rec_stride, st);
-    flush_stats(st, live ? 1u : 0u, counters);
 }
 
 __global__ void __launch_bounds__(kBlock) k_backward(const __grid_constant__ SceneParams sc, const __grid_constant__ PassParams ps,
@@ -191,6 +181,9 @@ struct sdfrt_ctx {
     float* film_adj = nullptr;
     size_t film_adj_capacity = 0;
     Counters* counters = nullptr;
+    WorkQueue* work = nullptr;
+    int num_sms = 0;
+    int march_blocks[2] = {0, 0};  // resident blocks per SM of k_march<false/true>
     // buffers of the host entry point
     float *h_sdf = nullptr, *h_film = nullptr, *h_image = nullptr, *h_gimg = nullptr, *h_grad = nullptr;
     size_t h_sdf_n = 0, h_film_n = 0, h_image_n = 0, h_grad_n = 0;
@@ -241,9 +234,15 @@ int launch_forward(sdfrt_ctx* ctx, const PassParams& ps, float* film, cudaStream
     SDFRT_CUDA(ctx, cudaMemsetAsync(film, 0, film_floats(ctx) * sizeof(float), st));
     const unsigned long long n = ps.lane_end - ps.lane_begin;
     if (n == 0) return SDFRT_OK;
-    const unsigned long long blocks = (n + kBlock - 1) / kBlock;
-    if (blocks > 0x7fffffffull) return fail(ctx, SDFRT_ERR_INVALID, "too many lanes for one launch");
-    k_forward<DIFF><<<(unsigned)blocks, kBlock, 0, st>>>(ctx->sc, ps, film, ctx->rec, ctx->rec_stride, ctx->counters);
+    const SensorParams& S = ctx->sc.S;
+    if ((unsigned long long)kBandRows * (unsigned long long)(S.W + 2 * S.border) * (unsigned long long)ps.spp > 0xffffffffull)
+        return fail(ctx, SDFRT_ERR_INVALID, "film row band exceeds 2^32 samples");
+    SDFRT_CUDA(ctx, cudaMemsetAsync(ctx->work, 0, sizeof(WorkQueue), st));
+    // persistent grid: every SM filled with resident blocks, capped by the amount of work
+    unsigned long long blocks = (unsigned long long)ctx->num_sms * (unsigned long long)ctx->march_blocks[DIFF ? 1 : 0];
+    const unsigned long long need = (n + kMarchBlock - 1) / kMarchBlock;
+    if (blocks > need) blocks = need;
+    k_march<DIFF><<<(unsigned)blocks, kMarchBlock, 0, st>>>(ctx->sc, ps, ctx->work, film, ctx->rec, ctx->rec_stride, ctx->counters);
     SDFRT_CUDA(ctx, cudaGetLastError());
     return SDFRT_OK;
 }
@@ -297,6 +296,15 @@ sdfrt_ctx* sdfrt_create(int device, int* status) {
         if (status) *status = SDFRT_ERR_CUDA;
         return nullptr;
     }
+    ctx->num_sms = prop.multiProcessorCount;
+    bool ok = cudaMalloc((void**)&ctx->work, sizeof(WorkQueue)) == cudaSuccess;
+    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->march_blocks[0], k_march<false>, kMarchBlock, 0) == cudaSuccess;
+    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->march_blocks[1], k_march<true>, kMarchBlock, 0) == cudaSuccess;
+    if (!ok || ctx->march_blocks[0] < 1 || ctx->march_blocks[1] < 1) {
+        sdfrt_destroy(ctx);
+        if (status) *status = SDFRT_ERR_CUDA;
+        return nullptr;
+    }
     if (status) *status = SDFRT_OK;
     return ctx;
 }
@@ -307,6 +315,7 @@ void sdfrt_destroy(sdfrt_ctx* ctx) {
     cudaFree(ctx->rec);
     cudaFree(ctx->film_adj);
     cudaFree(ctx->counters);
+    cudaFree(ctx->work);
     cudaFree(ctx->h_sdf); cudaFree(ctx->h_film); cudaFree(ctx->h_image); cudaFree(ctx->h_gimg); cudaFree(ctx->h_grad);
     delete ctx;
 }

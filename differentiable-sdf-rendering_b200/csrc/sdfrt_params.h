@@ -95,12 +95,12 @@ inline PassParams make_pass(const SensorParams& S, uint32_t seed, int spp, int r
     p.log2_spp = -1;
     for (int k = 0; k < 31; ++k)
         if ((1 << k) == spp) p.log2_spp = k;
-    const unsigned long long npix = (unsigned long long)(S.W + 2 * S.border) * (unsigned long long)(S.H + 2 * S.border);
-    // contiguous pixel ranges per rank (rows of the film first), spp lanes per pixel
-    const unsigned long long p0 = npix * (unsigned long long)rank / (unsigned long long)world;
-    const unsigned long long p1 = npix * (unsigned long long)(rank + 1) / (unsigned long long)world;
-    p.lane_begin = p0 * (unsigned long long)spp;
-    p.lane_end = p1 * (unsigned long long)spp;
+    // whole film rows per rank (contiguous lanes in the reference's scanline order)
+    const unsigned long long Wb = (unsigned long long)(S.W + 2 * S.border), Hb = (unsigned long long)(S.H + 2 * S.border);
+    const unsigned long long r0 = Hb * (unsigned long long)rank / (unsigned long long)world;
+    const unsigned long long r1 = Hb * (unsigned long long)(rank + 1) / (unsigned long long)world;
+    p.lane_begin = r0 * Wb * (unsigned long long)spp;
+    p.lane_end = r1 * Wb * (unsigned long long)spp;
     return p;
 }
 

@@ -1,0 +1,57 @@
+"""Multi-GPU data path: one process per GPU, the SDF grid replicated, the wavefront split by
+film rows (sdfrt_set_partition).  Exchange steps per view:
+  1. all-reduce(sum) of the primal film accumulator   (small: (H+2b)(W+2b)*4 floats)
+  2. all-reduce(sum) of the adjoint re-render's film  (the adjoint of I = V/Wt needs the global V, Wt)
+  3. all-reduce(sum) of dL/d(sdf.data) (+ reflectance grid) -- the one large collective per backward.
+The reference has no distributed path at all (single process, single device).
+`backend` is anything with the engine.Context rendering interface; the CPU tests inject a host stand-in
+under the gloo backend to exercise this logic without GPUs.
+"""
+import torch
+import torch.distributed as dist
+
+
+def _world(group):
+    if not (dist.is_available() and dist.is_initialized()):
+        return 0, 1
+    return dist.get_rank(group), dist.get_world_size(group)
+
+
+def render_view(backend, seed, spp, seed_grad, spp_grad, grad_image_fn, grad_sdf, grad_albedo=None, group=None,
+                async_grad_reduce=False):
+    """One optimisation-loop view (python/shape_opt.py:78-83) across the ranks of `group`.
+
+    grad_image_fn(image) -> dLoss/dImage, evaluated redundantly on every rank from the all-reduced image.
+    Gradients are ACCUMULATED into grad_sdf / grad_albedo (like dr.backward) and are complete (summed over
+    ranks) on return unless async_grad_reduce=True, in which case the pending work handles are returned.
+    """
+    rank, world = _world(group)
+    backend.set_partition(rank, world)
+    film = backend.render_primal(seed, spp)
+    if world > 1:
+        dist.all_reduce(film, group=group)
+    image = backend.develop(film)
+    grad_image = grad_image_fn(image)
+    film_a = backend.adjoint_accumulate(seed_grad, spp_grad)
+    if world > 1:
+        dist.all_reduce(film_a, group=group)
+    local = torch.zeros_like(grad_sdf)
+    local_alb = None if grad_albedo is None else torch.zeros_like(grad_albedo)
+    backend.adjoint_backprop(film_a, grad_image.contiguous(), local, local_alb)
+    handles = []
+    if world > 1:
+        handles.append(dist.all_reduce(local, group=group, async_op=True))
+        if local_alb is not None:
+            handles.append(dist.all_reduce(local_alb, group=group, async_op=True))
+
+    def finish():
+        for h in handles:
+            h.wait()
+        grad_sdf.add_(local)
+        if local_alb is not None:
+            grad_albedo.add_(local_alb)
+
+    if async_grad_reduce:
+        return image, finish
+    finish()
+    return image

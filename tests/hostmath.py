@@ -116,12 +116,16 @@ class HostScene:
                        fptr(its_t), fptr(warp_t), fptr(wtd), fptr(ww), fptr(wwd), fptr(ns))
         return dict(its_t=its_t, warp_t=warp_t, warp_t_d=wtd, warp_weight=ww, warp_weight_d=wwd, n_steps=ns)
 
-    def forward(self, seed, spp, diff):
+    def local_lanes(self, spp, rank=0, world=1):
+        lib().hh_local_lanes.restype = C.c_ulonglong
+        return int(lib().hh_local_lanes(C.byref(self.h), spp, rank, world))
+
+    def forward(self, seed, spp, diff, rank=0, world=1):
         film = np.zeros(self.film_shape, np.float32)
-        n = self.wavefront(spp)
-        rec = np.zeros((lib().hh_rec_count(), n), np.float32) if diff else np.zeros((1, 1), np.float32)
+        n = self.local_lanes(spp, rank, world)
+        rec = np.zeros((lib().hh_rec_count(), max(n, 1)), np.float32) if diff else np.zeros((1, 1), np.float32)
         stats = np.zeros(8, np.uint64)
-        lib().hh_forward(C.byref(self.h), C.c_uint(seed), spp, int(diff), fptr(film), fptr(rec), fptr(stats))
+        lib().hh_forward(C.byref(self.h), C.c_uint(seed), spp, int(diff), fptr(film), fptr(rec), fptr(stats), rank, world)
         return film, rec, stats
 
     def develop(self, film):
@@ -129,12 +133,12 @@ class HostScene:
         lib().hh_develop(C.byref(self.h), fptr(film), fptr(img))
         return img
 
-    def backward(self, seed, spp, film, rec, grad_image):
+    def backward(self, seed, spp, film, rec, grad_image, rank=0, world=1):
         grad_image = np.ascontiguousarray(grad_image, dtype=np.float32)
         g = np.zeros_like(self.sdf)
         ga = None if self.albedo is None else np.zeros_like(self.albedo)
         gp = np.zeros(3, np.float32)
         stats = np.zeros(8, np.uint64)
         lib().hh_backward(C.byref(self.h), C.c_uint(seed), spp, fptr(film), fptr(rec), fptr(grad_image), fptr(g),
-                          None if ga is None else fptr(ga), fptr(gp), fptr(stats))
+                          None if ga is None else fptr(ga), fptr(gp), fptr(stats), rank, world)
         return g, ga, gp, stats

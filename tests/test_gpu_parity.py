@@ -1,0 +1,222 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI (via the Python mirror of the reference
+interface), against the committed golden fixtures, the oracle on small seeded inputs, and size-independent
+properties at the BASELINE sizes.  Stated fp32 tolerances: images 2e-5 absolute; per-voxel gradients
+max-abs <= 2e-2 * ||g||_inf and relative L2 <= 5e-3 (see tests/test_golden.py for why)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def gold(name):
+    return dict(np.load(os.path.join(GOLD, name + '.npz')))
+
+
+@pytest.fixture(scope='module')
+def sdfrt_mod(built):
+    import sdfrt
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return sdfrt
+
+
+def build_scene(sdfrt, kind, R, W, integ, albedo_res=None, warp='default', H=None):
+    from oracle import sdf_oracle as O  # data + camera only; the renderer under test is the CUDA path
+    H = W if H is None else H
+    osc = O.make_scene(kind, res=R, width=W, height=H, albedo_grid_res=albedo_res)
+    sdf = sdfrt.Grid3d(osc.sdf.data.float().numpy(), device=0)
+    integrator = sdfrt.integrators.create(integ, sdf=sdf)
+    if warp == 'default':
+        wf = sdfrt.WarpField2D(sdf, weight_strategy=6, edge_eps=0.01)
+        wf.clamping_thresh = 0.05
+        integrator.warp_field = wf
+    elif warp == 'dummy':
+        integrator.warp_field = sdfrt.DummyWarpField(sdf)
+    alb = None if albedo_res is None else osc.albedo_grid.float().cuda().contiguous()
+    scene = sdfrt.Scene(integrator, [sdfrt.Sensor(osc.sensor.to_world, W, H)], albedo_grid=alb)
+    return scene, osc
+
+
+def test_library_is_the_cuda_build(sdfrt_mod):
+    ctx = sdfrt_mod.Context(0)
+    assert ctx.lib.sdfrt_version() == 100 and os.path.basename(sdfrt_mod._capi.LIB_PATH) == 'libsdfrt.so'
+
+
+@pytest.mark.parametrize('name', ['sphere_direct', 'knot_direct', 'blobs_tex_direct', 'knot_silhouette', 'sphere_simple'])
+def test_golden_image_gradient_and_rays(sdfrt_mod, name):
+    from golden import make_golden as MG
+    kind, R, W, spp, integ, ar = MG.CASES[name]
+    g = gold(name)
+    scene, _ = build_scene(sdfrt_mod, kind, R, W, integ, ar)
+    if ar is not None:
+        scene.albedo_grid.requires_grad_(True)
+    sdf = scene.integrator().sdf
+    sdf.data.requires_grad_(True)
+    img = sdfrt_mod.render(scene, sensor=0, seed=MG.SEED, spp=spp, seed_grad=MG.SEED_GRAD, spp_grad=spp)
+    assert np.abs(img.detach().cpu().numpy() - g['image']).max() < 2e-5
+    (img * torch.from_numpy(MG.grad_image(W)).float().cuda()).sum().backward()
+    gs = sdf.data.grad[..., 0].cpu().numpy()
+    assert np.abs(gs - g['grad_sdf']).max() < 2e-2 * np.abs(g['grad_sdf']).max()
+    assert np.linalg.norm(gs - g['grad_sdf']) < 5e-3 * np.linalg.norm(g['grad_sdf'])
+    assert np.abs(sdf.p_grad.cpu().numpy() - g['grad_p']).max() < 2e-2 * max(1.0, np.abs(g['grad_p']).max())
+    if ar is not None:
+        ga = scene.albedo_grid.grad.cpu().numpy()
+        assert np.abs(ga - g['grad_albedo']).max() < 1e-3 * np.abs(g['grad_albedo']).max()
+    # the developed image of the adjoint re-render
+    img_adj = sdf.ctx.develop(scene.integrator().last_film).cpu().numpy()
+    assert np.abs(img_adj - g['image_adj']).max() < 2e-5
+    # fixed rays through SDFBase.ray_intersect
+    ray = sdfrt_mod.Ray3f(torch.from_numpy(g['ray_o']).cuda(), torch.from_numpy(g['ray_d']).cuda(), torch.from_numpy(g['ray_maxt']).cuda())
+    its_t, warp_t, warp_t_d, ww, wwd = sdf.ray_intersect(ray, warp=scene.integrator().warp_field)
+    its_t, warp_t = its_t.cpu().numpy(), warp_t.cpu().numpy()
+    assert (np.isfinite(its_t) == np.isfinite(g['its_t'])).mean() > 0.99
+    both = np.isfinite(its_t) & np.isfinite(g['its_t'])
+    assert np.abs(its_t[both] - g['its_t'][both]).max() < 5e-5
+    wf = np.isfinite(warp_t) & np.isfinite(g['warp_t'])
+    assert np.quantile(np.abs(warp_t[wf] - g['warp_t'][wf]) / np.maximum(1, np.abs(g['warp_t'][wf])), 0.99) < 1e-3
+    assert np.quantile(np.abs(ww.cpu().numpy()[wf] - g['warp_weight'][wf]), 0.99) < 1e-3
+
+
+def test_eval_sdf_against_oracle(sdfrt_mod):
+    from oracle import sdf_oracle as O
+    scene, osc = build_scene(sdfrt_mod, 'blobs', 32, 8, 'sdf_direct_reparam')
+    sdf = scene.integrator().sdf
+    x = np.random.default_rng(0).uniform(-0.1, 1.1, size=(4096, 3))
+    v, g, H = osc.sdf._taps(torch.from_numpy(x), 2)
+    v2, _, g2, _, H2 = sdf.eval_all(x)
+    assert (v2.cpu().double() - v).abs().max() < 2e-6
+    assert (g2.cpu().double() - g).abs().max() < 2e-5
+    assert (H2.cpu().double() - H).abs().max() < 1e-5 * max(1.0, H.abs().max().item())
+    assert (sdf.eval(x).cpu().double() - v).abs().max() < 2e-6
+    assert (sdf.eval_grad(x).cpu().double() - g).abs().max() < 2e-5
+
+
+@pytest.mark.parametrize('warp,integ', [('dummy', 'sdf_direct_reparam'), (None, 'sdf_direct_reparam')])
+def test_variants_against_oracle(sdfrt_mod, warp, integ):
+    """DummyWarpField / warp_field=None: shading gradients only (configs.OnlyShadingGrad)."""
+    from oracle import sdf_oracle as O
+    W, spp = 20, 4
+    scene, osc = build_scene(sdfrt_mod, 'knot', 32, W, integ, warp=warp)
+    owf = O.DummyWarpField(osc.sdf) if warp == 'dummy' else None
+    g_in = np.random.default_rng(1).uniform(-1, 1, size=(W, W, 3))
+    img_o, g_o, _, _ = O.render_backward(osc, owf, integ, torch.from_numpy(g_in), seed=21, spp=spp)
+    sdf = scene.integrator().sdf
+    sdf.data.requires_grad_(True)
+    img = sdfrt_mod.render(scene, sensor=0, seed=21, spp=spp, seed_grad=21, spp_grad=spp)
+    assert (img.detach().cpu().double() - img_o).abs().max() < 2e-5
+    (img * torch.from_numpy(g_in).float().cuda()).sum().backward()
+    gs = sdf.data.grad[..., 0].cpu().double()
+    assert (gs - g_o).abs().max() < 2e-2 * g_o.abs().max()
+    assert (gs - g_o).norm() < 5e-3 * g_o.norm()
+
+
+def test_non_square_film_and_non_pow2_spp(sdfrt_mod):
+    from oracle import sdf_oracle as O
+    scene, osc = build_scene(sdfrt_mod, 'sphere', 24, 28, 'sdf_direct_reparam', H=12)
+    owf = O.WarpField2D(osc.sdf, weight_strategy=6, edge_eps=0.01)
+    owf.clamping_thresh = 0.05
+    with torch.no_grad():
+        img_o = O.render(osc, owf, 'sdf_direct_reparam', seed=2, spp=3)
+    img = scene.integrator().render(scene, sensor=0, seed=2, spp=3)
+    assert img.shape == (12, 28, 3)
+    assert (img.cpu().double() - img_o).abs().max() < 2e-5
+
+
+def test_error_behaviour(sdfrt_mod):
+    ctx = sdfrt_mod.Context(0)
+    film = ctx.new_film()
+    with pytest.raises(sdfrt_mod.SdfrtError):          # no SDF bound
+        ctx.render_primal(0, 4, film)
+    sdf = torch.from_numpy(sdfrt_mod.create_sphere_sdf((16, 16, 16))).cuda()
+    ctx.set_sdf(sdf)
+    ctx.set_sensor(np.eye(4), 16, 16)
+    film = ctx.new_film()
+    with pytest.raises(sdfrt_mod.SdfrtError):          # backprop before accumulate
+        ctx.adjoint_backprop(film, torch.ones(16, 16, 3, device='cuda'), torch.zeros_like(sdf))
+    with pytest.raises(sdfrt_mod.SdfrtError):
+        ctx.set_integrator(7)
+    with pytest.raises(sdfrt_mod.SdfrtError):          # python/integrators/reparam.py:48-50
+        ctx.set_sensor(np.eye(4), 8192, 8192)
+        ctx.render_primal(0, 4096, ctx.new_film())
+    with pytest.raises(sdfrt_mod.SdfrtError):          # CPU tensors are rejected, never silently copied
+        ctx.set_sdf(sdf.cpu())
+
+
+def test_empty_and_inside_cases(sdfrt_mod):
+    """Edge cases: an SDF with no surface (all positive), and a camera inside the bounding box."""
+    ctx = sdfrt_mod.Context(0)
+    ctx.set_sdf(torch.full((16, 16, 16), 0.5, device='cuda'))
+    cam = sdfrt_mod.get_regular_cameras(6, resx=16, resy=16)[0]
+    ctx.set_sensor(cam.to_world, 16, 16)
+    ctx.set_integrator('sdf_direct_reparam')
+    img = ctx.develop(ctx.render_primal(0, 4))
+    assert torch.allclose(img, torch.ones_like(img), atol=1e-6)     # background radiance only
+    g = torch.zeros(16, 16, 16, device='cuda')
+    film = ctx.adjoint_accumulate(1, 4)
+    ctx.adjoint_backprop(film, torch.ones(16, 16, 3, device='cuda'), g)
+    assert torch.isfinite(g).all()
+    ctx.set_sdf(torch.from_numpy(sdfrt_mod.create_sphere_sdf((16, 16, 16))).cuda())
+    ctx.set_sensor(sdfrt_mod.look_at([0.5, 0.5, 0.02], [0.5, 0.5, 0.5], [0, 1, 0]), 16, 16)
+    img = ctx.develop(ctx.render_primal(0, 4))
+    assert torch.isfinite(img).all() and img[8, 8].sum() < 3.0       # the sphere is seen from inside the bbox
+
+
+# ---- size-independent properties at the BASELINE sizes (256^3, 512x512, 64 spp adjoint) -----------------
+@pytest.fixture(scope='module')
+def big(sdfrt_mod):
+    from sdfrt import synthetic as syn
+    ctx = sdfrt_mod.Context(0)
+    sdf = syn.make_sdf_device('blobs', 256, 'cuda')
+    ctx.set_sdf(sdf)
+    cam = sdfrt_mod.get_regular_cameras(12, resx=512, resy=512)[0]
+    ctx.set_sensor(cam.to_world, 512, 512)
+    ctx.set_integrator('sdf_direct_reparam')
+    ctx.set_warp()
+    return ctx, sdf
+
+
+def test_full_size_partition_invariance_and_counts(big):
+    ctx, sdf = big
+    ctx.stats(reset=True)
+    ctx.set_partition(0, 1)
+    film = ctx.render_primal(5, 64).clone()
+    st = ctx.stats(reset=True)
+    assert st['n_rays'] == ctx.wavefront_size(64) == 516 * 516 * 64
+    parts = torch.zeros_like(film)
+    for r in range(4):
+        ctx.set_partition(r, 4)
+        parts += ctx.render_primal(5, 64)
+    st4 = ctx.stats(reset=True)
+    ctx.set_partition(0, 1)
+    assert st4['n_rays'] == st['n_rays'] and st4['n_evals_value'] == st['n_evals_value'] and st4['n_hits'] == st['n_hits']
+    assert (parts - film).abs().max() < 1e-3 * film.abs().max()       # atomics reorder the same addends
+    w = film[2:-2, 2:-2, 3]
+    assert (w > 0).all()                                               # every pixel received samples
+
+
+def test_full_size_adjoint_linearity_and_host_api(big):
+    ctx, sdf = big
+    film = ctx.adjoint_accumulate(9, 64)
+    rng = torch.Generator(device='cuda').manual_seed(0)
+    a = torch.randn(512, 512, 3, device='cuda', generator=rng)
+    b = torch.randn(512, 512, 3, device='cuda', generator=rng)
+    ga, gb, gab = (torch.zeros_like(sdf) for _ in range(3))
+    ctx.adjoint_backprop(film, a, ga)
+    ctx.adjoint_backprop(film, b, gb)
+    ctx.adjoint_backprop(film, (2 * a - 3 * b).contiguous(), gab)
+    ref = 2 * ga - 3 * gb
+    assert torch.isfinite(gab).all() and ga.abs().max() > 0
+    assert (gab - ref).abs().max() < 1e-3 * ref.abs().max()
+    # host-buffer entry point == device API (same seeds)
+    ones = torch.ones(512, 512, 3, device='cuda')
+    g_dev = torch.zeros_like(sdf)
+    img_dev = ctx.develop(ctx.render_primal(3, 16))
+    ctx.adjoint_backprop(ctx.adjoint_accumulate(4, 16), ones, g_dev)
+    img_h, g_h = ctx.render_view_host(sdf.cpu().pin_memory(), 3, 16, 4, 16)
+    ctx.set_sdf(sdf)
+    assert (img_h.cuda() - img_dev).abs().max() < 1e-4
+    assert (g_h.cuda() - g_dev).abs().max() < 1e-3 * g_dev.abs().max()
