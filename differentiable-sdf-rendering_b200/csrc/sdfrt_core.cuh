@@ -201,6 +201,24 @@ SDFRT_HD CellCoord cell_coord(const GridView& G, V3 x) {
 }
 SDFRT_HD int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
+// Clamp-to-edge addressing (WrapMode::Clamp) folded into the WEIGHTS: the interpolant is linear in the taps, so
+// taps i-1..i+2 clamped to [0, r-1] equal the 4 in-range taps b..b+3 (b = clamp(i, 0, r-4)) with the weights of
+// coinciding taps added up.  After folding every lookup is an unclamped 4x4x4 block read (r >= 4 per axis).
+SDFRT_HD int fold_base(int i, int r) { return clampi(i, 0, r - 4); }
+SDFRT_HD void fold_weights(int i, int b, int r, float w[4]) {
+    if (i == b) return;  // interior along this axis
+    float f[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int m = clampi(i + k, 0, r - 1) - b;  // 0..3
+        f[0] += (m == 0) ? w[k] : 0.f;
+        f[1] += (m == 1) ? w[k] : 0.f;
+        f[2] += (m == 2) ? w[k] : 0.f;
+        f[3] += (m == 3) ? w[k] : 0.f;
+    }
+    w[0] = f[0]; w[1] = f[1]; w[2] = f[2]; w[3] = f[3];
+}
+
 // ORDER 0: value; 1: + gradient; 2: + Hessian.  Separable evaluation: x-reduction per row,
 // then y, then z (~1/2 the FMAs of the naive 64 x 10 form).
 template <int ORDER>
@@ -210,19 +228,22 @@ SDFRT_HD void eval_sdf(const GridView& G, V3 x, float& v, V3& g, S3& H) {
     bspline_w(c.ax, wx); bspline_w(c.ay, wy); bspline_w(c.az, wz);
     if (ORDER >= 1) { bspline_dw(c.ax, dx); bspline_dw(c.ay, dy); bspline_dw(c.az, dz); }
     if (ORDER >= 2) { bspline_ddw(c.ax, ex); bspline_ddw(c.ay, ey); bspline_ddw(c.az, ez); }
-    int xo[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) xo[i] = c.interior ? (c.ix + i) : clampi(c.ix + i, 0, G.rx - 1);
+    const int bx = fold_base(c.ix, G.rx), by = fold_base(c.iy, G.ry), bz = fold_base(c.iz, G.rz);
+    if (!c.interior) {
+        fold_weights(c.ix, bx, G.rx, wx); fold_weights(c.iy, by, G.ry, wy); fold_weights(c.iz, bz, G.rz, wz);
+        if (ORDER >= 1) { fold_weights(c.ix, bx, G.rx, dx); fold_weights(c.iy, by, G.ry, dy); fold_weights(c.iz, bz, G.rz, dz); }
+        if (ORDER >= 2) { fold_weights(c.ix, bx, G.rx, ex); fold_weights(c.iy, by, G.ry, ey); fold_weights(c.iz, bz, G.rz, ez); }
+    }
+    const size_t sy = (size_t)G.rx, sz = (size_t)G.rx * (size_t)G.ry;
+    const float* base = G.data + ((size_t)bz * sz + (size_t)by * sy + (size_t)bx);
     float r_v = 0, r_gx = 0, r_gy = 0, r_gz = 0, r_xx = 0, r_yy = 0, r_zz = 0, r_xy = 0, r_xz = 0, r_yz = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const int zz = c.interior ? (c.iz + k) : clampi(c.iz + k, 0, G.rz - 1);
         float A0 = 0, A1 = 0, A2 = 0, B0 = 0, B1 = 0, C0 = 0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int yy = c.interior ? (c.iy + j) : clampi(c.iy + j, 0, G.ry - 1);
-            const float* row = G.data + ((size_t)zz * G.ry + yy) * (size_t)G.rx;
-            const float f0 = row[xo[0]], f1 = row[xo[1]], f2 = row[xo[2]], f3 = row[xo[3]];
+            const float* row = base + (size_t)k * sz + (size_t)j * sy;
+            const float f0 = row[0], f1 = row[1], f2 = row[2], f3 = row[3];
             const float a = wx[0] * f0 + wx[1] * f1 + wx[2] * f2 + wx[3] * f3;
             A0 += wy[j] * a;
             if (ORDER >= 1) {
@@ -254,11 +275,11 @@ SDFRT_HD void eval_sdf(const GridView& G, V3 x, float& v, V3& g, S3& H) {
     }
     v = r_v;
     if (ORDER >= 1) {
-        const float sx = (float)G.rx, sy = (float)G.ry, sz = (float)G.rz;
-        g = V3{r_gx * sx, r_gy * sy, r_gz * sz};
+        const float sx = (float)G.rx, sy_ = (float)G.ry, sz_ = (float)G.rz;
+        g = V3{r_gx * sx, r_gy * sy_, r_gz * sz_};
         if (ORDER >= 2) {
-            H.xx = r_xx * sx * sx; H.yy = r_yy * sy * sy; H.zz = r_zz * sz * sz;
-            H.xy = r_xy * sx * sy; H.xz = r_xz * sx * sz; H.yz = r_yz * sy * sz;
+            H.xx = r_xx * sx * sx; H.yy = r_yy * sy_ * sy_; H.zz = r_zz * sz_ * sz_;
+            H.xy = r_xy * sx * sy_; H.xz = r_xz * sx * sz_; H.yz = r_yz * sy_ * sz_;
         }
     }
 }

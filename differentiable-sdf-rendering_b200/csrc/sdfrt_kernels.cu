@@ -63,10 +63,14 @@ __global__ void __launch_bounds__(kBlock) k_backward(const __grid_constant__ Sce
                                                       const float* __restrict__ film_adj, const float* __restrict__ rec,
                                                       unsigned long long rec_stride, BackwardTargets tg, float* grad_p,
                                                       Counters* counters) {
-    const unsigned long long lane = ps.lane_begin + (unsigned long long)blockIdx.x * kBlock + threadIdx.x;
+    // records are stored in work-item (band) order; the lane index is needed for the sampler and the pixel
+    const unsigned long long item = (unsigned long long)blockIdx.x * kBlock + threadIdx.x;
     LaneStats st = {0, 0, 0, 0, 0, 0, 0};
     V3 gp = v3(0.f);
-    if (lane < ps.lane_end) lane_backward(sc, ps, lane, film_adj, rec, rec_stride, tg, gp, st);
+    if (item < ps.lane_end - ps.lane_begin) {
+        const WorkItem w = decode_item(sc.S, ps, item);
+        lane_backward(sc, ps, w.lane, film_adj, rec + item, rec_stride, tg, gp, st);
+    }
     flush_stats(st, 0u, counters);
     if (grad_p != nullptr) {
         const float gx = warp_sum_f(gp.x), gy = warp_sum_f(gp.y), gz = warp_sum_f(gp.z);
@@ -181,7 +185,10 @@ struct sdfrt_ctx {
     float* film_adj = nullptr;
     size_t film_adj_capacity = 0;
     Counters* counters = nullptr;
-    WorkQueue* work = nullptr;
+    unsigned* work = nullptr;  // WQ_COUNT counters
+    // per-batch scratch of the wavefront pipeline
+    float *segs = nullptr, *its = nullptr, *ssegs = nullptr, *sinfo = nullptr, *s_its = nullptr, *srec = nullptr;
+    size_t segs_n = 0, its_n = 0, ssegs_n = 0, sinfo_n = 0, s_its_n = 0, srec_n = 0;
     int num_sms = 0;
     int march_blocks[2] = {0, 0};  // resident blocks per SM of k_march<false/true>
     // buffers of the host entry point
@@ -228,6 +235,8 @@ int check_ready(sdfrt_ctx* ctx, int spp) {
     return SDFRT_OK;
 }
 
+constexpr unsigned long long kMaxBatch = 1ull << 26;  // camera samples per batch of the wavefront pipeline
+
 template <bool DIFF>
 int launch_forward(sdfrt_ctx* ctx, const PassParams& ps, float* film, cudaStream_t st) {
     SDFRT_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -237,13 +246,48 @@ int launch_forward(sdfrt_ctx* ctx, const PassParams& ps, float* film, cudaStream
     const SensorParams& S = ctx->sc.S;
     if ((unsigned long long)kBandRows * (unsigned long long)(S.W + 2 * S.border) * (unsigned long long)ps.spp > 0xffffffffull)
         return fail(ctx, SDFRT_ERR_INVALID, "film row band exceeds 2^32 samples");
-    SDFRT_CUDA(ctx, cudaMemsetAsync(ctx->work, 0, sizeof(WorkQueue), st));
-    // persistent grid: every SM filled with resident blocks, capped by the amount of work
-    unsigned long long blocks = (unsigned long long)ctx->num_sms * (unsigned long long)ctx->march_blocks[DIFF ? 1 : 0];
-    const unsigned long long need = (n + kMarchBlock - 1) / kMarchBlock;
-    if (blocks > need) blocks = need;
-    k_march<DIFF><<<(unsigned)blocks, kMarchBlock, 0, st>>>(ctx->sc, ps, ctx->work, film, ctx->rec, ctx->rec_stride, ctx->counters);
-    SDFRT_CUDA(ctx, cudaGetLastError());
+    const unsigned long long nbatch = (n + kMaxBatch - 1) / kMaxBatch;
+    const unsigned long long B = (n + nbatch - 1) / nbatch;
+    int rc;
+    if ((rc = ensure(ctx, &ctx->segs, &ctx->segs_n, (size_t)B * 8))) return rc;
+    if ((rc = ensure(ctx, &ctx->ssegs, &ctx->ssegs_n, (size_t)B * 8))) return rc;
+    if ((rc = ensure(ctx, &ctx->sinfo, &ctx->sinfo_n, (size_t)B * 4))) return rc;
+    if (DIFF) {
+        if ((rc = ensure(ctx, &ctx->srec, &ctx->srec_n, (size_t)B * 9))) return rc;
+    } else {
+        if ((rc = ensure(ctx, &ctx->its, &ctx->its_n, (size_t)B))) return rc;
+        if ((rc = ensure(ctx, &ctx->s_its, &ctx->s_its_n, (size_t)B))) return rc;
+    }
+    const unsigned persistent = (unsigned)ctx->num_sms * (unsigned)ctx->march_blocks[DIFF ? 1 : 0];
+    ShadowQueue q;
+    q.segs = reinterpret_cast<SegIn*>(ctx->ssegs);
+    q.info = reinterpret_cast<float4*>(ctx->sinfo);
+    for (unsigned long long b = 0; b < nbatch; ++b) {
+        const unsigned long long item0 = b * B;
+        const unsigned cnt = (unsigned)((n - item0 < B) ? (n - item0) : B);
+        const unsigned blocks256 = (cnt + 255u) / 256u;
+        SDFRT_CUDA(ctx, cudaMemsetAsync(ctx->work, 0, WQ_COUNT * sizeof(unsigned), st));
+        k_gen_primary<<<blocks256, 256, 0, st>>>(ctx->sc, ps, item0, cnt, reinterpret_cast<SegIn*>(ctx->segs));
+        // primary march (+ refine); DIFF writes its_t into row 0 of the lane records
+        float* rec_b = DIFF ? ctx->rec + item0 : nullptr;
+        const unsigned need = (cnt + kMarchBlock - 1) / kMarchBlock;
+        k_march<DIFF><<<persistent < need ? persistent : need, kMarchBlock, 0, st>>>(
+            ctx->sc.G, ctx->sc.T, reinterpret_cast<const SegIn*>(ctx->segs), nullptr, cnt, 1, ctx->its, rec_b, ctx->rec_stride,
+            ctx->work + WQ_PRIMARY_CHUNK, ctx->counters);
+        const float* its = DIFF ? rec_b : ctx->its;
+        k_shade<DIFF><<<blocks256, 256, 0, st>>>(ctx->sc, ps, item0, cnt, its, q, ctx->work + WQ_SHADOW_COUNT, film,
+                                                 DIFF ? rec_b + REC_S_STATE * ctx->rec_stride : nullptr, ctx->counters);
+        if (ctx->sc.integrator == INTEGRATOR_DIRECT) {
+            // shadow march over the compacted queue (count read on the device)
+            k_march<DIFF><<<persistent < need ? persistent : need, kMarchBlock, 0, st>>>(
+                ctx->sc.G, ctx->sc.T, reinterpret_cast<const SegIn*>(ctx->ssegs), ctx->work + WQ_SHADOW_COUNT, 0u, 0, ctx->s_its,
+                ctx->srec, B, ctx->work + WQ_SHADOW_CHUNK, ctx->counters);
+            k_shadow_splat<DIFF><<<blocks256, 256, 0, st>>>(ctx->sc, ps, item0, ctx->work + WQ_SHADOW_COUNT,
+                                                            reinterpret_cast<const float4*>(ctx->sinfo), ctx->s_its, ctx->srec, B, film,
+                                                            rec_b, ctx->rec_stride);
+        }
+        SDFRT_CUDA(ctx, cudaGetLastError());
+    }
     return SDFRT_OK;
 }
 
@@ -297,7 +341,7 @@ sdfrt_ctx* sdfrt_create(int device, int* status) {
         return nullptr;
     }
     ctx->num_sms = prop.multiProcessorCount;
-    bool ok = cudaMalloc((void**)&ctx->work, sizeof(WorkQueue)) == cudaSuccess;
+    bool ok = cudaMalloc((void**)&ctx->work, WQ_COUNT * sizeof(unsigned)) == cudaSuccess;
     ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->march_blocks[0], k_march<false>, kMarchBlock, 0) == cudaSuccess;
     ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->march_blocks[1], k_march<true>, kMarchBlock, 0) == cudaSuccess;
     if (!ok || ctx->march_blocks[0] < 1 || ctx->march_blocks[1] < 1) {
@@ -316,6 +360,7 @@ void sdfrt_destroy(sdfrt_ctx* ctx) {
     cudaFree(ctx->film_adj);
     cudaFree(ctx->counters);
     cudaFree(ctx->work);
+    cudaFree(ctx->segs); cudaFree(ctx->its); cudaFree(ctx->ssegs); cudaFree(ctx->sinfo); cudaFree(ctx->s_its); cudaFree(ctx->srec);
     cudaFree(ctx->h_sdf); cudaFree(ctx->h_film); cudaFree(ctx->h_image); cudaFree(ctx->h_gimg); cudaFree(ctx->h_grad);
     delete ctx;
 }
@@ -324,7 +369,7 @@ const char* sdfrt_last_error(const sdfrt_ctx* ctx) { return ctx ? ctx->err.c_str
 
 int sdfrt_set_sdf(sdfrt_ctx* ctx, const float* sdf, int rx, int ry, int rz, const float p[3]) {
     if (!ctx) return SDFRT_ERR_INVALID;
-    if (!sdf || rx < 1 || ry < 1 || rz < 1) return fail(ctx, SDFRT_ERR_INVALID, "bad SDF grid");
+    if (!sdf || rx < 4 || ry < 4 || rz < 4) return fail(ctx, SDFRT_ERR_INVALID, "bad SDF grid (need >= 4 texels per axis)");
     ctx->sc.G.data = sdf;
     ctx->sc.G.rx = rx; ctx->sc.G.ry = ry; ctx->sc.G.rz = rz;
     ctx->sc.G.px = p ? p[0] : 0.f; ctx->sc.G.py = p ? p[1] : 0.f; ctx->sc.G.pz = p ? p[2] : 0.f;

@@ -46,8 +46,8 @@ struct LaneStats {
 
 #if defined(__CUDA_ARCH__)
 #define SDFRT_ATOMIC_ADD(ptr, val) atomicAdd((ptr), (val))
-#else
-#define SDFRT_ATOMIC_ADD(ptr, val) (*(ptr) += (val))
+#elif !defined(SDFRT_ATOMIC_ADD)
+#define SDFRT_ATOMIC_ADD(ptr, val) (*(ptr) += (val))  // host builds (test harness): single-threaded unless overridden
 #endif
 
 SDFRT_HD bool reparam_at_depth(const WarpParams& W, int depth) {
@@ -246,11 +246,11 @@ struct BackwardTargets {
 // Returns this lane's contribution to dL/d(sdf.p) in grad_p.
 // ------------------------------------------------------------------------------------------------
 SDFRT_HD void lane_backward(const SceneParams& sc, const PassParams& ps, unsigned long long lane, const float* film_adj,
-                            const float* rec, unsigned long long rec_stride, const BackwardTargets& tg, V3& grad_p,
+                            const float* rec /* already offset to this lane's record */, unsigned long long rec_stride, const BackwardTargets& tg, V3& grad_p,
                             LaneStats& st) {
     CameraSample cs = camera_sample(sc, ps, lane);
     const V3 o = cs.o, d0 = cs.d;
-    const float* r = rec + (lane - ps.lane_begin);
+    const float* r = rec;
     const float its_t = r[REC_ITS_T * rec_stride];
     const bool hit = isfinite(its_t);
 

@@ -1,39 +1,43 @@
-// sdfrt_march.cuh -- persistent-threads wavefront marcher (device only).
+// sdfrt_march.cuh -- the forward sweep as a WAVEFRONT pipeline of compact kernels (device only).
 //
-// One warp holds 32 ray slots.  Every trip of the inner loop performs exactly ONE tricubic SDF
-// evaluation for every live slot (primary march, refine iteration or shadow march alike), so the
-// 64-tap gather -- the cost of this path -- always runs converged.  Slots whose segment finished wait
-// until fewer than kMinActive slots are stepping; then the warp (i) finishes them in one batch
-// (surface interaction, emitter sample, film splat, start of the shadow segment) and (ii) refills idle
-// slots with new camera samples drawn from a block-level chunk of a global work counter.  The
-// reference runs the same work as two Dr.Jit megakernels in which every lane waits for the slowest lane
-// of its warp (python/shapes.py:166-238 `mi.Loop`); ncu on the one-thread-per-lane version of this file
-// measured 13 of 32 threads active per instruction (profiles/r1_baseline_summary.md).
+//   k_gen_primary   one thread per camera sample: sampler + sensor ray + AABB clip  -> SegIn[item]
+//   k_march<DIFF>   persistent-threads sphere tracer over an array of ray segments (primary or shadow):
+//                   one warp = 32 ray slots; every trip of the stepping loop performs exactly ONE tricubic
+//                   SDF evaluation for every live slot, finished slots are refilled (ballot + popc ranks) from a
+//                   block-level chunk of a global work counter by two coalesced 16-byte loads.
+//   k_shade         one thread per camera sample: hit -> normal, emitter sample, BSDF gate -> pushes a shadow
+//                   segment into a compacted queue (warp-aggregated atomic); everything else is splatted.
+//   k_shadow_splat  one thread per shadow segment: visibility -> film splat (+ per-lane shadow record).
 //
-// Work items are camera samples in band order: the rank's film rows are cut into bands of 8 rows and a
-// band is walked column by column, so the samples in flight at any time cover a compact 8 x k pixel tile
-// (SDF bricks shared through L1/L2), while lane indices -- and therefore the sampler streams -- stay the
-// reference's scanline wavefront indices.
+// The reference runs the same work as one Dr.Jit megakernel per pass in which every lane of a warp waits for the
+// slowest lane of its two recorded loops (python/shapes.py:166-238, sdf_direct_reparam.py:21-52).  Splitting at the
+// loop boundaries costs ~40 B of queue traffic per ray (HBM: < 1 ms per pass at C3) and keeps the marcher -- where
+// > 85 % of the time goes -- small (I-cache resident) and converged.  The one-thread-per-lane form of this code ran
+// with 13/32 threads active per instruction, the fused persistent form with 20/32 (profiles/).
+//
+// Work items are camera samples in band order: the rank's film rows are cut into bands of 8 rows and a band is
+// walked column by column, so the samples in flight cover a compact pixel tile (SDF cells shared through L1/L2),
+// while lane indices -- and therefore the sampler streams -- stay the reference's scanline wavefront indices.
 #pragma once
 #include "sdfrt_lane.cuh"
 
 namespace sdfrt {
 
-constexpr int kMarchBlock = 128;        // threads per block
-constexpr int kBlockChunk = 2048;       // work items a block takes from the global counter at a time
-constexpr int kMinActive = 20;          // leave the stepping loop when fewer slots are live
+constexpr int kMarchBlock = 128;       // threads per block of k_march
+constexpr unsigned kBlockChunk = 1024; // segments a block takes from the global counter at a time
+constexpr int kMinActive = 24;         // leave the stepping loop when fewer slots are live
 constexpr int kBandRows = 8;
 
-struct WorkQueue {
-    unsigned long long next;  // global item counter (zeroed before every launch)
+// device work counters of one batch (zeroed before every batch)
+enum { WQ_PRIMARY_CHUNK = 0, WQ_SHADOW_CHUNK = 1, WQ_SHADOW_COUNT = 2, WQ_COUNT = 4 };
+
+// one ray segment ready to march: d normalised; maxt < 0 marks a segment that never enters the bounding box;
+// t0 == 0 <=> origin inside the box (python/shapes.py:141)
+struct SegIn {
+    float4 a;  // o.xyz, t0
+    float4 b;  // d.xyz, maxt
 };
 
-struct BlockQueue {
-    unsigned long long cur, end;
-    int lock;
-};
-
-// item -> (px, py, sample, lane)
 struct WorkItem {
     int px, py;
     unsigned long long lane;
@@ -44,7 +48,7 @@ __device__ __forceinline__ WorkItem decode_item(const SensorParams& S, const Pas
     const unsigned nrows = (unsigned)((ps.lane_end - ps.lane_begin) / ((unsigned long long)Wb * (unsigned)ps.spp));
     const unsigned long long per_band = (unsigned long long)kBandRows * Wb * (unsigned)ps.spp;
     const unsigned band = (unsigned)(k / per_band);
-    const unsigned r = (unsigned)(k - (unsigned long long)band * per_band);  // < 8 * Wb * spp (fits 32 bits: asserted on the host)
+    const unsigned r = (unsigned)(k - (unsigned long long)band * per_band);  // < 8 * Wb * spp (checked on the host)
     const unsigned rows_here = min((unsigned)kBandRows, nrows - band * kBandRows);
     const unsigned per_col = rows_here * (unsigned)ps.spp;
     const unsigned x = r / per_col;
@@ -58,30 +62,46 @@ __device__ __forceinline__ WorkItem decode_item(const SensorParams& S, const Pas
     return w;
 }
 
-// leader-only: take up to n consecutive items from the block's chunk (refilling it from the global counter)
-__device__ __forceinline__ int fetch_items(BlockQueue* bq, WorkQueue* gq, unsigned long long total, int n, unsigned long long& pos) {
-    while (atomicCAS(&bq->lock, 0, 1) != 0) __nanosleep(32);
-    __threadfence_block();
-    unsigned long long cur = *(volatile unsigned long long*)&bq->cur, end = *(volatile unsigned long long*)&bq->end;
-    if (cur >= end && cur < total) {
-        const unsigned long long base = atomicAdd(&gq->next, (unsigned long long)kBlockChunk);
-        if (base >= total) {
-            cur = end = total;
-        } else {
-            cur = base;
-            end = base + kBlockChunk < total ? base + kBlockChunk : total;
-        }
-    }
-    const unsigned long long avail = end - cur;
-    const int got = avail < (unsigned long long)n ? (int)avail : n;
-    pos = cur;
-    *(volatile unsigned long long*)&bq->cur = cur + got;
-    *(volatile unsigned long long*)&bq->end = end;
-    __threadfence_block();
-    atomicExch(&bq->lock, 0);
-    return got;
+// camera sample of a work item: ray + film position of its (re-projected) splat
+struct ItemRay {
+    V3 o, d;
+    float maxt, pfx, pfy;
+    unsigned long long lane;
+};
+__device__ __forceinline__ ItemRay item_ray(const SceneParams& sc, const PassParams& ps, unsigned long long k) {
+    const WorkItem w = decode_item(sc.S, ps, k);
+    ItemRay r;
+    r.lane = w.lane;
+    Pcg32 rng = sampler_seed(ps.seed, (uint32_t)w.lane);
+    const float r0 = pcg_next_f32(rng), r1 = pcg_next_f32(rng);
+    sensor_sample_ray(sc.S, (float)(w.px - sc.S.border) + r0, (float)(w.py - sc.S.border) + r1, r.o, r.d, r.maxt);
+    float u, v; bool inside; V3 ref;
+    sensor_project(sc.S, r.o + r.d, u, v, inside, ref);  // re-projection, python/integrators/reparam.py:100-105
+    r.pfx = u + ((float)sc.S.border - 0.5f);
+    r.pfy = v + ((float)sc.S.border - 0.5f);
+    return r;
 }
 
+__device__ __forceinline__ SegIn make_seg(const TracerParams& T, V3 o, V3 d, float ray_maxt) {
+    Segment s;
+    const bool active = segment_begin(s, T, o, d, ray_maxt);
+    SegIn g;
+    g.a = make_float4(s.o.x, s.o.y, s.o.z, s.t);
+    g.b = make_float4(s.d.x, s.d.y, s.d.z, active ? s.maxt : -1.f);
+    return g;
+}
+
+__global__ void __launch_bounds__(256) k_gen_primary(const __grid_constant__ SceneParams sc, const __grid_constant__ PassParams ps,
+                                                      unsigned long long item0, unsigned n, SegIn* __restrict__ segs) {
+    const unsigned i = blockIdx.x * 256u + threadIdx.x;
+    if (i >= n) return;
+    const ItemRay r = item_ray(sc, ps, item0 + i);
+    segs[i] = make_seg(sc.T, r.o, r.d, r.maxt);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// film splat (ImageBlock::put, oracle/ref_semantics.md S4)
+// ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void splat(const SensorParams& S, float* film, float pfx, float pfy, V3 rgb) {
     const int Wb = S.W + 2 * S.border, Hb = S.H + 2 * S.border;
     const float rad = S.filter_radius;
@@ -104,221 +124,260 @@ __device__ __forceinline__ void splat(const SensorParams& S, float* film, float 
     }
 }
 
-enum { SLOT_IDLE = 0, SLOT_MARCH = 1, SLOT_REFINE = 2, SLOT_DONE = 3 };
-enum { KIND_PRIMARY = 0, KIND_SHADOW = 1 };
+// ---------------------------------------------------------------------------------------------------------------
+// k_march: persistent sphere tracer over segments
+// ---------------------------------------------------------------------------------------------------------------
+constexpr unsigned long long kQueueExhausted = 0xFFFFFFFFull << 32;
 
+// Leader only.  The block's chunk is one 64-bit shared word (chunk id << 32 | items handed out); a fetch is a single
+// shared atomicAdd.  Returns the number of items taken (>= 0) or -1 when the segment array is exhausted.
+__device__ __forceinline__ int fetch_items(unsigned long long* word, unsigned* chunk_counter, unsigned n_total, int n, unsigned& pos) {
+    for (;;) {
+        const unsigned long long old = atomicAdd(word, (unsigned long long)n);
+        const unsigned id = (unsigned)(old >> 32), off = (unsigned)old;
+        if (id == 0xFFFFFFFFu) return -1;
+        if (off < kBlockChunk) {
+            int got = (off + (unsigned)n <= kBlockChunk) ? n : (int)(kBlockChunk - off);
+            if (off + (unsigned)n >= kBlockChunk) {  // this fetch used the chunk up: install the next one
+                const unsigned nid = atomicAdd(chunk_counter, 1u);
+                const unsigned long long nw = ((unsigned long long)nid * kBlockChunk >= n_total) ? kQueueExhausted
+                                                                                              : ((unsigned long long)nid << 32);
+                atomicExch(word, nw);
+            }
+            const unsigned long long p = (unsigned long long)id * kBlockChunk + off;
+            if (p >= n_total) return 0;
+            pos = (unsigned)p;
+            if (p + (unsigned)got > n_total) got = (int)(n_total - p);
+            return got;
+        }
+        __nanosleep(40);  // another warp is installing the next chunk
+    }
+}
+
+enum { SLOT_IDLE = 0, SLOT_MARCH = 1, SLOT_REFINE = 2, SLOT_DONE = 3 };
+
+// rec_out (DIFF): 9 rows [its_t, warp_t, warp_t_d xyz, warp_weight, warp_weight_d xyz] of stride rec_stride.
 template <bool DIFF>
-__global__ void __launch_bounds__(kMarchBlock) k_march(const __grid_constant__ SceneParams sc, const __grid_constant__ PassParams ps,
-                                                        WorkQueue* __restrict__ gq, float* __restrict__ film,
-                                                        float* __restrict__ rec, unsigned long long rec_stride,
+__global__ void __launch_bounds__(kMarchBlock) k_march(const GridView G, const TracerParams T, const SegIn* __restrict__ segs,
+                                                        const unsigned* __restrict__ n_ptr, unsigned n_fixed, int do_refine,
+                                                        float* __restrict__ out_its, float* __restrict__ rec_out,
+                                                        unsigned long long rec_stride, unsigned* __restrict__ chunk_counter,
                                                         Counters* __restrict__ counters) {
-    __shared__ BlockQueue bq;
-    if (threadIdx.x == 0) { bq.cur = 0; bq.end = 0; bq.lock = 0; }
+    __shared__ unsigned long long s_word;
+    const unsigned n_total = n_ptr ? *n_ptr : n_fixed;
+    if (threadIdx.x == 0) {
+        const unsigned id = atomicAdd(chunk_counter, 1u);
+        s_word = ((unsigned long long)id * kBlockChunk >= n_total) ? kQueueExhausted : ((unsigned long long)id << 32);
+    }
     __syncthreads();
     const unsigned FULL = 0xffffffffu;
     const int lane_id = threadIdx.x & 31;
-    const unsigned long long total = ps.lane_end - ps.lane_begin;
-    const bool warp_primary = DIFF && reparam_at_depth(sc.W, 0);
-    const bool warp_shadow = DIFF && reparam_at_depth(sc.W, 1);
-
-    // slot state
-    int state = SLOT_IDLE, kind = KIND_PRIMARY;
+    int state = SLOT_IDLE;
+    unsigned item = 0;
     Segment seg;
-    seg.o = v3(0.f); seg.d = v3(0.f, 0.f, 1.f); seg.t = 0.f; seg.maxt = 0.f; seg.trace_eps = 0.f; seg.its_t = INFINITY; seg.i = 0;
+    seg.o = v3(0.f); seg.d = v3(0.f, 0.f, 1.f); seg.t = 0.f; seg.maxt = -1.f; seg.trace_eps = 0.f; seg.its_t = INFINITY; seg.i = 0;
     seg.intersects = false; seg.inside = false;
     DiffAcc acc;
     if (DIFF) { acc.warp_t = 0; acc.prev_surf_dist = 0; acc.weight_sum = 0; acc.extra_weight_sum = 0; acc.prev_sdf_grad_c = v3(0.f);
                 acc.mixed_sum_d = v3(0.f); acc.weight_d_sum = v3(0.f); acc.extra_weight_sum_d = v3(0.f); acc.t_d = v3(0.f); }
-    bool seg_diff = false;             // this segment runs the differentiable tracer
-    unsigned long long lane = 0;       // wavefront lane of the camera sample in this slot
-    float pfx = 0.f, pfy = 0.f;        // film position of the sample (block coordinates)
-    V3 pend_rgb = v3(0.f);             // radiance added if the shadow segment is unoccluded
-    LaneStats st = {0, 0, 0, 0, 0, 0, 0};
-    unsigned n_rays = 0;
+    unsigned n_evals = 0, n_steps_max = 0;
     bool exhausted = false;
 
     while (true) {
-        // ---- (1) finish completed segments -------------------------------------------------------------
-        if (state == SLOT_DONE) {
-            float* r = rec + (lane - ps.lane_begin);
-            st.n_steps_max = max(st.n_steps_max, (unsigned)seg.i);
-            if (kind == KIND_PRIMARY) {
-                if (DIFF) {
-                    TraceOut tr;
-                    if (seg_diff) {
-                        diff_finalize(seg, acc, sc.T, tr);
-                    } else {
-                        tr.its_t = seg.its_t; tr.warp_t = INFINITY; tr.warp_t_d = v3(0.f); tr.warp_weight = 0.f; tr.warp_weight_d = v3(0.f);
-                    }
-                    r[REC_ITS_T * rec_stride] = tr.its_t;
-                    r[REC_TAU * rec_stride] = tr.warp_t;
-                    r[REC_TAU_DX * rec_stride] = tr.warp_t_d.x; r[REC_TAU_DY * rec_stride] = tr.warp_t_d.y; r[REC_TAU_DZ * rec_stride] = tr.warp_t_d.z;
-                    r[REC_OMEGA * rec_stride] = tr.warp_weight;
-                    r[REC_OMEGA_DX * rec_stride] = tr.warp_weight_d.x; r[REC_OMEGA_DY * rec_stride] = tr.warp_weight_d.y; r[REC_OMEGA_DZ * rec_stride] = tr.warp_weight_d.z;
-                    r[REC_S_STATE * rec_stride] = 0.f;
-                }
-                const bool hit = isfinite(seg.its_t);
-                st.n_hit += hit;
-                V3 rgb = v3(0.f);
-                bool shadow = false;
-                if (sc.integrator == INTEGRATOR_SILHOUETTE) {
-                    rgb = v3(hit ? 1.f : 0.f);
-                } else if (!hit) {
-                    if (sc.integrator == INTEGRATOR_DIRECT && !sc.Sh.hide_emitters) rgb = V3{sc.Sh.Le[0], sc.Sh.Le[1], sc.Sh.Le[2]};
-                } else {
-                    const V3 p = seg.o + seg.its_t * seg.d;
-                    float phi; V3 g; S3 H;
-                    eval_sdf<1>(sc.G, p, phi, g, H);
-                    st.n_grad += 1;
-                    const V3 n = normalize(g);
-                    if (sc.integrator == INTEGRATOR_SIMPLE_SHADING) {
-                        rgb = v3(fmaxf(0.f, (n.x + n.y + n.z) * 0.57735026918962576f));
-                    } else {
-                        const float cos_i = -dot(n, seg.d);
-                        Pcg32 rng = sampler_seed(ps.seed, (uint32_t)lane);
-                        (void)pcg_next_u32(rng); (void)pcg_next_u32(rng); (void)pcg_next_u32(rng);
-                        const float u0 = pcg_next_f32(rng), u1 = pcg_next_f32(rng);
-                        const ShadowRay sr = make_shadow_ray(sc.Sh, p, n, u0, u1);
-                        const float cos_o = dot(n, sr.d);
-                        if ((cos_i > 0.f) & (cos_o > 0.f)) {
-                            const V3 rho = eval_albedo(sc.A, p, nullptr, nullptr);
-                            st.n_albedo += (sc.A.data != nullptr);
-                            const float k = cos_o * 4.f;
-                            pend_rgb = V3{rho.x * k * sc.Sh.Le[0], rho.y * k * sc.Sh.Le[1], rho.z * k * sc.Sh.Le[2]};
-                            shadow = true;
-                            kind = KIND_SHADOW;
-                            seg_diff = warp_shadow;
-                            const bool active = segment_begin(seg, sc.T, sr.o, sr.d, sr.maxt);
-                            if (DIFF && seg_diff) diff_begin(acc, seg);
-                            state = active ? SLOT_MARCH : SLOT_DONE;
-                        }
-                    }
-                }
-                if (!shadow) {
-                    splat(sc.S, film, pfx, pfy, rgb);
-                    state = SLOT_IDLE;
-                }
-            }
-            if (state == SLOT_DONE && kind == KIND_SHADOW) {
-                const bool occluded = isfinite(seg.its_t);
-                if (DIFF && !occluded) {
-                    r[REC_S_STATE * rec_stride] = 1.f;
-                    TraceOut ts;
-                    if (seg_diff) {
-                        diff_finalize(seg, acc, sc.T, ts);
-                    } else {
-                        ts.warp_t = INFINITY; ts.warp_t_d = v3(0.f); ts.warp_weight = 0.f; ts.warp_weight_d = v3(0.f);
-                    }
-                    r[REC_S_TAU * rec_stride] = ts.warp_t;
-                    r[REC_S_TAU_DX * rec_stride] = ts.warp_t_d.x; r[REC_S_TAU_DY * rec_stride] = ts.warp_t_d.y; r[REC_S_TAU_DZ * rec_stride] = ts.warp_t_d.z;
-                    r[REC_S_OMEGA * rec_stride] = ts.warp_weight;
-                    r[REC_S_OMEGA_DX * rec_stride] = ts.warp_weight_d.x; r[REC_S_OMEGA_DY * rec_stride] = ts.warp_weight_d.y; r[REC_S_OMEGA_DZ * rec_stride] = ts.warp_weight_d.z;
-                }
-                splat(sc.S, film, pfx, pfy, occluded ? v3(0.f) : pend_rgb);
-                state = SLOT_IDLE;
-            }
+        // ---- finish (DIFF): tracer outputs of completed segments ----------------------------------------------
+        if (DIFF && state == SLOT_DONE) {
+            TraceOut tr;
+            diff_finalize(seg, acc, T, tr);
+            float* r = rec_out + item;
+            r[0 * rec_stride] = tr.its_t;
+            r[1 * rec_stride] = tr.warp_t;
+            r[2 * rec_stride] = tr.warp_t_d.x; r[3 * rec_stride] = tr.warp_t_d.y; r[4 * rec_stride] = tr.warp_t_d.z;
+            r[5 * rec_stride] = tr.warp_weight;
+            r[6 * rec_stride] = tr.warp_weight_d.x; r[7 * rec_stride] = tr.warp_weight_d.y; r[8 * rec_stride] = tr.warp_weight_d.z;
+            state = SLOT_IDLE;
         }
-
-        // ---- (2) refill idle slots ----------------------------------------------------------------------
+        // ---- refill idle slots ----------------------------------------------------------------------------------
         const unsigned idle = __ballot_sync(FULL, state == SLOT_IDLE);
         if (idle != 0u && !exhausted) {
-            const int n_idle = __popc(idle);
-            unsigned long long pos = 0;
+            unsigned pos = 0;
             int got = 0;
-            if (lane_id == 0) got = fetch_items(&bq, gq, total, n_idle, pos);
+            if (lane_id == 0) got = fetch_items(&s_word, chunk_counter, n_total, __popc(idle), pos);
             got = __shfl_sync(FULL, got, 0);
             pos = __shfl_sync(FULL, pos, 0);
-            if (got == 0) exhausted = true;
+            if (got < 0) exhausted = true;
             const int my = __popc(idle & ((1u << lane_id) - 1u));
             if (state == SLOT_IDLE && my < got) {
-                const WorkItem w = decode_item(sc.S, ps, pos + (unsigned long long)my);
-                lane = w.lane;
-                Pcg32 rng = sampler_seed(ps.seed, (uint32_t)lane);
-                const float r0 = pcg_next_f32(rng), r1 = pcg_next_f32(rng);
-                V3 o, d; float maxt;
-                sensor_sample_ray(sc.S, (float)(w.px - sc.S.border) + r0, (float)(w.py - sc.S.border) + r1, o, d, maxt);
-                float u, v; bool inside; V3 ref;
-                sensor_project(sc.S, o + d, u, v, inside, ref);  // re-projection, python/integrators/reparam.py:100-105
-                pfx = u + ((float)sc.S.border - 0.5f);
-                pfy = v + ((float)sc.S.border - 0.5f);
-                kind = KIND_PRIMARY;
-                seg_diff = warp_primary;
-                const bool active = segment_begin(seg, sc.T, o, d, maxt);
-                if (DIFF && seg_diff) diff_begin(acc, seg);
-                state = active ? SLOT_MARCH : SLOT_DONE;
-                ++n_rays;
+                item = pos + (unsigned)my;
+                const float4 a = __ldg(&segs[item].a), b = __ldg(&segs[item].b);
+                seg.o = V3{a.x, a.y, a.z}; seg.d = V3{b.x, b.y, b.z};
+                seg.t = a.w; seg.maxt = b.w;
+                seg.inside = (a.w == 0.f);
+                seg.intersects = b.w >= 0.f;
+                seg.trace_eps = T.trace_eps * fmaxf(b.w, 1.f);
+                seg.its_t = INFINITY;
+                seg.i = 0;
+                if (DIFF) diff_begin(acc, seg);
+                state = seg.intersects ? SLOT_MARCH : SLOT_DONE;
+                if (!DIFF && state == SLOT_DONE) { out_its[item] = INFINITY; state = SLOT_IDLE; }
             }
         }
-        if (__ballot_sync(FULL, state != SLOT_IDLE) == 0u) {
+        const bool stepping = (state == SLOT_MARCH) | (state == SLOT_REFINE);
+        if (__ballot_sync(FULL, stepping) == 0u) {
+            if (__ballot_sync(FULL, state == SLOT_DONE) != 0u) continue;
             if (exhausted) break;
             continue;
         }
-
-        // ---- (3) stepping loop: one SDF evaluation per live slot per trip ----------------------------------
+        // ---- stepping loop: one SDF evaluation per live slot per trip ------------------------------------------------
         const int min_active = exhausted ? 1 : kMinActive;
-        while (true) {
+        for (;;) {
             const bool live = (state == SLOT_MARCH) | (state == SLOT_REFINE);
             if (__popc(__ballot_sync(FULL, live)) < min_active) break;
             if (live) {
                 const float tt = (state == SLOT_MARCH) ? seg.t : seg.its_t;
                 const V3 x = seg.o + tt * seg.d;
+                ++n_evals;
+                bool cont;
                 if (DIFF) {
                     float v; V3 g; S3 H;
-                    eval_sdf<2>(sc.G, x, v, g, H);
-                    if (state == SLOT_MARCH) {
-                        bool active;
-                        if (seg_diff) {
-                            active = diff_step(seg, acc, sc.T, v, g, H);
-                            st.n_hess += 1;
-                        } else {
-                            active = value_step(seg, sc.T, v);
-                            st.n_value += 1;
-                        }
-                        if (!active) {
-                            st.n_steps_max = max(st.n_steps_max, (unsigned)seg.i);
-                            if (kind == KIND_PRIMARY && sc.T.refine_intersection && isfinite(seg.its_t)) { state = SLOT_REFINE; seg.i = 0; }
-                            else state = SLOT_DONE;
-                        }
-                    } else {
-                        st.n_value += 1;
-                        if (!refine_step(seg, v)) state = SLOT_DONE;
-                    }
+                    eval_sdf<2>(G, x, v, g, H);
+                    cont = (state == SLOT_MARCH) ? diff_step(seg, acc, T, v, g, H) : refine_step(seg, v);
                 } else {
-                    const float v = eval_value(sc.G, x);
-                    st.n_value += 1;
+                    const float v = eval_value(G, x);
+                    cont = (state == SLOT_MARCH) ? value_step(seg, T, v) : refine_step(seg, v);
+                }
+                if (!cont) {
                     if (state == SLOT_MARCH) {
-                        if (!value_step(seg, sc.T, v)) {
-                            st.n_steps_max = max(st.n_steps_max, (unsigned)seg.i);
-                            if (kind == KIND_PRIMARY && sc.T.refine_intersection && isfinite(seg.its_t)) { state = SLOT_REFINE; seg.i = 0; }
-                            else state = SLOT_DONE;
-                        }
+                        n_steps_max = max(n_steps_max, (unsigned)seg.i);
+                        if (do_refine && T.refine_intersection && isfinite(seg.its_t)) { state = SLOT_REFINE; seg.i = 0; }
+                        else state = SLOT_DONE;
                     } else {
-                        if (!refine_step(seg, v)) state = SLOT_DONE;
+                        state = SLOT_DONE;
                     }
+                    if (!DIFF && state == SLOT_DONE) { out_its[item] = seg.its_t; state = SLOT_IDLE; }
                 }
             }
         }
     }
-
-    // ---- counters ------------------------------------------------------------------------------------------
+    // ---- counters --------------------------------------------------------------------------------------------------
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        st.n_value += __shfl_xor_sync(FULL, st.n_value, o);
-        st.n_grad += __shfl_xor_sync(FULL, st.n_grad, o);
-        st.n_hess += __shfl_xor_sync(FULL, st.n_hess, o);
-        st.n_albedo += __shfl_xor_sync(FULL, st.n_albedo, o);
-        st.n_hit += __shfl_xor_sync(FULL, st.n_hit, o);
-        n_rays += __shfl_xor_sync(FULL, n_rays, o);
-        st.n_steps_max = max(st.n_steps_max, __shfl_xor_sync(FULL, st.n_steps_max, o));
+        n_evals += __shfl_xor_sync(FULL, n_evals, o);
+        n_steps_max = max(n_steps_max, __shfl_xor_sync(FULL, n_steps_max, o));
     }
     if (lane_id == 0) {
-        if (n_rays) atomicAdd(&counters->n_rays, (unsigned long long)n_rays);
-        if (st.n_value) atomicAdd(&counters->n_evals_value, (unsigned long long)st.n_value);
-        if (st.n_grad) atomicAdd(&counters->n_evals_grad, (unsigned long long)st.n_grad);
-        if (st.n_hess) atomicAdd(&counters->n_evals_hess, (unsigned long long)st.n_hess);
-        if (st.n_albedo) atomicAdd(&counters->n_albedo_lookups, (unsigned long long)st.n_albedo);
-        if (st.n_hit) atomicAdd(&counters->n_hits, (unsigned long long)st.n_hit);
-        atomicMax(&counters->n_steps_max, (unsigned long long)st.n_steps_max);
+        if (n_evals) atomicAdd(DIFF ? &counters->n_evals_hess : &counters->n_evals_value, (unsigned long long)n_evals);
+        atomicMax(&counters->n_steps_max, (unsigned long long)n_steps_max);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_shade: <integrator>.sample after the primary intersection (python/integrators/sdf_direct_reparam.py:24-84)
+// ---------------------------------------------------------------------------------------------------------------
+struct ShadowQueue {
+    SegIn* segs;     // shadow segments
+    float4* info;    // rgb added if unoccluded, item index (bit pattern) in .w
+};
+
+template <bool DIFF>
+__global__ void __launch_bounds__(256) k_shade(const __grid_constant__ SceneParams sc, const __grid_constant__ PassParams ps,
+                                                unsigned long long item0, unsigned n, const float* __restrict__ its,
+                                                ShadowQueue q, unsigned* __restrict__ shadow_count, float* __restrict__ film,
+                                                float* __restrict__ rec_state, Counters* __restrict__ counters) {
+    const unsigned i = blockIdx.x * 256u + threadIdx.x;
+    const bool live = i < n;
+    bool push = false;
+    SegIn sseg;
+    float4 info = make_float4(0.f, 0.f, 0.f, 0.f);
+    unsigned n_grad = 0, n_alb = 0, n_hit = 0;
+    if (live) {
+        const float its_t = its[i];
+        const bool hit = isfinite(its_t);
+        n_hit = hit;
+        const ItemRay r = item_ray(sc, ps, item0 + i);
+        V3 rgb = v3(0.f);
+        if (sc.integrator == INTEGRATOR_SILHOUETTE) {
+            rgb = v3(hit ? 1.f : 0.f);
+        } else if (!hit) {
+            if (sc.integrator == INTEGRATOR_DIRECT && !sc.Sh.hide_emitters) rgb = V3{sc.Sh.Le[0], sc.Sh.Le[1], sc.Sh.Le[2]};
+        } else {
+            const V3 p = r.o + its_t * r.d;
+            float phi; V3 g; S3 H;
+            eval_sdf<1>(sc.G, p, phi, g, H);
+            n_grad = 1;
+            const V3 n = normalize(g);
+            if (sc.integrator == INTEGRATOR_SIMPLE_SHADING) {
+                rgb = v3(fmaxf(0.f, (n.x + n.y + n.z) * 0.57735026918962576f));
+            } else {
+                const float cos_i = -dot(n, r.d);
+                Pcg32 rng = sampler_seed(ps.seed, (uint32_t)r.lane);
+                (void)pcg_next_u32(rng); (void)pcg_next_u32(rng); (void)pcg_next_u32(rng);
+                const float u0 = pcg_next_f32(rng), u1 = pcg_next_f32(rng);
+                const ShadowRay sr = make_shadow_ray(sc.Sh, p, n, u0, u1);
+                const float cos_o = dot(n, sr.d);
+                // a shadow ray whose BSDF gate is closed contributes exactly zero whatever it hits: not traced
+                if ((cos_i > 0.f) & (cos_o > 0.f)) {
+                    const V3 rho = eval_albedo(sc.A, p, nullptr, nullptr);
+                    n_alb = (sc.A.data != nullptr);
+                    const float k = cos_o * 4.f;  // (rho / pi) cos_o Le / (1 / 4 pi)
+                    info = make_float4(rho.x * k * sc.Sh.Le[0], rho.y * k * sc.Sh.Le[1], rho.z * k * sc.Sh.Le[2], __uint_as_float(i));
+                    sseg = make_seg(sc.T, sr.o, sr.d, sr.maxt);
+                    push = true;
+                }
+            }
+        }
+        if (DIFF) rec_state[i] = 0.f;
+        if (!push) splat(sc.S, film, r.pfx, r.pfy, rgb);
+    }
+    // compacted push, one atomic per warp
+    const unsigned FULL = 0xffffffffu;
+    const unsigned m = __ballot_sync(FULL, push);
+    if (m) {
+        const int lane_id = threadIdx.x & 31;
+        unsigned base = 0;
+        if (lane_id == (__ffs(m) - 1)) base = atomicAdd(shadow_count, (unsigned)__popc(m));
+        base = __shfl_sync(FULL, base, __ffs(m) - 1);
+        if (push) {
+            const unsigned j = base + (unsigned)__popc(m & ((1u << lane_id) - 1u));
+            q.segs[j] = sseg;
+            q.info[j] = info;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        n_grad += __shfl_xor_sync(FULL, n_grad, o);
+        n_alb += __shfl_xor_sync(FULL, n_alb, o);
+        n_hit += __shfl_xor_sync(FULL, n_hit, o);
+    }
+    const unsigned nr = __popc(__ballot_sync(FULL, live));
+    if ((threadIdx.x & 31) == 0) {
+        if (nr) atomicAdd(&counters->n_rays, (unsigned long long)nr);
+        if (n_grad) atomicAdd(&counters->n_evals_grad, (unsigned long long)n_grad);
+        if (n_alb) atomicAdd(&counters->n_albedo_lookups, (unsigned long long)n_alb);
+        if (n_hit) atomicAdd(&counters->n_hits, (unsigned long long)n_hit);
+    }
+}
+
+// one thread per shadow segment: visibility -> splat; DIFF: scatter the shadow tracer record to the lane records
+template <bool DIFF>
+__global__ void __launch_bounds__(256) k_shadow_splat(const __grid_constant__ SceneParams sc, const __grid_constant__ PassParams ps,
+                                                       unsigned long long item0, const unsigned* __restrict__ shadow_count,
+                                                       const float4* __restrict__ info, const float* __restrict__ s_its,
+                                                       const float* __restrict__ srec, unsigned long long srec_stride,
+                                                       float* __restrict__ film, float* __restrict__ rec,
+                                                       unsigned long long rec_stride) {
+    const unsigned j = blockIdx.x * 256u + threadIdx.x;
+    if (j >= *shadow_count) return;
+    const float4 inf = info[j];
+    const unsigned i = __float_as_uint(inf.w);
+    const float its_s = DIFF ? srec[j] : s_its[j];
+    const bool occluded = isfinite(its_s);
+    const ItemRay r = item_ray(sc, ps, item0 + i);
+    splat(sc.S, film, r.pfx, r.pfy, occluded ? v3(0.f) : V3{inf.x, inf.y, inf.z});
+    if (DIFF && !occluded) {
+        float* d = rec + i;
+        d[REC_S_STATE * rec_stride] = 1.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) d[(REC_S_TAU + k) * rec_stride] = srec[(1 + k) * srec_stride + j];
     }
 }
 

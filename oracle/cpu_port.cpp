@@ -1,0 +1,109 @@
+// oracle/cpu_port.cpp -- multi-threaded CPU build of the per-lane restatement, used ONLY as the timed CPU baseline
+// (bench.py `cpu_baseline` / `--impl reference`).  TEST/BENCH INFRASTRUCTURE: the product never links it.
+//
+// The reference's own CPU path (Mitsuba `llvm_ad_rgb`, python/optimize.py:70-78) cannot be installed offline, and the
+// parity oracle (oracle/sdf_oracle.py, torch autograd) is a vectorised-Python program that is ~100x slower than a
+// compiled implementation would be -- timing it would flatter the GPU.  This file therefore compiles the per-lane
+// forward/adjoint code (csrc/sdfrt_lane.cuh, `__host__ __device__`) with g++ -O3 -march=native -fopenmp so that the CPU
+// baseline is a compiled, all-cores implementation of the same algorithm (same evaluation counts per ray).
+// Parity is NOT judged against this file (it shares source with the kernels); it is judged against sdf_oracle.py.
+#include <omp.h>
+
+#include <chrono>
+#include <cstring>
+#include <vector>
+
+#define SDFRT_ATOMIC_ADD(ptr, val)                \
+    do {                                          \
+        _Pragma("omp atomic") *(ptr) += (val);    \
+    } while (0)
+#include "../differentiable-sdf-rendering_b200/csrc/sdfrt_params.h"
+
+using namespace sdfrt;
+
+struct cp_scene {
+    const float* sdf; int rx, ry, rz;
+    const float* albedo; int ax, ay, az;
+    sdfrt_tracer_params tracer;
+    sdfrt_warp_params warp;
+    sdfrt_sensor sensor;
+    sdfrt_shading shading;
+    int integrator;
+};
+
+extern "C" {
+
+void cp_defaults(cp_scene* h) {
+    std::memset(h, 0, sizeof(*h));
+    tracer_defaults(&h->tracer); warp_defaults(&h->warp); sensor_defaults(&h->sensor); shading_defaults(&h->shading);
+    h->integrator = INTEGRATOR_DIRECT;
+}
+
+int cp_threads() { return omp_get_max_threads(); }
+
+// Times `n_primal` primal lanes (seed, spp*mult) and `n_adjoint` adjoint lanes (forward with the differentiable tracer +
+// closed-form backward with grad_image = 1) taken from the middle of the respective wavefronts.
+// out[0] = seconds primal, out[1] = seconds adjoint, out[2] = value evals, out[3] = hess evals
+int cp_time_sample(const cp_scene* h, unsigned seed, int spp_primal, int spp_adjoint, long long n_primal, long long n_adjoint,
+                   float* grad_sdf /* rz*ry*rx, accumulated */, double* out) {
+    SceneParams sc;
+    std::memset(&sc, 0, sizeof(sc));
+    sc.G.data = h->sdf; sc.G.rx = h->rx; sc.G.ry = h->ry; sc.G.rz = h->rz;
+    sc.A.data = h->albedo; sc.A.rx = h->ax; sc.A.ry = h->ay; sc.A.rz = h->az;
+    sc.A.cr = h->shading.albedo[0]; sc.A.cg = h->shading.albedo[1]; sc.A.cb = h->shading.albedo[2];
+    sc.T = make_tracer(h->tracer); sc.W = make_warp(h->warp); sc.S = make_sensor(h->sensor); sc.Sh = make_shading(h->shading);
+    sc.integrator = h->integrator;
+    const size_t nf = (size_t)(sc.S.W + 2 * sc.S.border) * (sc.S.H + 2 * sc.S.border) * 4;
+    std::vector<float> film(nf, 0.f), film_adj(nf, 0.f);
+    double nv = 0, nh = 0;
+    // ---- primal sample
+    PassParams pp = make_pass(sc.S, seed, spp_primal, 0, 1);
+    long long lo = (long long)((pp.lane_end - pp.lane_begin) / 2) - n_primal / 2;
+    if (lo < 0) lo = 0;
+    auto t0 = std::chrono::steady_clock::now();
+#pragma omp parallel for schedule(dynamic, 512) reduction(+ : nv, nh)
+    for (long long l = lo; l < lo + n_primal; ++l) {
+        LaneStats st = {0, 0, 0, 0, 0, 0, 0};
+        lane_forward<false>(sc, pp, (unsigned long long)l, film.data(), nullptr, 0, st);
+        nv += st.n_value; nh += st.n_hess;
+    }
+    auto t1 = std::chrono::steady_clock::now();
+    // ---- adjoint sample: forward (records) + backward
+    PassParams pa = make_pass(sc.S, seed + 13, spp_adjoint, 0, 1);
+    long long la = (long long)((pa.lane_end - pa.lane_begin) / 2) - n_adjoint / 2;
+    if (la < 0) la = 0;
+    PassParams sub = pa;
+    sub.lane_begin = (unsigned long long)la;
+    sub.lane_end = (unsigned long long)(la + n_adjoint);
+    std::vector<float> rec((size_t)REC_COUNT * (size_t)n_adjoint, 0.f);
+    std::fill(film.begin(), film.end(), 0.f);
+#pragma omp parallel for schedule(dynamic, 512) reduction(+ : nv, nh)
+    for (long long l = la; l < la + n_adjoint; ++l) {
+        LaneStats st = {0, 0, 0, 0, 0, 0, 0};
+        lane_forward<true>(sc, sub, (unsigned long long)l, film.data(), rec.data(), (unsigned long long)n_adjoint, st);
+        nv += st.n_value; nh += st.n_hess;
+    }
+    const int Wb = sc.S.W + 2 * sc.S.border, Hb = sc.S.H + 2 * sc.S.border;
+    for (int i = 0; i < Wb * Hb; ++i) {  // grad_image = 1 (figures/benchmark/benchmark.py:44)
+        const float* a = film.data() + (size_t)i * 4;
+        if (a[3] == 0.f) continue;
+        const float iw = 1.f / a[3];
+        float* o = film_adj.data() + (size_t)i * 4;
+        o[0] = o[1] = o[2] = iw;
+        o[3] = -(a[0] + a[1] + a[2]) * iw * iw;
+    }
+    BackwardTargets tg; tg.grad_sdf = grad_sdf; tg.grad_albedo = nullptr;
+#pragma omp parallel for schedule(dynamic, 512) reduction(+ : nh)
+    for (long long l = la; l < la + n_adjoint; ++l) {
+        LaneStats st = {0, 0, 0, 0, 0, 0, 0};
+        V3 gp = v3(0.f);
+        lane_backward(sc, sub, (unsigned long long)l, film_adj.data(), rec.data() + (l - la), (unsigned long long)n_adjoint, tg, gp, st);
+        nh += st.n_hess;
+    }
+    auto t2 = std::chrono::steady_clock::now();
+    out[0] = std::chrono::duration<double>(t1 - t0).count();
+    out[1] = std::chrono::duration<double>(t2 - t1).count();
+    out[2] = nv; out[3] = nh;
+    return 0;
+}
+}

@@ -1,0 +1,55 @@
+"""ctypes driver of oracle/cpu_port.cpp (compiled, all-cores CPU build of the per-lane restatement).
+Bench infrastructure only (bench.py `cpu_baseline` and `--impl reference`)."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+SRC = os.path.join(HERE, 'cpu_port.cpp')
+LIB = os.path.join(HERE, 'libsdfrt_cpu_port.so')
+FLAGS = ['-O3', '-march=x86-64-v3', '-fopenmp', '-std=c++17', '-fPIC', '-shared', '-x', 'c++']
+
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+from hostmath import SensorParams, ShadingParams, TracerParams, WarpParams  # noqa: E402  (same public structs)
+
+
+class CPScene(C.Structure):
+    _fields_ = [('sdf', C.c_void_p), ('rx', C.c_int), ('ry', C.c_int), ('rz', C.c_int),
+                ('albedo', C.c_void_p), ('ax', C.c_int), ('ay', C.c_int), ('az', C.c_int),
+                ('tracer', TracerParams), ('warp', WarpParams), ('sensor', SensorParams), ('shading', ShadingParams),
+                ('integrator', C.c_int)]
+
+
+def build():
+    deps = [SRC] + [os.path.join(ROOT, 'differentiable-sdf-rendering_b200', 'csrc', f)
+                    for f in ('sdfrt_core.cuh', 'sdfrt_lane.cuh', 'sdfrt_params.h')]
+    if os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in deps):
+        return LIB
+    subprocess.check_call(['g++'] + FLAGS + [SRC, '-o', LIB])
+    return LIB
+
+
+def time_sample(sdf, albedo, to_world, W, H, seed, spp_primal, spp_adjoint, n_primal, n_adjoint):
+    """Returns dict(seconds_primal, seconds_adjoint, rays, threads)."""
+    lib = C.CDLL(build())
+    sc = CPScene()
+    lib.cp_defaults(C.byref(sc))
+    sdf = np.ascontiguousarray(sdf, dtype=np.float32)
+    sc.sdf = sdf.ctypes.data
+    sc.rz, sc.ry, sc.rx = sdf.shape
+    if albedo is not None:
+        albedo = np.ascontiguousarray(albedo, dtype=np.float32)
+        sc.albedo = albedo.ctypes.data
+        sc.az, sc.ay, sc.ax = albedo.shape[:3]
+    sc.sensor.to_world[:] = [float(v) for v in np.asarray(to_world, dtype=np.float64).reshape(-1)]
+    sc.sensor.width, sc.sensor.height = W, H
+    grad = np.zeros_like(sdf)
+    out = np.zeros(4, dtype=np.float64)
+    lib.cp_time_sample(C.byref(sc), C.c_uint(seed), spp_primal, spp_adjoint, C.c_longlong(n_primal), C.c_longlong(n_adjoint),
+                       grad.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    return dict(seconds_primal=out[0], seconds_adjoint=out[1], rays=n_primal + n_adjoint, threads=lib.cp_threads(),
+                evals=out[2] + out[3], grad_abs_max=float(np.abs(grad).max()))

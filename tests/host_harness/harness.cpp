@@ -126,7 +126,7 @@ int hh_backward(const hh_scene* h, unsigned seed, int spp, const float* film, co
     LaneStats st = {0, 0, 0, 0, 0, 0, 0};
     V3 gp = v3(0.f);
     const unsigned long long n = ps.lane_end - ps.lane_begin;
-    for (unsigned long long lane = ps.lane_begin; lane < ps.lane_end; ++lane) lane_backward(sc, ps, lane, adj.data(), rec, n, tg, gp, st);
+    for (unsigned long long lane = ps.lane_begin; lane < ps.lane_end; ++lane) lane_backward(sc, ps, lane, adj.data(), rec + (lane - ps.lane_begin), n, tg, gp, st);
     if (grad_p) { grad_p[0] += gp.x; grad_p[1] += gp.y; grad_p[2] += gp.z; }
     if (stats) { stats[0] = n; stats[3] = st.n_hess; stats[4] = st.n_sites; }
     return 0;
@@ -138,4 +138,39 @@ unsigned long long hh_local_lanes(const hh_scene* h, int spp, int rank, int worl
     PassParams ps = make_pass(S, 0, spp, rank, world);
     return ps.lane_end - ps.lane_begin;
 }
+}
+
+// ---- developer statistics: how the march spends its evaluations (guides kernel design, not a test) ----
+extern "C" int hh_march_profile(const hh_scene* h, unsigned seed, int spp, int stride, double* out) {
+    SceneParams sc = build(h);
+    PassParams ps = make_pass(sc.S, seed, spp, 0, 1);
+    double n_rays = 0, n_evals = 0, n_interior = 0, n_same_cell = 0, n_refine = 0, n_hit = 0, n_same_cell_refine = 0, n_x_aligned = 0;
+    for (unsigned long long lane = ps.lane_begin; lane < ps.lane_end; lane += stride) {
+        CameraSample cs = camera_sample(sc, ps, lane);
+        Segment s;
+        bool active = segment_begin(s, sc.T, cs.o, cs.d, cs.maxt);
+        CellCoord prev; prev.ix = -1000; prev.iy = prev.iz = 0;
+        n_rays += 1;
+        while (active) {
+            V3 x = s.o + s.t * s.d;
+            CellCoord c = cell_coord(sc.G, x);
+            n_evals += 1; n_interior += c.interior; n_x_aligned += ((c.ix & 3) == 0);
+            n_same_cell += (c.ix == prev.ix && c.iy == prev.iy && c.iz == prev.iz);
+            prev = c;
+            active = value_step(s, sc.T, eval_value(sc.G, x));
+        }
+        if (isfinite(s.its_t)) {
+            n_hit += 1;
+            s.i = 0; bool refining = true;
+            while (refining) {
+                V3 x = s.o + s.its_t * s.d;
+                CellCoord c = cell_coord(sc.G, x);
+                n_refine += 1; n_same_cell_refine += (c.ix == prev.ix && c.iy == prev.iy && c.iz == prev.iz);
+                prev = c;
+                refining = refine_step(s, eval_value(sc.G, x));
+            }
+        }
+    }
+    out[0] = n_rays; out[1] = n_evals; out[2] = n_interior; out[3] = n_same_cell; out[4] = n_refine; out[5] = n_hit; out[6] = n_same_cell_refine; out[7] = n_x_aligned;
+    return 0;
 }
