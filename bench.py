@@ -35,7 +35,6 @@ def parse():
     ap.add_argument('--impl', default='sdfrt', choices=['sdfrt', 'reference'])
     ap.add_argument('--workload', default='c3_blobs256_tex_512x512_64spp', choices=list(WORKLOADS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--cpu-sample-lanes', type=int, default=0, help='lanes per pass of the CPU sample (0 = auto)')
     return ap.parse_args()
 
 
@@ -80,77 +79,70 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the oracle (restated reference) on a bounded sample of the same workload
+# CPU arm: the compiled all-cores CPU port of the restated reference (oracle/cpu_port.cpp) on a bounded sample
 # ------------------------------------------------------------------------------------------------
-def build_oracle_scene(wl, dtype):
-    import numpy as np
-    import torch
-    from oracle import sdf_oracle as O
-    kind, R, AR, W, H, spp, mult, nsens = WORKLOADS[wl]
-    origins = O.regular_camera_origins(nsens)
-    sensor = O.Sensor(to_world=O.look_at(origins[0], [0.5, 0.5, 0.5], [0, 1, 0]), width=W, height=H)
-    sys.path.insert(0, ROOT)
-    import sdfrt.synthetic as syn
-    sdf = O.Grid3d(syn.make_sdf_device(kind, R, 'cpu').to(dtype))
-    alb = None if AR is None else torch.from_numpy(syn.make_albedo_grid(AR)).to(dtype)
-    sc = O.Scene(sdf=sdf, sensor=sensor, albedo_grid=alb)
-    wf = O.WarpField2D(sdf, weight_strategy=6, edge_eps=0.01)
-    wf.clamping_thresh = 0.05
-    return O, sc, wf
+_CPU_SCENE = {}
 
 
-def cpu_sample_pass(O, sc, wf, wl, lanes, seed):
-    """One bounded sample: `lanes` primal lanes + `lanes//mult` adjoint lanes (same 4:1 ratio as the workload),
-    taken from the middle of the wavefront (object-covering rows).  Returns (rays, seconds)."""
-    import torch
+def cpu_scene(wl):
+    if wl not in _CPU_SCENE:
+        import sdfrt
+        import sdfrt.synthetic as syn
+        kind, R, AR, W, H, spp, mult, nsens = WORKLOADS[wl]
+        sdf = syn.make_sdf_device(kind, R, 'cpu').numpy()
+        alb = None if AR is None else syn.make_albedo_grid(AR)
+        cam = sdfrt.get_regular_cameras(nsens, resx=W, resy=H)[0]
+        _CPU_SCENE[wl] = (sdf, alb, cam.to_world)
+    return _CPU_SCENE[wl]
+
+
+def cpu_sample(wl, n_primal, seed):
+    """`n_primal` primal + n_primal/mult adjoint lanes (the workload's 4:1 ratio) from the centre of the wavefronts."""
+    from oracle import cpu_port
     kind, R, AR, W, H, spp, mult, nsens = WORKLOADS[wl]
-    b = sc.sensor.border
-    wf_p = (W + 2 * b) * (H + 2 * b) * spp * mult
-    wf_a = (W + 2 * b) * (H + 2 * b) * spp
-    n_a = max(spp, lanes // mult)
-    t0 = time.perf_counter()
-    lo = wf_p // 2 - lanes // 2
-    with torch.no_grad():
-        O.render(sc, wf, 'sdf_direct_reparam', seed, spp * mult, lane_range=(lo, lo + lanes), develop=False)
-    lo = wf_a // 2 - n_a // 2
-    sdf = sc.sdf
-    d0, a0 = sdf.data, sc.albedo_grid
-    sdf.data = d0.detach().clone().requires_grad_(True)
-    if a0 is not None:
-        sc.albedo_grid = a0.detach().clone().requires_grad_(True)
-    try:
-        acc = O.render(sc, wf, 'sdf_direct_reparam', seed + 13, spp, mode_backward=True, lane_range=(lo, lo + n_a), develop=False)
-        loss = (acc[..., :3] / acc[..., 3:4].clamp_min(1e-3)).sum()
-        loss.backward()
-    finally:
-        sdf.data, sc.albedo_grid = d0, a0
-    return lanes + n_a, time.perf_counter() - t0
+    sdf, alb, tw = cpu_scene(wl)
+    r = cpu_port.time_sample(sdf, alb, tw, W, H, seed, spp * mult, spp, n_primal, max(spp, n_primal // mult))
+    r['seconds'] = r['seconds_primal'] + r['seconds_adjoint']
+    return r
+
+
+def cpu_calibrated_sample(wl, target_s, seed=100):
+    kind, R, AR, W, H, spp, mult, nsens = WORKLOADS[wl]
+    full = (W + 4) * (H + 4) * spp * mult
+    probe = cpu_sample(wl, min(full, 1 << 19), seed)
+    rate = probe['rays'] / probe['seconds']
+    n = int(min(full, max(1 << 19, target_s * rate * mult / (mult + 1))))
+    return n, cpu_sample(wl, n, seed)
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation = the oracle port (Mitsuba/Dr.Jit cannot be installed)."""
+    """--impl reference: the reference's CPU implementation.  Mitsuba llvm_ad_rgb cannot be installed offline, so this is
+    the compiled CPU port of the restated reference algorithm on all host cores (kind = "port")."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    import torch
     cores = len(os.sched_getaffinity(0))
-    torch.set_num_threads(cores)
-    O, sc, wf = build_oracle_scene(args.workload, torch.float32)
-    lanes = args.cpu_sample_lanes or 65536
-    for w in range(args.warmup):
-        cpu_sample_pass(O, sc, wf, args.workload, max(4096, lanes // 8), w)
+    os.environ.setdefault('OMP_NUM_THREADS', str(cores))
+    wl = args.workload
+    mult = WORKLOADS[wl][6]
+    n, _ = cpu_calibrated_sample(wl, 8.0 / max(1, args.steps))   # also the warm-up
+    for w in range(max(0, args.warmup - 1)):
+        cpu_sample(wl, max(1 << 16, n // 8), w)
     rays = secs = 0.0
+    threads = cores
     for s in range(args.steps):
-        r, t = cpu_sample_pass(O, sc, wf, args.workload, lanes, 100 + s)
-        rays += r
-        secs += t
+        r = cpu_sample(wl, n, 100 + s)
+        rays += r['rays']
+        secs += r['seconds']
+        threads = r['threads']
     val = rays / secs / 1e6
-    sample = f"{lanes} primal + {lanes // WORKLOADS[args.workload][6]} adjoint lanes per step from the wavefront centre"
+    sample = f"{n} primal + {max(WORKLOADS[wl][5], n // mult)} adjoint lanes per step from the wavefront centre"
     line = {"metric": METRIC, "value": val, "unit": "Mrays/s", "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "note": "oracle port of the reference (Mitsuba llvm_ad_rgb unavailable offline)"},
-            "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
+            "config": {"workload": wl, "note": "compiled CPU port of the restated reference (g++ -O3 -fopenmp); "
+                                               "Mitsuba llvm_ad_rgb is not installable offline"},
+            "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -296,13 +288,11 @@ def run_gpu(args):
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = len(os.sched_getaffinity(0))
-        torch.set_num_threads(cores)
-        O, osc, owf = build_oracle_scene(args.workload, torch.float32)
-        lanes = args.cpu_sample_lanes or 65536
-        cpu_sample_pass(O, osc, owf, args.workload, 8192, 0)
-        r, t = cpu_sample_pass(O, osc, owf, args.workload, lanes, 100)
-        cpu_baseline = {"value": r / t / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
-                        "sample": f"{lanes} primal + {lanes // mult} adjoint lanes from the wavefront centre, {t:.1f} s"}
+        os.environ.setdefault('OMP_NUM_THREADS', str(cores))
+        n, r = cpu_calibrated_sample(args.workload, 12.0)
+        cpu_baseline = {"value": r['rays'] / r['seconds'] / 1e6, "unit": "Mrays/s", "cores": r['threads'], "kind": "port",
+                        "sample": f"{n} primal + {max(spp, n // mult)} adjoint lanes from the wavefront centre, {r['seconds']:.1f} s; "
+                                  "compiled CPU port (g++ -O3 -fopenmp) of the restated reference"}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

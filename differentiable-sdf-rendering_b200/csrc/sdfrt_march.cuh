@@ -124,6 +124,67 @@ __device__ __forceinline__ void splat(const SensorParams& S, float* film, float 
     }
 }
 
+// Warp-cooperative splat.  The 32 lanes of a warp hold consecutive work items, i.e. samples of one pixel (or of a few
+// vertically adjacent pixels), so their filter footprints fall into one small window of the film.  Instead of
+// 32 x ~16 x 4 same-address atomics, every lane publishes its separable filter weights in shared memory and the window's
+// cells are summed "transposed" (one cell per lane, loop over the 32 samples), leaving <= 64 x 4 atomics per warp.
+// Must be called by all 32 lanes; falls back to per-lane atomics when the window is larger than 8 x 8 pixels.
+struct SplatSmem {
+    float fx[32][8];
+    float fy[32][8];
+    float4 c[32];
+};
+__device__ __forceinline__ void warp_splat(const SensorParams& S, float* film, SplatSmem& sm, bool active, float pfx, float pfy, V3 rgb) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane_id = threadIdx.x & 31;
+    const float rad = S.filter_radius;
+    int x0 = 0x7fffffff, y0 = 0x7fffffff, x1 = -0x7fffffff, y1 = -0x7fffffff;
+    if (active) {
+        x0 = (int)ceilf(pfx - rad); y0 = (int)ceilf(pfy - rad);
+        x1 = (int)floorf(pfx + rad); y1 = (int)floorf(pfy + rad);
+    }
+    int wx0 = x0, wy0 = y0, wx1 = x1, wy1 = y1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        wx0 = min(wx0, __shfl_xor_sync(FULL, wx0, o)); wy0 = min(wy0, __shfl_xor_sync(FULL, wy0, o));
+        wx1 = max(wx1, __shfl_xor_sync(FULL, wx1, o)); wy1 = max(wy1, __shfl_xor_sync(FULL, wy1, o));
+    }
+    if (wx1 < wx0) return;  // no active lane
+    const int Wx = wx1 - wx0 + 1, Wy = wy1 - wy0 + 1;
+    if (Wx > 8 || Wy > 8) {
+        if (active) splat(S, film, pfx, pfy, rgb);
+        return;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int bx = wx0 + i, by = wy0 + i;
+        sm.fx[lane_id][i] = (active && bx >= x0 && bx <= x1) ? filter_eval(S, (float)bx - pfx) : 0.f;
+        sm.fy[lane_id][i] = (active && by >= y0 && by <= y1) ? filter_eval(S, (float)by - pfy) : 0.f;
+    }
+    sm.c[lane_id] = make_float4(rgb.x, rgb.y, rgb.z, active ? 1.f : 0.f);
+    __syncwarp();
+    const int Wb = S.W + 2 * S.border, Hb = S.H + 2 * S.border;
+    for (int cell = lane_id; cell < Wx * Wy; cell += 32) {
+        const int cy = cell / Wx, cx = cell - cy * Wx;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+        for (int s = 0; s < 32; ++s) {
+            const float w = sm.fx[s][cx] * sm.fy[s][cy];
+            const float4 c = sm.c[s];
+            acc.x += w * c.x; acc.y += w * c.y; acc.z += w * c.z; acc.w += w * c.w;
+        }
+        const int bx = wx0 + cx, by = wy0 + cy;
+        if (bx >= 0 && bx < Wb && by >= 0 && by < Hb && acc.w != 0.f) {
+            float* px = film + ((size_t)by * Wb + bx) * 4;
+            if (acc.x != 0.f) atomicAdd(px + 0, acc.x);
+            if (acc.y != 0.f) atomicAdd(px + 1, acc.y);
+            if (acc.z != 0.f) atomicAdd(px + 2, acc.z);
+            atomicAdd(px + 3, acc.w);
+        }
+    }
+    __syncwarp();
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // k_march: persistent sphere tracer over segments
 // ---------------------------------------------------------------------------------------------------------------
@@ -283,12 +344,15 @@ __global__ void __launch_bounds__(256) k_shade(const __grid_constant__ ScenePara
                                                 unsigned long long item0, unsigned n, const float* __restrict__ its,
                                                 ShadowQueue q, unsigned* __restrict__ shadow_count, float* __restrict__ film,
                                                 float* __restrict__ rec_state, Counters* __restrict__ counters) {
+    __shared__ SplatSmem s_splat[8];
     const unsigned i = blockIdx.x * 256u + threadIdx.x;
     const bool live = i < n;
     bool push = false;
     SegIn sseg;
     float4 info = make_float4(0.f, 0.f, 0.f, 0.f);
     unsigned n_grad = 0, n_alb = 0, n_hit = 0;
+    float pfx = 0.f, pfy = 0.f;
+    V3 rgb_out = v3(0.f);
     if (live) {
         const float its_t = its[i];
         const bool hit = isfinite(its_t);
@@ -326,8 +390,9 @@ __global__ void __launch_bounds__(256) k_shade(const __grid_constant__ ScenePara
             }
         }
         if (DIFF) rec_state[i] = 0.f;
-        if (!push) splat(sc.S, film, r.pfx, r.pfy, rgb);
+        pfx = r.pfx; pfy = r.pfy; rgb_out = rgb;
     }
+    warp_splat(sc.S, film, s_splat[threadIdx.x >> 5], live && !push, pfx, pfy, rgb_out);
     // compacted push, one atomic per warp
     const unsigned FULL = 0xffffffffu;
     const unsigned m = __ballot_sync(FULL, push);
@@ -365,20 +430,27 @@ __global__ void __launch_bounds__(256) k_shadow_splat(const __grid_constant__ Sc
                                                        const float* __restrict__ srec, unsigned long long srec_stride,
                                                        float* __restrict__ film, float* __restrict__ rec,
                                                        unsigned long long rec_stride) {
+    __shared__ SplatSmem s_splat[8];
     const unsigned j = blockIdx.x * 256u + threadIdx.x;
-    if (j >= *shadow_count) return;
-    const float4 inf = info[j];
-    const unsigned i = __float_as_uint(inf.w);
-    const float its_s = DIFF ? srec[j] : s_its[j];
-    const bool occluded = isfinite(its_s);
-    const ItemRay r = item_ray(sc, ps, item0 + i);
-    splat(sc.S, film, r.pfx, r.pfy, occluded ? v3(0.f) : V3{inf.x, inf.y, inf.z});
-    if (DIFF && !occluded) {
-        float* d = rec + i;
-        d[REC_S_STATE * rec_stride] = 1.f;
+    const bool live = j < *shadow_count;
+    float pfx = 0.f, pfy = 0.f;
+    V3 rgb = v3(0.f);
+    if (live) {
+        const float4 inf = info[j];
+        const unsigned i = __float_as_uint(inf.w);
+        const float its_s = DIFF ? srec[j] : s_its[j];
+        const bool occluded = isfinite(its_s);
+        const ItemRay r = item_ray(sc, ps, item0 + i);
+        pfx = r.pfx; pfy = r.pfy;
+        if (!occluded) rgb = V3{inf.x, inf.y, inf.z};
+        if (DIFF && !occluded) {
+            float* d = rec + i;
+            d[REC_S_STATE * rec_stride] = 1.f;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) d[(REC_S_TAU + k) * rec_stride] = srec[(1 + k) * srec_stride + j];
+            for (int k = 0; k < 8; ++k) d[(REC_S_TAU + k) * rec_stride] = srec[(1 + k) * srec_stride + j];
+        }
     }
+    warp_splat(sc.S, film, s_splat[threadIdx.x >> 5], live, pfx, pfy, rgb);
 }
 
 }  // namespace sdfrt
