@@ -25,6 +25,8 @@ WORKLOADS = {
     'c4_blobs512_512x512_64spp': ('blobs', 512, None, 512, 512, 64, 4, 12),
 }
 METRIC = "primary+adjoint Mrays/s"
+# dram__bytes_read+write of the k_march launches of one c3 step, from the committed ncu capture (profiles/); None = not captured
+NCU_DRAM_BYTES_PER_STEP = None
 
 
 def parse():
@@ -222,6 +224,8 @@ def run_gpu(args):
         step(0, w * (1 + nsens), False)
     torch.cuda.synchronize(dev)
     ctx.stats(reset=True)
+    ctx.set_profiling(True)
+    ctx.timing()
     if world > 1:
         dist.barrier()
     t0 = torch.cuda.Event(enable_timing=True)
@@ -241,13 +245,19 @@ def run_gpu(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     ms = tt.item()
     stats = ctx.stats(reset=True)
+    ctx.set_profiling(False)
     rays_per_step = n_primal + n_adj
     value = rays_per_step * args.steps / (ms * 1e-3) / 1e6
 
-    # per-kernel timings (this rank) and the roofline of the dominant kernel
+    # per-kernel timings (this rank; CUDA events recorded by the library on the launching stream, inside the timed
+    # region) and the roofline of the dominant kernel
     t_primal = sum(ev['p0'][i].elapsed_time(ev['p1'][i]) for i in range(args.steps)) / args.steps
     t_accum = sum(ev['a0'][i].elapsed_time(ev['a1'][i]) for i in range(args.steps)) / args.steps
     t_back = sum(ev['a1'][i].elapsed_time(ev['b1'][i]) for i in range(args.steps)) / args.steps
+    kt = ctx.timing()
+    kernel_ms = {k: v[0] / args.steps for k, v in kt.items()}
+    kernel_ms['k_march (primary+shadow segments)'] = kernel_ms.pop('march_primary') + kernel_ms.pop('march_shadow')
+    launches_per_step = sum(v[1] for v in kt.values()) / args.steps
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
@@ -255,17 +265,19 @@ def run_gpu(args):
         pass
     peak = float(peaks.get('hbm_gbs', 6650.0))
     peak_src = 'measured' if 'hbm_gbs' in peaks else 'fallback'
-    # algorithmic bytes: 256 B per 64-tap evaluation (+ 2x256 B per adjoint scatter site), this rank, per step
-    ev_bytes = 256.0 * (stats['n_evals_value'] + stats['n_evals_grad'] + stats['n_evals_hess']) / args.steps
-    sc_bytes = 512.0 * stats['n_scatter_sites'] / args.steps
-    kernels = {'k_forward<primal>': t_primal, 'k_forward<diff>': t_accum, 'k_backward': t_back}
-    dom = max(kernels, key=kernels.get)
-    alg_bytes = ev_bytes + sc_bytes
-    achieved = alg_bytes / ((t_primal + t_accum + t_back) * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": peak_src, "dominant_kernel": dom,
-                "kernel_ms": kernels, "algorithmic_bytes_per_step": alg_bytes,
-                "note": "fetch-level bytes (256 B per B-spline evaluation); the 256^3 grid is L2-resident, see DESIGN.md"}
+    dom = max(kernel_ms, key=kernel_ms.get)
+    # algorithmic bytes of k_march: one 4x4x4 fp32 neighbourhood = 256 B per B-spline evaluation it performs
+    march_evals = (stats['n_evals_value'] + stats['n_evals_hess']) / args.steps
+    march_bytes = 256.0 * march_evals
+    march_ms = kernel_ms['k_march (primary+shadow segments)']
+    achieved = march_bytes / (march_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": NCU_DRAM_BYTES_PER_STEP, "peak_source": peak_src, "kernel": "k_march (all launches of one step)",
+                "dominant_kernel": dom, "kernel_ms_per_step": kernel_ms, "pass_ms": {"primal": t_primal, "adjoint_accumulate": t_accum,
+                                                                                  "adjoint_backprop": t_back},
+                "algorithmic_bytes_per_step": march_bytes, "evals_per_step": march_evals,
+                "note": "fetch-level bytes: 256 B per B-spline evaluation; the SDF grid is L2-resident at <= 256^3, so the fetches are "
+                        "served by L1/L2 and frac can exceed 1; `traffic` is the ncu dram__bytes of the same launches (profiles/)"}
 
     # e2e through the host-buffer C-ABI entry point (single GPU): H2D sdf + D2H image + grad every step
     e2e = None
@@ -301,7 +313,7 @@ def run_gpu(args):
                 "config": {"workload": args.workload, "sdf_res": R, "albedo_res": AR, "film": [W, H], "spp_primal": spp * mult,
                            "spp_adjoint": spp, "rays_per_step": rays_per_step, "partition": f"film rows x{world}",
                            "l2": "inputs (sdf+albedo+grads+lane records > 1 GB) exceed L2; no explicit flush"},
-                "clocks": clk.summary(), "e2e": e2e, "gpu_launches": 5 * args.steps,
+                "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(round(launches_per_step * args.steps)),
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "stats_per_step": {k: v / args.steps for k, v in stats.items()}}
         print(json.dumps(line))
     if world > 1:

@@ -36,7 +36,7 @@ class ShadingParams(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [(k, C.c_uint64) for k in ('n_rays', 'n_evals_value', 'n_evals_grad', 'n_evals_hess', 'n_scatter_sites',
-                                          'n_albedo_lookups', 'n_steps_max', 'n_hits')]
+                                          'n_albedo_lookups', 'n_steps_max', 'n_hits', 'n_evals_adjoint', 'n_tap_loads', 'n_launches')]
 
     def as_dict(self):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}
@@ -73,6 +73,8 @@ SIGNATURES = {
     'sdfrt_adjoint_accumulate': (C.c_int, [_P, C.c_uint32, C.c_int, _P, _P]),
     'sdfrt_adjoint_backprop': (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
     'sdfrt_get_stats': (C.c_int, [_P, C.POINTER(Stats), C.c_int, _P]),
+    'sdfrt_set_profiling': (C.c_int, [_P, C.c_int]),
+    'sdfrt_get_timing': (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     'sdfrt_trace_rays': (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.POINTER(RayOut), _P]),
     'sdfrt_eval_sdf': (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
     'sdfrt_render_view_host': (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_uint32, C.c_int,

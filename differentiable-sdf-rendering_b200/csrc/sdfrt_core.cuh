@@ -108,7 +108,7 @@ struct ShadingParams {
 };
 struct Counters {  // device work counters (unsigned long long for atomicAdd)
     unsigned long long n_rays, n_evals_value, n_evals_grad, n_evals_hess, n_scatter_sites, n_albedo_lookups,
-        n_steps_max, n_hits;
+        n_steps_max, n_hits, n_evals_adjoint, n_tap_loads;
 };
 
 constexpr float kBBoxDelta = 0.05f;     // python/shapes.py:416-418
@@ -219,57 +219,78 @@ SDFRT_HD void fold_weights(int i, int b, int r, float w[4]) {
     w[0] = f[0]; w[1] = f[1]; w[2] = f[2]; w[3] = f[3];
 }
 
-// ORDER 0: value; 1: + gradient; 2: + Hessian.  Separable evaluation: x-reduction per row,
-// then y, then z (~1/2 the FMAs of the naive 64 x 10 form).
+// A lookup is split in three stages so that the marcher can keep the 64 taps of the current cell across steps:
+//   cell_setup   -> base cell (after clamp folding) + the (folded) B-spline weights of the three axes
+//   load_taps    -> the 4x4x4 block f[(k*4+j)*4+i] = data[bz+k][by+j][bx+i]
+//   reduce_taps  -> separable reduction (x per row, then y, then z: ~1/2 the FMAs of the naive 64 x 10 form)
+// ORDER 0: value; 1: + gradient; 2: + Hessian.
 template <int ORDER>
-SDFRT_HD void eval_sdf(const GridView& G, V3 x, float& v, V3& g, S3& H) {
+struct CellSetup {
+    int bx, by, bz;
+    float wx[4], wy[4], wz[4];
+    float dx[ORDER >= 1 ? 4 : 1], dy[ORDER >= 1 ? 4 : 1], dz[ORDER >= 1 ? 4 : 1];
+    float ex[ORDER >= 2 ? 4 : 1], ey[ORDER >= 2 ? 4 : 1], ez[ORDER >= 2 ? 4 : 1];
+};
+template <int ORDER>
+SDFRT_HD void cell_setup(const GridView& G, V3 x, CellSetup<ORDER>& s) {
     const CellCoord c = cell_coord(G, x);
-    float wx[4], wy[4], wz[4], dx[4], dy[4], dz[4], ex[4], ey[4], ez[4];
-    bspline_w(c.ax, wx); bspline_w(c.ay, wy); bspline_w(c.az, wz);
-    if (ORDER >= 1) { bspline_dw(c.ax, dx); bspline_dw(c.ay, dy); bspline_dw(c.az, dz); }
-    if (ORDER >= 2) { bspline_ddw(c.ax, ex); bspline_ddw(c.ay, ey); bspline_ddw(c.az, ez); }
-    const int bx = fold_base(c.ix, G.rx), by = fold_base(c.iy, G.ry), bz = fold_base(c.iz, G.rz);
+    bspline_w(c.ax, s.wx); bspline_w(c.ay, s.wy); bspline_w(c.az, s.wz);
+    if (ORDER >= 1) { bspline_dw(c.ax, s.dx); bspline_dw(c.ay, s.dy); bspline_dw(c.az, s.dz); }
+    if (ORDER >= 2) { bspline_ddw(c.ax, s.ex); bspline_ddw(c.ay, s.ey); bspline_ddw(c.az, s.ez); }
+    s.bx = fold_base(c.ix, G.rx); s.by = fold_base(c.iy, G.ry); s.bz = fold_base(c.iz, G.rz);
     if (!c.interior) {
-        fold_weights(c.ix, bx, G.rx, wx); fold_weights(c.iy, by, G.ry, wy); fold_weights(c.iz, bz, G.rz, wz);
-        if (ORDER >= 1) { fold_weights(c.ix, bx, G.rx, dx); fold_weights(c.iy, by, G.ry, dy); fold_weights(c.iz, bz, G.rz, dz); }
-        if (ORDER >= 2) { fold_weights(c.ix, bx, G.rx, ex); fold_weights(c.iy, by, G.ry, ey); fold_weights(c.iz, bz, G.rz, ez); }
+        fold_weights(c.ix, s.bx, G.rx, s.wx); fold_weights(c.iy, s.by, G.ry, s.wy); fold_weights(c.iz, s.bz, G.rz, s.wz);
+        if (ORDER >= 1) { fold_weights(c.ix, s.bx, G.rx, s.dx); fold_weights(c.iy, s.by, G.ry, s.dy); fold_weights(c.iz, s.bz, G.rz, s.dz); }
+        if (ORDER >= 2) { fold_weights(c.ix, s.bx, G.rx, s.ex); fold_weights(c.iy, s.by, G.ry, s.ey); fold_weights(c.iz, s.bz, G.rz, s.ez); }
     }
+}
+SDFRT_HD void load_taps(const GridView& G, int bx, int by, int bz, float f[64]) {
     const size_t sy = (size_t)G.rx, sz = (size_t)G.rx * (size_t)G.ry;
     const float* base = G.data + ((size_t)bz * sz + (size_t)by * sy + (size_t)bx);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float* row = base + (size_t)k * sz + (size_t)j * sy;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) f[(k * 4 + j) * 4 + i] = row[i];
+        }
+}
+template <int ORDER>
+SDFRT_HD void reduce_taps(const float f[64], const CellSetup<ORDER>& s, const GridView& G, float& v, V3& g, S3& H) {
     float r_v = 0, r_gx = 0, r_gy = 0, r_gz = 0, r_xx = 0, r_yy = 0, r_zz = 0, r_xy = 0, r_xz = 0, r_yz = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         float A0 = 0, A1 = 0, A2 = 0, B0 = 0, B1 = 0, C0 = 0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const float* row = base + (size_t)k * sz + (size_t)j * sy;
-            const float f0 = row[0], f1 = row[1], f2 = row[2], f3 = row[3];
-            const float a = wx[0] * f0 + wx[1] * f1 + wx[2] * f2 + wx[3] * f3;
-            A0 += wy[j] * a;
+            const float f0 = f[(k * 4 + j) * 4 + 0], f1 = f[(k * 4 + j) * 4 + 1], f2 = f[(k * 4 + j) * 4 + 2], f3 = f[(k * 4 + j) * 4 + 3];
+            const float a = s.wx[0] * f0 + s.wx[1] * f1 + s.wx[2] * f2 + s.wx[3] * f3;
+            A0 += s.wy[j] * a;
             if (ORDER >= 1) {
-                const float b = dx[0] * f0 + dx[1] * f1 + dx[2] * f2 + dx[3] * f3;
-                A1 += dy[j] * a;
-                B0 += wy[j] * b;
+                const float b = s.dx[0] * f0 + s.dx[1] * f1 + s.dx[2] * f2 + s.dx[3] * f3;
+                A1 += s.dy[j] * a;
+                B0 += s.wy[j] * b;
                 if (ORDER >= 2) {
-                    const float cc = ex[0] * f0 + ex[1] * f1 + ex[2] * f2 + ex[3] * f3;
-                    A2 += ey[j] * a;
-                    B1 += dy[j] * b;
-                    C0 += wy[j] * cc;
+                    const float cc = s.ex[0] * f0 + s.ex[1] * f1 + s.ex[2] * f2 + s.ex[3] * f3;
+                    A2 += s.ey[j] * a;
+                    B1 += s.dy[j] * b;
+                    C0 += s.wy[j] * cc;
                 }
             }
         }
-        r_v += wz[k] * A0;
+        r_v += s.wz[k] * A0;
         if (ORDER >= 1) {
-            r_gz += dz[k] * A0;
-            r_gy += wz[k] * A1;
-            r_gx += wz[k] * B0;
+            r_gz += s.dz[k] * A0;
+            r_gy += s.wz[k] * A1;
+            r_gx += s.wz[k] * B0;
             if (ORDER >= 2) {
-                r_zz += ez[k] * A0;
-                r_yz += dz[k] * A1;
-                r_yy += wz[k] * A2;
-                r_xz += dz[k] * B0;
-                r_xy += wz[k] * B1;
-                r_xx += wz[k] * C0;
+                r_zz += s.ez[k] * A0;
+                r_yz += s.dz[k] * A1;
+                r_yy += s.wz[k] * A2;
+                r_xz += s.dz[k] * B0;
+                r_xy += s.wz[k] * B1;
+                r_xx += s.wz[k] * C0;
             }
         }
     }
@@ -282,6 +303,14 @@ SDFRT_HD void eval_sdf(const GridView& G, V3 x, float& v, V3& g, S3& H) {
             H.xy = r_xy * sx * sy_; H.xz = r_xz * sx * sz_; H.yz = r_yz * sy_ * sz_;
         }
     }
+}
+template <int ORDER>
+SDFRT_HD void eval_sdf(const GridView& G, V3 x, float& v, V3& g, S3& H) {
+    CellSetup<ORDER> s;
+    cell_setup<ORDER>(G, x, s);
+    float f[64];
+    load_taps(G, s.bx, s.by, s.bz, f);
+    reduce_taps<ORDER>(f, s, G, v, g, H);
 }
 SDFRT_HD float eval_value(const GridView& G, V3 x) {
     float v; V3 g; S3 H;

@@ -14,6 +14,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <utility>
+#include <vector>
 
 #include "sdfrt_params.h"
 #include "sdfrt_march.cuh"
@@ -24,39 +26,15 @@ namespace {
 
 constexpr int kBlock = 128;
 
-struct DeviceStats {
-    Counters c;
-};
-
 __device__ __forceinline__ unsigned warp_sum(unsigned v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-__device__ __forceinline__ unsigned warp_max(unsigned v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
 __device__ __forceinline__ float warp_sum_f(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
-}
-
-__device__ __forceinline__ void flush_stats(const LaneStats& st, unsigned n_rays, Counters* c) {
-    const unsigned a = warp_sum(st.n_value), b = warp_sum(st.n_grad), h = warp_sum(st.n_hess), s = warp_sum(st.n_sites),
-                   al = warp_sum(st.n_albedo), m = warp_max(st.n_steps_max), hi = warp_sum(st.n_hit), nr = warp_sum(n_rays);
-    if ((threadIdx.x & 31) == 0) {
-        if (nr) atomicAdd(&c->n_rays, (unsigned long long)nr);
-        if (a) atomicAdd(&c->n_evals_value, (unsigned long long)a);
-        if (b) atomicAdd(&c->n_evals_grad, (unsigned long long)b);
-        if (h) atomicAdd(&c->n_evals_hess, (unsigned long long)h);
-        if (s) atomicAdd(&c->n_scatter_sites, (unsigned long long)s);
-        if (al) atomicAdd(&c->n_albedo_lookups, (unsigned long long)al);
-        if (hi) atomicAdd(&c->n_hits, (unsigned long long)hi);
-        atomicMax(&c->n_steps_max, (unsigned long long)m);
-    }
 }
 
 __global__ void __launch_bounds__(kBlock) k_backward(const __grid_constant__ SceneParams sc, const __grid_constant__ PassParams ps,
@@ -71,7 +49,14 @@ __global__ void __launch_bounds__(kBlock) k_backward(const __grid_constant__ Sce
         const WorkItem w = decode_item(sc.S, ps, item);
         lane_backward(sc, ps, w.lane, film_adj, rec + item, rec_stride, tg, gp, st);
     }
-    flush_stats(st, 0u, counters);
+    {   // the adjoint sweep's evaluations are counted separately from the marchers'
+        const unsigned h = warp_sum(st.n_hess), sites = warp_sum(st.n_sites), al = warp_sum(st.n_albedo);
+        if ((threadIdx.x & 31) == 0) {
+            if (h) atomicAdd(&counters->n_evals_adjoint, (unsigned long long)h);
+            if (sites) atomicAdd(&counters->n_scatter_sites, (unsigned long long)sites);
+            if (al) atomicAdd(&counters->n_albedo_lookups, (unsigned long long)al);
+        }
+    }
     if (grad_p != nullptr) {
         const float gx = warp_sum_f(gp.x), gy = warp_sum_f(gp.y), gz = warp_sum_f(gp.z);
         if ((threadIdx.x & 31) == 0) {
@@ -186,11 +171,16 @@ struct sdfrt_ctx {
     size_t film_adj_capacity = 0;
     Counters* counters = nullptr;
     unsigned* work = nullptr;  // WQ_COUNT counters
+    unsigned long long n_launches = 0;
+    bool profiling = false;
+    std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> timed;  // (class, start/stop) of launches not yet collected
+    std::vector<cudaEvent_t> event_pool;
     // per-batch scratch of the wavefront pipeline
-    float *segs = nullptr, *its = nullptr, *ssegs = nullptr, *sinfo = nullptr, *s_its = nullptr, *srec = nullptr;
-    size_t segs_n = 0, its_n = 0, ssegs_n = 0, sinfo_n = 0, s_its_n = 0, srec_n = 0;
+    float *segs = nullptr, *its = nullptr, *ssegs = nullptr, *sinfo = nullptr, *s_its = nullptr, *srec = nullptr, *scount = nullptr;
+    size_t segs_n = 0, its_n = 0, ssegs_n = 0, sinfo_n = 0, s_its_n = 0, srec_n = 0, scount_n = 0;
     int num_sms = 0;
-    int march_blocks[2] = {0, 0};  // resident blocks per SM of k_march<false/true>
+    int march_blocks[6] = {0, 0, 0, 0, 0, 0};  // resident blocks per SM of k_march<DIFF, CACHE> at [3*DIFF + CACHE]
+    int cache_mode[4] = {1, 1, 0, 1};        // tap-cache mode of [value primary, value shadow, diff primary, diff shadow]
     // buffers of the host entry point
     float *h_sdf = nullptr, *h_film = nullptr, *h_image = nullptr, *h_gimg = nullptr, *h_grad = nullptr;
     size_t h_sdf_n = 0, h_film_n = 0, h_image_n = 0, h_grad_n = 0;
@@ -219,6 +209,26 @@ int ensure(sdfrt_ctx* ctx, float** buf, size_t* cap, size_t need) {
     return SDFRT_OK;
 }
 
+// RAII scope around one kernel launch: counts it and, when profiling, brackets it with events on `st`
+struct LaunchScope {
+    sdfrt_ctx* ctx;
+    cudaStream_t st;
+    cudaEvent_t e1 = nullptr;
+    LaunchScope(sdfrt_ctx* c, int cls, cudaStream_t s) : ctx(c), st(s) {
+        ++ctx->n_launches;
+        if (!ctx->profiling) return;
+        cudaEvent_t ev[2];
+        for (int i = 0; i < 2; ++i) {
+            if (!ctx->event_pool.empty()) { ev[i] = ctx->event_pool.back(); ctx->event_pool.pop_back(); }
+            else if (cudaEventCreate(&ev[i]) != cudaSuccess) return;
+        }
+        cudaEventRecord(ev[0], st);
+        e1 = ev[1];
+        ctx->timed.push_back({cls, {ev[0], ev[1]}});
+    }
+    ~LaunchScope() { if (e1) cudaEventRecord(e1, st); }
+};
+
 size_t film_floats(const sdfrt_ctx* ctx) {
     const SensorParams& S = ctx->sc.S;
     return (size_t)(S.W + 2 * S.border) * (size_t)(S.H + 2 * S.border) * 4;
@@ -235,7 +245,24 @@ int check_ready(sdfrt_ctx* ctx, int spp) {
     return SDFRT_OK;
 }
 
-constexpr unsigned long long kMaxBatch = 1ull << 26;  // camera samples per batch of the wavefront pipeline
+constexpr unsigned long long kMaxBatch = 1ull << 26;
+
+template <bool DIFF, int CACHE>
+void launch_march(sdfrt_ctx* ctx, unsigned grid, cudaStream_t st, const SegIn* segs, const unsigned* n_ptr, unsigned n_fixed, int do_refine,
+                  float* out_its, float* rec_out, unsigned long long rec_stride, unsigned* chunk_counter) {
+    k_march<DIFF, CACHE><<<grid, kMarchBlock, 0, st>>>(ctx->sc.G, ctx->sc.T, segs, n_ptr /* region fill or null */, n_fixed /* slots */, do_refine, out_its, rec_out, rec_stride,
+                                                       chunk_counter, ctx->counters);
+}
+template <bool DIFF>
+void launch_march_mode(sdfrt_ctx* ctx, int mode, unsigned need, cudaStream_t st, const SegIn* segs, const unsigned* n_ptr, unsigned n_fixed,
+                       int do_refine, float* out_its, float* rec_out, unsigned long long rec_stride, unsigned* chunk_counter) {
+    const int bps = ctx->march_blocks[(DIFF ? 3 : 0) + mode];
+    unsigned grid = (unsigned)ctx->num_sms * (unsigned)bps;
+    if (grid > need) grid = need;
+    if (mode == 0) launch_march<DIFF, 0>(ctx, grid, st, segs, n_ptr, n_fixed, do_refine, out_its, rec_out, rec_stride, chunk_counter);
+    else if (mode == 1) launch_march<DIFF, 1>(ctx, grid, st, segs, n_ptr, n_fixed, do_refine, out_its, rec_out, rec_stride, chunk_counter);
+    else launch_march<DIFF, 2>(ctx, grid, st, segs, n_ptr, n_fixed, do_refine, out_its, rec_out, rec_stride, chunk_counter);
+}  // camera samples per batch of the wavefront pipeline
 
 template <bool DIFF>
 int launch_forward(sdfrt_ctx* ctx, const PassParams& ps, float* film, cudaStream_t st) {
@@ -247,44 +274,47 @@ int launch_forward(sdfrt_ctx* ctx, const PassParams& ps, float* film, cudaStream
     if ((unsigned long long)kBandRows * (unsigned long long)(S.W + 2 * S.border) * (unsigned long long)ps.spp > 0xffffffffull)
         return fail(ctx, SDFRT_ERR_INVALID, "film row band exceeds 2^32 samples");
     const unsigned long long nbatch = (n + kMaxBatch - 1) / kMaxBatch;
-    const unsigned long long B = (n + nbatch - 1) / nbatch;
+    unsigned long long B = (n + nbatch - 1) / nbatch;
+    B = (B + kRegion - 1) / kRegion * kRegion;  // whole regions per batch
     int rc;
     if ((rc = ensure(ctx, &ctx->segs, &ctx->segs_n, (size_t)B * 8))) return rc;
     if ((rc = ensure(ctx, &ctx->ssegs, &ctx->ssegs_n, (size_t)B * 8))) return rc;
     if ((rc = ensure(ctx, &ctx->sinfo, &ctx->sinfo_n, (size_t)B * 4))) return rc;
+    if ((rc = ensure(ctx, &ctx->scount, &ctx->scount_n, (size_t)(B / kRegion) + 1))) return rc;
     if (DIFF) {
         if ((rc = ensure(ctx, &ctx->srec, &ctx->srec_n, (size_t)B * 9))) return rc;
     } else {
         if ((rc = ensure(ctx, &ctx->its, &ctx->its_n, (size_t)B))) return rc;
         if ((rc = ensure(ctx, &ctx->s_its, &ctx->s_its_n, (size_t)B))) return rc;
     }
-    const unsigned persistent = (unsigned)ctx->num_sms * (unsigned)ctx->march_blocks[DIFF ? 1 : 0];
     ShadowQueue q;
     q.segs = reinterpret_cast<SegIn*>(ctx->ssegs);
     q.info = reinterpret_cast<float4*>(ctx->sinfo);
-    for (unsigned long long b = 0; b < nbatch; ++b) {
-        const unsigned long long item0 = b * B;
+    q.count = reinterpret_cast<unsigned*>(ctx->scount);
+    for (unsigned long long item0 = 0; item0 < n; item0 += B) {
         const unsigned cnt = (unsigned)((n - item0 < B) ? (n - item0) : B);
         const unsigned blocks256 = (cnt + 255u) / 256u;
+        const unsigned regions = (cnt + kRegion - 1) / kRegion;
         SDFRT_CUDA(ctx, cudaMemsetAsync(ctx->work, 0, WQ_COUNT * sizeof(unsigned), st));
-        k_gen_primary<<<blocks256, 256, 0, st>>>(ctx->sc, ps, item0, cnt, reinterpret_cast<SegIn*>(ctx->segs));
+        { LaunchScope ls(ctx, 0, st); k_gen_primary<<<blocks256, 256, 0, st>>>(ctx->sc, ps, item0, cnt, reinterpret_cast<SegIn*>(ctx->segs)); }
         // primary march (+ refine); DIFF writes its_t into row 0 of the lane records
         float* rec_b = DIFF ? ctx->rec + item0 : nullptr;
         const unsigned need = (cnt + kMarchBlock - 1) / kMarchBlock;
-        k_march<DIFF><<<persistent < need ? persistent : need, kMarchBlock, 0, st>>>(
-            ctx->sc.G, ctx->sc.T, reinterpret_cast<const SegIn*>(ctx->segs), nullptr, cnt, 1, ctx->its, rec_b, ctx->rec_stride,
-            ctx->work + WQ_PRIMARY_CHUNK, ctx->counters);
+        { LaunchScope ls(ctx, 1, st);
+          launch_march_mode<DIFF>(ctx, ctx->cache_mode[DIFF ? 2 : 0], need, st, reinterpret_cast<const SegIn*>(ctx->segs), nullptr, cnt, 1,
+                                  ctx->its, rec_b, ctx->rec_stride, ctx->work + WQ_PRIMARY_CHUNK); }
         const float* its = DIFF ? rec_b : ctx->its;
-        k_shade<DIFF><<<blocks256, 256, 0, st>>>(ctx->sc, ps, item0, cnt, its, q, ctx->work + WQ_SHADOW_COUNT, film,
-                                                 DIFF ? rec_b + REC_S_STATE * ctx->rec_stride : nullptr, ctx->counters);
+        { LaunchScope ls(ctx, 2, st);
+          k_shade<DIFF><<<regions, 256, 0, st>>>(ctx->sc, ps, item0, cnt, its, q, film,
+                                                 DIFF ? rec_b + REC_S_STATE * ctx->rec_stride : nullptr, ctx->counters); }
         if (ctx->sc.integrator == INTEGRATOR_DIRECT) {
-            // shadow march over the compacted queue (count read on the device)
-            k_march<DIFF><<<persistent < need ? persistent : need, kMarchBlock, 0, st>>>(
-                ctx->sc.G, ctx->sc.T, reinterpret_cast<const SegIn*>(ctx->ssegs), ctx->work + WQ_SHADOW_COUNT, 0u, 0, ctx->s_its,
-                ctx->srec, B, ctx->work + WQ_SHADOW_CHUNK, ctx->counters);
-            k_shadow_splat<DIFF><<<blocks256, 256, 0, st>>>(ctx->sc, ps, item0, ctx->work + WQ_SHADOW_COUNT,
-                                                            reinterpret_cast<const float4*>(ctx->sinfo), ctx->s_its, ctx->srec, B, film,
-                                                            rec_b, ctx->rec_stride);
+            // shadow march over the region-compacted queue
+            { LaunchScope ls(ctx, 3, st);
+              launch_march_mode<DIFF>(ctx, ctx->cache_mode[DIFF ? 3 : 1], need, st, reinterpret_cast<const SegIn*>(ctx->ssegs), q.count,
+                                      regions * kRegion, 0, ctx->s_its, ctx->srec, B, ctx->work + WQ_SHADOW_CHUNK); }
+            { LaunchScope ls(ctx, 4, st);
+              k_shadow_splat<DIFF><<<regions, 256, 0, st>>>(ctx->sc, ps, item0, q.count, reinterpret_cast<const float4*>(ctx->sinfo),
+                                                            ctx->s_its, ctx->srec, B, film, rec_b, ctx->rec_stride); }
         }
         SDFRT_CUDA(ctx, cudaGetLastError());
     }
@@ -342,9 +372,17 @@ sdfrt_ctx* sdfrt_create(int device, int* status) {
     }
     ctx->num_sms = prop.multiProcessorCount;
     bool ok = cudaMalloc((void**)&ctx->work, WQ_COUNT * sizeof(unsigned)) == cudaSuccess;
-    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->march_blocks[0], k_march<false>, kMarchBlock, 0) == cudaSuccess;
-    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->march_blocks[1], k_march<true>, kMarchBlock, 0) == cudaSuccess;
-    if (!ok || ctx->march_blocks[0] < 1 || ctx->march_blocks[1] < 1) {
+    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->march_blocks[0], k_march<false, 0>, kMarchBlock, 0) == cudaSuccess;
+    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->march_blocks[1], k_march<false, 1>, kMarchBlock, 0) == cudaSuccess;
+    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->march_blocks[2], k_march<false, 2>, kMarchBlock, 0) == cudaSuccess;
+    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->march_blocks[3], k_march<true, 0>, kMarchBlock, 0) == cudaSuccess;
+    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->march_blocks[4], k_march<true, 1>, kMarchBlock, 0) == cudaSuccess;
+    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->march_blocks[5], k_march<true, 2>, kMarchBlock, 0) == cudaSuccess;
+    for (int i = 0; i < 6; ++i) ok = ok && ctx->march_blocks[i] >= 1;
+    if (const char* e = std::getenv("SDFRT_CACHE_MODES")) {  // developer override, e.g. "1102"
+        for (int i = 0; i < 4 && e[i]; ++i) ctx->cache_mode[i] = (e[i] - '0') % 3;
+    }
+    if (!ok) {
         sdfrt_destroy(ctx);
         if (status) *status = SDFRT_ERR_CUDA;
         return nullptr;
@@ -356,11 +394,13 @@ sdfrt_ctx* sdfrt_create(int device, int* status) {
 void sdfrt_destroy(sdfrt_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    for (auto& t : ctx->timed) { cudaEventDestroy(t.second.first); cudaEventDestroy(t.second.second); }
+    for (auto e : ctx->event_pool) cudaEventDestroy(e);
     cudaFree(ctx->rec);
     cudaFree(ctx->film_adj);
     cudaFree(ctx->counters);
     cudaFree(ctx->work);
-    cudaFree(ctx->segs); cudaFree(ctx->its); cudaFree(ctx->ssegs); cudaFree(ctx->sinfo); cudaFree(ctx->s_its); cudaFree(ctx->srec);
+    cudaFree(ctx->segs); cudaFree(ctx->its); cudaFree(ctx->ssegs); cudaFree(ctx->sinfo); cudaFree(ctx->s_its); cudaFree(ctx->srec); cudaFree(ctx->scount);
     cudaFree(ctx->h_sdf); cudaFree(ctx->h_film); cudaFree(ctx->h_image); cudaFree(ctx->h_gimg); cudaFree(ctx->h_grad);
     delete ctx;
 }
@@ -470,7 +510,7 @@ int sdfrt_develop(sdfrt_ctx* ctx, const float* film_accum, float* image, void* s
     SDFRT_CUDA(ctx, cudaSetDevice(ctx->device));
     const SensorParams& S = ctx->sc.S;
     const int n = S.W * S.H;
-    k_develop<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(film_accum, image, S.W, S.H, S.border);
+    { LaunchScope ls(ctx, 7, (cudaStream_t)stream); k_develop<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(film_accum, image, S.W, S.H, S.border); }
     SDFRT_CUDA(ctx, cudaGetLastError());
     return SDFRT_OK;
 }
@@ -503,7 +543,7 @@ int sdfrt_adjoint_backprop(sdfrt_ctx* ctx, const float* film_accum, const float*
     int rc = ensure(ctx, &ctx->film_adj, &ctx->film_adj_capacity, film_floats(ctx));
     if (rc) return rc;
     const int npix = (S.W + 2 * S.border) * (S.H + 2 * S.border);
-    k_film_adjoint<<<(npix + 255) / 256, 256, 0, st>>>(film_accum, grad_image, ctx->film_adj, S.W, S.H, S.border);
+    { LaunchScope ls(ctx, 5, st); k_film_adjoint<<<(npix + 255) / 256, 256, 0, st>>>(film_accum, grad_image, ctx->film_adj, S.W, S.H, S.border); }
     SDFRT_CUDA(ctx, cudaGetLastError());
     const PassParams& ps = ctx->adj_pass;
     const unsigned long long n = ps.lane_end - ps.lane_begin;
@@ -512,7 +552,7 @@ int sdfrt_adjoint_backprop(sdfrt_ctx* ctx, const float* film_accum, const float*
     tg.grad_sdf = grad_sdf;
     tg.grad_albedo = grad_albedo;
     const unsigned long long blocks = (n + kBlock - 1) / kBlock;
-    k_backward<<<(unsigned)blocks, kBlock, 0, st>>>(ctx->sc, ps, ctx->film_adj, ctx->rec, ctx->rec_stride, tg, grad_p, ctx->counters);
+    { LaunchScope ls(ctx, 6, st); k_backward<<<(unsigned)blocks, kBlock, 0, st>>>(ctx->sc, ps, ctx->film_adj, ctx->rec, ctx->rec_stride, tg, grad_p, ctx->counters); }
     SDFRT_CUDA(ctx, cudaGetLastError());
     return SDFRT_OK;
 }
@@ -527,7 +567,36 @@ int sdfrt_get_stats(sdfrt_ctx* ctx, sdfrt_stats* out, int reset, void* stream) {
     out->n_rays = c.n_rays; out->n_evals_value = c.n_evals_value; out->n_evals_grad = c.n_evals_grad;
     out->n_evals_hess = c.n_evals_hess; out->n_scatter_sites = c.n_scatter_sites; out->n_albedo_lookups = c.n_albedo_lookups;
     out->n_steps_max = c.n_steps_max; out->n_hits = c.n_hits;
-    if (reset) SDFRT_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, sizeof(Counters), st));
+    out->n_evals_adjoint = c.n_evals_adjoint;
+    out->n_tap_loads = c.n_tap_loads;
+    out->n_launches = ctx->n_launches;
+    if (reset) {
+        SDFRT_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, sizeof(Counters), st));
+        ctx->n_launches = 0;
+    }
+    return SDFRT_OK;
+}
+
+int sdfrt_set_profiling(sdfrt_ctx* ctx, int enable) {
+    if (!ctx) return SDFRT_ERR_INVALID;
+    ctx->profiling = enable != 0;
+    return SDFRT_OK;
+}
+
+int sdfrt_get_timing(sdfrt_ctx* ctx, float* ms, int* launches) {
+    if (!ctx || !ms || !launches) return SDFRT_ERR_INVALID;
+    SDFRT_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (int i = 0; i < SDFRT_NUM_KERNEL_CLASSES; ++i) { ms[i] = 0.f; launches[i] = 0; }
+    for (auto& t : ctx->timed) {
+        float e = 0.f;
+        SDFRT_CUDA(ctx, cudaEventSynchronize(t.second.second));
+        SDFRT_CUDA(ctx, cudaEventElapsedTime(&e, t.second.first, t.second.second));
+        ms[t.first] += e;
+        launches[t.first] += 1;
+        ctx->event_pool.push_back(t.second.first);
+        ctx->event_pool.push_back(t.second.second);
+    }
+    ctx->timed.clear();
     return SDFRT_OK;
 }
 

@@ -24,12 +24,13 @@
 namespace sdfrt {
 
 constexpr int kMarchBlock = 128;       // threads per block of k_march
-constexpr unsigned kBlockChunk = 1024; // segments a block takes from the global counter at a time
+constexpr unsigned kRegion = 2048;     // segments per region: the unit a marcher block takes from the global counter
+                                       // (= one 8-pixel film column at 256 spp); shadow segments are compacted per region
 constexpr int kMinActive = 24;         // leave the stepping loop when fewer slots are live
 constexpr int kBandRows = 8;
 
 // device work counters of one batch (zeroed before every batch)
-enum { WQ_PRIMARY_CHUNK = 0, WQ_SHADOW_CHUNK = 1, WQ_SHADOW_COUNT = 2, WQ_COUNT = 4 };
+enum { WQ_PRIMARY_CHUNK = 0, WQ_SHADOW_CHUNK = 1, WQ_COUNT = 4 };
 
 // one ray segment ready to march: d normalised; maxt < 0 marks a segment that never enters the bounding box;
 // t0 == 0 <=> origin inside the box (python/shapes.py:141)
@@ -128,10 +129,10 @@ __device__ __forceinline__ void splat(const SensorParams& S, float* film, float 
 // vertically adjacent pixels), so their filter footprints fall into one small window of the film.  Instead of
 // 32 x ~16 x 4 same-address atomics, every lane publishes its separable filter weights in shared memory and the window's
 // cells are summed "transposed" (one cell per lane, loop over the 32 samples), leaving <= 64 x 4 atomics per warp.
-// Must be called by all 32 lanes; falls back to per-lane atomics when the window is larger than 8 x 8 pixels.
+// Must be called by all 32 lanes; falls back to per-lane atomics when the window is larger than 8 x 16 pixels.
 struct SplatSmem {
     float fx[32][8];
-    float fy[32][8];
+    float fy[32][16];
     float4 c[32];
 };
 __device__ __forceinline__ void warp_splat(const SensorParams& S, float* film, SplatSmem& sm, bool active, float pfx, float pfy, V3 rgb) {
@@ -151,14 +152,17 @@ __device__ __forceinline__ void warp_splat(const SensorParams& S, float* film, S
     }
     if (wx1 < wx0) return;  // no active lane
     const int Wx = wx1 - wx0 + 1, Wy = wy1 - wy0 + 1;
-    if (Wx > 8 || Wy > 8) {
+    if (Wx > 8 || Wy > 16) {
         if (active) splat(S, film, pfx, pfy, rgb);
         return;
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const int bx = wx0 + i, by = wy0 + i;
+        const int bx = wx0 + i;
         sm.fx[lane_id][i] = (active && bx >= x0 && bx <= x1) ? filter_eval(S, (float)bx - pfx) : 0.f;
+    }
+    for (int i = 0; i < Wy; ++i) {
+        const int by = wy0 + i;
         sm.fy[lane_id][i] = (active && by >= y0 && by <= y1) ? filter_eval(S, (float)by - pfy) : 0.f;
     }
     sm.c[lane_id] = make_float4(rgb.x, rgb.y, rgb.z, active ? 1.f : 0.f);
@@ -190,45 +194,58 @@ __device__ __forceinline__ void warp_splat(const SensorParams& S, float* film, S
 // ---------------------------------------------------------------------------------------------------------------
 constexpr unsigned long long kQueueExhausted = 0xFFFFFFFFull << 32;
 
-// Leader only.  The block's chunk is one 64-bit shared word (chunk id << 32 | items handed out); a fetch is a single
-// shared atomicAdd.  Returns the number of items taken (>= 0) or -1 when the segment array is exhausted.
-__device__ __forceinline__ int fetch_items(unsigned long long* word, unsigned* chunk_counter, unsigned n_total, int n, unsigned& pos) {
+// Segments live in REGIONS of kRegion slots; region r holds fill(r) valid segments at its start (primary segments: all
+// slots; shadow segments: the count k_shade wrote).  Leader only.  The block's current region is one 64-bit shared word
+// (region id << 32 | slots handed out); a fetch is a single shared atomicAdd.  Returns the number of segments taken
+// (>= 0) or -1 when all regions are exhausted.
+__device__ __forceinline__ unsigned region_fill(const unsigned* region_count, unsigned id, unsigned n_slots) {
+    if (region_count) return region_count[id];
+    const unsigned long long base = (unsigned long long)id * kRegion;
+    return (base + kRegion <= n_slots) ? kRegion : (unsigned)(n_slots - base);
+}
+__device__ __forceinline__ int fetch_items(unsigned long long* word, unsigned* region_counter, const unsigned* region_count,
+                                           unsigned n_slots, int n, unsigned& pos) {
     for (;;) {
         const unsigned long long old = atomicAdd(word, (unsigned long long)n);
         const unsigned id = (unsigned)(old >> 32), off = (unsigned)old;
         if (id == 0xFFFFFFFFu) return -1;
-        if (off < kBlockChunk) {
-            int got = (off + (unsigned)n <= kBlockChunk) ? n : (int)(kBlockChunk - off);
-            if (off + (unsigned)n >= kBlockChunk) {  // this fetch used the chunk up: install the next one
-                const unsigned nid = atomicAdd(chunk_counter, 1u);
-                const unsigned long long nw = ((unsigned long long)nid * kBlockChunk >= n_total) ? kQueueExhausted
-                                                                                              : ((unsigned long long)nid << 32);
+        const unsigned fill = region_fill(region_count, id, n_slots);
+        if (off < fill || (off == 0 && fill == 0)) {
+            int got = (off + (unsigned)n <= fill) ? n : (int)(fill - off);
+            if (off + (unsigned)n >= fill) {  // this fetch used the region up: install the next one
+                const unsigned nid = atomicAdd(region_counter, 1u);
+                const unsigned long long nw = ((unsigned long long)nid * kRegion >= n_slots) ? kQueueExhausted
+                                                                                          : ((unsigned long long)nid << 32);
                 atomicExch(word, nw);
             }
-            const unsigned long long p = (unsigned long long)id * kBlockChunk + off;
-            if (p >= n_total) return 0;
-            pos = (unsigned)p;
-            if (p + (unsigned)got > n_total) got = (int)(n_total - p);
+            pos = id * kRegion + off;
             return got;
         }
-        __nanosleep(40);  // another warp is installing the next chunk
+        __nanosleep(40);  // another warp is installing the next region
     }
 }
 
 enum { SLOT_IDLE = 0, SLOT_MARCH = 1, SLOT_REFINE = 2, SLOT_DONE = 3 };
 
 // rec_out (DIFF): 9 rows [its_t, warp_t, warp_t_d xyz, warp_weight, warp_weight_d xyz] of stride rec_stride.
-template <bool DIFF>
-__global__ void __launch_bounds__(kMarchBlock) k_march(const GridView G, const TracerParams T, const SegIn* __restrict__ segs,
-                                                        const unsigned* __restrict__ n_ptr, unsigned n_fixed, int do_refine,
+// CACHE: 0 = gather every evaluation, 1 = tap cache in registers, 2 = tap cache in shared memory
+template <bool DIFF, int CACHE>
+__global__ void __launch_bounds__(kMarchBlock, DIFF ? (CACHE == 1 ? 3 : 4) : (CACHE == 1 ? 4 : 7)) k_march(const GridView G, const TracerParams T, const SegIn* __restrict__ segs,
+                                                        const unsigned* __restrict__ region_count, unsigned n_slots, int do_refine,
                                                         float* __restrict__ out_its, float* __restrict__ rec_out,
-                                                        unsigned long long rec_stride, unsigned* __restrict__ chunk_counter,
+                                                        unsigned long long rec_stride, unsigned* __restrict__ region_counter,
                                                         Counters* __restrict__ counters) {
     __shared__ unsigned long long s_word;
-    const unsigned n_total = n_ptr ? *n_ptr : n_fixed;
+    // Tap cache: the 4x4x4 block of the cell a slot evaluated last.  Near a surface the sphere-tracing steps are far
+    // smaller than a voxel, so consecutive evaluations mostly fall into the same cell and skip the 64-tap gather.
+    // The value-only marcher keeps the block in registers; the differentiable marcher (register-bound) in shared memory,
+    // laid out [tap][thread] so that every access is conflict free.
+    __shared__ float s_taps[CACHE == 2 ? 64 * kMarchBlock : 1];
+    float taps[CACHE == 1 ? 64 : 1];
+    int tap_key = -1;
     if (threadIdx.x == 0) {
-        const unsigned id = atomicAdd(chunk_counter, 1u);
-        s_word = ((unsigned long long)id * kBlockChunk >= n_total) ? kQueueExhausted : ((unsigned long long)id << 32);
+        const unsigned id = atomicAdd(region_counter, 1u);
+        s_word = ((unsigned long long)id * kRegion >= n_slots) ? kQueueExhausted : ((unsigned long long)id << 32);
     }
     __syncthreads();
     const unsigned FULL = 0xffffffffu;
@@ -241,7 +258,7 @@ __global__ void __launch_bounds__(kMarchBlock) k_march(const GridView G, const T
     DiffAcc acc;
     if (DIFF) { acc.warp_t = 0; acc.prev_surf_dist = 0; acc.weight_sum = 0; acc.extra_weight_sum = 0; acc.prev_sdf_grad_c = v3(0.f);
                 acc.mixed_sum_d = v3(0.f); acc.weight_d_sum = v3(0.f); acc.extra_weight_sum_d = v3(0.f); acc.t_d = v3(0.f); }
-    unsigned n_evals = 0, n_steps_max = 0;
+    unsigned n_evals = 0, n_steps_max = 0, n_loads = 0;
     bool exhausted = false;
 
     while (true) {
@@ -262,7 +279,7 @@ __global__ void __launch_bounds__(kMarchBlock) k_march(const GridView G, const T
         if (idle != 0u && !exhausted) {
             unsigned pos = 0;
             int got = 0;
-            if (lane_id == 0) got = fetch_items(&s_word, chunk_counter, n_total, __popc(idle), pos);
+            if (lane_id == 0) got = fetch_items(&s_word, region_counter, region_count, n_slots, __popc(idle), pos);
             got = __shfl_sync(FULL, got, 0);
             pos = __shfl_sync(FULL, pos, 0);
             if (got < 0) exhausted = true;
@@ -298,14 +315,40 @@ __global__ void __launch_bounds__(kMarchBlock) k_march(const GridView G, const T
                 const V3 x = seg.o + tt * seg.d;
                 ++n_evals;
                 bool cont;
-                if (DIFF) {
-                    float v; V3 g; S3 H;
-                    eval_sdf<2>(G, x, v, g, H);
-                    cont = (state == SLOT_MARCH) ? diff_step(seg, acc, T, v, g, H) : refine_step(seg, v);
+                float v; V3 g; S3 H;
+                constexpr int ORD = DIFF ? 2 : 0;
+                CellSetup<ORD> cs;
+                cell_setup<ORD>(G, x, cs);
+                const int key = (cs.bz * G.ry + cs.by) * G.rx + cs.bx;
+                if constexpr (CACHE == 1) {          // block of the last cell kept in registers
+                    if (key != tap_key) {
+                        load_taps(G, cs.bx, cs.by, cs.bz, taps);
+                        tap_key = key;
+                        ++n_loads;
+                    }
+                    reduce_taps<ORD>(taps, cs, G, v, g, H);
+                } else if constexpr (CACHE == 2) {   // ... in shared memory, [tap][thread]
+                    float f[64];
+                    float* st = s_taps + threadIdx.x;
+                    if (key != tap_key) {
+                        load_taps(G, cs.bx, cs.by, cs.bz, f);
+#pragma unroll
+                        for (int q = 0; q < 64; ++q) st[q * kMarchBlock] = f[q];
+                        tap_key = key;
+                        ++n_loads;
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 64; ++q) f[q] = st[q * kMarchBlock];
+                    }
+                    reduce_taps<ORD>(f, cs, G, v, g, H);
                 } else {
-                    const float v = eval_value(G, x);
-                    cont = (state == SLOT_MARCH) ? value_step(seg, T, v) : refine_step(seg, v);
+                    float f[64];
+                    load_taps(G, cs.bx, cs.by, cs.bz, f);
+                    ++n_loads;
+                    reduce_taps<ORD>(f, cs, G, v, g, H);
                 }
+                if (DIFF) cont = (state == SLOT_MARCH) ? diff_step(seg, acc, T, v, g, H) : refine_step(seg, v);
+                else cont = (state == SLOT_MARCH) ? value_step(seg, T, v) : refine_step(seg, v);
                 if (!cont) {
                     if (state == SLOT_MARCH) {
                         n_steps_max = max(n_steps_max, (unsigned)seg.i);
@@ -323,134 +366,154 @@ __global__ void __launch_bounds__(kMarchBlock) k_march(const GridView G, const T
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         n_evals += __shfl_xor_sync(FULL, n_evals, o);
+        n_loads += __shfl_xor_sync(FULL, n_loads, o);
         n_steps_max = max(n_steps_max, __shfl_xor_sync(FULL, n_steps_max, o));
     }
     if (lane_id == 0) {
         if (n_evals) atomicAdd(DIFF ? &counters->n_evals_hess : &counters->n_evals_value, (unsigned long long)n_evals);
+        if (n_loads) atomicAdd(&counters->n_tap_loads, (unsigned long long)n_loads);
         atomicMax(&counters->n_steps_max, (unsigned long long)n_steps_max);
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// k_shade: <integrator>.sample after the primary intersection (python/integrators/sdf_direct_reparam.py:24-84)
+// k_shade: <integrator>.sample after the primary intersection (python/integrators/sdf_direct_reparam.py:24-84).
+// One block per region of kRegion camera samples (8 iterations of 256).  Shadow segments are written compacted at the
+// start of the block's own region of the shadow arrays, so their order stays the band order of the camera samples (the
+// shadow marcher and the shadow splat then see rays of one 8-pixel film column at a time) and no global atomics or
+// prefix sums are needed.
 // ---------------------------------------------------------------------------------------------------------------
 struct ShadowQueue {
-    SegIn* segs;     // shadow segments
-    float4* info;    // rgb added if unoccluded, item index (bit pattern) in .w
+    SegIn* segs;      // [n_slots] shadow segments, region-compacted
+    float4* info;     // [n_slots] rgb added if unoccluded, item index (bit pattern) in .w
+    unsigned* count;  // [n_regions] valid segments per region
 };
 
 template <bool DIFF>
 __global__ void __launch_bounds__(256) k_shade(const __grid_constant__ SceneParams sc, const __grid_constant__ PassParams ps,
                                                 unsigned long long item0, unsigned n, const float* __restrict__ its,
-                                                ShadowQueue q, unsigned* __restrict__ shadow_count, float* __restrict__ film,
-                                                float* __restrict__ rec_state, Counters* __restrict__ counters) {
+                                                ShadowQueue q, float* __restrict__ film, float* __restrict__ rec_state,
+                                                Counters* __restrict__ counters) {
     __shared__ SplatSmem s_splat[8];
-    const unsigned i = blockIdx.x * 256u + threadIdx.x;
-    const bool live = i < n;
-    bool push = false;
-    SegIn sseg;
-    float4 info = make_float4(0.f, 0.f, 0.f, 0.f);
-    unsigned n_grad = 0, n_alb = 0, n_hit = 0;
-    float pfx = 0.f, pfy = 0.f;
-    V3 rgb_out = v3(0.f);
-    if (live) {
-        const float its_t = its[i];
-        const bool hit = isfinite(its_t);
-        n_hit = hit;
-        const ItemRay r = item_ray(sc, ps, item0 + i);
+    __shared__ unsigned s_count;
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
+    const unsigned FULL = 0xffffffffu;
+    const int lane_id = threadIdx.x & 31;
+    const unsigned region_base = blockIdx.x * kRegion;
+    unsigned n_grad = 0, n_alb = 0, n_hit = 0, n_rays = 0;
+    for (unsigned it = 0; it < kRegion / 256u; ++it) {
+        const unsigned i = region_base + it * 256u + threadIdx.x;
+        if (region_base + it * 256u >= n) break;  // block-uniform
+        const bool live = i < n;
+        bool push = false;
+        SegIn sseg;
+        float4 info = make_float4(0.f, 0.f, 0.f, 0.f);
+        float pfx = 0.f, pfy = 0.f;
         V3 rgb = v3(0.f);
-        if (sc.integrator == INTEGRATOR_SILHOUETTE) {
-            rgb = v3(hit ? 1.f : 0.f);
-        } else if (!hit) {
-            if (sc.integrator == INTEGRATOR_DIRECT && !sc.Sh.hide_emitters) rgb = V3{sc.Sh.Le[0], sc.Sh.Le[1], sc.Sh.Le[2]};
-        } else {
-            const V3 p = r.o + its_t * r.d;
-            float phi; V3 g; S3 H;
-            eval_sdf<1>(sc.G, p, phi, g, H);
-            n_grad = 1;
-            const V3 n = normalize(g);
-            if (sc.integrator == INTEGRATOR_SIMPLE_SHADING) {
-                rgb = v3(fmaxf(0.f, (n.x + n.y + n.z) * 0.57735026918962576f));
+        if (live) {
+            ++n_rays;
+            const float its_t = its[i];
+            const bool hit = isfinite(its_t);
+            n_hit += hit;
+            const ItemRay r = item_ray(sc, ps, item0 + i);
+            pfx = r.pfx; pfy = r.pfy;
+            if (sc.integrator == INTEGRATOR_SILHOUETTE) {
+                rgb = v3(hit ? 1.f : 0.f);
+            } else if (!hit) {
+                if (sc.integrator == INTEGRATOR_DIRECT && !sc.Sh.hide_emitters) rgb = V3{sc.Sh.Le[0], sc.Sh.Le[1], sc.Sh.Le[2]};
             } else {
-                const float cos_i = -dot(n, r.d);
-                Pcg32 rng = sampler_seed(ps.seed, (uint32_t)r.lane);
-                (void)pcg_next_u32(rng); (void)pcg_next_u32(rng); (void)pcg_next_u32(rng);
-                const float u0 = pcg_next_f32(rng), u1 = pcg_next_f32(rng);
-                const ShadowRay sr = make_shadow_ray(sc.Sh, p, n, u0, u1);
-                const float cos_o = dot(n, sr.d);
-                // a shadow ray whose BSDF gate is closed contributes exactly zero whatever it hits: not traced
-                if ((cos_i > 0.f) & (cos_o > 0.f)) {
-                    const V3 rho = eval_albedo(sc.A, p, nullptr, nullptr);
-                    n_alb = (sc.A.data != nullptr);
-                    const float k = cos_o * 4.f;  // (rho / pi) cos_o Le / (1 / 4 pi)
-                    info = make_float4(rho.x * k * sc.Sh.Le[0], rho.y * k * sc.Sh.Le[1], rho.z * k * sc.Sh.Le[2], __uint_as_float(i));
-                    sseg = make_seg(sc.T, sr.o, sr.d, sr.maxt);
-                    push = true;
+                const V3 p = r.o + its_t * r.d;
+                float phi; V3 g; S3 H;
+                eval_sdf<1>(sc.G, p, phi, g, H);
+                ++n_grad;
+                const V3 nrm = normalize(g);
+                if (sc.integrator == INTEGRATOR_SIMPLE_SHADING) {
+                    rgb = v3(fmaxf(0.f, (nrm.x + nrm.y + nrm.z) * 0.57735026918962576f));
+                } else {
+                    const float cos_i = -dot(nrm, r.d);
+                    Pcg32 rng = sampler_seed(ps.seed, (uint32_t)r.lane);
+                    (void)pcg_next_u32(rng); (void)pcg_next_u32(rng); (void)pcg_next_u32(rng);
+                    const float u0 = pcg_next_f32(rng), u1 = pcg_next_f32(rng);
+                    const ShadowRay sr = make_shadow_ray(sc.Sh, p, nrm, u0, u1);
+                    const float cos_o = dot(nrm, sr.d);
+                    // a shadow ray whose BSDF gate is closed contributes exactly zero whatever it hits: not traced
+                    if ((cos_i > 0.f) & (cos_o > 0.f)) {
+                        const V3 rho = eval_albedo(sc.A, p, nullptr, nullptr);
+                        n_alb += (sc.A.data != nullptr);
+                        const float k = cos_o * 4.f;  // (rho / pi) cos_o Le / (1 / 4 pi)
+                        info = make_float4(rho.x * k * sc.Sh.Le[0], rho.y * k * sc.Sh.Le[1], rho.z * k * sc.Sh.Le[2], __uint_as_float(i));
+                        sseg = make_seg(sc.T, sr.o, sr.d, sr.maxt);
+                        push = true;
+                    }
                 }
             }
+            if (DIFF) rec_state[i] = 0.f;
         }
-        if (DIFF) rec_state[i] = 0.f;
-        pfx = r.pfx; pfy = r.pfy; rgb_out = rgb;
-    }
-    warp_splat(sc.S, film, s_splat[threadIdx.x >> 5], live && !push, pfx, pfy, rgb_out);
-    // compacted push, one atomic per warp
-    const unsigned FULL = 0xffffffffu;
-    const unsigned m = __ballot_sync(FULL, push);
-    if (m) {
-        const int lane_id = threadIdx.x & 31;
-        unsigned base = 0;
-        if (lane_id == (__ffs(m) - 1)) base = atomicAdd(shadow_count, (unsigned)__popc(m));
-        base = __shfl_sync(FULL, base, __ffs(m) - 1);
-        if (push) {
-            const unsigned j = base + (unsigned)__popc(m & ((1u << lane_id) - 1u));
-            q.segs[j] = sseg;
-            q.info[j] = info;
+        warp_splat(sc.S, film, s_splat[threadIdx.x >> 5], live && !push, pfx, pfy, rgb);
+        const unsigned m = __ballot_sync(FULL, push);
+        if (m) {
+            unsigned base = 0;
+            if (lane_id == (__ffs(m) - 1)) base = atomicAdd(&s_count, (unsigned)__popc(m));
+            base = __shfl_sync(FULL, base, __ffs(m) - 1);
+            if (push) {
+                const unsigned slot = region_base + base + (unsigned)__popc(m & ((1u << lane_id) - 1u));
+                q.segs[slot] = sseg;
+                q.info[slot] = info;
+            }
         }
     }
+    __syncthreads();
+    if (threadIdx.x == 0) q.count[blockIdx.x] = s_count;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         n_grad += __shfl_xor_sync(FULL, n_grad, o);
         n_alb += __shfl_xor_sync(FULL, n_alb, o);
         n_hit += __shfl_xor_sync(FULL, n_hit, o);
+        n_rays += __shfl_xor_sync(FULL, n_rays, o);
     }
-    const unsigned nr = __popc(__ballot_sync(FULL, live));
-    if ((threadIdx.x & 31) == 0) {
-        if (nr) atomicAdd(&counters->n_rays, (unsigned long long)nr);
+    if (lane_id == 0) {
+        if (n_rays) atomicAdd(&counters->n_rays, (unsigned long long)n_rays);
         if (n_grad) atomicAdd(&counters->n_evals_grad, (unsigned long long)n_grad);
         if (n_alb) atomicAdd(&counters->n_albedo_lookups, (unsigned long long)n_alb);
         if (n_hit) atomicAdd(&counters->n_hits, (unsigned long long)n_hit);
     }
 }
 
-// one thread per shadow segment: visibility -> splat; DIFF: scatter the shadow tracer record to the lane records
+// one block per region: visibility -> splat; DIFF: scatter the shadow tracer record to the lane records
 template <bool DIFF>
 __global__ void __launch_bounds__(256) k_shadow_splat(const __grid_constant__ SceneParams sc, const __grid_constant__ PassParams ps,
-                                                       unsigned long long item0, const unsigned* __restrict__ shadow_count,
+                                                       unsigned long long item0, const unsigned* __restrict__ region_count,
                                                        const float4* __restrict__ info, const float* __restrict__ s_its,
                                                        const float* __restrict__ srec, unsigned long long srec_stride,
                                                        float* __restrict__ film, float* __restrict__ rec,
                                                        unsigned long long rec_stride) {
     __shared__ SplatSmem s_splat[8];
-    const unsigned j = blockIdx.x * 256u + threadIdx.x;
-    const bool live = j < *shadow_count;
-    float pfx = 0.f, pfy = 0.f;
-    V3 rgb = v3(0.f);
-    if (live) {
-        const float4 inf = info[j];
-        const unsigned i = __float_as_uint(inf.w);
-        const float its_s = DIFF ? srec[j] : s_its[j];
-        const bool occluded = isfinite(its_s);
-        const ItemRay r = item_ray(sc, ps, item0 + i);
-        pfx = r.pfx; pfy = r.pfy;
-        if (!occluded) rgb = V3{inf.x, inf.y, inf.z};
-        if (DIFF && !occluded) {
-            float* d = rec + i;
-            d[REC_S_STATE * rec_stride] = 1.f;
+    const unsigned cnt = region_count[blockIdx.x];
+    const unsigned region_base = blockIdx.x * kRegion;
+    for (unsigned j0 = 0; j0 < cnt; j0 += 256u) {
+        const unsigned j = j0 + threadIdx.x;
+        const bool live = j < cnt;
+        float pfx = 0.f, pfy = 0.f;
+        V3 rgb = v3(0.f);
+        if (live) {
+            const unsigned slot = region_base + j;
+            const float4 inf = info[slot];
+            const unsigned i = __float_as_uint(inf.w);
+            const float its_s = DIFF ? srec[slot] : s_its[slot];
+            const bool occluded = isfinite(its_s);
+            const ItemRay r = item_ray(sc, ps, item0 + i);
+            pfx = r.pfx; pfy = r.pfy;
+            if (!occluded) rgb = V3{inf.x, inf.y, inf.z};
+            if (DIFF && !occluded) {
+                float* d = rec + i;
+                d[REC_S_STATE * rec_stride] = 1.f;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) d[(REC_S_TAU + k) * rec_stride] = srec[(1 + k) * srec_stride + j];
+                for (int k = 0; k < 8; ++k) d[(REC_S_TAU + k) * rec_stride] = srec[(1 + k) * srec_stride + slot];
+            }
         }
+        warp_splat(sc.S, film, s_splat[threadIdx.x >> 5], live, pfx, pfy, rgb);
     }
-    warp_splat(sc.S, film, s_splat[threadIdx.x >> 5], live, pfx, pfy, rgb);
 }
 
 }  // namespace sdfrt

@@ -152,6 +152,18 @@ class Context:
         check(self.ctx, self.lib.sdfrt_get_stats(self.ctx, C.byref(s), int(reset), _stream(self.device)))
         return s.as_dict()
 
+    KERNEL_CLASSES = ('gen_primary', 'march_primary', 'shade', 'march_shadow', 'shadow_splat', 'film_adjoint', 'backward', 'develop')
+
+    def set_profiling(self, enable=True):
+        check(self.ctx, self.lib.sdfrt_set_profiling(self.ctx, int(enable)))
+
+    def timing(self):
+        """{class: (milliseconds, launches)} of the launches since the last call (CUDA events on the launching stream)."""
+        ms = (C.c_float * 8)()
+        n = (C.c_int * 8)()
+        check(self.ctx, self.lib.sdfrt_get_timing(self.ctx, ms, n))
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(self.KERNEL_CLASSES)}
+
     # ---- test hooks -----------------------------------------------------------------------------
     def trace_rays(self, o, d, maxt=None, differentiable=True):
         _f32c(o, self.device)

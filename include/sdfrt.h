@@ -82,6 +82,9 @@ typedef struct sdfrt_stats {
     uint64_t n_albedo_lookups;
     uint64_t n_steps_max;     /* longest march */
     uint64_t n_hits;
+    uint64_t n_evals_adjoint; /* value+gradient+Hessian evaluations of the adjoint sweep (k_backward) */
+    uint64_t n_tap_loads;     /* marcher evaluations that actually gathered their 4x4x4 block (tap-cache misses) */
+    uint64_t n_launches;      /* kernels launched by the library (host-side count) */
 } sdfrt_stats;
 
 /* per-ray tracer outputs of SDFBase.ray_intersect, python/shapes.py:288 (test hook) */
@@ -146,6 +149,14 @@ int sdfrt_adjoint_backprop(sdfrt_ctx* ctx, const float* film_accum, const float*
 
 /* device work counters accumulated since the last reset (synchronises `stream`) */
 int sdfrt_get_stats(sdfrt_ctx* ctx, sdfrt_stats* out, int reset, void* stream);
+
+/* Optional per-kernel timing with CUDA events recorded on the launching stream (for roofline reporting).
+ * classes: 0 gen_primary, 1 march (primary segments), 2 shade, 3 march (shadow segments), 4 shadow_splat,
+ *          5 film_adjoint, 6 backward, 7 develop.  sdfrt_get_timing synchronises the events, adds the elapsed
+ * milliseconds of every launch since the last call into ms[8] and the launch counts into launches[8]. */
+enum { SDFRT_NUM_KERNEL_CLASSES = 8 };
+int sdfrt_set_profiling(sdfrt_ctx* ctx, int enable);
+int sdfrt_get_timing(sdfrt_ctx* ctx, float* ms, int* launches);
 
 /* ---- test hooks / helpers used by the reference's callers ------------------------------ */
 /* SDFBase.ray_intersect / ray_intersect_non_diff, python/shapes.py:115-339; o, d: [n*3], maxt: [n] or NULL */
