@@ -245,13 +245,14 @@ SDFRT_HD void cell_setup(const GridView& G, V3 x, CellSetup<ORDER>& s) {
     }
 }
 SDFRT_HD void load_taps(const GridView& G, int bx, int by, int bz, float f[64]) {
-    const size_t sy = (size_t)G.rx, sz = (size_t)G.rx * (size_t)G.ry;
-    const float* base = G.data + ((size_t)bz * sz + (size_t)by * sy + (size_t)bx);
+    // 32-bit element offsets (grids up to 2^32 texels): one address computation per row, taps at +0..+3
+    const unsigned sy = (unsigned)G.rx, sz = (unsigned)G.rx * (unsigned)G.ry;
+    const unsigned o = (unsigned)bz * sz + (unsigned)by * sy + (unsigned)bx;
 #pragma unroll
     for (int k = 0; k < 4; ++k)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const float* row = base + (size_t)k * sz + (size_t)j * sy;
+            const float* row = G.data + (o + (unsigned)k * sz + (unsigned)j * sy);
 #pragma unroll
             for (int i = 0; i < 4; ++i) f[(k * 4 + j) * 4 + i] = row[i];
         }

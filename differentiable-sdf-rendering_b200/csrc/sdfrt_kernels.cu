@@ -37,29 +37,78 @@ __device__ __forceinline__ float warp_sum_f(float v) {
     return v;
 }
 
+// Adjoint sweep 2.  Lanes of a warp are samples of one pixel (or of neighbouring pixels), so their scatter sites -- above
+// all the surface-interaction site that every shaded hit owns -- fall into a few adjacent cells.  Each warp therefore
+// accumulates its 64-tap scatters in a shared 8x8x8-voxel window anchored at its first site (shared-memory atomics) and
+// flushes the touched voxels with one `red.global.add.f32` each; blocks of a site that leave the window go to global
+// memory directly.  (One-atomic-per-tap version: 6.3 ms at c3, see profiles/.)
+constexpr int kWin = 8;
+struct WindowAdd {
+    float* win;   // this warp's kWin^3 window
+    float* grad;
+    int ax, ay, az, rx, ry;
+    __device__ __forceinline__ void operator()(int ix, int iy, int iz, float v) const {
+        const unsigned cx = (unsigned)(ix - ax), cy = (unsigned)(iy - ay), cz = (unsigned)(iz - az);
+        if ((cx < (unsigned)kWin) & (cy < (unsigned)kWin) & (cz < (unsigned)kWin)) atomicAdd(win + (cz * kWin + cy) * kWin + cx, v);
+        else atomicAdd(grad + ((size_t)iz * ry + iy) * (size_t)rx + ix, v);
+    }
+};
+
 __global__ void __launch_bounds__(kBlock) k_backward(const __grid_constant__ SceneParams sc, const __grid_constant__ PassParams ps,
                                                       const float* __restrict__ film_adj, const float* __restrict__ rec,
                                                       unsigned long long rec_stride, BackwardTargets tg, float* grad_p,
                                                       Counters* counters) {
+    __shared__ float s_win[kBlock / 32][kWin * kWin * kWin];
+    const unsigned FULL = 0xffffffffu;
+    const int lane_id = threadIdx.x & 31;
+    float* win = s_win[threadIdx.x >> 5];
     // records are stored in work-item (band) order; the lane index is needed for the sampler and the pixel
     const unsigned long long item = (unsigned long long)blockIdx.x * kBlock + threadIdx.x;
     LaneStats st = {0, 0, 0, 0, 0, 0, 0};
     V3 gp = v3(0.f);
+    SiteList sites;
+    sites.n = 0;
     if (item < ps.lane_end - ps.lane_begin) {
         const WorkItem w = decode_item(sc.S, ps, item);
-        lane_backward(sc, ps, w.lane, film_adj, rec + item, rec_stride, tg, gp, st);
+        lane_backward(sc, ps, w.lane, film_adj, rec + item, rec_stride, tg, gp, sites, st);
+    }
+    const unsigned has = __ballot_sync(FULL, sites.n > 0);
+    if (has) {
+#pragma unroll
+        for (int c = lane_id; c < kWin * kWin * kWin; c += 32) win[c] = 0.f;
+        // anchor: two voxels below the block of the first lane's last site (the surface-interaction / primary warp site)
+        int bx = 0, by = 0, bz = 0;
+        if (sites.n > 0) {
+            const CellCoord cc = cell_coord(sc.G, sites.s[sites.n - 1].x);
+            bx = fold_base(cc.ix, sc.G.rx); by = fold_base(cc.iy, sc.G.ry); bz = fold_base(cc.iz, sc.G.rz);
+        }
+        const int src = __ffs(has) - 1;
+        WindowAdd add;
+        add.win = win; add.grad = tg.grad_sdf; add.rx = sc.G.rx; add.ry = sc.G.ry;
+        add.ax = __shfl_sync(FULL, bx, src) - 2; add.ay = __shfl_sync(FULL, by, src) - 2; add.az = __shfl_sync(FULL, bz, src) - 2;
+        __syncwarp();
+        for (int q = 0; q < sites.n; ++q) scatter_site_t(sc.G, sites.s[q].x, sites.s[q].phi_hat, sites.s[q].g_hat, add);
+        __syncwarp();
+#pragma unroll 4
+        for (int c = lane_id; c < kWin * kWin * kWin; c += 32) {
+            const float v = win[c];
+            if (v != 0.f) {
+                const int cx = c % kWin, cy = (c / kWin) % kWin, cz = c / (kWin * kWin);
+                atomicAdd(tg.grad_sdf + ((size_t)(add.az + cz) * sc.G.ry + (add.ay + cy)) * (size_t)sc.G.rx + (add.ax + cx), v);
+            }
+        }
     }
     {   // the adjoint sweep's evaluations are counted separately from the marchers'
-        const unsigned h = warp_sum(st.n_hess), sites = warp_sum(st.n_sites), al = warp_sum(st.n_albedo);
-        if ((threadIdx.x & 31) == 0) {
+        const unsigned h = warp_sum(st.n_hess), nsites = warp_sum(st.n_sites), al = warp_sum(st.n_albedo);
+        if (lane_id == 0) {
             if (h) atomicAdd(&counters->n_evals_adjoint, (unsigned long long)h);
-            if (sites) atomicAdd(&counters->n_scatter_sites, (unsigned long long)sites);
+            if (nsites) atomicAdd(&counters->n_scatter_sites, (unsigned long long)nsites);
             if (al) atomicAdd(&counters->n_albedo_lookups, (unsigned long long)al);
         }
     }
     if (grad_p != nullptr) {
         const float gx = warp_sum_f(gp.x), gy = warp_sum_f(gp.y), gz = warp_sum_f(gp.z);
-        if ((threadIdx.x & 31) == 0) {
+        if (lane_id == 0) {
             if (gx != 0.f) atomicAdd(grad_p + 0, gx);
             if (gy != 0.f) atomicAdd(grad_p + 1, gy);
             if (gz != 0.f) atomicAdd(grad_p + 2, gz);
@@ -248,20 +297,20 @@ int check_ready(sdfrt_ctx* ctx, int spp) {
 constexpr unsigned long long kMaxBatch = 1ull << 26;
 
 template <bool DIFF, int CACHE>
-void launch_march(sdfrt_ctx* ctx, unsigned grid, cudaStream_t st, const SegIn* segs, const unsigned* n_ptr, unsigned n_fixed, int do_refine,
-                  float* out_its, float* rec_out, unsigned long long rec_stride, unsigned* chunk_counter) {
-    k_march<DIFF, CACHE><<<grid, kMarchBlock, 0, st>>>(ctx->sc.G, ctx->sc.T, segs, n_ptr /* region fill or null */, n_fixed /* slots */, do_refine, out_its, rec_out, rec_stride,
+void launch_march(sdfrt_ctx* ctx, unsigned grid, cudaStream_t st, const SegIn* segs, const unsigned* n_ptr, unsigned n_fixed, unsigned region,
+                  int do_refine, float* out_its, float* rec_out, unsigned long long rec_stride, unsigned* chunk_counter) {
+    k_march<DIFF, CACHE><<<grid, kMarchBlock, 0, st>>>(ctx->sc.G, ctx->sc.T, segs, n_ptr /* region fill or null */, n_fixed /* slots */, region, do_refine, out_its, rec_out, rec_stride,
                                                        chunk_counter, ctx->counters);
 }
 template <bool DIFF>
 void launch_march_mode(sdfrt_ctx* ctx, int mode, unsigned need, cudaStream_t st, const SegIn* segs, const unsigned* n_ptr, unsigned n_fixed,
-                       int do_refine, float* out_its, float* rec_out, unsigned long long rec_stride, unsigned* chunk_counter) {
+                       unsigned region, int do_refine, float* out_its, float* rec_out, unsigned long long rec_stride, unsigned* chunk_counter) {
     const int bps = ctx->march_blocks[(DIFF ? 3 : 0) + mode];
     unsigned grid = (unsigned)ctx->num_sms * (unsigned)bps;
     if (grid > need) grid = need;
-    if (mode == 0) launch_march<DIFF, 0>(ctx, grid, st, segs, n_ptr, n_fixed, do_refine, out_its, rec_out, rec_stride, chunk_counter);
-    else if (mode == 1) launch_march<DIFF, 1>(ctx, grid, st, segs, n_ptr, n_fixed, do_refine, out_its, rec_out, rec_stride, chunk_counter);
-    else launch_march<DIFF, 2>(ctx, grid, st, segs, n_ptr, n_fixed, do_refine, out_its, rec_out, rec_stride, chunk_counter);
+    if (mode == 0) launch_march<DIFF, 0>(ctx, grid, st, segs, n_ptr, n_fixed, region, do_refine, out_its, rec_out, rec_stride, chunk_counter);
+    else if (mode == 1) launch_march<DIFF, 1>(ctx, grid, st, segs, n_ptr, n_fixed, region, do_refine, out_its, rec_out, rec_stride, chunk_counter);
+    else launch_march<DIFF, 2>(ctx, grid, st, segs, n_ptr, n_fixed, region, do_refine, out_its, rec_out, rec_stride, chunk_counter);
 }  // camera samples per batch of the wavefront pipeline
 
 template <bool DIFF>
@@ -275,12 +324,12 @@ int launch_forward(sdfrt_ctx* ctx, const PassParams& ps, float* film, cudaStream
         return fail(ctx, SDFRT_ERR_INVALID, "film row band exceeds 2^32 samples");
     const unsigned long long nbatch = (n + kMaxBatch - 1) / kMaxBatch;
     unsigned long long B = (n + nbatch - 1) / nbatch;
-    B = (B + kRegion - 1) / kRegion * kRegion;  // whole regions per batch
+    B = (B + kMaxRegion - 1) / kMaxRegion * kMaxRegion;  // whole regions per batch
     int rc;
     if ((rc = ensure(ctx, &ctx->segs, &ctx->segs_n, (size_t)B * 8))) return rc;
     if ((rc = ensure(ctx, &ctx->ssegs, &ctx->ssegs_n, (size_t)B * 8))) return rc;
     if ((rc = ensure(ctx, &ctx->sinfo, &ctx->sinfo_n, (size_t)B * 4))) return rc;
-    if ((rc = ensure(ctx, &ctx->scount, &ctx->scount_n, (size_t)(B / kRegion) + 1))) return rc;
+    if ((rc = ensure(ctx, &ctx->scount, &ctx->scount_n, (size_t)(B / 256) + 1))) return rc;
     if (DIFF) {
         if ((rc = ensure(ctx, &ctx->srec, &ctx->srec_n, (size_t)B * 9))) return rc;
     } else {
@@ -294,26 +343,29 @@ int launch_forward(sdfrt_ctx* ctx, const PassParams& ps, float* film, cudaStream
     for (unsigned long long item0 = 0; item0 < n; item0 += B) {
         const unsigned cnt = (unsigned)((n - item0 < B) ? (n - item0) : B);
         const unsigned blocks256 = (cnt + 255u) / 256u;
-        const unsigned regions = (cnt + kRegion - 1) / kRegion;
+        // region size: large enough to keep a block's rays on one film column, small enough to balance the persistent grid
+        unsigned region = kMaxRegion;
+        while (region > 256u && (unsigned long long)cnt / region < 8ull * (unsigned long long)ctx->num_sms * 4ull) region >>= 1;
+        const unsigned regions = (cnt + region - 1) / region;
         SDFRT_CUDA(ctx, cudaMemsetAsync(ctx->work, 0, WQ_COUNT * sizeof(unsigned), st));
         { LaunchScope ls(ctx, 0, st); k_gen_primary<<<blocks256, 256, 0, st>>>(ctx->sc, ps, item0, cnt, reinterpret_cast<SegIn*>(ctx->segs)); }
         // primary march (+ refine); DIFF writes its_t into row 0 of the lane records
         float* rec_b = DIFF ? ctx->rec + item0 : nullptr;
         const unsigned need = (cnt + kMarchBlock - 1) / kMarchBlock;
         { LaunchScope ls(ctx, 1, st);
-          launch_march_mode<DIFF>(ctx, ctx->cache_mode[DIFF ? 2 : 0], need, st, reinterpret_cast<const SegIn*>(ctx->segs), nullptr, cnt, 1,
+          launch_march_mode<DIFF>(ctx, ctx->cache_mode[DIFF ? 2 : 0], need, st, reinterpret_cast<const SegIn*>(ctx->segs), nullptr, cnt, region, 1,
                                   ctx->its, rec_b, ctx->rec_stride, ctx->work + WQ_PRIMARY_CHUNK); }
         const float* its = DIFF ? rec_b : ctx->its;
         { LaunchScope ls(ctx, 2, st);
-          k_shade<DIFF><<<regions, 256, 0, st>>>(ctx->sc, ps, item0, cnt, its, q, film,
+          k_shade<DIFF><<<regions, 256, 0, st>>>(ctx->sc, ps, item0, cnt, region, its, q, film,
                                                  DIFF ? rec_b + REC_S_STATE * ctx->rec_stride : nullptr, ctx->counters); }
         if (ctx->sc.integrator == INTEGRATOR_DIRECT) {
             // shadow march over the region-compacted queue
             { LaunchScope ls(ctx, 3, st);
               launch_march_mode<DIFF>(ctx, ctx->cache_mode[DIFF ? 3 : 1], need, st, reinterpret_cast<const SegIn*>(ctx->ssegs), q.count,
-                                      regions * kRegion, 0, ctx->s_its, ctx->srec, B, ctx->work + WQ_SHADOW_CHUNK); }
+                                      regions * region, region, 0, ctx->s_its, ctx->srec, B, ctx->work + WQ_SHADOW_CHUNK); }
             { LaunchScope ls(ctx, 4, st);
-              k_shadow_splat<DIFF><<<regions, 256, 0, st>>>(ctx->sc, ps, item0, q.count, reinterpret_cast<const float4*>(ctx->sinfo),
+              k_shadow_splat<DIFF><<<regions, 256, 0, st>>>(ctx->sc, ps, item0, region, q.count, reinterpret_cast<const float4*>(ctx->sinfo),
                                                             ctx->s_its, ctx->srec, B, film, rec_b, ctx->rec_stride); }
         }
         SDFRT_CUDA(ctx, cudaGetLastError());

@@ -207,37 +207,58 @@ SDFRT_HD void lane_forward(const SceneParams& sc, const PassParams& ps, unsigned
 }
 
 // ------------------------------------------------------------------------------------------------
-// adjoint scatter of one B-spline site: grad[k] += phi_hat * B_k(x) + g_hat . grad B_k(x)
+// adjoint scatter of one B-spline site: grad[k] += phi_hat * B_k(x) + g_hat . grad B_k(x) over the 64 taps.
+// Clamp-to-edge is folded into the weights (cell_setup), so the taps are the unclamped block [b, b+3]^3.
+// `add(ix, iy, iz, v)` receives grid coordinates.
 // ------------------------------------------------------------------------------------------------
-SDFRT_HD void scatter_site(float* grad, const GridView& G, V3 x, float phi_hat, V3 g_hat) {
-    const CellCoord c = cell_coord(G, x);
-    float wx[4], wy[4], wz[4], dx[4], dy[4], dz[4];
-    bspline_w(c.ax, wx); bspline_w(c.ay, wy); bspline_w(c.az, wz);
-    bspline_dw(c.ax, dx); bspline_dw(c.ay, dy); bspline_dw(c.az, dz);
+template <class Add>
+SDFRT_HD void scatter_site_t(const GridView& G, V3 x, float phi_hat, V3 g_hat, Add add) {
+    CellSetup<1> s;
+    cell_setup<1>(G, x, s);
     const float gx = g_hat.x * (float)G.rx, gy = g_hat.y * (float)G.ry, gz = g_hat.z * (float)G.rz;
     float ex[4];  // phi_hat * wx + gx * dx  (x-direction factor shared by all rows)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) ex[i] = phi_hat * wx[i] + gx * dx[i];
+    for (int i = 0; i < 4; ++i) ex[i] = phi_hat * s.wx[i] + gx * s.dx[i];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const int zz = clampi(c.iz + k, 0, G.rz - 1);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int yy = clampi(c.iy + j, 0, G.ry - 1);
-            float* row = grad + ((size_t)zz * G.ry + yy) * (size_t)G.rx;
-            const float a = wy[j] * wz[k];                               // multiplies ex[i]
-            const float bq = gy * dy[j] * wz[k] + gz * wy[j] * dz[k];    // multiplies wx[i]
+            const float a = s.wy[j] * s.wz[k];                                   // multiplies ex[i]
+            const float bq = gy * s.dy[j] * s.wz[k] + gz * s.wy[j] * s.dz[k];    // multiplies wx[i]
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int xx = clampi(c.ix + i, 0, G.rx - 1);
-                SDFRT_ATOMIC_ADD(row + xx, a * ex[i] + bq * wx[i]);
-            }
+            for (int i = 0; i < 4; ++i) add(s.bx + i, s.by + j, s.bz + k, a * ex[i] + bq * s.wx[i]);
         }
     }
 }
+struct GlobalAdd {
+    float* grad;
+    int rx, ry;
+    SDFRT_HD void operator()(int ix, int iy, int iz, float v) const {
+        SDFRT_ATOMIC_ADD(grad + ((size_t)iz * ry + iy) * (size_t)rx + ix, v);
+    }
+};
+SDFRT_HD void scatter_site(float* grad, const GridView& G, V3 x, float phi_hat, V3 g_hat) {
+    scatter_site_t(G, x, phi_hat, g_hat, GlobalAdd{grad, G.rx, G.ry});
+}
+
+// The <= 3 scatter sites of one lane (shadow warp site, surface interaction, primary warp site).  lane_backward only
+// collects them; the caller scatters (directly, or warp-aggregated through shared memory in k_backward).
+struct Site {
+    V3 x;
+    float phi_hat;
+    V3 g_hat;
+};
+struct SiteList {
+    int n;
+    Site s[3];
+};
+SDFRT_HD void push_site(SiteList& L, V3 x, float phi_hat, V3 g_hat) {
+    L.s[L.n].x = x; L.s[L.n].phi_hat = phi_hat; L.s[L.n].g_hat = g_hat;
+    ++L.n;
+}
 
 struct BackwardTargets {
-    float* grad_sdf;     // (rz, ry, rx), accumulated
+    float* grad_sdf;     // (rz, ry, rx), accumulated (by the caller, from the SiteList)
     float* grad_albedo;  // (rz, ry, rx, 3) or nullptr
 };
 
@@ -247,7 +268,8 @@ struct BackwardTargets {
 // ------------------------------------------------------------------------------------------------
 SDFRT_HD void lane_backward(const SceneParams& sc, const PassParams& ps, unsigned long long lane, const float* film_adj,
                             const float* rec /* already offset to this lane's record */, unsigned long long rec_stride, const BackwardTargets& tg, V3& grad_p,
-                            LaneStats& st) {
+                            SiteList& sites, LaneStats& st) {
+    sites.n = 0;
     CameraSample cs = camera_sample(sc, ps, lane);
     const V3 o = cs.o, d0 = cs.d;
     const float* r = rec;
@@ -382,7 +404,7 @@ SDFRT_HD void lane_backward(const SceneParams& sc, const PassParams& ps, unsigne
                 if (ws.active) {
                     const float phi_hat = div_s_hat * ws.cphi_div + dot(ds_hat, ws.cphi_dir);
                     const V3 g_hat = div_s_hat * ws.cg_div;
-                    scatter_site(tg.grad_sdf, sc.G, sr.o + tau * sr.d, phi_hat, g_hat);
+                    push_site(sites, sr.o + tau * sr.d, phi_hat, g_hat);
                     st.n_sites += 1;
                     const V3 os_hat = phi_hat * ws.g + mul(ws.H, g_hat);
                     p_hat += os_hat;
@@ -400,7 +422,7 @@ SDFRT_HD void lane_backward(const SceneParams& sc, const PassParams& ps, unsigne
         const V3 dd = its_t * p_hat + (its_t * phi2_hat) * g_p;
         if (isfinite(phi2_hat) & isfinite(gp_hat.x + gp_hat.y + gp_hat.z) & isfinite(dd.x + dd.y + dd.z)) {
             d_hat += dd;
-            scatter_site(tg.grad_sdf, sc.G, p, phi2_hat, gp_hat);
+            push_site(sites, p, phi2_hat, gp_hat);
             st.n_sites += 1;
             grad_p = grad_p - (phi2_hat * g_p + mul(H_p, gp_hat));
         }
@@ -417,7 +439,7 @@ SDFRT_HD void lane_backward(const SceneParams& sc, const PassParams& ps, unsigne
             const float phi_hat = div_hat * ws.cphi_div + dot(d_hat, ws.cphi_dir);
             const V3 g_hat = div_hat * ws.cg_div;
             if (isfinite(phi_hat) & isfinite(g_hat.x + g_hat.y + g_hat.z)) {
-                scatter_site(tg.grad_sdf, sc.G, o + tau * d0, phi_hat, g_hat);
+                push_site(sites, o + tau * d0, phi_hat, g_hat);
                 st.n_sites += 1;
                 grad_p = grad_p - (phi_hat * ws.g + mul(ws.H, g_hat));
             }

@@ -24,8 +24,9 @@
 namespace sdfrt {
 
 constexpr int kMarchBlock = 128;       // threads per block of k_march
-constexpr unsigned kRegion = 2048;     // segments per region: the unit a marcher block takes from the global counter
-                                       // (= one 8-pixel film column at 256 spp); shadow segments are compacted per region
+constexpr unsigned kMaxRegion = 2048;  // segments per region (a power of two in [256, 2048] chosen per launch): the unit a
+                                       // marcher block takes from the global counter (2048 = one 8-pixel film column at
+                                       // 256 spp); shadow segments are compacted per region
 constexpr int kMinActive = 24;         // leave the stepping loop when fewer slots are live
 constexpr int kBandRows = 8;
 
@@ -194,31 +195,31 @@ __device__ __forceinline__ void warp_splat(const SensorParams& S, float* film, S
 // ---------------------------------------------------------------------------------------------------------------
 constexpr unsigned long long kQueueExhausted = 0xFFFFFFFFull << 32;
 
-// Segments live in REGIONS of kRegion slots; region r holds fill(r) valid segments at its start (primary segments: all
+// Segments live in REGIONS of `region` slots; region r holds fill(r) valid segments at its start (primary segments: all
 // slots; shadow segments: the count k_shade wrote).  Leader only.  The block's current region is one 64-bit shared word
 // (region id << 32 | slots handed out); a fetch is a single shared atomicAdd.  Returns the number of segments taken
 // (>= 0) or -1 when all regions are exhausted.
-__device__ __forceinline__ unsigned region_fill(const unsigned* region_count, unsigned id, unsigned n_slots) {
+__device__ __forceinline__ unsigned region_fill(const unsigned* region_count, unsigned id, unsigned n_slots, unsigned region) {
     if (region_count) return region_count[id];
-    const unsigned long long base = (unsigned long long)id * kRegion;
-    return (base + kRegion <= n_slots) ? kRegion : (unsigned)(n_slots - base);
+    const unsigned long long base = (unsigned long long)id * region;
+    return (base + region <= n_slots) ? region : (unsigned)(n_slots - base);
 }
 __device__ __forceinline__ int fetch_items(unsigned long long* word, unsigned* region_counter, const unsigned* region_count,
-                                           unsigned n_slots, int n, unsigned& pos) {
+                                           unsigned n_slots, unsigned region, int n, unsigned& pos) {
     for (;;) {
         const unsigned long long old = atomicAdd(word, (unsigned long long)n);
         const unsigned id = (unsigned)(old >> 32), off = (unsigned)old;
         if (id == 0xFFFFFFFFu) return -1;
-        const unsigned fill = region_fill(region_count, id, n_slots);
+        const unsigned fill = region_fill(region_count, id, n_slots, region);
         if (off < fill || (off == 0 && fill == 0)) {
             int got = (off + (unsigned)n <= fill) ? n : (int)(fill - off);
             if (off + (unsigned)n >= fill) {  // this fetch used the region up: install the next one
                 const unsigned nid = atomicAdd(region_counter, 1u);
-                const unsigned long long nw = ((unsigned long long)nid * kRegion >= n_slots) ? kQueueExhausted
+                const unsigned long long nw = ((unsigned long long)nid * region >= n_slots) ? kQueueExhausted
                                                                                           : ((unsigned long long)nid << 32);
                 atomicExch(word, nw);
             }
-            pos = id * kRegion + off;
+            pos = id * region + off;
             return got;
         }
         __nanosleep(40);  // another warp is installing the next region
@@ -231,7 +232,7 @@ enum { SLOT_IDLE = 0, SLOT_MARCH = 1, SLOT_REFINE = 2, SLOT_DONE = 3 };
 // CACHE: 0 = gather every evaluation, 1 = tap cache in registers, 2 = tap cache in shared memory
 template <bool DIFF, int CACHE>
 __global__ void __launch_bounds__(kMarchBlock, DIFF ? (CACHE == 1 ? 3 : 4) : (CACHE == 1 ? 4 : 7)) k_march(const GridView G, const TracerParams T, const SegIn* __restrict__ segs,
-                                                        const unsigned* __restrict__ region_count, unsigned n_slots, int do_refine,
+                                                        const unsigned* __restrict__ region_count, unsigned n_slots, unsigned region, int do_refine,
                                                         float* __restrict__ out_its, float* __restrict__ rec_out,
                                                         unsigned long long rec_stride, unsigned* __restrict__ region_counter,
                                                         Counters* __restrict__ counters) {
@@ -245,7 +246,7 @@ __global__ void __launch_bounds__(kMarchBlock, DIFF ? (CACHE == 1 ? 3 : 4) : (CA
     int tap_key = -1;
     if (threadIdx.x == 0) {
         const unsigned id = atomicAdd(region_counter, 1u);
-        s_word = ((unsigned long long)id * kRegion >= n_slots) ? kQueueExhausted : ((unsigned long long)id << 32);
+        s_word = ((unsigned long long)id * region >= n_slots) ? kQueueExhausted : ((unsigned long long)id << 32);
     }
     __syncthreads();
     const unsigned FULL = 0xffffffffu;
@@ -279,7 +280,7 @@ __global__ void __launch_bounds__(kMarchBlock, DIFF ? (CACHE == 1 ? 3 : 4) : (CA
         if (idle != 0u && !exhausted) {
             unsigned pos = 0;
             int got = 0;
-            if (lane_id == 0) got = fetch_items(&s_word, region_counter, region_count, n_slots, __popc(idle), pos);
+            if (lane_id == 0) got = fetch_items(&s_word, region_counter, region_count, n_slots, region, __popc(idle), pos);
             got = __shfl_sync(FULL, got, 0);
             pos = __shfl_sync(FULL, pos, 0);
             if (got < 0) exhausted = true;
@@ -378,7 +379,7 @@ __global__ void __launch_bounds__(kMarchBlock, DIFF ? (CACHE == 1 ? 3 : 4) : (CA
 
 // ---------------------------------------------------------------------------------------------------------------
 // k_shade: <integrator>.sample after the primary intersection (python/integrators/sdf_direct_reparam.py:24-84).
-// One block per region of kRegion camera samples (8 iterations of 256).  Shadow segments are written compacted at the
+// One block per region of `region` camera samples (region / 256 iterations).  Shadow segments are written compacted at the
 // start of the block's own region of the shadow arrays, so their order stays the band order of the camera samples (the
 // shadow marcher and the shadow splat then see rays of one 8-pixel film column at a time) and no global atomics or
 // prefix sums are needed.
@@ -391,7 +392,7 @@ struct ShadowQueue {
 
 template <bool DIFF>
 __global__ void __launch_bounds__(256) k_shade(const __grid_constant__ SceneParams sc, const __grid_constant__ PassParams ps,
-                                                unsigned long long item0, unsigned n, const float* __restrict__ its,
+                                                unsigned long long item0, unsigned n, unsigned region, const float* __restrict__ its,
                                                 ShadowQueue q, float* __restrict__ film, float* __restrict__ rec_state,
                                                 Counters* __restrict__ counters) {
     __shared__ SplatSmem s_splat[8];
@@ -400,9 +401,9 @@ __global__ void __launch_bounds__(256) k_shade(const __grid_constant__ ScenePara
     __syncthreads();
     const unsigned FULL = 0xffffffffu;
     const int lane_id = threadIdx.x & 31;
-    const unsigned region_base = blockIdx.x * kRegion;
+    const unsigned region_base = blockIdx.x * region;
     unsigned n_grad = 0, n_alb = 0, n_hit = 0, n_rays = 0;
-    for (unsigned it = 0; it < kRegion / 256u; ++it) {
+    for (unsigned it = 0; it < region / 256u; ++it) {
         const unsigned i = region_base + it * 256u + threadIdx.x;
         if (region_base + it * 256u >= n) break;  // block-uniform
         const bool live = i < n;
@@ -483,14 +484,14 @@ __global__ void __launch_bounds__(256) k_shade(const __grid_constant__ ScenePara
 // one block per region: visibility -> splat; DIFF: scatter the shadow tracer record to the lane records
 template <bool DIFF>
 __global__ void __launch_bounds__(256) k_shadow_splat(const __grid_constant__ SceneParams sc, const __grid_constant__ PassParams ps,
-                                                       unsigned long long item0, const unsigned* __restrict__ region_count,
+                                                       unsigned long long item0, unsigned region, const unsigned* __restrict__ region_count,
                                                        const float4* __restrict__ info, const float* __restrict__ s_its,
                                                        const float* __restrict__ srec, unsigned long long srec_stride,
                                                        float* __restrict__ film, float* __restrict__ rec,
                                                        unsigned long long rec_stride) {
     __shared__ SplatSmem s_splat[8];
     const unsigned cnt = region_count[blockIdx.x];
-    const unsigned region_base = blockIdx.x * kRegion;
+    const unsigned region_base = blockIdx.x * region;
     for (unsigned j0 = 0; j0 < cnt; j0 += 256u) {
         const unsigned j = j0 + threadIdx.x;
         const bool live = j < cnt;

@@ -97,7 +97,9 @@ int cp_time_sample(const cp_scene* h, unsigned seed, int spp_primal, int spp_adj
     for (long long l = la; l < la + n_adjoint; ++l) {
         LaneStats st = {0, 0, 0, 0, 0, 0, 0};
         V3 gp = v3(0.f);
-        lane_backward(sc, sub, (unsigned long long)l, film_adj.data(), rec.data() + (l - la), (unsigned long long)n_adjoint, tg, gp, st);
+        SiteList sites;
+        lane_backward(sc, sub, (unsigned long long)l, film_adj.data(), rec.data() + (l - la), (unsigned long long)n_adjoint, tg, gp, sites, st);
+        for (int q = 0; q < sites.n; ++q) scatter_site(grad_sdf, sc.G, sites.s[q].x, sites.s[q].phi_hat, sites.s[q].g_hat);
         nh += st.n_hess;
     }
     auto t2 = std::chrono::steady_clock::now();

@@ -126,7 +126,11 @@ int hh_backward(const hh_scene* h, unsigned seed, int spp, const float* film, co
     LaneStats st = {0, 0, 0, 0, 0, 0, 0};
     V3 gp = v3(0.f);
     const unsigned long long n = ps.lane_end - ps.lane_begin;
-    for (unsigned long long lane = ps.lane_begin; lane < ps.lane_end; ++lane) lane_backward(sc, ps, lane, adj.data(), rec + (lane - ps.lane_begin), n, tg, gp, st);
+    for (unsigned long long lane = ps.lane_begin; lane < ps.lane_end; ++lane) {
+        SiteList sites;
+        lane_backward(sc, ps, lane, adj.data(), rec + (lane - ps.lane_begin), n, tg, gp, sites, st);
+        for (int q = 0; q < sites.n; ++q) scatter_site(grad_sdf, sc.G, sites.s[q].x, sites.s[q].phi_hat, sites.s[q].g_hat);
+    }
     if (grad_p) { grad_p[0] += gp.x; grad_p[1] += gp.y; grad_p[2] += gp.z; }
     if (stats) { stats[0] = n; stats[3] = st.n_hess; stats[4] = st.n_sites; }
     return 0;
