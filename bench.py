@@ -279,23 +279,47 @@ def run_gpu(args):
                 "note": "fetch-level bytes: 256 B per B-spline evaluation; the SDF grid is L2-resident at <= 256^3, so the fetches are "
                         "served by L1/L2 and frac can exceed 1; `traffic` is the ncu dram__bytes of the same launches (profiles/)"}
 
-    # e2e through the host-buffer C-ABI entry point (single GPU): H2D sdf + D2H image + grad every step
+    # e2e: HOST buffers in, host buffers out, copies inside the timed region.
+    #  N = 1: the host-buffer C-ABI entry point sdfrt_render_view_host (H2D sdf; D2H image + grad_sdf every step)
+    #  N > 1: the Python mirror's multi-GPU path (sdfrt.dist.render_view): every rank uploads the grid from pinned host memory,
+    #         renders its film rows, NCCL all-reduces film and gradient, rank 0 downloads image + gradient.
     e2e = None
+    e_steps = max(1, min(args.steps, 5))
+    sdf_h = sdf.cpu().pin_memory()
+    img_h = torch.empty((H, W, 3)).pin_memory()
+    g_h = torch.empty((R, R, R)).pin_memory()
     if world == 1:
-        sdf_h = sdf.cpu().pin_memory()
-        img_h = torch.empty((H, W, 3)).pin_memory()
-        g_h = torch.empty((R, R, R)).pin_memory()
         for w in range(2):
             ctx.render_view_host(sdf_h, w, spp * mult, w + 1 + nsens, spp, None, img_h, g_h)
         torch.cuda.synchronize(dev)
-        e_steps = max(1, min(args.steps, 5))
         tw = time.perf_counter()
         for s in range(e_steps):
             ctx.render_view_host(sdf_h, 1000 + s, spp * mult, 1001 + s + nsens, spp, None, img_h, g_h)
         tw = time.perf_counter() - tw
-        e2e = {"value": rays_per_step * e_steps / tw / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": sdf_h.numel() * 4,
-               "d2h_bytes_per_step": img_h.numel() * 4 + g_h.numel() * 4, "steps": e_steps}
         ctx.set_sdf(sdf)
+    else:
+        def one(seed):
+            sdf.copy_(sdf_h, non_blocking=True)
+            grad_sdf.zero_()
+            img = sdfrt.dist.render_view(ctx, seed, spp * mult, seed + 1 + nsens, spp, lambda im: grad_image, grad_sdf)
+            if rank == 0:
+                img_h.copy_(img, non_blocking=True)
+                g_h.copy_(grad_sdf, non_blocking=True)
+            torch.cuda.synchronize(dev)
+        for w in range(2):
+            one(w)
+        dist.barrier()
+        tw = time.perf_counter()
+        for s in range(e_steps):
+            one(1000 + s)
+        dist.barrier()
+        tw = time.perf_counter() - tw
+        twt = torch.tensor([tw], device=dev, dtype=torch.float64)
+        dist.all_reduce(twt, op=dist.ReduceOp.MAX)
+        tw = twt.item()
+    e2e = {"value": rays_per_step * e_steps / tw / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": sdf_h.numel() * 4 * world,
+           "d2h_bytes_per_step": img_h.numel() * 4 + g_h.numel() * 4, "steps": e_steps,
+           "api": "sdfrt_render_view_host" if world == 1 else "sdfrt.dist.render_view"}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

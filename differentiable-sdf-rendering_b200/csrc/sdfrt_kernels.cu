@@ -37,31 +37,16 @@ __device__ __forceinline__ float warp_sum_f(float v) {
     return v;
 }
 
-// Adjoint sweep 2.  Lanes of a warp are samples of one pixel (or of neighbouring pixels), so their scatter sites -- above
-// all the surface-interaction site that every shaded hit owns -- fall into a few adjacent cells.  Each warp therefore
-// accumulates its 64-tap scatters in a shared 8x8x8-voxel window anchored at its first site (shared-memory atomics) and
-// flushes the touched voxels with one `red.global.add.f32` each; blocks of a site that leave the window go to global
-// memory directly.  (One-atomic-per-tap version: 6.3 ms at c3, see profiles/.)
-constexpr int kWin = 8;
-struct WindowAdd {
-    float* win;   // this warp's kWin^3 window
-    float* grad;
-    int ax, ay, az, rx, ry;
-    __device__ __forceinline__ void operator()(int ix, int iy, int iz, float v) const {
-        const unsigned cx = (unsigned)(ix - ax), cy = (unsigned)(iy - ay), cz = (unsigned)(iz - az);
-        if ((cx < (unsigned)kWin) & (cy < (unsigned)kWin) & (cz < (unsigned)kWin)) atomicAdd(win + (cz * kWin + cy) * kWin + cx, v);
-        else atomicAdd(grad + ((size_t)iz * ry + iy) * (size_t)rx + ix, v);
-    }
-};
-
+// Adjoint sweep 2: closed-form adjoint per lane, 64-tap scatter of each site with `red.global.add.f32`.
+// (A per-warp shared-memory accumulation window was tried -- 8^3 voxels, shared atomics, one global red per touched
+// voxel -- and was slower: 10.1 ms vs 6.3 ms at c3; zeroing/flushing the window costs more than the L2 atomics it saves.)
 __global__ void __launch_bounds__(kBlock) k_backward(const __grid_constant__ SceneParams sc, const __grid_constant__ PassParams ps,
                                                       const float* __restrict__ film_adj, const float* __restrict__ rec,
                                                       unsigned long long rec_stride, BackwardTargets tg, float* grad_p,
                                                       Counters* counters) {
-    __shared__ float s_win[kBlock / 32][kWin * kWin * kWin];
     const unsigned FULL = 0xffffffffu;
     const int lane_id = threadIdx.x & 31;
-    float* win = s_win[threadIdx.x >> 5];
+    (void)FULL;
     // records are stored in work-item (band) order; the lane index is needed for the sampler and the pixel
     const unsigned long long item = (unsigned long long)blockIdx.x * kBlock + threadIdx.x;
     LaneStats st = {0, 0, 0, 0, 0, 0, 0};
@@ -72,32 +57,7 @@ __global__ void __launch_bounds__(kBlock) k_backward(const __grid_constant__ Sce
         const WorkItem w = decode_item(sc.S, ps, item);
         lane_backward(sc, ps, w.lane, film_adj, rec + item, rec_stride, tg, gp, sites, st);
     }
-    const unsigned has = __ballot_sync(FULL, sites.n > 0);
-    if (has) {
-#pragma unroll
-        for (int c = lane_id; c < kWin * kWin * kWin; c += 32) win[c] = 0.f;
-        // anchor: two voxels below the block of the first lane's last site (the surface-interaction / primary warp site)
-        int bx = 0, by = 0, bz = 0;
-        if (sites.n > 0) {
-            const CellCoord cc = cell_coord(sc.G, sites.s[sites.n - 1].x);
-            bx = fold_base(cc.ix, sc.G.rx); by = fold_base(cc.iy, sc.G.ry); bz = fold_base(cc.iz, sc.G.rz);
-        }
-        const int src = __ffs(has) - 1;
-        WindowAdd add;
-        add.win = win; add.grad = tg.grad_sdf; add.rx = sc.G.rx; add.ry = sc.G.ry;
-        add.ax = __shfl_sync(FULL, bx, src) - 2; add.ay = __shfl_sync(FULL, by, src) - 2; add.az = __shfl_sync(FULL, bz, src) - 2;
-        __syncwarp();
-        for (int q = 0; q < sites.n; ++q) scatter_site_t(sc.G, sites.s[q].x, sites.s[q].phi_hat, sites.s[q].g_hat, add);
-        __syncwarp();
-#pragma unroll 4
-        for (int c = lane_id; c < kWin * kWin * kWin; c += 32) {
-            const float v = win[c];
-            if (v != 0.f) {
-                const int cx = c % kWin, cy = (c / kWin) % kWin, cz = c / (kWin * kWin);
-                atomicAdd(tg.grad_sdf + ((size_t)(add.az + cz) * sc.G.ry + (add.ay + cy)) * (size_t)sc.G.rx + (add.ax + cx), v);
-            }
-        }
-    }
+    for (int q = 0; q < sites.n; ++q) scatter_site(tg.grad_sdf, sc.G, sites.s[q].x, sites.s[q].phi_hat, sites.s[q].g_hat);
     {   // the adjoint sweep's evaluations are counted separately from the marchers'
         const unsigned h = warp_sum(st.n_hess), nsites = warp_sum(st.n_sites), al = warp_sum(st.n_albedo);
         if (lane_id == 0) {
@@ -225,8 +185,12 @@ struct sdfrt_ctx {
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> timed;  // (class, start/stop) of launches not yet collected
     std::vector<cudaEvent_t> event_pool;
     // per-batch scratch of the wavefront pipeline
-    float *segs = nullptr, *its = nullptr, *ssegs = nullptr, *sinfo = nullptr, *s_its = nullptr, *srec = nullptr, *scount = nullptr;
-    size_t segs_n = 0, its_n = 0, ssegs_n = 0, sinfo_n = 0, s_its_n = 0, srec_n = 0, scount_n = 0;
+    struct Scratch {
+        float *segs = nullptr, *its = nullptr, *ssegs = nullptr, *sinfo = nullptr, *s_its = nullptr, *srec = nullptr, *scount = nullptr;
+        size_t segs_n = 0, its_n = 0, ssegs_n = 0, sinfo_n = 0, s_its_n = 0, srec_n = 0, scount_n = 0;
+    } scratch[2];                 // one per pipeline slot
+    cudaStream_t aux[2] = {nullptr, nullptr};   // batches alternate between two internal streams so that the tail of one
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};  // batch's persistent kernels overlaps the next batch
     int num_sms = 0;
     int march_blocks[6] = {0, 0, 0, 0, 0, 0};  // resident blocks per SM of k_march<DIFF, CACHE> at [3*DIFF + CACHE]
     int cache_mode[4] = {1, 1, 0, 1};        // tap-cache mode of [value primary, value shadow, diff primary, diff shadow]
@@ -294,7 +258,7 @@ int check_ready(sdfrt_ctx* ctx, int spp) {
     return SDFRT_OK;
 }
 
-constexpr unsigned long long kMaxBatch = 1ull << 26;
+constexpr unsigned long long kBatchTarget = 1ull << 23;  // camera samples per batch of the wavefront pipeline
 
 template <bool DIFF, int CACHE>
 void launch_march(sdfrt_ctx* ctx, unsigned grid, cudaStream_t st, const SegIn* segs, const unsigned* n_ptr, unsigned n_fixed, unsigned region,
@@ -322,53 +286,74 @@ int launch_forward(sdfrt_ctx* ctx, const PassParams& ps, float* film, cudaStream
     const SensorParams& S = ctx->sc.S;
     if ((unsigned long long)kBandRows * (unsigned long long)(S.W + 2 * S.border) * (unsigned long long)ps.spp > 0xffffffffull)
         return fail(ctx, SDFRT_ERR_INVALID, "film row band exceeds 2^32 samples");
-    const unsigned long long nbatch = (n + kMaxBatch - 1) / kMaxBatch;
+    const unsigned long long nbatch = (n + kBatchTarget - 1) / kBatchTarget;
     unsigned long long B = (n + nbatch - 1) / nbatch;
     B = (B + kMaxRegion - 1) / kMaxRegion * kMaxRegion;  // whole regions per batch
+    const int nslots = nbatch > 1 ? 2 : 1;
     int rc;
-    if ((rc = ensure(ctx, &ctx->segs, &ctx->segs_n, (size_t)B * 8))) return rc;
-    if ((rc = ensure(ctx, &ctx->ssegs, &ctx->ssegs_n, (size_t)B * 8))) return rc;
-    if ((rc = ensure(ctx, &ctx->sinfo, &ctx->sinfo_n, (size_t)B * 4))) return rc;
-    if ((rc = ensure(ctx, &ctx->scount, &ctx->scount_n, (size_t)(B / 256) + 1))) return rc;
-    if (DIFF) {
-        if ((rc = ensure(ctx, &ctx->srec, &ctx->srec_n, (size_t)B * 9))) return rc;
-    } else {
-        if ((rc = ensure(ctx, &ctx->its, &ctx->its_n, (size_t)B))) return rc;
-        if ((rc = ensure(ctx, &ctx->s_its, &ctx->s_its_n, (size_t)B))) return rc;
+    for (int sl = 0; sl < nslots; ++sl) {
+        sdfrt_ctx::Scratch& sc = ctx->scratch[sl];
+        if ((rc = ensure(ctx, &sc.segs, &sc.segs_n, (size_t)B * 8))) return rc;
+        if ((rc = ensure(ctx, &sc.ssegs, &sc.ssegs_n, (size_t)B * 8))) return rc;
+        if ((rc = ensure(ctx, &sc.sinfo, &sc.sinfo_n, (size_t)B * 4))) return rc;
+        if ((rc = ensure(ctx, &sc.scount, &sc.scount_n, (size_t)(B / 256) + 1))) return rc;
+        if (DIFF) {
+            if ((rc = ensure(ctx, &sc.srec, &sc.srec_n, (size_t)B * 9))) return rc;
+        } else {
+            if ((rc = ensure(ctx, &sc.its, &sc.its_n, (size_t)B))) return rc;
+            if ((rc = ensure(ctx, &sc.s_its, &sc.s_its_n, (size_t)B))) return rc;
+        }
     }
-    ShadowQueue q;
-    q.segs = reinterpret_cast<SegIn*>(ctx->ssegs);
-    q.info = reinterpret_cast<float4*>(ctx->sinfo);
-    q.count = reinterpret_cast<unsigned*>(ctx->scount);
-    for (unsigned long long item0 = 0; item0 < n; item0 += B) {
+    // fork: the internal streams wait for everything queued on the caller's stream (film memset included)
+    if (nslots > 1) {
+        SDFRT_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
+        for (int sl = 0; sl < 2; ++sl) SDFRT_CUDA(ctx, cudaStreamWaitEvent(ctx->aux[sl], ctx->ev_fork, 0));
+    }
+    unsigned long long bi = 0;
+    for (unsigned long long item0 = 0; item0 < n; item0 += B, ++bi) {
+        const int sl = nslots > 1 ? (int)(bi & 1) : 0;
+        cudaStream_t bs = nslots > 1 ? ctx->aux[sl] : st;
+        sdfrt_ctx::Scratch& sc = ctx->scratch[sl];
+        unsigned* work = ctx->work + sl * WQ_COUNT;
+        ShadowQueue q;
+        q.segs = reinterpret_cast<SegIn*>(sc.ssegs);
+        q.info = reinterpret_cast<float4*>(sc.sinfo);
+        q.count = reinterpret_cast<unsigned*>(sc.scount);
         const unsigned cnt = (unsigned)((n - item0 < B) ? (n - item0) : B);
         const unsigned blocks256 = (cnt + 255u) / 256u;
         // region size: large enough to keep a block's rays on one film column, small enough to balance the persistent grid
         unsigned region = kMaxRegion;
         while (region > 256u && (unsigned long long)cnt / region < 8ull * (unsigned long long)ctx->num_sms * 4ull) region >>= 1;
         const unsigned regions = (cnt + region - 1) / region;
-        SDFRT_CUDA(ctx, cudaMemsetAsync(ctx->work, 0, WQ_COUNT * sizeof(unsigned), st));
-        { LaunchScope ls(ctx, 0, st); k_gen_primary<<<blocks256, 256, 0, st>>>(ctx->sc, ps, item0, cnt, reinterpret_cast<SegIn*>(ctx->segs)); }
+        SDFRT_CUDA(ctx, cudaMemsetAsync(work, 0, WQ_COUNT * sizeof(unsigned), bs));
+        { LaunchScope ls(ctx, 0, bs); k_gen_primary<<<blocks256, 256, 0, bs>>>(ctx->sc, ps, item0, cnt, reinterpret_cast<SegIn*>(sc.segs)); }
         // primary march (+ refine); DIFF writes its_t into row 0 of the lane records
         float* rec_b = DIFF ? ctx->rec + item0 : nullptr;
         const unsigned need = (cnt + kMarchBlock - 1) / kMarchBlock;
-        { LaunchScope ls(ctx, 1, st);
-          launch_march_mode<DIFF>(ctx, ctx->cache_mode[DIFF ? 2 : 0], need, st, reinterpret_cast<const SegIn*>(ctx->segs), nullptr, cnt, region, 1,
-                                  ctx->its, rec_b, ctx->rec_stride, ctx->work + WQ_PRIMARY_CHUNK); }
-        const float* its = DIFF ? rec_b : ctx->its;
-        { LaunchScope ls(ctx, 2, st);
-          k_shade<DIFF><<<regions, 256, 0, st>>>(ctx->sc, ps, item0, cnt, region, its, q, film,
+        { LaunchScope ls(ctx, 1, bs);
+          launch_march_mode<DIFF>(ctx, ctx->cache_mode[DIFF ? 2 : 0], need, bs, reinterpret_cast<const SegIn*>(sc.segs), nullptr, cnt, region, 1,
+                                  sc.its, rec_b, ctx->rec_stride, work + WQ_PRIMARY_CHUNK); }
+        const float* its = DIFF ? rec_b : sc.its;
+        { LaunchScope ls(ctx, 2, bs);
+          k_shade<DIFF><<<regions, 256, 0, bs>>>(ctx->sc, ps, item0, cnt, region, its, q, film,
                                                  DIFF ? rec_b + REC_S_STATE * ctx->rec_stride : nullptr, ctx->counters); }
         if (ctx->sc.integrator == INTEGRATOR_DIRECT) {
             // shadow march over the region-compacted queue
-            { LaunchScope ls(ctx, 3, st);
-              launch_march_mode<DIFF>(ctx, ctx->cache_mode[DIFF ? 3 : 1], need, st, reinterpret_cast<const SegIn*>(ctx->ssegs), q.count,
-                                      regions * region, region, 0, ctx->s_its, ctx->srec, B, ctx->work + WQ_SHADOW_CHUNK); }
-            { LaunchScope ls(ctx, 4, st);
-              k_shadow_splat<DIFF><<<regions, 256, 0, st>>>(ctx->sc, ps, item0, region, q.count, reinterpret_cast<const float4*>(ctx->sinfo),
-                                                            ctx->s_its, ctx->srec, B, film, rec_b, ctx->rec_stride); }
+            { LaunchScope ls(ctx, 3, bs);
+              launch_march_mode<DIFF>(ctx, ctx->cache_mode[DIFF ? 3 : 1], need, bs, reinterpret_cast<const SegIn*>(sc.ssegs), q.count,
+                                      regions * region, region, 0, sc.s_its, sc.srec, B, work + WQ_SHADOW_CHUNK); }
+            { LaunchScope ls(ctx, 4, bs);
+              k_shadow_splat<DIFF><<<regions, 256, 0, bs>>>(ctx->sc, ps, item0, region, q.count, reinterpret_cast<const float4*>(sc.sinfo),
+                                                            sc.s_its, sc.srec, B, film, rec_b, ctx->rec_stride); }
         }
         SDFRT_CUDA(ctx, cudaGetLastError());
+    }
+    // join: the caller's stream continues after both internal streams are done
+    if (nslots > 1) {
+        for (int sl = 0; sl < 2; ++sl) {
+            SDFRT_CUDA(ctx, cudaEventRecord(ctx->ev_join[sl], ctx->aux[sl]));
+            SDFRT_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join[sl], 0));
+        }
     }
     return SDFRT_OK;
 }
@@ -423,7 +408,12 @@ sdfrt_ctx* sdfrt_create(int device, int* status) {
         return nullptr;
     }
     ctx->num_sms = prop.multiProcessorCount;
-    bool ok = cudaMalloc((void**)&ctx->work, WQ_COUNT * sizeof(unsigned)) == cudaSuccess;
+    bool ok = cudaMalloc((void**)&ctx->work, 2 * WQ_COUNT * sizeof(unsigned)) == cudaSuccess;
+    for (int i = 0; i < 2; ++i) {
+        ok = ok && cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
+    }
+    ok = ok && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->march_blocks[0], k_march<false, 0>, kMarchBlock, 0) == cudaSuccess;
     ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->march_blocks[1], k_march<false, 1>, kMarchBlock, 0) == cudaSuccess;
     ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->march_blocks[2], k_march<false, 2>, kMarchBlock, 0) == cudaSuccess;
@@ -452,7 +442,14 @@ void sdfrt_destroy(sdfrt_ctx* ctx) {
     cudaFree(ctx->film_adj);
     cudaFree(ctx->counters);
     cudaFree(ctx->work);
-    cudaFree(ctx->segs); cudaFree(ctx->its); cudaFree(ctx->ssegs); cudaFree(ctx->sinfo); cudaFree(ctx->s_its); cudaFree(ctx->srec); cudaFree(ctx->scount);
+    for (auto& sc : ctx->scratch) {
+        cudaFree(sc.segs); cudaFree(sc.its); cudaFree(sc.ssegs); cudaFree(sc.sinfo); cudaFree(sc.s_its); cudaFree(sc.srec); cudaFree(sc.scount);
+    }
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->aux[i]) cudaStreamDestroy(ctx->aux[i]);
+        if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
+    }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     cudaFree(ctx->h_sdf); cudaFree(ctx->h_film); cudaFree(ctx->h_image); cudaFree(ctx->h_gimg); cudaFree(ctx->h_grad);
     delete ctx;
 }
