@@ -74,6 +74,7 @@ SIGNATURES = {
     'sdfrt_adjoint_backprop': (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
     'sdfrt_get_stats': (C.c_int, [_P, C.POINTER(Stats), C.c_int, _P]),
     'sdfrt_set_profiling': (C.c_int, [_P, C.c_int]),
+    'sdfrt_set_overlap': (C.c_int, [_P, C.c_int]),
     'sdfrt_get_timing': (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     'sdfrt_trace_rays': (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.POINTER(RayOut), _P]),
     'sdfrt_eval_sdf': (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),

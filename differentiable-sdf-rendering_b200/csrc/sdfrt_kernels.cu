@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <string>
 #include <utility>
 #include <vector>
@@ -160,6 +161,8 @@ __global__ void k_eval_sdf(GridView G, const float* __restrict__ x, int n, int o
 // ----------------------------------------------------------------------------------------------------
 // context
 // ----------------------------------------------------------------------------------------------------
+constexpr int kSlots = 4;  // pipeline slots (internal streams + scratch sets) available to a forward sweep
+
 struct sdfrt_ctx {
     int device = 0;
     std::string err;
@@ -182,15 +185,18 @@ struct sdfrt_ctx {
     unsigned* work = nullptr;  // WQ_COUNT counters
     unsigned long long n_launches = 0;
     bool profiling = false;
+    bool overlap = true;
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> timed;  // (class, start/stop) of launches not yet collected
     std::vector<cudaEvent_t> event_pool;
     // per-batch scratch of the wavefront pipeline
     struct Scratch {
         float *segs = nullptr, *its = nullptr, *ssegs = nullptr, *sinfo = nullptr, *s_its = nullptr, *srec = nullptr, *scount = nullptr;
         size_t segs_n = 0, its_n = 0, ssegs_n = 0, sinfo_n = 0, s_its_n = 0, srec_n = 0, scount_n = 0;
-    } scratch[2];                 // one per pipeline slot
-    cudaStream_t aux[2] = {nullptr, nullptr};   // batches alternate between two internal streams so that the tail of one
-    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};  // batch's persistent kernels overlaps the next batch
+    } scratch[kSlots];            // one per pipeline slot
+    cudaStream_t aux[kSlots] = {};   // batches rotate over internal streams so that the tail of one batch's persistent
+    cudaEvent_t ev_fork = nullptr, ev_join[kSlots] = {};  // kernels overlaps the following batches
+    int max_slots = kSlots;
+    unsigned long long batch_target = 0;  // camera samples per batch; 0 = n / 6 clamped to [2^22, 2^24] (measured best at c3)
     int num_sms = 0;
     int march_blocks[6] = {0, 0, 0, 0, 0, 0};  // resident blocks per SM of k_march<DIFF, CACHE> at [3*DIFF + CACHE]
     int cache_mode[4] = {1, 1, 0, 1};        // tap-cache mode of [value primary, value shadow, diff primary, diff shadow]
@@ -258,7 +264,6 @@ int check_ready(sdfrt_ctx* ctx, int spp) {
     return SDFRT_OK;
 }
 
-constexpr unsigned long long kBatchTarget = 1ull << 23;  // camera samples per batch of the wavefront pipeline
 
 template <bool DIFF, int CACHE>
 void launch_march(sdfrt_ctx* ctx, unsigned grid, cudaStream_t st, const SegIn* segs, const unsigned* n_ptr, unsigned n_fixed, unsigned region,
@@ -286,10 +291,12 @@ int launch_forward(sdfrt_ctx* ctx, const PassParams& ps, float* film, cudaStream
     const SensorParams& S = ctx->sc.S;
     if ((unsigned long long)kBandRows * (unsigned long long)(S.W + 2 * S.border) * (unsigned long long)ps.spp > 0xffffffffull)
         return fail(ctx, SDFRT_ERR_INVALID, "film row band exceeds 2^32 samples");
-    const unsigned long long nbatch = (n + kBatchTarget - 1) / kBatchTarget;
+    unsigned long long target = ctx->batch_target;
+    if (target == 0) target = std::max<unsigned long long>(1ull << 22, std::min<unsigned long long>(1ull << 24, n / 6));
+    const unsigned long long nbatch = (n + target - 1) / target;
     unsigned long long B = (n + nbatch - 1) / nbatch;
     B = (B + kMaxRegion - 1) / kMaxRegion * kMaxRegion;  // whole regions per batch
-    const int nslots = nbatch > 1 ? 2 : 1;
+    const int nslots = (nbatch > 1 && ctx->overlap) ? (int)std::min<unsigned long long>(nbatch, (unsigned long long)ctx->max_slots) : 1;
     int rc;
     for (int sl = 0; sl < nslots; ++sl) {
         sdfrt_ctx::Scratch& sc = ctx->scratch[sl];
@@ -307,11 +314,11 @@ int launch_forward(sdfrt_ctx* ctx, const PassParams& ps, float* film, cudaStream
     // fork: the internal streams wait for everything queued on the caller's stream (film memset included)
     if (nslots > 1) {
         SDFRT_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
-        for (int sl = 0; sl < 2; ++sl) SDFRT_CUDA(ctx, cudaStreamWaitEvent(ctx->aux[sl], ctx->ev_fork, 0));
+        for (int sl = 0; sl < nslots; ++sl) SDFRT_CUDA(ctx, cudaStreamWaitEvent(ctx->aux[sl], ctx->ev_fork, 0));
     }
     unsigned long long bi = 0;
     for (unsigned long long item0 = 0; item0 < n; item0 += B, ++bi) {
-        const int sl = nslots > 1 ? (int)(bi & 1) : 0;
+        const int sl = (int)(bi % (unsigned long long)nslots);
         cudaStream_t bs = nslots > 1 ? ctx->aux[sl] : st;
         sdfrt_ctx::Scratch& sc = ctx->scratch[sl];
         unsigned* work = ctx->work + sl * WQ_COUNT;
@@ -335,7 +342,7 @@ int launch_forward(sdfrt_ctx* ctx, const PassParams& ps, float* film, cudaStream
                                   sc.its, rec_b, ctx->rec_stride, work + WQ_PRIMARY_CHUNK); }
         const float* its = DIFF ? rec_b : sc.its;
         { LaunchScope ls(ctx, 2, bs);
-          k_shade<DIFF><<<regions, 256, 0, bs>>>(ctx->sc, ps, item0, cnt, region, its, q, film,
+          k_shade<DIFF><<<regions, 256, 0, bs>>>(ctx->sc, ps, item0, cnt, region, reinterpret_cast<const SegIn*>(sc.segs), its, q, film,
                                                  DIFF ? rec_b + REC_S_STATE * ctx->rec_stride : nullptr, ctx->counters); }
         if (ctx->sc.integrator == INTEGRATOR_DIRECT) {
             // shadow march over the region-compacted queue
@@ -343,14 +350,14 @@ int launch_forward(sdfrt_ctx* ctx, const PassParams& ps, float* film, cudaStream
               launch_march_mode<DIFF>(ctx, ctx->cache_mode[DIFF ? 3 : 1], need, bs, reinterpret_cast<const SegIn*>(sc.ssegs), q.count,
                                       regions * region, region, 0, sc.s_its, sc.srec, B, work + WQ_SHADOW_CHUNK); }
             { LaunchScope ls(ctx, 4, bs);
-              k_shadow_splat<DIFF><<<regions, 256, 0, bs>>>(ctx->sc, ps, item0, region, q.count, reinterpret_cast<const float4*>(sc.sinfo),
+              k_shadow_splat<DIFF><<<regions, 256, 0, bs>>>(ctx->sc, ps, item0, region, reinterpret_cast<const SegIn*>(sc.segs), q.count, reinterpret_cast<const float4*>(sc.sinfo),
                                                             sc.s_its, sc.srec, B, film, rec_b, ctx->rec_stride); }
         }
         SDFRT_CUDA(ctx, cudaGetLastError());
     }
     // join: the caller's stream continues after both internal streams are done
     if (nslots > 1) {
-        for (int sl = 0; sl < 2; ++sl) {
+        for (int sl = 0; sl < nslots; ++sl) {
             SDFRT_CUDA(ctx, cudaEventRecord(ctx->ev_join[sl], ctx->aux[sl]));
             SDFRT_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join[sl], 0));
         }
@@ -408,8 +415,10 @@ sdfrt_ctx* sdfrt_create(int device, int* status) {
         return nullptr;
     }
     ctx->num_sms = prop.multiProcessorCount;
-    bool ok = cudaMalloc((void**)&ctx->work, 2 * WQ_COUNT * sizeof(unsigned)) == cudaSuccess;
-    for (int i = 0; i < 2; ++i) {
+    bool ok = cudaMalloc((void**)&ctx->work, kSlots * WQ_COUNT * sizeof(unsigned)) == cudaSuccess;
+    if (const char* e = std::getenv("SDFRT_SLOTS")) ctx->max_slots = std::max(1, std::min(kSlots, std::atoi(e)));          // developer overrides
+    if (const char* e = std::getenv("SDFRT_BATCH_LOG2")) ctx->batch_target = 1ull << std::max(16, std::min(28, std::atoi(e)));
+    for (int i = 0; i < kSlots; ++i) {
         ok = ok && cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking) == cudaSuccess;
         ok = ok && cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
     }
@@ -445,7 +454,7 @@ void sdfrt_destroy(sdfrt_ctx* ctx) {
     for (auto& sc : ctx->scratch) {
         cudaFree(sc.segs); cudaFree(sc.its); cudaFree(sc.ssegs); cudaFree(sc.sinfo); cudaFree(sc.s_its); cudaFree(sc.srec); cudaFree(sc.scount);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kSlots; ++i) {
         if (ctx->aux[i]) cudaStreamDestroy(ctx->aux[i]);
         if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
     }
@@ -629,6 +638,12 @@ int sdfrt_get_stats(sdfrt_ctx* ctx, sdfrt_stats* out, int reset, void* stream) {
 int sdfrt_set_profiling(sdfrt_ctx* ctx, int enable) {
     if (!ctx) return SDFRT_ERR_INVALID;
     ctx->profiling = enable != 0;
+    return SDFRT_OK;
+}
+
+int sdfrt_set_overlap(sdfrt_ctx* ctx, int enable) {
+    if (!ctx) return SDFRT_ERR_INVALID;
+    ctx->overlap = enable != 0;
     return SDFRT_OK;
 }
 

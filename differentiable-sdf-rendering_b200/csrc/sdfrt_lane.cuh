@@ -326,22 +326,34 @@ SDFRT_HD void lane_backward(const SceneParams& sc, const PassParams& ps, unsigne
     const int x1 = (int)floorf(pfx + rad), y1 = (int)floorf(pfy + rad);
     V3 c_hat = v3(0.f);
     float wch_hat = 0.f, u_hat = 0.f, v_hat = 0.f;
-    for (int by = y0; by <= y1; ++by) {
-        if (by < 0 || by >= Hb) continue;
-        const float fy = filter_eval(sc.S, (float)by - pfy);
-        const float dfy = filter_deriv(sc.S, (float)by - pfy);
-        for (int bx = x0; bx <= x1; ++bx) {
-            if (bx < 0 || bx >= Wb) continue;
-            const float fx = filter_eval(sc.S, (float)bx - pfx);
-            const float dfx = filter_deriv(sc.S, (float)bx - pfx);
-            const float* a = film_adj + ((size_t)by * Wb + bx) * 4;
-            const float a0 = a[0], a1 = a[1], a2 = a[2], a3 = a[3];
-            const float w = fx * fy;
-            c_hat += w * V3{a0, a1, a2};
-            wch_hat += w * a3;
-            const float s = a0 * rgb.x + a1 * rgb.y + a2 * rgb.z + a3;  // d L / d f_q  (c = rgb, wch = 1)
-            u_hat += -dfx * fy * s;  // d f_q / d u = -fx'(bx - pfx) fy
-            v_hat += -fx * dfy * s;
+    {
+        // separable filter: <= 5 taps per axis (radius <= 2.5), weights and derivatives evaluated once per axis
+        float fxs[6], dfxs[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const float t = (float)(x0 + i) - pfx;
+            const bool in = (x0 + i <= x1) & (x0 + i >= 0) & (x0 + i < Wb);
+            fxs[i] = in ? filter_eval(sc.S, t) : 0.f;
+            dfxs[i] = in ? filter_deriv(sc.S, t) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            const int by = y0 + j;
+            if (by > y1 || by < 0 || by >= Hb) continue;
+            const float fy = filter_eval(sc.S, (float)by - pfy);
+            const float dfy = filter_deriv(sc.S, (float)by - pfy);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                if (fxs[i] == 0.f && dfxs[i] == 0.f) continue;
+                const float* a = film_adj + ((size_t)by * Wb + (x0 + i)) * 4;
+                const float a0 = a[0], a1 = a[1], a2 = a[2], a3 = a[3];
+                const float w = fxs[i] * fy;
+                c_hat += w * V3{a0, a1, a2};
+                wch_hat += w * a3;
+                const float sq = a0 * rgb.x + a1 * rgb.y + a2 * rgb.z + a3;  // d L / d f_q  (c = rgb, wch = 1)
+                u_hat += -dfxs[i] * fy * sq;  // d f_q / d u = -fx'(bx - pfx) fy
+                v_hat += -fxs[i] * dfy * sq;
+            }
         }
     }
     // c = rw * rgb, wch = div * rw  (values rw = div = 1)

@@ -84,6 +84,16 @@ __device__ __forceinline__ ItemRay item_ray(const SceneParams& sc, const PassPar
     return r;
 }
 
+// film position of the re-projected sample from the (unit) camera-ray direction: sensor_project(o + d) only depends on d
+__device__ __forceinline__ void film_pos_from_dir(const SensorParams& S, V3 d, float& pfx, float& pfy) {
+    const V3 ref = V3{S.R[0][0] * d.x + S.R[1][0] * d.y + S.R[2][0] * d.z, S.R[0][1] * d.x + S.R[1][1] * d.y + S.R[2][1] * d.z,
+                      S.R[0][2] * d.x + S.R[1][2] * d.y + S.R[2][2] * d.z};
+    const float sx = 0.5f - 0.5f * ref.x / (ref.z * S.tan_half_fov);
+    const float sy = 0.5f - 0.5f * S.aspect * ref.y / (ref.z * S.tan_half_fov);
+    pfx = sx * (float)S.W + ((float)S.border - 0.5f);
+    pfy = sy * (float)S.H + ((float)S.border - 0.5f);
+}
+
 __device__ __forceinline__ SegIn make_seg(const TracerParams& T, V3 o, V3 d, float ray_maxt) {
     Segment s;
     const bool active = segment_begin(s, T, o, d, ray_maxt);
@@ -391,9 +401,9 @@ struct ShadowQueue {
 };
 
 template <bool DIFF>
-__global__ void __launch_bounds__(256) k_shade(const __grid_constant__ SceneParams sc, const __grid_constant__ PassParams ps,
-                                                unsigned long long item0, unsigned n, unsigned region, const float* __restrict__ its,
-                                                ShadowQueue q, float* __restrict__ film, float* __restrict__ rec_state,
+__global__ void __launch_bounds__(256, 3) k_shade(const __grid_constant__ SceneParams sc, const __grid_constant__ PassParams ps,
+                                                unsigned long long item0, unsigned n, unsigned region, const SegIn* __restrict__ psegs,
+                                                const float* __restrict__ its, ShadowQueue q, float* __restrict__ film, float* __restrict__ rec_state,
                                                 Counters* __restrict__ counters) {
     __shared__ SplatSmem s_splat[8];
     __shared__ unsigned s_count;
@@ -417,8 +427,12 @@ __global__ void __launch_bounds__(256) k_shade(const __grid_constant__ ScenePara
             const float its_t = its[i];
             const bool hit = isfinite(its_t);
             n_hit += hit;
-            const ItemRay r = item_ray(sc, ps, item0 + i);
-            pfx = r.pfx; pfy = r.pfy;
+            // the camera ray comes back from the primary segment (o, unit d): no sampler / sensor math for the 3/4 of the
+            // samples that miss; the wavefront lane index is only needed for the emitter sample of a hit
+            const float4 sa = __ldg(&psegs[i].a), sb = __ldg(&psegs[i].b);
+            struct { V3 o, d; } r;
+            r.o = V3{sa.x, sa.y, sa.z}; r.d = V3{sb.x, sb.y, sb.z};
+            film_pos_from_dir(sc.S, r.d, pfx, pfy);
             if (sc.integrator == INTEGRATOR_SILHOUETTE) {
                 rgb = v3(hit ? 1.f : 0.f);
             } else if (!hit) {
@@ -433,7 +447,7 @@ __global__ void __launch_bounds__(256) k_shade(const __grid_constant__ ScenePara
                     rgb = v3(fmaxf(0.f, (nrm.x + nrm.y + nrm.z) * 0.57735026918962576f));
                 } else {
                     const float cos_i = -dot(nrm, r.d);
-                    Pcg32 rng = sampler_seed(ps.seed, (uint32_t)r.lane);
+                    Pcg32 rng = sampler_seed(ps.seed, (uint32_t)decode_item(sc.S, ps, item0 + i).lane);
                     (void)pcg_next_u32(rng); (void)pcg_next_u32(rng); (void)pcg_next_u32(rng);
                     const float u0 = pcg_next_f32(rng), u1 = pcg_next_f32(rng);
                     const ShadowRay sr = make_shadow_ray(sc.Sh, p, nrm, u0, u1);
@@ -484,8 +498,8 @@ __global__ void __launch_bounds__(256) k_shade(const __grid_constant__ ScenePara
 // one block per region: visibility -> splat; DIFF: scatter the shadow tracer record to the lane records
 template <bool DIFF>
 __global__ void __launch_bounds__(256) k_shadow_splat(const __grid_constant__ SceneParams sc, const __grid_constant__ PassParams ps,
-                                                       unsigned long long item0, unsigned region, const unsigned* __restrict__ region_count,
-                                                       const float4* __restrict__ info, const float* __restrict__ s_its,
+                                                       unsigned long long item0, unsigned region, const SegIn* __restrict__ psegs,
+                                                       const unsigned* __restrict__ region_count, const float4* __restrict__ info, const float* __restrict__ s_its,
                                                        const float* __restrict__ srec, unsigned long long srec_stride,
                                                        float* __restrict__ film, float* __restrict__ rec,
                                                        unsigned long long rec_stride) {
@@ -503,8 +517,8 @@ __global__ void __launch_bounds__(256) k_shadow_splat(const __grid_constant__ Sc
             const unsigned i = __float_as_uint(inf.w);
             const float its_s = DIFF ? srec[slot] : s_its[slot];
             const bool occluded = isfinite(its_s);
-            const ItemRay r = item_ray(sc, ps, item0 + i);
-            pfx = r.pfx; pfy = r.pfy;
+            const float4 sb = __ldg(&psegs[i].b);
+            film_pos_from_dir(sc.S, V3{sb.x, sb.y, sb.z}, pfx, pfy);
             if (!occluded) rgb = V3{inf.x, inf.y, inf.z};
             if (DIFF && !occluded) {
                 float* d = rec + i;

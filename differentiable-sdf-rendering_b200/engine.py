@@ -157,6 +157,9 @@ class Context:
     def set_profiling(self, enable=True):
         check(self.ctx, self.lib.sdfrt_set_profiling(self.ctx, int(enable)))
 
+    def set_overlap(self, enable=True):
+        check(self.ctx, self.lib.sdfrt_set_overlap(self.ctx, int(enable)))
+
     def timing(self):
         """{class: (milliseconds, launches)} of the launches since the last call (CUDA events on the launching stream)."""
         ms = (C.c_float * 8)()

@@ -156,6 +156,10 @@ int sdfrt_get_stats(sdfrt_ctx* ctx, sdfrt_stats* out, int reset, void* stream);
  * milliseconds of every launch since the last call into ms[8] and the launch counts into launches[8]. */
 enum { SDFRT_NUM_KERNEL_CLASSES = 8 };
 int sdfrt_set_profiling(sdfrt_ctx* ctx, int enable);
+/* Batches of a forward sweep normally alternate between two internal streams (the tail of one batch's persistent
+ * kernels overlaps the next batch).  enable = 0 serialises them on the caller's stream, which makes the per-kernel
+ * event timings additive (used for roofline reporting). */
+int sdfrt_set_overlap(sdfrt_ctx* ctx, int enable);
 int sdfrt_get_timing(sdfrt_ctx* ctx, float* ms, int* launches);
 
 /* ---- test hooks / helpers used by the reference's callers ------------------------------ */
