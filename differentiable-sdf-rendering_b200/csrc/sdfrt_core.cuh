@@ -22,6 +22,13 @@
 #else
 #define SDFRT_HD inline
 #endif
+// Division in the silhouette-weight arithmetic of the differentiable tracer (weights, not positions): on the device the
+// 2-ulp MUFU-based form; the hit/miss decisions and step lengths never go through it.
+#if defined(__CUDA_ARCH__)
+#define SDFRT_FDIV(a, b) __fdividef((a), (b))
+#else
+#define SDFRT_FDIV(a, b) ((a) / (b))
+#endif
 
 namespace sdfrt {
 
@@ -108,7 +115,7 @@ struct ShadingParams {
 };
 struct Counters {  // device work counters (unsigned long long for atomicAdd)
     unsigned long long n_rays, n_evals_value, n_evals_grad, n_evals_hess, n_scatter_sites, n_albedo_lookups,
-        n_steps_max, n_hits, n_evals_adjoint, n_tap_loads;
+        n_steps_max, n_hits, n_evals_adjoint, n_tap_loads, n_skipped;
 };
 
 constexpr float kBBoxDelta = 0.05f;     // python/shapes.py:416-418
@@ -373,18 +380,18 @@ SDFRT_HD float ipow(float b, int e) {
 SDFRT_HD float eval_trace_weight(const TracerParams& P, V3 d, int i, V3 x, float sdf_value, V3 g, const S3& H, V3& weight_d) {
     const float n_dot_d = dot(g, d);
     const float n_dot_n = dot(g, g);
-    const float dot_ratio = n_dot_d / n_dot_n;
+    const float dot_ratio = SDFRT_FDIV(n_dot_d, n_dot_n);
     const float denom = P.sil_weight_epsilon + fabsf(sdf_value) + P.sil_weight_offset * n_dot_d * dot_ratio;
-    const float dist_weight = 1.f / ipow(denom, P.weight_power);
+    const float dist_weight = SDFRT_FDIV(1.f, ipow(denom, P.weight_power));
     V3 bbox_dist_d;
     const float bbox_dist = bbox_distance_inside_d(x, bbox_dist_d);
     const float bbox_eps = 0.01f;
-    const float bbox_weight = (i > 0) ? fminf(bbox_dist, bbox_eps) / bbox_eps : 1.f;
+    const float bbox_weight = (i > 0) ? SDFRT_FDIV(fminf(bbox_dist, bbox_eps), bbox_eps) : 1.f;
     const float weight = dist_weight * bbox_weight;
-    const V3 bbox_weight_d = ((i > 0) & (bbox_dist < bbox_eps)) ? bbox_dist_d / bbox_eps : v3(0.f);
+    const V3 bbox_weight_d = ((i > 0) & (bbox_dist < bbox_eps)) ? bbox_dist_d * SDFRT_FDIV(1.f, bbox_eps) : v3(0.f);
     const V3 gradient = (2.f * dot_ratio) * (d - dot_ratio * g);
     const V3 denom_d = sign1(sdf_value) * g + P.sil_weight_offset * mul(H, gradient);  // gradient @ H (H symmetric)
-    const V3 dist_weight_d = (-(float)P.weight_power * dist_weight / denom) * denom_d;
+    const V3 dist_weight_d = SDFRT_FDIV(-(float)P.weight_power * dist_weight, denom) * denom_d;
     weight_d = dist_weight * bbox_weight_d + bbox_weight * dist_weight_d;
     return weight;
 }
@@ -485,7 +492,7 @@ SDFRT_HD bool diff_step(Segment& s, DiffAcc& a, const TracerParams& P, float sdf
     float weight = eval_trace_weight(P, d, s.i, x, sdf_value, g, H, weight_d);
     float inv_extra_w_den = 0.f, dist_difference = 0.f;
     if (P.use_extra_weight) {
-        inv_extra_w_den = 1.f / fminf(P.extra_thresh, surf_dist);
+        inv_extra_w_den = SDFRT_FDIV(1.f, fminf(P.extra_thresh, surf_dist));
         dist_difference = a.prev_surf_dist - surf_dist;
         a.extra_weight_sum += (dist_difference >= 0.f) ? dist_difference * inv_extra_w_den : 0.f;
         a.extra_weight_sum = fminf(a.extra_weight_sum, 1.f);
@@ -758,6 +765,90 @@ SDFRT_HD V3 eval_albedo(const AlbedoView& A, V3 p, AlbedoTaps* taps, V3 dwd[3] /
         dwd[2] = V3{gx.z, gy.z, gz.z};
     }
     return rho;
+}
+
+// ------------------------------------------------------------------------------------
+// Conservative empty-space test: per-brick SDF minima + 3-D DDA (rationale in sdfrt_march.cuh)
+// ------------------------------------------------------------------------------------
+constexpr int kBrick = 4;  // brick edge in texels
+struct BrickView {
+    const float* data;  // (nz, ny, nx) brick minima dilated by `dilation` bricks, or nullptr
+    int nx, ny, nz;
+};
+
+// 3-D DDA over the brick lattice in texel coordinates c = x * R - 0.5 (cells of kBrick texels; indices clamped on read):
+// true iff every brick pierced by o + t d, t in [t0, t1], has a (dilated) minimum > thresh.
+SDFRT_HD bool ray_provably_clear(const BrickView& B, const GridView& G, V3 o, V3 d, float t0, float t1, float thresh) {
+    if (B.data == nullptr || !(t1 >= t0)) return false;
+    const float inv = 1.f / (float)kBrick;
+    const float cx = ((o.x - G.px) * (float)G.rx - 0.5f) * inv, cy = ((o.y - G.py) * (float)G.ry - 0.5f) * inv,
+                cz = ((o.z - G.pz) * (float)G.rz - 0.5f) * inv;
+    const float dx = d.x * (float)G.rx * inv, dy = d.y * (float)G.ry * inv, dz = d.z * (float)G.rz * inv;
+    const float px = cx + t0 * dx, py = cy + t0 * dy, pz = cz + t0 * dz;
+    int ix = (int)floorf(px), iy = (int)floorf(py), iz = (int)floorf(pz);
+    const int sx = dx > 0.f ? 1 : -1, sy = dy > 0.f ? 1 : -1, sz = dz > 0.f ? 1 : -1;
+    const float idx = dx != 0.f ? 1.f / fabsf(dx) : INFINITY, idy = dy != 0.f ? 1.f / fabsf(dy) : INFINITY,
+                idz = dz != 0.f ? 1.f / fabsf(dz) : INFINITY;
+    float tx = dx != 0.f ? t0 + ((dx > 0.f ? (float)(ix + 1) - px : px - (float)ix)) * idx : INFINITY;
+    float ty = dy != 0.f ? t0 + ((dy > 0.f ? (float)(iy + 1) - py : py - (float)iy)) * idy : INFINITY;
+    float tz = dz != 0.f ? t0 + ((dz > 0.f ? (float)(iz + 1) - pz : pz - (float)iz)) * idz : INFINITY;
+    for (int it = 0; it < 8192; ++it) {
+        const int qx = clampi(ix, 0, B.nx - 1), qy = clampi(iy, 0, B.ny - 1), qz = clampi(iz, 0, B.nz - 1);
+        if (!(B.data[(qz * B.ny + qy) * B.nx + qx] > thresh)) return false;
+        const float tn = fminf(tx, fminf(ty, tz));
+        if (tn > t1) return true;
+        if (tx <= ty && tx <= tz) { ix += sx; tx += idx; }
+        else if (ty <= tz) { iy += sy; ty += idy; }
+        else { iz += sz; tz += idz; }
+    }
+    return false;
+}
+
+// The test is made once per PIXEL for the ray through the pixel centre.  Every sample ray of the pixel passes through the
+// camera apex within the angle `half_diag` of the centre ray, so each of its points y has a centre-line point y' with
+// |y - y'| <= delta = apex_dist_max * half_diag.  The base texel of y is then within ceil(delta R) + 1 texels of that of
+// y', and its 4 taps per axis within the brick of y' dilated by `dilation` = ceil((2 + ceil(delta R) + 1) / kBrick) bricks.
+struct EmptySpaceParams {
+    float delta;          // max distance between a sample-ray point and the centre line
+    float maxt_bound;     // upper bound of any segment's maxt (scales trace_eps / the warp epsilon)
+    float skip_eps;       // 0 (value pass) or the warp's edge_eps (DIFF pass, weight strategy 6); < 0 disables the test
+    int dilation;         // bricks
+};
+SDFRT_HD EmptySpaceParams empty_space_params(const SensorParams& S, const GridView& G, float skip_eps) {
+    EmptySpaceParams e;
+    const float ax = S.tan_half_fov / (float)S.W, ay = S.tan_half_fov / (S.aspect * (float)S.H);
+    const float half_diag = sqrtf(ax * ax + ay * ay);
+    const float cx = S.c[0] - 0.5f, cy = S.c[1] - 0.5f, cz = S.c[2] - 0.5f;
+    const float apex_dist_max = sqrtf(cx * cx + cy * cy + cz * cz) + 0.5f * 1.7320508f * (1.f + 2.f * kBBoxDelta) + 0.05f;
+    e.delta = apex_dist_max * half_diag * 1.05f;
+    e.maxt_bound = apex_dist_max;
+    e.skip_eps = skip_eps;
+    const float rmax = (float)(G.rx > G.ry ? (G.rx > G.rz ? G.rx : G.rz) : (G.ry > G.rz ? G.ry : G.rz));
+    const int k = (int)ceilf(e.delta * rmax) + 1;
+    e.dilation = (2 + k + kBrick - 1) / kBrick;
+    if (e.dilation > 4) e.skip_eps = -1.f;  // pixels too coarse relative to the grid: the bound would be useless
+    return e;
+}
+SDFRT_HD float empty_space_threshold(const TracerParams& T, const EmptySpaceParams& e) {
+    return fmaxf(T.trace_eps, e.skip_eps) * fmaxf(e.maxt_bound, 1.f) + 1e-4f;
+}
+SDFRT_HD bool pixel_provably_clear(const SensorParams& S, const GridView& G, const TracerParams& T, const BrickView& B,
+                                   const EmptySpaceParams& e, int px, int py) {
+    if (e.skip_eps < 0.f) return false;
+    V3 o, d; float maxt;
+    sensor_sample_ray(S, (float)(px - S.border) + 0.5f, (float)(py - S.border) + 0.5f, o, d, maxt);
+    d = normalize(d);
+    // centre line clipped against the bounding box inflated by delta (slab test as ray_box, python/shapes.py:129-131)
+    const float lo = -kBBoxDelta - e.delta, hi = 1.f + kBBoxDelta + e.delta;
+    const V3 r = V3{1.f / d.x, 1.f / d.y, 1.f / d.z};
+    const V3 t1 = V3{(lo - o.x) * r.x, (lo - o.y) * r.y, (lo - o.z) * r.z};
+    const V3 t2 = V3{(hi - o.x) * r.x, (hi - o.y) * r.y, (hi - o.z) * r.z};
+    float tn = fmaxf(fminf(t1.x, t2.x), fmaxf(fminf(t1.y, t2.y), fminf(t1.z, t2.z)));
+    float tf = fminf(fmaxf(t1.x, t2.x), fminf(fmaxf(t1.y, t2.y), fmaxf(t1.z, t2.z)));
+    if (!(tf >= tn)) return true;  // the whole pixel misses the bounding box: nothing to march anyway
+    tn = fmaxf(tn - e.delta, -e.delta);
+    tf = tf + e.delta;
+    return ray_provably_clear(B, G, o, d, tn, tf, empty_space_threshold(T, e));
 }
 
 }  // namespace sdfrt

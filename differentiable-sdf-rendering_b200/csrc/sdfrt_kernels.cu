@@ -195,6 +195,9 @@ struct sdfrt_ctx {
     } scratch[kSlots];            // one per pipeline slot
     cudaStream_t aux[kSlots] = {};   // batches rotate over internal streams so that the tail of one batch's persistent
     cudaEvent_t ev_fork = nullptr, ev_join[kSlots] = {};  // kernels overlaps the following batches
+    float *brick_raw = nullptr, *brick = nullptr, *pix_mask = nullptr;  // per-brick SDF minima (two ping-pong buffers) and the
+    size_t brick_raw_n = 0, brick_n = 0, pix_mask_n = 0;                // per-pixel result of the empty-space test
+    bool skip_empty = true;
     int max_slots = kSlots;
     unsigned long long batch_target = 0;  // camera samples per batch; 0 = n / 6 clamped to [2^22, 2^24] (measured best at c3)
     int num_sms = 0;
@@ -311,6 +314,37 @@ int launch_forward(sdfrt_ctx* ctx, const PassParams& ps, float* film, cudaStream
             if ((rc = ensure(ctx, &sc.s_its, &sc.s_its_n, (size_t)B))) return rc;
         }
     }
+    // empty-space test (rebuilt every sweep: the caller may have updated the grid in place): brick minima -> dilation ->
+    // one DDA per film pixel -> mask consumed by k_gen_primary
+    const unsigned char* mask = nullptr;
+    if (ctx->skip_empty) {
+        const GridView& G = ctx->sc.G;
+        // value pass: only the hit threshold matters.  DIFF pass: also the largest warp epsilon a lane can see
+        // (strategy 6: edge_eps * warp_t <= edge_eps * maxt, python/warp.py:41-45), so that its warp weight is exactly 0.
+        float skip_eps = 0.f;
+        if (DIFF && ctx->sc.W.kind == WARP_2D) skip_eps = ctx->sc.W.weight_strategy == 6 ? ctx->sc.W.edge_eps : -1.f;
+        if (ctx->sc.T.step_scale != 1.f) skip_eps = -1.f;  // scaled SDF values: the bound does not apply as is
+        const EmptySpaceParams e = empty_space_params(S, G, skip_eps);
+        if (e.skip_eps >= 0.f) {
+            BrickView bricks;
+            bricks.nx = (G.rx + kBrick - 1) / kBrick; bricks.ny = (G.ry + kBrick - 1) / kBrick; bricks.nz = (G.rz + kBrick - 1) / kBrick;
+            const size_t nb = (size_t)bricks.nx * bricks.ny * bricks.nz;
+            const int npix = (S.W + 2 * S.border) * (S.H + 2 * S.border);
+            if ((rc = ensure(ctx, &ctx->brick_raw, &ctx->brick_raw_n, nb))) return rc;
+            if ((rc = ensure(ctx, &ctx->brick, &ctx->brick_n, nb))) return rc;
+            if ((rc = ensure(ctx, &ctx->pix_mask, &ctx->pix_mask_n, (size_t)npix / 4 + 1))) return rc;
+            const unsigned gb = (unsigned)((nb + 255) / 256);
+            LaunchScope ls(ctx, 0, st);
+            k_brick_min<<<gb, 256, 0, st>>>(G, ctx->brick_raw, bricks.nx, bricks.ny, bricks.nz);
+            k_brick_dilate<<<gb, 256, 0, st>>>(ctx->brick_raw, ctx->brick, bricks.nx, bricks.ny, bricks.nz, e.dilation, 0);
+            k_brick_dilate<<<gb, 256, 0, st>>>(ctx->brick, ctx->brick_raw, bricks.nx, bricks.ny, bricks.nz, e.dilation, 1);
+            k_brick_dilate<<<gb, 256, 0, st>>>(ctx->brick_raw, ctx->brick, bricks.nx, bricks.ny, bricks.nz, e.dilation, 2);
+            bricks.data = ctx->brick;
+            k_pixel_clear<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(ctx->sc, bricks, e, reinterpret_cast<unsigned char*>(ctx->pix_mask));
+            ctx->n_launches += 4;
+            mask = reinterpret_cast<const unsigned char*>(ctx->pix_mask);
+        }
+    }
     // fork: the internal streams wait for everything queued on the caller's stream (film memset included)
     if (nslots > 1) {
         SDFRT_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
@@ -333,7 +367,7 @@ int launch_forward(sdfrt_ctx* ctx, const PassParams& ps, float* film, cudaStream
         while (region > 256u && (unsigned long long)cnt / region < 8ull * (unsigned long long)ctx->num_sms * 4ull) region >>= 1;
         const unsigned regions = (cnt + region - 1) / region;
         SDFRT_CUDA(ctx, cudaMemsetAsync(work, 0, WQ_COUNT * sizeof(unsigned), bs));
-        { LaunchScope ls(ctx, 0, bs); k_gen_primary<<<blocks256, 256, 0, bs>>>(ctx->sc, ps, item0, cnt, reinterpret_cast<SegIn*>(sc.segs)); }
+        { LaunchScope ls(ctx, 0, bs); k_gen_primary<<<blocks256, 256, 0, bs>>>(ctx->sc, ps, item0, cnt, reinterpret_cast<SegIn*>(sc.segs), mask, ctx->counters); }
         // primary march (+ refine); DIFF writes its_t into row 0 of the lane records
         float* rec_b = DIFF ? ctx->rec + item0 : nullptr;
         const unsigned need = (cnt + kMarchBlock - 1) / kMarchBlock;
@@ -417,6 +451,7 @@ sdfrt_ctx* sdfrt_create(int device, int* status) {
     ctx->num_sms = prop.multiProcessorCount;
     bool ok = cudaMalloc((void**)&ctx->work, kSlots * WQ_COUNT * sizeof(unsigned)) == cudaSuccess;
     if (const char* e = std::getenv("SDFRT_SLOTS")) ctx->max_slots = std::max(1, std::min(kSlots, std::atoi(e)));          // developer overrides
+    if (const char* e = std::getenv("SDFRT_SKIP_EMPTY")) ctx->skip_empty = std::atoi(e) != 0;
     if (const char* e = std::getenv("SDFRT_BATCH_LOG2")) ctx->batch_target = 1ull << std::max(16, std::min(28, std::atoi(e)));
     for (int i = 0; i < kSlots; ++i) {
         ok = ok && cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking) == cudaSuccess;
@@ -451,6 +486,7 @@ void sdfrt_destroy(sdfrt_ctx* ctx) {
     cudaFree(ctx->film_adj);
     cudaFree(ctx->counters);
     cudaFree(ctx->work);
+    cudaFree(ctx->brick_raw); cudaFree(ctx->brick); cudaFree(ctx->pix_mask);
     for (auto& sc : ctx->scratch) {
         cudaFree(sc.segs); cudaFree(sc.its); cudaFree(sc.ssegs); cudaFree(sc.sinfo); cudaFree(sc.s_its); cudaFree(sc.srec); cudaFree(sc.scount);
     }
@@ -627,6 +663,7 @@ int sdfrt_get_stats(sdfrt_ctx* ctx, sdfrt_stats* out, int reset, void* stream) {
     out->n_steps_max = c.n_steps_max; out->n_hits = c.n_hits;
     out->n_evals_adjoint = c.n_evals_adjoint;
     out->n_tap_loads = c.n_tap_loads;
+    out->n_skipped = c.n_skipped;
     out->n_launches = ctx->n_launches;
     if (reset) {
         SDFRT_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, sizeof(Counters), st));

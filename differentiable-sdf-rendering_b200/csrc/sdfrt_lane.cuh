@@ -270,11 +270,14 @@ SDFRT_HD void lane_backward(const SceneParams& sc, const PassParams& ps, unsigne
                             const float* rec /* already offset to this lane's record */, unsigned long long rec_stride, const BackwardTargets& tg, V3& grad_p,
                             SiteList& sites, LaneStats& st) {
     sites.n = 0;
-    CameraSample cs = camera_sample(sc, ps, lane);
-    const V3 o = cs.o, d0 = cs.d;
     const float* r = rec;
     const float its_t = r[REC_ITS_T * rec_stride];
     const bool hit = isfinite(its_t);
+    // A sample that misses and has no valid warp site (warp_t = inf: weight below threshold, bbox miss, or a ray the
+    // empty-space test skipped) carries no derivative at all: its only differentiable quantities are the warp outputs.
+    if (!hit && !(reparam_at_depth(sc.W, 0) && isfinite(r[REC_TAU * rec_stride]))) return;
+    CameraSample cs = camera_sample(sc, ps, lane);
+    const V3 o = cs.o, d0 = cs.d;
 
     // ---- recompute the forward values that the adjoint needs -----------------------------------
     V3 rgb = v3(0.f);

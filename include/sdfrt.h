@@ -84,6 +84,7 @@ typedef struct sdfrt_stats {
     uint64_t n_hits;
     uint64_t n_evals_adjoint; /* value+gradient+Hessian evaluations of the adjoint sweep (k_backward) */
     uint64_t n_tap_loads;     /* marcher evaluations that actually gathered their 4x4x4 block (tap-cache misses) */
+    uint64_t n_skipped;       /* camera rays proven clear of the surface by the brick lower bound (never marched) */
     uint64_t n_launches;      /* kernels launched by the library (host-side count) */
 } sdfrt_stats;
 

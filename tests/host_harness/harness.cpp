@@ -178,3 +178,71 @@ extern "C" int hh_march_profile(const hh_scene* h, unsigned seed, int spp, int s
     out[0] = n_rays; out[1] = n_evals; out[2] = n_interior; out[3] = n_same_cell; out[4] = n_refine; out[5] = n_hit; out[6] = n_same_cell_refine; out[7] = n_x_aligned;
     return 0;
 }
+
+// developer statistic: share of primary-march evaluations spent on rays that stay farther than `margin` from the surface
+extern "C" int hh_miss_profile(const hh_scene* h, unsigned seed, int spp, int stride, float margin, double* out) {
+    SceneParams sc = build(h);
+    PassParams ps = make_pass(sc.S, seed, spp, 0, 1);
+    double n_rays = 0, n_evals = 0, n_far_rays = 0, n_far_evals = 0, n_hit = 0, n_hit_evals = 0;
+    for (unsigned long long lane = ps.lane_begin; lane < ps.lane_end; lane += stride) {
+        CameraSample cs = camera_sample(sc, ps, lane);
+        Segment s;
+        bool active = segment_begin(s, sc.T, cs.o, cs.d, cs.maxt);
+        float minphi = 1e30f; int n = 0;
+        while (active) { float v = eval_value(sc.G, s.o + s.t * s.d); minphi = fminf(minphi, v); ++n; active = value_step(s, sc.T, v); }
+        n_rays += 1; n_evals += n;
+        if (isfinite(s.its_t)) { n_hit += 1; n_hit_evals += n; }
+        else if (minphi > margin) { n_far_rays += 1; n_far_evals += n; }
+    }
+    out[0] = n_rays; out[1] = n_evals; out[2] = n_far_rays; out[3] = n_far_evals; out[4] = n_hit; out[5] = n_hit_evals;
+    return 0;
+}
+
+// ---- empty-space test (csrc pixel_provably_clear): host construction of the dilated brick minima + property check ----
+// For every film pixel the test declares clear, EVERY sample ray of that pixel (all spp jitters of this seed) must never
+// see an SDF value <= its own threshold (hence cannot hit, and has zero warp weight).  Returns the number of violations;
+// out[0] = active rays in clear pixels, out[1] = active rays, out[2] = dilation used.
+extern "C" int hh_check_empty_space(const hh_scene* h, unsigned seed, int spp, float skip_eps, double* out) {
+    SceneParams sc = build(h);
+    PassParams ps = make_pass(sc.S, seed, spp, 0, 1);
+    const GridView& G = sc.G;
+    const EmptySpaceParams e = empty_space_params(sc.S, G, skip_eps);
+    out[2] = e.dilation;
+    const int nx = (G.rx + kBrick - 1) / kBrick, ny = (G.ry + kBrick - 1) / kBrick, nz = (G.rz + kBrick - 1) / kBrick;
+    std::vector<float> raw((size_t)nx * ny * nz, INFINITY), dil((size_t)nx * ny * nz, INFINITY);
+    for (int z = 0; z < G.rz; ++z) for (int y = 0; y < G.ry; ++y) for (int x = 0; x < G.rx; ++x) {
+        float& m = raw[((size_t)(z / kBrick) * ny + y / kBrick) * nx + x / kBrick];
+        m = fminf(m, G.data[((size_t)z * G.ry + y) * G.rx + x]);
+    }
+    const int D = e.dilation;
+    for (int bz = 0; bz < nz; ++bz) for (int by = 0; by < ny; ++by) for (int bx = 0; bx < nx; ++bx) {
+        float m = INFINITY;
+        for (int dz = -D; dz <= D; ++dz) for (int dy = -D; dy <= D; ++dy) for (int dx = -D; dx <= D; ++dx)
+            m = fminf(m, raw[((size_t)clampi(bz + dz, 0, nz - 1) * ny + clampi(by + dy, 0, ny - 1)) * nx + clampi(bx + dx, 0, nx - 1)]);
+        dil[((size_t)bz * ny + by) * nx + bx] = m;
+    }
+    BrickView B; B.data = dil.data(); B.nx = nx; B.ny = ny; B.nz = nz;
+    const int Wb = sc.S.W + 2 * sc.S.border;
+    int violations = 0; double n_clear = 0, n_rays = 0;
+    for (unsigned long long lane = ps.lane_begin; lane < ps.lane_end; ++lane) {
+        const unsigned long long pix = lane / (unsigned long long)spp;
+        const int py = (int)(pix / Wb), px = (int)(pix - (unsigned long long)py * Wb);
+        CameraSample cs = camera_sample(sc, ps, lane);
+        Segment s;
+        bool active = segment_begin(s, sc.T, cs.o, cs.d, cs.maxt);
+        if (!active) continue;
+        n_rays += 1;
+        if (!pixel_provably_clear(sc.S, G, sc.T, B, e, px, py)) continue;
+        n_clear += 1;
+        if (s.maxt > e.maxt_bound) ++violations;  // the bound used for the threshold must dominate every segment's maxt
+        const float own = fmaxf(sc.T.trace_eps, skip_eps) * fmaxf(s.maxt, 1.f);
+        while (active) {
+            const float v = eval_value(G, s.o + s.t * s.d);
+            if (!(v > own)) { ++violations; break; }
+            active = value_step(s, sc.T, v);
+        }
+        if (isfinite(s.its_t)) ++violations;
+    }
+    out[0] = n_clear; out[1] = n_rays;
+    return violations;
+}

@@ -138,3 +138,17 @@ def test_adjoint_is_linear_in_grad_image():
     gb = hs.backward(5, 4, film, rec, b)[0]
     gab = hs.backward(5, 4, film, rec, 2 * a - 3 * b)[0]
     assert np.abs(gab - (2 * ga - 3 * gb)).max() < 1e-4 * max(np.abs(ga).max(), np.abs(gb).max())
+
+
+@pytest.mark.parametrize('kind,R,W', [('sphere', 64, 48), ('knot', 64, 64), ('blobs', 96, 40)])
+def test_empty_space_test_is_conservative(kind, R, W):
+    """csrc pixel_provably_clear: no sample ray of a pixel declared clear ever sees an SDF value below its threshold (so
+    skipping its march cannot change its_t, and its warp weight is exactly zero)."""
+    import ctypes as C
+    sc, _, hs = make_pair(kind, R, W)
+    for skip_eps in (0.0, 0.01):
+        out = np.zeros(3)
+        HM.lib().hh_check_empty_space.restype = C.c_int
+        v = HM.lib().hh_check_empty_space(C.byref(hs.h), 3, 8, C.c_float(skip_eps), HM.fptr(out))
+        assert v == 0
+        assert out[0] > 0.1 * out[1], out    # and the test is not vacuous: a good share of the rays is skipped
