@@ -54,8 +54,8 @@ __global__ void __launch_bounds__(kBlock) k_backward(const __grid_constant__ Sce
     V3 gp = v3(0.f);
     SiteList sites;
     sites.n = 0;
-    if (item < ps.lane_end - ps.lane_begin) {
-        const WorkItem w = decode_item(sc.S, ps, item);
+    if (item < ps.n_items) {
+        const WorkItem w = decode_item(ps, item);
         lane_backward(sc, ps, w.lane, film_adj, rec + item, rec_stride, tg, gp, sites, st);
     }
     for (int q = 0; q < sites.n; ++q) scatter_site(tg.grad_sdf, sc.G, sites.s[q].x, sites.s[q].phi_hat, sites.s[q].g_hat);
@@ -198,6 +198,7 @@ struct sdfrt_ctx {
     float *brick_raw = nullptr, *brick = nullptr, *pix_mask = nullptr;  // per-brick SDF minima (two ping-pong buffers) and the
     size_t brick_raw_n = 0, brick_n = 0, pix_mask_n = 0;                // per-pixel result of the empty-space test
     bool skip_empty = true;
+    int min_live = kMinActive;  // slots that must be stepping for a warp to stay in the stepping loop
     int max_slots = kSlots;
     unsigned long long batch_target = 0;  // camera samples per batch; 0 = n / 6 clamped to [2^22, 2^24] (measured best at c3)
     int num_sms = 0;
@@ -271,7 +272,7 @@ int check_ready(sdfrt_ctx* ctx, int spp) {
 template <bool DIFF, int CACHE>
 void launch_march(sdfrt_ctx* ctx, unsigned grid, cudaStream_t st, const SegIn* segs, const unsigned* n_ptr, unsigned n_fixed, unsigned region,
                   int do_refine, float* out_its, float* rec_out, unsigned long long rec_stride, unsigned* chunk_counter) {
-    k_march<DIFF, CACHE><<<grid, kMarchBlock, 0, st>>>(ctx->sc.G, ctx->sc.T, segs, n_ptr /* region fill or null */, n_fixed /* slots */, region, do_refine, out_its, rec_out, rec_stride,
+    k_march<DIFF, CACHE><<<grid, kMarchBlock, 0, st>>>(ctx->sc.G, ctx->sc.T, segs, n_ptr /* region fill or null */, n_fixed /* slots */, region,  do_refine, ctx->min_live, out_its, rec_out, rec_stride,
                                                        chunk_counter, ctx->counters);
 }
 template <bool DIFF>
@@ -289,7 +290,7 @@ template <bool DIFF>
 int launch_forward(sdfrt_ctx* ctx, const PassParams& ps, float* film, cudaStream_t st) {
     SDFRT_CUDA(ctx, cudaSetDevice(ctx->device));
     SDFRT_CUDA(ctx, cudaMemsetAsync(film, 0, film_floats(ctx) * sizeof(float), st));
-    const unsigned long long n = ps.lane_end - ps.lane_begin;
+    const unsigned long long n = ps.n_items;
     if (n == 0) return SDFRT_OK;
     const SensorParams& S = ctx->sc.S;
     if ((unsigned long long)kBandRows * (unsigned long long)(S.W + 2 * S.border) * (unsigned long long)ps.spp > 0xffffffffull)
@@ -451,6 +452,7 @@ sdfrt_ctx* sdfrt_create(int device, int* status) {
     ctx->num_sms = prop.multiProcessorCount;
     bool ok = cudaMalloc((void**)&ctx->work, kSlots * WQ_COUNT * sizeof(unsigned)) == cudaSuccess;
     if (const char* e = std::getenv("SDFRT_SLOTS")) ctx->max_slots = std::max(1, std::min(kSlots, std::atoi(e)));          // developer overrides
+    if (const char* e = std::getenv("SDFRT_MIN_LIVE")) ctx->min_live = std::max(1, std::min(32, std::atoi(e)));
     if (const char* e = std::getenv("SDFRT_SKIP_EMPTY")) ctx->skip_empty = std::atoi(e) != 0;
     if (const char* e = std::getenv("SDFRT_BATCH_LOG2")) ctx->batch_target = 1ull << std::max(16, std::min(28, std::atoi(e)));
     for (int i = 0; i < kSlots; ++i) {
@@ -615,7 +617,7 @@ int sdfrt_adjoint_accumulate(sdfrt_ctx* ctx, uint32_t seed_grad, int spp_grad, f
     if (!film_accum) return fail(ctx, SDFRT_ERR_INVALID, "film_accum is null");
     SDFRT_CUDA(ctx, cudaSetDevice(ctx->device));
     const PassParams ps = make_pass(ctx->sc.S, seed_grad, spp_grad, ctx->rank, ctx->world);
-    const unsigned long long n = ps.lane_end - ps.lane_begin;
+    const unsigned long long n = ps.n_items;
     rc = ensure(ctx, &ctx->rec, &ctx->rec_capacity, (size_t)n * REC_COUNT + 1);
     if (rc) return rc;
     ctx->rec_stride = n;
@@ -640,7 +642,7 @@ int sdfrt_adjoint_backprop(sdfrt_ctx* ctx, const float* film_accum, const float*
     { LaunchScope ls(ctx, 5, st); k_film_adjoint<<<(npix + 255) / 256, 256, 0, st>>>(film_accum, grad_image, ctx->film_adj, S.W, S.H, S.border); }
     SDFRT_CUDA(ctx, cudaGetLastError());
     const PassParams& ps = ctx->adj_pass;
-    const unsigned long long n = ps.lane_end - ps.lane_begin;
+    const unsigned long long n = ps.n_items;
     if (n == 0) return SDFRT_OK;
     BackwardTargets tg;
     tg.grad_sdf = grad_sdf;

@@ -29,8 +29,42 @@ struct PassParams {
     uint32_t seed;
     int spp;
     int log2_spp;               // >= 0 if spp is a power of two (python/integrators/reparam.py:144-148)
-    unsigned long long lane_begin, lane_end;  // this rank's slice of the wavefront
+    // Multi-GPU partition: the film rows are cut into bands of kBandRows rows; rank r owns the bands r, r + world, ...
+    // (interleaved, so that every rank sees a similar mix of object and background).  `n_items` = camera samples of this rank.
+    int rank, world;
+    int Wb, Hb;                 // film size incl. border
+    unsigned long long n_items;
 };
+
+constexpr int kBandRows = 8;
+
+// Work item k of this rank -> pixel and wavefront lane.  Items walk the rank's bands in order, each band column by column
+// (8 rows x spp samples per column), so neighbouring items are neighbouring samples; lane indices -- and with them the
+// sampler streams -- stay the reference's scanline wavefront indices (python/integrators/reparam.py:141-155).
+struct WorkItem {
+    int px, py;
+    unsigned long long lane;
+};
+SDFRT_HD WorkItem decode_item(const PassParams& ps, unsigned long long k) {
+    const unsigned Wb = (unsigned)ps.Wb;
+    const unsigned long long per_band = (unsigned long long)kBandRows * Wb * (unsigned)ps.spp;  // < 2^32 (checked on the host)
+    const unsigned bl = (unsigned)(k / per_band);
+    const unsigned r = (unsigned)(k - (unsigned long long)bl * per_band);
+    const unsigned g = bl * (unsigned)ps.world + (unsigned)ps.rank;  // global band
+    const unsigned row0 = g * (unsigned)kBandRows;
+    const unsigned left = (unsigned)ps.Hb - row0;
+    const unsigned rows_here = left < (unsigned)kBandRows ? left : (unsigned)kBandRows;
+    const unsigned per_col = rows_here * (unsigned)ps.spp;
+    const unsigned x = r / per_col;
+    const unsigned rr = r - x * per_col;
+    const unsigned y_in = ps.log2_spp >= 0 ? (rr >> ps.log2_spp) : (rr / (unsigned)ps.spp);
+    const unsigned sidx = rr - y_in * (unsigned)ps.spp;
+    WorkItem w;
+    w.px = (int)x;
+    w.py = (int)(row0 + y_in);
+    w.lane = ((unsigned long long)w.py * Wb + x) * (unsigned)ps.spp + sidx;
+    return w;
+}
 
 // per-lane record written by lane_forward<true>, SoA with stride = number of local lanes
 enum {
@@ -96,8 +130,8 @@ SDFRT_HD ShadowRay make_shadow_ray(const ShadingParams& Sh, V3 p, V3 n, float u0
 // forward lane
 // ------------------------------------------------------------------------------------------------
 template <bool DIFF>
-SDFRT_HD void lane_forward(const SceneParams& sc, const PassParams& ps, unsigned long long lane, float* film, float* rec,
-                           unsigned long long rec_stride, LaneStats& st) {
+SDFRT_HD void lane_forward(const SceneParams& sc, const PassParams& ps, unsigned long long lane, float* film,
+                           float* rec /* already offset to this sample's record */, unsigned long long rec_stride, LaneStats& st) {
     CameraSample cs = camera_sample(sc, ps, lane);
     const V3 o = cs.o, d0 = cs.d;
     int nv = 0, nh = 0, nsteps = 0;
@@ -166,8 +200,7 @@ SDFRT_HD void lane_forward(const SceneParams& sc, const PassParams& ps, unsigned
     st.n_steps_max = st.n_steps_max > (unsigned)nsteps ? st.n_steps_max : (unsigned)nsteps;
 
     if (DIFF) {
-        const unsigned long long l = lane - ps.lane_begin;
-        float* r = rec + l;
+        float* r = rec;
         r[REC_ITS_T * rec_stride] = tr.its_t;
         r[REC_TAU * rec_stride] = tr.warp_t;
         r[REC_TAU_DX * rec_stride] = tr.warp_t_d.x; r[REC_TAU_DY * rec_stride] = tr.warp_t_d.y; r[REC_TAU_DZ * rec_stride] = tr.warp_t_d.z;

@@ -28,7 +28,6 @@ constexpr unsigned kMaxRegion = 2048;  // segments per region (a power of two in
                                        // marcher block takes from the global counter (2048 = one 8-pixel film column at
                                        // 256 spp); shadow segments are compacted per region
 constexpr int kMinActive = 24;         // leave the stepping loop when fewer slots are live
-constexpr int kBandRows = 8;
 
 // device work counters of one batch (zeroed before every batch)
 enum { WQ_PRIMARY_CHUNK = 0, WQ_SHADOW_CHUNK = 1, WQ_COUNT = 4 };
@@ -40,30 +39,6 @@ struct SegIn {
     float4 b;  // d.xyz, maxt
 };
 
-struct WorkItem {
-    int px, py;
-    unsigned long long lane;
-};
-__device__ __forceinline__ WorkItem decode_item(const SensorParams& S, const PassParams& ps, unsigned long long k) {
-    const unsigned Wb = (unsigned)(S.W + 2 * S.border);
-    const unsigned long long row0 = ps.lane_begin / ((unsigned long long)Wb * (unsigned)ps.spp);
-    const unsigned nrows = (unsigned)((ps.lane_end - ps.lane_begin) / ((unsigned long long)Wb * (unsigned)ps.spp));
-    const unsigned long long per_band = (unsigned long long)kBandRows * Wb * (unsigned)ps.spp;
-    const unsigned band = (unsigned)(k / per_band);
-    const unsigned r = (unsigned)(k - (unsigned long long)band * per_band);  // < 8 * Wb * spp (checked on the host)
-    const unsigned rows_here = min((unsigned)kBandRows, nrows - band * kBandRows);
-    const unsigned per_col = rows_here * (unsigned)ps.spp;
-    const unsigned x = r / per_col;
-    const unsigned rr = r - x * per_col;
-    const unsigned y_in = ps.log2_spp >= 0 ? (rr >> ps.log2_spp) : (rr / (unsigned)ps.spp);
-    const unsigned s = rr - y_in * (unsigned)ps.spp;
-    WorkItem w;
-    w.px = (int)x;
-    w.py = (int)(row0 + band * kBandRows + y_in);
-    w.lane = ((unsigned long long)w.py * Wb + x) * (unsigned)ps.spp + s;
-    return w;
-}
-
 // camera sample of a work item: ray + film position of its (re-projected) splat
 struct ItemRay {
     V3 o, d;
@@ -71,7 +46,7 @@ struct ItemRay {
     unsigned long long lane;
 };
 __device__ __forceinline__ ItemRay item_ray(const SceneParams& sc, const PassParams& ps, unsigned long long k) {
-    const WorkItem w = decode_item(sc.S, ps, k);
+    const WorkItem w = decode_item(ps, k);
     ItemRay r;
     r.lane = w.lane;
     Pcg32 rng = sampler_seed(ps.seed, (uint32_t)w.lane);
@@ -152,7 +127,7 @@ __global__ void __launch_bounds__(256) k_gen_primary(const __grid_constant__ Sce
     const unsigned i = blockIdx.x * 256u + threadIdx.x;
     bool skipped = false;
     if (i < n) {
-        const WorkItem w = decode_item(sc.S, ps, item0 + i);
+        const WorkItem w = decode_item(ps, item0 + i);
         const ItemRay r = item_ray(sc, ps, item0 + i);
         SegIn g = make_seg(sc.T, r.o, r.d, r.maxt);
         if (mask != nullptr && g.b.w >= 0.f && mask[w.py * (sc.S.W + 2 * sc.S.border) + w.px]) {
@@ -296,7 +271,7 @@ enum { SLOT_IDLE = 0, SLOT_MARCH = 1, SLOT_REFINE = 2, SLOT_DONE = 3 };
 // CACHE: 0 = gather every evaluation, 1 = tap cache in registers, 2 = tap cache in shared memory
 template <bool DIFF, int CACHE>
 __global__ void __launch_bounds__(kMarchBlock, DIFF ? (CACHE == 1 ? 3 : 4) : (CACHE == 1 ? 4 : 7)) k_march(const GridView G, const TracerParams T, const SegIn* __restrict__ segs,
-                                                        const unsigned* __restrict__ region_count, unsigned n_slots, unsigned region, int do_refine,
+                                                        const unsigned* __restrict__ region_count, unsigned n_slots, unsigned region, int do_refine, int min_live,
                                                         float* __restrict__ out_its, float* __restrict__ rec_out,
                                                         unsigned long long rec_stride, unsigned* __restrict__ region_counter,
                                                         Counters* __restrict__ counters) {
@@ -371,7 +346,7 @@ __global__ void __launch_bounds__(kMarchBlock, DIFF ? (CACHE == 1 ? 3 : 4) : (CA
             continue;
         }
         // ---- stepping loop: one SDF evaluation per live slot per trip ------------------------------------------------
-        const int min_active = exhausted ? 1 : kMinActive;
+        const int min_active = exhausted ? 1 : min_live;
         for (;;) {
             const bool live = (state == SLOT_MARCH) | (state == SLOT_REFINE);
             if (__popc(__ballot_sync(FULL, live)) < min_active) break;
@@ -501,7 +476,7 @@ __global__ void __launch_bounds__(256, 3) k_shade(const __grid_constant__ SceneP
                     rgb = v3(fmaxf(0.f, (nrm.x + nrm.y + nrm.z) * 0.57735026918962576f));
                 } else {
                     const float cos_i = -dot(nrm, r.d);
-                    Pcg32 rng = sampler_seed(ps.seed, (uint32_t)decode_item(sc.S, ps, item0 + i).lane);
+                    Pcg32 rng = sampler_seed(ps.seed, (uint32_t)decode_item(ps, item0 + i).lane);
                     (void)pcg_next_u32(rng); (void)pcg_next_u32(rng); (void)pcg_next_u32(rng);
                     const float u0 = pcg_next_f32(rng), u1 = pcg_next_f32(rng);
                     const ShadowRay sr = make_shadow_ray(sc.Sh, p, nrm, u0, u1);

@@ -1,6 +1,7 @@
 // sdfrt_params.h -- host-side translation of the public C structs (include/sdfrt.h) into the
 // plain parameter blocks consumed by the per-lane code (sdfrt_core.cuh / sdfrt_lane.cuh).
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
@@ -95,12 +96,15 @@ inline PassParams make_pass(const SensorParams& S, uint32_t seed, int spp, int r
     p.log2_spp = -1;
     for (int k = 0; k < 31; ++k)
         if ((1 << k) == spp) p.log2_spp = k;
-    // whole film rows per rank (contiguous lanes in the reference's scanline order)
-    const unsigned long long Wb = (unsigned long long)(S.W + 2 * S.border), Hb = (unsigned long long)(S.H + 2 * S.border);
-    const unsigned long long r0 = Hb * (unsigned long long)rank / (unsigned long long)world;
-    const unsigned long long r1 = Hb * (unsigned long long)(rank + 1) / (unsigned long long)world;
-    p.lane_begin = r0 * Wb * (unsigned long long)spp;
-    p.lane_end = r1 * Wb * (unsigned long long)spp;
+    p.rank = rank;
+    p.world = world;
+    p.Wb = S.W + 2 * S.border;
+    p.Hb = S.H + 2 * S.border;
+    // bands rank, rank + world, ... of kBandRows film rows each (the last band of the film may be shorter)
+    const int nbands = (p.Hb + kBandRows - 1) / kBandRows;
+    unsigned long long rows = 0;
+    for (int g = rank; g < nbands; g += world) rows += (unsigned long long)std::min(kBandRows, p.Hb - g * kBandRows);
+    p.n_items = rows * (unsigned long long)p.Wb * (unsigned long long)spp;
     return p;
 }
 

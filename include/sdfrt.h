@@ -120,9 +120,9 @@ int sdfrt_set_warp(sdfrt_ctx* ctx, const sdfrt_warp_params* p);   /* integrator.
 int sdfrt_set_sensor(sdfrt_ctx* ctx, const sdfrt_sensor* s);
 int sdfrt_set_shading(sdfrt_ctx* ctx, const sdfrt_shading* s);
 int sdfrt_set_integrator(sdfrt_ctx* ctx, int integrator);         /* SDFRT_INTEGRATOR_* */
-/* multi-GPU ray partition: this context renders wavefront lanes [lane_begin, lane_end) of the
- * (W+2b)(H+2b)*spp wavefront; expressed as fractions rank/world so it is spp-independent.
- * RNG streams stay keyed by the global lane index (python/integrators/reparam.py:51). */
+/* multi-GPU ray partition: the film rows (border included) are cut into bands of 8 rows; this context renders the
+ * samples of the bands rank, rank + world, ... (interleaved for load balance).  RNG streams stay keyed by the global
+ * wavefront lane index (python/integrators/reparam.py:51), so results do not depend on the world size. */
 int sdfrt_set_partition(sdfrt_ctx* ctx, int rank, int world);
 
 /* ---- rendering ---------------------------------------------------------------------- */

@@ -58,29 +58,27 @@ int cp_time_sample(const cp_scene* h, unsigned seed, int spp_primal, int spp_adj
     double nv = 0, nh = 0;
     // ---- primal sample
     PassParams pp = make_pass(sc.S, seed, spp_primal, 0, 1);
-    long long lo = (long long)((pp.lane_end - pp.lane_begin) / 2) - n_primal / 2;
+    long long lo = (long long)(pp.n_items / 2) - n_primal / 2;
     if (lo < 0) lo = 0;
     auto t0 = std::chrono::steady_clock::now();
 #pragma omp parallel for schedule(dynamic, 512) reduction(+ : nv, nh)
     for (long long l = lo; l < lo + n_primal; ++l) {
         LaneStats st = {0, 0, 0, 0, 0, 0, 0};
-        lane_forward<false>(sc, pp, (unsigned long long)l, film.data(), nullptr, 0, st);
+        lane_forward<false>(sc, pp, decode_item(pp, (unsigned long long)l).lane, film.data(), nullptr, 0, st);
         nv += st.n_value; nh += st.n_hess;
     }
     auto t1 = std::chrono::steady_clock::now();
     // ---- adjoint sample: forward (records) + backward
     PassParams pa = make_pass(sc.S, seed + 13, spp_adjoint, 0, 1);
-    long long la = (long long)((pa.lane_end - pa.lane_begin) / 2) - n_adjoint / 2;
+    long long la = (long long)(pa.n_items / 2) - n_adjoint / 2;
     if (la < 0) la = 0;
-    PassParams sub = pa;
-    sub.lane_begin = (unsigned long long)la;
-    sub.lane_end = (unsigned long long)(la + n_adjoint);
+    const PassParams& sub = pa;
     std::vector<float> rec((size_t)REC_COUNT * (size_t)n_adjoint, 0.f);
     std::fill(film.begin(), film.end(), 0.f);
 #pragma omp parallel for schedule(dynamic, 512) reduction(+ : nv, nh)
     for (long long l = la; l < la + n_adjoint; ++l) {
         LaneStats st = {0, 0, 0, 0, 0, 0, 0};
-        lane_forward<true>(sc, sub, (unsigned long long)l, film.data(), rec.data(), (unsigned long long)n_adjoint, st);
+        lane_forward<true>(sc, sub, decode_item(sub, (unsigned long long)l).lane, film.data(), rec.data() + (l - la), (unsigned long long)n_adjoint, st);
         nv += st.n_value; nh += st.n_hess;
     }
     const int Wb = sc.S.W + 2 * sc.S.border, Hb = sc.S.H + 2 * sc.S.border;
@@ -98,7 +96,7 @@ int cp_time_sample(const cp_scene* h, unsigned seed, int spp_primal, int spp_adj
         LaneStats st = {0, 0, 0, 0, 0, 0, 0};
         V3 gp = v3(0.f);
         SiteList sites;
-        lane_backward(sc, sub, (unsigned long long)l, film_adj.data(), rec.data() + (l - la), (unsigned long long)n_adjoint, tg, gp, sites, st);
+        lane_backward(sc, sub, decode_item(sub, (unsigned long long)l).lane, film_adj.data(), rec.data() + (l - la), (unsigned long long)n_adjoint, tg, gp, sites, st);
         for (int q = 0; q < sites.n; ++q) scatter_site(grad_sdf, sc.G, sites.s[q].x, sites.s[q].phi_hat, sites.s[q].g_hat);
         nh += st.n_hess;
     }

@@ -82,9 +82,10 @@ int hh_forward(const hh_scene* h, unsigned seed, int spp, int diff, float* film,
     const size_t nf = (size_t)(sc.S.W + 2 * sc.S.border) * (sc.S.H + 2 * sc.S.border) * 4;
     std::memset(film, 0, nf * sizeof(float));
     LaneStats st = {0, 0, 0, 0, 0, 0, 0};
-    const unsigned long long n = ps.lane_end - ps.lane_begin;
-    for (unsigned long long lane = ps.lane_begin; lane < ps.lane_end; ++lane) {
-        if (diff) lane_forward<true>(sc, ps, lane, film, rec, n, st);
+    const unsigned long long n = ps.n_items;
+    for (unsigned long long k = 0; k < n; ++k) {
+        const unsigned long long lane = decode_item(ps, k).lane;
+        if (diff) lane_forward<true>(sc, ps, lane, film, rec + k, n, st);
         else lane_forward<false>(sc, ps, lane, film, rec, n, st);
     }
     if (stats) { stats[0] = n; stats[1] = st.n_value; stats[2] = st.n_grad; stats[3] = st.n_hess; stats[4] = st.n_sites; stats[5] = st.n_steps_max; stats[6] = st.n_hit; }
@@ -125,10 +126,11 @@ int hh_backward(const hh_scene* h, unsigned seed, int spp, const float* film, co
     BackwardTargets tg; tg.grad_sdf = grad_sdf; tg.grad_albedo = grad_albedo;
     LaneStats st = {0, 0, 0, 0, 0, 0, 0};
     V3 gp = v3(0.f);
-    const unsigned long long n = ps.lane_end - ps.lane_begin;
-    for (unsigned long long lane = ps.lane_begin; lane < ps.lane_end; ++lane) {
+    const unsigned long long n = ps.n_items;
+    for (unsigned long long k = 0; k < n; ++k) {
+        const unsigned long long lane = decode_item(ps, k).lane;
         SiteList sites;
-        lane_backward(sc, ps, lane, adj.data(), rec + (lane - ps.lane_begin), n, tg, gp, sites, st);
+        lane_backward(sc, ps, lane, adj.data(), rec + k, n, tg, gp, sites, st);
         for (int q = 0; q < sites.n; ++q) scatter_site(grad_sdf, sc.G, sites.s[q].x, sites.s[q].phi_hat, sites.s[q].g_hat);
     }
     if (grad_p) { grad_p[0] += gp.x; grad_p[1] += gp.y; grad_p[2] += gp.z; }
@@ -140,7 +142,7 @@ int hh_rec_count() { return REC_COUNT; }
 unsigned long long hh_local_lanes(const hh_scene* h, int spp, int rank, int world) {
     SensorParams S = make_sensor(h->sensor);
     PassParams ps = make_pass(S, 0, spp, rank, world);
-    return ps.lane_end - ps.lane_begin;
+    return ps.n_items;
 }
 }
 
@@ -149,7 +151,7 @@ extern "C" int hh_march_profile(const hh_scene* h, unsigned seed, int spp, int s
     SceneParams sc = build(h);
     PassParams ps = make_pass(sc.S, seed, spp, 0, 1);
     double n_rays = 0, n_evals = 0, n_interior = 0, n_same_cell = 0, n_refine = 0, n_hit = 0, n_same_cell_refine = 0, n_x_aligned = 0;
-    for (unsigned long long lane = ps.lane_begin; lane < ps.lane_end; lane += stride) {
+    for (unsigned long long lane = 0; lane < ps.n_items; lane += stride) {
         CameraSample cs = camera_sample(sc, ps, lane);
         Segment s;
         bool active = segment_begin(s, sc.T, cs.o, cs.d, cs.maxt);
@@ -184,7 +186,7 @@ extern "C" int hh_miss_profile(const hh_scene* h, unsigned seed, int spp, int st
     SceneParams sc = build(h);
     PassParams ps = make_pass(sc.S, seed, spp, 0, 1);
     double n_rays = 0, n_evals = 0, n_far_rays = 0, n_far_evals = 0, n_hit = 0, n_hit_evals = 0;
-    for (unsigned long long lane = ps.lane_begin; lane < ps.lane_end; lane += stride) {
+    for (unsigned long long lane = 0; lane < ps.n_items; lane += stride) {
         CameraSample cs = camera_sample(sc, ps, lane);
         Segment s;
         bool active = segment_begin(s, sc.T, cs.o, cs.d, cs.maxt);
@@ -224,7 +226,7 @@ extern "C" int hh_check_empty_space(const hh_scene* h, unsigned seed, int spp, f
     BrickView B; B.data = dil.data(); B.nx = nx; B.ny = ny; B.nz = nz;
     const int Wb = sc.S.W + 2 * sc.S.border;
     int violations = 0; double n_clear = 0, n_rays = 0;
-    for (unsigned long long lane = ps.lane_begin; lane < ps.lane_end; ++lane) {
+    for (unsigned long long lane = 0; lane < ps.n_items; ++lane) {
         const unsigned long long pix = lane / (unsigned long long)spp;
         const int py = (int)(pix / Wb), px = (int)(pix - (unsigned long long)py * Wb);
         CameraSample cs = camera_sample(sc, ps, lane);
