@@ -38,16 +38,26 @@ __device__ __forceinline__ float warp_sum_f(float v) {
     return v;
 }
 
-// Adjoint sweep 2: closed-form adjoint per lane, 64-tap scatter of each site with `red.global.add.f32`.
-// (A per-warp shared-memory accumulation window was tried -- 8^3 voxels, shared atomics, one global red per touched
-// voxel -- and was slower: 10.1 ms vs 6.3 ms at c3; zeroing/flushing the window costs more than the L2 atomics it saves.)
+// Adjoint sweep 2: closed-form adjoint per lane, then the 64-tap scatter of its <= 3 sites.
+// ncu on the one-atomic-per-tap version: issue active 15 %, lg_throttle 6.2 + long_scoreboard 5.8 stall cycles per issued
+// instruction -- bound by the RED queue, not by arithmetic (profiles/r1_backward_direct_atomics.md).  Lanes of a warp are
+// samples of one pixel, so many of their sites share the SAME 4x4x4 block.  Each lane therefore publishes its 64 tap
+// values in shared memory ([lane][65], conflict free); lanes with equal block are grouped (ballot on the block key), the
+// group's values are summed "transposed" (tap t by lane t mod 32) and one `red.global.add.f32` per tap and group is issued.
+// (A per-warp 8^3 accumulation window with shared atomics was tried first and was slower: 10.1 vs 6.3 ms.)
+struct RowStore {
+    float* row;
+    __device__ __forceinline__ void operator()(int t, float v) const { row[t] = v; }
+};
+
 __global__ void __launch_bounds__(kBlock) k_backward(const __grid_constant__ SceneParams sc, const __grid_constant__ PassParams ps,
                                                       const float* __restrict__ film_adj, const float* __restrict__ rec,
                                                       unsigned long long rec_stride, BackwardTargets tg, float* grad_p,
                                                       Counters* counters) {
+    __shared__ float s_vals[kBlock / 32][32][65];
     const unsigned FULL = 0xffffffffu;
     const int lane_id = threadIdx.x & 31;
-    (void)FULL;
+    float(*vals)[65] = s_vals[threadIdx.x >> 5];
     // records are stored in work-item (band) order; the lane index is needed for the sampler and the pixel
     const unsigned long long item = (unsigned long long)blockIdx.x * kBlock + threadIdx.x;
     LaneStats st = {0, 0, 0, 0, 0, 0, 0};
@@ -58,7 +68,35 @@ __global__ void __launch_bounds__(kBlock) k_backward(const __grid_constant__ Sce
         const WorkItem w = decode_item(ps, item);
         lane_backward(sc, ps, w.lane, film_adj, rec + item, rec_stride, tg, gp, sites, st);
     }
-    for (int q = 0; q < sites.n; ++q) scatter_site(tg.grad_sdf, sc.G, sites.s[q].x, sites.s[q].phi_hat, sites.s[q].g_hat);
+    for (int q = 0; q < 3; ++q) {
+        const bool has = q < sites.n;
+        unsigned rem = __ballot_sync(FULL, has);
+        if (rem == 0u) break;
+        int bx = 0, by = 0, bz = 0, key = -1;
+        if (has) {
+            site_tap_values(sc.G, sites.s[q].x, sites.s[q].phi_hat, sites.s[q].g_hat, bx, by, bz, RowStore{vals[lane_id]});
+            key = (bz * sc.G.ry + by) * sc.G.rx + bx;
+        }
+        __syncwarp();
+        while (rem) {
+            const int leader = __ffs(rem) - 1;
+            const int lkey = __shfl_sync(FULL, key, leader);
+            const unsigned members = __ballot_sync(FULL, has && key == lkey);
+            const int lbx = __shfl_sync(FULL, bx, leader), lby = __shfl_sync(FULL, by, leader), lbz = __shfl_sync(FULL, bz, leader);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int t = lane_id + 32 * h;
+                float acc = 0.f;
+                for (unsigned m = members; m; m &= m - 1) acc += vals[__ffs(m) - 1][t];
+                if (acc != 0.f) {
+                    const int i = t & 3, j = (t >> 2) & 3, k = t >> 4;
+                    atomicAdd(tg.grad_sdf + ((size_t)(lbz + k) * sc.G.ry + (lby + j)) * (size_t)sc.G.rx + (lbx + i), acc);
+                }
+            }
+            rem &= ~members;
+        }
+        __syncwarp();
+    }
     {   // the adjoint sweep's evaluations are counted separately from the marchers'
         const unsigned h = warp_sum(st.n_hess), nsites = warp_sum(st.n_sites), al = warp_sum(st.n_albedo);
         if (lane_id == 0) {
@@ -308,11 +346,11 @@ int launch_forward(sdfrt_ctx* ctx, const PassParams& ps, float* film, cudaStream
         if ((rc = ensure(ctx, &sc.ssegs, &sc.ssegs_n, (size_t)B * 8))) return rc;
         if ((rc = ensure(ctx, &sc.sinfo, &sc.sinfo_n, (size_t)B * 4))) return rc;
         if ((rc = ensure(ctx, &sc.scount, &sc.scount_n, (size_t)(B / 256) + 1))) return rc;
+        if ((rc = ensure(ctx, &sc.s_its, &sc.s_its_n, (size_t)B))) return rc;
         if (DIFF) {
             if ((rc = ensure(ctx, &sc.srec, &sc.srec_n, (size_t)B * 9))) return rc;
         } else {
             if ((rc = ensure(ctx, &sc.its, &sc.its_n, (size_t)B))) return rc;
-            if ((rc = ensure(ctx, &sc.s_its, &sc.s_its_n, (size_t)B))) return rc;
         }
     }
     // empty-space test (rebuilt every sweep: the caller may have updated the grid in place): brick minima -> dilation ->
@@ -373,20 +411,31 @@ int launch_forward(sdfrt_ctx* ctx, const PassParams& ps, float* film, cudaStream
         float* rec_b = DIFF ? ctx->rec + item0 : nullptr;
         const unsigned need = (cnt + kMarchBlock - 1) / kMarchBlock;
         { LaunchScope ls(ctx, 1, bs);
-          launch_march_mode<DIFF>(ctx, ctx->cache_mode[DIFF ? 2 : 0], need, bs, reinterpret_cast<const SegIn*>(sc.segs), nullptr, cnt, region, 1,
-                                  sc.its, rec_b, ctx->rec_stride, work + WQ_PRIMARY_CHUNK); }
+          if (DIFF && reparam_at_depth(ctx->sc.W, 0))
+              launch_march_mode<true>(ctx, ctx->cache_mode[2], need, bs, reinterpret_cast<const SegIn*>(sc.segs), nullptr, cnt, region, 1,
+                                      nullptr, rec_b, ctx->rec_stride, work + WQ_PRIMARY_CHUNK);
+          else  // value tracer; a DIFF pass without a primary warp (DummyWarpField / None) only needs its_t (record row 0)
+              launch_march_mode<false>(ctx, ctx->cache_mode[0], need, bs, reinterpret_cast<const SegIn*>(sc.segs), nullptr, cnt, region, 1,
+                                       DIFF ? rec_b : sc.its, nullptr, 0, work + WQ_PRIMARY_CHUNK); }
         const float* its = DIFF ? rec_b : sc.its;
         { LaunchScope ls(ctx, 2, bs);
           k_shade<DIFF><<<regions, 256, 0, bs>>>(ctx->sc, ps, item0, cnt, region, reinterpret_cast<const SegIn*>(sc.segs), its, q, film,
                                                  DIFF ? rec_b + REC_S_STATE * ctx->rec_stride : nullptr, ctx->counters); }
         if (ctx->sc.integrator == INTEGRATOR_DIRECT) {
-            // shadow march over the region-compacted queue
+            // shadow march over the region-compacted queue.  The differentiable tracer is only needed if shadow rays are
+            // reparameterised (python/warp.py:103: max_reparam_depth); otherwise the value tracer's its_t is all the pass uses.
+            const bool shadow_diff = DIFF && reparam_at_depth(ctx->sc.W, 1);
             { LaunchScope ls(ctx, 3, bs);
-              launch_march_mode<DIFF>(ctx, ctx->cache_mode[DIFF ? 3 : 1], need, bs, reinterpret_cast<const SegIn*>(sc.ssegs), q.count,
-                                      regions * region, region, 0, sc.s_its, sc.srec, B, work + WQ_SHADOW_CHUNK); }
+              if (shadow_diff)
+                  launch_march_mode<true>(ctx, ctx->cache_mode[3], need, bs, reinterpret_cast<const SegIn*>(sc.ssegs), q.count,
+                                          regions * region, region, 0, nullptr, sc.srec, B, work + WQ_SHADOW_CHUNK);
+              else
+                  launch_march_mode<false>(ctx, ctx->cache_mode[1], need, bs, reinterpret_cast<const SegIn*>(sc.ssegs), q.count,
+                                           regions * region, region, 0, sc.s_its, nullptr, 0, work + WQ_SHADOW_CHUNK); }
+            const float* shadow_its = shadow_diff ? sc.srec : sc.s_its;
             { LaunchScope ls(ctx, 4, bs);
               k_shadow_splat<DIFF><<<regions, 256, 0, bs>>>(ctx->sc, ps, item0, region, reinterpret_cast<const SegIn*>(sc.segs), q.count, reinterpret_cast<const float4*>(sc.sinfo),
-                                                            sc.s_its, sc.srec, B, film, rec_b, ctx->rec_stride); }
+                                                            shadow_its, sc.srec, B, film, rec_b, ctx->rec_stride); }
         }
         SDFRT_CUDA(ctx, cudaGetLastError());
     }

@@ -263,6 +263,27 @@ SDFRT_HD void scatter_site_t(const GridView& G, V3 x, float phi_hat, V3 g_hat, A
         }
     }
 }
+// the 64 tap values of a site in block order t = (k*4 + j)*4 + i, and the block's base texel
+template <class Store>
+SDFRT_HD void site_tap_values(const GridView& G, V3 x, float phi_hat, V3 g_hat, int& bx, int& by, int& bz, Store store) {
+    CellSetup<1> s;
+    cell_setup<1>(G, x, s);
+    bx = s.bx; by = s.by; bz = s.bz;
+    const float gx = g_hat.x * (float)G.rx, gy = g_hat.y * (float)G.ry, gz = g_hat.z * (float)G.rz;
+    float ex[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ex[i] = phi_hat * s.wx[i] + gx * s.dx[i];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float a = s.wy[j] * s.wz[k];
+            const float bq = gy * s.dy[j] * s.wz[k] + gz * s.wy[j] * s.dz[k];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) store((k * 4 + j) * 4 + i, a * ex[i] + bq * s.wx[i]);
+        }
+    }
+}
 struct GlobalAdd {
     float* grad;
     int rx, ry;

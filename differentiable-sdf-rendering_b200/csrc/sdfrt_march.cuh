@@ -544,7 +544,7 @@ __global__ void __launch_bounds__(256) k_shadow_splat(const __grid_constant__ Sc
             const unsigned slot = region_base + j;
             const float4 inf = info[slot];
             const unsigned i = __float_as_uint(inf.w);
-            const float its_s = DIFF ? srec[slot] : s_its[slot];
+            const float its_s = s_its[slot];  // its_t of the shadow segment (value tracer's output, or row 0 of the DIFF records)
             const bool occluded = isfinite(its_s);
             const float4 sb = __ldg(&psegs[i].b);
             film_pos_from_dir(sc.S, V3{sb.x, sb.y, sb.z}, pfx, pfy);

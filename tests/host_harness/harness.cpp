@@ -248,3 +248,38 @@ extern "C" int hh_check_empty_space(const hh_scene* h, unsigned seed, int spp, f
     out[0] = n_clear; out[1] = n_rays;
     return violations;
 }
+
+// developer statistic: shadow rays (emitter samples of hit lanes): occluded / unoccluded-monotone / unoccluded-non-monotone
+extern "C" int hh_shadow_profile(const hh_scene* h, unsigned seed, int spp, int stride, double* out) {
+    SceneParams sc = build(h);
+    PassParams ps = make_pass(sc.S, seed, spp, 0, 1);
+    double n_shadow = 0, n_occ = 0, n_mono = 0, n_nonmono = 0, ev_occ = 0, ev_mono = 0, ev_nonmono = 0;
+    for (unsigned long long lane = 0; lane < ps.n_items; lane += stride) {
+        CameraSample cs = camera_sample(sc, ps, lane);
+        int ns = 0, nv = 0;
+        const float its_t = trace_non_diff(sc.G, sc.T, cs.o, cs.d, cs.maxt, true, ns, nv);
+        if (!isfinite(its_t)) continue;
+        const V3 p = cs.o + its_t * normalize(cs.d);
+        float phi; V3 g; S3 H;
+        eval_sdf<1>(sc.G, p, phi, g, H);
+        const V3 n = normalize(g);
+        const float u0 = pcg_next_f32(cs.rng), u1 = pcg_next_f32(cs.rng);
+        const ShadowRay sr = make_shadow_ray(sc.Sh, p, n, u0, u1);
+        if (!((-dot(n, normalize(cs.d)) > 0.f) & (dot(n, sr.d) > 0.f))) continue;
+        Segment s;
+        bool active = segment_begin(s, sc.T, sr.o, sr.d, sr.maxt);
+        float prev = 0.f; bool mono = true; int steps = 0;
+        while (active) {
+            const float v = eval_value(sc.G, s.o + s.t * s.d);
+            if (!(fabsf(v) > prev)) mono = false;
+            prev = fabsf(v); ++steps;
+            active = value_step(s, sc.T, v);
+        }
+        n_shadow += 1;
+        if (isfinite(s.its_t)) { n_occ += 1; ev_occ += steps; }
+        else if (mono) { n_mono += 1; ev_mono += steps; }
+        else { n_nonmono += 1; ev_nonmono += steps; }
+    }
+    out[0] = n_shadow; out[1] = n_occ; out[2] = n_mono; out[3] = n_nonmono; out[4] = ev_occ; out[5] = ev_mono; out[6] = ev_nonmono;
+    return 0;
+}

@@ -36,6 +36,12 @@ def build_scene(sdfrt, kind, R, W, integ, albedo_res=None, warp='default', H=Non
         integrator.warp_field = wf
     elif warp == 'dummy':
         integrator.warp_field = sdfrt.DummyWarpField(sdf)
+    elif isinstance(warp, dict):
+        wf = sdfrt.WarpField2D(sdf, weight_strategy=warp.get('weight_strategy', 6), edge_eps=warp.get('edge_eps', 0.01))
+        wf.clamping_thresh = warp.get('clamping_thresh', 0.05)
+        wf.max_reparam_depth = warp.get('max_reparam_depth', -1)
+        wf.normalize_warp_field = warp.get('normalize_warp_field', True)
+        integrator.warp_field = wf
     alb = None if albedo_res is None else osc.albedo_grid.float().cuda().contiguous()
     scene = sdfrt.Scene(integrator, [sdfrt.Sensor(osc.sensor.to_world, W, H)], albedo_grid=alb)
     return scene, osc
@@ -95,13 +101,26 @@ def test_eval_sdf_against_oracle(sdfrt_mod):
     assert (sdf.eval_grad(x).cpu().double() - g).abs().max() < 2e-5
 
 
-@pytest.mark.parametrize('warp,integ', [('dummy', 'sdf_direct_reparam'), (None, 'sdf_direct_reparam')])
+VARIANTS = [('dummy', 'sdf_direct_reparam'), (None, 'sdf_direct_reparam'),
+            (dict(max_reparam_depth=0), 'sdf_direct_reparam'),                        # configs.WarpPrimary
+            (dict(normalize_warp_field=False), 'sdf_direct_reparam'),                 # configs.WarpNotNormalized
+            (dict(weight_strategy=4, edge_eps=0.05, clamping_thresh=0.0), 'sdf_silhouette_reparam')]  # WarpField2D ctor defaults
+
+
+@pytest.mark.parametrize('warp,integ', VARIANTS)
 def test_variants_against_oracle(sdfrt_mod, warp, integ):
-    """DummyWarpField / warp_field=None: shading gradients only (configs.OnlyShadingGrad)."""
+    """Configurations of python/configs.py beyond the default `Warp`: DummyWarpField / None (shading gradients only),
+    WarpPrimary, WarpNotNormalized, and the WarpField2D constructor defaults."""
     from oracle import sdf_oracle as O
     W, spp = 20, 4
     scene, osc = build_scene(sdfrt_mod, 'knot', 32, W, integ, warp=warp)
-    owf = O.DummyWarpField(osc.sdf) if warp == 'dummy' else None
+    if isinstance(warp, dict):
+        owf = O.WarpField2D(osc.sdf, weight_strategy=warp.get('weight_strategy', 6), edge_eps=warp.get('edge_eps', 0.01))
+        owf.clamping_thresh = warp.get('clamping_thresh', 0.05)
+        owf.max_reparam_depth = warp.get('max_reparam_depth', -1)
+        owf.normalize_warp_field = warp.get('normalize_warp_field', True)
+    else:
+        owf = O.DummyWarpField(osc.sdf) if warp == 'dummy' else None
     g_in = np.random.default_rng(1).uniform(-1, 1, size=(W, W, 3))
     img_o, g_o, _, _ = O.render_backward(osc, owf, integ, torch.from_numpy(g_in), seed=21, spp=spp)
     sdf = scene.integrator().sdf
@@ -220,3 +239,41 @@ def test_full_size_adjoint_linearity_and_host_api(big):
     ctx.set_sdf(sdf)
     assert (img_h.cuda() - img_dev).abs().max() < 1e-4
     assert (g_h.cuda() - g_dev).abs().max() < 1e-3 * g_dev.abs().max()
+
+
+def test_optimization_loop_reduces_loss(sdfrt_mod):
+    """The loop of python/shape_opt.py:76-105 in miniature (render -> L1 loss -> backward -> Adam step on sdf.data):
+    starting from a sphere of radius 0.3, the rendering moves towards that of radius 0.22."""
+    sdfrt = sdfrt_mod
+    R, W, spp = 48, 48, 16
+    sensors = sdfrt.get_regular_cameras(6, resx=W, resy=W)
+
+    def make(radius):
+        sdf = sdfrt.Grid3d(sdfrt.create_sphere_sdf((R, R, R), radius=radius), device=0)
+        integ = sdfrt.integrators.create('sdf_direct_reparam', sdf=sdf)
+        wf = sdfrt.WarpField2D(sdf, weight_strategy=6, edge_eps=0.01)
+        wf.clamping_thresh = 0.05
+        integ.warp_field = wf
+        return sdfrt.Scene(integ, sensors), sdf, integ
+
+    tscene, _, _ = make(0.22)
+    targets = [sdfrt.render(tscene, sensor=i, seed=100 + i, spp=64).clone() for i in range(3)]
+    scene, sdf, integ = make(0.3)
+    sdf.data.requires_grad_(True)
+    opt = torch.optim.Adam([sdf.data], lr=4e-3)
+    losses, seed = [], 0
+    for it in range(12):
+        opt.zero_grad()
+        total = 0.0
+        for i in range(3):
+            img = sdfrt.render(scene, sensor=i, seed=seed, spp=spp * 4, seed_grad=seed + 1 + 6, spp_grad=spp)
+            seed += 1 + 6
+            loss = (img - targets[i]).abs().mean() / 3
+            loss.backward()
+            total += loss.item()
+        sdf.data.grad.clamp_(-0.1, 0.1)             # python/variables.py:193-199
+        opt.step()
+        integ.parameters_changed()
+        losses.append(total)
+    assert np.isfinite(losses).all()
+    assert np.mean(losses[-3:]) < 0.8 * np.mean(losses[:3]), losses
