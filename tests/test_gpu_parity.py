@@ -241,11 +241,13 @@ def test_full_size_adjoint_linearity_and_host_api(big):
     assert (g_h.cuda() - g_dev).abs().max() < 1e-3 * g_dev.abs().max()
 
 
-def test_optimization_loop_reduces_loss(sdfrt_mod):
-    """The loop of python/shape_opt.py:76-105 in miniature (render -> L1 loss -> backward -> Adam step on sdf.data):
-    starting from a sphere of radius 0.3, the rendering moves towards that of radius 0.22."""
+def test_gradient_matches_finite_differences_of_the_loss(sdfrt_mod):
+    """The reference's own validation method (figures/result_utils.py:126-161: AD vs finite differences of a scene
+    parameter), applied to the optimisation loss of python/shape_opt.py:78-83: for the uniform offset sdf.data += c (which
+    shrinks / grows the object) dL/dc = sum of dL/d(sdf.data) must match the central difference of the primal loss.  The sum
+    averages the Monte Carlo noise of the per-voxel gradient; on the oracle the two agree to 4 %."""
     sdfrt = sdfrt_mod
-    R, W, spp = 48, 48, 16
+    R, W, spp = 48, 64, 64
     sensors = sdfrt.get_regular_cameras(6, resx=W, resy=W)
 
     def make(radius):
@@ -257,23 +259,24 @@ def test_optimization_loop_reduces_loss(sdfrt_mod):
         return sdfrt.Scene(integ, sensors), sdf, integ
 
     tscene, _, _ = make(0.22)
-    targets = [sdfrt.render(tscene, sensor=i, seed=100 + i, spp=64).clone() for i in range(3)]
+    targets = [sdfrt.render(tscene, sensor=i, seed=100 + i, spp=256).clone() for i in range(3)]
     scene, sdf, integ = make(0.3)
-    sdf.data.requires_grad_(True)
-    opt = torch.optim.Adam([sdf.data], lr=4e-3)
-    losses, seed = [], 0
-    for it in range(12):
-        opt.zero_grad()
-        total = 0.0
-        for i in range(3):
-            img = sdfrt.render(scene, sensor=i, seed=seed, spp=spp * 4, seed_grad=seed + 1 + 6, spp_grad=spp)
-            seed += 1 + 6
-            loss = (img - targets[i]).abs().mean() / 3
-            loss.backward()
-            total += loss.item()
-        sdf.data.grad.clamp_(-0.1, 0.1)             # python/variables.py:193-199
-        opt.step()
+    base = sdf.data.detach().clone()
+
+    def loss_at(offset, spp_primal):
+        with torch.no_grad():
+            sdf.data.copy_(base + offset)
         integ.parameters_changed()
-        losses.append(total)
-    assert np.isfinite(losses).all()
-    assert np.mean(losses[-3:]) < 0.8 * np.mean(losses[:3]), losses
+        with torch.no_grad():
+            return sum(((sdfrt.render(scene, sensor=i, seed=7 + i, spp=spp_primal) - targets[i]).abs().mean() / 3).item() for i in range(3))
+
+    sdf.data.requires_grad_(True)
+    for i in range(3):
+        img = sdfrt.render(scene, sensor=i, seed=7 + i, spp=256, seed_grad=20 + i, spp_grad=spp)
+        ((img - targets[i]).abs().mean() / 3).backward()
+    dL_dc = sdf.data.grad.sum().item()
+    sdf.data.requires_grad_(False)
+    delta = 0.01
+    fd = (loss_at(delta, 1024) - loss_at(-delta, 1024)) / (2 * delta)
+    assert fd < 0 and dL_dc < 0                       # shrinking the sphere towards the target lowers the loss
+    assert abs(dL_dc - fd) < 0.15 * abs(fd), (dL_dc, fd)

@@ -129,3 +129,43 @@ def test_reparam_gradient_matches_finite_differences_on_translation():
         fd.append((vals[0] - vals[1]) / (2 * eps))
     sc.sdf.p = torch.zeros(3, dtype=torch.float64)
     assert abs(gp[0].item() - fd[0]) < 0.2 * abs(fd[0]), (gp, fd)
+
+
+@pytest.mark.slow
+def test_loss_gradient_matches_finite_differences_uniform_offset():
+    """dL/dc for sdf.data += c (sum of the per-voxel gradient) vs the central difference of the primal L1 loss
+    (python/shape_opt.py:78-83 with the direct integrator); same method as figures/result_utils.py:126-161."""
+    R, W = 32, 32
+
+    def scene(radius, sidx):
+        x, y, z = O._grid_points(R)
+        sdf = (np.sqrt((x - .5) ** 2 + (y - .5) ** 2 + (z - .5) ** 2) - radius).astype(np.float32)
+        sensor = O.Sensor(to_world=O.look_at(O.regular_camera_origins(6)[sidx], [.5, .5, .5], [0, 1, 0]), width=W, height=W)
+        return O.Scene(sdf=O.Grid3d(torch.from_numpy(sdf).double()), sensor=sensor)
+
+    views = (0, 1)
+    with torch.no_grad():
+        targets = [O.render(scene(0.22, i), None, 'sdf_direct_reparam', seed=100 + i, spp=64) for i in views]
+    data = scene(0.3, 0).sdf.data.clone()
+
+    def loss_at(d, spp):
+        L = 0.0
+        for k, i in enumerate(views):
+            sc = scene(0.3, i)
+            sc.sdf.data = d
+            with torch.no_grad():
+                L += (O.render(sc, None, 'sdf_direct_reparam', seed=7 + i, spp=spp) - targets[k]).abs().mean().item() / len(views)
+        return L
+
+    g_sum = 0.0
+    for k, i in enumerate(views):
+        sc = scene(0.3, i)
+        sc.sdf.data = data
+        wf = O.WarpField2D(sc.sdf, weight_strategy=6, edge_eps=0.01)
+        wf.clamping_thresh = 0.05
+        with torch.no_grad():
+            img = O.render(sc, wf, 'sdf_direct_reparam', seed=7 + i, spp=64)
+        g_in = torch.sign(img - targets[k]) / img.numel() / len(views)
+        g_sum += O.render_backward(sc, wf, 'sdf_direct_reparam', g_in, seed=20 + i, spp=16)[1].sum().item()
+    fd = (loss_at(data + 0.01, 128) - loss_at(data - 0.01, 128)) / 0.02
+    assert fd < 0 and abs(g_sum - fd) < 0.15 * abs(fd), (g_sum, fd)
