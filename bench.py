@@ -25,8 +25,10 @@ WORKLOADS = {
     'c4_blobs512_512x512_64spp': ('blobs', 512, None, 512, 512, 64, 4, 12),
 }
 METRIC = "primary+adjoint Mrays/s"
-# dram__bytes_read+write of the k_march launches of one c3 step, from the committed ncu capture (profiles/); None = not captured
-NCU_DRAM_BYTES_PER_STEP = None
+# dram__bytes_read + dram__bytes_write of the k_march launches of ONE c3 step, from the committed ncu launch list
+# profiles/r1_final_launches_c3.csv (30 k_march launches: 6.03 GB; a step has 28) -- mostly the segment arrays and lane
+# records, the SDF grid itself stays in L2.  Only meaningful for the default workload.
+NCU_DRAM_BYTES_PER_STEP = {'c3_blobs256_tex_512x512_64spp': 5.6e9}
 
 
 def parse():
@@ -283,7 +285,7 @@ def run_gpu(args):
     march_ms = kernel_ms['k_march (primary+shadow segments)']
     achieved = march_bytes / (march_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": NCU_DRAM_BYTES_PER_STEP, "peak_source": peak_src, "kernel": "k_march (all launches of one step; batches serialised for this measurement)",
+                "traffic": NCU_DRAM_BYTES_PER_STEP.get(args.workload), "peak_source": peak_src, "kernel": "k_march (all launches of one step; batches serialised for this measurement)",
                 "dominant_kernel": dom, "kernel_ms_per_step": kernel_ms, "pass_ms": {"primal": t_primal, "adjoint_accumulate": t_accum,
                                                                                   "adjoint_backprop": t_back},
                 "algorithmic_bytes_per_step": march_bytes, "evals_per_step": march_evals,
