@@ -238,7 +238,7 @@ struct sdfrt_ctx {
     bool skip_empty = true;
     int min_live = kMinActive;  // slots that must be stepping for a warp to stay in the stepping loop
     int max_slots = kSlots;
-    unsigned long long batch_target = 0;  // camera samples per batch; 0 = n / 6 clamped to [2^22, 2^24] (measured best at c3)
+    unsigned long long batch_target = 0;  // camera samples per batch; 0 = n / 6 clamped to [2^20, 2^24] (measured best at c3)
     int num_sms = 0;
     int march_blocks[6] = {0, 0, 0, 0, 0, 0};  // resident blocks per SM of k_march<DIFF, CACHE> at [3*DIFF + CACHE]
     int cache_mode[4] = {1, 1, 0, 1};        // tap-cache mode of [value primary, value shadow, diff primary, diff shadow]
@@ -308,20 +308,21 @@ int check_ready(sdfrt_ctx* ctx, int spp) {
 
 
 template <bool DIFF, int CACHE>
-void launch_march(sdfrt_ctx* ctx, unsigned grid, cudaStream_t st, const SegIn* segs, const unsigned* n_ptr, unsigned n_fixed, unsigned region,
-                  int do_refine, float* out_its, float* rec_out, unsigned long long rec_stride, unsigned* chunk_counter) {
-    k_march<DIFF, CACHE><<<grid, kMarchBlock, 0, st>>>(ctx->sc.G, ctx->sc.T, segs, n_ptr /* region fill or null */, n_fixed /* slots */, region,  do_refine, ctx->min_live, out_its, rec_out, rec_stride,
-                                                       chunk_counter, ctx->counters);
+void launch_march(sdfrt_ctx* ctx, unsigned grid, cudaStream_t st, const SegIn* segs, const unsigned* region_fill, unsigned n_slots, unsigned region,
+                  int do_refine, float* out_its, float* rec_out, unsigned long long rec_stride, unsigned* region_counter) {
+    k_march<DIFF, CACHE><<<grid, kMarchBlock, 0, st>>>(ctx->sc.G, ctx->sc.T, segs, region_fill, n_slots, region, do_refine, ctx->min_live, out_its, rec_out,
+                                                       rec_stride, region_counter, ctx->counters);
 }
 template <bool DIFF>
-void launch_march_mode(sdfrt_ctx* ctx, int mode, unsigned need, cudaStream_t st, const SegIn* segs, const unsigned* n_ptr, unsigned n_fixed,
-                       unsigned region, int do_refine, float* out_its, float* rec_out, unsigned long long rec_stride, unsigned* chunk_counter) {
+void launch_march_mode(sdfrt_ctx* ctx, int mode, unsigned need, cudaStream_t st, const SegIn* segs, const unsigned* region_fill,
+                       unsigned n_slots, unsigned region, int do_refine, float* out_its, float* rec_out, unsigned long long rec_stride,
+                       unsigned* region_counter) {
     const int bps = ctx->march_blocks[(DIFF ? 3 : 0) + mode];
     unsigned grid = (unsigned)ctx->num_sms * (unsigned)bps;
     if (grid > need) grid = need;
-    if (mode == 0) launch_march<DIFF, 0>(ctx, grid, st, segs, n_ptr, n_fixed, region, do_refine, out_its, rec_out, rec_stride, chunk_counter);
-    else if (mode == 1) launch_march<DIFF, 1>(ctx, grid, st, segs, n_ptr, n_fixed, region, do_refine, out_its, rec_out, rec_stride, chunk_counter);
-    else launch_march<DIFF, 2>(ctx, grid, st, segs, n_ptr, n_fixed, region, do_refine, out_its, rec_out, rec_stride, chunk_counter);
+    if (mode == 0) launch_march<DIFF, 0>(ctx, grid, st, segs, region_fill, n_slots, region, do_refine, out_its, rec_out, rec_stride, region_counter);
+    else if (mode == 1) launch_march<DIFF, 1>(ctx, grid, st, segs, region_fill, n_slots, region, do_refine, out_its, rec_out, rec_stride, region_counter);
+    else launch_march<DIFF, 2>(ctx, grid, st, segs, region_fill, n_slots, region, do_refine, out_its, rec_out, rec_stride, region_counter);
 }  // camera samples per batch of the wavefront pipeline
 
 template <bool DIFF>
@@ -334,7 +335,7 @@ int launch_forward(sdfrt_ctx* ctx, const PassParams& ps, float* film, cudaStream
     if ((unsigned long long)kBandRows * (unsigned long long)(S.W + 2 * S.border) * (unsigned long long)ps.spp > 0xffffffffull)
         return fail(ctx, SDFRT_ERR_INVALID, "film row band exceeds 2^32 samples");
     unsigned long long target = ctx->batch_target;
-    if (target == 0) target = std::max<unsigned long long>(1ull << 22, std::min<unsigned long long>(1ull << 24, n / 6));
+    if (target == 0) target = std::max<unsigned long long>(1ull << 20, std::min<unsigned long long>(1ull << 24, n / 6));
     const unsigned long long nbatch = (n + target - 1) / target;
     unsigned long long B = (n + nbatch - 1) / nbatch;
     B = (B + kMaxRegion - 1) / kMaxRegion * kMaxRegion;  // whole regions per batch
