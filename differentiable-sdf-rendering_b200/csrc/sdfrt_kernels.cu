@@ -199,7 +199,7 @@ __global__ void k_eval_sdf(GridView G, const float* __restrict__ x, int n, int o
 // ----------------------------------------------------------------------------------------------------
 // context
 // ----------------------------------------------------------------------------------------------------
-constexpr int kSlots = 4;  // pipeline slots (internal streams + scratch sets) available to a forward sweep
+constexpr int kSlots = 8;  // pipeline slots (internal streams + scratch sets) available to a forward sweep
 
 struct sdfrt_ctx {
     int device = 0;
@@ -237,7 +237,7 @@ struct sdfrt_ctx {
     size_t brick_raw_n = 0, brick_n = 0, pix_mask_n = 0;                // per-pixel result of the empty-space test
     bool skip_empty = true;
     int min_live = kMinActive;  // slots that must be stepping for a warp to stay in the stepping loop
-    int max_slots = kSlots;
+    int max_slots = 4;
     unsigned long long batch_target = 0;  // camera samples per batch; 0 = n / 6 clamped to [2^20, 2^24] (measured best at c3)
     int num_sms = 0;
     int march_blocks[6] = {0, 0, 0, 0, 0, 0};  // resident blocks per SM of k_march<DIFF, CACHE> at [3*DIFF + CACHE]
