@@ -34,7 +34,7 @@ NCU_DRAM_BYTES_PER_STEP = {'c3_blobs256_tex_512x512_64spp': 5.6e9}
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='sdfrt', choices=['sdfrt', 'reference'])
     ap.add_argument('--workload', default='c3_blobs256_tex_512x512_64spp', choices=list(WORKLOADS))
@@ -62,7 +62,7 @@ class ClockSampler:
                     self.samples.append([s.strip() for s in out.split(',')])
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.01)
 
     def __enter__(self):
         self.t.start()
