@@ -280,3 +280,15 @@ def test_gradient_matches_finite_differences_of_the_loss(sdfrt_mod):
     fd = (loss_at(delta, 1024) - loss_at(-delta, 1024)) / (2 * delta)
     assert fd < 0 and dL_dc < 0                       # shrinking the sphere towards the target lowers the loss
     assert abs(dL_dc - fd) < 0.15 * abs(fd), (dL_dc, fd)
+
+
+def test_upsample_sdf_matches_oracle(sdfrt_mod):
+    """variables.upsample_sdf (python/variables.py:18-23): cubic lookup at the cell centres of the x2 grid."""
+    from oracle import sdf_oracle as O
+    scene, osc = build_scene(sdfrt_mod, 'blobs', 16, 8, 'sdf_direct_reparam')
+    up = sdfrt_mod.variables.upsample_sdf(scene.integrator().sdf)
+    assert up.shape == (32, 32, 32, 1)
+    c = (torch.arange(32, dtype=torch.float64) + 0.5) / 32
+    Z, Y, X = torch.meshgrid(c, c, c, indexing='ij')
+    ref = osc.sdf.eval(torch.stack([X.reshape(-1), Y.reshape(-1), Z.reshape(-1)], -1)).reshape(32, 32, 32)
+    assert (up[..., 0].cpu().double() - ref).abs().max() < 2e-6
