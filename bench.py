@@ -196,22 +196,19 @@ def run_gpu(args):
     ev = {k: [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)] for k in ('p0', 'p1', 'a0', 'a1', 'b1')}
 
     def step(i, seed, timed):
+        # primal render (spp * mult) and adjoint sweep 1 (spp_grad) are independent: one pipelined call (sdfrt_render_view)
         if timed:
             ev['p0'][i].record(stream)
-        ctx.render_primal(seed, spp * mult, film_p)
+        ctx.render_view(seed, spp * mult, seed + 1 + nsens, spp, film_p, film_a)
         if world > 1:
             dist.all_reduce(film_p)
+            dist.all_reduce(film_a)
         ctx.develop(film_p, image)
         if timed:
             ev['p1'][i].record(stream)
         grad_sdf.zero_()
         if grad_alb is not None:
             grad_alb.zero_()
-        if timed:
-            ev['a0'][i].record(stream)
-        ctx.adjoint_accumulate(seed + 1 + nsens, spp, film_a)
-        if world > 1:
-            dist.all_reduce(film_a)
         if timed:
             ev['a1'][i].record(stream)
         ctx.adjoint_backprop(film_a, grad_image, grad_sdf, grad_alb)
@@ -250,8 +247,7 @@ def run_gpu(args):
 
     # per-kernel timings (this rank; CUDA events recorded by the library on the launching stream, inside the timed
     # region) and the roofline of the dominant kernel
-    t_primal = sum(ev['p0'][i].elapsed_time(ev['p1'][i]) for i in range(args.steps)) / args.steps
-    t_accum = sum(ev['a0'][i].elapsed_time(ev['a1'][i]) for i in range(args.steps)) / args.steps
+    t_forward = sum(ev['p0'][i].elapsed_time(ev['p1'][i]) for i in range(args.steps)) / args.steps
     t_back = sum(ev['a1'][i].elapsed_time(ev['b1'][i]) for i in range(args.steps)) / args.steps
     # second timed loop, batches serialised on the launching stream so that the per-launch CUDA-event durations are additive
     ctx.set_overlap(False)
@@ -286,8 +282,7 @@ def run_gpu(args):
     achieved = march_bytes / (march_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": NCU_DRAM_BYTES_PER_STEP.get(args.workload), "peak_source": peak_src, "kernel": "k_march (all launches of one step; batches serialised for this measurement)",
-                "dominant_kernel": dom, "kernel_ms_per_step": kernel_ms, "pass_ms": {"primal": t_primal, "adjoint_accumulate": t_accum,
-                                                                                  "adjoint_backprop": t_back},
+                "dominant_kernel": dom, "kernel_ms_per_step": kernel_ms, "pass_ms": {"primal+adjoint_sweep1": t_forward, "adjoint_backprop": t_back},
                 "algorithmic_bytes_per_step": march_bytes, "evals_per_step": march_evals,
                 "note": "fetch-level bytes: 256 B per B-spline evaluation; the SDF grid is L2-resident at <= 256^3, so the fetches are "
                         "served by L1/L2 and frac can exceed 1; `traffic` is the ncu dram__bytes of the same launches (profiles/)"}
@@ -348,7 +343,7 @@ def run_gpu(args):
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": args.workload, "sdf_res": R, "albedo_res": AR, "film": [W, H], "spp_primal": spp * mult,
-                           "spp_adjoint": spp, "rays_per_step": rays_per_step, "partition": f"film rows x{world}",
+                           "spp_adjoint": spp, "rays_per_step": rays_per_step, "partition": f"interleaved 8-row film bands x{world}",
                            "l2": "inputs (sdf+albedo+grads+lane records > 1 GB) exceed L2; no explicit flush"},
                 "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(round(launches_per_step * args.steps)),
                 "roofline": roofline, "cpu_baseline": cpu_baseline, "stats_per_step": {k: v / args.steps for k, v in stats.items()}}

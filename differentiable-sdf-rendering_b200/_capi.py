@@ -71,6 +71,7 @@ SIGNATURES = {
     'sdfrt_render_primal': (C.c_int, [_P, C.c_uint32, C.c_int, _P, _P]),
     'sdfrt_develop': (C.c_int, [_P, _P, _P, _P]),
     'sdfrt_adjoint_accumulate': (C.c_int, [_P, C.c_uint32, C.c_int, _P, _P]),
+    'sdfrt_render_view': (C.c_int, [_P, C.c_uint32, C.c_int, _P, C.c_uint32, C.c_int, _P, _P]),
     'sdfrt_adjoint_backprop': (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
     'sdfrt_get_stats': (C.c_int, [_P, C.POINTER(Stats), C.c_int, _P]),
     'sdfrt_set_profiling': (C.c_int, [_P, C.c_int]),

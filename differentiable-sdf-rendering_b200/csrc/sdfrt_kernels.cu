@@ -243,8 +243,8 @@ struct sdfrt_ctx {
     int march_blocks[6] = {0, 0, 0, 0, 0, 0};  // resident blocks per SM of k_march<DIFF, CACHE> at [3*DIFF + CACHE]
     int cache_mode[4] = {1, 1, 0, 1};        // tap-cache mode of [value primary, value shadow, diff primary, diff shadow]
     // buffers of the host entry point
-    float *h_sdf = nullptr, *h_film = nullptr, *h_image = nullptr, *h_gimg = nullptr, *h_grad = nullptr;
-    size_t h_sdf_n = 0, h_film_n = 0, h_image_n = 0, h_grad_n = 0;
+    float *h_sdf = nullptr, *h_film = nullptr, *h_film2 = nullptr, *h_image = nullptr, *h_gimg = nullptr, *h_grad = nullptr;
+    size_t h_sdf_n = 0, h_film_n = 0, h_film2_n = 0, h_image_n = 0, h_grad_n = 0;
 };
 
 namespace {
@@ -325,122 +325,170 @@ void launch_march_mode(sdfrt_ctx* ctx, int mode, unsigned need, cudaStream_t st,
     else launch_march<DIFF, 2>(ctx, grid, st, segs, region_fill, n_slots, region, do_refine, out_its, rec_out, rec_stride, region_counter);
 }  // camera samples per batch of the wavefront pipeline
 
+// One forward sweep over this rank's camera samples: the primal render (value tracers) or adjoint sweep 1 (differentiable
+// tracers + lane records).  Several sweeps can be enqueued together (run_sweeps): their batches then share the pipeline
+// slots, so the latency tail of one sweep's persistent kernels is filled with the other's work.
+struct Sweep {
+    bool diff;
+    PassParams ps;
+    float* film;
+    const unsigned char* mask;  // per-pixel result of the empty-space test (or nullptr)
+    unsigned long long B;       // camera samples per batch
+};
+
 template <bool DIFF>
-int launch_forward(sdfrt_ctx* ctx, const PassParams& ps, float* film, cudaStream_t st) {
+int enqueue_batch(sdfrt_ctx* ctx, const Sweep& sw, unsigned long long item0, int sl, cudaStream_t bs) {
+    const PassParams& ps = sw.ps;
+    const unsigned long long n = ps.n_items, B = sw.B;
+    float* film = sw.film;
+    sdfrt_ctx::Scratch& sc = ctx->scratch[sl];
+    unsigned* work = ctx->work + sl * WQ_COUNT;
+    ShadowQueue q;
+    q.segs = reinterpret_cast<SegIn*>(sc.ssegs);
+    q.info = reinterpret_cast<float4*>(sc.sinfo);
+    q.count = reinterpret_cast<unsigned*>(sc.scount);
+    const unsigned cnt = (unsigned)((n - item0 < B) ? (n - item0) : B);
+    const unsigned blocks256 = (cnt + 255u) / 256u;
+    // region size: large enough to keep a block's rays on one film column, small enough to balance the persistent grid
+    unsigned region = kMaxRegion;
+    while (region > 256u && (unsigned long long)cnt / region < 8ull * (unsigned long long)ctx->num_sms * 4ull) region >>= 1;
+    const unsigned regions = (cnt + region - 1) / region;
+    SDFRT_CUDA(ctx, cudaMemsetAsync(work, 0, WQ_COUNT * sizeof(unsigned), bs));
+    { LaunchScope ls(ctx, 0, bs); k_gen_primary<<<blocks256, 256, 0, bs>>>(ctx->sc, ps, item0, cnt, reinterpret_cast<SegIn*>(sc.segs), sw.mask, ctx->counters); }
+    // primary march (+ refine); DIFF writes its_t into row 0 of the lane records
+    float* rec_b = DIFF ? ctx->rec + item0 : nullptr;
+    const unsigned need = (cnt + kMarchBlock - 1) / kMarchBlock;
+    { LaunchScope ls(ctx, 1, bs);
+      if (DIFF && reparam_at_depth(ctx->sc.W, 0))
+          launch_march_mode<true>(ctx, ctx->cache_mode[2], need, bs, reinterpret_cast<const SegIn*>(sc.segs), nullptr, cnt, region, 1,
+                                  nullptr, rec_b, ctx->rec_stride, work + WQ_PRIMARY_CHUNK);
+      else  // value tracer; a DIFF pass without a primary warp (DummyWarpField / None) only needs its_t (record row 0)
+          launch_march_mode<false>(ctx, ctx->cache_mode[0], need, bs, reinterpret_cast<const SegIn*>(sc.segs), nullptr, cnt, region, 1,
+                                   DIFF ? rec_b : sc.its, nullptr, 0, work + WQ_PRIMARY_CHUNK); }
+    const float* its = DIFF ? rec_b : sc.its;
+    { LaunchScope ls(ctx, 2, bs);
+      k_shade<DIFF><<<regions, 256, 0, bs>>>(ctx->sc, ps, item0, cnt, region, reinterpret_cast<const SegIn*>(sc.segs), its, q, film,
+                                             DIFF ? rec_b + REC_S_STATE * ctx->rec_stride : nullptr, ctx->counters); }
+    if (ctx->sc.integrator == INTEGRATOR_DIRECT) {
+        // shadow march over the region-compacted queue.  The differentiable tracer is only needed if shadow rays are
+        // reparameterised (python/warp.py:103: max_reparam_depth); otherwise the value tracer's its_t is all the pass uses.
+        const bool shadow_diff = DIFF && reparam_at_depth(ctx->sc.W, 1);
+        { LaunchScope ls(ctx, 3, bs);
+          if (shadow_diff)
+              launch_march_mode<true>(ctx, ctx->cache_mode[3], need, bs, reinterpret_cast<const SegIn*>(sc.ssegs), q.count,
+                                      regions * region, region, 0, nullptr, sc.srec, B, work + WQ_SHADOW_CHUNK);
+          else
+              launch_march_mode<false>(ctx, ctx->cache_mode[1], need, bs, reinterpret_cast<const SegIn*>(sc.ssegs), q.count,
+                                       regions * region, region, 0, sc.s_its, nullptr, 0, work + WQ_SHADOW_CHUNK); }
+        const float* shadow_its = shadow_diff ? sc.srec : sc.s_its;
+        { LaunchScope ls(ctx, 4, bs);
+          k_shadow_splat<DIFF><<<regions, 256, 0, bs>>>(ctx->sc, ps, item0, region, reinterpret_cast<const SegIn*>(sc.segs), q.count,
+                                                        reinterpret_cast<const float4*>(sc.sinfo), shadow_its, sc.srec, B, film, rec_b,
+                                                        ctx->rec_stride); }
+    }
+    SDFRT_CUDA(ctx, cudaGetLastError());
+    return SDFRT_OK;
+}
+
+int run_sweeps(sdfrt_ctx* ctx, Sweep* sweeps, int ns, cudaStream_t st) {
     SDFRT_CUDA(ctx, cudaSetDevice(ctx->device));
-    SDFRT_CUDA(ctx, cudaMemsetAsync(film, 0, film_floats(ctx) * sizeof(float), st));
-    const unsigned long long n = ps.n_items;
-    if (n == 0) return SDFRT_OK;
     const SensorParams& S = ctx->sc.S;
-    if ((unsigned long long)kBandRows * (unsigned long long)(S.W + 2 * S.border) * (unsigned long long)ps.spp > 0xffffffffull)
-        return fail(ctx, SDFRT_ERR_INVALID, "film row band exceeds 2^32 samples");
-    unsigned long long target = ctx->batch_target;
-    if (target == 0) target = std::max<unsigned long long>(1ull << 20, std::min<unsigned long long>(1ull << 24, n / 6));
-    const unsigned long long nbatch = (n + target - 1) / target;
-    unsigned long long B = (n + nbatch - 1) / nbatch;
-    B = (B + kMaxRegion - 1) / kMaxRegion * kMaxRegion;  // whole regions per batch
-    const int nslots = (nbatch > 1 && ctx->overlap) ? (int)std::min<unsigned long long>(nbatch, (unsigned long long)ctx->max_slots) : 1;
     int rc;
+    unsigned long long Bmax = 0, total_batches = 0;
+    bool any_diff = false, any_value = false;
+    for (int k = 0; k < ns; ++k) {
+        Sweep& sw = sweeps[k];
+        SDFRT_CUDA(ctx, cudaMemsetAsync(sw.film, 0, film_floats(ctx) * sizeof(float), st));
+        sw.mask = nullptr;
+        sw.B = 0;
+        const unsigned long long n = sw.ps.n_items;
+        if (n == 0) continue;
+        if ((unsigned long long)kBandRows * (unsigned long long)(S.W + 2 * S.border) * (unsigned long long)sw.ps.spp > 0xffffffffull)
+            return fail(ctx, SDFRT_ERR_INVALID, "film row band exceeds 2^32 samples");
+        unsigned long long target = ctx->batch_target;
+        if (target == 0) target = std::max<unsigned long long>(1ull << 20, std::min<unsigned long long>(1ull << 24, n / 6));
+        const unsigned long long nbatch = (n + target - 1) / target;
+        unsigned long long B = (n + nbatch - 1) / nbatch;
+        sw.B = (B + kMaxRegion - 1) / kMaxRegion * kMaxRegion;  // whole regions per batch
+        Bmax = std::max(Bmax, sw.B);
+        total_batches += (n + sw.B - 1) / sw.B;
+        (sw.diff ? any_diff : any_value) = true;
+    }
+    if (total_batches == 0) return SDFRT_OK;
+    const int nslots = (total_batches > 1 && ctx->overlap) ? (int)std::min<unsigned long long>(total_batches, (unsigned long long)ctx->max_slots) : 1;
     for (int sl = 0; sl < nslots; ++sl) {
         sdfrt_ctx::Scratch& sc = ctx->scratch[sl];
-        if ((rc = ensure(ctx, &sc.segs, &sc.segs_n, (size_t)B * 8))) return rc;
-        if ((rc = ensure(ctx, &sc.ssegs, &sc.ssegs_n, (size_t)B * 8))) return rc;
-        if ((rc = ensure(ctx, &sc.sinfo, &sc.sinfo_n, (size_t)B * 4))) return rc;
-        if ((rc = ensure(ctx, &sc.scount, &sc.scount_n, (size_t)(B / 256) + 1))) return rc;
-        if ((rc = ensure(ctx, &sc.s_its, &sc.s_its_n, (size_t)B))) return rc;
-        if (DIFF) {
-            if ((rc = ensure(ctx, &sc.srec, &sc.srec_n, (size_t)B * 9))) return rc;
-        } else {
-            if ((rc = ensure(ctx, &sc.its, &sc.its_n, (size_t)B))) return rc;
-        }
+        if ((rc = ensure(ctx, &sc.segs, &sc.segs_n, (size_t)Bmax * 8))) return rc;
+        if ((rc = ensure(ctx, &sc.ssegs, &sc.ssegs_n, (size_t)Bmax * 8))) return rc;
+        if ((rc = ensure(ctx, &sc.sinfo, &sc.sinfo_n, (size_t)Bmax * 4))) return rc;
+        if ((rc = ensure(ctx, &sc.scount, &sc.scount_n, (size_t)(Bmax / 256) + 1))) return rc;
+        if ((rc = ensure(ctx, &sc.s_its, &sc.s_its_n, (size_t)Bmax))) return rc;
+        if (any_diff && (rc = ensure(ctx, &sc.srec, &sc.srec_n, (size_t)Bmax * 9))) return rc;
+        if (any_value && (rc = ensure(ctx, &sc.its, &sc.its_n, (size_t)Bmax))) return rc;
     }
-    // empty-space test (rebuilt every sweep: the caller may have updated the grid in place): brick minima -> dilation ->
-    // one DDA per film pixel -> mask consumed by k_gen_primary
-    const unsigned char* mask = nullptr;
+    // empty-space test (rebuilt every call: the caller may have updated the grid in place): brick minima -> dilation -> one
+    // DDA per film pixel and sweep -> masks consumed by k_gen_primary
     if (ctx->skip_empty) {
         const GridView& G = ctx->sc.G;
-        // value pass: only the hit threshold matters.  DIFF pass: also the largest warp epsilon a lane can see
-        // (strategy 6: edge_eps * warp_t <= edge_eps * maxt, python/warp.py:41-45), so that its warp weight is exactly 0.
-        float skip_eps = 0.f;
-        if (DIFF && ctx->sc.W.kind == WARP_2D) skip_eps = ctx->sc.W.weight_strategy == 6 ? ctx->sc.W.edge_eps : -1.f;
-        if (ctx->sc.T.step_scale != 1.f) skip_eps = -1.f;  // scaled SDF values: the bound does not apply as is
-        const EmptySpaceParams e = empty_space_params(S, G, skip_eps);
-        if (e.skip_eps >= 0.f) {
-            BrickView bricks;
-            bricks.nx = (G.rx + kBrick - 1) / kBrick; bricks.ny = (G.ry + kBrick - 1) / kBrick; bricks.nz = (G.rz + kBrick - 1) / kBrick;
-            const size_t nb = (size_t)bricks.nx * bricks.ny * bricks.nz;
-            const int npix = (S.W + 2 * S.border) * (S.H + 2 * S.border);
-            if ((rc = ensure(ctx, &ctx->brick_raw, &ctx->brick_raw_n, nb))) return rc;
-            if ((rc = ensure(ctx, &ctx->brick, &ctx->brick_n, nb))) return rc;
-            if ((rc = ensure(ctx, &ctx->pix_mask, &ctx->pix_mask_n, (size_t)npix / 4 + 1))) return rc;
-            const unsigned gb = (unsigned)((nb + 255) / 256);
-            LaunchScope ls(ctx, 0, st);
-            k_brick_min<<<gb, 256, 0, st>>>(G, ctx->brick_raw, bricks.nx, bricks.ny, bricks.nz);
-            k_brick_dilate<<<gb, 256, 0, st>>>(ctx->brick_raw, ctx->brick, bricks.nx, bricks.ny, bricks.nz, e.dilation, 0);
-            k_brick_dilate<<<gb, 256, 0, st>>>(ctx->brick, ctx->brick_raw, bricks.nx, bricks.ny, bricks.nz, e.dilation, 1);
-            k_brick_dilate<<<gb, 256, 0, st>>>(ctx->brick_raw, ctx->brick, bricks.nx, bricks.ny, bricks.nz, e.dilation, 2);
-            bricks.data = ctx->brick;
-            k_pixel_clear<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(ctx->sc, bricks, e, reinterpret_cast<unsigned char*>(ctx->pix_mask));
-            ctx->n_launches += 4;
-            mask = reinterpret_cast<const unsigned char*>(ctx->pix_mask);
+        const int npix = (S.W + 2 * S.border) * (S.H + 2 * S.border);
+        const size_t mask_words = (size_t)npix / 4 + 1;
+        bool bricks_ready = false;
+        BrickView bricks;
+        bricks.data = nullptr;
+        bricks.nx = (G.rx + kBrick - 1) / kBrick; bricks.ny = (G.ry + kBrick - 1) / kBrick; bricks.nz = (G.rz + kBrick - 1) / kBrick;
+        for (int k = 0; k < ns; ++k) {
+            Sweep& sw = sweeps[k];
+            if (sw.ps.n_items == 0) continue;
+            // value pass: only the hit threshold matters.  DIFF pass: also the largest warp epsilon a lane can see
+            // (strategy 6: edge_eps * warp_t <= edge_eps * maxt, python/warp.py:41-45), so that its warp weight is exactly 0.
+            float skip_eps = 0.f;
+            if (sw.diff && ctx->sc.W.kind == WARP_2D) skip_eps = ctx->sc.W.weight_strategy == 6 ? ctx->sc.W.edge_eps : -1.f;
+            if (ctx->sc.T.step_scale != 1.f) skip_eps = -1.f;  // scaled SDF values: the bound does not apply as is
+            const EmptySpaceParams e = empty_space_params(S, G, skip_eps);
+            if (e.skip_eps < 0.f) continue;
+            if (!bricks_ready) {
+                const size_t nb = (size_t)bricks.nx * bricks.ny * bricks.nz;
+                if ((rc = ensure(ctx, &ctx->brick_raw, &ctx->brick_raw_n, nb))) return rc;
+                if ((rc = ensure(ctx, &ctx->brick, &ctx->brick_n, nb))) return rc;
+                if ((rc = ensure(ctx, &ctx->pix_mask, &ctx->pix_mask_n, 2 * mask_words))) return rc;
+                const unsigned gb = (unsigned)((nb + 255) / 256);
+                LaunchScope ls(ctx, 0, st);
+                k_brick_min<<<gb, 256, 0, st>>>(G, ctx->brick_raw, bricks.nx, bricks.ny, bricks.nz);
+                k_brick_dilate<<<gb, 256, 0, st>>>(ctx->brick_raw, ctx->brick, bricks.nx, bricks.ny, bricks.nz, e.dilation, 0);
+                k_brick_dilate<<<gb, 256, 0, st>>>(ctx->brick, ctx->brick_raw, bricks.nx, bricks.ny, bricks.nz, e.dilation, 1);
+                k_brick_dilate<<<gb, 256, 0, st>>>(ctx->brick_raw, ctx->brick, bricks.nx, bricks.ny, bricks.nz, e.dilation, 2);
+                ctx->n_launches += 3;
+                bricks.data = ctx->brick;
+                bricks_ready = true;
+            }
+            unsigned char* m = reinterpret_cast<unsigned char*>(ctx->pix_mask + (sw.diff ? mask_words : 0));
+            { LaunchScope ls(ctx, 0, st); k_pixel_clear<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(ctx->sc, bricks, e, m); }
+            sw.mask = m;
         }
     }
-    // fork: the internal streams wait for everything queued on the caller's stream (film memset included)
+    // fork: the internal streams wait for everything queued on the caller's stream (film memsets, masks)
     if (nslots > 1) {
         SDFRT_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
         for (int sl = 0; sl < nslots; ++sl) SDFRT_CUDA(ctx, cudaStreamWaitEvent(ctx->aux[sl], ctx->ev_fork, 0));
     }
+    // batches of the sweeps, interleaved round-robin over the slots
+    unsigned long long next[4] = {0, 0, 0, 0};
     unsigned long long bi = 0;
-    for (unsigned long long item0 = 0; item0 < n; item0 += B, ++bi) {
-        const int sl = (int)(bi % (unsigned long long)nslots);
-        cudaStream_t bs = nslots > 1 ? ctx->aux[sl] : st;
-        sdfrt_ctx::Scratch& sc = ctx->scratch[sl];
-        unsigned* work = ctx->work + sl * WQ_COUNT;
-        ShadowQueue q;
-        q.segs = reinterpret_cast<SegIn*>(sc.ssegs);
-        q.info = reinterpret_cast<float4*>(sc.sinfo);
-        q.count = reinterpret_cast<unsigned*>(sc.scount);
-        const unsigned cnt = (unsigned)((n - item0 < B) ? (n - item0) : B);
-        const unsigned blocks256 = (cnt + 255u) / 256u;
-        // region size: large enough to keep a block's rays on one film column, small enough to balance the persistent grid
-        unsigned region = kMaxRegion;
-        while (region > 256u && (unsigned long long)cnt / region < 8ull * (unsigned long long)ctx->num_sms * 4ull) region >>= 1;
-        const unsigned regions = (cnt + region - 1) / region;
-        SDFRT_CUDA(ctx, cudaMemsetAsync(work, 0, WQ_COUNT * sizeof(unsigned), bs));
-        { LaunchScope ls(ctx, 0, bs); k_gen_primary<<<blocks256, 256, 0, bs>>>(ctx->sc, ps, item0, cnt, reinterpret_cast<SegIn*>(sc.segs), mask, ctx->counters); }
-        // primary march (+ refine); DIFF writes its_t into row 0 of the lane records
-        float* rec_b = DIFF ? ctx->rec + item0 : nullptr;
-        const unsigned need = (cnt + kMarchBlock - 1) / kMarchBlock;
-        { LaunchScope ls(ctx, 1, bs);
-          if (DIFF && reparam_at_depth(ctx->sc.W, 0))
-              launch_march_mode<true>(ctx, ctx->cache_mode[2], need, bs, reinterpret_cast<const SegIn*>(sc.segs), nullptr, cnt, region, 1,
-                                      nullptr, rec_b, ctx->rec_stride, work + WQ_PRIMARY_CHUNK);
-          else  // value tracer; a DIFF pass without a primary warp (DummyWarpField / None) only needs its_t (record row 0)
-              launch_march_mode<false>(ctx, ctx->cache_mode[0], need, bs, reinterpret_cast<const SegIn*>(sc.segs), nullptr, cnt, region, 1,
-                                       DIFF ? rec_b : sc.its, nullptr, 0, work + WQ_PRIMARY_CHUNK); }
-        const float* its = DIFF ? rec_b : sc.its;
-        { LaunchScope ls(ctx, 2, bs);
-          k_shade<DIFF><<<regions, 256, 0, bs>>>(ctx->sc, ps, item0, cnt, region, reinterpret_cast<const SegIn*>(sc.segs), its, q, film,
-                                                 DIFF ? rec_b + REC_S_STATE * ctx->rec_stride : nullptr, ctx->counters); }
-        if (ctx->sc.integrator == INTEGRATOR_DIRECT) {
-            // shadow march over the region-compacted queue.  The differentiable tracer is only needed if shadow rays are
-            // reparameterised (python/warp.py:103: max_reparam_depth); otherwise the value tracer's its_t is all the pass uses.
-            const bool shadow_diff = DIFF && reparam_at_depth(ctx->sc.W, 1);
-            { LaunchScope ls(ctx, 3, bs);
-              if (shadow_diff)
-                  launch_march_mode<true>(ctx, ctx->cache_mode[3], need, bs, reinterpret_cast<const SegIn*>(sc.ssegs), q.count,
-                                          regions * region, region, 0, nullptr, sc.srec, B, work + WQ_SHADOW_CHUNK);
-              else
-                  launch_march_mode<false>(ctx, ctx->cache_mode[1], need, bs, reinterpret_cast<const SegIn*>(sc.ssegs), q.count,
-                                           regions * region, region, 0, sc.s_its, nullptr, 0, work + WQ_SHADOW_CHUNK); }
-            const float* shadow_its = shadow_diff ? sc.srec : sc.s_its;
-            { LaunchScope ls(ctx, 4, bs);
-              k_shadow_splat<DIFF><<<regions, 256, 0, bs>>>(ctx->sc, ps, item0, region, reinterpret_cast<const SegIn*>(sc.segs), q.count, reinterpret_cast<const float4*>(sc.sinfo),
-                                                            shadow_its, sc.srec, B, film, rec_b, ctx->rec_stride); }
+    for (bool more = true; more;) {
+        more = false;
+        for (int k = 0; k < ns; ++k) {
+            Sweep& sw = sweeps[k];
+            if (sw.B == 0 || next[k] >= sw.ps.n_items) continue;
+            const int sl = (int)(bi % (unsigned long long)nslots);
+            cudaStream_t bs = nslots > 1 ? ctx->aux[sl] : st;
+            rc = sw.diff ? enqueue_batch<true>(ctx, sw, next[k], sl, bs) : enqueue_batch<false>(ctx, sw, next[k], sl, bs);
+            if (rc) return rc;
+            next[k] += sw.B;
+            ++bi;
+            more = true;
         }
-        SDFRT_CUDA(ctx, cudaGetLastError());
     }
-    // join: the caller's stream continues after both internal streams are done
+    // join: the caller's stream continues after all internal streams are done
     if (nslots > 1) {
         for (int sl = 0; sl < nslots; ++sl) {
             SDFRT_CUDA(ctx, cudaEventRecord(ctx->ev_join[sl], ctx->aux[sl]));
@@ -547,7 +595,7 @@ void sdfrt_destroy(sdfrt_ctx* ctx) {
         if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
     }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
-    cudaFree(ctx->h_sdf); cudaFree(ctx->h_film); cudaFree(ctx->h_image); cudaFree(ctx->h_gimg); cudaFree(ctx->h_grad);
+    cudaFree(ctx->h_sdf); cudaFree(ctx->h_film); cudaFree(ctx->h_film2); cudaFree(ctx->h_image); cudaFree(ctx->h_gimg); cudaFree(ctx->h_grad);
     delete ctx;
 }
 
@@ -647,8 +695,11 @@ int sdfrt_render_primal(sdfrt_ctx* ctx, uint32_t seed, int spp, float* film_accu
     int rc = check_ready(ctx, spp);
     if (rc) return rc;
     if (!film_accum) return fail(ctx, SDFRT_ERR_INVALID, "film_accum is null");
-    const PassParams ps = make_pass(ctx->sc.S, seed, spp, ctx->rank, ctx->world);
-    return launch_forward<false>(ctx, ps, film_accum, (cudaStream_t)stream);
+    Sweep sw;
+    sw.diff = false;
+    sw.ps = make_pass(ctx->sc.S, seed, spp, ctx->rank, ctx->world);
+    sw.film = film_accum;
+    return run_sweeps(ctx, &sw, 1, (cudaStream_t)stream);
 }
 
 int sdfrt_develop(sdfrt_ctx* ctx, const float* film_accum, float* image, void* stream) {
@@ -666,14 +717,40 @@ int sdfrt_adjoint_accumulate(sdfrt_ctx* ctx, uint32_t seed_grad, int spp_grad, f
     if (rc) return rc;
     if (!film_accum) return fail(ctx, SDFRT_ERR_INVALID, "film_accum is null");
     SDFRT_CUDA(ctx, cudaSetDevice(ctx->device));
-    const PassParams ps = make_pass(ctx->sc.S, seed_grad, spp_grad, ctx->rank, ctx->world);
-    const unsigned long long n = ps.n_items;
-    rc = ensure(ctx, &ctx->rec, &ctx->rec_capacity, (size_t)n * REC_COUNT + 1);
+    Sweep sw;
+    sw.diff = true;
+    sw.ps = make_pass(ctx->sc.S, seed_grad, spp_grad, ctx->rank, ctx->world);
+    sw.film = film_accum;
+    rc = ensure(ctx, &ctx->rec, &ctx->rec_capacity, (size_t)sw.ps.n_items * REC_COUNT + 1);
     if (rc) return rc;
-    ctx->rec_stride = n;
-    rc = launch_forward<true>(ctx, ps, film_accum, (cudaStream_t)stream);
+    ctx->rec_stride = sw.ps.n_items;
+    rc = run_sweeps(ctx, &sw, 1, (cudaStream_t)stream);
     if (rc) return rc;
-    ctx->adj_pass = ps;
+    ctx->adj_pass = sw.ps;
+    ctx->adj_ready = true;
+    return SDFRT_OK;
+}
+
+int sdfrt_render_view(sdfrt_ctx* ctx, uint32_t seed, int spp, float* film_primal, uint32_t seed_grad, int spp_grad,
+                      float* film_adjoint, void* stream) {
+    int rc = check_ready(ctx, spp);
+    if (rc) return rc;
+    if ((rc = check_ready(ctx, spp_grad))) return rc;
+    if (!film_primal || !film_adjoint) return fail(ctx, SDFRT_ERR_INVALID, "film buffer is null");
+    SDFRT_CUDA(ctx, cudaSetDevice(ctx->device));
+    Sweep sw[2];
+    sw[0].diff = false;
+    sw[0].ps = make_pass(ctx->sc.S, seed, spp, ctx->rank, ctx->world);
+    sw[0].film = film_primal;
+    sw[1].diff = true;
+    sw[1].ps = make_pass(ctx->sc.S, seed_grad, spp_grad, ctx->rank, ctx->world);
+    sw[1].film = film_adjoint;
+    rc = ensure(ctx, &ctx->rec, &ctx->rec_capacity, (size_t)sw[1].ps.n_items * REC_COUNT + 1);
+    if (rc) return rc;
+    ctx->rec_stride = sw[1].ps.n_items;
+    rc = run_sweeps(ctx, sw, 2, (cudaStream_t)stream);
+    if (rc) return rc;
+    ctx->adj_pass = sw[1].ps;
     ctx->adj_ready = true;
     return SDFRT_OK;
 }
@@ -787,6 +864,7 @@ int sdfrt_render_view_host(sdfrt_ctx* ctx, const float* sdf_host, int rx, int ry
     if ((rc = ensure(ctx, &ctx->h_sdf, &ctx->h_sdf_n, nvox))) return rc;
     if ((rc = ensure(ctx, &ctx->h_grad, &ctx->h_grad_n, nvox))) return rc;
     if ((rc = ensure(ctx, &ctx->h_film, &ctx->h_film_n, film_floats(ctx)))) return rc;
+    if ((rc = ensure(ctx, &ctx->h_film2, &ctx->h_film2_n, film_floats(ctx)))) return rc;
     if (ctx->h_image_n < nimg) {
         size_t cap = ctx->h_image_n;
         if ((rc = ensure(ctx, &ctx->h_image, &cap, nimg))) return rc;
@@ -798,7 +876,8 @@ int sdfrt_render_view_host(sdfrt_ctx* ctx, const float* sdf_host, int rx, int ry
     SDFRT_CUDA(ctx, cudaMemcpyAsync(ctx->h_sdf, sdf_host, nvox * sizeof(float), cudaMemcpyHostToDevice, st));
     const float p0[3] = {ctx->sc.G.px, ctx->sc.G.py, ctx->sc.G.pz};
     if ((rc = sdfrt_set_sdf(ctx, ctx->h_sdf, rx, ry, rz, ctx->have_sdf ? p0 : nullptr))) return rc;
-    if ((rc = sdfrt_render_primal(ctx, seed, spp, ctx->h_film, st))) return rc;
+    // primal render and adjoint sweep 1 do not depend on each other: one pipelined call
+    if ((rc = sdfrt_render_view(ctx, seed, spp, ctx->h_film, seed_grad, spp_grad, ctx->h_film2, st))) return rc;
     if ((rc = sdfrt_develop(ctx, ctx->h_film, ctx->h_image, st))) return rc;
     SDFRT_CUDA(ctx, cudaMemcpyAsync(image_host, ctx->h_image, nimg * sizeof(float), cudaMemcpyDeviceToHost, st));
     if (grad_image_host) {
@@ -808,8 +887,7 @@ int sdfrt_render_view_host(sdfrt_ctx* ctx, const float* sdf_host, int rx, int ry
         SDFRT_CUDA(ctx, cudaGetLastError());
     }
     SDFRT_CUDA(ctx, cudaMemsetAsync(ctx->h_grad, 0, nvox * sizeof(float), st));
-    if ((rc = sdfrt_adjoint_accumulate(ctx, seed_grad, spp_grad, ctx->h_film, st))) return rc;
-    if ((rc = sdfrt_adjoint_backprop(ctx, ctx->h_film, ctx->h_gimg, ctx->h_grad, nullptr, nullptr, st))) return rc;
+    if ((rc = sdfrt_adjoint_backprop(ctx, ctx->h_film2, ctx->h_gimg, ctx->h_grad, nullptr, nullptr, st))) return rc;
     SDFRT_CUDA(ctx, cudaMemcpyAsync(grad_sdf_host, ctx->h_grad, nvox * sizeof(float), cudaMemcpyDeviceToHost, st));
     SDFRT_CUDA(ctx, cudaStreamSynchronize(st));
     return SDFRT_OK;

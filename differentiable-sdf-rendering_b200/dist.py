@@ -27,14 +27,23 @@ def render_view(backend, seed, spp, seed_grad, spp_grad, grad_image_fn, grad_sdf
     """
     rank, world = _world(group)
     backend.set_partition(rank, world)
-    film = backend.render_primal(seed, spp)
-    if world > 1:
-        dist.all_reduce(film, group=group)
-    image = backend.develop(film)
-    grad_image = grad_image_fn(image)
-    film_a = backend.adjoint_accumulate(seed_grad, spp_grad)
-    if world > 1:
-        dist.all_reduce(film_a, group=group)
+    if hasattr(backend, 'render_view'):
+        # the primal render and adjoint sweep 1 are independent: one pipelined call, then both (small) film all-reduces
+        film, film_a = backend.render_view(seed, spp, seed_grad, spp_grad)
+        if world > 1:
+            dist.all_reduce(film, group=group)
+            dist.all_reduce(film_a, group=group)
+        image = backend.develop(film)
+        grad_image = grad_image_fn(image)
+    else:
+        film = backend.render_primal(seed, spp)
+        if world > 1:
+            dist.all_reduce(film, group=group)
+        image = backend.develop(film)
+        grad_image = grad_image_fn(image)
+        film_a = backend.adjoint_accumulate(seed_grad, spp_grad)
+        if world > 1:
+            dist.all_reduce(film_a, group=group)
     local = torch.zeros_like(grad_sdf)
     local_alb = None if grad_albedo is None else torch.zeros_like(grad_albedo)
     backend.adjoint_backprop(film_a, grad_image.contiguous(), local, local_alb)

@@ -141,6 +141,14 @@ class Context:
                                                           _stream(self.device)))
         return film
 
+    def render_view(self, seed, spp, seed_grad, spp_grad, film_primal=None, film_adjoint=None):
+        """Primal render + adjoint sweep 1 in one pipelined call (they are independent); returns both film accumulators."""
+        film_primal = self.new_film() if film_primal is None else film_primal
+        film_adjoint = self.new_film() if film_adjoint is None else film_adjoint
+        check(self.ctx, self.lib.sdfrt_render_view(self.ctx, seed & 0xFFFFFFFF, spp, _ptr(film_primal), seed_grad & 0xFFFFFFFF, spp_grad,
+                                                   _ptr(film_adjoint), _stream(self.device)))
+        return film_primal, film_adjoint
+
     def adjoint_backprop(self, film, grad_image, grad_sdf, grad_albedo=None, grad_p=None):
         _f32c(grad_image, self.device)
         _f32c(grad_sdf, self.device)

@@ -73,6 +73,31 @@ class ReparamIntegrator:
         film = ctx.render_primal(seed, spp)
         return ctx.develop(film)
 
+    def render_with_adjoint_sweep(self, scene, sensor, seed, spp, seed_grad, spp_grad):
+        """Primal image plus the film of adjoint sweep 1, from ONE pipelined call (sdfrt_render_view): what `mi.render`
+        does when gradients are enabled, with the re-render of render_backward hoisted next to the primal render (it does
+        not depend on the loss).  `backprop_adjoint_sweep` then plays the role of render_backward."""
+        ctx = self._bind(scene, sensor)
+        self._check_wavefront(ctx, spp)
+        self._check_wavefront(ctx, spp_grad)
+        film, film_a = ctx.render_view(seed, spp, seed_grad, spp_grad)
+        self.last_film = film_a
+        return ctx.develop(film), film_a
+
+    def backprop_adjoint_sweep(self, scene, film_a, grad_in):
+        ctx = self.sdf.ctx
+        data = self.sdf.data
+        if data.grad is None:
+            data.grad = torch.zeros_like(data)
+        galb = None
+        if scene.albedo_grid is not None and scene.albedo_grid.requires_grad:
+            if scene.albedo_grid.grad is None:
+                scene.albedo_grid.grad = torch.zeros_like(scene.albedo_grid)
+            galb = scene.albedo_grid.grad
+        if not hasattr(self.sdf, 'p_grad') or self.sdf.p_grad is None:
+            self.sdf.p_grad = torch.zeros(3, dtype=torch.float32, device=ctx.device)
+        ctx.adjoint_backprop(film_a, grad_in.contiguous(), data.grad, galb, self.sdf.p_grad)
+
     def render_backward(self, scene, params, grad_in, sensor=0, seed=0, spp=0):
         """Accumulates dLoss/d(sdf.data) into `sdf.data.grad` (and the reflectance grid's .grad)."""
         ctx = self._bind(scene, sensor)

@@ -8,18 +8,22 @@ class _RenderOp(torch.autograd.Function):
     @staticmethod
     def forward(ctx, sdf_data, scene, sensor, seed, spp, seed_grad, spp_grad):
         integrator = scene.integrator()
-        ctx.args = (scene, sensor, seed_grad, spp_grad)
         with torch.no_grad():
-            return integrator.render(scene, sensor=sensor, seed=seed, spp=spp)
+            image, film_a = integrator.render_with_adjoint_sweep(scene, sensor, seed, spp, seed_grad, spp_grad)
+        ctx.args = (scene, film_a)
+        return image
 
     @staticmethod
     def backward(ctx, grad_out):
-        scene, sensor, seed_grad, spp_grad = ctx.args
+        scene, film_a = ctx.args
         integrator = scene.integrator()
         data = integrator.sdf.data
         saved = data.grad
         data.grad = torch.zeros_like(data)
-        integrator.render_backward(scene, None, grad_out.contiguous(), sensor=sensor, seed=seed_grad, spp=spp_grad)
+        # NOTE: the lane records of adjoint sweep 1 live in the context until the next sweep: backward() must follow the
+        # forward of the same view before another view is rendered (the reference's loop does exactly that,
+        # python/shape_opt.py:78-83)
+        integrator.backprop_adjoint_sweep(scene, film_a, grad_out.contiguous())
         g, data.grad = data.grad, saved
         return g, None, None, None, None, None, None
 

@@ -145,6 +145,12 @@ int sdfrt_develop(sdfrt_ctx* ctx, const float* film_accum, float* image, void* s
  *              dLoss/d(albedo) into grad_albedo (or NULL) and dLoss/d(sdf.p) into grad_p[3]
  *              (device pointer, or NULL). */
 int sdfrt_adjoint_accumulate(sdfrt_ctx* ctx, uint32_t seed_grad, int spp_grad, float* film_accum, void* stream);
+/* Primal render at (seed, spp) and adjoint sweep 1 at (seed_grad, spp_grad) in ONE pipelined call: the two sweeps do not
+ * depend on each other (the re-render of render_backward does not need the loss, python/integrators/reparam.py:187-189),
+ * so their batches share the pipeline and fill each other's latency tails.  Equivalent to sdfrt_render_primal followed by
+ * sdfrt_adjoint_accumulate; sdfrt_adjoint_backprop follows once dLoss/dImage is known. */
+int sdfrt_render_view(sdfrt_ctx* ctx, uint32_t seed, int spp, float* film_primal, uint32_t seed_grad, int spp_grad,
+                      float* film_adjoint, void* stream);
 int sdfrt_adjoint_backprop(sdfrt_ctx* ctx, const float* film_accum, const float* grad_image,
                            float* grad_sdf, float* grad_albedo, float* grad_p, void* stream);
 

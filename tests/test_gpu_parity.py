@@ -292,3 +292,19 @@ def test_upsample_sdf_matches_oracle(sdfrt_mod):
     Z, Y, X = torch.meshgrid(c, c, c, indexing='ij')
     ref = osc.sdf.eval(torch.stack([X.reshape(-1), Y.reshape(-1), Z.reshape(-1)], -1)).reshape(32, 32, 32)
     assert (up[..., 0].cpu().double() - ref).abs().max() < 2e-6
+
+
+def test_pipelined_view_equals_separate_sweeps(big):
+    """sdfrt_render_view (primal + adjoint sweep 1 in one pipelined call) == sdfrt_render_primal + sdfrt_adjoint_accumulate."""
+    ctx, sdf = big
+    fp = ctx.render_primal(21, 32).clone()
+    fa = ctx.adjoint_accumulate(22, 16).clone()
+    g_sep = torch.zeros_like(sdf)
+    gi = torch.ones(512, 512, 3, device='cuda')
+    ctx.adjoint_backprop(fa, gi, g_sep)
+    fp2, fa2 = ctx.render_view(21, 32, 22, 16)
+    g_cmb = torch.zeros_like(sdf)
+    ctx.adjoint_backprop(fa2, gi, g_cmb)
+    assert (fp2 - fp).abs().max() < 1e-3 * fp.abs().max()
+    assert (fa2 - fa).abs().max() < 1e-3 * fa.abs().max()
+    assert (g_cmb - g_sep).abs().max() < 1e-3 * g_sep.abs().max()
