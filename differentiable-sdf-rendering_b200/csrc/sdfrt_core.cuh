@@ -30,6 +30,10 @@
 #define SDFRT_FDIV(a, b) ((a) / (b))
 #endif
 
+#if !defined(__CUDACC__)
+struct alignas(16) float4 { float x, y, z, w; };  // host builds (test harness, CPU port)
+#endif
+
 namespace sdfrt {
 
 // ------------------------------------------------------------------------------------
@@ -82,6 +86,9 @@ struct GridView {
     const float* data;  // (rz, ry, rx), x fastest
     int rx, ry, rz;
     float px, py, pz;  // sdf.p: lookups use x - p (python/shapes.py:408-414)
+    // optional row-expanded copy for the marchers: rows4[(z * ry + y) * rx + x] = data[z][y][x .. x+3] (x <= rx - 4),
+    // so that one 16-byte load fetches a whole x-row of a 4x4x4 block.  nullptr = read `data`.
+    const float4* rows4;
 };
 struct AlbedoView {
     const float* data;  // (rz, ry, rx, 3) or nullptr
@@ -251,18 +258,29 @@ SDFRT_HD void cell_setup(const GridView& G, V3 x, CellSetup<ORDER>& s) {
         if (ORDER >= 2) { fold_weights(c.ix, s.bx, G.rx, s.ex); fold_weights(c.iy, s.by, G.ry, s.ey); fold_weights(c.iz, s.bz, G.rz, s.ez); }
     }
 }
+template <bool ROWS4 = false>
 SDFRT_HD void load_taps(const GridView& G, int bx, int by, int bz, float f[64]) {
     // 32-bit element offsets (grids up to 2^32 texels): one address computation per row, taps at +0..+3
     const unsigned sy = (unsigned)G.rx, sz = (unsigned)G.rx * (unsigned)G.ry;
     const unsigned o = (unsigned)bz * sz + (unsigned)by * sy + (unsigned)bx;
+    if (ROWS4) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
+        for (int k = 0; k < 4; ++k)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float* row = G.data + (o + (unsigned)k * sz + (unsigned)j * sy);
+            for (int j = 0; j < 4; ++j) {
+                const float4 r = G.rows4[o + (unsigned)k * sz + (unsigned)j * sy];
+                f[(k * 4 + j) * 4 + 0] = r.x; f[(k * 4 + j) * 4 + 1] = r.y; f[(k * 4 + j) * 4 + 2] = r.z; f[(k * 4 + j) * 4 + 3] = r.w;
+            }
+    } else {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) f[(k * 4 + j) * 4 + i] = row[i];
-        }
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float* row = G.data + (o + (unsigned)k * sz + (unsigned)j * sy);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) f[(k * 4 + j) * 4 + i] = row[i];
+            }
+    }
 }
 template <int ORDER>
 SDFRT_HD void reduce_taps(const float f[64], const CellSetup<ORDER>& s, const GridView& G, float& v, V3& g, S3& H) {

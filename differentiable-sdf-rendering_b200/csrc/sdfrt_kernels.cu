@@ -10,6 +10,7 @@
 // No CPU fallback exists: every entry point launches device work or fails.
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -20,6 +21,7 @@
 
 #include "sdfrt_params.h"
 #include "sdfrt_march.cuh"
+#include "sdfrt_grid.cuh"
 
 using namespace sdfrt;
 
@@ -241,6 +243,20 @@ struct sdfrt_ctx {
     unsigned long long batch_target = 0;  // camera samples per batch; 0 = n / 6 clamped to [2^20, 2^24] (measured best at c3)
     int num_sms = 0;
     int march_blocks[6] = {0, 0, 0, 0, 0, 0};  // resident blocks per SM of k_march<DIFF, CACHE> at [3*DIFF + CACHE]
+    // Row-expanded copy of the SDF grid for the marchers (GridView::rows4): 4x the memory, one 16-byte load per x-row of a
+    // block instead of four 4-byte loads.  Pays while the copy stays mostly L2-resident (256^3: +18 %), loses at 512^3
+    // (2 GiB copy, DRAM-bound: -12 %), hence the size gate.  rows4_roles = bitmask over the four marcher roles, -1 = by size.
+    // grid-update scratch (sdfrt_grid.cuh)
+    unsigned* rd_work = nullptr;             // [2][n_tiles] work lists + [2][n_tiles] flags
+    size_t rd_work_n = 0;
+    RdState* rd_state = nullptr;
+    int rd_blocks = 0;                       // co-resident blocks of k_rd_solve
+    float* lap_r = nullptr;
+    size_t lap_r_n = 0;
+    float4* rows4 = nullptr;
+    size_t rows4_n = 0;
+    int rows4_roles = -1, march_role = 0;
+    bool rows4_on = false;
     int cache_mode[4] = {1, 1, 0, 1};        // tap-cache mode of [value primary, value shadow, diff primary, diff shadow]
     // buffers of the host entry point
     float *h_sdf = nullptr, *h_film = nullptr, *h_film2 = nullptr, *h_image = nullptr, *h_gimg = nullptr, *h_grad = nullptr;
@@ -310,13 +326,21 @@ int check_ready(sdfrt_ctx* ctx, int spp) {
 template <bool DIFF, int CACHE>
 void launch_march(sdfrt_ctx* ctx, unsigned grid, cudaStream_t st, const SegIn* segs, const unsigned* region_fill, unsigned n_slots, unsigned region,
                   int do_refine, float* out_its, float* rec_out, unsigned long long rec_stride, unsigned* region_counter) {
-    k_march<DIFF, CACHE><<<grid, kMarchBlock, 0, st>>>(ctx->sc.G, ctx->sc.T, segs, region_fill, n_slots, region, do_refine, ctx->min_live, out_its, rec_out,
+    GridView G = ctx->sc.G;
+    G.rows4 = (ctx->rows4_on && ((ctx->rows4_roles < 0 ? 15 : ctx->rows4_roles) >> ctx->march_role & 1)) ? ctx->rows4 : nullptr;
+    if (G.rows4)
+        k_march<DIFF, CACHE, true><<<grid, kMarchBlock, 0, st>>>(G, ctx->sc.T, segs, region_fill, n_slots, region, do_refine, ctx->min_live, out_its, rec_out,
+                                                                 rec_stride, region_counter, ctx->counters);
+    else
+    k_march<DIFF, CACHE, false><<<grid, kMarchBlock, 0, st>>>(G, ctx->sc.T, segs, region_fill, n_slots, region, do_refine, ctx->min_live, out_its, rec_out,
                                                        rec_stride, region_counter, ctx->counters);
 }
 template <bool DIFF>
-void launch_march_mode(sdfrt_ctx* ctx, int mode, unsigned need, cudaStream_t st, const SegIn* segs, const unsigned* region_fill,
+void launch_march_mode(sdfrt_ctx* ctx, int role /* index into cache_mode */, unsigned need, cudaStream_t st, const SegIn* segs, const unsigned* region_fill,
                        unsigned n_slots, unsigned region, int do_refine, float* out_its, float* rec_out, unsigned long long rec_stride,
                        unsigned* region_counter) {
+    const int mode = ctx->cache_mode[role];
+    ctx->march_role = role;
     const int bps = ctx->march_blocks[(DIFF ? 3 : 0) + mode];
     unsigned grid = (unsigned)ctx->num_sms * (unsigned)bps;
     if (grid > need) grid = need;
@@ -328,6 +352,8 @@ void launch_march_mode(sdfrt_ctx* ctx, int mode, unsigned need, cudaStream_t st,
 // One forward sweep over this rank's camera samples: the primal render (value tracers) or adjoint sweep 1 (differentiable
 // tracers + lane records).  Several sweeps can be enqueued together (run_sweeps): their batches then share the pipeline
 // slots, so the latency tail of one sweep's persistent kernels is filled with the other's work.
+constexpr size_t kRows4MaxTexels = (size_t)1 << 24;  // 256^3: 256 MiB expanded copy
+
 struct Sweep {
     bool diff;
     PassParams ps;
@@ -360,10 +386,10 @@ int enqueue_batch(sdfrt_ctx* ctx, const Sweep& sw, unsigned long long item0, int
     const unsigned need = (cnt + kMarchBlock - 1) / kMarchBlock;
     { LaunchScope ls(ctx, 1, bs);
       if (DIFF && reparam_at_depth(ctx->sc.W, 0))
-          launch_march_mode<true>(ctx, ctx->cache_mode[2], need, bs, reinterpret_cast<const SegIn*>(sc.segs), nullptr, cnt, region, 1,
+          launch_march_mode<true>(ctx, 2, need, bs, reinterpret_cast<const SegIn*>(sc.segs), nullptr, cnt, region, 1,
                                   nullptr, rec_b, ctx->rec_stride, work + WQ_PRIMARY_CHUNK);
       else  // value tracer; a DIFF pass without a primary warp (DummyWarpField / None) only needs its_t (record row 0)
-          launch_march_mode<false>(ctx, ctx->cache_mode[0], need, bs, reinterpret_cast<const SegIn*>(sc.segs), nullptr, cnt, region, 1,
+          launch_march_mode<false>(ctx, 0, need, bs, reinterpret_cast<const SegIn*>(sc.segs), nullptr, cnt, region, 1,
                                    DIFF ? rec_b : sc.its, nullptr, 0, work + WQ_PRIMARY_CHUNK); }
     const float* its = DIFF ? rec_b : sc.its;
     { LaunchScope ls(ctx, 2, bs);
@@ -375,10 +401,10 @@ int enqueue_batch(sdfrt_ctx* ctx, const Sweep& sw, unsigned long long item0, int
         const bool shadow_diff = DIFF && reparam_at_depth(ctx->sc.W, 1);
         { LaunchScope ls(ctx, 3, bs);
           if (shadow_diff)
-              launch_march_mode<true>(ctx, ctx->cache_mode[3], need, bs, reinterpret_cast<const SegIn*>(sc.ssegs), q.count,
+              launch_march_mode<true>(ctx, 3, need, bs, reinterpret_cast<const SegIn*>(sc.ssegs), q.count,
                                       regions * region, region, 0, nullptr, sc.srec, B, work + WQ_SHADOW_CHUNK);
           else
-              launch_march_mode<false>(ctx, ctx->cache_mode[1], need, bs, reinterpret_cast<const SegIn*>(sc.ssegs), q.count,
+              launch_march_mode<false>(ctx, 1, need, bs, reinterpret_cast<const SegIn*>(sc.ssegs), q.count,
                                        regions * region, region, 0, sc.s_its, nullptr, 0, work + WQ_SHADOW_CHUNK); }
         const float* shadow_its = shadow_diff ? sc.srec : sc.s_its;
         { LaunchScope ls(ctx, 4, bs);
@@ -466,6 +492,23 @@ int run_sweeps(sdfrt_ctx* ctx, Sweep* sweeps, int ns, cudaStream_t st) {
             sw.mask = m;
         }
     }
+    ctx->rows4_on = false;
+    if (ctx->rows4_roles != 0) {
+        const GridView& G = ctx->sc.G;
+        const size_t nt = (size_t)G.rx * G.ry * G.rz;
+        ctx->rows4_on = ctx->rows4_roles > 0 || nt <= kRows4MaxTexels;
+    }
+    if (ctx->rows4_on) {
+        const GridView& G = ctx->sc.G;
+        const size_t nt = (size_t)G.rx * G.ry * G.rz;
+        if (ctx->rows4_n < nt) {
+            cudaFree(ctx->rd_work); cudaFree(ctx->rd_state); cudaFree(ctx->lap_r); cudaFree(ctx->rows4); ctx->rows4 = nullptr; ctx->rows4_n = 0;
+            SDFRT_CUDA(ctx, cudaMalloc(&ctx->rows4, nt * sizeof(float4)));
+            ctx->rows4_n = nt;
+        }
+        { LaunchScope ls(ctx, 0, st); k_expand_rows<<<(unsigned)ctx->num_sms * 8, 256, 0, st>>>(G, ctx->rows4); }
+        ctx->n_launches += 1;
+    }
     // fork: the internal streams wait for everything queued on the caller's stream (film memsets, masks)
     if (nslots > 1) {
         SDFRT_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
@@ -549,6 +592,7 @@ sdfrt_ctx* sdfrt_create(int device, int* status) {
     }
     ctx->num_sms = prop.multiProcessorCount;
     bool ok = cudaMalloc((void**)&ctx->work, kSlots * WQ_COUNT * sizeof(unsigned)) == cudaSuccess;
+    if (const char* e = std::getenv("SDFRT_ROWS4")) ctx->rows4_roles = std::atoi(e) & 15;   // developer override: 0 = off, else role mask
     if (const char* e = std::getenv("SDFRT_SLOTS")) ctx->max_slots = std::max(1, std::min(kSlots, std::atoi(e)));          // developer overrides
     if (const char* e = std::getenv("SDFRT_MIN_LIVE")) ctx->min_live = std::max(1, std::min(32, std::atoi(e)));
     if (const char* e = std::getenv("SDFRT_SKIP_EMPTY")) ctx->skip_empty = std::atoi(e) != 0;
@@ -558,12 +602,12 @@ sdfrt_ctx* sdfrt_create(int device, int* status) {
         ok = ok && cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
     }
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
-    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->march_blocks[0], k_march<false, 0>, kMarchBlock, 0) == cudaSuccess;
-    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->march_blocks[1], k_march<false, 1>, kMarchBlock, 0) == cudaSuccess;
-    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->march_blocks[2], k_march<false, 2>, kMarchBlock, 0) == cudaSuccess;
-    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->march_blocks[3], k_march<true, 0>, kMarchBlock, 0) == cudaSuccess;
-    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->march_blocks[4], k_march<true, 1>, kMarchBlock, 0) == cudaSuccess;
-    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->march_blocks[5], k_march<true, 2>, kMarchBlock, 0) == cudaSuccess;
+    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->march_blocks[0], k_march<false, 0, false>, kMarchBlock, 0) == cudaSuccess;
+    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->march_blocks[1], k_march<false, 1, false>, kMarchBlock, 0) == cudaSuccess;
+    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->march_blocks[2], k_march<false, 2, false>, kMarchBlock, 0) == cudaSuccess;
+    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->march_blocks[3], k_march<true, 0, false>, kMarchBlock, 0) == cudaSuccess;
+    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->march_blocks[4], k_march<true, 1, false>, kMarchBlock, 0) == cudaSuccess;
+    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->march_blocks[5], k_march<true, 2, false>, kMarchBlock, 0) == cudaSuccess;
     for (int i = 0; i < 6; ++i) ok = ok && ctx->march_blocks[i] >= 1;
     if (const char* e = std::getenv("SDFRT_CACHE_MODES")) {  // developer override, e.g. "1102"
         for (int i = 0; i < 4 && e[i]; ++i) ctx->cache_mode[i] = (e[i] - '0') % 3;
@@ -586,7 +630,7 @@ void sdfrt_destroy(sdfrt_ctx* ctx) {
     cudaFree(ctx->film_adj);
     cudaFree(ctx->counters);
     cudaFree(ctx->work);
-    cudaFree(ctx->brick_raw); cudaFree(ctx->brick); cudaFree(ctx->pix_mask);
+    cudaFree(ctx->rows4); cudaFree(ctx->brick_raw); cudaFree(ctx->brick); cudaFree(ctx->pix_mask);
     for (auto& sc : ctx->scratch) {
         cudaFree(sc.segs); cudaFree(sc.its); cudaFree(sc.ssegs); cudaFree(sc.sinfo); cudaFree(sc.s_its); cudaFree(sc.srec); cudaFree(sc.scount);
     }
@@ -605,6 +649,7 @@ int sdfrt_set_sdf(sdfrt_ctx* ctx, const float* sdf, int rx, int ry, int rz, cons
     if (!ctx) return SDFRT_ERR_INVALID;
     if (!sdf || rx < 4 || ry < 4 || rz < 4) return fail(ctx, SDFRT_ERR_INVALID, "bad SDF grid (need >= 4 texels per axis)");
     ctx->sc.G.data = sdf;
+    ctx->sc.G.rows4 = nullptr;
     ctx->sc.G.rx = rx; ctx->sc.G.ry = ry; ctx->sc.G.rz = rz;
     ctx->sc.G.px = p ? p[0] : 0.f; ctx->sc.G.py = p ? p[1] : 0.f; ctx->sc.G.pz = p ? p[2] : 0.f;
     ctx->have_sdf = true;
@@ -848,6 +893,93 @@ int sdfrt_eval_sdf(sdfrt_ctx* ctx, const float* x, int n, int order, float* out,
     SDFRT_CUDA(ctx, cudaSetDevice(ctx->device));
     k_eval_sdf<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(ctx->sc.G, x, n, order, out);
     SDFRT_CUDA(ctx, cudaGetLastError());
+    return SDFRT_OK;
+}
+
+int sdfrt_redistance(sdfrt_ctx* ctx, const float* phi, const float* lower_bound, float* out, int rx, int ry, int rz, int* iters_out,
+                     void* stream) {
+    if (!ctx || !phi || !out) return SDFRT_ERR_INVALID;
+    if (rx < 1 || ry < 1 || rz < 1) return fail(ctx, SDFRT_ERR_INVALID, "bad grid size");
+    if (phi == out) return fail(ctx, SDFRT_ERR_INVALID, "redistance cannot run in place");
+    SDFRT_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)rx * ry * rz;
+    const size_t n_tiles = (size_t)((rx + kRdTile - 1) / kRdTile) * ((ry + kRdTile - 1) / kRdTile) * ((rz + kRdTile - 1) / kRdTile);
+    if (n_tiles > 0x7fffffffull) return fail(ctx, SDFRT_ERR_INVALID, "grid too large");
+    if (ctx->rd_work_n < 4 * n_tiles) {
+        cudaFree(ctx->rd_work); ctx->rd_work = nullptr; ctx->rd_work_n = 0;
+        SDFRT_CUDA(ctx, cudaMalloc(&ctx->rd_work, 4 * n_tiles * sizeof(unsigned)));
+        ctx->rd_work_n = 4 * n_tiles;
+    }
+    if (!ctx->rd_state) SDFRT_CUDA(ctx, cudaMalloc(&ctx->rd_state, sizeof(RdState)));
+    if (ctx->rd_blocks == 0) {
+        int coop = 0, per_sm = 0;
+        SDFRT_CUDA(ctx, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
+        if (!coop) return fail(ctx, SDFRT_ERR_STATE, "device lacks cooperative launch");
+        SDFRT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rd_solve, kRdThreads, 0));
+        if (per_sm < 1) return fail(ctx, SDFRT_ERR_STATE, "k_rd_solve does not fit on an SM");
+        ctx->rd_blocks = per_sm * ctx->num_sms;
+    }
+    RdGrid g;
+    g.phi = phi; g.lower_bound = lower_bound; g.rx = rx; g.ry = ry; g.rz = rz;
+    g.hx = 1.0f / (float)rx; g.hy = 1.0f / (float)ry; g.hz = 1.0f / (float)rz;
+    const unsigned gb = (unsigned)((n + 255) / 256);
+    unsigned* lists = ctx->rd_work;
+    unsigned* flags = ctx->rd_work + 2 * n_tiles;
+    SDFRT_CUDA(ctx, cudaMemsetAsync(ctx->rd_state, 0, sizeof(RdState), st));
+    SDFRT_CUDA(ctx, cudaMemsetAsync(flags, 0, 2 * n_tiles * sizeof(unsigned), st));
+    k_rd_init<<<gb, 256, 0, st>>>(g, out);
+    {
+        RdState* state = ctx->rd_state;
+        float hx = g.hx, hy = g.hy, hz = g.hz;
+        void* args[] = {&out, &rx, &ry, &rz, &hx, &hy, &hz, &lists, &flags, &state};
+        unsigned blocks = (unsigned)std::min<size_t>((size_t)ctx->rd_blocks, n_tiles);
+        SDFRT_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)k_rd_solve, dim3(blocks), dim3(kRdThreads), args, 0, st));
+    }
+    k_rd_finish<<<gb, 256, 0, st>>>(g, out);
+    SDFRT_CUDA(ctx, cudaGetLastError());
+    ctx->n_launches += 3;
+    if (iters_out) {
+        unsigned head[4];
+        SDFRT_CUDA(ctx, cudaMemcpyAsync(head, ctx->rd_state, sizeof(head), cudaMemcpyDeviceToHost, st));
+        SDFRT_CUDA(ctx, cudaStreamSynchronize(st));
+        if (head[2] != 0u) return fail(ctx, SDFRT_ERR_CUDA, head[2] == 1u ? "redistance: grid barrier timed out" : "redistance: iteration cap reached");
+        *iters_out = (int)head[3];
+    }
+    return SDFRT_OK;
+}
+
+int sdfrt_adam_step(sdfrt_ctx* ctx, float* param, float* grad, float* m, float* v, size_t n, float lr, float beta1, float beta2, float eps,
+                    int t, float grad_clamp, float lo, float hi, void* stream) {
+    if (!ctx || !param || !grad || !m || !v) return SDFRT_ERR_INVALID;
+    if (t < 1) return fail(ctx, SDFRT_ERR_INVALID, "Adam step count starts at 1");
+    if (n == 0) return SDFRT_OK;
+    SDFRT_CUDA(ctx, cudaSetDevice(ctx->device));
+    AdamParams a;
+    // lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t), evaluated in double like the reference's Python scalars
+    a.lr_t = (float)((double)lr * std::sqrt(1.0 - std::pow((double)beta2, (double)t)) / (1.0 - std::pow((double)beta1, (double)t)));
+    a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.grad_clamp = grad_clamp; a.lo = lo; a.hi = hi;
+    const unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)ctx->num_sms * 16);
+    k_adam_step<<<grid, 256, 0, (cudaStream_t)stream>>>(param, grad, m, v, n, a);
+    SDFRT_CUDA(ctx, cudaGetLastError());
+    ctx->n_launches += 1;
+    return SDFRT_OK;
+}
+
+int sdfrt_laplacian_reg(sdfrt_ctx* ctx, const float* data, int rx, int ry, int rz, float weight, double* loss_out, float* grad,
+                        void* stream) {
+    if (!ctx || !data) return SDFRT_ERR_INVALID;
+    if (rx < 1 || ry < 1 || rz < 1) return fail(ctx, SDFRT_ERR_INVALID, "bad grid size");
+    SDFRT_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n = (size_t)rx * ry * rz;
+    int rc;
+    if ((rc = ensure(ctx, &ctx->lap_r, &ctx->lap_r_n, n))) return rc;
+    const unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)ctx->num_sms * 8);
+    k_laplacian_residual<<<grid, 256, 0, st>>>(data, ctx->lap_r, rx, ry, rz, (double)weight, loss_out);
+    if (grad) k_laplacian_grad<<<grid, 256, 0, st>>>(ctx->lap_r, grad, rx, ry, rz, weight);
+    SDFRT_CUDA(ctx, cudaGetLastError());
+    ctx->n_launches += grad ? 2 : 1;
     return SDFRT_OK;
 }
 

@@ -196,6 +196,45 @@ class Context:
         check(self.ctx, self.lib.sdfrt_eval_sdf(self.ctx, _ptr(x), n, order, _ptr(out), _stream(self.device)))
         return out
 
+    # ---- per-iteration grid update (sdfrt_grid.cuh) -------------------------------------------------------------
+    def redistance(self, phi, lower_bound=None, return_iters=False):
+        """redistancing.redistance(max(phi, lower_bound)) (python/redistancing.py:4-13, python/variables.py:185-189)."""
+        shape = phi.shape
+        grid = phi.reshape(shape[:3]) if phi.dim() == 4 else phi
+        _f32c(grid, self.device)
+        if lower_bound is not None:
+            lower_bound = lower_bound.reshape(grid.shape)
+            _f32c(lower_bound, self.device)
+        out = torch.empty_like(grid)
+        rz, ry, rx = grid.shape
+        iters = C.c_int(0)
+        check(self.ctx, self.lib.sdfrt_redistance(self.ctx, _ptr(grid), _ptr(lower_bound) if lower_bound is not None else None,
+                                                  _ptr(out), rx, ry, rz, C.byref(iters) if return_iters else None,
+                                                  _stream(self.device)))
+        out = out.reshape(shape)
+        return (out, iters.value) if return_iters else out
+
+    def adam_step(self, param, grad, m, v, lr, t, beta1=0.9, beta2=0.999, eps=1e-8, grad_clamp=0.0, lo=1.0, hi=0.0):
+        """In-place mi.ad.Adam.step on one tensor with the reference's gradient / value validation fused in."""
+        for a in (param, grad, m, v):
+            _f32c(a, self.device)
+        check(self.ctx, self.lib.sdfrt_adam_step(self.ctx, _ptr(param), _ptr(grad), _ptr(m), _ptr(v), param.numel(), lr, beta1,
+                                                 beta2, eps, int(t), grad_clamp, lo, hi, _stream(self.device)))
+
+    def laplacian_reg(self, data, weight=1.0, grad=None, return_loss=True):
+        """regularizations.eval_discrete_laplacian_reg (python/regularizations.py:5-25): returns weight * R as a 0-d float64
+        tensor (if return_loss) and adds weight * dR/d(data) to `grad` (if given)."""
+        grid = data.reshape(data.shape[:3]) if data.dim() == 4 else data
+        _f32c(grid, self.device)
+        rz, ry, rx = grid.shape
+        loss = torch.zeros((), dtype=torch.float64, device=self.device) if return_loss else None
+        if grad is not None:
+            _f32c(grad, self.device)
+        check(self.ctx, self.lib.sdfrt_laplacian_reg(self.ctx, _ptr(grid), rx, ry, rz, weight,
+                                                     _ptr(loss) if loss is not None else None,
+                                                     _ptr(grad) if grad is not None else None, _stream(self.device)))
+        return loss
+
     def render_view_host(self, sdf_host, seed, spp, seed_grad, spp_grad, grad_image_host=None, image_host=None,
                          grad_sdf_host=None):
         """End-to-end call with HOST (numpy / pinned torch CPU) buffers."""

@@ -53,8 +53,9 @@ class Grid3d(SDFBase):
 
     def __init__(self, data, transform=None, device=0, context=None):
         super().__init__()
-        if isinstance(data, str):
-            raise NotImplementedError("loading .vol files / redistancing is outside the hot path (SURVEY 8f#3)")
+        if isinstance(data, str):  # python/shapes.py:384-386: load a .vol grid and re-distance it
+            from . import redistancing, volio
+            data = redistancing.redistance(volio.read_vol(data)[0][..., 0])
         if transform is not None:
             raise NotImplementedError("sdf_to_world transforms are not supported (has_transform == False path only)")
         self.has_transform = False
@@ -146,8 +147,22 @@ class BoxSDF(SDFBase):
         return torch.linalg.norm(q.clamp_min(0.0), dim=-1) + q.max(-1).values.clamp_max(0.0) - self.smoothing
 
 
-def create_sphere_sdf(res, center=(0.5, 0.5, 0.5), radius=0.3):
-    """python/shapes.py:557-581 without noise and without the redistancing pass (exact SDF already)."""
+def create_sphere_sdf(res, center=(0.5, 0.5, 0.5), radius=0.3, redistance=False):
+    """python/shapes.py:557-581 without noise.  The reference finishes with `redistancing.redistance` (:580); that pass needs
+    the GPU here, so it is opt-in (`redistance=True` returns a CUDA tensor), the default returns the analytic numpy grid."""
     z, y, x = np.meshgrid(np.linspace(0, 1, res[0]), np.linspace(0, 1, res[1]), np.linspace(0, 1, res[2]), indexing='ij')
     pts = np.stack([x.ravel(), y.ravel(), z.ravel()], axis=1)
-    return np.reshape(np.linalg.norm(pts - np.asarray(center), axis=-1) - radius, res).astype(np.float32)
+    sdf = np.reshape(np.linalg.norm(pts - np.asarray(center), axis=-1) - radius, res).astype(np.float32)
+    if redistance:
+        from . import redistancing
+        return redistancing.redistance(sdf)
+    return sdf
+
+
+def create_block_sdf(resolution, center=(0.5, 0.5, 0.5)):
+    """python/shapes.py:584-590: a +-1 occupancy block turned into an SDF by the redistancing pass (CUDA tensor)."""
+    from . import redistancing
+    r2 = resolution // 2
+    signed_dist = np.ones([resolution] * 3, dtype=np.float32)
+    signed_dist[r2 - r2 // 6:r2 + r2 // 6, r2 - r2 // 6:r2 + r2 // 6, r2 - r2 // 2:r2 + r2 // 2] = -1
+    return redistancing.redistance(signed_dist)

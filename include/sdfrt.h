@@ -178,6 +178,28 @@ int sdfrt_trace_rays(sdfrt_ctx* ctx, const float* o, const float* d, const float
  * Also serves variables.upsample_sdf (python/variables.py:18-23). */
 int sdfrt_eval_sdf(sdfrt_ctx* ctx, const float* x, int n, int order, float* out, void* stream);
 
+/* ---- per-iteration grid update (the step on the other side of the gradient) ------------------
+ * These calls work on caller-owned device grids of (rz, ry, rx) floats and do not touch the bound scene. */
+
+/* redistancing.redistance(phi) = fastsweep.redistance, python/redistancing.py:4-13, as applied by
+ * SdfVariable.validate (python/variables.py:185-189) to max(sdf, bbox_sdf): `lower_bound` (optional) is that
+ * bbox_sdf grid.  Unit-cube domain, node spacing 1/resolution per axis, sign of the input kept.  out != phi.
+ * Asynchronous on `stream` unless iters_out (host int, optional: number of work lists the solver ran) is given. */
+int sdfrt_redistance(sdfrt_ctx* ctx, const float* phi, const float* lower_bound, float* out, int rx, int ry, int rz,
+                     int* iters_out, void* stream);
+
+/* mi.ad.Adam.step (python/shape_opt.py:53,102) for one parameter tensor of n floats with the reference's validation fused
+ * in: gradient NaN scrub + clamp to [-grad_clamp, grad_clamp] (SdfVariable.validate_gradient, python/variables.py:193-199;
+ * grad_clamp <= 0 disables it; the scrubbed gradient is written back) and value clamp to [lo, hi]
+ * (VolumeVariable.validate, python/variables.py:114-117; lo > hi disables it).  t = 1-based step count of this tensor. */
+int sdfrt_adam_step(sdfrt_ctx* ctx, float* param, float* grad, float* m, float* v, size_t n, float lr, float beta1, float beta2,
+                    float eps, int t, float grad_clamp, float lo, float hi, void* stream);
+
+/* regularizations.eval_discrete_laplacian_reg (python/regularizations.py:5-25): *loss_out (device double, optional) +=
+ * weight * sum_i (c_i - mean of the 6 clamped neighbours)^2, grad (optional) += weight * d(sum)/dc. */
+int sdfrt_laplacian_reg(sdfrt_ctx* ctx, const float* data, int rx, int ry, int rz, float weight, double* loss_out, float* grad,
+                        void* stream);
+
 /* ---- end-to-end entry point with HOST buffers (what a plugin without device memory calls) --
  * One optimisation-loop view: upload sdf (host, rz*ry*rx floats), render primal at (seed, spp),
  * re-render + backprop at (seed_grad, spp_grad) against grad_image_host (H*W*3; if NULL the

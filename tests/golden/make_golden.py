@@ -52,7 +52,22 @@ def run_case(name):
     return out
 
 
+def redistance_case():
+    """Re-distancing fixture (oracle/redistance_oracle.c): a level-set function with a wobbly sphere-like zero set on an
+    anisotropic 28 x 24 x 20 grid and its re-distanced field."""
+    from oracle import redistance_oracle as ro
+    sys.path.insert(0, os.path.dirname(HERE))
+    import test_redistance_oracle as T
+    phi = T.wobbly((20, 24, 28), seed=42)
+    return dict(phi=phi, dist=ro.redistance(phi))
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'redistance':      # only the grid-update fixtures (the render cases take minutes)
+        np.savez_compressed(os.path.join(HERE, 'redistance_wobbly.npz'), **redistance_case())
+        print('wrote redistance_wobbly')
+        sys.exit(0)
+    np.savez_compressed(os.path.join(HERE, 'redistance_wobbly.npz'), **redistance_case())
     for name in CASES:
         np.savez_compressed(os.path.join(HERE, name + '.npz'), **run_case(name))
         print('wrote', name)

@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "../../differentiable-sdf-rendering_b200/csrc/sdfrt_params.h"
+#include "../../differentiable-sdf-rendering_b200/csrc/sdfrt_grid.cuh"
 
 using namespace sdfrt;
 
@@ -282,4 +283,90 @@ extern "C" int hh_shadow_profile(const hh_scene* h, unsigned seed, int spp, int 
     }
     out[0] = n_shadow; out[1] = n_occ; out[2] = n_mono; out[3] = n_nonmono; out[4] = ev_occ; out[5] = ev_mono; out[6] = ev_nonmono;
     return 0;
+}
+
+// Sequential emulation of the block-asynchronous re-distancing order of k_rd_solve (csrc/sdfrt_grid.cuh): same node
+// arithmetic (rd_init_node / rd_solve are shared source), same tile size, round cap, work lists and wake rules; the tiles
+// of a list are visited one after the other instead of by concurrent blocks.  Lets CPU-only tests check that this update
+// order reaches the fixed point the oracle's sweeps reach.  Returns the number of work lists; visits_out = tile visits.
+extern "C" int hh_redistance_tiles(const float* phi, const float* lower_bound, float* out, int rx, int ry, int rz, long long* visits_out) {
+    RdGrid g;
+    g.phi = phi; g.lower_bound = lower_bound; g.rx = rx; g.ry = ry; g.rz = rz;
+    g.hx = 1.0f / (float)rx; g.hy = 1.0f / (float)ry; g.hz = 1.0f / (float)rz;
+    const size_t sy = (size_t)rx, sz = (size_t)rx * ry, n = sz * rz;
+    std::vector<float> u(n);
+    std::vector<unsigned char> frozen(n);
+    for (int z = 0; z < rz; ++z) for (int y = 0; y < ry; ++y) for (int x = 0; x < rx; ++x) {
+        const size_t i = (size_t)z * sz + (size_t)y * sy + (size_t)x;
+        const float d = rd_init_node(g, x, y, z);
+        frozen[i] = d < kRdInf;
+        u[i] = d;
+    }
+    const int T = kRdTile, P = T + 2;
+    const int ntx = (rx + T - 1) / T, nty = (ry + T - 1) / T, ntz = (rz + T - 1) / T;
+    const int n_tiles = ntx * nty * ntz;
+    std::vector<int> list(n_tiles), next;
+    for (int t = 0; t < n_tiles; ++t) list[t] = t;
+    std::vector<unsigned char> flag(n_tiles, 0);
+    std::vector<float> s(P * P * P), s2(P * P * P);
+    long long visits = 0;
+    int iters = 0;
+    while (!list.empty()) {
+        next.clear();
+        std::fill(flag.begin(), flag.end(), 0);
+        for (int tile : list) {
+            const int tix = tile % ntx, tiy = (tile / ntx) % nty, tiz = tile / (ntx * nty);
+            const int x0 = tix * T - 1, y0 = tiy * T - 1, z0 = tiz * T - 1;
+            bool any_known = false;
+            for (int q = 0; q < P * P * P; ++q) {
+                const int gx = x0 + q % P, gy = y0 + (q / P) % P, gz = z0 + q / (P * P);
+                float v = kRdInf;
+                if (gx >= 0 && gx < rx && gy >= 0 && gy < ry && gz >= 0 && gz < rz) v = u[(size_t)gz * sz + (size_t)gy * sy + (size_t)gx];
+                s[q] = v;
+                any_known |= v < kRdInf;
+            }
+            if (!any_known) continue;
+            ++visits;
+            const std::vector<float> orig = s;
+            bool capped = true;
+            for (int round = 0; round < kRdMaxRounds; ++round) {
+                bool any = false;
+                s2 = s;
+                for (int tz = 0; tz < T; ++tz) for (int ty = 0; ty < T; ++ty) for (int tx = 0; tx < T; ++tx) {
+                    const int gx = x0 + 1 + tx, gy = y0 + 1 + ty, gz = z0 + 1 + tz;
+                    if (gx >= rx || gy >= ry || gz >= rz) continue;
+                    if (frozen[(size_t)gz * sz + (size_t)gy * sy + (size_t)gx]) continue;
+                    const int me = ((tz + 1) * P + (ty + 1)) * P + (tx + 1);
+                    const float cand = rd_solve(fminf(s[me - 1], s[me + 1]), rd_axis(g.hx), fminf(s[me - P], s[me + P]), rd_axis(g.hy),
+                                                fminf(s[me - P * P], s[me + P * P]), rd_axis(g.hz));
+                    if (cand < s[me]) { s2[me] = cand; any = true; }
+                }
+                s.swap(s2);
+                if (!any) { capped = false; break; }
+            }
+            bool face[6] = {false, false, false, false, false, false};
+            for (int tz = 0; tz < T; ++tz) for (int ty = 0; ty < T; ++ty) for (int tx = 0; tx < T; ++tx) {
+                const int me = ((tz + 1) * P + (ty + 1)) * P + (tx + 1);
+                if (!(s[me] < orig[me])) continue;
+                const int gx = x0 + 1 + tx, gy = y0 + 1 + ty, gz = z0 + 1 + tz;
+                u[(size_t)gz * sz + (size_t)gy * sy + (size_t)gx] = s[me];
+                if (tx == 0) face[0] = true; if (tx == T - 1) face[1] = true;
+                if (ty == 0) face[2] = true; if (ty == T - 1) face[3] = true;
+                if (tz == 0) face[4] = true; if (tz == T - 1) face[5] = true;
+            }
+            const int dn[7][3] = {{-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1}, {0, 0, 0}};
+            for (int f = 0; f < 7; ++f) {
+                if (!(f < 6 ? face[f] : capped)) continue;
+                const int nx = tix + dn[f][0], ny = tiy + dn[f][1], nz = tiz + dn[f][2];
+                if (nx < 0 || nx >= ntx || ny < 0 || ny >= nty || nz < 0 || nz >= ntz) continue;
+                const int nt = (nz * nty + ny) * ntx + nx;
+                if (!flag[nt]) { flag[nt] = 1; next.push_back(nt); }
+            }
+        }
+        list.swap(next);
+        ++iters;
+    }
+    for (size_t i = 0; i < n; ++i) out[i] = rd_input(g, i) < 0.0f ? -u[i] : u[i];
+    if (visits_out) *visits_out = visits;
+    return iters;
 }

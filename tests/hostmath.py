@@ -46,7 +46,7 @@ class HHScene(C.Structure):
 
 def build():
     srcs = [SRC] + [os.path.join(HERE, '..', 'differentiable-sdf-rendering_b200', 'csrc', f)
-                    for f in ('sdfrt_core.cuh', 'sdfrt_lane.cuh', 'sdfrt_params.h')]
+                    for f in ('sdfrt_core.cuh', 'sdfrt_lane.cuh', 'sdfrt_params.h', 'sdfrt_grid.cuh')]
     if os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(s) for s in srcs):
         return LIB
     subprocess.check_call(['g++', '-O2', '-std=c++17', '-fPIC', '-shared', '-x', 'c++', SRC, '-o', LIB])

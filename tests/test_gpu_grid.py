@@ -1,0 +1,179 @@
+"""GPU tests (-m gpu) of the per-iteration grid update: sdfrt_redistance / sdfrt_adam_step / sdfrt_laplacian_reg
+through the C ABI (via the Python mirror) against the CPU restatements in oracle/, plus the reconstruction loop built from them.
+Tolerances: re-distancing 1e-6 absolute against the oracle's fixed point (values are O(1); the update order changes the rounding by
+an ulp); Adam and the regulariser gradient 1e-6 relative (fp32 kernels vs float64 restatements)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+@pytest.fixture(scope='module')
+def sdfrt_mod(built):
+    import sdfrt
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return sdfrt
+
+
+@pytest.fixture(scope='module')
+def ctx(sdfrt_mod):
+    return sdfrt_mod.redistancing.shared_context(0)
+
+
+def wobbly(shape, seed=0):
+    import test_redistance_oracle as T
+    return T.wobbly(shape, seed)
+
+
+@pytest.mark.parametrize('shape', [(16, 16, 16), (32, 32, 32), (20, 13, 9), (40, 24, 17), (64, 64, 64)])
+def test_redistance_matches_oracle(ctx, shape):
+    from oracle import redistance_oracle as ro
+    phi = wobbly(shape, seed=shape[2])
+    want = ro.redistance(phi)
+    got, lists = ctx.redistance(torch.from_numpy(phi).cuda(), return_iters=True)
+    got = got.cpu().numpy()
+    assert lists >= 2
+    assert np.abs(got - want).max() <= 1e-6
+    chk = ro.check(phi, got)
+    assert chk['sign_mismatches'] == 0 and chk['frozen'] == 0.0 and chk['eikonal'] < 1e-6
+
+
+def test_redistance_golden_and_lower_bound(ctx, sdfrt_mod):
+    from oracle import redistance_oracle as ro
+    g = dict(np.load(os.path.join(GOLD, 'redistance_wobbly.npz')))
+    got = ctx.redistance(torch.from_numpy(g['phi']).cuda()).cpu().numpy()
+    assert np.abs(got - g['dist']).max() <= 1e-6
+    # max(sdf, bbox_sdf) fused into the call (python/variables.py:185-189), 4-d tensors like sdf.data
+    R = 24
+    phi = wobbly((R, R, R), seed=3) - 0.3                 # grows beyond the box constraint
+    box = sdfrt_mod.synthetic.box_sdf_grid(R).astype(np.float32)
+    want = ro.redistance(np.maximum(phi, box))
+    got = sdfrt_mod.redistancing.redistance(torch.from_numpy(phi)[..., None].cuda(), lower_bound=torch.from_numpy(box)[..., None].cuda())
+    assert got.shape == (R, R, R, 1)
+    assert np.abs(got[..., 0].cpu().numpy() - want).max() <= 1e-6
+
+
+def test_redistance_edge_cases(ctx, sdfrt_mod):
+    one = torch.full((8, 8, 8), 0.7, device='cuda')
+    assert (ctx.redistance(one) >= 1e29).all()            # no interface: every node stays unknown (as in the oracle)
+    phi = torch.ones((8, 8, 8), device='cuda')
+    phi[4, 4, 4] = 0.0
+    d = ctx.redistance(phi)
+    assert d[4, 4, 4] == 0.0 and abs(float(d[4, 4, 5]) - 1 / 8) < 1e-7
+    import ctypes as C
+    ptr = C.c_void_p(phi.data_ptr())
+    assert ctx.lib.sdfrt_redistance(ctx.ctx, ptr, None, ptr, 8, 8, 8, None, None) < 0     # in place is refused
+    assert b'in place' in ctx.lib.sdfrt_last_error(ctx.ctx)
+    from oracle import redistance_oracle as ro
+    blk = sdfrt_mod.create_block_sdf(16)                  # python/shapes.py:584-590: +-1 occupancy block, re-distanced
+    occ = np.ones((16, 16, 16), np.float32)
+    occ[7:9, 7:9, 4:12] = -1
+    assert blk.shape == (16, 16, 16) and np.abs(blk.cpu().numpy() - ro.redistance(occ)).max() <= 1e-6
+    assert abs(float(blk[8, 8, 3]) - 0.5 / 16) < 1e-6     # interface half way between the cells
+    sph = sdfrt_mod.create_sphere_sdf((32, 32, 32), redistance=True)
+    assert sph.is_cuda and abs(float(sph[16, 16, 16]) + 0.3) < 2.0 / 32
+
+
+def test_redistance_full_size_properties(ctx, sdfrt_mod):
+    """256^3 (BASELINE c3 grid): the oracle's own fixed-point check on the GPU result + determinism + agreement with the oracle."""
+    from oracle import redistance_oracle as ro
+    R = 256
+    sdf = sdfrt_mod.synthetic.make_sdf('blobs', R).astype(np.float32)
+    phi = (sdf * (1.0 + 0.5 * np.sin(np.linspace(0, 40, R))[None, None, :])).astype(np.float32)   # same zero set, not a distance
+    t = torch.from_numpy(phi).cuda()
+    got, lists = ctx.redistance(t, return_iters=True)
+    again = ctx.redistance(t)
+    assert torch.equal(got, again)                        # the fixed point does not depend on the block schedule
+    got = got.cpu().numpy()
+    chk = ro.check(phi, got)
+    assert chk['sign_mismatches'] == 0 and chk['frozen'] == 0.0 and chk['eikonal'] < 1e-6
+    assert lists < 3 * R // 8 + 16                        # the front advances a tile per work list
+    want = ro.redistance(phi)
+    assert np.abs(got - want).max() <= 2e-6
+
+
+@pytest.mark.parametrize('variant', ['sdf', 'reflectance', 'plain'])
+def test_adam_step_matches_restatement(ctx, variant):
+    from oracle import grid_update_oracle as go
+    rng = np.random.default_rng(7)
+    n = 40 * 33 * 17
+    p0 = rng.uniform(0.0, 1.0, n).astype(np.float32)
+    kw = dict(sdf=dict(grad_clamp=0.1), reflectance=dict(lo=1e-5, hi=1.0), plain={})[variant]
+    p = torch.from_numpy(p0).cuda()
+    m = torch.zeros_like(p)
+    v = torch.zeros_like(p)
+    pr, mr, vr = p0.astype(np.float64), np.zeros(n), np.zeros(n)
+    for t in range(1, 6):
+        g0 = (rng.standard_normal(n) * (0.3 if variant == 'sdf' else 1e-3)).astype(np.float32)
+        if variant == 'sdf':
+            g0[::97] = np.nan
+        g = torch.from_numpy(g0).cuda()
+        ctx.adam_step(p, g, m, v, lr=4e-2, t=t, **kw)
+        pr, gr, mr, vr = go.adam_step(pr, g0, mr, vr, 4e-2, t, **kw)
+        if variant == 'sdf':
+            assert np.array_equal(g.cpu().numpy(), gr.astype(np.float32))        # the scrubbed gradient is written back
+        assert np.abs(p.cpu().numpy() - pr).max() <= 2e-6 * t
+        assert np.abs(m.cpu().numpy() - mr).max() <= 1e-6 * max(1.0, np.abs(mr).max())
+        assert np.abs(v.cpu().numpy() - vr).max() <= 1e-6 * max(1e-6, np.abs(vr).max())
+    if variant == 'reflectance':
+        assert float(p.min()) >= 1e-5 and float(p.max()) <= 1.0
+
+
+def test_laplacian_regulariser_value_and_gradient(ctx, sdfrt_mod):
+    from oracle import grid_update_oracle as go
+    rng = np.random.default_rng(11)
+    d = rng.standard_normal((19, 24, 31)).astype(np.float32)
+    want, want_grad = go.laplacian_reg(d)
+    t = torch.from_numpy(d)[..., None].cuda().requires_grad_(True)
+    val = sdfrt_mod.regularizations.eval_discrete_laplacian_reg(t)
+    (0.25 * val).backward()
+    assert abs(float(val) - want) <= 1e-5 * want
+    assert np.abs(t.grad[..., 0].cpu().numpy() - 0.25 * want_grad).max() <= 1e-5 * np.abs(want_grad).max()
+    # the torch formulation (reference_laplacian_reg) agrees as well, value and autograd gradient
+    t64 = torch.from_numpy(d).double().requires_grad_(True)
+    ref = sdfrt_mod.regularizations.reference_laplacian_reg(t64)
+    ref.backward()
+    assert abs(float(ref) - want) <= 1e-9 * want and np.abs(t64.grad.numpy() - want_grad).max() <= 1e-9
+
+
+def test_reconstruction_loop_moves_the_surface(sdfrt_mod):
+    """A few iterations of shape_opt.optimize_shape: sphere r = 0.3 -> images of a sphere r = 0.2.  The silhouette gradient must
+    shrink the shape (fewer interior voxels), the grid must stay a re-distanced SDF inside the box constraint, the Adam state
+    must survive, and the x2 upsampling step must go through."""
+    from oracle import redistance_oracle as ro
+    sdfrt = sdfrt_mod
+    R, W = 16, 48
+    sensors = sdfrt.get_regular_cameras(4, resx=W, resy=W)
+    target_sdf = sdfrt.Grid3d(sdfrt.create_sphere_sdf((32, 32, 32), radius=0.2), device=0)
+    target_scene = sdfrt.Scene(sdfrt.integrators.create('sdf_direct_reparam', sdf=target_sdf), sensors)
+    refs = [sdfrt.render(target_scene, sensor=i, seed=100 + i, spp=64) for i in range(4)]
+    sdf = sdfrt.Grid3d(sdfrt.create_sphere_sdf((R, R, R)), device=0)
+    integrator = sdfrt.integrators.create('sdf_direct_reparam', sdf=sdf)
+    wf = sdfrt.WarpField2D(sdf, weight_strategy=6, edge_eps=0.01)
+    wf.clamping_thresh = 0.05
+    integrator.warp_field = wf
+    scene = sdfrt.Scene(integrator, sensors)
+    var = sdfrt.variables.SdfVariable(sdfrt.shape_opt.SDF_KEY, 2 * R, upsample_iter=[6], beta=0.5,
+                                      regularizer=sdfrt.regularizations.eval_discrete_laplacian_reg, regularizer_weight=1e-3)
+    assert tuple(var.shape) == (R, R, R)                  # python/variables.py:88-91: start at resolution / 2^len(upsample_iter)
+    seen = []
+    opt, losses = sdfrt.shape_opt.optimize_shape(scene, [var], refs, n_iter=8, spp=16, primal_spp_mult=2, learning_rate=5e-3,
+                                                 callback=lambda i, l, o: seen.append((i, tuple(o[sdfrt.shape_opt.SDF_KEY].shape))))
+    data = opt[sdfrt.shape_opt.SDF_KEY]
+    assert len(losses) == 8 and all(np.isfinite(losses))
+    assert seen[5][1] == (R, R, R, 1) and seen[6][1] == (2 * R, 2 * R, 2 * R, 1)          # upsampled at iteration 6
+    assert opt.t[sdfrt.shape_opt.SDF_KEY] == 1 and var.mean.shape == data.shape           # state reset by the new shape
+    d = data[..., 0].detach().cpu().numpy()
+    inside_before = (sdfrt.create_sphere_sdf((2 * R,) * 3) < 0).mean()
+    assert 0.2 * inside_before < (d < 0).mean() < 0.85 * inside_before   # the shape shrank towards the target (and is still there)
+    box = sdfrt.synthetic.box_sdf_grid(2 * R).astype(np.float32)
+    assert ((d < 0) & (box > 0)).sum() == 0               # bbox constraint holds
+    chk = ro.check(d, ro.redistance(d))
+    assert chk['sign_mismatches'] == 0
+    assert np.abs(ro.redistance(d) - d).max() < 1.5 / (2 * R)    # already a distance field: re-distancing barely moves it
+    assert scene.integrator().sdf.data.data_ptr() == data.data_ptr()   # the scene renders the optimiser's tensor

@@ -4,6 +4,8 @@ import struct
 import numpy as np
 import torch
 
+import pytest
+
 import sdfrt
 from sdfrt import losses, regularizations, variables, volio
 
@@ -60,10 +62,12 @@ def test_laplacian_regulariser():
                 nb = sum(d[min(max(z + dz, 0), 4), min(max(y + dy, 0), 4), min(max(x + dx, 0), 4)]
                          for dz, dy, dx in ((-1, 0, 0), (1, 0, 0), (0, -1, 0), (0, 1, 0), (0, 0, -1), (0, 0, 1)))
                 ref += (d[z, y, x] - nb / 6) ** 2
-    assert abs(regularizations.eval_discrete_laplacian_reg(torch.from_numpy(d)[..., None]).item() - ref) < 1e-10
+    assert abs(regularizations.reference_laplacian_reg(torch.from_numpy(d)[..., None]).item() - ref) < 1e-10
     lin = torch.arange(5, dtype=torch.float64)[None, None, :].expand(5, 5, 5)
     # a linear field has zero Laplacian away from the clamped faces
-    assert regularizations.eval_discrete_laplacian_reg(lin.contiguous()).item() < 2 * 25 * (1 / 6) ** 2 + 1e-12
+    assert regularizations.reference_laplacian_reg(lin.contiguous()).item() < 2 * 25 * (1 / 6) ** 2 + 1e-12
+    with pytest.raises(sdfrt.SdfrtError):   # the product entry point has no CPU path
+        regularizations.eval_discrete_laplacian_reg(lin.contiguous().float())
 
 
 def test_variable_helpers():
