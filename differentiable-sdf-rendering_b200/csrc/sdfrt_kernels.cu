@@ -502,7 +502,7 @@ int run_sweeps(sdfrt_ctx* ctx, Sweep* sweeps, int ns, cudaStream_t st) {
         const GridView& G = ctx->sc.G;
         const size_t nt = (size_t)G.rx * G.ry * G.rz;
         if (ctx->rows4_n < nt) {
-            cudaFree(ctx->rd_work); cudaFree(ctx->rd_state); cudaFree(ctx->lap_r); cudaFree(ctx->rows4); ctx->rows4 = nullptr; ctx->rows4_n = 0;
+            cudaFree(ctx->rows4); ctx->rows4 = nullptr; ctx->rows4_n = 0;
             SDFRT_CUDA(ctx, cudaMalloc(&ctx->rows4, nt * sizeof(float4)));
             ctx->rows4_n = nt;
         }
@@ -631,6 +631,7 @@ void sdfrt_destroy(sdfrt_ctx* ctx) {
     cudaFree(ctx->counters);
     cudaFree(ctx->work);
     cudaFree(ctx->rows4); cudaFree(ctx->brick_raw); cudaFree(ctx->brick); cudaFree(ctx->pix_mask);
+    cudaFree(ctx->rd_work); cudaFree(ctx->rd_state); cudaFree(ctx->lap_r);
     for (auto& sc : ctx->scratch) {
         cudaFree(sc.segs); cudaFree(sc.its); cudaFree(sc.ssegs); cudaFree(sc.sinfo); cudaFree(sc.s_its); cudaFree(sc.srec); cudaFree(sc.scount);
     }

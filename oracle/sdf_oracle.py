@@ -924,6 +924,385 @@ def render_backward(scene, warp_field, integrator, grad_in, seed, spp):
 
 
 # --------------------------------------------------------------------------------------
+# Path replay backpropagation integrator (python/integrators/sdf_prb_reparam.py), SURVEY §8f#1
+# --------------------------------------------------------------------------------------
+
+
+def coordinate_system(n):
+    """mitsuba `coordinate_system` (Duff et al. 2017), used by `initialize_sh_frame` when dp_du == 0
+    (python/shapes.py:360: dp_du is still zero there).  Returns (s, t); ref_semantics S14."""
+    sign = torch.where(n[:, 2] >= 0, torch.ones_like(n[:, 2]), -torch.ones_like(n[:, 2]))
+    a = -1.0 / (sign + n[:, 2])
+    b = n[:, 0] * n[:, 1] * a
+    s = torch.stack([sign * n[:, 0] * n[:, 0] * a + 1.0, sign * b, -sign * n[:, 0]], -1)
+    t = torch.stack([b, sign + n[:, 1] * n[:, 1] * a, -n[:, 1]], -1)
+    return s, t
+
+
+def sh_frame(n):
+    """SurfaceInteraction.initialize_sh_frame: s = coordinate_system(n).first, t = cross(n, s)."""
+    s, _ = coordinate_system(n)
+    t = torch.linalg.cross(n, s)
+    return s, t
+
+
+def square_to_uniform_disk_concentric(u):
+    """mitsuba warp::square_to_uniform_disk_concentric (Shirley-Chiu); ref_semantics S15."""
+    x = 2 * u[:, 0] - 1
+    y = 2 * u[:, 1] - 1
+    is_zero = (x == 0) & (y == 0)
+    q13 = x.abs() < y.abs()
+    r = torch.where(q13, y, x)
+    rp = torch.where(q13, x, y)
+    r_safe = torch.where(is_zero, torch.ones_like(r), r)
+    phi = 0.25 * math.pi * rp / r_safe
+    phi = torch.where(q13, 0.5 * math.pi - phi, phi)
+    phi = torch.where(is_zero, torch.zeros_like(phi), phi)
+    return torch.stack([r * torch.cos(phi), r * torch.sin(phi)], -1)
+
+
+def square_to_cosine_hemisphere(u):
+    p = square_to_uniform_disk_concentric(u)
+    z = torch.sqrt((1 - (p * p).sum(-1)).clamp_min(0.0))
+    return torch.cat([p, z[:, None]], -1)
+
+
+def mis_weight(pdf_a, pdf_b):
+    """mitsuba.ad.integrators.common.mis_weight: power heuristic, detached, 0 where not finite."""
+    a2 = pdf_a * pdf_a
+    b2 = pdf_b * pdf_b
+    den = a2 + b2
+    w = torch.where(den > 0, a2 / torch.where(den > 0, den, torch.ones_like(den)), torch.zeros_like(den))
+    return w.detach()
+
+
+def _spawn_offset(p, n, d):
+    """Interaction.offset_p: p + detach(n) * detach(mulsign((1 + max|p|) * RayEpsilon, n . d)) (ref_semantics S6)."""
+    pd, nd = p.detach(), n.detach()
+    mag = (1 + pd.abs().max(-1).values) * RAY_EPSILON
+    return p + (mag * dr_sign(dot(nd, d.detach())))[:, None] * nd
+
+
+@dataclass
+class PrbConfig:
+    """Props of SdfPrbReparamIntegrator (python/integrators/sdf_prb_reparam.py:35-48, reparam.py:14)."""
+    max_depth: int = 4
+    rr_depth: int = 5
+
+
+def _clone_sampler(sampler):
+    import copy
+    return copy.deepcopy(sampler)
+
+
+def sample_prb(scene, warp_field, sampler, o, d, maxt, cfg, mode='primal', dL=None, state_in=None):
+    """SdfPrbReparamIntegrator.sample (python/integrators/sdf_prb_reparam.py:242-439), diffuse BSDF + constant
+    environment emitter.  mode 'primal' returns (L, valid_ray); mode 'backward' returns the scalar
+    sum over vertices of <dL, Lo> whose autograd gradient is what `dr.backward_from(dL * Lo)` (:428) accumulates.
+    """
+    primal = mode == 'primal'
+    sdf = scene.sdf
+    dtype = o.dtype
+    N = o.shape[0]
+    INV_4PI = 1.0 / (4 * math.pi)
+    Le_env = torch.as_tensor(scene.env_radiance, dtype=dtype)
+    use_warp = isinstance(warp_field, WarpField2D)
+    depth = torch.zeros(N, dtype=torch.int64)
+    L = torch.zeros(N, 3, dtype=dtype) if primal else state_in.detach().clone()
+    beta = torch.ones(N, 3, dtype=dtype)
+    eta = torch.ones(N, dtype=dtype)
+    mis_em = torch.ones(N, dtype=dtype)
+    active = torch.ones(N, dtype=torch.bool)
+    o_prev = torch.zeros(N, 3, dtype=dtype)
+    d_prev = torch.zeros(N, 3, dtype=dtype)
+    t_prev = torch.full((N,), INF, dtype=dtype)
+    o_cur, d_cur, maxt_cur = o.detach().clone(), d.detach().clone(), maxt.detach().clone()
+    t_cur = sdf.ray_intersect_non_diff(o_cur, d_cur, maxt_cur, active)  # ray_intersect_preliminary (:264)
+    valid_ray = torch.isfinite(t_cur) | (not scene.hide_emitters)
+    if use_warp:  # :267-272
+        m = warp_field.max_reparam_depth
+        reparam_max_depth = m if m >= 0 else 100000
+    else:
+        reparam_max_depth = cfg.max_depth
+    shade_gradient_max_depth = reparam_max_depth
+    loss = torch.zeros((), dtype=dtype)
+    big = torch.full((N,), INF, dtype=dtype)
+
+    for _it in range(cfg.max_depth):  # loop.set_max_iterations(self.max_depth) (:283)
+        # the sampler advances on every lane; values of inactive lanes are never used
+        u_em = sampler.next_2d()
+        u_b1 = sampler.next_1d()  # noqa: F841  (component sample, unused by `diffuse`)
+        u_b2 = sampler.next_2d()
+        u_rr = sampler.next_1d()
+        if not bool(active.any()):
+            break
+        A = torch.nonzero(active).squeeze(-1)
+        nA = A.numel()
+        first = depth[A] == 0
+        oc, dc, tc = o_cur[A], d_cur[A], t_cur[A]
+        hit = torch.isfinite(tc)
+
+        # ---- reparameterise (differential phase only, :290-296) -----------------------------------
+        d_rep = dc
+        det = torch.ones(nA, dtype=dtype)
+        si_prev = None
+        nf = torch.nonzero(~first).squeeze(-1)
+        if not primal:
+            o_rp = oc
+            if nf.numel() > 0:
+                si_prev = sdf.compute_surface_interaction(o_prev[A][nf], d_prev[A][nf], t_prev[A][nf])
+                o_sp = _spawn_offset(si_prev['p'], si_prev['n'], dc[nf])  # si_prev.spawn_ray(ray_cur.d)
+                o_rp = oc.index_add(0, nf, o_sp - oc[nf])
+                si_prev = {k: v.detach() for k, v in si_prev.items()}  # dr.disable_grad(si_prev) (:296)
+            if use_warp:
+                rp_active = depth[A] <= reparam_max_depth
+                mt = torch.where(first, maxt_cur[A], big[:nA])
+                _, d_rep, div, _ = warp_field.ray_intersect(o_rp, dc, mt, depth=0, ray_test=True, reparam=True, active=rp_active)
+                det = torch.where(first, torch.ones_like(div), div)  # ray_reparam_det[first_vertex] = 1
+
+        # ---- current interaction, attached in the differential phase (:298-304) ---------------------
+        h = torch.nonzero(hit).squeeze(-1)
+        nh = h.numel()
+        with torch.set_grad_enabled(not primal):
+            if nh > 0:
+                si = sdf.compute_surface_interaction(oc[h], d_rep[h], tc[h])
+                p, n, cos_i = si['p'], si['n'], si['wi_z']
+            Le = torch.zeros(nA, 3, dtype=dtype)
+            miss = torch.nonzero(~hit).squeeze(-1)
+            if miss.numel() > 0:  # emitter.eval(si_cur): the constant environment for escaped rays
+                Le = Le.index_add(0, miss, beta[A][miss] * mis_em[A][miss, None] * Le_env)
+
+        # ---- next event estimation (:306-333) -----------------------------------------------------------
+        active_next = (depth[A] + 1 < cfg.max_depth) & hit
+        Lr_dir = torch.zeros(nA, 3, dtype=dtype)
+        rho = None
+        if nh > 0:
+            act_em = active_next[h]
+            with torch.no_grad():
+                d_e = square_to_uniform_sphere(u_em[A][h])
+                ds_p = p.detach() + d_e * scene.env_dist
+                ds_pdf = INV_4PI
+            with torch.set_grad_enabled(not primal):
+                o_s = _spawn_offset(p, n, ds_p - p.detach())  # si_cur.spawn_ray_to(ds.p)
+                dvec = ds_p - o_s
+                dist = torch.linalg.norm(dvec, dim=-1)
+                d_s = (dvec / dist[:, None]).detach()  # em_ray.d = detach(em_ray.d) (:317)
+                maxt_s = (dist * (1 - SHADOW_EPSILON)).detach()
+                its_s, d_s_att, det_e, _ = _ray_intersect(scene, warp_field, o_s, d_s, maxt_s, 1, not primal, active=act_em)
+                occluded = torch.isfinite(its_s)
+                act_em = act_em & ~occluded
+                em_weight = Le_env / ds_pdf
+                cos_o = dot(n, d_s_att)
+                rho = eval_albedo(scene, p)
+                gate = (cos_i > 0) & (cos_o > 0) & act_em
+                bsdf_value_em = torch.where(gate[:, None], rho / math.pi * cos_o[:, None], torch.zeros_like(rho))
+                bsdf_pdf_em = torch.where(gate, cos_o.detach() / math.pi, torch.zeros_like(cos_o)).detach()
+                mis_direct = mis_weight(torch.full_like(bsdf_pdf_em, ds_pdf), bsdf_pdf_em)
+                lr = beta[A][h] * mis_direct[:, None] * bsdf_value_em * em_weight * det_e[:, None]
+                lr = torch.where(act_em[:, None], lr, torch.zeros_like(lr))
+                Lr_dir = Lr_dir.index_add(0, h, lr)
+
+        # ---- BSDF sampling (:335-340) -------------------------------------------------------------------
+        with torch.no_grad():
+            bsdf_weight = torch.zeros(nA, 3, dtype=dtype)
+            bs_pdf = torch.zeros(nA, dtype=dtype)
+            wo_w = torch.zeros(nA, 3, dtype=dtype)
+            o_next = torch.zeros(nA, 3, dtype=dtype)
+            if nh > 0:
+                wo_l = square_to_cosine_hemisphere(u_b2[A][h])
+                pdf_h = wo_l[:, 2] / math.pi
+                ok = active_next[h] & (cos_i.detach() > 0) & (pdf_h > 0)
+                bsdf_weight[h] = torch.where(ok[:, None], rho.detach(), torch.zeros_like(rho))
+                bs_pdf[h] = torch.where(ok, pdf_h, torch.zeros_like(pdf_h))
+                nd = n.detach()
+                fs, ft = sh_frame(nd)
+                wo_w[h] = fs * wo_l[:, 0:1] + ft * wo_l[:, 1:2] + nd * wo_l[:, 2:3]
+                o_next[h] = _spawn_offset(p.detach(), nd, wo_w[h])
+            beta_A = beta[A] * bsdf_weight
+        L_prev = L[A]
+        L_A = (L_prev + Le.detach() + Lr_dir.detach()) if primal else (L_prev - Le.detach() - Lr_dir.detach())
+
+        # ---- stopping criterion (:342-349) --------------------------------------------------------------
+        with torch.no_grad():
+            beta_max = beta_A.max(-1).values
+            active_next = active_next & (beta_max != 0)
+            rr_prob = torch.minimum(beta_max * eta[A] ** 2, torch.full_like(beta_max, 0.95))
+            rr_active = depth[A] >= cfg.rr_depth
+            scale = torch.where(rr_active & (rr_prob > 0), 1 / torch.where(rr_prob > 0, rr_prob, torch.ones_like(rr_prob)),
+                                torch.ones_like(rr_prob))
+            beta_A = beta_A * scale[:, None]
+            rr_continue = u_rr[A] < rr_prob
+            active_next = active_next & (~rr_active | rr_continue)
+
+            # ---- next surface (:351-363) ---------------------------------------------------------------
+            t_next = sdf.ray_intersect_non_diff(o_next, wo_w, big[:nA], active_next)
+            next_hit = torch.isfinite(t_next)
+            pdf_em = torch.where(next_hit, torch.zeros(nA, dtype=dtype), torch.full((nA,), INV_4PI, dtype=dtype))
+            mis_em_A = mis_weight(bs_pdf, pdf_em)
+
+        if not primal:
+            sampler_clone = _clone_sampler(sampler)
+            u_em_n = sampler_clone.next_2d()[A]
+            _ = sampler_clone.next_1d()
+            u_b2_n = sampler_clone.next_2d()[A]
+            ann = active_next & next_hit & (depth[A] + 2 < cfg.max_depth)  # active_next_next (:367)
+            Lr_dir_next = torch.zeros(nA, 3, dtype=dtype)
+            bsdf_val_next = torch.zeros(nA, 3, dtype=dtype)
+            k = torch.nonzero(next_hit).squeeze(-1)
+            if k.numel() > 0:
+                with torch.no_grad():
+                    si_n = sdf.compute_surface_interaction(o_next[k], wo_w[k], t_next[k])
+                    cos_i_n = si_n['wi_z']
+                    d_en = square_to_uniform_sphere(u_em_n[k])  # sample_emitter_direction(si_next, ..., test_vis=True):
+                    cos_o_n = dot(si_n['n'], d_en)              # the SDF is not scene geometry, so never occluded
+                    rho_n = eval_albedo(scene, si_n['p'])
+                    g_n = ann[k] & (cos_i_n > 0) & (cos_o_n > 0)
+                    bv = torch.where(g_n[:, None], rho_n / math.pi * cos_o_n[:, None], torch.zeros_like(rho_n))
+                    bp = torch.where(g_n, cos_o_n / math.pi, torch.zeros_like(cos_o_n))
+                    md = mis_weight(torch.full_like(bp, INV_4PI), bp)
+                    lrn = beta_A[k] * md[:, None] * bv * (Le_env / INV_4PI)
+                    Lr_dir_next[k] = torch.where(ann[k, None], lrn, torch.zeros_like(lrn))
+                    wo_nn = square_to_cosine_hemisphere(u_b2_n[k])
+                    g_nn = (cos_i_n > 0) & (wo_nn[:, 2] > 0)
+                    bsdf_val_next[k] = torch.where(g_nn[:, None], rho_n / math.pi * wo_nn[:, 2:3], torch.zeros_like(rho_n))
+            Le_next = torch.where((active_next & ~next_hit)[:, None], beta_A * mis_em_A[:, None] * Le_env,
+                                  torch.zeros(nA, 3, dtype=dtype))
+            L_next = L_A - Le_next - Lr_dir_next
+            extra = Le_next.clone()
+            # previous vertex' BSDF, differentiated through si_cur.p only (:387-406)
+            if nf.numel() > 0 and nh > 0:
+                # lanes that are both non-first and hit: position within h of every such lane
+                in_h = torch.full((nA,), -1, dtype=torch.int64)
+                in_h[h] = torch.arange(nh)
+                in_nf = torch.full((nA,), -1, dtype=torch.int64)
+                in_nf[nf] = torch.arange(nf.numel())
+                both = torch.nonzero((~first) & hit).squeeze(-1)
+                if both.numel() > 0:
+                    pc = p[in_h[both]]
+                    pp = si_prev['p'][in_nf[both]]
+                    npv = si_prev['n'][in_nf[both]]
+                    wo_prev = normalize(pc - pp)
+                    cos_p = dot(npv, wo_prev)
+                    ok_p = (si_prev['wi_z'][in_nf[both]] > 0) & (cos_p.detach() > 0)
+                    sel = both[ok_p]
+                    if sel.numel() > 0:
+                        cp = cos_p[ok_p]
+                        ratio = cp / cp.detach()  # rho_prev / pi cancels
+                        extra = extra.index_add(0, sel, L_prev[sel] * ratio[:, None])
+            # next vertex' BSDF (:399,406): for `diffuse` its value does not depend on wi_next, the term carries
+            # no derivative; written out for completeness with the NaN-free reciprocal
+            inv_n = torch.where(bsdf_val_next != 0, 1 / torch.where(bsdf_val_next != 0, bsdf_val_next, torch.ones_like(bsdf_val_next)),
+                                torch.zeros_like(bsdf_val_next))
+            extra = extra + torch.where(next_hit[:, None], L_next * (bsdf_val_next * inv_n), torch.zeros_like(L_next))
+            # indirect term through the current BSDF (:407-412)
+            Lr_ind = torch.zeros(nA, 3, dtype=dtype)
+            if nh > 0:
+                cos_n = dot(n, wo_w[h])
+                g_c = active_next[h] & (cos_i > 0) & (cos_n > 0)
+                bsdf_val = torch.where(g_c[:, None], rho / math.pi * cos_n[:, None], torch.zeros_like(rho))
+                bsdf_val_det = bsdf_weight[h] * bs_pdf[h, None]
+                inv_det = torch.where(bsdf_val_det != 0, 1 / torch.where(bsdf_val_det != 0, bsdf_val_det, torch.ones_like(bsdf_val_det)),
+                                      torch.zeros_like(bsdf_val_det))
+                Lr_ind = Lr_ind.index_add(0, h, L_A[h] * replace_grad(torch.ones_like(bsdf_val), inv_det * bsdf_val))
+            Lo = (Le + Lr_dir + Lr_ind) * det[:, None] + extra
+            keep = depth[A] <= shade_gradient_max_depth
+            Lo = torch.where(keep[:, None], Lo, torch.zeros_like(Lo))
+            loss = loss + (dL[A] * Lo).sum()
+
+        # ---- advance (:433-438) ------------------------------------------------------------------------------
+        with torch.no_grad():
+            L[A] = L_A
+            beta[A] = beta_A
+            mis_em[A] = mis_em_A
+            o_prev[A], d_prev[A], t_prev[A] = oc, dc, tc
+            o_cur[A], d_cur[A], t_cur[A] = o_next, wo_w, t_next
+            maxt_cur[A] = big[:nA]
+            depth[A] = depth[A] + hit.to(torch.int64)
+            active = active.clone()
+            active[A] = active_next
+    if primal:
+        return L, valid_ray
+    return loss
+
+
+def _camera_rays(scene, seed, spp, lane_range=None):
+    """sample_rays up to the sensor ray (python/integrators/sdf_prb_reparam.py:441-497)."""
+    sensor = scene.sensor
+    dtype = scene.sdf.dtype
+    b = sensor.border
+    Wb, Hb = sensor.width + 2 * b, sensor.height + 2 * b
+    wavefront = Wb * Hb * spp
+    lo, hi = (0, wavefront) if lane_range is None else lane_range
+    idx = torch.arange(lo, hi, dtype=torch.int64)
+    pix = idx // spp
+    py = pix // Wb
+    px = pix - py * Wb
+    pos = torch.stack([px - b, py - b], -1).to(dtype)
+    sampler = IndependentSampler(seed, wavefront, dtype, lane_offset=lo, lane_count=hi - lo)
+    pos_f = pos + sampler.next_2d()
+    _sample1 = sampler.next_1d()  # `sample1` of sample_ray_differential (:492)
+    o, d, maxt = sensor.sample_ray(pos_f, dtype)
+    return sampler, pos_f, o, d, maxt
+
+
+def render_prb(scene, warp_field, seed, spp, cfg=None, lane_range=None, develop=True):
+    """SdfPrbReparamIntegrator.render (python/integrators/sdf_prb_reparam.py:54-76)."""
+    cfg = cfg or PrbConfig()
+    with torch.no_grad():
+        sampler, pos_f, o, d, maxt = _camera_rays(scene, seed, spp, lane_range)
+        L, _valid = sample_prb(scene, warp_field, sampler, o, d, maxt, cfg, 'primal')
+        acc = film_put(scene.sensor, pos_f, torch.cat([L, torch.ones_like(L[:, :1])], -1))
+        return film_develop(scene.sensor, acc) if develop else acc
+
+
+def render_backward_prb(scene, warp_field, grad_in, seed, spp, cfg=None):
+    """SdfPrbReparamIntegrator.render_backward (python/integrators/sdf_prb_reparam.py:154-240).
+
+    Returns (image of the re-render, grad wrt sdf.data, grad wrt sdf.p, grad wrt albedo grid or None)."""
+    cfg = cfg or PrbConfig()
+    if isinstance(warp_field, DummyWarpField):
+        raise AttributeError("'DummyWarpField' object has no attribute 'reparam'")  # python/warp.py:179-196
+    sdf = scene.sdf
+    data0, p0, alb0 = sdf.data, sdf.p, scene.albedo_grid
+    sdf.data = data0.detach().clone().requires_grad_(True)
+    sdf.p = p0.detach().clone().requires_grad_(True)
+    if alb0 is not None:
+        scene.albedo_grid = alb0.detach().clone().requires_grad_(True)
+    try:
+        wrt = [sdf.data, sdf.p] + ([scene.albedo_grid] if alb0 is not None else [])
+        sampler, pos_f, o, d, maxt = _camera_rays(scene, seed, spp)
+        N = o.shape[0]
+        det = torch.ones(N, dtype=o.dtype)
+        uv = pos_f
+        if isinstance(warp_field, WarpField2D):  # sample_rays with reparam (:499-511)
+            m = warp_field.max_reparam_depth
+            act = torch.ones(N, dtype=torch.bool) if (m < 0 or 0 <= m) else torch.zeros(N, dtype=torch.bool)
+            _, d_att, det, _ = warp_field.ray_intersect(o, d, maxt, depth=0, ray_test=True, reparam=True, active=act)
+            uv, _rw = scene.sensor.sample_direction(o + d_att)
+        with torch.no_grad():
+            L, _valid = sample_prb(scene, warp_field, _clone_sampler(sampler), o, d, maxt, cfg, 'primal')
+        Ld = L.clone().requires_grad_(True)
+        acc = film_put(scene.sensor, uv, torch.cat([Ld * det[:, None], det[:, None]], -1))  # value = L*weight*det, weight = det
+        image = film_develop(scene.sensor, acc)
+        loss1 = (image * grad_in).sum()
+        g1 = torch.autograd.grad(loss1, [Ld] + wrt, allow_unused=True)
+        dL = g1[0]
+        loss2 = sample_prb(scene, warp_field, sampler, o, d, maxt, cfg, 'backward', dL=dL, state_in=L)
+        g2 = torch.autograd.grad(loss2, wrt, allow_unused=True) if loss2.requires_grad else [None] * len(wrt)
+        out = []
+        for a, b_, ref in zip(g1[1:], g2, wrt):
+            g = torch.zeros_like(ref)
+            if a is not None:
+                g = g + a
+            if b_ is not None:
+                g = g + b_
+            out.append(g)
+        return image.detach(), out[0], out[1], (out[2] if alb0 is not None else None)
+    finally:
+        sdf.data, sdf.p, scene.albedo_grid = data0, p0, alb0
+
+
+# --------------------------------------------------------------------------------------
 # Synthetic stand-in SDFs (SURVEY §8d) -- scenes of the reference are a separate download
 # --------------------------------------------------------------------------------------
 
