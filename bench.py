@@ -26,8 +26,8 @@ WORKLOADS = {
 }
 METRIC = "primary+adjoint Mrays/s"
 # dram__bytes_read + dram__bytes_write of the k_march launches of ONE c3 step, from the committed ncu launch list
-# profiles/r1_final_launches_c3.csv (30 k_march launches: 6.03 GB; a step has 28) -- mostly the segment arrays and lane
-# records, the SDF grid itself stays in L2.  Only meaningful for the default workload.
+# (segment arrays, lane records and the L2 misses of the row-expanded grid copy; before that copy: 5.6 GB,
+# profiles/r1_final_launches_c3.csv).  Only meaningful for the default workload.
 NCU_DRAM_BYTES_PER_STEP = {'c3_blobs256_tex_512x512_64spp': 11.95e9}  # profiles/r1_launches_rows4_c3.csv: 24 k_march launches per step
 
 

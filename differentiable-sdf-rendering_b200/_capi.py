@@ -7,7 +7,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libsdfrt.so')
 
 SDFRT_OK = 0
-INTEGRATOR_SILHOUETTE, INTEGRATOR_SIMPLE_SHADING, INTEGRATOR_DIRECT = 0, 1, 2
+INTEGRATOR_SILHOUETTE, INTEGRATOR_SIMPLE_SHADING, INTEGRATOR_DIRECT, INTEGRATOR_PRB = 0, 1, 2, 3
 WARP_NONE, WARP_DUMMY, WARP_2D = 0, 1, 2
 
 
@@ -32,6 +32,10 @@ class SensorParams(C.Structure):
 class ShadingParams(C.Structure):
     _fields_ = [('env_radiance', C.c_float * 3), ('env_dist', C.c_float), ('albedo', C.c_float * 3),
                 ('hide_emitters', C.c_int32)]
+
+
+class PrbParams(C.Structure):
+    _fields_ = [('max_depth', C.c_int32), ('rr_depth', C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -65,6 +69,8 @@ SIGNATURES = {
     'sdfrt_set_sensor': (C.c_int, [_P, C.POINTER(SensorParams)]),
     'sdfrt_set_shading': (C.c_int, [_P, C.POINTER(ShadingParams)]),
     'sdfrt_set_integrator': (C.c_int, [_P, C.c_int]),
+    'sdfrt_prb_defaults': (None, [C.POINTER(PrbParams)]),
+    'sdfrt_set_prb': (C.c_int, [_P, C.POINTER(PrbParams)]),
     'sdfrt_set_partition': (C.c_int, [_P, C.c_int, C.c_int]),
     'sdfrt_film_dims': (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     'sdfrt_wavefront_size': (C.c_uint64, [_P, C.c_int]),

@@ -196,6 +196,81 @@ __global__ void k_eval_sdf(GridView G, const float* __restrict__ x, int n, int o
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Path replay integrator (sdfrt_prb.cuh): one thread per camera sample walks its whole path.  First correct form of
+// SURVEY 8f#1 -- the bounce-by-bounce wavefront form on top of k_march is the next step.
+//   k_prb_primal    L per sample -> warp-cooperative film splat; optionally stores L (the state_in of the replay)
+//   k_prb_backward  replays the path with delta_L from the film adjoint and scatters the vertex adjoints
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_prb_primal(const __grid_constant__ SceneParams sc, const __grid_constant__ PassParams ps,
+                                                        float* __restrict__ film, float* __restrict__ L_rec, unsigned long long rec_stride,
+                                                        Counters* counters) {
+    __shared__ SplatSmem s_splat[kBlock / 32];
+    const int lane_id = threadIdx.x & 31;
+    const unsigned long long item = (unsigned long long)blockIdx.x * kBlock + threadIdx.x;
+    const bool valid = item < ps.n_items;
+    LaneStats st = {0, 0, 0, 0, 0, 0, 0};
+    V3 L = v3(0.f);
+    float pfx = 0.f, pfy = 0.f;
+    if (valid) {
+        const WorkItem w = decode_item(ps, item);
+        NoEmit ne;
+        V3 gp = v3(0.f);
+        L = lane_prb<false>(sc, ps, w.lane, nullptr, v3(0.f), ne, gp, st);
+        if (L_rec) {
+            L_rec[item] = L.x; L_rec[item + rec_stride] = L.y; L_rec[item + 2 * rec_stride] = L.z;
+        }
+        // sample position of the splat: the (un-reparameterised) jittered pixel position re-projected (render(), :54-76)
+        Pcg32 rng = sampler_seed(ps.seed, (uint32_t)w.lane);
+        const float r0 = pcg_next_f32(rng), r1 = pcg_next_f32(rng);
+        pfx = (float)(w.px - sc.S.border) + r0 + ((float)sc.S.border - 0.5f);
+        pfy = (float)(w.py - sc.S.border) + r1 + ((float)sc.S.border - 0.5f);
+    }
+    warp_splat(sc.S, film, s_splat[threadIdx.x >> 5], valid, pfx, pfy, L);
+    const unsigned nvv = warp_sum(st.n_value), ng = warp_sum(st.n_grad), al = warp_sum(st.n_albedo), hits = warp_sum(st.n_hit);
+    const unsigned nr = warp_sum(valid ? 1u : 0u);
+    if (lane_id == 0) {
+        atomicAdd(&counters->n_rays, (unsigned long long)nr);
+        if (nvv) atomicAdd(&counters->n_evals_value, (unsigned long long)nvv);
+        if (ng) atomicAdd(&counters->n_evals_grad, (unsigned long long)ng);
+        if (al) atomicAdd(&counters->n_albedo_lookups, (unsigned long long)al);
+        if (hits) atomicAdd(&counters->n_hits, (unsigned long long)hits);
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) k_prb_backward(const __grid_constant__ SceneParams sc, const __grid_constant__ PassParams ps,
+                                                          const float* __restrict__ film_adj, const float* __restrict__ L_rec,
+                                                          unsigned long long rec_stride, BackwardTargets tg, float* grad_p, Counters* counters) {
+    const int lane_id = threadIdx.x & 31;
+    const unsigned long long item = (unsigned long long)blockIdx.x * kBlock + threadIdx.x;
+    LaneStats st = {0, 0, 0, 0, 0, 0, 0};
+    V3 gp = v3(0.f);
+    if (item < ps.n_items) {
+        const WorkItem w = decode_item(ps, item);
+        const V3 L = V3{L_rec[item], L_rec[item + rec_stride], L_rec[item + 2 * rec_stride]};
+        DirectEmit em{tg.grad_sdf, tg.grad_albedo, sc.G};
+        (void)lane_prb<true>(sc, ps, w.lane, film_adj, L, em, gp, st);
+    }
+    const unsigned nvv = warp_sum(st.n_value), h = warp_sum(st.n_hess), nsites = warp_sum(st.n_sites), al = warp_sum(st.n_albedo),
+                   ng = warp_sum(st.n_grad);
+    if (lane_id == 0) {
+        if (nvv) atomicAdd(&counters->n_evals_value, (unsigned long long)nvv);
+        if (ng) atomicAdd(&counters->n_evals_grad, (unsigned long long)ng);
+        if (h) atomicAdd(&counters->n_evals_adjoint, (unsigned long long)h);
+        if (nsites) atomicAdd(&counters->n_scatter_sites, (unsigned long long)nsites);
+        if (al) atomicAdd(&counters->n_albedo_lookups, (unsigned long long)al);
+    }
+    if (grad_p != nullptr) {
+        const float gx = warp_sum_f(gp.x), gy = warp_sum_f(gp.y), gz = warp_sum_f(gp.z);
+        if (lane_id == 0) {
+            if (gx != 0.f) atomicAdd(grad_p + 0, gx);
+            if (gy != 0.f) atomicAdd(grad_p + 1, gy);
+            if (gz != 0.f) atomicAdd(grad_p + 2, gz);
+        }
+    }
+}
+
 }  // namespace
 
 // ----------------------------------------------------------------------------------------------------
@@ -211,6 +286,7 @@ struct sdfrt_ctx {
     sdfrt_warp_params warp_pub;
     sdfrt_sensor sensor_pub;
     sdfrt_shading shading_pub;
+    sdfrt_prb_params prb_pub;
     int rank = 0, world = 1;
     bool have_sdf = false;
     // adjoint state
@@ -541,6 +617,21 @@ int run_sweeps(sdfrt_ctx* ctx, Sweep* sweeps, int ns, cudaStream_t st) {
     return SDFRT_OK;
 }
 
+
+// sdf_prb_reparam forward sweep: primal render, or the re-render of render_backward that also keeps L per sample
+int run_prb_sweep(sdfrt_ctx* ctx, const PassParams& ps, float* film, float* L_rec, unsigned long long rec_stride, cudaStream_t st) {
+    SDFRT_CUDA(ctx, cudaSetDevice(ctx->device));
+    SDFRT_CUDA(ctx, cudaMemsetAsync(film, 0, film_floats(ctx) * sizeof(float), st));
+    if (ps.n_items == 0) return SDFRT_OK;
+    if ((unsigned long long)kBandRows * (unsigned long long)ps.Wb * (unsigned long long)ps.spp > 0xffffffffull)
+        return fail(ctx, SDFRT_ERR_INVALID, "film row band exceeds 2^32 samples");
+    const unsigned long long blocks = (ps.n_items + kBlock - 1) / kBlock;
+    if (blocks > 0x7fffffffull) return fail(ctx, SDFRT_ERR_INVALID, "too many samples for one launch");
+    { LaunchScope ls(ctx, 1, st); k_prb_primal<<<(unsigned)blocks, kBlock, 0, st>>>(ctx->sc, ps, film, L_rec, rec_stride, ctx->counters); }
+    SDFRT_CUDA(ctx, cudaGetLastError());
+    return SDFRT_OK;
+}
+
 }  // namespace
 
 // ----------------------------------------------------------------------------------------------------
@@ -554,6 +645,7 @@ void sdfrt_tracer_defaults(sdfrt_tracer_params* p) { tracer_defaults(p); }
 void sdfrt_warp_defaults(sdfrt_warp_params* p) { warp_defaults(p); }
 void sdfrt_sensor_defaults(sdfrt_sensor* s) { sensor_defaults(s); }
 void sdfrt_shading_defaults(sdfrt_shading* s) { shading_defaults(s); }
+void sdfrt_prb_defaults(sdfrt_prb_params* p) { prb_defaults(p); }
 
 sdfrt_ctx* sdfrt_create(int device, int* status) {
     int n = 0;
@@ -582,6 +674,8 @@ sdfrt_ctx* sdfrt_create(int device, int* status) {
     ctx->sc.W = make_warp(ctx->warp_pub);
     ctx->sc.S = make_sensor(ctx->sensor_pub);
     ctx->sc.Sh = make_shading(ctx->shading_pub);
+    prb_defaults(&ctx->prb_pub);
+    ctx->sc.prb = make_prb(ctx->prb_pub);
     ctx->sc.A.data = nullptr;
     ctx->sc.A.cr = ctx->shading_pub.albedo[0]; ctx->sc.A.cg = ctx->shading_pub.albedo[1]; ctx->sc.A.cb = ctx->shading_pub.albedo[2];
     ctx->sc.integrator = INTEGRATOR_DIRECT;
@@ -706,9 +800,18 @@ int sdfrt_set_shading(sdfrt_ctx* ctx, const sdfrt_shading* s) {
 
 int sdfrt_set_integrator(sdfrt_ctx* ctx, int integrator) {
     if (!ctx) return SDFRT_ERR_INVALID;
-    if (integrator < SDFRT_INTEGRATOR_SILHOUETTE || integrator > SDFRT_INTEGRATOR_DIRECT)
+    if (integrator < SDFRT_INTEGRATOR_SILHOUETTE || integrator > SDFRT_INTEGRATOR_PRB)
         return fail(ctx, SDFRT_ERR_INVALID, "unknown integrator");
     ctx->sc.integrator = integrator;
+    ctx->adj_ready = false;
+    return SDFRT_OK;
+}
+
+int sdfrt_set_prb(sdfrt_ctx* ctx, const sdfrt_prb_params* p) {
+    if (!ctx || !p) return SDFRT_ERR_INVALID;
+    if (p->max_depth < 1 || p->max_depth > 1024 || p->rr_depth < 0) return fail(ctx, SDFRT_ERR_INVALID, "bad PRB parameters (need 1 <= max_depth <= 1024, rr_depth >= 0)");
+    ctx->prb_pub = *p;
+    ctx->sc.prb = make_prb(*p);
     ctx->adj_ready = false;
     return SDFRT_OK;
 }
@@ -741,6 +844,8 @@ int sdfrt_render_primal(sdfrt_ctx* ctx, uint32_t seed, int spp, float* film_accu
     int rc = check_ready(ctx, spp);
     if (rc) return rc;
     if (!film_accum) return fail(ctx, SDFRT_ERR_INVALID, "film_accum is null");
+    if (ctx->sc.integrator == INTEGRATOR_PRB)
+        return run_prb_sweep(ctx, make_pass(ctx->sc.S, seed, spp, ctx->rank, ctx->world), film_accum, nullptr, 0, (cudaStream_t)stream);
     Sweep sw;
     sw.diff = false;
     sw.ps = make_pass(ctx->sc.S, seed, spp, ctx->rank, ctx->world);
@@ -770,7 +875,10 @@ int sdfrt_adjoint_accumulate(sdfrt_ctx* ctx, uint32_t seed_grad, int spp_grad, f
     rc = ensure(ctx, &ctx->rec, &ctx->rec_capacity, (size_t)sw.ps.n_items * REC_COUNT + 1);
     if (rc) return rc;
     ctx->rec_stride = sw.ps.n_items;
-    rc = run_sweeps(ctx, &sw, 1, (cudaStream_t)stream);
+    if (ctx->sc.integrator == INTEGRATOR_PRB)  // re-render of render_backward (:204-206); rows 0..2 of the records keep L
+        rc = run_prb_sweep(ctx, sw.ps, film_accum, ctx->rec, ctx->rec_stride, (cudaStream_t)stream);
+    else
+        rc = run_sweeps(ctx, &sw, 1, (cudaStream_t)stream);
     if (rc) return rc;
     ctx->adj_pass = sw.ps;
     ctx->adj_ready = true;
@@ -794,7 +902,12 @@ int sdfrt_render_view(sdfrt_ctx* ctx, uint32_t seed, int spp, float* film_primal
     rc = ensure(ctx, &ctx->rec, &ctx->rec_capacity, (size_t)sw[1].ps.n_items * REC_COUNT + 1);
     if (rc) return rc;
     ctx->rec_stride = sw[1].ps.n_items;
-    rc = run_sweeps(ctx, sw, 2, (cudaStream_t)stream);
+    if (ctx->sc.integrator == INTEGRATOR_PRB) {
+        rc = run_prb_sweep(ctx, sw[0].ps, film_primal, nullptr, 0, (cudaStream_t)stream);
+        if (!rc) rc = run_prb_sweep(ctx, sw[1].ps, film_adjoint, ctx->rec, ctx->rec_stride, (cudaStream_t)stream);
+    } else {
+        rc = run_sweeps(ctx, sw, 2, (cudaStream_t)stream);
+    }
     if (rc) return rc;
     ctx->adj_pass = sw[1].ps;
     ctx->adj_ready = true;
@@ -821,7 +934,13 @@ int sdfrt_adjoint_backprop(sdfrt_ctx* ctx, const float* film_accum, const float*
     tg.grad_sdf = grad_sdf;
     tg.grad_albedo = grad_albedo;
     const unsigned long long blocks = (n + kBlock - 1) / kBlock;
-    { LaunchScope ls(ctx, 6, st); k_backward<<<(unsigned)blocks, kBlock, 0, st>>>(ctx->sc, ps, ctx->film_adj, ctx->rec, ctx->rec_stride, tg, grad_p, ctx->counters); }
+    if (ctx->sc.integrator == INTEGRATOR_PRB) {
+        LaunchScope ls(ctx, 6, st);
+        k_prb_backward<<<(unsigned)blocks, kBlock, 0, st>>>(ctx->sc, ps, ctx->film_adj, ctx->rec, ctx->rec_stride, tg, grad_p, ctx->counters);
+    } else {
+        LaunchScope ls(ctx, 6, st);
+        k_backward<<<(unsigned)blocks, kBlock, 0, st>>>(ctx->sc, ps, ctx->film_adj, ctx->rec, ctx->rec_stride, tg, grad_p, ctx->counters);
+    }
     SDFRT_CUDA(ctx, cudaGetLastError());
     return SDFRT_OK;
 }

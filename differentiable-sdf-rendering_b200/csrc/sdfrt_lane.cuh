@@ -12,8 +12,12 @@
 
 namespace sdfrt {
 
-enum { INTEGRATOR_SILHOUETTE = 0, INTEGRATOR_SIMPLE_SHADING = 1, INTEGRATOR_DIRECT = 2 };
+enum { INTEGRATOR_SILHOUETTE = 0, INTEGRATOR_SIMPLE_SHADING = 1, INTEGRATOR_DIRECT = 2, INTEGRATOR_PRB = 3 };
 enum { WARP_NONE = 0, WARP_DUMMY = 1, WARP_2D = 2 };
+
+struct PrbParams {  // props of SdfPrbReparamIntegrator (python/integrators/sdf_prb_reparam.py:35-48, reparam.py:14)
+    int max_depth, rr_depth;
+};
 
 struct SceneParams {
     GridView G;
@@ -23,6 +27,7 @@ struct SceneParams {
     SensorParams S;
     ShadingParams Sh;
     int integrator;
+    PrbParams prb;
 };
 
 struct PassParams {

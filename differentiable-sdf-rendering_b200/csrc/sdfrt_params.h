@@ -6,7 +6,7 @@
 #include <cstring>
 
 #include "../../include/sdfrt.h"
-#include "sdfrt_lane.cuh"
+#include "sdfrt_prb.cuh"
 
 namespace sdfrt {
 
@@ -47,6 +47,17 @@ inline void shading_defaults(sdfrt_shading* s) {
     s->env_dist = 2.f * std::sqrt(3.f);
     s->albedo[0] = s->albedo[1] = s->albedo[2] = 0.5f;
     s->hide_emitters = 0;
+}
+
+inline void prb_defaults(sdfrt_prb_params* p) {  // python/integrators/reparam.py:14, sdf_prb_reparam.py:41
+    p->max_depth = 4;
+    p->rr_depth = 5;
+}
+inline PrbParams make_prb(const sdfrt_prb_params& p) {
+    PrbParams o;
+    o.max_depth = p.max_depth;
+    o.rr_depth = p.rr_depth;
+    return o;
 }
 
 inline TracerParams make_tracer(const sdfrt_tracer_params& p) {

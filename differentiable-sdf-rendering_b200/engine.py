@@ -6,12 +6,13 @@ import numpy as np
 import torch
 
 from . import _capi
-from ._capi import (INTEGRATOR_DIRECT, INTEGRATOR_SILHOUETTE, INTEGRATOR_SIMPLE_SHADING, WARP_2D, WARP_DUMMY, WARP_NONE,
+from ._capi import (INTEGRATOR_DIRECT, INTEGRATOR_PRB, INTEGRATOR_SILHOUETTE, INTEGRATOR_SIMPLE_SHADING, WARP_2D, WARP_DUMMY, WARP_NONE,
                     SdfrtError, check)
 
 INTEGRATOR_IDS = {'sdf_silhouette_reparam': INTEGRATOR_SILHOUETTE,
                   'sdf_simple_shading_reparam': INTEGRATOR_SIMPLE_SHADING,
-                  'sdf_direct_reparam': INTEGRATOR_DIRECT}
+                  'sdf_direct_reparam': INTEGRATOR_DIRECT,
+                  'sdf_prb_reparam': INTEGRATOR_PRB}
 
 
 def _ptr(t):
@@ -107,6 +108,10 @@ class Context:
     def set_integrator(self, name_or_id):
         i = INTEGRATOR_IDS[name_or_id] if isinstance(name_or_id, str) else int(name_or_id)
         check(self.ctx, self.lib.sdfrt_set_integrator(self.ctx, i))
+
+    def set_prb(self, max_depth=4, rr_depth=5):
+        p = _capi.PrbParams(int(max_depth), int(rr_depth))
+        check(self.ctx, self.lib.sdfrt_set_prb(self.ctx, C.byref(p)))
 
     def set_partition(self, rank, world):
         check(self.ctx, self.lib.sdfrt_set_partition(self.ctx, rank, world))

@@ -1,0 +1,40 @@
+from .reparam import ReparamIntegrator, Properties
+from ..warp import DummyWarpField
+
+
+class SdfPrbReparamIntegrator(ReparamIntegrator):
+    """python/integrators/sdf_prb_reparam.py:33-521: path replay backpropagation with reparameterised segments
+    (emitter sampling + BSDF sampling combined by MIS, Russian roulette from `rr_depth` on).
+
+    Scope of the CUDA path (csrc/sdfrt_prb.cuh): `diffuse` BSDF (constant or grid reflectance) and one `constant`
+    environment emitter, i.e. the same shading model as the direct integrator; `WarpField2D` or no warp field.
+    """
+    integrator_name = 'sdf_prb_reparam'
+
+    def __init__(self, props=None, sdf=None):
+        super().__init__(props, sdf)
+        props = Properties(props or {})
+        self.reparam_max_depth = props.get('reparam_max_depth', self.max_depth)   # :37
+        self.shade_gradient_max_depth = self.reparam_max_depth                    # :38
+        self.rr_depth = props.get('rr_depth', 5)                                  # :41
+        # Bangaru-2020 convolution warp knobs (:43-45): accepted, unused (WarpFieldConvolution is out of scope)
+        self.reparam_rays = props.get('reparam_rays', 16)
+        self.reparam_kappa = props.get('reparam_kappa', 1e5)
+        self.reparam_exp = props.get('reparam_exp', 3.0)
+
+    def aovs(self):
+        return []
+
+    def _bind(self, scene, sensor):
+        if isinstance(self.warp_field, DummyWarpField):
+            # the reference calls warp_field.reparam (sdf_prb_reparam.py:181), which DummyWarpField lacks (python/warp.py:179-196)
+            raise AttributeError("'DummyWarpField' object has no attribute 'reparam'")
+        if self.max_depth < 1:
+            raise ValueError("max_depth must be >= 1 (unbounded paths, max_depth = -1, are not supported)")
+        ctx = super()._bind(scene, sensor)
+        ctx.set_prb(self.max_depth, self.rr_depth)
+        if self.warp_field is not None:  # :267-272
+            m = self.warp_field.max_reparam_depth
+            self.reparam_max_depth = m if m >= 0 else 100000
+            self.shade_gradient_max_depth = self.reparam_max_depth
+        return ctx

@@ -24,8 +24,8 @@ typedef struct sdfrt_ctx sdfrt_ctx;
 
 enum { SDFRT_OK = 0, SDFRT_ERR_INVALID = -1, SDFRT_ERR_CUDA = -2, SDFRT_ERR_STATE = -3 };
 
-/* integrator plugins, python/integrators/{sdf_silhouette,sdf_simple_shading,sdf_direct}_reparam.py */
-enum { SDFRT_INTEGRATOR_SILHOUETTE = 0, SDFRT_INTEGRATOR_SIMPLE_SHADING = 1, SDFRT_INTEGRATOR_DIRECT = 2 };
+/* integrator plugins, python/integrators/{sdf_silhouette,sdf_simple_shading,sdf_direct,sdf_prb}_reparam.py */
+enum { SDFRT_INTEGRATOR_SILHOUETTE = 0, SDFRT_INTEGRATOR_SIMPLE_SHADING = 1, SDFRT_INTEGRATOR_DIRECT = 2, SDFRT_INTEGRATOR_PRB = 3 };
 /* warp field kinds, python/warp.py: None / DummyWarpField(:179) / WarpField2D(:7) */
 enum { SDFRT_WARP_NONE = 0, SDFRT_WARP_DUMMY = 1, SDFRT_WARP_2D = 2 };
 
@@ -71,6 +71,13 @@ typedef struct sdfrt_shading {
     float albedo[3];       /* used when no albedo grid is bound */
     int32_t hide_emitters; /* python/integrators/sdf_direct_reparam.py:12 */
 } sdfrt_shading;
+
+/* props of the path-replay integrator, python/integrators/sdf_prb_reparam.py:35-48 + reparam.py:14 (max_depth);
+ * diffuse BSDF + constant environment emitter (the shading block above) */
+typedef struct sdfrt_prb_params {
+    int32_t max_depth;  /* loop iterations = path vertices incl. the escaping one; default 4 */
+    int32_t rr_depth;   /* Russian roulette from this depth on; default 5 */
+} sdfrt_prb_params;
 
 /* device-counted work, for the roofline byte count */
 typedef struct sdfrt_stats {
@@ -120,6 +127,8 @@ int sdfrt_set_warp(sdfrt_ctx* ctx, const sdfrt_warp_params* p);   /* integrator.
 int sdfrt_set_sensor(sdfrt_ctx* ctx, const sdfrt_sensor* s);
 int sdfrt_set_shading(sdfrt_ctx* ctx, const sdfrt_shading* s);
 int sdfrt_set_integrator(sdfrt_ctx* ctx, int integrator);         /* SDFRT_INTEGRATOR_* */
+void sdfrt_prb_defaults(sdfrt_prb_params* p);
+int sdfrt_set_prb(sdfrt_ctx* ctx, const sdfrt_prb_params* p);      /* used when the integrator is SDFRT_INTEGRATOR_PRB */
 /* multi-GPU ray partition: the film rows (border included) are cut into bands of 8 rows; this context renders the
  * samples of the bands rank, rank + world, ... (interleaved for load balance).  RNG streams stay keyed by the global
  * wavefront lane index (python/integrators/reparam.py:51), so results do not depend on the world size. */

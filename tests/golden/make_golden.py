@@ -23,6 +23,12 @@ CASES = {
     'knot_silhouette': ('knot', 32, 24, 8, 'sdf_silhouette_reparam', None),
     'sphere_simple': ('sphere', 32, 24, 8, 'sdf_simple_shading_reparam', None),
 }
+# sdf_prb_reparam fixtures: name: (sdf kind, R, W, spp, albedo_res, max_depth, rr_depth, max_reparam_depth)
+PRB_CASES = {
+    'blobs_tex_prb': ('blobs', 32, 16, 4, 8, 4, 5, -1),      # interreflections + reflectance grid
+    'knot_prb_rr': ('knot', 32, 16, 4, None, 6, 1, -1),      # Russian roulette from the second vertex on
+    'blobs_prb_primary': ('blobs', 32, 16, 4, None, 3, 5, 0),  # configs.WarpPRBPrimary: max_reparam_depth = 0
+}
 SEED, SEED_GRAD = 3, 11
 
 
@@ -52,6 +58,22 @@ def run_case(name):
     return out
 
 
+def run_prb_case(name):
+    kind, R, W, spp, ar, max_depth, rr_depth, mrd = PRB_CASES[name]
+    sc = O.make_scene(kind, res=R, width=W, height=W, albedo_grid_res=ar)
+    wf = O.WarpField2D(sc.sdf, weight_strategy=6, edge_eps=0.01)
+    wf.clamping_thresh = 0.05
+    wf.max_reparam_depth = mrd
+    cfg = O.PrbConfig(max_depth=max_depth, rr_depth=rr_depth)
+    img = O.render_prb(sc, wf, seed=SEED, spp=spp, cfg=cfg)
+    img_adj, g, gp, ga = O.render_backward_prb(sc, wf, torch.from_numpy(grad_image(W)), seed=SEED_GRAD, spp=spp, cfg=cfg)
+    out = dict(image=img.numpy().astype(np.float32), image_adj=img_adj.numpy().astype(np.float32),
+               grad_sdf=g.numpy().astype(np.float32), grad_p=gp.numpy().astype(np.float32))
+    if ga is not None:
+        out['grad_albedo'] = ga.numpy().astype(np.float32)
+    return out
+
+
 def redistance_case():
     """Re-distancing fixture (oracle/redistance_oracle.c): a level-set function with a wobbly sphere-like zero set on an
     anisotropic 28 x 24 x 20 grid and its re-distanced field."""
@@ -67,7 +89,15 @@ if __name__ == '__main__':
         np.savez_compressed(os.path.join(HERE, 'redistance_wobbly.npz'), **redistance_case())
         print('wrote redistance_wobbly')
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'prb':
+        for name in PRB_CASES:
+            np.savez_compressed(os.path.join(HERE, name + '.npz'), **run_prb_case(name))
+            print('wrote', name)
+        sys.exit(0)
     np.savez_compressed(os.path.join(HERE, 'redistance_wobbly.npz'), **redistance_case())
+    for name in PRB_CASES:
+        np.savez_compressed(os.path.join(HERE, name + '.npz'), **run_prb_case(name))
+        print('wrote', name)
     for name in CASES:
         np.savez_compressed(os.path.join(HERE, name + '.npz'), **run_case(name))
         print('wrote', name)

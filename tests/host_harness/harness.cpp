@@ -18,6 +18,7 @@ struct hh_scene {
     sdfrt_sensor sensor;
     sdfrt_shading shading;
     int integrator;
+    sdfrt_prb_params prb;
 };
 
 static SceneParams build(const hh_scene* h) {
@@ -32,6 +33,7 @@ static SceneParams build(const hh_scene* h) {
     sc.S = make_sensor(h->sensor);
     sc.Sh = make_shading(h->shading);
     sc.integrator = h->integrator;
+    sc.prb = make_prb(h->prb);
     return sc;
 }
 
@@ -44,6 +46,7 @@ void hh_defaults(hh_scene* h) {
     sensor_defaults(&h->sensor);
     shading_defaults(&h->shading);
     h->integrator = INTEGRATOR_DIRECT;
+    prb_defaults(&h->prb);
 }
 
 int hh_eval_sdf(const hh_scene* h, const float* x, int n, int order, float* out) {
@@ -133,6 +136,71 @@ int hh_backward(const hh_scene* h, unsigned seed, int spp, const float* film, co
         SiteList sites;
         lane_backward(sc, ps, lane, adj.data(), rec + k, n, tg, gp, sites, st);
         for (int q = 0; q < sites.n; ++q) scatter_site(grad_sdf, sc.G, sites.s[q].x, sites.s[q].phi_hat, sites.s[q].g_hat);
+    }
+    if (grad_p) { grad_p[0] += gp.x; grad_p[1] += gp.y; grad_p[2] += gp.z; }
+    if (stats) { stats[0] = n; stats[3] = st.n_hess; stats[4] = st.n_sites; }
+    return 0;
+}
+
+// sdf_prb_reparam: primal sweep (film zeroed here; L_rec: 3 * n floats, may be null)
+int hh_prb_forward(const hh_scene* h, unsigned seed, int spp, float* film, float* L_rec, int rank, int world) {
+    SceneParams sc = build(h);
+    PassParams ps = make_pass(sc.S, seed, spp, rank, world);
+    const int Wb = sc.S.W + 2 * sc.S.border, Hb = sc.S.H + 2 * sc.S.border;
+    std::memset(film, 0, (size_t)Wb * Hb * 4 * sizeof(float));
+    LaneStats st = {0, 0, 0, 0, 0, 0, 0};
+    const unsigned long long n = ps.n_items;
+    for (unsigned long long k = 0; k < n; ++k) {
+        const WorkItem w = decode_item(ps, k);
+        NoEmit ne;
+        V3 gp = v3(0.f);
+        const V3 L = lane_prb<false>(sc, ps, w.lane, nullptr, v3(0.f), ne, gp, st);
+        if (L_rec) { L_rec[k] = L.x; L_rec[k + n] = L.y; L_rec[k + 2 * n] = L.z; }
+        Pcg32 rng = sampler_seed(ps.seed, (uint32_t)w.lane);
+        const float r0 = pcg_next_f32(rng), r1 = pcg_next_f32(rng);
+        const float pfx = (float)(w.px - sc.S.border) + r0 + ((float)sc.S.border - 0.5f);
+        const float pfy = (float)(w.py - sc.S.border) + r1 + ((float)sc.S.border - 0.5f);
+        const float rad = sc.S.filter_radius;
+        for (int by = (int)ceilf(pfy - rad); by <= (int)floorf(pfy + rad); ++by) {
+            if (by < 0 || by >= Hb) continue;
+            const float wy = filter_eval(sc.S, (float)by - pfy);
+            for (int bx = (int)ceilf(pfx - rad); bx <= (int)floorf(pfx + rad); ++bx) {
+                if (bx < 0 || bx >= Wb) continue;
+                const float wgt = wy * filter_eval(sc.S, (float)bx - pfx);
+                float* px = film + ((size_t)by * Wb + bx) * 4;
+                px[0] += L.x * wgt; px[1] += L.y * wgt; px[2] += L.z * wgt; px[3] += wgt;
+            }
+        }
+    }
+    return 0;
+}
+
+int hh_prb_backward(const hh_scene* h, unsigned seed, int spp, const float* film, const float* L_rec, const float* grad_image,
+                    float* grad_sdf, float* grad_albedo, float* grad_p, unsigned long long* stats, int rank, int world) {
+    SceneParams sc = build(h);
+    PassParams ps = make_pass(sc.S, seed, spp, rank, world);
+    const SensorParams& S = sc.S;
+    const int Wb = S.W + 2 * S.border, Hb = S.H + 2 * S.border;
+    std::vector<float> adj((size_t)Wb * Hb * 4, 0.f);
+    for (int by = 0; by < Hb; ++by)
+        for (int bx = 0; bx < Wb; ++bx) {
+            const int qx = bx - S.border, qy = by - S.border;
+            if (qx < 0 || qx >= S.W || qy < 0 || qy >= S.H) continue;
+            const float* a = film + ((size_t)by * Wb + bx) * 4;
+            const float* g = grad_image + ((size_t)qy * S.W + qx) * 3;
+            if (a[3] == 0.f) continue;
+            const float iw = 1.f / a[3];
+            float* o = adj.data() + ((size_t)by * Wb + bx) * 4;
+            o[0] = g[0] * iw; o[1] = g[1] * iw; o[2] = g[2] * iw;
+            o[3] = -(g[0] * a[0] + g[1] * a[1] + g[2] * a[2]) * iw * iw;
+        }
+    LaneStats st = {0, 0, 0, 0, 0, 0, 0};
+    V3 gp = v3(0.f);
+    const unsigned long long n = ps.n_items;
+    for (unsigned long long k = 0; k < n; ++k) {
+        const WorkItem w = decode_item(ps, k);
+        DirectEmit em{grad_sdf, grad_albedo, sc.G};
+        (void)lane_prb<true>(sc, ps, w.lane, adj.data(), V3{L_rec[k], L_rec[k + n], L_rec[k + 2 * n]}, em, gp, st);
     }
     if (grad_p) { grad_p[0] += gp.x; grad_p[1] += gp.y; grad_p[2] += gp.z; }
     if (stats) { stats[0] = n; stats[3] = st.n_hess; stats[4] = st.n_sites; }

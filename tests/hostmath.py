@@ -37,16 +37,20 @@ class ShadingParams(C.Structure):
                 ('hide_emitters', C.c_int32)]
 
 
+class PrbParams(C.Structure):
+    _fields_ = [('max_depth', C.c_int32), ('rr_depth', C.c_int32)]
+
+
 class HHScene(C.Structure):
     _fields_ = [('sdf', C.c_void_p), ('rx', C.c_int), ('ry', C.c_int), ('rz', C.c_int), ('p', C.c_float * 3),
                 ('albedo', C.c_void_p), ('ax', C.c_int), ('ay', C.c_int), ('az', C.c_int),
                 ('tracer', TracerParams), ('warp', WarpParams), ('sensor', SensorParams), ('shading', ShadingParams),
-                ('integrator', C.c_int)]
+                ('integrator', C.c_int), ('prb', PrbParams)]
 
 
 def build():
     srcs = [SRC] + [os.path.join(HERE, '..', 'differentiable-sdf-rendering_b200', 'csrc', f)
-                    for f in ('sdfrt_core.cuh', 'sdfrt_lane.cuh', 'sdfrt_params.h', 'sdfrt_grid.cuh')]
+                    for f in ('sdfrt_core.cuh', 'sdfrt_lane.cuh', 'sdfrt_prb.cuh', 'sdfrt_params.h', 'sdfrt_grid.cuh')]
     if os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(s) for s in srcs):
         return LIB
     subprocess.check_call(['g++', '-O2', '-std=c++17', '-fPIC', '-shared', '-x', 'c++', SRC, '-o', LIB])
@@ -141,4 +145,22 @@ class HostScene:
         stats = np.zeros(8, np.uint64)
         lib().hh_backward(C.byref(self.h), C.c_uint(seed), spp, fptr(film), fptr(rec), fptr(grad_image), fptr(g),
                           None if ga is None else fptr(ga), fptr(gp), fptr(stats), rank, world)
+        return g, ga, gp, stats
+
+    # ---- sdf_prb_reparam (integrator 3) ----
+    def prb_forward(self, seed, spp, rank=0, world=1):
+        film = np.zeros(self.film_shape, np.float32)
+        n = self.local_lanes(spp, rank, world)
+        L = np.zeros((3, max(n, 1)), np.float32)
+        lib().hh_prb_forward(C.byref(self.h), C.c_uint(seed), spp, fptr(film), fptr(L), rank, world)
+        return film, L
+
+    def prb_backward(self, seed, spp, film, L, grad_image, rank=0, world=1):
+        grad_image = np.ascontiguousarray(grad_image, dtype=np.float32)
+        g = np.zeros_like(self.sdf)
+        ga = None if self.albedo is None else np.zeros_like(self.albedo)
+        gp = np.zeros(3, np.float32)
+        stats = np.zeros(8, np.uint64)
+        lib().hh_prb_backward(C.byref(self.h), C.c_uint(seed), spp, fptr(film), fptr(L), fptr(grad_image), fptr(g),
+                              None if ga is None else fptr(ga), fptr(gp), fptr(stats), rank, world)
         return g, ga, gp, stats
