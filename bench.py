@@ -23,7 +23,10 @@ WORKLOADS = {
     'c2_blobs128_256x256_16spp': ('blobs', 128, None, 256, 256, 16, 4, 12),
     'c1_sphere64_128x128_4spp': ('sphere', 64, None, 128, 128, 4, 4, 6),
     'c4_blobs512_512x512_64spp': ('blobs', 512, None, 512, 512, 64, 4, 12),
+    # BASELINE configs[4] (sdf_prb_reparam, 2-bounce GI): secondary line, `python bench.py --workload c5_...`
+    'c5_prb_blobs256_512x512_128spp': ('blobs', 256, None, 512, 512, 128, 1, 12),
 }
+PRB_WORKLOADS = {'c5_prb_blobs256_512x512_128spp': dict(max_depth=3, rr_depth=5)}  # camera hit + 2 bounces
 METRIC = "primary+adjoint Mrays/s"
 # dram__bytes_read + dram__bytes_write of the k_march launches of ONE c3 step, from the committed ncu launch list
 # (segment arrays, lane records and the L2 misses of the row-expanded grid copy; before that copy: 5.6 GB,
@@ -392,9 +395,97 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+def run_gpu_prb(args):
+    """Secondary line: the path replay integrator in its first, one-thread-per-sample form.  Same step
+    structure and timing rules as the headline (primal + re-render in one call, then the replay/backprop), camera samples
+    counted as rays; no roofline claim yet -- the wavefront form on k_march is the next step."""
+    import torch
+    import torch.distributed as dist
+    import sdfrt
+    from sdfrt import synthetic as syn
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    kind, R, AR, W, H, spp, mult, nsens = WORKLOADS[args.workload]
+    ctx = sdfrt.Context(local)
+    sdf = syn.make_sdf_device(kind, R, dev)
+    sensor = sdfrt.get_regular_cameras(nsens, resx=W, resy=H)[0]
+    ctx.set_sdf(sdf)
+    ctx.set_albedo(None)
+    ctx.set_sensor(sensor.to_world, W, H)
+    ctx.set_shading()
+    ctx.set_integrator('sdf_prb_reparam')
+    ctx.set_prb(**PRB_WORKLOADS[args.workload])
+    ctx.set_warp()
+    ctx.set_partition(rank, world)
+    Hb, Wb, b = ctx.film_dims()
+    rays_per_step = Hb * Wb * spp * (mult + 1)
+    film_p, film_a = ctx.new_film(), ctx.new_film()
+    image = torch.empty((H, W, 3), device=dev)
+    grad_image = torch.ones((H, W, 3), device=dev)
+    grad_sdf = torch.zeros_like(sdf)
+    stream = torch.cuda.current_stream(dev)
+
+    def step(seed):
+        ctx.render_view(seed, spp * mult, seed + 1 + nsens, spp, film_p, film_a)
+        if world > 1:
+            dist.all_reduce(film_p)
+            dist.all_reduce(film_a)
+        ctx.develop(film_p, image)
+        grad_sdf.zero_()
+        ctx.adjoint_backprop(film_a, grad_image, grad_sdf)
+        if world > 1:
+            dist.all_reduce(grad_sdf)
+
+    for w in range(args.warmup):
+        step(w * (1 + nsens))
+    torch.cuda.synchronize(dev)
+    ctx.stats(reset=True)
+    if world > 1:
+        dist.barrier()
+    t0, t1, tm = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    with ClockSampler(local) as clk:
+        torch.cuda.synchronize(dev)
+        t0.record(stream)
+        for s in range(args.steps):
+            step(1000 + s * (1 + nsens))
+        t1.record(stream)
+        torch.cuda.synchronize(dev)
+    ms = t0.elapsed_time(t1)
+    tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms = tt.item()
+    stats = ctx.stats(reset=True)
+    if rank == 0:
+        evals = (stats['n_evals_value'] + stats['n_evals_grad'] + stats['n_evals_hess'] + stats['n_evals_adjoint']) / args.steps
+        line = {"metric": METRIC, "value": rays_per_step * args.steps / (ms * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": args.workload, "integrator": "sdf_prb_reparam", **PRB_WORKLOADS[args.workload], "sdf_res": R,
+                           "film": [W, H], "spp_primal": spp * mult, "spp_adjoint": spp, "rays_per_step": rays_per_step,
+                           "note": "camera samples counted as rays; every sample walks up to max_depth path segments plus "
+                                   "their shadow rays (see evals_per_step)"},
+                "clocks": clk.summary(), "gpu_launches": int(stats['n_launches']), "evals_per_step": evals,
+                "fetch_GBps": 256.0 * evals / (ms / args.steps * 1e-3) / 1e9,
+                "stats_per_step": {k: v / args.steps for k, v in stats.items()}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 if __name__ == '__main__':
     a = parse()
-    if a.impl == 'reference':
+    if a.impl == 'reference' and a.workload in PRB_WORKLOADS:
+        if int(os.environ.get('RANK', '0')) == 0:  # secondary workload: the compiled CPU port covers the direct integrator only
+            print(json.dumps({"impl": "reference", "unavailable": "no multi-threaded CPU port of sdf_prb_reparam yet (oracle: oracle/sdf_oracle.py sample_prb)"}))
+    elif a.impl == 'reference':
         run_reference(a)
+    elif a.workload in PRB_WORKLOADS:
+        run_gpu_prb(a)
     else:
         run_gpu(a)
