@@ -108,7 +108,8 @@ def cpu_sample(wl, n_primal, seed):
     from oracle import cpu_port
     kind, R, AR, W, H, spp, mult, nsens = WORKLOADS[wl]
     sdf, alb, tw = cpu_scene(wl)
-    r = cpu_port.time_sample(sdf, alb, tw, W, H, seed, spp * mult, spp, n_primal, max(spp, n_primal // mult))
+    r = cpu_port.time_sample(sdf, alb, tw, W, H, seed, spp * mult, spp, n_primal, max(spp, n_primal // mult),
+                             prb=PRB_WORKLOADS.get(wl))
     r['seconds'] = r['seconds_primal'] + r['seconds_adjoint']
     return r
 
@@ -480,10 +481,7 @@ def run_gpu_prb(args):
 
 if __name__ == '__main__':
     a = parse()
-    if a.impl == 'reference' and a.workload in PRB_WORKLOADS:
-        if int(os.environ.get('RANK', '0')) == 0:  # secondary workload: the compiled CPU port covers the direct integrator only
-            print(json.dumps({"impl": "reference", "unavailable": "no multi-threaded CPU port of sdf_prb_reparam yet (oracle: oracle/sdf_oracle.py sample_prb)"}))
-    elif a.impl == 'reference':
+    if a.impl == 'reference':
         run_reference(a)
     elif a.workload in PRB_WORKLOADS:
         run_gpu_prb(a)

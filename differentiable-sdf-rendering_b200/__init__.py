@@ -4,8 +4,8 @@ Python surface mirroring the reference plugins: shapes.Grid3d, warp.WarpField2D 
 integrators.sdf_{direct,silhouette,simple_shading}_reparam and a `render()` with the mi.render contract.
 All rendering runs in hand-written sm_100a CUDA kernels behind the C ABI of libsdfrt.so.
 """
-from . import (_capi, dist, engine, integrators, losses, optimizers, redistancing, regularizations, scene, shapes, synthetic,  # noqa: F401
-               variables, volio, warp)  # noqa: F401
+from . import (_capi, dist, engine, integrators, losses, optimizers, redistancing, regularizations, scene, shape_opt, shapes,  # noqa: F401
+               synthetic, variables, volio, warp)  # noqa: F401
 from ._capi import SdfrtError  # noqa: F401
 from .engine import Context  # noqa: F401
 from .render import render  # noqa: F401

@@ -86,7 +86,7 @@ SIGNATURES = {
     'sdfrt_trace_rays': (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.POINTER(RayOut), _P]),
     'sdfrt_eval_sdf': (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
     'sdfrt_redistance': (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), _P]),
-    'sdfrt_adam_step': (C.c_int, [_P, _P, _P, _P, _P, C.c_size_t, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int,
+    'sdfrt_adam_step': (C.c_int, [_P, _P, _P, _P, _P, C.c_size_t, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int,
                                   C.c_float, C.c_float, C.c_float, _P]),
     'sdfrt_laplacian_reg': (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_float, _P, _P, _P]),
     'sdfrt_render_view_host': (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_uint32, C.c_int,

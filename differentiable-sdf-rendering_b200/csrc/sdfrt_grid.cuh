@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(kRdThreads) k_rd_solve(float* __restrict__ u, 
 //   p   <- clamp(p, lo, hi)                                          python/variables.py:114-117 (lo > hi: off)
 // ---------------------------------------------------------------------------------------------------------------
 struct AdamParams {
-    float lr_t, beta1, beta2, eps, grad_clamp, lo, hi;
+    float lr_t, beta1, beta2, omb1, omb2, eps, grad_clamp, lo, hi;
 };
 __global__ void k_adam_step(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, size_t n, AdamParams a) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -292,8 +292,8 @@ __global__ void k_adam_step(float* __restrict__ p, float* __restrict__ g, float*
             gi = isnan(gi) ? 0.f : fminf(fmaxf(gi, -a.grad_clamp), a.grad_clamp);
             g[i] = gi;
         }
-        const float mi = a.beta1 * m[i] + (1.f - a.beta1) * gi;
-        const float vi = a.beta2 * v[i] + (1.f - a.beta2) * gi * gi;
+        const float mi = a.beta1 * m[i] + a.omb1 * gi;
+        const float vi = a.beta2 * v[i] + a.omb2 * gi * gi;
         m[i] = mi;
         v[i] = vi;
         float pi = fmaf(-a.lr_t, mi / (sqrtf(vi) + a.eps), p[i]);

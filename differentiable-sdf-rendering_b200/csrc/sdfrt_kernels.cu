@@ -1069,7 +1069,7 @@ int sdfrt_redistance(sdfrt_ctx* ctx, const float* phi, const float* lower_bound,
     return SDFRT_OK;
 }
 
-int sdfrt_adam_step(sdfrt_ctx* ctx, float* param, float* grad, float* m, float* v, size_t n, float lr, float beta1, float beta2, float eps,
+int sdfrt_adam_step(sdfrt_ctx* ctx, float* param, float* grad, float* m, float* v, size_t n, double lr, double beta1, double beta2, double eps,
                     int t, float grad_clamp, float lo, float hi, void* stream) {
     if (!ctx || !param || !grad || !m || !v) return SDFRT_ERR_INVALID;
     if (t < 1) return fail(ctx, SDFRT_ERR_INVALID, "Adam step count starts at 1");
@@ -1077,8 +1077,11 @@ int sdfrt_adam_step(sdfrt_ctx* ctx, float* param, float* grad, float* m, float* 
     SDFRT_CUDA(ctx, cudaSetDevice(ctx->device));
     AdamParams a;
     // lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t), evaluated in double like the reference's Python scalars
-    a.lr_t = (float)((double)lr * std::sqrt(1.0 - std::pow((double)beta2, (double)t)) / (1.0 - std::pow((double)beta1, (double)t)));
-    a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.grad_clamp = grad_clamp; a.lo = lo; a.hi = hi;
+    a.lr_t = (float)(lr * std::sqrt(1.0 - std::pow(beta2, (double)t)) / (1.0 - std::pow(beta1, (double)t)));
+    // the reference's hyper-parameters are Python (double) scalars that meet fp32 arrays one by one: beta and (1 - beta) are
+    // rounded to fp32 separately (1 - 0.999 -> 0.001f, not 1.f - 0.999f which is 1.3e-5 off)
+    a.beta1 = (float)beta1; a.beta2 = (float)beta2; a.omb1 = (float)(1.0 - beta1); a.omb2 = (float)(1.0 - beta2);
+    a.eps = (float)eps; a.grad_clamp = grad_clamp; a.lo = lo; a.hi = hi;
     const unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)ctx->num_sms * 16);
     k_adam_step<<<grid, 256, 0, (cudaStream_t)stream>>>(param, grad, m, v, n, a);
     SDFRT_CUDA(ctx, cudaGetLastError());

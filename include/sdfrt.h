@@ -200,9 +200,10 @@ int sdfrt_redistance(sdfrt_ctx* ctx, const float* phi, const float* lower_bound,
 /* mi.ad.Adam.step (python/shape_opt.py:53,102) for one parameter tensor of n floats with the reference's validation fused
  * in: gradient NaN scrub + clamp to [-grad_clamp, grad_clamp] (SdfVariable.validate_gradient, python/variables.py:193-199;
  * grad_clamp <= 0 disables it; the scrubbed gradient is written back) and value clamp to [lo, hi]
- * (VolumeVariable.validate, python/variables.py:114-117; lo > hi disables it).  t = 1-based step count of this tensor. */
-int sdfrt_adam_step(sdfrt_ctx* ctx, float* param, float* grad, float* m, float* v, size_t n, float lr, float beta1, float beta2,
-                    float eps, int t, float grad_clamp, float lo, float hi, void* stream);
+ * (VolumeVariable.validate, python/variables.py:114-117; lo > hi disables it).  t = 1-based step count of this tensor.
+ * The hyper-parameters are doubles like the reference's Python scalars (beta and 1 - beta are rounded to fp32 separately). */
+int sdfrt_adam_step(sdfrt_ctx* ctx, float* param, float* grad, float* m, float* v, size_t n, double lr, double beta1, double beta2,
+                    double eps, int t, float grad_clamp, float lo, float hi, void* stream);
 
 /* regularizations.eval_discrete_laplacian_reg (python/regularizations.py:5-25): *loss_out (device double, optional) +=
  * weight * sum_i (c_i - mean of the 6 clamped neighbours)^2, grad (optional) += weight * d(sum)/dc. */

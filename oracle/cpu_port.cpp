@@ -29,7 +29,29 @@ struct cp_scene {
     sdfrt_sensor sensor;
     sdfrt_shading shading;
     int integrator;
+    sdfrt_prb_params prb;   // used when integrator == INTEGRATOR_PRB
 };
+
+// per-sample film splat at the jittered pixel position (ImageBlock::put), atomics via SDFRT_ATOMIC_ADD
+static void splat_at(const SceneParams& sc, const PassParams& ps, const WorkItem& w, V3 rgb, float* film) {
+    Pcg32 rng = sampler_seed(ps.seed, (uint32_t)w.lane);
+    const float r0 = pcg_next_f32(rng), r1 = pcg_next_f32(rng);
+    const int b = sc.S.border, Wb = sc.S.W + 2 * b, Hb = sc.S.H + 2 * b;
+    const float pfx = (float)(w.px - b) + r0 + ((float)b - 0.5f), pfy = (float)(w.py - b) + r1 + ((float)b - 0.5f);
+    const float rad = sc.S.filter_radius;
+    for (int by = (int)ceilf(pfy - rad); by <= (int)floorf(pfy + rad); ++by) {
+        if (by < 0 || by >= Hb) continue;
+        const float wy = filter_eval(sc.S, (float)by - pfy);
+        for (int bx = (int)ceilf(pfx - rad); bx <= (int)floorf(pfx + rad); ++bx) {
+            if (bx < 0 || bx >= Wb) continue;
+            const float wgt = wy * filter_eval(sc.S, (float)bx - pfx);
+            if (wgt == 0.f) continue;
+            float* px = film + ((size_t)by * Wb + bx) * 4;
+            SDFRT_ATOMIC_ADD(px + 0, rgb.x * wgt); SDFRT_ATOMIC_ADD(px + 1, rgb.y * wgt); SDFRT_ATOMIC_ADD(px + 2, rgb.z * wgt);
+            SDFRT_ATOMIC_ADD(px + 3, wgt);
+        }
+    }
+}
 
 extern "C" {
 
@@ -37,6 +59,7 @@ void cp_defaults(cp_scene* h) {
     std::memset(h, 0, sizeof(*h));
     tracer_defaults(&h->tracer); warp_defaults(&h->warp); sensor_defaults(&h->sensor); shading_defaults(&h->shading);
     h->integrator = INTEGRATOR_DIRECT;
+    prb_defaults(&h->prb);
 }
 
 int cp_threads() { return omp_get_max_threads(); }
@@ -53,6 +76,8 @@ int cp_time_sample(const cp_scene* h, unsigned seed, int spp_primal, int spp_adj
     sc.A.cr = h->shading.albedo[0]; sc.A.cg = h->shading.albedo[1]; sc.A.cb = h->shading.albedo[2];
     sc.T = make_tracer(h->tracer); sc.W = make_warp(h->warp); sc.S = make_sensor(h->sensor); sc.Sh = make_shading(h->shading);
     sc.integrator = h->integrator;
+    sc.prb = make_prb(h->prb);
+    const bool prb = sc.integrator == INTEGRATOR_PRB;
     const size_t nf = (size_t)(sc.S.W + 2 * sc.S.border) * (sc.S.H + 2 * sc.S.border) * 4;
     std::vector<float> film(nf, 0.f), film_adj(nf, 0.f);
     double nv = 0, nh = 0;
@@ -64,7 +89,13 @@ int cp_time_sample(const cp_scene* h, unsigned seed, int spp_primal, int spp_adj
 #pragma omp parallel for schedule(dynamic, 512) reduction(+ : nv, nh)
     for (long long l = lo; l < lo + n_primal; ++l) {
         LaneStats st = {0, 0, 0, 0, 0, 0, 0};
-        lane_forward<false>(sc, pp, decode_item(pp, (unsigned long long)l).lane, film.data(), nullptr, 0, st);
+        if (prb) {
+            const WorkItem w = decode_item(pp, (unsigned long long)l);
+            NoEmit ne; V3 gp = v3(0.f);
+            splat_at(sc, pp, w, lane_prb<false>(sc, pp, w.lane, nullptr, v3(0.f), ne, gp, st), film.data());
+        } else {
+            lane_forward<false>(sc, pp, decode_item(pp, (unsigned long long)l).lane, film.data(), nullptr, 0, st);
+        }
         nv += st.n_value; nh += st.n_hess;
     }
     auto t1 = std::chrono::steady_clock::now();
@@ -78,7 +109,16 @@ int cp_time_sample(const cp_scene* h, unsigned seed, int spp_primal, int spp_adj
 #pragma omp parallel for schedule(dynamic, 512) reduction(+ : nv, nh)
     for (long long l = la; l < la + n_adjoint; ++l) {
         LaneStats st = {0, 0, 0, 0, 0, 0, 0};
-        lane_forward<true>(sc, sub, decode_item(sub, (unsigned long long)l).lane, film.data(), rec.data() + (l - la), (unsigned long long)n_adjoint, st);
+        if (prb) {  // re-render of render_backward: keeps L per sample (rows 0..2 of the records)
+            const WorkItem w = decode_item(sub, (unsigned long long)l);
+            NoEmit ne; V3 gp = v3(0.f);
+            const V3 L = lane_prb<false>(sc, sub, w.lane, nullptr, v3(0.f), ne, gp, st);
+            float* r = rec.data() + (l - la);
+            r[0] = L.x; r[n_adjoint] = L.y; r[2 * n_adjoint] = L.z;
+            splat_at(sc, sub, w, L, film.data());
+        } else {
+            lane_forward<true>(sc, sub, decode_item(sub, (unsigned long long)l).lane, film.data(), rec.data() + (l - la), (unsigned long long)n_adjoint, st);
+        }
         nv += st.n_value; nh += st.n_hess;
     }
     const int Wb = sc.S.W + 2 * sc.S.border, Hb = sc.S.H + 2 * sc.S.border;
@@ -95,6 +135,13 @@ int cp_time_sample(const cp_scene* h, unsigned seed, int spp_primal, int spp_adj
     for (long long l = la; l < la + n_adjoint; ++l) {
         LaneStats st = {0, 0, 0, 0, 0, 0, 0};
         V3 gp = v3(0.f);
+        if (prb) {
+            const float* r = rec.data() + (l - la);
+            DirectEmit em{grad_sdf, nullptr, sc.G};
+            (void)lane_prb<true>(sc, sub, decode_item(sub, (unsigned long long)l).lane, film_adj.data(), V3{r[0], r[n_adjoint], r[2 * n_adjoint]}, em, gp, st);
+            nh += st.n_hess;
+            continue;
+        }
         SiteList sites;
         lane_backward(sc, sub, decode_item(sub, (unsigned long long)l).lane, film_adj.data(), rec.data() + (l - la), (unsigned long long)n_adjoint, tg, gp, sites, st);
         for (int q = 0; q < sites.n; ++q) scatter_site(grad_sdf, sc.G, sites.s[q].x, sites.s[q].phi_hat, sites.s[q].g_hat);

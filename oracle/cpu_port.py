@@ -14,26 +14,26 @@ LIB = os.path.join(HERE, 'libsdfrt_cpu_port.so')
 FLAGS = ['-O3', '-march=x86-64-v3', '-fopenmp', '-std=c++17', '-fPIC', '-shared', '-x', 'c++']
 
 sys.path.insert(0, os.path.join(ROOT, 'tests'))
-from hostmath import SensorParams, ShadingParams, TracerParams, WarpParams  # noqa: E402  (same public structs)
+from hostmath import PrbParams, SensorParams, ShadingParams, TracerParams, WarpParams  # noqa: E402  (same public structs)
 
 
 class CPScene(C.Structure):
     _fields_ = [('sdf', C.c_void_p), ('rx', C.c_int), ('ry', C.c_int), ('rz', C.c_int),
                 ('albedo', C.c_void_p), ('ax', C.c_int), ('ay', C.c_int), ('az', C.c_int),
                 ('tracer', TracerParams), ('warp', WarpParams), ('sensor', SensorParams), ('shading', ShadingParams),
-                ('integrator', C.c_int)]
+                ('integrator', C.c_int), ('prb', PrbParams)]
 
 
 def build():
     deps = [SRC] + [os.path.join(ROOT, 'differentiable-sdf-rendering_b200', 'csrc', f)
-                    for f in ('sdfrt_core.cuh', 'sdfrt_lane.cuh', 'sdfrt_params.h')]
+                    for f in ('sdfrt_core.cuh', 'sdfrt_lane.cuh', 'sdfrt_prb.cuh', 'sdfrt_params.h')]
     if os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in deps):
         return LIB
     subprocess.check_call(['g++'] + FLAGS + [SRC, '-o', LIB])
     return LIB
 
 
-def time_sample(sdf, albedo, to_world, W, H, seed, spp_primal, spp_adjoint, n_primal, n_adjoint):
+def time_sample(sdf, albedo, to_world, W, H, seed, spp_primal, spp_adjoint, n_primal, n_adjoint, prb=None):
     """Returns dict(seconds_primal, seconds_adjoint, rays, threads)."""
     lib = C.CDLL(build())
     sc = CPScene()
@@ -47,6 +47,9 @@ def time_sample(sdf, albedo, to_world, W, H, seed, spp_primal, spp_adjoint, n_pr
         sc.az, sc.ay, sc.ax = albedo.shape[:3]
     sc.sensor.to_world[:] = [float(v) for v in np.asarray(to_world, dtype=np.float64).reshape(-1)]
     sc.sensor.width, sc.sensor.height = W, H
+    if prb is not None:  # sdf_prb_reparam: dict(max_depth, rr_depth)
+        sc.integrator = 3
+        sc.prb.max_depth, sc.prb.rr_depth = prb['max_depth'], prb['rr_depth']
     grad = np.zeros_like(sdf)
     out = np.zeros(4, dtype=np.float64)
     lib.cp_time_sample(C.byref(sc), C.c_uint(seed), spp_primal, spp_adjoint, C.c_longlong(n_primal), C.c_longlong(n_adjoint),

@@ -125,7 +125,7 @@ def test_adam_step_matches_restatement(ctx, variant):
         assert np.abs(m.cpu().numpy() - mr).max() <= 1e-6 * max(1.0, np.abs(mr).max())
         assert np.abs(v.cpu().numpy() - vr).max() <= 1e-6 * max(1e-6, np.abs(vr).max())
     if variant == 'reflectance':
-        assert float(p.min()) >= 1e-5 and float(p.max()) <= 1.0
+        assert float(p.min()) >= float(np.float32(1e-5)) and float(p.max()) <= 1.0
 
 
 def test_laplacian_regulariser_value_and_gradient(ctx, sdfrt_mod):
