@@ -14,6 +14,7 @@
 #ifndef SDFRT_H
 #define SDFRT_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus

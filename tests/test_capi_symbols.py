@@ -71,3 +71,20 @@ def test_facade_mirrors_reference_defaults():
     assert np.allclose(cams[0].to_world, O.look_at(O.regular_camera_origins(6)[0], [0.5, 0.5, 0.5], [0, 1, 0]))
     a = sdfrt.synthetic.make_sdf('blobs', 16)
     assert np.array_equal(a, O.make_sdf('blobs', 16))
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/sdfrt.h compiles as C99 (no C++-isms, no torch / CUDA types in the signatures) and a C caller links against
+    the library's symbols -- the binding a maintainer of a C host would write."""
+    import subprocess
+    src = tmp_path / 'probe.c'
+    src.write_text(
+        '#include "sdfrt.h"\n'
+        'int probe(void) {\n'
+        '    sdfrt_tracer_params t; sdfrt_warp_params w; sdfrt_sensor s; sdfrt_shading sh; sdfrt_prb_params p;\n'
+        '    sdfrt_tracer_defaults(&t); sdfrt_warp_defaults(&w); sdfrt_sensor_defaults(&s); sdfrt_shading_defaults(&sh);\n'
+        '    sdfrt_prb_defaults(&p);\n'
+        '    return sdfrt_version() + p.max_depth + (int)sizeof(sdfrt_stats) + (int)sizeof(sdfrt_ray_out);\n'
+        '}\n')
+    subprocess.check_call(['gcc', '-std=c99', '-pedantic', '-Wall', '-Werror', '-I', os.path.join(ROOT, 'include'), '-c', str(src),
+                           '-o', str(tmp_path / 'probe.o')])

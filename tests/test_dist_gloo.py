@@ -18,29 +18,37 @@ W, SPP, R = 20, 4, 24
 class HostBackend:
     """engine.Context's rendering interface on top of hostmath.HostScene."""
 
-    def __init__(self):
+    def __init__(self, prb=False):
         import hostmath as HM
         from oracle import sdf_oracle as O
         osc = O.make_scene('knot', res=R, width=W, height=W)
-        self.hs = HM.HostScene(osc.sdf.data.numpy(), osc.sensor.to_world, W, W, integrator=2)
+        self.prb = prb
+        self.hs = HM.HostScene(osc.sdf.data.numpy(), osc.sensor.to_world, W, W, integrator=3 if prb else 2)
+        self.hs.h.prb.max_depth = 3
         self.rank, self.world = 0, 1
 
     def set_partition(self, rank, world):
         self.rank, self.world = rank, world
 
     def render_primal(self, seed, spp):
+        if self.prb:
+            return torch.from_numpy(self.hs.prb_forward(seed, spp, self.rank, self.world)[0])
         return torch.from_numpy(self.hs.forward(seed, spp, False, self.rank, self.world)[0])
 
     def develop(self, film):
         return torch.from_numpy(self.hs.develop(film.numpy()))
 
     def adjoint_accumulate(self, seed, spp):
-        film, self.rec, _ = self.hs.forward(seed, spp, True, self.rank, self.world)
+        if self.prb:
+            film, self.rec = self.hs.prb_forward(seed, spp, self.rank, self.world)
+        else:
+            film, self.rec, _ = self.hs.forward(seed, spp, True, self.rank, self.world)
         self.adj = (seed, spp)
         return torch.from_numpy(film)
 
     def adjoint_backprop(self, film, grad_image, grad_sdf, grad_albedo=None):
-        g, _, _, _ = self.hs.backward(self.adj[0], self.adj[1], film.numpy(), self.rec, grad_image.numpy(), self.rank, self.world)
+        fn = self.hs.prb_backward if self.prb else self.hs.backward
+        g, _, _, _ = fn(self.adj[0], self.adj[1], film.numpy(), self.rec, grad_image.numpy(), self.rank, self.world)
         grad_sdf += torch.from_numpy(g)
 
 
@@ -48,14 +56,14 @@ def _loss_grad(image):
     return torch.sign(image - 0.5) / image.numel()      # d/dI of mean |I - 0.5|
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, prb=False):
     for p in (ROOT, os.path.join(ROOT, 'tests')):
         sys.path.insert(0, p)
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
     dist.init_process_group('gloo', rank=rank, world_size=world)
     import sdfrt
-    be = HostBackend()
+    be = HostBackend(prb)
     g = torch.zeros(R, R, R)
     img = sdfrt.dist.render_view(be, 3, SPP * 4, 3 + 1 + 6, SPP, _loss_grad, g)
     if rank == 0:
@@ -63,16 +71,17 @@ def _worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
-def test_two_rank_view_matches_single_rank(tmp_path, built):
+@pytest.mark.parametrize('prb', [False, True], ids=['sdf_direct_reparam', 'sdf_prb_reparam'])
+def test_two_rank_view_matches_single_rank(tmp_path, built, prb):
     import sdfrt
-    be = HostBackend()
+    be = HostBackend(prb)
     g1 = torch.zeros(R, R, R)
     img1 = sdfrt.dist.render_view(be, 3, SPP * 4, 3 + 1 + 6, SPP, _loss_grad, g1)   # no process group: world 1
     with socket.socket() as s:
         s.bind(('127.0.0.1', 0))
         port = s.getsockname()[1]
     out = str(tmp_path / 'r0.npz')
-    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, out, prb), nprocs=2, join=True)
     r = np.load(out)
     assert np.abs(r['image'] - img1.numpy()).max() < 1e-5
     assert np.abs(r['grad'] - g1.numpy()).max() < 1e-4 * np.abs(g1.numpy()).max()
