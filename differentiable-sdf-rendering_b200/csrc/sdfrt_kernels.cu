@@ -239,7 +239,8 @@ __global__ void __launch_bounds__(kBlock) k_prb_primal(const __grid_constant__ S
     }
 }
 
-__global__ void __launch_bounds__(kBlock) k_prb_backward(const __grid_constant__ SceneParams sc, const __grid_constant__ PassParams ps,
+template <int MIN_BLOCKS>  // resident blocks per SM the register allocation is tuned for (2: 255 registers, 3: 168)
+__global__ void __launch_bounds__(kBlock, MIN_BLOCKS) k_prb_backward(const __grid_constant__ SceneParams sc, const __grid_constant__ PassParams ps,
                                                           const float* __restrict__ film_adj, const float* __restrict__ L_rec,
                                                           unsigned long long rec_stride, BackwardTargets tg, float* grad_p, Counters* counters) {
     const int lane_id = threadIdx.x & 31;
@@ -333,6 +334,7 @@ struct sdfrt_ctx {
     size_t rows4_n = 0;
     int rows4_roles = -1, march_role = 0;
     bool rows4_on = false;
+    int prb_min_blocks = 2;                  // register-allocation variant of k_prb_backward (SDFRT_PRB_OCC)
     int cache_mode[4] = {1, 1, 0, 1};        // tap-cache mode of [value primary, value shadow, diff primary, diff shadow]
     // buffers of the host entry point
     float *h_sdf = nullptr, *h_film = nullptr, *h_film2 = nullptr, *h_image = nullptr, *h_gimg = nullptr, *h_grad = nullptr;
@@ -689,6 +691,7 @@ sdfrt_ctx* sdfrt_create(int device, int* status) {
     if (const char* e = std::getenv("SDFRT_ROWS4")) ctx->rows4_roles = std::atoi(e) & 15;   // developer override: 0 = off, else role mask
     if (const char* e = std::getenv("SDFRT_SLOTS")) ctx->max_slots = std::max(1, std::min(kSlots, std::atoi(e)));          // developer overrides
     if (const char* e = std::getenv("SDFRT_MIN_LIVE")) ctx->min_live = std::max(1, std::min(32, std::atoi(e)));
+    if (const char* e = std::getenv("SDFRT_PRB_OCC")) ctx->prb_min_blocks = std::atoi(e);
     if (const char* e = std::getenv("SDFRT_SKIP_EMPTY")) ctx->skip_empty = std::atoi(e) != 0;
     if (const char* e = std::getenv("SDFRT_BATCH_LOG2")) ctx->batch_target = 1ull << std::max(16, std::min(28, std::atoi(e)));
     for (int i = 0; i < kSlots; ++i) {
@@ -936,7 +939,10 @@ int sdfrt_adjoint_backprop(sdfrt_ctx* ctx, const float* film_accum, const float*
     const unsigned long long blocks = (n + kBlock - 1) / kBlock;
     if (ctx->sc.integrator == INTEGRATOR_PRB) {
         LaunchScope ls(ctx, 6, st);
-        k_prb_backward<<<(unsigned)blocks, kBlock, 0, st>>>(ctx->sc, ps, ctx->film_adj, ctx->rec, ctx->rec_stride, tg, grad_p, ctx->counters);
+        if (ctx->prb_min_blocks >= 3)
+            k_prb_backward<3><<<(unsigned)blocks, kBlock, 0, st>>>(ctx->sc, ps, ctx->film_adj, ctx->rec, ctx->rec_stride, tg, grad_p, ctx->counters);
+        else
+            k_prb_backward<2><<<(unsigned)blocks, kBlock, 0, st>>>(ctx->sc, ps, ctx->film_adj, ctx->rec, ctx->rec_stride, tg, grad_p, ctx->counters);
     } else {
         LaunchScope ls(ctx, 6, st);
         k_backward<<<(unsigned)blocks, kBlock, 0, st>>>(ctx->sc, ps, ctx->film_adj, ctx->rec, ctx->rec_stride, tg, grad_p, ctx->counters);

@@ -25,6 +25,52 @@ namespace sdfrt {
 
 constexpr float kInv4Pi = 0.07957747154594767f;
 
+// The path walker marches up to three kinds of segment per vertex and evaluates up to three warp sites.  Inlining every
+// call site made k_prb_backward instruction-fetch bound (ncu: `no_instruction` 5.6 stall cycles per issued instruction, 255
+// registers; profiles/r1_prb_per_lane.md), so the three heavy routines are real calls here, one copy each.
+#if defined(__CUDACC__)
+#define SDFRT_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define SDFRT_HD_NOINLINE __attribute__((noinline))
+#endif
+struct ValueTrace {
+    float its_t;
+    int n_steps, n_evals;
+};
+SDFRT_HD_NOINLINE ValueTrace prb_trace_value(const GridView& G, const TracerParams& T, V3 o, V3 d, float ray_maxt, bool do_refine) {
+    ValueTrace r;
+    r.n_steps = 0; r.n_evals = 0;
+    r.its_t = trace_non_diff(G, T, o, d, ray_maxt, do_refine, r.n_steps, r.n_evals);
+    return r;
+}
+struct DiffTrace {
+    TraceOut out;
+    int n_hess, n_value;
+};
+SDFRT_HD_NOINLINE DiffTrace prb_trace_diff(const GridView& G, const TracerParams& T, V3 o, V3 d, float ray_maxt) {
+    DiffTrace r;
+    r.n_hess = 0; r.n_value = 0;
+    r.out.warp_t = INFINITY; r.out.warp_t_d = v3(0.f); r.out.warp_weight = 0.f; r.out.warp_weight_d = v3(0.f);
+    trace_diff(G, T, o, d, ray_maxt, false, r.out, r.n_hess, r.n_value);
+    return r;
+}
+struct Lookup2 {
+    float phi;
+    V3 g;
+    S3 H;
+};
+SDFRT_HD_NOINLINE Lookup2 prb_eval2(const GridView& G, V3 x) {
+    Lookup2 r;
+    eval_sdf<2>(G, x, r.phi, r.g, r.H);
+    return r;
+}
+SDFRT_HD_NOINLINE void prb_scatter_site(float* grad, const GridView& G, V3 x, float phi_hat, V3 g_hat) {
+    scatter_site(grad, G, x, phi_hat, g_hat);
+}
+SDFRT_HD_NOINLINE WarpSite prb_warp_site(const GridView& G, const WarpParams& W, const TracerParams& T, V3 o, V3 d0, const TraceOut& tr) {
+    return warp_site(G, W, T, o, d0, tr.warp_t, tr.warp_t_d, tr.warp_weight, tr.warp_weight_d);
+}
+
 // mitsuba `coordinate_system` (Duff et al. 2017) -- the frame initialize_sh_frame builds when dp_du == 0
 // (python/shapes.py:360); s = first vector, t = cross(n, s).  oracle/ref_semantics.md S14
 SDFRT_HD void sh_frame(V3 n, V3& s, V3& t) {
@@ -103,7 +149,11 @@ SDFRT_HD V3 lane_prb(const SceneParams& sc, const PassParams& ps, unsigned long 
     int nv = 0, nh = 0, nsteps = 0;
 
     V3 o_cur = cs.o, d_cur = cs.d;
-    float t_cur = trace_non_diff(G, T, o_cur, d_cur, cs.maxt, true, nsteps, nv);  // ray_intersect_preliminary (:264)
+    float t_cur;
+    {   // ray_intersect_preliminary (:264)
+        const ValueTrace vt = prb_trace_value(G, T, o_cur, d_cur, cs.maxt, true);
+        t_cur = vt.its_t; nsteps = vt.n_steps; nv += vt.n_evals;
+    }
     st.n_hit += isfinite(t_cur);
     V3 L = BWD ? L_total : v3(0.f);
     V3 beta = v3(1.f);
@@ -118,7 +168,10 @@ SDFRT_HD V3 lane_prb(const SceneParams& sc, const PassParams& ps, unsigned long 
     TraceOut tr0;
     tr0.warp_t = INFINITY; tr0.warp_t_d = v3(0.f); tr0.warp_weight = 0.f; tr0.warp_weight_d = v3(0.f);
     if (BWD) {
-        if (warp2d) trace_diff(G, T, o_cur, d_cur, cs.maxt, false, tr0, nh, nv);  // sample_rays with reparam (:499-511)
+        if (warp2d) {  // sample_rays with reparam (:499-511)
+            const DiffTrace dt = prb_trace_diff(G, T, o_cur, d_cur, cs.maxt);
+            tr0 = dt.out; nh += dt.n_hess; nv += dt.n_value;
+        }
         // a sample that escapes and has no valid primary warp carries no derivative at all
         if (!isfinite(t_cur) && !isfinite(tr0.warp_t)) {
             st.n_value += nv; st.n_hess += nh;
@@ -156,8 +209,9 @@ SDFRT_HD V3 lane_prb(const SceneParams& sc, const PassParams& ps, unsigned long 
         WarpSite wseg;
         wseg.active = false;
         if (grad_here && !first && warp2d) {
-            trace_diff(G, T, o_cur, d_cur, INFINITY, false, trs, nh, nv);  // o_cur == si_prev.spawn_ray(ray_cur.d).o
-            wseg = warp_site(G, W, T, o_cur, d_cur, trs.warp_t, trs.warp_t_d, trs.warp_weight, trs.warp_weight_d);
+            const DiffTrace dt = prb_trace_diff(G, T, o_cur, d_cur, INFINITY);  // o_cur == si_prev.spawn_ray(ray_cur.d).o
+            trs = dt.out; nh += dt.n_hess; nv += dt.n_value;
+            wseg = prb_warp_site(G, W, T, o_cur, d_cur, trs);
             nh += isfinite(trs.warp_t);
         }
 
@@ -183,7 +237,7 @@ SDFRT_HD V3 lane_prb(const SceneParams& sc, const PassParams& ps, unsigned long 
             float phi;
             eval_sdf<1>(G, p, phi, g_p, H_p);  // the replay takes the normal from the same lookup as the primal pass
             st.n_grad += 1;
-            if (grad_here) { float phi2; V3 g2; eval_sdf<2>(G, p, phi2, g2, H_p); nh += 1; }
+            if (grad_here) { H_p = prb_eval2(G, p).H; nh += 1; }
             n = normalize(g_p);
             cos_i = -dot(n, d_cur);
             if (active_next) {
@@ -192,15 +246,18 @@ SDFRT_HD V3 lane_prb(const SceneParams& sc, const PassParams& ps, unsigned long 
                 sr = make_shadow_ray(sc.Sh, p, n, u_em0, u_em1);  // si_cur.spawn_ray_to(ds.p), d detached (:316-317)
                 cos_o = dot(n, sr.d);
                 if ((cos_i > 0.f) & (cos_o > 0.f)) {  // a closed BSDF gate contributes exactly zero: not marched
-                    int ns = 0;
-                    const float its_s = trace_non_diff(G, T, sr.o, sr.d, sr.maxt, false, ns, nv);
-                    if (!isfinite(its_s)) {
+                    const ValueTrace vs = prb_trace_value(G, T, sr.o, sr.d, sr.maxt, false);
+                    nv += vs.n_evals;
+                    if (!isfinite(vs.its_t)) {
                         nee = true;
                         mis_direct = mis_weight(kInv4Pi, cos_o * (1.f / kPi));
                         const float k = 4.f * cos_o * mis_direct;  // (rho / pi) cos_o * Le / (1 / 4 pi) * mis
                         Lr_dir = k * (beta * rho * Le_env);
                         // the shadow ray's warp record is only needed where it is reparameterised (static depth 1, :321)
-                        if (grad_here && reparam_at_depth(W, 1)) trace_diff(G, T, sr.o, sr.d, sr.maxt, false, ts, nh, nv);
+                        if (grad_here && reparam_at_depth(W, 1)) {
+                            const DiffTrace dt = prb_trace_diff(G, T, sr.o, sr.d, sr.maxt);
+                            ts = dt.out; nh += dt.n_hess; nv += dt.n_value;
+                        }
                     }
                 }
                 // BSDF sampling (:335-338): cosine hemisphere
@@ -229,9 +286,9 @@ SDFRT_HD V3 lane_prb(const SceneParams& sc, const PassParams& ps, unsigned long 
         // ---- next surface and the MIS weight of hitting the emitter by BSDF sampling (:351-363) ---------------
         float t_next = INFINITY;
         if (active_next) {
-            int ns = 0;
-            t_next = trace_non_diff(G, T, o_next, wo_w, INFINITY, true, ns, nv);
-            nsteps = nsteps > ns ? nsteps : ns;
+            const ValueTrace vn = prb_trace_value(G, T, o_next, wo_w, INFINITY, true);
+            t_next = vn.its_t; nv += vn.n_evals;
+            nsteps = nsteps > vn.n_steps ? nsteps : vn.n_steps;
         }
         const float mis_em_new = mis_weight(bs_pdf, isfinite(t_next) ? 0.f : kInv4Pi);
 
@@ -250,7 +307,7 @@ SDFRT_HD V3 lane_prb(const SceneParams& sc, const PassParams& ps, unsigned long 
                     const float det_s_hat = dot(dL, Lr_dir);
                     rho_hat += cos_o * a;
                     if (reparam_at_depth(W, 1)) {
-                        const WarpSite ws = warp_site(G, W, T, sr.o, sr.d, ts.warp_t, ts.warp_t_d, ts.warp_weight, ts.warp_weight_d);
+                        const WarpSite ws = prb_warp_site(G, W, T, sr.o, sr.d, ts);
                         nh += isfinite(ts.warp_t);
                         if (ws.active) {
                             const float phi_hat = det_s_hat * ws.cphi_div + dot(ds_hat, ws.cphi_dir);
@@ -307,7 +364,7 @@ SDFRT_HD V3 lane_prb(const SceneParams& sc, const PassParams& ps, unsigned long 
             }
             if (first) {
                 if (warp2d) {  // the primary warp site collects the film's and the first vertex' direction adjoints
-                    const WarpSite ws = warp_site(G, W, T, cs.o, cs.d, tr0.warp_t, tr0.warp_t_d, tr0.warp_weight, tr0.warp_weight_d);
+                    const WarpSite ws = prb_warp_site(G, W, T, cs.o, cs.d, tr0);
                     nh += isfinite(tr0.warp_t);
                     if (ws.active) {
                         const float phi_hat = det_hat0 * ws.cphi_div + dot(d_hat0 + d_hat, ws.cphi_dir);
@@ -361,7 +418,7 @@ struct DirectEmit {
     float* grad_sdf;
     float* grad_albedo;
     GridView G;
-    SDFRT_HD void site(V3 x, float phi_hat, V3 g_hat) { scatter_site(grad_sdf, G, x, phi_hat, g_hat); }
+    SDFRT_HD void site(V3 x, float phi_hat, V3 g_hat) { prb_scatter_site(grad_sdf, G, x, phi_hat, g_hat); }
     SDFRT_HD void albedo(const AlbedoTaps& taps, V3 rho_hat) {
         if (grad_albedo == nullptr) return;
         for (int k = 0; k < 8; ++k) {
