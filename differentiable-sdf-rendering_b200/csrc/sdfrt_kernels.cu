@@ -224,8 +224,9 @@ __global__ void __launch_bounds__(kBlock) k_prb_primal(const __grid_constant__ S
         // sample position of the splat: the (un-reparameterised) jittered pixel position re-projected (render(), :54-76)
         Pcg32 rng = sampler_seed(ps.seed, (uint32_t)w.lane);
         const float r0 = pcg_next_f32(rng), r1 = pcg_next_f32(rng);
-        pfx = (float)(w.px - sc.S.border) + r0 + ((float)sc.S.border - 0.5f);
-        pfy = (float)(w.py - sc.S.border) + r1 + ((float)sc.S.border - 0.5f);
+        const bool anti = (w.lane & kAntiBit) != 0ull;
+        pfx = sample_position(w.px - sc.S.border, r0, anti) + ((float)sc.S.border - 0.5f);
+        pfy = sample_position(w.py - sc.S.border, r1, anti) + ((float)sc.S.border - 0.5f);
     }
     warp_splat(sc.S, film, s_splat[threadIdx.x >> 5], valid, pfx, pfy, L);
     const unsigned nvv = warp_sum(st.n_value), ng = warp_sum(st.n_grad), al = warp_sum(st.n_albedo), hits = warp_sum(st.n_hit);
@@ -289,6 +290,7 @@ struct sdfrt_ctx {
     sdfrt_shading shading_pub;
     sdfrt_prb_params prb_pub;
     int rank = 0, world = 1;
+    int antithetic = 0;  // ReparamIntegrator.antithetic_sampling (python/integrators/reparam.py:19); not used by sdf_prb_reparam
     bool have_sdf = false;
     // adjoint state
     float* rec = nullptr;
@@ -507,7 +509,7 @@ int run_sweeps(sdfrt_ctx* ctx, Sweep* sweeps, int ns, cudaStream_t st) {
         sw.B = 0;
         const unsigned long long n = sw.ps.n_items;
         if (n == 0) continue;
-        if ((unsigned long long)kBandRows * (unsigned long long)(S.W + 2 * S.border) * (unsigned long long)sw.ps.spp > 0xffffffffull)
+        if ((unsigned long long)kBandRows * (unsigned long long)(S.W + 2 * S.border) * (unsigned long long)sw.ps.spp * (1ull + sw.ps.antithetic) > 0xffffffffull)
             return fail(ctx, SDFRT_ERR_INVALID, "film row band exceeds 2^32 samples");
         unsigned long long target = ctx->batch_target;
         if (target == 0) target = std::max<unsigned long long>(1ull << 20, std::min<unsigned long long>(1ull << 24, n / 6));
@@ -810,6 +812,13 @@ int sdfrt_set_integrator(sdfrt_ctx* ctx, int integrator) {
     return SDFRT_OK;
 }
 
+int sdfrt_set_antithetic(sdfrt_ctx* ctx, int enable) {
+    if (!ctx) return SDFRT_ERR_INVALID;
+    ctx->antithetic = enable ? 1 : 0;
+    ctx->adj_ready = false;
+    return SDFRT_OK;
+}
+
 int sdfrt_set_prb(sdfrt_ctx* ctx, const sdfrt_prb_params* p) {
     if (!ctx || !p) return SDFRT_ERR_INVALID;
     if (p->max_depth < 1 || p->max_depth > 1024 || p->rr_depth < 0) return fail(ctx, SDFRT_ERR_INVALID, "bad PRB parameters (need 1 <= max_depth <= 1024, rr_depth >= 0)");
@@ -851,7 +860,7 @@ int sdfrt_render_primal(sdfrt_ctx* ctx, uint32_t seed, int spp, float* film_accu
         return run_prb_sweep(ctx, make_pass(ctx->sc.S, seed, spp, ctx->rank, ctx->world), film_accum, nullptr, 0, (cudaStream_t)stream);
     Sweep sw;
     sw.diff = false;
-    sw.ps = make_pass(ctx->sc.S, seed, spp, ctx->rank, ctx->world);
+    sw.ps = make_pass(ctx->sc.S, seed, spp, ctx->rank, ctx->world, ctx->antithetic);
     sw.film = film_accum;
     return run_sweeps(ctx, &sw, 1, (cudaStream_t)stream);
 }
@@ -873,7 +882,7 @@ int sdfrt_adjoint_accumulate(sdfrt_ctx* ctx, uint32_t seed_grad, int spp_grad, f
     SDFRT_CUDA(ctx, cudaSetDevice(ctx->device));
     Sweep sw;
     sw.diff = true;
-    sw.ps = make_pass(ctx->sc.S, seed_grad, spp_grad, ctx->rank, ctx->world);
+    sw.ps = make_pass(ctx->sc.S, seed_grad, spp_grad, ctx->rank, ctx->world, ctx->sc.integrator == INTEGRATOR_PRB ? 0 : ctx->antithetic);
     sw.film = film_accum;
     rc = ensure(ctx, &ctx->rec, &ctx->rec_capacity, (size_t)sw.ps.n_items * REC_COUNT + 1);
     if (rc) return rc;
@@ -897,10 +906,11 @@ int sdfrt_render_view(sdfrt_ctx* ctx, uint32_t seed, int spp, float* film_primal
     SDFRT_CUDA(ctx, cudaSetDevice(ctx->device));
     Sweep sw[2];
     sw[0].diff = false;
-    sw[0].ps = make_pass(ctx->sc.S, seed, spp, ctx->rank, ctx->world);
+    const int anti = ctx->sc.integrator == INTEGRATOR_PRB ? 0 : ctx->antithetic;  // sdf_prb_reparam.sample_rays has no antithetic mode
+    sw[0].ps = make_pass(ctx->sc.S, seed, spp, ctx->rank, ctx->world, anti);
     sw[0].film = film_primal;
     sw[1].diff = true;
-    sw[1].ps = make_pass(ctx->sc.S, seed_grad, spp_grad, ctx->rank, ctx->world);
+    sw[1].ps = make_pass(ctx->sc.S, seed_grad, spp_grad, ctx->rank, ctx->world, anti);
     sw[1].film = film_adjoint;
     rc = ensure(ctx, &ctx->rec, &ctx->rec_capacity, (size_t)sw[1].ps.n_items * REC_COUNT + 1);
     if (rc) return rc;

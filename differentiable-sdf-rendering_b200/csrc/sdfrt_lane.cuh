@@ -39,7 +39,12 @@ struct PassParams {
     int rank, world;
     int Wb, Hb;                 // film size incl. border
     unsigned long long n_items;
+    // antithetic_sampling (python/integrators/reparam.py:19,167-178): every wavefront lane is evaluated twice, the second time
+    // at the mirrored film position pos - r + 1 with a clone of the sampler; work items 2l and 2l + 1 are the two samples
+    int antithetic;
 };
+
+constexpr unsigned long long kAntiBit = 1ull << 63;  // WorkItem::lane carries the "mirrored sample" flag in bit 63
 
 constexpr int kBandRows = 8;
 
@@ -48,9 +53,11 @@ constexpr int kBandRows = 8;
 // sampler streams -- stay the reference's scanline wavefront indices (python/integrators/reparam.py:141-155).
 struct WorkItem {
     int px, py;
-    unsigned long long lane;
+    unsigned long long lane;  // wavefront lane index | kAntiBit for the mirrored sample of an antithetic pair
 };
 SDFRT_HD WorkItem decode_item(const PassParams& ps, unsigned long long k) {
+    const unsigned long long anti = ps.antithetic ? (k & 1ull) : 0ull;
+    if (ps.antithetic) k >>= 1;
     const unsigned Wb = (unsigned)ps.Wb;
     const unsigned long long per_band = (unsigned long long)kBandRows * Wb * (unsigned)ps.spp;  // < 2^32 (checked on the host)
     const unsigned bl = (unsigned)(k / per_band);
@@ -67,7 +74,7 @@ SDFRT_HD WorkItem decode_item(const PassParams& ps, unsigned long long k) {
     WorkItem w;
     w.px = (int)x;
     w.py = (int)(row0 + y_in);
-    w.lane = ((unsigned long long)w.py * Wb + x) * (unsigned)ps.spp + sidx;
+    w.lane = (((unsigned long long)w.py * Wb + x) * (unsigned)ps.spp + sidx) | (anti ? kAntiBit : 0ull);
     return w;
 }
 
@@ -98,7 +105,13 @@ struct CameraSample {
     float maxt;
     Pcg32 rng;
 };
+// film position of a sample from its pixel and jitter; the mirrored sample of an antithetic pair sits at pos - r + 1
+// (python/integrators/reparam.py:171-174), evaluated in that order
+SDFRT_HD float sample_position(int pix, float r, bool anti) { return anti ? ((float)pix - r) + 1.f : (float)pix + r; }
+
 SDFRT_HD CameraSample camera_sample(const SceneParams& sc, const PassParams& ps, unsigned long long lane) {
+    const bool anti = (lane & kAntiBit) != 0ull;
+    lane &= ~kAntiBit;
     const int b = sc.S.border;
     const int Wb = sc.S.W + 2 * b;
     const unsigned long long pix = ps.log2_spp >= 0 ? (lane >> ps.log2_spp) : (lane / (unsigned long long)ps.spp);
@@ -108,7 +121,7 @@ SDFRT_HD CameraSample camera_sample(const SceneParams& sc, const PassParams& ps,
     cs.rng = sampler_seed(ps.seed, (uint32_t)lane);
     const float r0 = pcg_next_f32(cs.rng), r1 = pcg_next_f32(cs.rng);
     (void)pcg_next_f32(cs.rng);  // wavelength sample, consumed even in RGB (python/integrators/reparam.py:90)
-    sensor_sample_ray(sc.S, (float)(px - b) + r0, (float)(py - b) + r1, cs.o, cs.d, cs.maxt);
+    sensor_sample_ray(sc.S, sample_position(px - b, r0, anti), sample_position(py - b, r1, anti), cs.o, cs.d, cs.maxt);
     return cs;
 }
 

@@ -51,7 +51,8 @@ __device__ __forceinline__ ItemRay item_ray(const SceneParams& sc, const PassPar
     r.lane = w.lane;
     Pcg32 rng = sampler_seed(ps.seed, (uint32_t)w.lane);
     const float r0 = pcg_next_f32(rng), r1 = pcg_next_f32(rng);
-    sensor_sample_ray(sc.S, (float)(w.px - sc.S.border) + r0, (float)(w.py - sc.S.border) + r1, r.o, r.d, r.maxt);
+    const bool anti = (w.lane & kAntiBit) != 0ull;
+    sensor_sample_ray(sc.S, sample_position(w.px - sc.S.border, r0, anti), sample_position(w.py - sc.S.border, r1, anti), r.o, r.d, r.maxt);
     float u, v; bool inside; V3 ref;
     sensor_project(sc.S, r.o + r.d, u, v, inside, ref);  // re-projection, python/integrators/reparam.py:100-105
     r.pfx = u + ((float)sc.S.border - 0.5f);

@@ -100,7 +100,7 @@ inline ShadingParams make_shading(const sdfrt_shading& s) {
     o.hide_emitters = s.hide_emitters;
     return o;
 }
-inline PassParams make_pass(const SensorParams& S, uint32_t seed, int spp, int rank, int world) {
+inline PassParams make_pass(const SensorParams& S, uint32_t seed, int spp, int rank, int world, int antithetic = 0) {
     PassParams p;
     p.seed = seed;
     p.spp = spp;
@@ -115,7 +115,8 @@ inline PassParams make_pass(const SensorParams& S, uint32_t seed, int spp, int r
     const int nbands = (p.Hb + kBandRows - 1) / kBandRows;
     unsigned long long rows = 0;
     for (int g = rank; g < nbands; g += world) rows += (unsigned long long)std::min(kBandRows, p.Hb - g * kBandRows);
-    p.n_items = rows * (unsigned long long)p.Wb * (unsigned long long)spp;
+    p.antithetic = antithetic ? 1 : 0;
+    p.n_items = rows * (unsigned long long)p.Wb * (unsigned long long)spp * (unsigned long long)(1 + p.antithetic);
     return p;
 }
 

@@ -43,6 +43,16 @@ SDFRT_HD_NOINLINE ValueTrace prb_trace_value(const GridView& G, const TracerPara
     r.its_t = trace_non_diff(G, T, o, d, ray_maxt, do_refine, r.n_steps, r.n_evals);
     return r;
 }
+// primal walker: inlined (ncu: the call costs it 18 % -- long_scoreboard 1.9 -> 4.7 stall cycles per issue, fewer loads in
+// flight across the call boundary); replay walker: the real call (its problem was instruction fetch)
+template <bool CALL>
+SDFRT_HD ValueTrace trace_value_sel(const GridView& G, const TracerParams& T, V3 o, V3 d, float ray_maxt, bool do_refine) {
+    if (CALL) return prb_trace_value(G, T, o, d, ray_maxt, do_refine);
+    ValueTrace r;
+    r.n_steps = 0; r.n_evals = 0;
+    r.its_t = trace_non_diff(G, T, o, d, ray_maxt, do_refine, r.n_steps, r.n_evals);
+    return r;
+}
 struct DiffTrace {
     TraceOut out;
     int n_hess, n_value;
@@ -151,7 +161,7 @@ SDFRT_HD V3 lane_prb(const SceneParams& sc, const PassParams& ps, unsigned long 
     V3 o_cur = cs.o, d_cur = cs.d;
     float t_cur;
     {   // ray_intersect_preliminary (:264)
-        const ValueTrace vt = prb_trace_value(G, T, o_cur, d_cur, cs.maxt, true);
+        const ValueTrace vt = trace_value_sel<BWD>(G, T, o_cur, d_cur, cs.maxt, true);
         t_cur = vt.its_t; nsteps = vt.n_steps; nv += vt.n_evals;
     }
     st.n_hit += isfinite(t_cur);
@@ -246,7 +256,7 @@ SDFRT_HD V3 lane_prb(const SceneParams& sc, const PassParams& ps, unsigned long 
                 sr = make_shadow_ray(sc.Sh, p, n, u_em0, u_em1);  // si_cur.spawn_ray_to(ds.p), d detached (:316-317)
                 cos_o = dot(n, sr.d);
                 if ((cos_i > 0.f) & (cos_o > 0.f)) {  // a closed BSDF gate contributes exactly zero: not marched
-                    const ValueTrace vs = prb_trace_value(G, T, sr.o, sr.d, sr.maxt, false);
+                    const ValueTrace vs = trace_value_sel<BWD>(G, T, sr.o, sr.d, sr.maxt, false);
                     nv += vs.n_evals;
                     if (!isfinite(vs.its_t)) {
                         nee = true;
@@ -286,7 +296,7 @@ SDFRT_HD V3 lane_prb(const SceneParams& sc, const PassParams& ps, unsigned long 
         // ---- next surface and the MIS weight of hitting the emitter by BSDF sampling (:351-363) ---------------
         float t_next = INFINITY;
         if (active_next) {
-            const ValueTrace vn = prb_trace_value(G, T, o_next, wo_w, INFINITY, true);
+            const ValueTrace vn = trace_value_sel<BWD>(G, T, o_next, wo_w, INFINITY, true);
             t_next = vn.its_t; nv += vn.n_evals;
             nsteps = nsteps > vn.n_steps ? nsteps : vn.n_steps;
         }

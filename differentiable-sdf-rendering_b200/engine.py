@@ -109,6 +109,9 @@ class Context:
         i = INTEGRATOR_IDS[name_or_id] if isinstance(name_or_id, str) else int(name_or_id)
         check(self.ctx, self.lib.sdfrt_set_integrator(self.ctx, i))
 
+    def set_antithetic(self, enable):
+        check(self.ctx, self.lib.sdfrt_set_antithetic(self.ctx, int(bool(enable))))
+
     def set_prb(self, max_depth=4, rr_depth=5):
         p = _capi.PrbParams(int(max_depth), int(rr_depth))
         check(self.ctx, self.lib.sdfrt_set_prb(self.ctx, C.byref(p)))

@@ -25,9 +25,7 @@ class ReparamIntegrator:
         self.use_mis = props.get('use_mis', False)
         if self.use_mis:
             raise NotImplementedError("the BSDF-sampling MIS branch (sdf_direct_reparam.py:87-107) is not on the hot path")
-        self.antithetic_sampling = props.get('antithetic_sampling', False)
-        if self.antithetic_sampling:
-            raise NotImplementedError("antithetic_sampling is evaluation-only in the reference and not provided")
+        self.antithetic_sampling = props.get('antithetic_sampling', False)   # python/integrators/reparam.py:19,167-178
         self.use_aovs = props.get('use_aovs', False)
         self.hide_emitters = props.get('hide_emitters', False)
         self.sdf = sdf
@@ -56,6 +54,7 @@ class ReparamIntegrator:
         ctx.set_shading(scene.env_radiance, scene.env_dist, scene.albedo, self.hide_emitters)
         ctx.set_albedo(scene.albedo_grid)
         ctx.set_integrator(self.integrator_name)
+        ctx.set_antithetic(self.antithetic_sampling)
         ctx.set_warp(**warp_params_of(self.warp_field))
         ctx.set_tracer(**self.sdf.tracer_params())
         return ctx

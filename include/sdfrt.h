@@ -128,6 +128,10 @@ int sdfrt_set_warp(sdfrt_ctx* ctx, const sdfrt_warp_params* p);   /* integrator.
 int sdfrt_set_sensor(sdfrt_ctx* ctx, const sdfrt_sensor* s);
 int sdfrt_set_shading(sdfrt_ctx* ctx, const sdfrt_shading* s);
 int sdfrt_set_integrator(sdfrt_ctx* ctx, int integrator);         /* SDFRT_INTEGRATOR_* */
+/* props `antithetic_sampling` of ReparamIntegrator (python/integrators/reparam.py:19,167-178; default off, "used in evaluation"):
+ * every wavefront lane is evaluated twice, the second time at the mirrored film position with a clone of the sampler.
+ * Applies to the three ReparamIntegrator.render-based integrators; sdf_prb_reparam has its own render without it. */
+int sdfrt_set_antithetic(sdfrt_ctx* ctx, int enable);
 void sdfrt_prb_defaults(sdfrt_prb_params* p);
 int sdfrt_set_prb(sdfrt_ctx* ctx, const sdfrt_prb_params* p);      /* used when the integrator is SDFRT_INTEGRATOR_PRB */
 /* multi-GPU ray partition: the film rows (border included) are cut into bands of 8 rows; this context renders the

@@ -858,7 +858,7 @@ INTEGRATORS = {'sdf_silhouette_reparam': sample_silhouette,
                'sdf_direct_reparam': sample_direct}
 
 
-def render(scene, warp_field, integrator, seed, spp, mode_backward=False, lane_range=None, develop=True):
+def render(scene, warp_field, integrator, seed, spp, mode_backward=False, lane_range=None, develop=True, antithetic=False):
     """ReparamIntegrator.render (python/integrators/reparam.py:120-185) + eval_sample (:82-118).
 
     mode_backward=False == dr.ADMode.Primal (no reparameterisation in the direct integrator).
@@ -879,25 +879,31 @@ def render(scene, warp_field, integrator, seed, spp, mode_backward=False, lane_r
     pos = torch.stack([px - b, py - b], -1).to(dtype)
     sampler = IndependentSampler(seed, wavefront, dtype, lane_offset=lo, lane_count=hi - lo)
     r = sampler.next_2d()
-    position_sample = pos + r
-    _wavelength = sampler.next_1d()  # consumed even in RGB (python/integrators/reparam.py:90)
-    o, d, maxt = sensor.sample_ray(position_sample, dtype)
-    rgb, d_att, det = INTEGRATORS[integrator](scene, warp_field, sampler, o, d, maxt, mode_backward)
-    # re-projection (python/integrators/reparam.py:100-106)
-    it_p = o + d_att
-    uv, rw = sensor.sample_direction(it_p)
-    rw_safe = torch.where(rw > 0, rw, torch.ones_like(rw))
-    rw1 = torch.where(rw > 0, rw_safe / rw_safe.detach(), torch.ones_like(rw))
-    rw1 = replace_grad(torch.ones_like(rw1), rw1)
-    rgb = rw1[:, None] * rgb
-    wch = replace_grad(torch.ones_like(det), det * rw1)
-    acc = film_put(sensor, uv, torch.cat([rgb, wch[:, None]], -1))
+    samples = [(pos + r, sampler)]
+    if antithetic:  # python/integrators/reparam.py:171-178: mirrored position, clone of the sampler after the jitter draw
+        import copy
+        samples.append((pos - r + 1.0, copy.deepcopy(sampler)))
+    acc = None
+    for position_sample, smp in samples:
+        _wavelength = smp.next_1d()  # consumed even in RGB (python/integrators/reparam.py:90)
+        o, d, maxt = sensor.sample_ray(position_sample, dtype)
+        rgb, d_att, det = INTEGRATORS[integrator](scene, warp_field, smp, o, d, maxt, mode_backward)
+        # re-projection (python/integrators/reparam.py:100-106)
+        it_p = o + d_att
+        uv, rw = sensor.sample_direction(it_p)
+        rw_safe = torch.where(rw > 0, rw, torch.ones_like(rw))
+        rw1 = torch.where(rw > 0, rw_safe / rw_safe.detach(), torch.ones_like(rw))
+        rw1 = replace_grad(torch.ones_like(rw1), rw1)
+        rgb = rw1[:, None] * rgb
+        wch = replace_grad(torch.ones_like(det), det * rw1)
+        a = film_put(sensor, uv, torch.cat([rgb, wch[:, None]], -1))
+        acc = a if acc is None else acc + a
     if not develop:
         return acc
     return film_develop(sensor, acc)
 
 
-def render_backward(scene, warp_field, integrator, grad_in, seed, spp):
+def render_backward(scene, warp_field, integrator, grad_in, seed, spp, antithetic=False):
     """ReparamIntegrator.render_backward (python/integrators/reparam.py:187-190).
 
     Returns (image, grad wrt sdf.data (Z,Y,X), grad wrt sdf.p (3,), grad wrt albedo grid or None).
@@ -909,7 +915,7 @@ def render_backward(scene, warp_field, integrator, grad_in, seed, spp):
     if alb0 is not None:
         scene.albedo_grid = alb0.detach().clone().requires_grad_(True)
     try:
-        image = render(scene, warp_field, integrator, seed, spp, mode_backward=True)
+        image = render(scene, warp_field, integrator, seed, spp, mode_backward=True, antithetic=antithetic)
         loss = (image * grad_in).sum()
         wrt = [sdf.data, sdf.p] + ([scene.albedo_grid] if alb0 is not None else [])
         grads = torch.autograd.grad(loss, wrt, allow_unused=True)

@@ -19,6 +19,7 @@ struct hh_scene {
     sdfrt_shading shading;
     int integrator;
     sdfrt_prb_params prb;
+    int antithetic;   // ReparamIntegrator.antithetic_sampling (hh_forward / hh_backward / hh_local_lanes)
 };
 
 static SceneParams build(const hh_scene* h) {
@@ -82,7 +83,7 @@ int hh_trace(const hh_scene* h, const float* o, const float* d, const float* max
 // forward pass over the whole wavefront; film: (Hb, Wb, 4) zeroed here; rec: REC_COUNT * n floats (diff only)
 int hh_forward(const hh_scene* h, unsigned seed, int spp, int diff, float* film, float* rec, unsigned long long* stats, int rank, int world) {
     SceneParams sc = build(h);
-    PassParams ps = make_pass(sc.S, seed, spp, rank, world);
+    PassParams ps = make_pass(sc.S, seed, spp, rank, world, h->antithetic);
     const size_t nf = (size_t)(sc.S.W + 2 * sc.S.border) * (sc.S.H + 2 * sc.S.border) * 4;
     std::memset(film, 0, nf * sizeof(float));
     LaneStats st = {0, 0, 0, 0, 0, 0, 0};
@@ -111,7 +112,7 @@ int hh_develop(const hh_scene* h, const float* film, float* image) {
 int hh_backward(const hh_scene* h, unsigned seed, int spp, const float* film, const float* rec, const float* grad_image,
                 float* grad_sdf, float* grad_albedo, float* grad_p, unsigned long long* stats, int rank, int world) {
     SceneParams sc = build(h);
-    PassParams ps = make_pass(sc.S, seed, spp, rank, world);
+    PassParams ps = make_pass(sc.S, seed, spp, rank, world, h->antithetic);
     const SensorParams& S = sc.S;
     const int Wb = S.W + 2 * S.border, Hb = S.H + 2 * S.border;
     std::vector<float> adj((size_t)Wb * Hb * 4, 0.f);
@@ -210,7 +211,7 @@ int hh_prb_backward(const hh_scene* h, unsigned seed, int spp, const float* film
 int hh_rec_count() { return REC_COUNT; }
 unsigned long long hh_local_lanes(const hh_scene* h, int spp, int rank, int world) {
     SensorParams S = make_sensor(h->sensor);
-    PassParams ps = make_pass(S, 0, spp, rank, world);
+    PassParams ps = make_pass(S, 0, spp, rank, world, h->antithetic);
     return ps.n_items;
 }
 }

@@ -45,7 +45,7 @@ class HHScene(C.Structure):
     _fields_ = [('sdf', C.c_void_p), ('rx', C.c_int), ('ry', C.c_int), ('rz', C.c_int), ('p', C.c_float * 3),
                 ('albedo', C.c_void_p), ('ax', C.c_int), ('ay', C.c_int), ('az', C.c_int),
                 ('tracer', TracerParams), ('warp', WarpParams), ('sensor', SensorParams), ('shading', ShadingParams),
-                ('integrator', C.c_int), ('prb', PrbParams)]
+                ('integrator', C.c_int), ('prb', PrbParams), ('antithetic', C.c_int)]
 
 
 def build():

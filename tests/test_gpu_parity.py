@@ -308,3 +308,33 @@ def test_pipelined_view_equals_separate_sweeps(big):
     assert (fp2 - fp).abs().max() < 1e-3 * fp.abs().max()
     assert (fa2 - fa).abs().max() < 1e-3 * fa.abs().max()
     assert (g_cmb - g_sep).abs().max() < 1e-3 * g_sep.abs().max()
+
+
+def test_antithetic_sampling_against_oracle(sdfrt_mod):
+    """prop antithetic_sampling through the wavefront pipeline: doubled work list, mirrored film positions, cloned samplers."""
+    from oracle import sdf_oracle as O
+    W, spp = 16, 4
+    osc = O.make_scene('knot', res=32, width=W, height=W)
+    sdf = sdfrt_mod.Grid3d(osc.sdf.data.float().numpy(), device=0)
+    integ = sdfrt_mod.integrators.create('sdf_direct_reparam', dict(antithetic_sampling=True), sdf=sdf)
+    wf = sdfrt_mod.WarpField2D(sdf, weight_strategy=6, edge_eps=0.01)
+    wf.clamping_thresh = 0.05
+    integ.warp_field = wf
+    scene = sdfrt_mod.Scene(integ, [sdfrt_mod.Sensor(osc.sensor.to_world, W, W)])
+    owf = O.WarpField2D(osc.sdf, weight_strategy=6, edge_eps=0.01)
+    owf.clamping_thresh = 0.05
+    with torch.no_grad():
+        img_o = O.render(osc, owf, 'sdf_direct_reparam', seed=3, spp=spp, antithetic=True).numpy()
+    sdf.data.requires_grad_(True)
+    img = sdfrt_mod.render(scene, sensor=0, seed=3, spp=spp, seed_grad=11, spp_grad=spp)
+    assert np.abs(img.detach().cpu().numpy() - img_o).max() < 2e-5
+    g_in = np.random.default_rng(5).uniform(-1, 1, size=(W, W, 3))
+    _, g_o, _, _ = O.render_backward(osc, owf, 'sdf_direct_reparam', torch.from_numpy(g_in), seed=11, spp=spp, antithetic=True)
+    (img * torch.from_numpy(g_in).float().cuda()).sum().backward()
+    gs, g_o = sdf.data.grad[..., 0].cpu().numpy(), g_o.numpy()
+    assert np.abs(gs - g_o).max() < 2e-2 * np.abs(g_o).max() and np.linalg.norm(gs - g_o) < 5e-3 * np.linalg.norm(g_o)
+    assert sdf.ctx.stats()['n_rays'] > 0
+    integ.antithetic_sampling = False        # and the switch goes back off
+    img_plain = integ.render(scene, sensor=0, seed=3, spp=spp)
+    with torch.no_grad():
+        assert np.abs(img_plain.cpu().numpy() - O.render(osc, owf, 'sdf_direct_reparam', seed=3, spp=spp).numpy()).max() < 2e-5

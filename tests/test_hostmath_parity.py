@@ -152,3 +152,28 @@ def test_empty_space_test_is_conservative(kind, R, W):
         v = HM.lib().hh_check_empty_space(C.byref(hs.h), 3, 8, C.c_float(skip_eps), HM.fptr(out))
         assert v == 0
         assert out[0] > 0.1 * out[1], out    # and the test is not vacuous: a good share of the rays is skipped
+
+
+def test_antithetic_sampling_parity():
+    """antithetic_sampling (python/integrators/reparam.py:19,167-178): every lane evaluated twice, the second sample at the
+    mirrored film position with a clone of the sampler -- image, gradient and the rank partition of the doubled work list."""
+    W, spp = 16, 4
+    sc, wf, hs = make_pair('knot', 32, W, 'sdf_direct_reparam')
+    hs.h.antithetic = 1
+    assert hs.local_lanes(spp) == 2 * hs.wavefront(spp)
+    with torch.no_grad():
+        img_o = O.render(sc, wf, 'sdf_direct_reparam', seed=3, spp=spp, antithetic=True).numpy()
+        img_plain = O.render(sc, wf, 'sdf_direct_reparam', seed=3, spp=spp).numpy()
+    film, _, _ = hs.forward(3, spp, False)
+    assert np.abs(hs.develop(film) - img_o).max() < 2e-5 and np.abs(img_o - img_plain).max() > 1e-2
+    g_in = np.random.default_rng(5).uniform(-1, 1, size=(W, W, 3))
+    img2, g_o, _, _ = O.render_backward(sc, wf, 'sdf_direct_reparam', torch.from_numpy(g_in), seed=11, spp=spp, antithetic=True)
+    film, rec, _ = hs.forward(11, spp, True)
+    assert np.abs(hs.develop(film) - img2.numpy()).max() < 2e-5
+    g_h = hs.backward(11, spp, film, rec, g_in)[0]
+    g_o = g_o.numpy()
+    assert np.abs(g_h - g_o).max() < 2e-2 * np.abs(g_o).max() and np.linalg.norm(g_h - g_o) < 5e-3 * np.linalg.norm(g_o)
+    whole = hs.forward(3, spp, False)[0]
+    for world in (2, 3):
+        parts = sum(hs.forward(3, spp, False, r, world)[0] for r in range(world))
+        assert np.abs(parts - whole).max() < 2e-5
