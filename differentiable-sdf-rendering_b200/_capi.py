@@ -63,6 +63,7 @@ SIGNATURES = {
     'sdfrt_sensor_defaults': (None, [C.POINTER(SensorParams)]),
     'sdfrt_shading_defaults': (None, [C.POINTER(ShadingParams)]),
     'sdfrt_set_sdf': (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    'sdfrt_set_sdf_transform': (C.c_int, [_P, C.POINTER(C.c_float)]),
     'sdfrt_set_albedo': (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int]),
     'sdfrt_set_tracer': (C.c_int, [_P, C.POINTER(TracerParams)]),
     'sdfrt_set_warp': (C.c_int, [_P, C.POINTER(WarpParams)]),

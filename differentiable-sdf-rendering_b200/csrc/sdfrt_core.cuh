@@ -89,6 +89,10 @@ struct GridView {
     // optional row-expanded copy for the marchers: rows4[(z * ry + y) * rx + x] = data[z][y][x .. x+3] (x <= rx - 4),
     // so that one 16-byte load fetches a whole x-row of a 4x4x4 block.  nullptr = read `data`.
     const float4* rows4;
+    // Grid3d(data, transform) (python/shapes.py:378-392): lookups use x_local = A (x - p) + tl (`to_local`), gradients and
+    // Hessians are pulled back with A^T (python/shapes.py:423-448).  has_transform == 0: identity (the reference's fast path).
+    int has_transform;
+    float A[9], tl[3];
 };
 struct AlbedoView {
     const float* data;  // (rz, ry, rx, 3) or nullptr
@@ -100,6 +104,9 @@ struct TracerParams {
     int refine_intersection, use_extra_weight;
     float extra_thresh, sil_weight_offset, sil_weight_epsilon;
     int weight_power, use_weight_sum_weight, max_steps;
+    // Grid3d.bbox(): world AABB of the transformed unit cube, inflated by 0.05 (python/shapes.py:394-403,416-418).  Kept with the
+    // tracer parameters because every tracer routine that needs it already receives them.
+    float bmin[3], bmax[3];
 };
 struct WarpParams {
     int kind;
@@ -200,9 +207,16 @@ struct CellCoord {  // base tap index (may be out of range -> clamped per tap) a
 };
 SDFRT_HD CellCoord cell_coord(const GridView& G, V3 x) {
     CellCoord c;
-    float ux = (x.x - G.px) * (float)G.rx - 0.5f;
-    float uy = (x.y - G.py) * (float)G.ry - 0.5f;
-    float uz = (x.z - G.pz) * (float)G.rz - 0.5f;
+    float lx = x.x - G.px, ly = x.y - G.py, lz = x.z - G.pz;
+    if (G.has_transform) {  // call_wrap: to_local @ (x - p), python/shapes.py:408-414
+        const float tx = G.A[0] * lx + G.A[1] * ly + G.A[2] * lz + G.tl[0];
+        const float ty = G.A[3] * lx + G.A[4] * ly + G.A[5] * lz + G.tl[1];
+        const float tz = G.A[6] * lx + G.A[7] * ly + G.A[8] * lz + G.tl[2];
+        lx = tx; ly = ty; lz = tz;
+    }
+    float ux = lx * (float)G.rx - 0.5f;
+    float uy = ly * (float)G.ry - 0.5f;
+    float uz = lz * (float)G.rz - 0.5f;
     float fx = floorf(ux), fy = floorf(uy), fz = floorf(uz);
     c.ax = ux - fx; c.ay = uy - fy; c.az = uz - fz;
     // keep the int conversion defined for far-away points (texels clamp anyway)
@@ -328,6 +342,21 @@ SDFRT_HD void reduce_taps(const float f[64], const CellSetup<ORDER>& s, const Gr
             H.xx = r_xx * sx * sx; H.yy = r_yy * sy_ * sy_; H.zz = r_zz * sz_ * sz_;
             H.xy = r_xy * sx * sy_; H.xz = r_xz * sx * sz_; H.yz = r_yz * sy_ * sz_;
         }
+        if (G.has_transform) {  // g <- A^T g, H <- A^T H A (python/shapes.py:426-428,445-448)
+            const float* A = G.A;
+            const V3 gl = g;
+            g = V3{A[0] * gl.x + A[3] * gl.y + A[6] * gl.z, A[1] * gl.x + A[4] * gl.y + A[7] * gl.z, A[2] * gl.x + A[5] * gl.y + A[8] * gl.z};
+            if (ORDER >= 2) {
+                const float Hl[3][3] = {{H.xx, H.xy, H.xz}, {H.xy, H.yy, H.yz}, {H.xz, H.yz, H.zz}};
+                float HA[3][3], R[3][3];
+                for (int i = 0; i < 3; ++i)
+                    for (int j = 0; j < 3; ++j) HA[i][j] = Hl[i][0] * A[0 + j] + Hl[i][1] * A[3 + j] + Hl[i][2] * A[6 + j];
+                for (int i = 0; i < 3; ++i)
+                    for (int j = 0; j < 3; ++j) R[i][j] = A[0 + i] * HA[0][j] + A[3 + i] * HA[1][j] + A[6 + i] * HA[2][j];
+                H.xx = R[0][0]; H.yy = R[1][1]; H.zz = R[2][2];
+                H.xy = 0.5f * (R[0][1] + R[1][0]); H.xz = 0.5f * (R[0][2] + R[2][0]); H.yz = 0.5f * (R[1][2] + R[2][1]);
+            }
+        }
     }
 }
 template <int ORDER>
@@ -345,12 +374,11 @@ SDFRT_HD float eval_value(const GridView& G, V3 x) {
 }
 
 // ------------------------------------------------------------------------------------
-// math_util.bbox_distance_inside_d (python/math_util.py:31-41); bbox = unit cube +- 0.05
+// math_util.bbox_distance_inside_d (python/math_util.py:31-41); bbox = Grid3d.bbox() (unit cube +- 0.05 without a transform)
 // ------------------------------------------------------------------------------------
-SDFRT_HD float bbox_distance_inside_d(V3 x, V3& dist_d) {
-    const float lo = -kBBoxDelta, hi = 1.f + kBBoxDelta;
-    const V3 dmin = V3{x.x - lo, x.y - lo, x.z - lo};
-    const V3 dmax = V3{hi - x.x, hi - x.y, hi - x.z};
+SDFRT_HD float bbox_distance_inside_d(const TracerParams& P, V3 x, V3& dist_d) {
+    const V3 dmin = V3{x.x - P.bmin[0], x.y - P.bmin[1], x.z - P.bmin[2]};
+    const V3 dmax = V3{P.bmax[0] - x.x, P.bmax[1] - x.y, P.bmax[2] - x.z};
     const float dist = fmaxf(0.f, fminf(fminf3(dmin), fminf3(dmax)));
     const V3 amax = V3{fabsf(dmax.x), fabsf(dmax.y), fabsf(dmax.z)};
     const V3 amin = V3{fabsf(dmin.x), fabsf(dmin.y), fabsf(dmin.z)};
@@ -371,15 +399,15 @@ struct BoxHit {
     bool intersects, inside;
     float mint, maxt;
 };
-SDFRT_HD BoxHit ray_box(V3 o, V3 d) {
-    const float lo = -kBBoxDelta, hi = 1.f + kBBoxDelta;
+SDFRT_HD BoxHit ray_box(const TracerParams& P, V3 o, V3 d) {
     BoxHit b;
     const V3 r = V3{1.f / d.x, 1.f / d.y, 1.f / d.z};
-    const V3 t1 = V3{(lo - o.x) * r.x, (lo - o.y) * r.y, (lo - o.z) * r.z};
-    const V3 t2 = V3{(hi - o.x) * r.x, (hi - o.y) * r.y, (hi - o.z) * r.z};
+    const V3 t1 = V3{(P.bmin[0] - o.x) * r.x, (P.bmin[1] - o.y) * r.y, (P.bmin[2] - o.z) * r.z};
+    const V3 t2 = V3{(P.bmax[0] - o.x) * r.x, (P.bmax[1] - o.y) * r.y, (P.bmax[2] - o.z) * r.z};
     b.mint = fmaxf(fminf(t1.x, t2.x), fmaxf(fminf(t1.y, t2.y), fminf(t1.z, t2.z)));
     b.maxt = fminf(fmaxf(t1.x, t2.x), fminf(fmaxf(t1.y, t2.y), fmaxf(t1.z, t2.z)));
-    const bool inx = (o.x >= lo) & (o.x <= hi), iny = (o.y >= lo) & (o.y <= hi), inz = (o.z >= lo) & (o.z <= hi);
+    const bool inx = (o.x >= P.bmin[0]) & (o.x <= P.bmax[0]), iny = (o.y >= P.bmin[1]) & (o.y <= P.bmax[1]),
+               inz = (o.z >= P.bmin[2]) & (o.z <= P.bmax[2]);
     b.inside = inx & iny & inz;
     const bool act = ((d.x != 0.f) | inx) & ((d.y != 0.f) | iny) & ((d.z != 0.f) | inz);
     b.intersects = act & (b.maxt >= b.mint);
@@ -402,7 +430,7 @@ SDFRT_HD float eval_trace_weight(const TracerParams& P, V3 d, int i, V3 x, float
     const float denom = P.sil_weight_epsilon + fabsf(sdf_value) + P.sil_weight_offset * n_dot_d * dot_ratio;
     const float dist_weight = SDFRT_FDIV(1.f, ipow(denom, P.weight_power));
     V3 bbox_dist_d;
-    const float bbox_dist = bbox_distance_inside_d(x, bbox_dist_d);
+    const float bbox_dist = bbox_distance_inside_d(P, x, bbox_dist_d);
     const float bbox_eps = 0.01f;
     const float bbox_weight = (i > 0) ? SDFRT_FDIV(fminf(bbox_dist, bbox_eps), bbox_eps) : 1.f;
     const float weight = dist_weight * bbox_weight;
@@ -441,7 +469,7 @@ struct Segment {
 SDFRT_HD bool segment_begin(Segment& s, const TracerParams& P, V3 o, V3 d, float ray_maxt) {
     s.o = o;
     s.d = normalize(d);
-    const BoxHit b = ray_box(o, s.d);
+    const BoxHit b = ray_box(P, o, s.d);
     s.maxt = fminf(b.maxt, ray_maxt);
     s.trace_eps = P.trace_eps * fmaxf(s.maxt, 1.f);
     s.its_t = INFINITY;
@@ -477,14 +505,13 @@ struct DiffAcc {
 };
 
 // entry face of the bounding box and initial dt/dx (python/shapes.py:142-164)
-SDFRT_HD void diff_begin(DiffAcc& a, const Segment& s) {
+SDFRT_HD void diff_begin(DiffAcc& a, const Segment& s, const TracerParams& P) {
     a.warp_t = 0.f; a.prev_surf_dist = 0.f; a.weight_sum = 0.f; a.extra_weight_sum = 0.f;
     a.prev_sdf_grad_c = v3(0.f); a.mixed_sum_d = v3(0.f); a.weight_d_sum = v3(0.f); a.extra_weight_sum_d = v3(0.f);
     a.t_d = v3(0.f);
-    const float lo = -kBBoxDelta, hi = 1.f + kBBoxDelta;
     const V3 q = s.o + s.t * s.d;
-    const V3 md = V3{fminf(fabsf(lo - q.x), fabsf(hi - q.x)), fminf(fabsf(lo - q.y), fabsf(hi - q.y)),
-                     fminf(fabsf(lo - q.z), fabsf(hi - q.z))};
+    const V3 md = V3{fminf(fabsf(P.bmin[0] - q.x), fabsf(P.bmax[0] - q.x)), fminf(fabsf(P.bmin[1] - q.y), fabsf(P.bmax[1] - q.y)),
+                     fminf(fabsf(P.bmin[2] - q.z), fabsf(P.bmax[2] - q.z))};
     V3 n = v3(0.f);
     if ((md.x < md.y) & (md.x < md.z)) n = v3(1, 0, 0);
     if ((md.y < md.z) & (md.y < md.x)) n = v3(0, 1, 0);
@@ -590,7 +617,7 @@ SDFRT_HD void trace_diff(const GridView& G, const TracerParams& P, V3 o, V3 d, f
     Segment s;
     DiffAcc a;
     bool active = segment_begin(s, P, o, d, ray_maxt);
-    diff_begin(a, s);
+    diff_begin(a, s, P);
     while (active) {
         float v; V3 g; S3 H;
         eval_sdf<2>(G, s.o + s.t * s.d, v, g, H);
@@ -610,9 +637,9 @@ SDFRT_HD void trace_diff(const GridView& G, const TracerParams& P, V3 o, V3 d, f
 // ------------------------------------------------------------------------------------
 // WarpField2D.weight / weight_epsilon (python/warp.py:25-45)
 // ------------------------------------------------------------------------------------
-SDFRT_HD float warp_weight_fn(V3 x, float sdf_value, V3 g, float edge_eps, V3& w_d, float& edge_eps_d_out) {
+SDFRT_HD float warp_weight_fn(const TracerParams& P, V3 x, float sdf_value, V3 g, float edge_eps, V3& w_d, float& edge_eps_d_out) {
     V3 bbox_dist_d;
-    const float bbox_dist = bbox_distance_inside_d(x, bbox_dist_d);
+    const float bbox_dist = bbox_distance_inside_d(P, x, bbox_dist_d);
     const bool use_edge_eps = edge_eps <= bbox_dist;
     const V3 edge_eps_d = use_edge_eps ? v3(0.f) : bbox_dist_d;
     edge_eps = fminf(edge_eps, bbox_dist);
@@ -670,7 +697,7 @@ SDFRT_HD WarpSite warp_site(const GridView& G, const WarpParams& W, const Tracer
     // weight of the warp field (python/warp.py:66-76)
     const float eps = (W.weight_strategy == 6) ? W.edge_eps * tau : W.edge_eps;
     V3 w_g; float eps_d;
-    float w = warp_weight_fn(x, phi, g, eps, w_g, eps_d);
+    float w = warp_weight_fn(T, x, phi, g, eps, w_g, eps_d);
     w_g = w_g + (eps_d * W.edge_eps) * d0;
     if (T.use_weight_sum_weight) {
         w_g = w_g * omega + w * omega_d;

@@ -290,6 +290,8 @@ struct sdfrt_ctx {
     sdfrt_shading shading_pub;
     sdfrt_prb_params prb_pub;
     int rank = 0, world = 1;
+    float to_world[16];      // Grid3d's transform (row-major) when has_xf
+    bool has_xf = false;
     int antithetic = 0;  // ReparamIntegrator.antithetic_sampling (python/integrators/reparam.py:19); not used by sdf_prb_reparam
     bool have_sdf = false;
     // adjoint state
@@ -534,7 +536,7 @@ int run_sweeps(sdfrt_ctx* ctx, Sweep* sweeps, int ns, cudaStream_t st) {
     }
     // empty-space test (rebuilt every call: the caller may have updated the grid in place): brick minima -> dilation -> one
     // DDA per film pixel and sweep -> masks consumed by k_gen_primary
-    if (ctx->skip_empty) {
+    if (ctx->skip_empty && !ctx->sc.G.has_transform) {  // the brick DDA walks grid space = world space: identity to_world only
         const GridView& G = ctx->sc.G;
         const int npix = (S.W + 2 * S.border) * (S.H + 2 * S.border);
         const size_t mask_words = (size_t)npix / 4 + 1;
@@ -675,6 +677,7 @@ sdfrt_ctx* sdfrt_create(int device, int* status) {
     sensor_defaults(&ctx->sensor_pub);
     shading_defaults(&ctx->shading_pub);
     ctx->sc.T = make_tracer(ctx->tracer_pub);
+    set_grid_transform(ctx->sc.G, ctx->sc.T, nullptr);
     ctx->sc.W = make_warp(ctx->warp_pub);
     ctx->sc.S = make_sensor(ctx->sensor_pub);
     ctx->sc.Sh = make_shading(ctx->shading_pub);
@@ -771,6 +774,7 @@ int sdfrt_set_tracer(sdfrt_ctx* ctx, const sdfrt_tracer_params* p) {
     if (p->weight_power < 1 || p->weight_power > 8) return fail(ctx, SDFRT_ERR_INVALID, "weight_power out of range");
     ctx->tracer_pub = *p;
     ctx->sc.T = make_tracer(*p);
+    set_grid_transform(ctx->sc.G, ctx->sc.T, ctx->has_xf ? ctx->to_world : nullptr);  // the bbox travels with the tracer block
     ctx->adj_ready = false;
     return SDFRT_OK;
 }
@@ -808,6 +812,25 @@ int sdfrt_set_integrator(sdfrt_ctx* ctx, int integrator) {
     if (integrator < SDFRT_INTEGRATOR_SILHOUETTE || integrator > SDFRT_INTEGRATOR_PRB)
         return fail(ctx, SDFRT_ERR_INVALID, "unknown integrator");
     ctx->sc.integrator = integrator;
+    ctx->adj_ready = false;
+    return SDFRT_OK;
+}
+
+int sdfrt_set_sdf_transform(sdfrt_ctx* ctx, const float* to_world) {
+    if (!ctx) return SDFRT_ERR_INVALID;
+    if (to_world) {
+        for (int i = 0; i < 16; ++i)
+            if (!std::isfinite(to_world[i])) return fail(ctx, SDFRT_ERR_INVALID, "sdf_to_world has non-finite entries");
+        if (to_world[12] != 0.f || to_world[13] != 0.f || to_world[14] != 0.f || to_world[15] != 1.f)
+            return fail(ctx, SDFRT_ERR_INVALID, "sdf_to_world must be affine (last row 0 0 0 1)");
+    }
+    GridView G = ctx->sc.G;
+    TracerParams T = ctx->sc.T;
+    if (!set_grid_transform(G, T, to_world)) return fail(ctx, SDFRT_ERR_INVALID, "sdf_to_world is singular");
+    ctx->sc.G = G;
+    ctx->sc.T = T;
+    ctx->has_xf = to_world != nullptr;
+    if (to_world) std::memcpy(ctx->to_world, to_world, sizeof(ctx->to_world));
     ctx->adj_ready = false;
     return SDFRT_OK;
 }

@@ -266,6 +266,9 @@ template <class Add>
 SDFRT_HD void scatter_site_t(const GridView& G, V3 x, float phi_hat, V3 g_hat, Add add) {
     CellSetup<1> s;
     cell_setup<1>(G, x, s);
+    if (G.has_transform)  // g_world = A^T g_local  =>  adjoint: g_hat_local = A g_hat_world
+        g_hat = V3{G.A[0] * g_hat.x + G.A[1] * g_hat.y + G.A[2] * g_hat.z, G.A[3] * g_hat.x + G.A[4] * g_hat.y + G.A[5] * g_hat.z,
+                   G.A[6] * g_hat.x + G.A[7] * g_hat.y + G.A[8] * g_hat.z};
     const float gx = g_hat.x * (float)G.rx, gy = g_hat.y * (float)G.ry, gz = g_hat.z * (float)G.rz;
     float ex[4];  // phi_hat * wx + gx * dx  (x-direction factor shared by all rows)
 #pragma unroll
@@ -287,6 +290,9 @@ SDFRT_HD void site_tap_values(const GridView& G, V3 x, float phi_hat, V3 g_hat, 
     CellSetup<1> s;
     cell_setup<1>(G, x, s);
     bx = s.bx; by = s.by; bz = s.bz;
+    if (G.has_transform)  // g_world = A^T g_local  =>  adjoint: g_hat_local = A g_hat_world
+        g_hat = V3{G.A[0] * g_hat.x + G.A[1] * g_hat.y + G.A[2] * g_hat.z, G.A[3] * g_hat.x + G.A[4] * g_hat.y + G.A[5] * g_hat.z,
+                   G.A[6] * g_hat.x + G.A[7] * g_hat.y + G.A[8] * g_hat.z};
     const float gx = g_hat.x * (float)G.rx, gy = g_hat.y * (float)G.ry, gz = g_hat.z * (float)G.rz;
     float ex[4];
 #pragma unroll

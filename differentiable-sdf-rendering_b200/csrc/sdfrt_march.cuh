@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(kMarchBlock, DIFF ? (CACHE == 1 ? 3 : 4) : (CA
                 seg.trace_eps = T.trace_eps * fmaxf(b.w, 1.f);
                 seg.its_t = INFINITY;
                 seg.i = 0;
-                if (DIFF) diff_begin(acc, seg);
+                if (DIFF) diff_begin(acc, seg, T);
                 state = seg.intersects ? SLOT_MARCH : SLOT_DONE;
                 if (!DIFF && state == SLOT_DONE) { out_its[item] = INFINITY; state = SLOT_IDLE; }
             }

@@ -67,7 +67,46 @@ inline TracerParams make_tracer(const sdfrt_tracer_params& p) {
     t.extra_thresh = p.extra_thresh; t.sil_weight_offset = p.sil_weight_offset; t.sil_weight_epsilon = p.sil_weight_epsilon;
     t.weight_power = p.weight_power; t.use_weight_sum_weight = p.use_weight_sum_weight;
     t.max_steps = p.max_steps > 0 ? p.max_steps : (1 << 16);
+    for (int i = 0; i < 3; ++i) { t.bmin[i] = -kBBoxDelta; t.bmax[i] = 1.f + kBBoxDelta; }  // identity to_world
     return t;
+}
+// Grid3d(data, transform) (python/shapes.py:378-403): to_local = inverse(to_world) (affine part), bbox = AABB of the eight
+// transformed unit-cube corners +- 0.05.  to_world: row-major 4x4, or nullptr for the identity.  Returns false if singular.
+inline bool set_grid_transform(GridView& G, TracerParams& T, const float* to_world) {
+    G.has_transform = 0;
+    for (int i = 0; i < 9; ++i) G.A[i] = (i % 4 == 0) ? 1.f : 0.f;
+    G.tl[0] = G.tl[1] = G.tl[2] = 0.f;
+    for (int i = 0; i < 3; ++i) { T.bmin[i] = -kBBoxDelta; T.bmax[i] = 1.f + kBBoxDelta; }
+    if (to_world == nullptr) return true;
+    double M[3][3], t[3];
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) M[i][j] = to_world[i * 4 + j];
+        t[i] = to_world[i * 4 + 3];
+    }
+    const double det = M[0][0] * (M[1][1] * M[2][2] - M[1][2] * M[2][1]) - M[0][1] * (M[1][0] * M[2][2] - M[1][2] * M[2][0]) +
+                       M[0][2] * (M[1][0] * M[2][1] - M[1][1] * M[2][0]);
+    if (!(std::fabs(det) > 1e-30)) return false;
+    double inv[3][3];
+    inv[0][0] = (M[1][1] * M[2][2] - M[1][2] * M[2][1]) / det; inv[0][1] = (M[0][2] * M[2][1] - M[0][1] * M[2][2]) / det;
+    inv[0][2] = (M[0][1] * M[1][2] - M[0][2] * M[1][1]) / det; inv[1][0] = (M[1][2] * M[2][0] - M[1][0] * M[2][2]) / det;
+    inv[1][1] = (M[0][0] * M[2][2] - M[0][2] * M[2][0]) / det; inv[1][2] = (M[0][2] * M[1][0] - M[0][0] * M[1][2]) / det;
+    inv[2][0] = (M[1][0] * M[2][1] - M[1][1] * M[2][0]) / det; inv[2][1] = (M[0][1] * M[2][0] - M[0][0] * M[2][1]) / det;
+    inv[2][2] = (M[0][0] * M[1][1] - M[0][1] * M[1][0]) / det;
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) G.A[i * 3 + j] = (float)inv[i][j];
+        G.tl[i] = (float)(-(inv[i][0] * t[0] + inv[i][1] * t[1] + inv[i][2] * t[2]));
+    }
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int c = 0; c < 8; ++c) {
+        const double x = c & 1, y = (c >> 1) & 1, z = (c >> 2) & 1;
+        for (int i = 0; i < 3; ++i) {
+            const double w = (double)(float)(M[i][0] * x + M[i][1] * y + M[i][2] * z + t[i]);
+            lo[i] = std::min(lo[i], w); hi[i] = std::max(hi[i], w);
+        }
+    }
+    for (int i = 0; i < 3; ++i) { T.bmin[i] = (float)lo[i] - kBBoxDelta; T.bmax[i] = (float)hi[i] + kBBoxDelta; }
+    G.has_transform = 1;
+    return true;
 }
 inline WarpParams make_warp(const sdfrt_warp_params& p) {
     WarpParams w;

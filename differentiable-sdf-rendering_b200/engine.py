@@ -63,6 +63,14 @@ class Context:
         self._keep['sdf'] = data
         self.sdf_shape = (rz, ry, rx)
 
+    def set_sdf_transform(self, to_world=None):
+        """Grid3d's `transform` / integrator prop `sdf_to_world`: 4x4 affine (row-major) or None for the identity."""
+        if to_world is None:
+            check(self.ctx, self.lib.sdfrt_set_sdf_transform(self.ctx, None))
+        else:
+            m = (C.c_float * 16)(*[float(v) for v in np.asarray(to_world, dtype=np.float64).reshape(16)])
+            check(self.ctx, self.lib.sdfrt_set_sdf_transform(self.ctx, m))
+
     def set_albedo(self, grid):
         if grid is None:
             check(self.ctx, self.lib.sdfrt_set_albedo(self.ctx, None, 0, 0, 0))

@@ -28,6 +28,11 @@ class ReparamIntegrator:
         self.antithetic_sampling = props.get('antithetic_sampling', False)   # python/integrators/reparam.py:19,167-178
         self.use_aovs = props.get('use_aovs', False)
         self.hide_emitters = props.get('hide_emitters', False)
+        # python/integrators/reparam.py:21-30: `sdf_filename` (+ optional `sdf_to_world`) build the Grid3d; a ready Grid3d can
+        # be passed instead (what shape_opt does after `scene.integrator().sdf`)
+        if sdf is None and props.get('sdf_filename', '') != '':
+            tf = props.get('sdf_to_world', None) if props.has_property('sdf_to_world') else None
+            sdf = Grid3d(props['sdf_filename'], transform=tf)
         self.sdf = sdf
         self.warp_field = None
         self.last_film = None

@@ -49,16 +49,16 @@ def atleast_4d(t):
 
 
 class Grid3d(SDFBase):
-    """python/shapes.py:375-483.  `data`: (Z, Y, X[, 1]) array/tensor; identity `to_world` only."""
+    """python/shapes.py:375-483.  `data`: (Z, Y, X[, 1]) array/tensor; `transform`: affine to_world (4x4) or None."""
 
     def __init__(self, data, transform=None, device=0, context=None):
         super().__init__()
         if isinstance(data, str):  # python/shapes.py:384-386: load a .vol grid and re-distance it
             from . import redistancing, volio
             data = redistancing.redistance(volio.read_vol(data)[0][..., 0])
-        if transform is not None:
-            raise NotImplementedError("sdf_to_world transforms are not supported (has_transform == False path only)")
-        self.has_transform = False
+        self.has_transform = transform is not None          # python/shapes.py:381
+        self.to_world = np.eye(4) if transform is None else np.asarray(getattr(transform, 'matrix', transform), dtype=np.float64).reshape(4, 4)
+        self.to_local = np.linalg.inv(self.to_world)
         self.ctx = context if context is not None else engine.Context(device)
         dev = self.ctx.device
         t = torch.as_tensor(np.asarray(data) if not torch.is_tensor(data) else data, dtype=torch.float32)
@@ -86,14 +86,17 @@ class Grid3d(SDFBase):
 
     def update(self):
         self.ctx.set_sdf(self._data, self.p)
+        self.ctx.set_sdf_transform(self.to_world if self.has_transform else None)
         self.ctx.set_tracer(**self.tracer_params())
 
     def parameters_changed(self, keys=None):
         self.update()
 
     def bbox(self, expand=True):
+        """python/shapes.py:394-403,416-418: AABB of the transformed unit cube, inflated by 0.05."""
         delta = 0.05 if expand else 0.0
-        return (-delta,) * 3, (1 + delta,) * 3
+        c = np.array([[x, y, z, 1.0] for x in (0, 1) for y in (0, 1) for z in (0, 1)]) @ self.to_world.T
+        return tuple(c[:, :3].min(0) - delta), tuple(c[:, :3].max(0) + delta)
 
     # -- lookups (python/shapes.py:420-450) --
     def _pts(self, x):

@@ -119,8 +119,12 @@ void sdfrt_shading_defaults(sdfrt_shading* s);
 
 /* ---- scene state (borrowed pointers; valid until the next set_* of the same kind) ------ */
 /* Grid3d(data) + traverse()'s `sdf.data` / `sdf.p`: python/shapes.py:378-392,469-479.
- * sdf is (rz, ry, rx) C-order, x fastest; identity to_world (has_transform == False). */
+ * sdf is (rz, ry, rx) C-order, x fastest; to_world: sdfrt_set_sdf_transform (identity unless set). */
 int sdfrt_set_sdf(sdfrt_ctx* ctx, const float* sdf, int rx, int ry, int rz, const float p[3]);
+/* Grid3d(data, transform) / integrator prop `sdf_to_world` (python/shapes.py:378-403, python/integrators/reparam.py:21-24):
+ * affine to_world as a row-major 4x4 (last row 0 0 0 1), or NULL for the identity.  Lookups use to_local @ (x - p), gradients
+ * and Hessians are pulled back with to_local^T, the bounding box becomes the AABB of the transformed unit cube +- 0.05. */
+int sdfrt_set_sdf_transform(sdfrt_ctx* ctx, const float* to_world);
 /* `main-bsdf.reflectance.volume.data`: (rz, ry, rx, 3) trilinear grid on [0,1]^3, or NULL */
 int sdfrt_set_albedo(sdfrt_ctx* ctx, const float* rgb_grid, int rx, int ry, int rz);
 int sdfrt_set_tracer(sdfrt_ctx* ctx, const sdfrt_tracer_params* p);

@@ -159,15 +159,18 @@ def _bspline_w(a):
 
 
 class Grid3d:
-    """python/shapes.py:375-483 (identity `to_world` only) + SDFBase knobs `:28-41`."""
+    """python/shapes.py:375-483 + SDFBase knobs `:28-41`.  `to_world`: optional affine 4x4 (Grid3d's `transform`)."""
 
-    def __init__(self, data, p=None):
+    def __init__(self, data, p=None, to_world=None):
         data = torch.as_tensor(data)
         if data.dim() == 4:
             data = data[..., 0]
         self.data = data  # (Z, Y, X), x fastest; may require grad
         self.dtype = data.dtype
         self.p = torch.zeros(3, dtype=self.dtype) if p is None else torch.as_tensor(p, dtype=self.dtype)
+        self.has_transform = to_world is not None                      # python/shapes.py:381
+        self.to_world = np.eye(4) if to_world is None else np.asarray(to_world, dtype=np.float64).reshape(4, 4)
+        self.to_local = np.linalg.inv(self.to_world)
         # SDFBase.__init__ defaults (python/shapes.py:28-41)
         self.step_scale = 1.0
         self.trace_eps = 1e-6
@@ -186,9 +189,10 @@ class Grid3d:
         return tuple(self.data.shape)
 
     def bbox(self):
-        """python/shapes.py:416-418: unit cube +-0.05; ignores self.p (Appendix C #13)."""
-        lo = torch.full((3,), -0.05, dtype=self.dtype)
-        hi = torch.full((3,), 1.05, dtype=self.dtype)
+        """python/shapes.py:394-403,416-418: AABB of the transformed unit cube +-0.05; ignores self.p (Appendix C #13)."""
+        c = np.array([[x, y, z, 1.0] for x in (0, 1) for y in (0, 1) for z in (0, 1)]) @ self.to_world.T
+        lo = torch.as_tensor(c[:, :3].min(0) - 0.05, dtype=self.dtype)
+        hi = torch.as_tensor(c[:, :3].max(0) + 0.05, dtype=self.dtype)
         return lo, hi
 
     def _taps(self, x, order):
@@ -197,6 +201,10 @@ class Grid3d:
         Z, Y, X = self.data.shape
         res = torch.tensor([X, Y, Z], dtype=self.dtype)
         xl = x - self.p  # call_wrap: to_local @ (x - p) (python/shapes.py:408-414)
+        A = None
+        if self.has_transform:
+            A = torch.as_tensor(self.to_local[:3, :3], dtype=self.dtype)
+            xl = xl @ A.T + torch.as_tensor(self.to_local[:3, 3], dtype=self.dtype)
         u = xl * res - 0.5
         uf = torch.floor(u.detach())
         a = u - uf
@@ -218,6 +226,8 @@ class Grid3d:
         if order == 0:
             return v
         g = torch.stack([red(wz, wy, dwx) * res[0], red(wz, dwy, wx) * res[1], red(dwz, wy, wx) * res[2]], -1)
+        if A is not None:
+            g = g @ A  # to_world @ Normal3f(g) = to_local^T g (python/shapes.py:426-428,434-436,445-447)
         if order == 1:
             return v, g
         hxx = red(wz, wy, ddwx) * res[0] * res[0]
@@ -228,6 +238,8 @@ class Grid3d:
         hyz = red(dwz, dwy, wx) * res[1] * res[2]
         H = torch.stack([torch.stack([hxx, hxy, hxz], -1), torch.stack([hxy, hyy, hyz], -1),
                          torch.stack([hxz, hyz, hzz], -1)], -2)
+        if A is not None:
+            H = A.T @ H @ A  # python/shapes.py:448
         return v, g, H
 
     def eval(self, x):

@@ -20,6 +20,8 @@ struct hh_scene {
     int integrator;
     sdfrt_prb_params prb;
     int antithetic;   // ReparamIntegrator.antithetic_sampling (hh_forward / hh_backward / hh_local_lanes)
+    int has_transform;   // Grid3d(data, transform): row-major 4x4 to_world
+    float to_world[16];
 };
 
 static SceneParams build(const hh_scene* h) {
@@ -35,6 +37,7 @@ static SceneParams build(const hh_scene* h) {
     sc.Sh = make_shading(h->shading);
     sc.integrator = h->integrator;
     sc.prb = make_prb(h->prb);
+    set_grid_transform(sc.G, sc.T, h->has_transform ? h->to_world : nullptr);
     return sc;
 }
 

@@ -45,7 +45,8 @@ class HHScene(C.Structure):
     _fields_ = [('sdf', C.c_void_p), ('rx', C.c_int), ('ry', C.c_int), ('rz', C.c_int), ('p', C.c_float * 3),
                 ('albedo', C.c_void_p), ('ax', C.c_int), ('ay', C.c_int), ('az', C.c_int),
                 ('tracer', TracerParams), ('warp', WarpParams), ('sensor', SensorParams), ('shading', ShadingParams),
-                ('integrator', C.c_int), ('prb', PrbParams), ('antithetic', C.c_int)]
+                ('integrator', C.c_int), ('prb', PrbParams), ('antithetic', C.c_int), ('has_transform', C.c_int),
+                ('to_world', C.c_float * 16)]
 
 
 def build():
@@ -74,7 +75,7 @@ def fptr(a):
 class HostScene:
     """Owns the numpy buffers referenced by an HHScene."""
 
-    def __init__(self, sdf, sensor_to_world, width, height, integrator=2, albedo_grid=None, p=(0, 0, 0)):
+    def __init__(self, sdf, sensor_to_world, width, height, integrator=2, albedo_grid=None, p=(0, 0, 0), sdf_to_world=None):
         self.h = HHScene()
         lib().hh_defaults(C.byref(self.h))
         self.sdf = np.ascontiguousarray(sdf, dtype=np.float32)
@@ -91,6 +92,9 @@ class HostScene:
         self.h.sensor.to_world[:] = list(tw)
         self.h.sensor.width, self.h.sensor.height = width, height
         self.h.integrator = integrator
+        if sdf_to_world is not None:
+            self.h.has_transform = 1
+            self.h.to_world[:] = [float(v) for v in np.asarray(sdf_to_world, dtype=np.float64).reshape(16)]
         self.border = 2
 
     @property

@@ -338,3 +338,44 @@ def test_antithetic_sampling_against_oracle(sdfrt_mod):
     img_plain = integ.render(scene, sensor=0, seed=3, spp=spp)
     with torch.no_grad():
         assert np.abs(img_plain.cpu().numpy() - O.render(osc, owf, 'sdf_direct_reparam', seed=3, spp=spp).numpy()).max() < 2e-5
+
+
+def test_sdf_to_world_transform_against_oracle(sdfrt_mod):
+    """Grid3d(data, transform): general affine to_world through the wavefront pipeline (empty-space test off, world AABB,
+    pulled-back gradients / Hessians, grid-space scatter) and through sdf_prb_reparam."""
+    from oracle import sdf_oracle as O
+    from test_hostmath_parity import _affine
+    W, spp, M = 16, 4, _affine()
+    osc = O.make_scene('knot', res=32, width=W, height=W)
+    osc.sdf = O.Grid3d(osc.sdf.data, to_world=M)
+    owf = O.WarpField2D(osc.sdf, weight_strategy=6, edge_eps=0.01)
+    owf.clamping_thresh = 0.05
+    sdf = sdfrt_mod.Grid3d(osc.sdf.data.float().numpy(), transform=M, device=0)
+    assert sdf.has_transform and min(np.subtract(*sdf.bbox()[::-1])) > 1.1
+    g_in = np.random.default_rng(5).uniform(-1, 1, size=(W, W, 3))
+    for name in ('sdf_direct_reparam', 'sdf_prb_reparam'):
+        integ = sdfrt_mod.integrators.create(name, dict(max_depth=3), sdf=sdf)
+        wf = sdfrt_mod.WarpField2D(sdf, weight_strategy=6, edge_eps=0.01)
+        wf.clamping_thresh = 0.05
+        integ.warp_field = wf
+        scene = sdfrt_mod.Scene(integ, [sdfrt_mod.Sensor(osc.sensor.to_world, W, W)])
+        sdf.data.requires_grad_(True)
+        sdf.data.grad = None
+        img = sdfrt_mod.render(scene, sensor=0, seed=3, spp=spp, seed_grad=11, spp_grad=spp)
+        (img * torch.from_numpy(g_in).float().cuda()).sum().backward()
+        if name == 'sdf_prb_reparam':
+            cfg = O.PrbConfig(max_depth=3)
+            img_o = O.render_prb(osc, owf, seed=3, spp=spp, cfg=cfg).numpy()
+            g_o = O.render_backward_prb(osc, owf, torch.from_numpy(g_in), seed=11, spp=spp, cfg=cfg)[1].numpy()
+        else:
+            with torch.no_grad():
+                img_o = O.render(osc, owf, name, seed=3, spp=spp).numpy()
+            g_o = O.render_backward(osc, owf, name, torch.from_numpy(g_in), seed=11, spp=spp)[1].numpy()
+        assert np.abs(img.detach().cpu().numpy() - img_o).max() < 2e-5, name
+        gs = sdf.data.grad[..., 0].cpu().numpy()
+        assert np.abs(gs - g_o).max() < 2e-2 * np.abs(g_o).max() and np.linalg.norm(gs - g_o) < 5e-3 * np.linalg.norm(g_o), name
+    x = np.random.default_rng(0).uniform(-0.1, 1.1, size=(256, 3))
+    v, g, H = osc.sdf._taps(torch.from_numpy(x), 2)
+    v2, _, g2, _, H2 = sdf.eval_all(x)
+    assert (v2.cpu().double() - v).abs().max() < 2e-6 and (g2.cpu().double() - g).abs().max() < 2e-5
+    assert (H2.cpu().double() - H).abs().max() < 1e-5 * max(1.0, H.abs().max().item())

@@ -177,3 +177,53 @@ def test_antithetic_sampling_parity():
     for world in (2, 3):
         parts = sum(hs.forward(3, spp, False, r, world)[0] for r in range(world))
         assert np.abs(parts - whole).max() < 2e-5
+
+
+def _affine():
+    """A general affine sdf_to_world: two rotations, anisotropic scale, shift about the cube centre."""
+    def rot(ax, a):
+        c, s = np.cos(a), np.sin(a)
+        R = np.eye(3)
+        i, j = [(1, 2), (0, 2), (0, 1)][ax]
+        R[i, i] = R[j, j] = c
+        R[i, j], R[j, i] = -s, s
+        return R
+    M = np.eye(4)
+    L = rot(1, 0.4) @ rot(0, -0.3) @ np.diag([1.1, 0.9, 1.2])
+    M[:3, :3] = L
+    M[:3, 3] = np.array([0.5, 0.5, 0.5]) - L @ np.array([0.5, 0.5, 0.5]) + np.array([0.03, -0.02, 0.04])
+    return M
+
+
+@pytest.mark.parametrize('kind,integ', [('knot', 'sdf_direct_reparam'), ('blobs', 'sdf_silhouette_reparam')])
+def test_sdf_to_world_transform_parity(kind, integ):
+    """Grid3d(data, transform) / prop sdf_to_world (python/shapes.py:378-448): lookups through to_local, gradient / Hessian
+    pulled back with to_local^T, bounding box = AABB of the transformed cube, scatter in grid space."""
+    W, spp, M = 16, 4, _affine()
+    sc = O.make_scene(kind, res=32, width=W, height=W)
+    sc.sdf = O.Grid3d(sc.sdf.data, to_world=M)
+    hs = HM.HostScene(sc.sdf.data.numpy(), sc.sensor.to_world, W, W, integrator=INTEG[integ], sdf_to_world=M)
+    hs.h.warp.kind, hs.h.warp.edge_eps, hs.h.warp.weight_strategy, hs.h.warp.clamping_thresh = 2, 0.01, 6, 0.05
+    hs.h.warp.normalize_warp_field, hs.h.warp.max_reparam_depth = 1, -1
+    wf = O.WarpField2D(sc.sdf, weight_strategy=6, edge_eps=0.01)
+    wf.clamping_thresh = 0.05
+    x = np.random.default_rng(0).uniform(-0.1, 1.1, size=(500, 3))
+    v, g, H = sc.sdf._taps(torch.from_numpy(x), 2)
+    out = hs.eval_sdf(x, 2)
+    assert np.abs(out[:, 0] - v.numpy()).max() < 2e-6 and np.abs(out[:, 1:4] - g.numpy()).max() < 2e-5
+    Hh = np.stack([out[:, 4], out[:, 7], out[:, 8], out[:, 7], out[:, 5], out[:, 9], out[:, 8], out[:, 9], out[:, 6]], -1).reshape(-1, 3, 3)
+    assert np.abs(Hh - H.numpy()).max() < 1e-5 * max(1.0, H.abs().max().item())
+    lo, hi = sc.sdf.bbox()
+    assert (hi - lo).min() > 1.1          # the box really changed (rotated cube: AABB larger than 1.1)
+    with torch.no_grad():
+        img_o = O.render(sc, wf, integ, seed=3, spp=spp).numpy()
+    film, _, _ = hs.forward(3, spp, False)
+    assert np.abs(hs.develop(film) - img_o).max() < 2e-5
+    g_in = np.random.default_rng(5).uniform(-1, 1, size=(W, W, 3))
+    img2, g_o, gp_o, _ = O.render_backward(sc, wf, integ, torch.from_numpy(g_in), seed=11, spp=spp)
+    film, rec, _ = hs.forward(11, spp, True)
+    assert np.abs(hs.develop(film) - img2.numpy()).max() < 2e-5
+    g_h, _, gp_h, _ = hs.backward(11, spp, film, rec, g_in)
+    g_o = g_o.numpy()
+    assert np.abs(g_h - g_o).max() < 2e-2 * np.abs(g_o).max() and np.linalg.norm(g_h - g_o) < 5e-3 * np.linalg.norm(g_o)
+    assert np.abs(gp_h - gp_o.numpy()).max() < 1e-2 * max(1.0, np.abs(gp_o.numpy()).max())
