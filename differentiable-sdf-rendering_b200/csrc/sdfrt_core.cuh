@@ -126,6 +126,10 @@ struct ShadingParams {
     float Le[3];
     float env_dist;
     int hide_emitters;
+    // which interaction the shadow ray of sdf_direct_reparam is spawned from (python/integrators/sdf_direct_reparam.py:44-49):
+    // 0 = si (attached, default), 1 = detach(si) (`detach_indirect_si`), 2 = si_d0 (`decouple_reparam`: the interaction of the
+    // detached primary ray -- it still moves with the SDF, but not with the primary ray's warp)
+    int shadow_origin;
 };
 struct Counters {  // device work counters (unsigned long long for atomicAdd)
     unsigned long long n_rays, n_evals_value, n_evals_grad, n_evals_hess, n_scatter_sites, n_albedo_lookups,

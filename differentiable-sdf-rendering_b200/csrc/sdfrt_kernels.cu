@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(kBlock) k_backward(const __grid_constant__ Sce
         const WorkItem w = decode_item(ps, item);
         lane_backward(sc, ps, w.lane, film_adj, rec + item, rec_stride, tg, gp, sites, st);
     }
-    for (int q = 0; q < 3; ++q) {
+    for (int q = 0; q < 4; ++q) {
         const bool has = q < sites.n;
         unsigned rem = __ballot_sync(FULL, has);
         if (rem == 0u) break;
@@ -292,6 +292,7 @@ struct sdfrt_ctx {
     int rank = 0, world = 1;
     float to_world[16];      // Grid3d's transform (row-major) when has_xf
     bool has_xf = false;
+    int shadow_origin = 0;   // sdf_direct_reparam props detach_indirect_si (1) / decouple_reparam (2)
     int antithetic = 0;  // ReparamIntegrator.antithetic_sampling (python/integrators/reparam.py:19); not used by sdf_prb_reparam
     bool have_sdf = false;
     // adjoint state
@@ -802,6 +803,7 @@ int sdfrt_set_shading(sdfrt_ctx* ctx, const sdfrt_shading* s) {
     if (!ctx || !s) return SDFRT_ERR_INVALID;
     ctx->shading_pub = *s;
     ctx->sc.Sh = make_shading(*s);
+    ctx->sc.Sh.shadow_origin = ctx->shadow_origin;
     ctx->sc.A.cr = s->albedo[0]; ctx->sc.A.cg = s->albedo[1]; ctx->sc.A.cb = s->albedo[2];
     ctx->adj_ready = false;
     return SDFRT_OK;
@@ -831,6 +833,15 @@ int sdfrt_set_sdf_transform(sdfrt_ctx* ctx, const float* to_world) {
     ctx->sc.T = T;
     ctx->has_xf = to_world != nullptr;
     if (to_world) std::memcpy(ctx->to_world, to_world, sizeof(ctx->to_world));
+    ctx->adj_ready = false;
+    return SDFRT_OK;
+}
+
+int sdfrt_set_shadow_origin(sdfrt_ctx* ctx, int mode) {
+    if (!ctx) return SDFRT_ERR_INVALID;
+    if (mode < 0 || mode > 2) return fail(ctx, SDFRT_ERR_INVALID, "shadow origin mode must be 0 (si), 1 (detach_indirect_si) or 2 (decouple_reparam)");
+    ctx->shadow_origin = mode;
+    ctx->sc.Sh.shadow_origin = mode;
     ctx->adj_ready = false;
     return SDFRT_OK;
 }

@@ -328,7 +328,7 @@ struct Site {
 };
 struct SiteList {
     int n;
-    Site s[3];
+    Site s[4];  // shadow warp site, (decouple_reparam: detached-ray interaction), surface interaction, primary warp site
 };
 SDFRT_HD void push_site(SiteList& L, V3 x, float phi_hat, V3 g_hat) {
     L.s[L.n].x = x; L.s[L.n].phi_hat = phi_hat; L.s[L.n].g_hat = g_hat;
@@ -500,8 +500,17 @@ SDFRT_HD void lane_backward(const SceneParams& sc, const PassParams& ps, unsigne
                     push_site(sites, sr.o + tau * sr.d, phi_hat, g_hat);
                     st.n_sites += 1;
                     const V3 os_hat = phi_hat * ws.g + mul(ws.H, g_hat);
-                    p_hat += os_hat;
                     grad_p = grad_p - os_hat;
+                    if (sc.Sh.shadow_origin == 0) {
+                        p_hat += os_hat;                       // spawned from the attached si
+                    } else if (sc.Sh.shadow_origin == 2) {     // si_d0: p0 = ray0(t~), t~ = t <- phi(p) / detach(g . -d0); no path to d
+                        const float phi0_hat = dot(os_hat, d0) / (-dot(g_p, d0));
+                        if (isfinite(phi0_hat)) {
+                            push_site(sites, p, phi0_hat, v3(0.f));
+                            st.n_sites += 1;
+                            grad_p = grad_p - phi0_hat * g_p;
+                        }
+                    }                                          // 1: detach(si) -- the origin carries no derivative
                 }
             }
         }

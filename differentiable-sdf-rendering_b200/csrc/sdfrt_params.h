@@ -137,6 +137,7 @@ inline ShadingParams make_shading(const sdfrt_shading& s) {
     for (int i = 0; i < 3; ++i) o.Le[i] = s.env_radiance[i];
     o.env_dist = s.env_dist;
     o.hide_emitters = s.hide_emitters;
+    o.shadow_origin = 0;
     return o;
 }
 inline PassParams make_pass(const SensorParams& S, uint32_t seed, int spp, int rank, int world, int antithetic = 0) {

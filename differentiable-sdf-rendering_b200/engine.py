@@ -120,6 +120,9 @@ class Context:
     def set_antithetic(self, enable):
         check(self.ctx, self.lib.sdfrt_set_antithetic(self.ctx, int(bool(enable))))
 
+    def set_shadow_origin(self, mode):
+        check(self.ctx, self.lib.sdfrt_set_shadow_origin(self.ctx, int(mode)))
+
     def set_prb(self, max_depth=4, rr_depth=5):
         p = _capi.PrbParams(int(max_depth), int(rr_depth))
         check(self.ctx, self.lib.sdfrt_set_prb(self.ctx, C.byref(p)))

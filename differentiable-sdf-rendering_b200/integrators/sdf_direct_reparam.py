@@ -1,4 +1,4 @@
-from .reparam import ReparamIntegrator
+from .reparam import ReparamIntegrator, Properties
 
 
 class SdfDirectReparamIntegrator(ReparamIntegrator):
@@ -7,6 +7,12 @@ class SdfDirectReparamIntegrator(ReparamIntegrator):
 
     def __init__(self, props=None, sdf=None):
         super().__init__(props, sdf)
-        props = props or {}
-        if props.get('detach_indirect_si', False) or props.get('decouple_reparam', False):
-            raise NotImplementedError("detach_indirect_si / decouple_reparam variants are not provided")
+        props = Properties(props or {})
+        self.detach_indirect_si = props.get('detach_indirect_si', False)   # :13
+        self.decouple_reparam = props.get('decouple_reparam', False)       # :14
+
+    def _bind(self, scene, sensor):
+        ctx = super()._bind(scene, sensor)
+        # :44-49: which interaction the shadow ray is spawned from (detach_indirect_si wins, as the if/elif there)
+        ctx.set_shadow_origin(1 if self.detach_indirect_si else (2 if self.decouple_reparam else 0))
+        return ctx

@@ -136,6 +136,9 @@ int sdfrt_set_integrator(sdfrt_ctx* ctx, int integrator);         /* SDFRT_INTEG
  * every wavefront lane is evaluated twice, the second time at the mirrored film position with a clone of the sampler.
  * Applies to the three ReparamIntegrator.render-based integrators; sdf_prb_reparam has its own render without it. */
 int sdfrt_set_antithetic(sdfrt_ctx* ctx, int enable);
+/* props `detach_indirect_si` / `decouple_reparam` of sdf_direct_reparam (python/integrators/sdf_direct_reparam.py:13-14,44-49): the
+ * interaction the shadow ray is spawned from -- 0 = si (default), 1 = detach(si), 2 = si_d0 (interaction of the detached primary ray) */
+int sdfrt_set_shadow_origin(sdfrt_ctx* ctx, int mode);
 void sdfrt_prb_defaults(sdfrt_prb_params* p);
 int sdfrt_set_prb(sdfrt_ctx* ctx, const sdfrt_prb_params* p);      /* used when the integrator is SDFRT_INTEGRATOR_PRB */
 /* multi-GPU ray partition: the film rows (border included) are cut into bands of 8 rows; this context renders the

@@ -748,6 +748,8 @@ class Scene:
     albedo_grid: torch.Tensor = None          # optional (Z,Y,X,3) trilinear gridvolume on [0,1]^3
     env_dist: float = 2.0 * math.sqrt(3.0)    # constant emitter: 2 * scene bsphere radius (unit cube + margin)
     hide_emitters: bool = False
+    detach_indirect_si: bool = False          # sdf_direct_reparam props (python/integrators/sdf_direct_reparam.py:13-14,44-49)
+    decouple_reparam: bool = False
 
 
 def eval_albedo(scene, p):
@@ -845,7 +847,13 @@ def sample_direct(scene, warp_field, sampler, o, d, maxt, reparam_mode):
         mag = (1 + p.detach().abs().max(-1).values) * RAY_EPSILON
         sgn = dr_sign(dot(n.detach(), ds_p - p.detach()))
         off = (mag * sgn)[:, None] * n.detach()
-    o_s = p + off
+    if scene.detach_indirect_si:      # shadow_ray = si_d.spawn_ray_to(ds.p), si_d = detach(si) (:44-45)
+        o_s = p.detach() + off
+    elif scene.decouple_reparam:      # shadow_ray = si_d0.spawn_ray_to(ds.p): interaction of the detached ray (:46-47, python/warp.py:121)
+        si0 = sdf.compute_surface_interaction(o[h].detach(), d[h].detach(), its_t[h])
+        o_s = si0['p'] + off
+    else:
+        o_s = p + off
     dvec = ds_p - o_s
     dist = torch.linalg.norm(dvec, dim=-1)
     d_s = (dvec / dist[:, None]).detach()  # shadow_ray.d = detach(shadow_ray.d) (:51)

@@ -22,6 +22,7 @@ struct hh_scene {
     int antithetic;   // ReparamIntegrator.antithetic_sampling (hh_forward / hh_backward / hh_local_lanes)
     int has_transform;   // Grid3d(data, transform): row-major 4x4 to_world
     float to_world[16];
+    int shadow_origin;   // sdf_direct_reparam: 0 si, 1 detach_indirect_si, 2 decouple_reparam
 };
 
 static SceneParams build(const hh_scene* h) {
@@ -35,6 +36,7 @@ static SceneParams build(const hh_scene* h) {
     sc.W = make_warp(h->warp);
     sc.S = make_sensor(h->sensor);
     sc.Sh = make_shading(h->shading);
+    sc.Sh.shadow_origin = h->shadow_origin;
     sc.integrator = h->integrator;
     sc.prb = make_prb(h->prb);
     set_grid_transform(sc.G, sc.T, h->has_transform ? h->to_world : nullptr);

@@ -379,3 +379,24 @@ def test_sdf_to_world_transform_against_oracle(sdfrt_mod):
     v2, _, g2, _, H2 = sdf.eval_all(x)
     assert (v2.cpu().double() - v).abs().max() < 2e-6 and (g2.cpu().double() - g).abs().max() < 2e-5
     assert (H2.cpu().double() - H).abs().max() < 1e-5 * max(1.0, H.abs().max().item())
+
+
+@pytest.mark.parametrize('prop', ['detach_indirect_si', 'decouple_reparam'])
+def test_direct_integrator_shadow_origin_variants(sdfrt_mod, prop):
+    from oracle import sdf_oracle as O
+    W, spp = 16, 4
+    osc = O.make_scene('knot', res=32, width=W, height=W)
+    setattr(osc, prop, True)
+    owf = O.WarpField2D(osc.sdf, weight_strategy=6, edge_eps=0.01)
+    owf.clamping_thresh = 0.05
+    sdf = sdfrt_mod.Grid3d(osc.sdf.data.float().numpy(), device=0)
+    integ = sdfrt_mod.integrators.create('sdf_direct_reparam', {prop: True}, sdf=sdf)
+    wf = sdfrt_mod.WarpField2D(sdf, weight_strategy=6, edge_eps=0.01)
+    wf.clamping_thresh = 0.05
+    integ.warp_field = wf
+    scene = sdfrt_mod.Scene(integ, [sdfrt_mod.Sensor(osc.sensor.to_world, W, W)])
+    g_in = np.random.default_rng(5).uniform(-1, 1, size=(W, W, 3))
+    g_o = O.render_backward(osc, owf, 'sdf_direct_reparam', torch.from_numpy(g_in), seed=11, spp=spp)[1].numpy()
+    integ.render_backward(scene, None, torch.from_numpy(g_in).float().cuda(), sensor=0, seed=11, spp=spp)
+    gs = sdf.data.grad[..., 0].cpu().numpy()
+    assert np.abs(gs - g_o).max() < 2e-2 * np.abs(g_o).max() and np.linalg.norm(gs - g_o) < 5e-3 * np.linalg.norm(g_o)

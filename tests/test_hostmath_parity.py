@@ -227,3 +227,20 @@ def test_sdf_to_world_transform_parity(kind, integ):
     g_o = g_o.numpy()
     assert np.abs(g_h - g_o).max() < 2e-2 * np.abs(g_o).max() and np.linalg.norm(g_h - g_o) < 5e-3 * np.linalg.norm(g_o)
     assert np.abs(gp_h - gp_o.numpy()).max() < 1e-2 * max(1.0, np.abs(gp_o.numpy()).max())
+
+
+@pytest.mark.parametrize('mode', [1, 2], ids=['detach_indirect_si', 'decouple_reparam'])
+def test_direct_integrator_shadow_origin_variants(mode):
+    """props detach_indirect_si / decouple_reparam (python/integrators/sdf_direct_reparam.py:13-14,44-49): the interaction the
+    shadow ray is spawned from.  Same image, different gradient (the variants differ by 20-80 % of ||g||_inf on this scene)."""
+    W, spp = 16, 4
+    sc, wf, hs = make_pair('knot', 32, W, 'sdf_direct_reparam')
+    g_in = np.random.default_rng(5).uniform(-1, 1, size=(W, W, 3))
+    g_default = O.render_backward(sc, wf, 'sdf_direct_reparam', torch.from_numpy(g_in), seed=11, spp=spp)[1].numpy()
+    sc.detach_indirect_si, sc.decouple_reparam = mode == 1, mode == 2
+    hs.h.shadow_origin = mode
+    g_o = O.render_backward(sc, wf, 'sdf_direct_reparam', torch.from_numpy(g_in), seed=11, spp=spp)[1].numpy()
+    film, rec, _ = hs.forward(11, spp, True)
+    g_h = hs.backward(11, spp, film, rec, g_in)[0]
+    assert np.abs(g_o - g_default).max() > 0.1 * np.abs(g_default).max()
+    assert np.abs(g_h - g_o).max() < 2e-2 * np.abs(g_o).max() and np.linalg.norm(g_h - g_o) < 5e-3 * np.linalg.norm(g_o)
