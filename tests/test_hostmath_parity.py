@@ -244,3 +244,30 @@ def test_direct_integrator_shadow_origin_variants(mode):
     g_h = hs.backward(11, spp, film, rec, g_in)[0]
     assert np.abs(g_o - g_default).max() > 0.1 * np.abs(g_default).max()
     assert np.abs(g_h - g_o).max() < 2e-2 * np.abs(g_o).max() and np.linalg.norm(g_h - g_o) < 5e-3 * np.linalg.norm(g_o)
+
+
+def test_evaluation_counts_match_the_oracle():
+    """the device counters are the basis of the algorithmic-bytes figure; they must equal the oracle's count of
+    64-tap evaluations for the same seeds (that equality is the proof the kernel did the work).  Primal silhouette render
+    without a warp field: value-only marches + refinement, nothing else -- equal up to the handful of rays whose step count
+    differs between the fp32 kernel and the fp64 oracle.  (With a WarpField2D the reference's silhouette integrator evaluates the
+    value-free warp even in primal mode; the kernels only evaluate it in the adjoint -- ref_semantics.md.)  Direct integrator: the kernel skips the shadow march of samples whose BSDF gate is closed
+    (oracle/ref_semantics.md, "deliberate evaluation-count deviations"), so it may only be lower, and not by much."""
+    W, spp = 24, 4
+    sc, wf, hs = make_pair('knot', 32, W, 'sdf_silhouette_reparam')
+    sc.sdf.n_evals = 0
+    with torch.no_grad():
+        O.render(sc, None, 'sdf_silhouette_reparam', seed=3, spp=spp)
+    n_oracle = sc.sdf.n_evals
+    _, _, st = hs.forward(3, spp, False)
+    n_kernel = int(st[1] + st[2] + st[3])
+    assert n_oracle > 10000 and abs(n_kernel - n_oracle) <= 2e-3 * n_oracle, (n_kernel, n_oracle)
+    sc, wf, hs = make_pair('knot', 32, W, 'sdf_direct_reparam')
+    sc.sdf.n_evals = 0
+    with torch.no_grad():
+        O.render(sc, wf, 'sdf_direct_reparam', seed=3, spp=spp)
+    n_oracle = sc.sdf.n_evals
+    _, _, st = hs.forward(3, spp, False)
+    n_kernel = int(st[1] + st[2] + st[3])
+    # oracle: primary march + refine, 2 lookups per hit (compute_surface_interaction), every shadow ray marched
+    assert 0.75 * n_oracle < n_kernel <= n_oracle, (n_kernel, n_oracle)
