@@ -203,13 +203,17 @@ __global__ void k_eval_sdf(GridView G, const float* __restrict__ x, int n, int o
 //   k_prb_primal    L per sample -> warp-cooperative film splat; optionally stores L (the state_in of the replay)
 //   k_prb_backward  replays the path with delta_L from the film adjoint and scatters the vertex adjoints
 // ---------------------------------------------------------------------------------------------------------------
+// items [item0, item0 + cnt); `its` (or nullptr): hit distance of the camera ray per item of this range, from the wavefront marcher;
+// L_rec (or nullptr): rows of `rec_stride` floats, already offset to item0
 __global__ void __launch_bounds__(kBlock) k_prb_primal(const __grid_constant__ SceneParams sc, const __grid_constant__ PassParams ps,
+                                                        unsigned long long item0, unsigned long long cnt, const float* __restrict__ its,
                                                         float* __restrict__ film, float* __restrict__ L_rec, unsigned long long rec_stride,
                                                         Counters* counters) {
     __shared__ SplatSmem s_splat[kBlock / 32];
     const int lane_id = threadIdx.x & 31;
-    const unsigned long long item = (unsigned long long)blockIdx.x * kBlock + threadIdx.x;
-    const bool valid = item < ps.n_items;
+    const unsigned long long idx = (unsigned long long)blockIdx.x * kBlock + threadIdx.x;
+    const unsigned long long item = item0 + idx;
+    const bool valid = idx < cnt;
     LaneStats st = {0, 0, 0, 0, 0, 0, 0};
     V3 L = v3(0.f);
     float pfx = 0.f, pfy = 0.f;
@@ -217,9 +221,11 @@ __global__ void __launch_bounds__(kBlock) k_prb_primal(const __grid_constant__ S
         const WorkItem w = decode_item(ps, item);
         NoEmit ne;
         V3 gp = v3(0.f);
-        L = lane_prb<false>(sc, ps, w.lane, nullptr, v3(0.f), ne, gp, st);
+        PrbPrimary pre;
+        if (its) { pre.its_t = its[idx]; pre.tr.warp_t = INFINITY; }
+        L = lane_prb<false>(sc, ps, w.lane, nullptr, v3(0.f), ne, gp, st, its ? &pre : nullptr);
         if (L_rec) {
-            L_rec[item] = L.x; L_rec[item + rec_stride] = L.y; L_rec[item + 2 * rec_stride] = L.z;
+            L_rec[idx] = L.x; L_rec[idx + rec_stride] = L.y; L_rec[idx + 2 * rec_stride] = L.z;
         }
         // sample position of the splat: the (un-reparameterised) jittered pixel position re-projected (render(), :54-76)
         Pcg32 rng = sampler_seed(ps.seed, (uint32_t)w.lane);
@@ -243,6 +249,7 @@ __global__ void __launch_bounds__(kBlock) k_prb_primal(const __grid_constant__ S
 template <int MIN_BLOCKS>  // resident blocks per SM the register allocation is tuned for (2: 255 registers, 3: 168)
 __global__ void __launch_bounds__(kBlock, MIN_BLOCKS) k_prb_backward(const __grid_constant__ SceneParams sc, const __grid_constant__ PassParams ps,
                                                           const float* __restrict__ film_adj, const float* __restrict__ L_rec,
+                                                          const float* __restrict__ prim_rec /* rows REC_ITS_T.. of the lane records, or nullptr */,
                                                           unsigned long long rec_stride, BackwardTargets tg, float* grad_p, Counters* counters) {
     const int lane_id = threadIdx.x & 31;
     const unsigned long long item = (unsigned long long)blockIdx.x * kBlock + threadIdx.x;
@@ -252,7 +259,18 @@ __global__ void __launch_bounds__(kBlock, MIN_BLOCKS) k_prb_backward(const __gri
         const WorkItem w = decode_item(ps, item);
         const V3 L = V3{L_rec[item], L_rec[item + rec_stride], L_rec[item + 2 * rec_stride]};
         DirectEmit em{tg.grad_sdf, tg.grad_albedo, sc.G};
-        (void)lane_prb<true>(sc, ps, w.lane, film_adj, L, em, gp, st);
+        PrbPrimary pre;
+        if (prim_rec) {
+            const float* r = prim_rec + item;
+            pre.its_t = r[REC_ITS_T * rec_stride];
+            pre.tr.its_t = pre.its_t;
+            pre.tr.warp_t = r[REC_TAU * rec_stride];
+            pre.tr.warp_t_d = V3{r[REC_TAU_DX * rec_stride], r[REC_TAU_DY * rec_stride], r[REC_TAU_DZ * rec_stride]};
+            pre.tr.warp_weight = r[REC_OMEGA * rec_stride];
+            pre.tr.warp_weight_d = V3{r[REC_OMEGA_DX * rec_stride], r[REC_OMEGA_DY * rec_stride], r[REC_OMEGA_DZ * rec_stride]};
+            pre.tr.n_steps = 0;
+        }
+        (void)lane_prb<true>(sc, ps, w.lane, film_adj, L, em, gp, st, prim_rec ? &pre : nullptr);
     }
     const unsigned nvv = warp_sum(st.n_value), h = warp_sum(st.n_hess), nsites = warp_sum(st.n_sites), al = warp_sum(st.n_albedo),
                    ng = warp_sum(st.n_grad);
@@ -339,6 +357,7 @@ struct sdfrt_ctx {
     size_t rows4_n = 0;
     int rows4_roles = -1, march_role = 0;
     bool rows4_on = false;
+    bool prb_primary_wavefront = true;       // camera rays of sdf_prb_reparam through k_march (SDFRT_PRB_PRIMARY=0: per lane)
     int prb_min_blocks = 2;                  // register-allocation variant of k_prb_backward (SDFRT_PRB_OCC)
     int cache_mode[4] = {1, 1, 0, 1};        // tap-cache mode of [value primary, value shadow, diff primary, diff shadow]
     // buffers of the host entry point
@@ -475,6 +494,15 @@ int enqueue_batch(sdfrt_ctx* ctx, const Sweep& sw, unsigned long long item0, int
           launch_march_mode<false>(ctx, 0, need, bs, reinterpret_cast<const SegIn*>(sc.segs), nullptr, cnt, region, 1,
                                    DIFF ? rec_b : sc.its, nullptr, 0, work + WQ_PRIMARY_CHUNK); }
     const float* its = DIFF ? rec_b : sc.its;
+    if (ctx->sc.integrator == INTEGRATOR_PRB) {
+        // path replay integrator: the camera ray was marched above by the wavefront marcher (empty-space test included); the
+        // rest of the path is walked per sample.  The re-render of render_backward (DIFF) keeps L in rows 9..11 of the records.
+        LaunchScope ls(ctx, 2, bs);
+        k_prb_primal<<<(cnt + kBlock - 1) / kBlock, kBlock, 0, bs>>>(ctx->sc, ps, item0, (unsigned long long)cnt, its, film,
+                                                                      DIFF ? rec_b + (size_t)REC_S_STATE * ctx->rec_stride : nullptr, ctx->rec_stride, ctx->counters);
+        SDFRT_CUDA(ctx, cudaGetLastError());
+        return SDFRT_OK;
+    }
     { LaunchScope ls(ctx, 2, bs);
       k_shade<DIFF><<<regions, 256, 0, bs>>>(ctx->sc, ps, item0, cnt, region, reinterpret_cast<const SegIn*>(sc.segs), its, q, film,
                                              DIFF ? rec_b + REC_S_STATE * ctx->rec_stride : nullptr, ctx->counters); }
@@ -634,7 +662,7 @@ int run_prb_sweep(sdfrt_ctx* ctx, const PassParams& ps, float* film, float* L_re
         return fail(ctx, SDFRT_ERR_INVALID, "film row band exceeds 2^32 samples");
     const unsigned long long blocks = (ps.n_items + kBlock - 1) / kBlock;
     if (blocks > 0x7fffffffull) return fail(ctx, SDFRT_ERR_INVALID, "too many samples for one launch");
-    { LaunchScope ls(ctx, 1, st); k_prb_primal<<<(unsigned)blocks, kBlock, 0, st>>>(ctx->sc, ps, film, L_rec, rec_stride, ctx->counters); }
+    { LaunchScope ls(ctx, 1, st); k_prb_primal<<<(unsigned)blocks, kBlock, 0, st>>>(ctx->sc, ps, 0ull, ps.n_items, nullptr, film, L_rec, rec_stride, ctx->counters); }
     SDFRT_CUDA(ctx, cudaGetLastError());
     return SDFRT_OK;
 }
@@ -698,6 +726,7 @@ sdfrt_ctx* sdfrt_create(int device, int* status) {
     if (const char* e = std::getenv("SDFRT_SLOTS")) ctx->max_slots = std::max(1, std::min(kSlots, std::atoi(e)));          // developer overrides
     if (const char* e = std::getenv("SDFRT_MIN_LIVE")) ctx->min_live = std::max(1, std::min(32, std::atoi(e)));
     if (const char* e = std::getenv("SDFRT_PRB_OCC")) ctx->prb_min_blocks = std::atoi(e);
+    if (const char* e = std::getenv("SDFRT_PRB_PRIMARY")) ctx->prb_primary_wavefront = std::atoi(e) != 0;
     if (const char* e = std::getenv("SDFRT_SKIP_EMPTY")) ctx->skip_empty = std::atoi(e) != 0;
     if (const char* e = std::getenv("SDFRT_BATCH_LOG2")) ctx->batch_target = 1ull << std::max(16, std::min(28, std::atoi(e)));
     for (int i = 0; i < kSlots; ++i) {
@@ -890,11 +919,12 @@ int sdfrt_render_primal(sdfrt_ctx* ctx, uint32_t seed, int spp, float* film_accu
     int rc = check_ready(ctx, spp);
     if (rc) return rc;
     if (!film_accum) return fail(ctx, SDFRT_ERR_INVALID, "film_accum is null");
-    if (ctx->sc.integrator == INTEGRATOR_PRB)
+    const bool prb = ctx->sc.integrator == INTEGRATOR_PRB;
+    if (prb && !ctx->prb_primary_wavefront)
         return run_prb_sweep(ctx, make_pass(ctx->sc.S, seed, spp, ctx->rank, ctx->world), film_accum, nullptr, 0, (cudaStream_t)stream);
     Sweep sw;
     sw.diff = false;
-    sw.ps = make_pass(ctx->sc.S, seed, spp, ctx->rank, ctx->world, ctx->antithetic);
+    sw.ps = make_pass(ctx->sc.S, seed, spp, ctx->rank, ctx->world, prb ? 0 : ctx->antithetic);
     sw.film = film_accum;
     return run_sweeps(ctx, &sw, 1, (cudaStream_t)stream);
 }
@@ -921,8 +951,8 @@ int sdfrt_adjoint_accumulate(sdfrt_ctx* ctx, uint32_t seed_grad, int spp_grad, f
     rc = ensure(ctx, &ctx->rec, &ctx->rec_capacity, (size_t)sw.ps.n_items * REC_COUNT + 1);
     if (rc) return rc;
     ctx->rec_stride = sw.ps.n_items;
-    if (ctx->sc.integrator == INTEGRATOR_PRB)  // re-render of render_backward (:204-206); rows 0..2 of the records keep L
-        rc = run_prb_sweep(ctx, sw.ps, film_accum, ctx->rec, ctx->rec_stride, (cudaStream_t)stream);
+    if (ctx->sc.integrator == INTEGRATOR_PRB && !ctx->prb_primary_wavefront)  // re-render of render_backward (:204-206), keeps L per sample
+        rc = run_prb_sweep(ctx, sw.ps, film_accum, ctx->rec + (size_t)REC_S_STATE * ctx->rec_stride, ctx->rec_stride, (cudaStream_t)stream);
     else
         rc = run_sweeps(ctx, &sw, 1, (cudaStream_t)stream);
     if (rc) return rc;
@@ -949,9 +979,9 @@ int sdfrt_render_view(sdfrt_ctx* ctx, uint32_t seed, int spp, float* film_primal
     rc = ensure(ctx, &ctx->rec, &ctx->rec_capacity, (size_t)sw[1].ps.n_items * REC_COUNT + 1);
     if (rc) return rc;
     ctx->rec_stride = sw[1].ps.n_items;
-    if (ctx->sc.integrator == INTEGRATOR_PRB) {
+    if (ctx->sc.integrator == INTEGRATOR_PRB && !ctx->prb_primary_wavefront) {
         rc = run_prb_sweep(ctx, sw[0].ps, film_primal, nullptr, 0, (cudaStream_t)stream);
-        if (!rc) rc = run_prb_sweep(ctx, sw[1].ps, film_adjoint, ctx->rec, ctx->rec_stride, (cudaStream_t)stream);
+        if (!rc) rc = run_prb_sweep(ctx, sw[1].ps, film_adjoint, ctx->rec + (size_t)REC_S_STATE * ctx->rec_stride, ctx->rec_stride, (cudaStream_t)stream);
     } else {
         rc = run_sweeps(ctx, sw, 2, (cudaStream_t)stream);
     }
@@ -983,10 +1013,12 @@ int sdfrt_adjoint_backprop(sdfrt_ctx* ctx, const float* film_accum, const float*
     const unsigned long long blocks = (n + kBlock - 1) / kBlock;
     if (ctx->sc.integrator == INTEGRATOR_PRB) {
         LaunchScope ls(ctx, 6, st);
+        const float* L_rec = ctx->rec + (size_t)REC_S_STATE * ctx->rec_stride;   // rows 9..11: L of the re-render
+        const float* prim = ctx->prb_primary_wavefront ? ctx->rec : nullptr;     // rows 0..8: camera ray's march by k_march
         if (ctx->prb_min_blocks >= 3)
-            k_prb_backward<3><<<(unsigned)blocks, kBlock, 0, st>>>(ctx->sc, ps, ctx->film_adj, ctx->rec, ctx->rec_stride, tg, grad_p, ctx->counters);
+            k_prb_backward<3><<<(unsigned)blocks, kBlock, 0, st>>>(ctx->sc, ps, ctx->film_adj, L_rec, prim, ctx->rec_stride, tg, grad_p, ctx->counters);
         else
-            k_prb_backward<2><<<(unsigned)blocks, kBlock, 0, st>>>(ctx->sc, ps, ctx->film_adj, ctx->rec, ctx->rec_stride, tg, grad_p, ctx->counters);
+            k_prb_backward<2><<<(unsigned)blocks, kBlock, 0, st>>>(ctx->sc, ps, ctx->film_adj, L_rec, prim, ctx->rec_stride, tg, grad_p, ctx->counters);
     } else {
         LaunchScope ls(ctx, 6, st);
         k_backward<<<(unsigned)blocks, kBlock, 0, st>>>(ctx->sc, ps, ctx->film_adj, ctx->rec, ctx->rec_stride, tg, grad_p, ctx->counters);

@@ -144,9 +144,16 @@ SDFRT_HD void film_gather(const SensorParams& S, const float* film_adj, float u,
     }
 }
 
+// Result of the camera ray's march when it was done by the wavefront marcher (k_march over the primary segments, with the
+// empty-space test): hit distance and, for the replay, the differentiable tracer's record.  nullptr = march here.
+struct PrbPrimary {
+    float its_t;
+    TraceOut tr;   // warp_t = inf if there is none
+};
+
 template <bool BWD, class Emit>
 SDFRT_HD V3 lane_prb(const SceneParams& sc, const PassParams& ps, unsigned long long lane, const float* film_adj, V3 L_total, Emit& emit,
-                     V3& grad_p, LaneStats& st) {
+                     V3& grad_p, LaneStats& st, const PrbPrimary* pre = nullptr) {
     const GridView& G = sc.G;
     const TracerParams& T = sc.T;
     const WarpParams& W = sc.W;
@@ -160,7 +167,9 @@ SDFRT_HD V3 lane_prb(const SceneParams& sc, const PassParams& ps, unsigned long 
 
     V3 o_cur = cs.o, d_cur = cs.d;
     float t_cur;
-    {   // ray_intersect_preliminary (:264)
+    if (pre != nullptr) {
+        t_cur = pre->its_t;
+    } else {  // ray_intersect_preliminary (:264)
         const ValueTrace vt = trace_value_sel<BWD>(G, T, o_cur, d_cur, cs.maxt, true);
         t_cur = vt.its_t; nsteps = vt.n_steps; nv += vt.n_evals;
     }
@@ -178,7 +187,9 @@ SDFRT_HD V3 lane_prb(const SceneParams& sc, const PassParams& ps, unsigned long 
     TraceOut tr0;
     tr0.warp_t = INFINITY; tr0.warp_t_d = v3(0.f); tr0.warp_weight = 0.f; tr0.warp_weight_d = v3(0.f);
     if (BWD) {
-        if (warp2d) {  // sample_rays with reparam (:499-511)
+        if (warp2d && pre != nullptr) {
+            tr0 = pre->tr;
+        } else if (warp2d) {  // sample_rays with reparam (:499-511)
             const DiffTrace dt = prb_trace_diff(G, T, o_cur, d_cur, cs.maxt);
             tr0 = dt.out; nh += dt.n_hess; nv += dt.n_value;
         }
