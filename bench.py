@@ -462,6 +462,30 @@ def run_gpu_prb(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     ms = tt.item()
     stats = ctx.stats(reset=True)
+    # e2e: host buffers in, host buffers out through the host entry point of the C ABI (N = 1 only)
+    e2e = None
+    if world == 1:
+        sdf_h = sdf.cpu().pin_memory()
+        img_h = torch.empty((H, W, 3)).pin_memory()
+        g_h = torch.empty((R, R, R)).pin_memory()
+        ctx.render_view_host(sdf_h, 0, spp * mult, 1 + nsens, spp, None, img_h, g_h)
+        torch.cuda.synchronize(dev)
+        e_steps = max(1, min(args.steps, 3))
+        tw = time.perf_counter()
+        for s in range(e_steps):
+            ctx.render_view_host(sdf_h, 1000 + s, spp * mult, 1001 + s + nsens, spp, None, img_h, g_h)
+        tw = time.perf_counter() - tw
+        ctx.set_sdf(sdf)
+        e2e = {"value": rays_per_step * e_steps / tw / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": sdf_h.numel() * 4,
+               "d2h_bytes_per_step": img_h.numel() * 4 + g_h.numel() * 4, "steps": e_steps, "api": "sdfrt_render_view_host"}
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = len(os.sched_getaffinity(0))
+        os.environ.setdefault('OMP_NUM_THREADS', str(cores))
+        n, r = cpu_calibrated_sample(args.workload, 12.0)
+        cpu_baseline = {"value": r['rays'] / r['seconds'] / 1e6, "unit": "Mrays/s", "cores": r['threads'], "kind": "port",
+                        "sample": f"{n} primal + {max(spp, n // mult)} adjoint lanes from the wavefront centre, {r['seconds']:.1f} s; "
+                                  "compiled CPU port (g++ -O3 -fopenmp) of the restated sdf_prb_reparam"}
     if rank == 0:
         evals = (stats['n_evals_value'] + stats['n_evals_grad'] + stats['n_evals_hess'] + stats['n_evals_adjoint']) / args.steps
         line = {"metric": METRIC, "value": rays_per_step * args.steps / (ms * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world,
@@ -471,7 +495,7 @@ def run_gpu_prb(args):
                            "film": [W, H], "spp_primal": spp * mult, "spp_adjoint": spp, "rays_per_step": rays_per_step,
                            "note": "camera samples counted as rays; every sample walks up to max_depth path segments plus "
                                    "their shadow rays (see evals_per_step)"},
-                "clocks": clk.summary(), "gpu_launches": int(stats['n_launches']), "evals_per_step": evals,
+                "clocks": clk.summary(), "e2e": e2e, "cpu_baseline": cpu_baseline, "gpu_launches": int(stats['n_launches']), "evals_per_step": evals,
                 "fetch_GBps": 256.0 * evals / (ms / args.steps * 1e-3) / 1e9,
                 "stats_per_step": {k: v / args.steps for k, v in stats.items()}}
         print(json.dumps(line))
