@@ -207,6 +207,7 @@ __global__ void k_eval_sdf(GridView G, const float* __restrict__ x, int n, int o
 // L_rec (or nullptr): rows of `rec_stride` floats, already offset to item0
 __global__ void __launch_bounds__(kBlock) k_prb_primal(const __grid_constant__ SceneParams sc, const __grid_constant__ PassParams ps,
                                                         unsigned long long item0, unsigned long long cnt, const float* __restrict__ its,
+                                                        PrbRecords recs /* wavefront form: records of all segments, offset to item0 */,
                                                         float* __restrict__ film, float* __restrict__ L_rec, unsigned long long rec_stride,
                                                         Counters* counters) {
     __shared__ SplatSmem s_splat[kBlock / 32];
@@ -223,7 +224,9 @@ __global__ void __launch_bounds__(kBlock) k_prb_primal(const __grid_constant__ S
         V3 gp = v3(0.f);
         PrbPrimary pre;
         if (its) { pre.its_t = its[idx]; pre.tr.warp_t = INFINITY; }
-        L = lane_prb<false>(sc, ps, w.lane, nullptr, v3(0.f), ne, gp, st, its ? &pre : nullptr);
+        PrbRecords my = recs;
+        if (my.base) my.base += idx;
+        L = lane_prb<false>(sc, ps, w.lane, nullptr, v3(0.f), ne, gp, st, its ? &pre : nullptr, my);
         if (L_rec) {
             L_rec[idx] = L.x; L_rec[idx + rec_stride] = L.y; L_rec[idx + 2 * rec_stride] = L.z;
         }
@@ -246,10 +249,36 @@ __global__ void __launch_bounds__(kBlock) k_prb_primal(const __grid_constant__ S
     }
 }
 
+// Wavefront form, segment generator of bounce `k`: walks the path of every sample from the records of the marches done so far and
+// writes the two rays that leave vertex k -- emitter-sample shadow ray and BSDF-sampled continuation -- as segments for k_march
+// (inactive segments for samples whose path has ended or whose BSDF gate is closed).
+__global__ void __launch_bounds__(kBlock) k_prb_wf_emit(const __grid_constant__ SceneParams sc, const __grid_constant__ PassParams ps,
+                                                         unsigned long long item0, unsigned cnt, int k, PrbRecords recs,
+                                                         SegIn* __restrict__ next_segs, SegIn* __restrict__ shadow_segs) {
+    const unsigned idx = blockIdx.x * kBlock + threadIdx.x;
+    if (idx >= cnt) return;
+    const WorkItem w = decode_item(ps, item0 + idx);
+    PrbStop stop;
+    stop.stop_at = k; stop.shadow_active = false; stop.next_active = false;
+    stop.shadow_o = v3(0.f); stop.shadow_d = v3(0.f, 0.f, 1.f); stop.next_o = v3(0.f); stop.next_d = v3(0.f, 0.f, 1.f); stop.shadow_maxt = 0.f;
+    NoEmit ne;
+    V3 gp = v3(0.f);
+    LaneStats st = {0, 0, 0, 0, 0, 0, 0};
+    PrbRecords my = recs;
+    my.base += idx;
+    (void)lane_prb<false>(sc, ps, w.lane, nullptr, v3(0.f), ne, gp, st, nullptr, my, &stop);
+    SegIn dead;
+    dead.a = make_float4(0.f, 0.f, 0.f, 0.f);
+    dead.b = make_float4(0.f, 0.f, 1.f, -1.f);
+    shadow_segs[idx] = stop.shadow_active ? make_seg(sc.T, stop.shadow_o, stop.shadow_d, stop.shadow_maxt) : dead;
+    next_segs[idx] = stop.next_active ? make_seg(sc.T, stop.next_o, stop.next_d, INFINITY) : dead;
+}
+
 template <int MIN_BLOCKS>  // resident blocks per SM the register allocation is tuned for (2: 255 registers, 3: 168)
 __global__ void __launch_bounds__(kBlock, MIN_BLOCKS) k_prb_backward(const __grid_constant__ SceneParams sc, const __grid_constant__ PassParams ps,
                                                           const float* __restrict__ film_adj, const float* __restrict__ L_rec,
                                                           const float* __restrict__ prim_rec /* rows REC_ITS_T.. of the lane records, or nullptr */,
+                                                          PrbRecords recs /* wavefront form: no marching in the replay */,
                                                           unsigned long long rec_stride, BackwardTargets tg, float* grad_p, Counters* counters) {
     const int lane_id = threadIdx.x & 31;
     const unsigned long long item = (unsigned long long)blockIdx.x * kBlock + threadIdx.x;
@@ -270,7 +299,9 @@ __global__ void __launch_bounds__(kBlock, MIN_BLOCKS) k_prb_backward(const __gri
             pre.tr.warp_weight_d = V3{r[REC_OMEGA_DX * rec_stride], r[REC_OMEGA_DY * rec_stride], r[REC_OMEGA_DZ * rec_stride]};
             pre.tr.n_steps = 0;
         }
-        (void)lane_prb<true>(sc, ps, w.lane, film_adj, L, em, gp, st, prim_rec ? &pre : nullptr);
+        PrbRecords my = recs;
+        if (my.base) my.base += item;
+        (void)lane_prb<true>(sc, ps, w.lane, film_adj, L, em, gp, st, prim_rec ? &pre : nullptr, my);
     }
     const unsigned nvv = warp_sum(st.n_value), h = warp_sum(st.n_hess), nsites = warp_sum(st.n_sites), al = warp_sum(st.n_albedo),
                    ng = warp_sum(st.n_grad);
@@ -330,8 +361,8 @@ struct sdfrt_ctx {
     std::vector<cudaEvent_t> event_pool;
     // per-batch scratch of the wavefront pipeline
     struct Scratch {
-        float *segs = nullptr, *its = nullptr, *ssegs = nullptr, *sinfo = nullptr, *s_its = nullptr, *srec = nullptr, *scount = nullptr;
-        size_t segs_n = 0, its_n = 0, ssegs_n = 0, sinfo_n = 0, s_its_n = 0, srec_n = 0, scount_n = 0;
+        float *segs = nullptr, *its = nullptr, *ssegs = nullptr, *sinfo = nullptr, *s_its = nullptr, *srec = nullptr, *scount = nullptr, *prb_rec = nullptr;
+        size_t segs_n = 0, its_n = 0, ssegs_n = 0, sinfo_n = 0, s_its_n = 0, srec_n = 0, scount_n = 0, prb_rec_n = 0;
     } scratch[kSlots];            // one per pipeline slot
     cudaStream_t aux[kSlots] = {};   // batches rotate over internal streams so that the tail of one batch's persistent
     cudaEvent_t ev_fork = nullptr, ev_join[kSlots] = {};  // kernels overlaps the following batches
@@ -357,6 +388,9 @@ struct sdfrt_ctx {
     size_t rows4_n = 0;
     int rows4_roles = -1, march_role = 0;
     bool rows4_on = false;
+    bool prb_wavefront = false;              // sdf_prb_reparam bounce by bounce through k_march (SDFRT_PRB_WAVEFRONT=1)
+    float* prb_rec = nullptr;                // DIFF sweep: per-vertex march records [max_depth * 18][n_items]
+    size_t prb_rec_n = 0;
     bool prb_primary_wavefront = true;       // camera rays of sdf_prb_reparam through k_march (SDFRT_PRB_PRIMARY=0: per lane)
     int prb_min_blocks = 2;                  // register-allocation variant of k_prb_backward (SDFRT_PRB_OCC)
     int cache_mode[4] = {1, 1, 0, 1};        // tap-cache mode of [value primary, value shadow, diff primary, diff shadow]
@@ -485,20 +519,68 @@ int enqueue_batch(sdfrt_ctx* ctx, const Sweep& sw, unsigned long long item0, int
     { LaunchScope ls(ctx, 0, bs); k_gen_primary<<<blocks256, 256, 0, bs>>>(ctx->sc, ps, item0, cnt, reinterpret_cast<SegIn*>(sc.segs), sw.mask, ctx->counters); }
     // primary march (+ refine); DIFF writes its_t into row 0 of the lane records
     float* rec_b = DIFF ? ctx->rec + item0 : nullptr;
+    unsigned long long rec_stride = ctx->rec_stride;
+    float* its_out = sc.its;
+    // sdf_prb_reparam, wavefront form: every segment's march lands in the per-vertex records (PrbRecords layout)
+    const bool prb_wf = ctx->sc.integrator == INTEGRATOR_PRB && ctx->prb_wavefront;
+    PrbRecords prec{nullptr, 0, 9};
+    if (prb_wf) {
+        if (DIFF) { prec.base = ctx->prb_rec + item0; prec.stride = ps.n_items; prec.rows = 9; }
+        else { prec.base = sc.prb_rec; prec.stride = B; prec.rows = 1; }
+        rec_b = const_cast<float*>(prec.base);
+        rec_stride = prec.stride;
+        its_out = const_cast<float*>(prec.base);
+    }
     const unsigned need = (cnt + kMarchBlock - 1) / kMarchBlock;
     { LaunchScope ls(ctx, 1, bs);
       if (DIFF && reparam_at_depth(ctx->sc.W, 0))
           launch_march_mode<true>(ctx, 2, need, bs, reinterpret_cast<const SegIn*>(sc.segs), nullptr, cnt, region, 1,
-                                  nullptr, rec_b, ctx->rec_stride, work + WQ_PRIMARY_CHUNK);
+                                  nullptr, rec_b, rec_stride, work + WQ_PRIMARY_CHUNK);
       else  // value tracer; a DIFF pass without a primary warp (DummyWarpField / None) only needs its_t (record row 0)
           launch_march_mode<false>(ctx, 0, need, bs, reinterpret_cast<const SegIn*>(sc.segs), nullptr, cnt, region, 1,
-                                   DIFF ? rec_b : sc.its, nullptr, 0, work + WQ_PRIMARY_CHUNK); }
-    const float* its = DIFF ? rec_b : sc.its;
+                                   DIFF ? rec_b : its_out, nullptr, 0, work + WQ_PRIMARY_CHUNK); }
+    const float* its = DIFF ? rec_b : its_out;
+    if (prb_wf) {
+        // bounce by bounce: k_prb_wf_emit regenerates the path from the records and emits the rays leaving vertex k, k_march
+        // marches them (differentiable tracer where the replay will read a warp record), the final kernel walks the finished
+        // records once more for L and splats.  No per-sample path state is stored: the walk is arithmetic + one lookup per vertex.
+        const int max_depth = ctx->sc.prb.max_depth;
+        const bool warp2d = ctx->sc.W.kind == WARP_2D;
+        const int rmd = warp2d ? (ctx->sc.W.max_reparam_depth >= 0 ? ctx->sc.W.max_reparam_depth : 100000) : max_depth;
+        SegIn* nsegs = reinterpret_cast<SegIn*>(sc.segs);
+        SegIn* ssegs = reinterpret_cast<SegIn*>(sc.ssegs);
+        float* rb = const_cast<float*>(prec.base);
+        for (int k = 0; k < max_depth; ++k) {
+            { LaunchScope ls(ctx, 2, bs);
+              k_prb_wf_emit<<<(cnt + kBlock - 1) / kBlock, kBlock, 0, bs>>>(ctx->sc, ps, item0, cnt, k, prec, nsegs, ssegs); }
+            float* srec = rb + (size_t)((k * 2 + 1) * prec.rows) * prec.stride;
+            SDFRT_CUDA(ctx, cudaMemsetAsync(work, 0, WQ_COUNT * sizeof(unsigned), bs));
+            { LaunchScope ls(ctx, 3, bs);
+              if (DIFF && warp2d && reparam_at_depth(ctx->sc.W, 1) && k <= rmd)
+                  launch_march_mode<true>(ctx, 3, need, bs, ssegs, nullptr, cnt, region, 0, nullptr, srec, prec.stride, work + WQ_SHADOW_CHUNK);
+              else
+                  launch_march_mode<false>(ctx, 1, need, bs, ssegs, nullptr, cnt, region, 0, srec, nullptr, 0, work + WQ_SHADOW_CHUNK); }
+            if (k + 1 < max_depth) {
+                float* nrec = rb + (size_t)(((k + 1) * 2) * prec.rows) * prec.stride;
+                { LaunchScope ls(ctx, 1, bs);
+                  if (DIFF && warp2d && (k + 1) <= rmd)
+                      launch_march_mode<true>(ctx, 2, need, bs, nsegs, nullptr, cnt, region, 1, nullptr, nrec, prec.stride, work + WQ_PRIMARY_CHUNK);
+                  else
+                      launch_march_mode<false>(ctx, 0, need, bs, nsegs, nullptr, cnt, region, 1, nrec, nullptr, 0, work + WQ_PRIMARY_CHUNK); }
+            }
+        }
+        { LaunchScope ls(ctx, 4, bs);
+          k_prb_primal<<<(cnt + kBlock - 1) / kBlock, kBlock, 0, bs>>>(ctx->sc, ps, item0, (unsigned long long)cnt, nullptr, prec, film,
+                                                                        DIFF ? ctx->rec + item0 + (size_t)REC_S_STATE * ctx->rec_stride : nullptr,
+                                                                        ctx->rec_stride, ctx->counters); }
+        SDFRT_CUDA(ctx, cudaGetLastError());
+        return SDFRT_OK;
+    }
     if (ctx->sc.integrator == INTEGRATOR_PRB) {
-        // path replay integrator: the camera ray was marched above by the wavefront marcher (empty-space test included); the
-        // rest of the path is walked per sample.  The re-render of render_backward (DIFF) keeps L in rows 9..11 of the records.
+        // path replay integrator, per-lane form: the camera ray was marched above by the wavefront marcher (empty-space test
+        // included); the rest of the path is walked per sample.  The re-render of render_backward (DIFF) keeps L in rows 9..11.
         LaunchScope ls(ctx, 2, bs);
-        k_prb_primal<<<(cnt + kBlock - 1) / kBlock, kBlock, 0, bs>>>(ctx->sc, ps, item0, (unsigned long long)cnt, its, film,
+        k_prb_primal<<<(cnt + kBlock - 1) / kBlock, kBlock, 0, bs>>>(ctx->sc, ps, item0, (unsigned long long)cnt, its, PrbRecords{nullptr, 0, 9}, film,
                                                                       DIFF ? rec_b + (size_t)REC_S_STATE * ctx->rec_stride : nullptr, ctx->rec_stride, ctx->counters);
         SDFRT_CUDA(ctx, cudaGetLastError());
         return SDFRT_OK;
@@ -562,6 +644,8 @@ int run_sweeps(sdfrt_ctx* ctx, Sweep* sweeps, int ns, cudaStream_t st) {
         if ((rc = ensure(ctx, &sc.s_its, &sc.s_its_n, (size_t)Bmax))) return rc;
         if (any_diff && (rc = ensure(ctx, &sc.srec, &sc.srec_n, (size_t)Bmax * 9))) return rc;
         if (any_value && (rc = ensure(ctx, &sc.its, &sc.its_n, (size_t)Bmax))) return rc;
+        if (any_value && ctx->sc.integrator == INTEGRATOR_PRB && ctx->prb_wavefront &&
+            (rc = ensure(ctx, &sc.prb_rec, &sc.prb_rec_n, (size_t)Bmax * 2 * (size_t)ctx->sc.prb.max_depth))) return rc;
     }
     // empty-space test (rebuilt every call: the caller may have updated the grid in place): brick minima -> dilation -> one
     // DDA per film pixel and sweep -> masks consumed by k_gen_primary
@@ -662,7 +746,7 @@ int run_prb_sweep(sdfrt_ctx* ctx, const PassParams& ps, float* film, float* L_re
         return fail(ctx, SDFRT_ERR_INVALID, "film row band exceeds 2^32 samples");
     const unsigned long long blocks = (ps.n_items + kBlock - 1) / kBlock;
     if (blocks > 0x7fffffffull) return fail(ctx, SDFRT_ERR_INVALID, "too many samples for one launch");
-    { LaunchScope ls(ctx, 1, st); k_prb_primal<<<(unsigned)blocks, kBlock, 0, st>>>(ctx->sc, ps, 0ull, ps.n_items, nullptr, film, L_rec, rec_stride, ctx->counters); }
+    { LaunchScope ls(ctx, 1, st); k_prb_primal<<<(unsigned)blocks, kBlock, 0, st>>>(ctx->sc, ps, 0ull, ps.n_items, nullptr, PrbRecords{nullptr, 0, 9}, film, L_rec, rec_stride, ctx->counters); }
     SDFRT_CUDA(ctx, cudaGetLastError());
     return SDFRT_OK;
 }
@@ -726,6 +810,7 @@ sdfrt_ctx* sdfrt_create(int device, int* status) {
     if (const char* e = std::getenv("SDFRT_SLOTS")) ctx->max_slots = std::max(1, std::min(kSlots, std::atoi(e)));          // developer overrides
     if (const char* e = std::getenv("SDFRT_MIN_LIVE")) ctx->min_live = std::max(1, std::min(32, std::atoi(e)));
     if (const char* e = std::getenv("SDFRT_PRB_OCC")) ctx->prb_min_blocks = std::atoi(e);
+    if (const char* e = std::getenv("SDFRT_PRB_WAVEFRONT")) ctx->prb_wavefront = std::atoi(e) != 0;
     if (const char* e = std::getenv("SDFRT_PRB_PRIMARY")) ctx->prb_primary_wavefront = std::atoi(e) != 0;
     if (const char* e = std::getenv("SDFRT_SKIP_EMPTY")) ctx->skip_empty = std::atoi(e) != 0;
     if (const char* e = std::getenv("SDFRT_BATCH_LOG2")) ctx->batch_target = 1ull << std::max(16, std::min(28, std::atoi(e)));
@@ -763,9 +848,9 @@ void sdfrt_destroy(sdfrt_ctx* ctx) {
     cudaFree(ctx->counters);
     cudaFree(ctx->work);
     cudaFree(ctx->rows4); cudaFree(ctx->brick_raw); cudaFree(ctx->brick); cudaFree(ctx->pix_mask);
-    cudaFree(ctx->rd_work); cudaFree(ctx->rd_state); cudaFree(ctx->lap_r);
+    cudaFree(ctx->rd_work); cudaFree(ctx->rd_state); cudaFree(ctx->lap_r); cudaFree(ctx->prb_rec);
     for (auto& sc : ctx->scratch) {
-        cudaFree(sc.segs); cudaFree(sc.its); cudaFree(sc.ssegs); cudaFree(sc.sinfo); cudaFree(sc.s_its); cudaFree(sc.srec); cudaFree(sc.scount);
+        cudaFree(sc.prb_rec); cudaFree(sc.segs); cudaFree(sc.its); cudaFree(sc.ssegs); cudaFree(sc.sinfo); cudaFree(sc.s_its); cudaFree(sc.srec); cudaFree(sc.scount);
     }
     for (int i = 0; i < kSlots; ++i) {
         if (ctx->aux[i]) cudaStreamDestroy(ctx->aux[i]);
@@ -920,7 +1005,7 @@ int sdfrt_render_primal(sdfrt_ctx* ctx, uint32_t seed, int spp, float* film_accu
     if (rc) return rc;
     if (!film_accum) return fail(ctx, SDFRT_ERR_INVALID, "film_accum is null");
     const bool prb = ctx->sc.integrator == INTEGRATOR_PRB;
-    if (prb && !ctx->prb_primary_wavefront)
+    if (prb && !ctx->prb_primary_wavefront && !ctx->prb_wavefront)
         return run_prb_sweep(ctx, make_pass(ctx->sc.S, seed, spp, ctx->rank, ctx->world), film_accum, nullptr, 0, (cudaStream_t)stream);
     Sweep sw;
     sw.diff = false;
@@ -951,7 +1036,9 @@ int sdfrt_adjoint_accumulate(sdfrt_ctx* ctx, uint32_t seed_grad, int spp_grad, f
     rc = ensure(ctx, &ctx->rec, &ctx->rec_capacity, (size_t)sw.ps.n_items * REC_COUNT + 1);
     if (rc) return rc;
     ctx->rec_stride = sw.ps.n_items;
-    if (ctx->sc.integrator == INTEGRATOR_PRB && !ctx->prb_primary_wavefront)  // re-render of render_backward (:204-206), keeps L per sample
+    if (ctx->sc.integrator == INTEGRATOR_PRB && ctx->prb_wavefront &&
+        (rc = ensure(ctx, &ctx->prb_rec, &ctx->prb_rec_n, (size_t)sw.ps.n_items * kPrbRecFloats * (size_t)ctx->sc.prb.max_depth + 1))) return rc;
+    if (ctx->sc.integrator == INTEGRATOR_PRB && !ctx->prb_primary_wavefront && !ctx->prb_wavefront)  // re-render of render_backward (:204-206), keeps L per sample
         rc = run_prb_sweep(ctx, sw.ps, film_accum, ctx->rec + (size_t)REC_S_STATE * ctx->rec_stride, ctx->rec_stride, (cudaStream_t)stream);
     else
         rc = run_sweeps(ctx, &sw, 1, (cudaStream_t)stream);
@@ -979,7 +1066,9 @@ int sdfrt_render_view(sdfrt_ctx* ctx, uint32_t seed, int spp, float* film_primal
     rc = ensure(ctx, &ctx->rec, &ctx->rec_capacity, (size_t)sw[1].ps.n_items * REC_COUNT + 1);
     if (rc) return rc;
     ctx->rec_stride = sw[1].ps.n_items;
-    if (ctx->sc.integrator == INTEGRATOR_PRB && !ctx->prb_primary_wavefront) {
+    if (ctx->sc.integrator == INTEGRATOR_PRB && ctx->prb_wavefront &&
+        (rc = ensure(ctx, &ctx->prb_rec, &ctx->prb_rec_n, (size_t)sw[1].ps.n_items * kPrbRecFloats * (size_t)ctx->sc.prb.max_depth + 1))) return rc;
+    if (ctx->sc.integrator == INTEGRATOR_PRB && !ctx->prb_primary_wavefront && !ctx->prb_wavefront) {
         rc = run_prb_sweep(ctx, sw[0].ps, film_primal, nullptr, 0, (cudaStream_t)stream);
         if (!rc) rc = run_prb_sweep(ctx, sw[1].ps, film_adjoint, ctx->rec + (size_t)REC_S_STATE * ctx->rec_stride, ctx->rec_stride, (cudaStream_t)stream);
     } else {
@@ -1014,11 +1103,12 @@ int sdfrt_adjoint_backprop(sdfrt_ctx* ctx, const float* film_accum, const float*
     if (ctx->sc.integrator == INTEGRATOR_PRB) {
         LaunchScope ls(ctx, 6, st);
         const float* L_rec = ctx->rec + (size_t)REC_S_STATE * ctx->rec_stride;   // rows 9..11: L of the re-render
-        const float* prim = ctx->prb_primary_wavefront ? ctx->rec : nullptr;     // rows 0..8: camera ray's march by k_march
+        const float* prim = (ctx->prb_primary_wavefront && !ctx->prb_wavefront) ? ctx->rec : nullptr;  // rows 0..8: camera ray's march by k_march
+        const PrbRecords recs = ctx->prb_wavefront ? PrbRecords{ctx->prb_rec, ps.n_items, 9} : PrbRecords{nullptr, 0, 9};
         if (ctx->prb_min_blocks >= 3)
-            k_prb_backward<3><<<(unsigned)blocks, kBlock, 0, st>>>(ctx->sc, ps, ctx->film_adj, L_rec, prim, ctx->rec_stride, tg, grad_p, ctx->counters);
+            k_prb_backward<3><<<(unsigned)blocks, kBlock, 0, st>>>(ctx->sc, ps, ctx->film_adj, L_rec, prim, recs, ctx->rec_stride, tg, grad_p, ctx->counters);
         else
-            k_prb_backward<2><<<(unsigned)blocks, kBlock, 0, st>>>(ctx->sc, ps, ctx->film_adj, L_rec, prim, ctx->rec_stride, tg, grad_p, ctx->counters);
+            k_prb_backward<2><<<(unsigned)blocks, kBlock, 0, st>>>(ctx->sc, ps, ctx->film_adj, L_rec, prim, recs, ctx->rec_stride, tg, grad_p, ctx->counters);
     } else {
         LaunchScope ls(ctx, 6, st);
         k_backward<<<(unsigned)blocks, kBlock, 0, st>>>(ctx->sc, ps, ctx->film_adj, ctx->rec, ctx->rec_stride, tg, grad_p, ctx->counters);

@@ -151,9 +151,40 @@ struct PrbPrimary {
     TraceOut tr;   // warp_t = inf if there is none
 };
 
+// Wavefront form: every segment of the path is marched by k_march, bounce by bounce, and its result is
+// kept as a 9-float record (its_t + the differentiable tracer's outputs; a value march fills row 0 only).  Record (v, s) belongs to
+// vertex v: s = 0 the segment that ENDS at the vertex (camera ray for v = 0), s = 1 its emitter-sample shadow ray.
+// Row r of record (v, s) of sample i is base[((v * 2 + s) * 9 + r) * stride + i]; `base` is already offset to the sample.
+struct PrbRecords {
+    const float* base;  // nullptr: march inline (per-lane form, host harness)
+    unsigned long long stride;
+    int rows;           // rows per record: 9, or 1 in value-only sweeps (its_t alone)
+    SDFRT_HD float its(int v, int s) const { return base[(size_t)((v * 2 + s) * rows) * stride]; }
+    SDFRT_HD TraceOut rec(int v, int s) const {  // rows == 9 only
+        const float* r = base + (size_t)((v * 2 + s) * 9) * stride;
+        TraceOut t;
+        t.its_t = r[0];
+        t.warp_t = r[1 * stride];
+        t.warp_t_d = V3{r[2 * stride], r[3 * stride], r[4 * stride]};
+        t.warp_weight = r[5 * stride];
+        t.warp_weight_d = V3{r[6 * stride], r[7 * stride], r[8 * stride]};
+        t.n_steps = 0;
+        return t;
+    }
+};
+constexpr int kPrbRecFloats = 18;  // per vertex: segment record + shadow record
+// The walker as segment generator: walk (from records) up to vertex `stop_at`, report the two rays that leave it, return.
+struct PrbStop {
+    int stop_at;
+    bool shadow_active, next_active;
+    V3 shadow_o, shadow_d, next_o, next_d;
+    float shadow_maxt;
+};
+
 template <bool BWD, class Emit>
 SDFRT_HD V3 lane_prb(const SceneParams& sc, const PassParams& ps, unsigned long long lane, const float* film_adj, V3 L_total, Emit& emit,
-                     V3& grad_p, LaneStats& st, const PrbPrimary* pre = nullptr) {
+                     V3& grad_p, LaneStats& st, const PrbPrimary* pre = nullptr, PrbRecords recs = PrbRecords{nullptr, 0, 9},
+                     PrbStop* stop = nullptr) {
     const GridView& G = sc.G;
     const TracerParams& T = sc.T;
     const WarpParams& W = sc.W;
@@ -167,7 +198,9 @@ SDFRT_HD V3 lane_prb(const SceneParams& sc, const PassParams& ps, unsigned long 
 
     V3 o_cur = cs.o, d_cur = cs.d;
     float t_cur;
-    if (pre != nullptr) {
+    if (recs.base != nullptr) {
+        t_cur = recs.its(0, 0);
+    } else if (pre != nullptr) {
         t_cur = pre->its_t;
     } else {  // ray_intersect_preliminary (:264)
         const ValueTrace vt = trace_value_sel<BWD>(G, T, o_cur, d_cur, cs.maxt, true);
@@ -187,7 +220,9 @@ SDFRT_HD V3 lane_prb(const SceneParams& sc, const PassParams& ps, unsigned long 
     TraceOut tr0;
     tr0.warp_t = INFINITY; tr0.warp_t_d = v3(0.f); tr0.warp_weight = 0.f; tr0.warp_weight_d = v3(0.f);
     if (BWD) {
-        if (warp2d && pre != nullptr) {
+        if (warp2d && recs.base != nullptr) {
+            tr0 = recs.rec(0, 0);
+        } else if (warp2d && pre != nullptr) {
             tr0 = pre->tr;
         } else if (warp2d) {  // sample_rays with reparam (:499-511)
             const DiffTrace dt = prb_trace_diff(G, T, o_cur, d_cur, cs.maxt);
@@ -230,8 +265,12 @@ SDFRT_HD V3 lane_prb(const SceneParams& sc, const PassParams& ps, unsigned long 
         WarpSite wseg;
         wseg.active = false;
         if (grad_here && !first && warp2d) {
-            const DiffTrace dt = prb_trace_diff(G, T, o_cur, d_cur, INFINITY);  // o_cur == si_prev.spawn_ray(ray_cur.d).o
-            trs = dt.out; nh += dt.n_hess; nv += dt.n_value;
+            if (recs.base != nullptr) {
+                trs = recs.rec(it, 0);
+            } else {
+                const DiffTrace dt = prb_trace_diff(G, T, o_cur, d_cur, INFINITY);  // o_cur == si_prev.spawn_ray(ray_cur.d).o
+                trs = dt.out; nh += dt.n_hess; nv += dt.n_value;
+            }
             wseg = prb_warp_site(G, W, T, o_cur, d_cur, trs);
             nh += isfinite(trs.warp_t);
         }
@@ -266,18 +305,33 @@ SDFRT_HD V3 lane_prb(const SceneParams& sc, const PassParams& ps, unsigned long 
                 st.n_albedo += (sc.A.data != nullptr);
                 sr = make_shadow_ray(sc.Sh, p, n, u_em0, u_em1);  // si_cur.spawn_ray_to(ds.p), d detached (:316-317)
                 cos_o = dot(n, sr.d);
-                if ((cos_i > 0.f) & (cos_o > 0.f)) {  // a closed BSDF gate contributes exactly zero: not marched
-                    const ValueTrace vs = trace_value_sel<BWD>(G, T, sr.o, sr.d, sr.maxt, false);
-                    nv += vs.n_evals;
-                    if (!isfinite(vs.its_t)) {
+                if (stop != nullptr && it == stop->stop_at) {
+                    if ((cos_i > 0.f) & (cos_o > 0.f)) {
+                        stop->shadow_active = true;
+                        stop->shadow_o = sr.o; stop->shadow_d = sr.d; stop->shadow_maxt = sr.maxt;
+                    }
+                } else if ((cos_i > 0.f) & (cos_o > 0.f)) {  // a closed BSDF gate contributes exactly zero: not marched
+                    float its_s;
+                    if (recs.base != nullptr) {
+                        its_s = recs.its(it, 1);
+                    } else {
+                        const ValueTrace vs = trace_value_sel<BWD>(G, T, sr.o, sr.d, sr.maxt, false);
+                        nv += vs.n_evals;
+                        its_s = vs.its_t;
+                    }
+                    if (!isfinite(its_s)) {
                         nee = true;
                         mis_direct = mis_weight(kInv4Pi, cos_o * (1.f / kPi));
                         const float k = 4.f * cos_o * mis_direct;  // (rho / pi) cos_o * Le / (1 / 4 pi) * mis
                         Lr_dir = k * (beta * rho * Le_env);
                         // the shadow ray's warp record is only needed where it is reparameterised (static depth 1, :321)
                         if (grad_here && reparam_at_depth(W, 1)) {
-                            const DiffTrace dt = prb_trace_diff(G, T, sr.o, sr.d, sr.maxt);
-                            ts = dt.out; nh += dt.n_hess; nv += dt.n_value;
+                            if (recs.base != nullptr) {
+                                ts = recs.rec(it, 1);
+                            } else {
+                                const DiffTrace dt = prb_trace_diff(G, T, sr.o, sr.d, sr.maxt);
+                                ts = dt.out; nh += dt.n_hess; nv += dt.n_value;
+                            }
                         }
                     }
                 }
@@ -305,8 +359,15 @@ SDFRT_HD V3 lane_prb(const SceneParams& sc, const PassParams& ps, unsigned long 
         }
 
         // ---- next surface and the MIS weight of hitting the emitter by BSDF sampling (:351-363) ---------------
+        if (stop != nullptr && it == stop->stop_at) {  // wavefront: the continuation ray of this vertex goes to the marcher
+            stop->next_active = active_next;
+            stop->next_o = o_next; stop->next_d = wo_w;
+            return L;
+        }
         float t_next = INFINITY;
-        if (active_next) {
+        if (active_next && recs.base != nullptr) {
+            t_next = recs.its(it + 1, 0);
+        } else if (active_next) {
             const ValueTrace vn = trace_value_sel<BWD>(G, T, o_next, wo_w, INFINITY, true);
             t_next = vn.its_t; nv += vn.n_evals;
             nsteps = nsteps > vn.n_steps ? nsteps : vn.n_steps;

@@ -213,6 +213,112 @@ int hh_prb_backward(const hh_scene* h, unsigned seed, int spp, const float* film
     return 0;
 }
 
+// ---- wavefront form of sdf_prb_reparam, emulated on the host: the same walker (lane_prb with records / stop hooks) that the
+// device kernels call, with k_march replaced by the per-ray tracers.  recs: max_depth * 18 rows of n floats (PrbRecords layout).
+static void hh_march_into(const SceneParams& sc, V3 o, V3 d, float maxt, bool refine, bool diff, float* rec, unsigned long long stride) {
+    if (diff) {
+        TraceOut tr; tr.warp_t = INFINITY; tr.warp_t_d = v3(0.f); tr.warp_weight = 0.f; tr.warp_weight_d = v3(0.f);
+        int nh = 0, nv = 0;
+        trace_diff(sc.G, sc.T, o, d, maxt, refine, tr, nh, nv);
+        rec[0] = tr.its_t; rec[1 * stride] = tr.warp_t;
+        rec[2 * stride] = tr.warp_t_d.x; rec[3 * stride] = tr.warp_t_d.y; rec[4 * stride] = tr.warp_t_d.z;
+        rec[5 * stride] = tr.warp_weight;
+        rec[6 * stride] = tr.warp_weight_d.x; rec[7 * stride] = tr.warp_weight_d.y; rec[8 * stride] = tr.warp_weight_d.z;
+    } else {
+        int ns = 0, nv = 0;
+        rec[0] = trace_non_diff(sc.G, sc.T, o, d, maxt, refine, ns, nv);
+    }
+}
+
+int hh_prb_wf_forward(const hh_scene* h, unsigned seed, int spp, int diff, float* film, float* L_rec, float* recs, int rank, int world) {
+    SceneParams sc = build(h);
+    PassParams ps = make_pass(sc.S, seed, spp, rank, world);
+    const int Wb = sc.S.W + 2 * sc.S.border, Hb = sc.S.H + 2 * sc.S.border;
+    std::memset(film, 0, (size_t)Wb * Hb * 4 * sizeof(float));
+    const unsigned long long n = ps.n_items;
+    const bool warp2d = sc.W.kind == WARP_2D;
+    const int rmd = warp2d ? (sc.W.max_reparam_depth >= 0 ? sc.W.max_reparam_depth : 100000) : sc.prb.max_depth;
+    for (size_t q = 0; q < (size_t)n * sc.prb.max_depth * kPrbRecFloats; ++q) recs[q] = NAN;  // reading an unwritten row must show
+    LaneStats st = {0, 0, 0, 0, 0, 0, 0};
+    for (int k = 0; k < sc.prb.max_depth; ++k) {
+        for (unsigned long long i = 0; i < n; ++i) {
+            const WorkItem w = decode_item(ps, i);
+            float* base = recs + i;
+            if (k == 0) {
+                const CameraSample cs = camera_sample(sc, ps, w.lane);
+                hh_march_into(sc, cs.o, cs.d, cs.maxt, true, diff && warp2d, base, n);
+            }
+            PrbStop stop;
+            stop.stop_at = k; stop.shadow_active = false; stop.next_active = false;
+            NoEmit ne; V3 gp = v3(0.f);
+            (void)lane_prb<false>(sc, ps, w.lane, nullptr, v3(0.f), ne, gp, st, nullptr, PrbRecords{base, n, 9}, &stop);
+            float* srec = base + (size_t)((k * 2 + 1) * 9) * n;
+            if (stop.shadow_active) hh_march_into(sc, stop.shadow_o, stop.shadow_d, stop.shadow_maxt, false,
+                                                  diff && warp2d && reparam_at_depth(sc.W, 1) && k <= rmd, srec, n);
+            else srec[0] = INFINITY;
+            if (k + 1 < sc.prb.max_depth) {
+                float* nrec = base + (size_t)(((k + 1) * 2) * 9) * n;
+                if (stop.next_active) hh_march_into(sc, stop.next_o, stop.next_d, INFINITY, true, diff && warp2d && (k + 1) <= rmd, nrec, n);
+                else nrec[0] = INFINITY;
+            }
+        }
+    }
+    for (unsigned long long i = 0; i < n; ++i) {
+        const WorkItem w = decode_item(ps, i);
+        NoEmit ne; V3 gp = v3(0.f);
+        const V3 L = lane_prb<false>(sc, ps, w.lane, nullptr, v3(0.f), ne, gp, st, nullptr, PrbRecords{recs + i, n, 9});
+        if (L_rec) { L_rec[i] = L.x; L_rec[i + n] = L.y; L_rec[i + 2 * n] = L.z; }
+        Pcg32 rng = sampler_seed(ps.seed, (uint32_t)w.lane);
+        const float r0 = pcg_next_f32(rng), r1 = pcg_next_f32(rng);
+        const float pfx = (float)(w.px - sc.S.border) + r0 + ((float)sc.S.border - 0.5f);
+        const float pfy = (float)(w.py - sc.S.border) + r1 + ((float)sc.S.border - 0.5f);
+        const float rad = sc.S.filter_radius;
+        for (int by = (int)ceilf(pfy - rad); by <= (int)floorf(pfy + rad); ++by) {
+            if (by < 0 || by >= Hb) continue;
+            const float wy = filter_eval(sc.S, (float)by - pfy);
+            for (int bx = (int)ceilf(pfx - rad); bx <= (int)floorf(pfx + rad); ++bx) {
+                if (bx < 0 || bx >= Wb) continue;
+                const float wgt = wy * filter_eval(sc.S, (float)bx - pfx);
+                float* px = film + ((size_t)by * Wb + bx) * 4;
+                px[0] += L.x * wgt; px[1] += L.y * wgt; px[2] += L.z * wgt; px[3] += wgt;
+            }
+        }
+    }
+    return 0;
+}
+
+int hh_prb_wf_backward(const hh_scene* h, unsigned seed, int spp, const float* film, const float* L_rec, const float* recs,
+                       const float* grad_image, float* grad_sdf, float* grad_albedo, float* grad_p, int rank, int world) {
+    SceneParams sc = build(h);
+    PassParams ps = make_pass(sc.S, seed, spp, rank, world);
+    const SensorParams& S = sc.S;
+    const int Wb = S.W + 2 * S.border, Hb = S.H + 2 * S.border;
+    std::vector<float> adj((size_t)Wb * Hb * 4, 0.f);
+    for (int by = 0; by < Hb; ++by)
+        for (int bx = 0; bx < Wb; ++bx) {
+            const int qx = bx - S.border, qy = by - S.border;
+            if (qx < 0 || qx >= S.W || qy < 0 || qy >= S.H) continue;
+            const float* a = film + ((size_t)by * Wb + bx) * 4;
+            const float* g = grad_image + ((size_t)qy * S.W + qx) * 3;
+            if (a[3] == 0.f) continue;
+            const float iw = 1.f / a[3];
+            float* o = adj.data() + ((size_t)by * Wb + bx) * 4;
+            o[0] = g[0] * iw; o[1] = g[1] * iw; o[2] = g[2] * iw;
+            o[3] = -(g[0] * a[0] + g[1] * a[1] + g[2] * a[2]) * iw * iw;
+        }
+    LaneStats st = {0, 0, 0, 0, 0, 0, 0};
+    V3 gp = v3(0.f);
+    const unsigned long long n = ps.n_items;
+    for (unsigned long long k = 0; k < n; ++k) {
+        const WorkItem w = decode_item(ps, k);
+        DirectEmit em{grad_sdf, grad_albedo, sc.G};
+        (void)lane_prb<true>(sc, ps, w.lane, adj.data(), V3{L_rec[k], L_rec[k + n], L_rec[k + 2 * n]}, em, gp, st, nullptr,
+                             PrbRecords{recs + k, n, 9});
+    }
+    if (grad_p) { grad_p[0] += gp.x; grad_p[1] += gp.y; grad_p[2] += gp.z; }
+    return 0;
+}
+
 int hh_rec_count() { return REC_COUNT; }
 unsigned long long hh_local_lanes(const hh_scene* h, int spp, int rank, int world) {
     SensorParams S = make_sensor(h->sensor);

@@ -168,3 +168,21 @@ class HostScene:
         lib().hh_prb_backward(C.byref(self.h), C.c_uint(seed), spp, fptr(film), fptr(L), fptr(grad_image), fptr(g),
                               None if ga is None else fptr(ga), fptr(gp), fptr(stats), rank, world)
         return g, ga, gp, stats
+
+    # wavefront form (records + stop hooks), emulated on the host
+    def prb_wf_forward(self, seed, spp, diff, rank=0, world=1):
+        film = np.zeros(self.film_shape, np.float32)
+        n = self.local_lanes(spp, rank, world)
+        L = np.zeros((3, max(n, 1)), np.float32)
+        recs = np.zeros((self.h.prb.max_depth * 18, max(n, 1)), np.float32)
+        lib().hh_prb_wf_forward(C.byref(self.h), C.c_uint(seed), spp, int(diff), fptr(film), fptr(L), fptr(recs), rank, world)
+        return film, L, recs
+
+    def prb_wf_backward(self, seed, spp, film, L, recs, grad_image, rank=0, world=1):
+        grad_image = np.ascontiguousarray(grad_image, dtype=np.float32)
+        g = np.zeros_like(self.sdf)
+        ga = None if self.albedo is None else np.zeros_like(self.albedo)
+        gp = np.zeros(3, np.float32)
+        lib().hh_prb_wf_backward(C.byref(self.h), C.c_uint(seed), spp, fptr(film), fptr(L), fptr(recs), fptr(grad_image), fptr(g),
+                                 None if ga is None else fptr(ga), fptr(gp), rank, world)
+        return g, ga, gp

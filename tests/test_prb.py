@@ -182,3 +182,20 @@ def test_adjoint_is_linear_in_grad_image():
     gb = hs.prb_backward(5, 2, film, L, b)[0]
     gab = hs.prb_backward(5, 2, film, L, 2 * a - 3 * b)[0]
     assert np.abs(gab - (2 * ga - 3 * gb)).max() < 1e-4 * max(np.abs(ga).max(), np.abs(gb).max())
+
+
+@pytest.mark.parametrize('kind,R,albedo_res,max_depth,rr_depth,mrd,warp', CASES[1:4])
+def test_wavefront_form_equals_per_lane_walker(kind, R, albedo_res, max_depth, rr_depth, mrd, warp):
+    """The wavefront form (every segment marched separately, results kept as per-vertex records, the walker re-run from the
+    records as segment generator and for the replay) emulated on the host with the per-ray tracers in place of k_march:
+    film, L and gradient equal the per-lane walker bit for bit, and no record row is read before it was written (the emulation
+    poisons the records with NaN)."""
+    _, _, hs, _ = make_pair(kind, R, 16, albedo_res, max_depth, rr_depth, mrd, warp)
+    g_in = MG.grad_image(16)
+    film, L = hs.prb_forward(11, 4)
+    film_w, L_w, _ = hs.prb_wf_forward(11, 4, False)
+    assert np.array_equal(film, film_w) and np.array_equal(L, L_w)
+    g = hs.prb_backward(11, 4, film, L, g_in)[0]
+    film_d, L_d, recs = hs.prb_wf_forward(11, 4, True)
+    g_w = hs.prb_wf_backward(11, 4, film_d, L_d, recs, g_in)[0]
+    assert np.array_equal(film, film_d) and np.array_equal(g, g_w) and np.isfinite(g_w).all()
