@@ -388,7 +388,7 @@ struct sdfrt_ctx {
     size_t rows4_n = 0;
     int rows4_roles = -1, march_role = 0;
     bool rows4_on = false;
-    bool prb_wavefront = false;              // sdf_prb_reparam bounce by bounce through k_march (SDFRT_PRB_WAVEFRONT=1)
+    bool prb_wavefront = true;               // sdf_prb_reparam bounce by bounce through k_march (SDFRT_PRB_WAVEFRONT=0: per-lane walker)
     float* prb_rec = nullptr;                // DIFF sweep: per-vertex march records [max_depth * 18][n_items]
     size_t prb_rec_n = 0;
     bool prb_primary_wavefront = true;       // camera rays of sdf_prb_reparam through k_march (SDFRT_PRB_PRIMARY=0: per lane)
