@@ -198,10 +198,13 @@ __global__ void k_eval_sdf(GridView G, const float* __restrict__ x, int n, int o
 
 
 // ---------------------------------------------------------------------------------------------------------------
-// Path replay integrator (sdfrt_prb.cuh): one thread per camera sample walks its whole path.  First correct form of
-// SURVEY 8f#1 -- the bounce-by-bounce wavefront form on top of k_march is the next step.
-//   k_prb_primal    L per sample -> warp-cooperative film splat; optionally stores L (the state_in of the replay)
-//   k_prb_backward  replays the path with delta_L from the film adjoint and scatters the vertex adjoints
+// Path replay integrator (sdfrt_prb.cuh).  Default = wavefront form: every segment of every path is marched by k_march, bounce by
+// bounce (enqueue_batch), and kept as a per-vertex record; the kernels here only WALK records:
+//   k_prb_wf_emit   walker as segment generator: the shadow and continuation rays leaving vertex k -> SegIn arrays for k_march
+//   k_prb_primal    final walk: L per sample -> warp-cooperative film splat; the re-render of render_backward also keeps L
+//   k_prb_backward  the replay: vertex adjoints from the records (no marching), scattered with red.global.add
+// Per-lane form (SDFRT_PRB_WAVEFRONT=0; also what the host harness runs): the same two kernels march inline with the per-ray
+// tracers, optionally taking the camera ray's march from k_march (SDFRT_PRB_PRIMARY).
 // ---------------------------------------------------------------------------------------------------------------
 // items [item0, item0 + cnt); `its` (or nullptr): hit distance of the camera ray per item of this range, from the wavefront marcher;
 // L_rec (or nullptr): rows of `rec_stride` floats, already offset to item0

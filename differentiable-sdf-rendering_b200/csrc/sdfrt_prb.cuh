@@ -17,7 +17,8 @@
 //   Lr_ind            L * (bsdf_val / detach(bsdf_val)),  bsdf_val = rho(p)/pi * (n . wo)               (:407-412)
 //   extra             L_prev * cos(n_prev, normalize(p - p_prev)) / detach(.)   (:389-406; the `next` term of :399,406
 //                     carries no derivative for a diffuse BSDF, and Le_next none for a constant emitter)
-// Derivation and parity: DESIGN.md section 9, tests/test_prb_hostmath.py (against the autograd oracle).
+// The walker marches inline (per-lane form, host harness) or reads the marches from per-vertex records (wavefront form: PrbRecords,
+// PrbStop below).  Derivation and parity: DESIGN.md section 8, tests/test_prb.py (against the autograd oracle), tests/test_gpu_prb.py.
 #pragma once
 #include "sdfrt_lane.cuh"
 

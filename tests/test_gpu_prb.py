@@ -1,5 +1,5 @@
-"""GPU parity tests (-m gpu) of the path replay integrator `sdf_prb_reparam` (csrc/sdfrt_prb.cuh, k_prb_primal /
-k_prb_backward), called through the C ABI via the Python mirror: golden fixtures (fp64 oracle), the oracle on a
+"""GPU parity tests (-m gpu) of the path replay integrator `sdf_prb_reparam` (csrc/sdfrt_prb.cuh; wavefront form by default,
+`SDFRT_PRB_WAVEFRONT=0` runs the same tests on the per-lane walker), called through the C ABI via the Python mirror: golden fixtures (fp64 oracle), the oracle on a
 seeded case, world-size independence of the row partition and a size-independent property at a BASELINE-sized film.
 Stated fp32 tolerances as in test_gpu_parity.py."""
 import os
