@@ -748,6 +748,7 @@ class Scene:
     albedo_grid: torch.Tensor = None          # optional (Z,Y,X,3) trilinear gridvolume on [0,1]^3
     env_dist: float = 2.0 * math.sqrt(3.0)    # constant emitter: 2 * scene bsphere radius (unit cube + margin)
     hide_emitters: bool = False
+    use_mis: bool = False                     # ReparamIntegrator prop (python/integrators/reparam.py:17): BSDF-sampling MIS branch
     detach_indirect_si: bool = False          # sdf_direct_reparam props (python/integrators/sdf_direct_reparam.py:13-14,44-49)
     decouple_reparam: bool = False
 
@@ -867,9 +868,34 @@ def sample_direct(scene, warp_field, sampler, o, d, maxt, reparam_mode):
     gate = (~occluded) & (cos_i > 0) & (cos_o > 0)
     bsdf_val = rho / math.pi * cos_o[:, None]
     nee = bsdf_val * emitter_val
+    if scene.use_mis:  # :77-79: power heuristic against the (detached) BSDF pdf of the sampled direction
+        bsdf_pdf = torch.where((cos_i > 0) & (cos_o > 0), cos_o.detach() / math.pi, torch.zeros_like(cos_o)).detach()
+        nee = nee * mis_weight(torch.full_like(bsdf_pdf, ds_pdf), bsdf_pdf)[:, None]
     contrib = det[h, None] * nee * det_e[:, None]
     contrib = torch.where(gate[:, None], contrib, torch.zeros_like(contrib))
     result = result.index_add(0, h, contrib)
+    if scene.use_mis:
+        # ---- BSDF sampling (python/integrators/sdf_direct_reparam.py:87-107); not built in the CUDA path yet ----
+        u1 = sampler.next_1d()  # noqa: F841  component sample
+        u2 = sampler.next_2d()
+        with torch.no_grad():
+            wo_l = square_to_cosine_hemisphere(u2[h])
+            bs_pdf = wo_l[:, 2] / math.pi
+            act = (cos_i.detach() > 0) & (bs_pdf > 0)               # active &= bs.pdf > 0 (:92); bsdf.sample gates on cos_i
+            nd = n.detach()
+            fs, ft = sh_frame(nd)
+            wo_w = fs * wo_l[:, 0:1] + ft * wo_l[:, 1:2] + nd * wo_l[:, 2:3]   # si_d.to_world(bs.wo)
+        o_b = _spawn_offset(p, n, wo_w)                              # si.spawn_ray (attached origin), d detached (:93-94)
+        its_b, _d_b, det_b, _ = _ray_intersect(scene, warp_field, o_b, wo_w, torch.full_like(bs_pdf, INF), 1, reparametrize, active=act)
+        escaped = ~torch.isfinite(its_b)
+        # bsdf.eval(ctx, si, bs.wo): local direction, so only rho(p) carries a derivative (:97)
+        bsdf_val_b = torch.where(act[:, None], rho / math.pi * wo_l[:, 2:3], torch.zeros_like(rho))
+        emitter_pdf = torch.where(escaped, torch.full_like(bs_pdf, 1.0 / (4 * math.pi)), torch.zeros_like(bs_pdf))
+        w_b = mis_weight(bs_pdf, emitter_pdf)
+        inv_pdf = torch.where(bs_pdf > 0, 1 / torch.where(bs_pdf > 0, bs_pdf, torch.ones_like(bs_pdf)), torch.zeros_like(bs_pdf))
+        contrib_b = det[h, None] * bsdf_val_b * inv_pdf[:, None] * Le * w_b[:, None] * det_b[:, None]
+        contrib_b = torch.where((act & escaped)[:, None], contrib_b, torch.zeros_like(contrib_b))
+        result = result.index_add(0, h, contrib_b)
     return result, d_att, det
 
 
