@@ -1,6 +1,8 @@
 """One PRB view (primal + re-render + replay/backprop) on a 128^3 grid, 256x256 film, 16 spp -- the command profiled under ncu
 for profiles/r1_prb_per_lane.md:
   ncu --set full --clock-control none --import-source on -k regex:k_prb -c 3 -o gpurun_out/prb python profiles/prb_profile_run.py
+r1_prb_per_lane.md was captured with the per-lane walker (now SDFRT_PRB_WAVEFRONT=0).  For the wavefront form (the default) the
+kernels of interest are k_prb_wf_emit, the k_march launches of the bounces and k_prb_backward:  -k "regex:k_prb|k_march" -c 40.
 """
 import os
 import sys
