@@ -68,7 +68,8 @@ __global__ void __launch_bounds__(kBlock) k_backward(const __grid_constant__ Sce
     sites.n = 0;
     if (item < ps.n_items) {
         const WorkItem w = decode_item(ps, item);
-        lane_backward(sc, ps, w.lane, film_adj, rec + item, rec_stride, tg, gp, sites, st);
+        const unsigned long long wl = w.lane & ~kAntiBit;
+        if (wl >= ps.win_lo && wl < ps.win_hi) lane_backward(sc, ps, w.lane, film_adj, rec + item, rec_stride, tg, gp, sites, st);
     }
     for (int q = 0; q < 4; ++q) {
         const bool has = q < sites.n;
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(kBlock) k_backward(const __grid_constant__ Sce
                 const int t = lane_id + 32 * h;
                 float acc = 0.f;
                 for (unsigned m = members; m; m &= m - 1) acc += vals[__ffs(m) - 1][t];
-                if (acc != 0.f) {
+                if (acc != 0.f && tg.grad_sdf != nullptr) {
                     const int i = t & 3, j = (t >> 2) & 3, k = t >> 4;
                     atomicAdd(tg.grad_sdf + ((size_t)(lbz + k) * sc.G.ry + (lby + j)) * (size_t)sc.G.rx + (lbx + i), acc);
                 }
@@ -287,7 +288,7 @@ __global__ void __launch_bounds__(kBlock, MIN_BLOCKS) k_prb_backward(const __gri
     const unsigned long long item = (unsigned long long)blockIdx.x * kBlock + threadIdx.x;
     LaneStats st = {0, 0, 0, 0, 0, 0, 0};
     V3 gp = v3(0.f);
-    if (item < ps.n_items) {
+    if (item < ps.n_items && (decode_item(ps, item).lane & ~kAntiBit) >= ps.win_lo && (decode_item(ps, item).lane & ~kAntiBit) < ps.win_hi) {
         const WorkItem w = decode_item(ps, item);
         const V3 L = V3{L_rec[item], L_rec[item + rec_stride], L_rec[item + 2 * rec_stride]};
         DirectEmit em{tg.grad_sdf, tg.grad_albedo, sc.G};
@@ -353,6 +354,11 @@ struct sdfrt_ctx {
     unsigned long long rec_stride = 0;
     PassParams adj_pass;
     bool adj_ready = false;
+    unsigned long long adj_generation = 0;   // bumped by every adjoint sweep 1; sdfrt_adjoint_token
+    unsigned long long win_lo = 0ull, win_hi = ~0ull;  // sdfrt_set_lane_window
+    unsigned* rd_err_host = nullptr;         // pinned copy of the re-distancing solver's error word (async callers)
+    cudaEvent_t rd_err_event = nullptr;
+    bool rd_err_pending = false;
     float* film_adj = nullptr;
     size_t film_adj_capacity = 0;
     Counters* counters = nullptr;
@@ -860,6 +866,8 @@ void sdfrt_destroy(sdfrt_ctx* ctx) {
         if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
     }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->rd_err_host) cudaFreeHost(ctx->rd_err_host);
+    if (ctx->rd_err_event) cudaEventDestroy(ctx->rd_err_event);
     cudaFree(ctx->h_sdf); cudaFree(ctx->h_film); cudaFree(ctx->h_film2); cudaFree(ctx->h_image); cudaFree(ctx->h_gimg); cudaFree(ctx->h_grad);
     delete ctx;
 }
@@ -988,6 +996,23 @@ int sdfrt_set_partition(sdfrt_ctx* ctx, int rank, int world) {
     return SDFRT_OK;
 }
 
+int sdfrt_set_lane_window(sdfrt_ctx* ctx, uint64_t lane_lo, uint64_t lane_hi) {
+    if (!ctx) return SDFRT_ERR_INVALID;
+    if (lane_lo == 0 && lane_hi == 0) { ctx->win_lo = 0ull; ctx->win_hi = ~0ull; return SDFRT_OK; }
+    if (lane_hi <= lane_lo) return fail(ctx, SDFRT_ERR_INVALID, "empty lane window");
+    ctx->win_lo = lane_lo;
+    ctx->win_hi = lane_hi;
+    return SDFRT_OK;
+}
+
+int sdfrt_set_empty_space_skip(sdfrt_ctx* ctx, int enable) {
+    if (!ctx) return SDFRT_ERR_INVALID;
+    ctx->skip_empty = enable != 0;
+    return SDFRT_OK;
+}
+
+uint64_t sdfrt_adjoint_token(const sdfrt_ctx* ctx) { return (ctx && ctx->adj_ready) ? ctx->adj_generation : 0ull; }
+
 int sdfrt_film_dims(const sdfrt_ctx* ctx, int* height_b, int* width_b, int* border) {
     if (!ctx) return SDFRT_ERR_INVALID;
     const SensorParams& S = ctx->sc.S;
@@ -1048,6 +1073,7 @@ int sdfrt_adjoint_accumulate(sdfrt_ctx* ctx, uint32_t seed_grad, int spp_grad, f
     if (rc) return rc;
     ctx->adj_pass = sw.ps;
     ctx->adj_ready = true;
+    ++ctx->adj_generation;
     return SDFRT_OK;
 }
 
@@ -1080,6 +1106,7 @@ int sdfrt_render_view(sdfrt_ctx* ctx, uint32_t seed, int spp, float* film_primal
     if (rc) return rc;
     ctx->adj_pass = sw[1].ps;
     ctx->adj_ready = true;
+    ++ctx->adj_generation;
     return SDFRT_OK;
 }
 
@@ -1087,7 +1114,8 @@ int sdfrt_adjoint_backprop(sdfrt_ctx* ctx, const float* film_accum, const float*
                            float* grad_albedo, float* grad_p, void* stream) {
     if (!ctx) return SDFRT_ERR_INVALID;
     if (!ctx->adj_ready) return fail(ctx, SDFRT_ERR_STATE, "sdfrt_adjoint_accumulate must run first (and no set_* in between)");
-    if (!film_accum || !grad_image || !grad_sdf) return fail(ctx, SDFRT_ERR_INVALID, "null buffer");
+    if (!film_accum || !grad_image) return fail(ctx, SDFRT_ERR_INVALID, "null buffer");
+    if (!grad_sdf && !grad_albedo && !grad_p) return fail(ctx, SDFRT_ERR_INVALID, "no gradient target");
     SDFRT_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     const SensorParams& S = ctx->sc.S;
@@ -1096,7 +1124,9 @@ int sdfrt_adjoint_backprop(sdfrt_ctx* ctx, const float* film_accum, const float*
     const int npix = (S.W + 2 * S.border) * (S.H + 2 * S.border);
     { LaunchScope ls(ctx, 5, st); k_film_adjoint<<<(npix + 255) / 256, 256, 0, st>>>(film_accum, grad_image, ctx->film_adj, S.W, S.H, S.border); }
     SDFRT_CUDA(ctx, cudaGetLastError());
-    const PassParams& ps = ctx->adj_pass;
+    PassParams ps = ctx->adj_pass;
+    ps.win_lo = ctx->win_lo;
+    ps.win_hi = ctx->win_hi;
     const unsigned long long n = ps.n_items;
     if (n == 0) return SDFRT_OK;
     BackwardTargets tg;
@@ -1207,6 +1237,14 @@ int sdfrt_redistance(sdfrt_ctx* ctx, const float* phi, const float* lower_bound,
         ctx->rd_work_n = 4 * n_tiles;
     }
     if (!ctx->rd_state) SDFRT_CUDA(ctx, cudaMalloc(&ctx->rd_state, sizeof(RdState)));
+    if (!ctx->rd_err_host) {
+        SDFRT_CUDA(ctx, cudaMallocHost((void**)&ctx->rd_err_host, 4 * sizeof(unsigned)));
+        SDFRT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->rd_err_event, cudaEventDisableTiming));
+    }
+    {   // an asynchronous solve that aborted earlier (barrier time-out / iteration cap) must not go unnoticed
+        const int prev = sdfrt_redistance_status(ctx);
+        if (prev != SDFRT_OK) return prev;
+    }
     if (ctx->rd_blocks == 0) {
         int coop = 0, per_sm = 0;
         SDFRT_CUDA(ctx, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
@@ -1234,13 +1272,26 @@ int sdfrt_redistance(sdfrt_ctx* ctx, const float* phi, const float* lower_bound,
     k_rd_finish<<<gb, 256, 0, st>>>(g, out);
     SDFRT_CUDA(ctx, cudaGetLastError());
     ctx->n_launches += 3;
+    // the solver's error word always travels to a pinned host word; synchronous callers check it now, asynchronous callers
+    // at their next sdfrt_redistance / sdfrt_redistance_status call (an aborted solve leaves unreached nodes at +-1e30)
+    SDFRT_CUDA(ctx, cudaMemcpyAsync(ctx->rd_err_host, ctx->rd_state, 4 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    SDFRT_CUDA(ctx, cudaEventRecord(ctx->rd_err_event, st));
+    ctx->rd_err_pending = true;
     if (iters_out) {
-        unsigned head[4];
-        SDFRT_CUDA(ctx, cudaMemcpyAsync(head, ctx->rd_state, sizeof(head), cudaMemcpyDeviceToHost, st));
-        SDFRT_CUDA(ctx, cudaStreamSynchronize(st));
-        if (head[2] != 0u) return fail(ctx, SDFRT_ERR_CUDA, head[2] == 1u ? "redistance: grid barrier timed out" : "redistance: iteration cap reached");
-        *iters_out = (int)head[3];
+        const int rc = sdfrt_redistance_status(ctx);
+        if (rc != SDFRT_OK) return rc;
+        *iters_out = (int)ctx->rd_err_host[3];
     }
+    return SDFRT_OK;
+}
+
+int sdfrt_redistance_status(sdfrt_ctx* ctx) {
+    if (!ctx) return SDFRT_ERR_INVALID;
+    if (!ctx->rd_err_pending) return SDFRT_OK;
+    SDFRT_CUDA(ctx, cudaEventSynchronize(ctx->rd_err_event));
+    ctx->rd_err_pending = false;
+    const unsigned e = ctx->rd_err_host[2];
+    if (e != 0u) return fail(ctx, SDFRT_ERR_CUDA, e == 1u ? "redistance: grid barrier timed out" : "redistance: iteration cap reached");
     return SDFRT_OK;
 }
 

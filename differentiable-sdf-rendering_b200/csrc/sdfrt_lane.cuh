@@ -42,6 +42,8 @@ struct PassParams {
     // antithetic_sampling (python/integrators/reparam.py:19,167-178): every wavefront lane is evaluated twice, the second time
     // at the mirrored film position pos - r + 1 with a clone of the sampler; work items 2l and 2l + 1 are the two samples
     int antithetic;
+    // validation hook (sdfrt_set_lane_window): adjoint sweep 2 only back-propagates the wavefront lanes in [win_lo, win_hi)
+    unsigned long long win_lo, win_hi;
 };
 
 constexpr unsigned long long kAntiBit = 1ull << 63;  // WorkItem::lane carries the "mirrored sample" flag in bit 63

@@ -157,6 +157,8 @@ inline PassParams make_pass(const SensorParams& S, uint32_t seed, int spp, int r
     for (int g = rank; g < nbands; g += world) rows += (unsigned long long)std::min(kBandRows, p.Hb - g * kBandRows);
     p.antithetic = antithetic ? 1 : 0;
     p.n_items = rows * (unsigned long long)p.Wb * (unsigned long long)spp * (unsigned long long)(1 + p.antithetic);
+    p.win_lo = 0ull;
+    p.win_hi = ~0ull;
     return p;
 }
 

@@ -501,7 +501,7 @@ struct DirectEmit {
     float* grad_sdf;
     float* grad_albedo;
     GridView G;
-    SDFRT_HD void site(V3 x, float phi_hat, V3 g_hat) { prb_scatter_site(grad_sdf, G, x, phi_hat, g_hat); }
+    SDFRT_HD void site(V3 x, float phi_hat, V3 g_hat) { if (grad_sdf != nullptr) prb_scatter_site(grad_sdf, G, x, phi_hat, g_hat); }
     SDFRT_HD void albedo(const AlbedoTaps& taps, V3 rho_hat) {
         if (grad_albedo == nullptr) return;
         for (int k = 0; k < 8; ++k) {

@@ -130,6 +130,18 @@ class Context:
     def set_partition(self, rank, world):
         check(self.ctx, self.lib.sdfrt_set_partition(self.ctx, rank, world))
 
+    def set_lane_window(self, lane_lo=0, lane_hi=0):
+        """Validation hook: adjoint_backprop only back-propagates wavefront lanes [lane_lo, lane_hi); (0, 0) = all."""
+        check(self.ctx, self.lib.sdfrt_set_lane_window(self.ctx, int(lane_lo), int(lane_hi)))
+
+    def set_empty_space_skip(self, enable=True):
+        """enable=False marches every camera ray (reference behaviour); results are identical, only the work counters change."""
+        check(self.ctx, self.lib.sdfrt_set_empty_space_skip(self.ctx, int(bool(enable))))
+
+    def adjoint_token(self):
+        """Identifies the adjoint sweep 1 whose lane records the context holds (0: none valid)."""
+        return int(self.lib.sdfrt_adjoint_token(self.ctx))
+
     # ---- rendering ----------------------------------------------------------------------------
     def film_dims(self):
         h, w, b = C.c_int(), C.c_int(), C.c_int()
@@ -170,7 +182,10 @@ class Context:
 
     def adjoint_backprop(self, film, grad_image, grad_sdf, grad_albedo=None, grad_p=None):
         _f32c(grad_image, self.device)
-        _f32c(grad_sdf, self.device)
+        if grad_sdf is not None:
+            _f32c(grad_sdf, self.device)
+        if grad_albedo is not None:
+            _f32c(grad_albedo, self.device)
         check(self.ctx, self.lib.sdfrt_adjoint_backprop(self.ctx, _ptr(film), _ptr(grad_image), _ptr(grad_sdf),
                                                         _ptr(grad_albedo), _ptr(grad_p), _stream(self.device)))
 
@@ -232,6 +247,10 @@ class Context:
                                                   _stream(self.device)))
         out = out.reshape(shape)
         return (out, iters.value) if return_iters else out
+
+    def redistance_status(self):
+        """Waits for the last asynchronous redistance and raises SdfrtError if the solver aborted."""
+        check(self.ctx, self.lib.sdfrt_redistance_status(self.ctx))
 
     def adam_step(self, param, grad, m, v, lr, t, beta1=0.9, beta2=0.999, eps=1e-8, grad_clamp=0.0, lo=1.0, hi=0.0):
         """In-place mi.ad.Adam.step on one tensor with the reference's gradient / value validation fused in."""

@@ -88,8 +88,22 @@ class ReparamIntegrator:
         self.last_film = film_a
         return ctx.develop(film), film_a
 
-    def backprop_adjoint_sweep(self, scene, film_a, grad_in):
+    def adjoint_sweep(self, scene, sensor, seed_grad, spp_grad):
+        """Adjoint sweep 1 alone (the re-render of render_backward): rebinds the view and refills the context's lane records."""
+        ctx = self._bind(scene, sensor)
+        self._check_wavefront(ctx, spp_grad)
+        self.last_film = ctx.adjoint_accumulate(seed_grad, spp_grad)
+        return self.last_film
+
+    def backprop_into(self, film_a, grad_in, grad_sdf, grad_albedo):
+        """Adjoint sweep 2 for the view whose records the context holds: ADDS into grad_sdf / grad_albedo (either may be None)
+        and into `sdf.p_grad` (the gradient w.r.t. the translation `sdf.p`, python/shapes.py:389)."""
         ctx = self.sdf.ctx
+        if not hasattr(self.sdf, 'p_grad') or self.sdf.p_grad is None:
+            self.sdf.p_grad = torch.zeros(3, dtype=torch.float32, device=ctx.device)
+        ctx.adjoint_backprop(film_a, grad_in.contiguous(), grad_sdf, grad_albedo, self.sdf.p_grad)
+
+    def backprop_adjoint_sweep(self, scene, film_a, grad_in):
         data = self.sdf.data
         if data.grad is None:
             data.grad = torch.zeros_like(data)
@@ -98,9 +112,7 @@ class ReparamIntegrator:
             if scene.albedo_grid.grad is None:
                 scene.albedo_grid.grad = torch.zeros_like(scene.albedo_grid)
             galb = scene.albedo_grid.grad
-        if not hasattr(self.sdf, 'p_grad') or self.sdf.p_grad is None:
-            self.sdf.p_grad = torch.zeros(3, dtype=torch.float32, device=ctx.device)
-        ctx.adjoint_backprop(film_a, grad_in.contiguous(), data.grad, galb, self.sdf.p_grad)
+        self.backprop_into(film_a, grad_in, data.grad, galb)
 
     def render_backward(self, scene, params, grad_in, sensor=0, seed=0, spp=0):
         """Accumulates dLoss/d(sdf.data) into `sdf.data.grad` (and the reflectance grid's .grad)."""

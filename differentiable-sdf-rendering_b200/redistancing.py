@@ -34,4 +34,7 @@ def redistance(phi, method='fastsweep', lower_bound=None, context=None):
     phi = phi.to(torch.float32).contiguous()
     if lower_bound is not None:
         lower_bound = torch.as_tensor(lower_bound, dtype=torch.float32).to(phi.device).contiguous()
-    return ctx.redistance(phi, lower_bound)
+    # synchronous on purpose: the solver's error word (barrier time-out / iteration cap) is checked before the grid is handed
+    # to the optimiser -- an aborted solve would leave unreached nodes at +-1e30
+    out, _ = ctx.redistance(phi, lower_bound, return_iters=True)
+    return out

@@ -40,7 +40,8 @@ def optimize_shape(scene, variables, ref_images, n_iter, spp=16, primal_spp_mult
     variables          list of variables.Variable (at least the SdfVariable for SDF_KEY)
     ref_images         per sensor: (H, W, 3) CUDA tensor or {width: tensor}
     loss               loss(img, ref) -> scalar tensor; default losses.l1
-    batch_size         sensors per iteration (default: all, in order; python/opt_configs.py:57-66 cycles through batches)
+    batch_size         sensors per iteration (default: all, in order); smaller batches are strided over the rig like
+                       get_sensor_iterator (python/opt_configs.py:57-66)
     resolution_schedule {iteration: (resx, resy)}: the `update_scene` hook of the scene configs (python/opt_configs.py:53-55)
     callback           callback(i, loss_value, opt) after every iteration
     """
@@ -62,9 +63,14 @@ def optimize_shape(scene, variables, ref_images, n_iter, spp=16, primal_spp_mult
     for i in range(n_iter):
         total = torch.zeros((), dtype=torch.float32, device=opt[SDF_KEY].device)
         opt.zero_grad()
-        first = (i * batch_size) % n_sensors
-        for b in range(batch_size):
-            idx = (first + b) % n_sensors
+        # python/opt_configs.py:57-66 (get_sensor_iterator): all sensors in order, or `batch_size` sensors strided over the rig
+        # ((j * steps + i % steps) % n) so that every mini-batch covers the full range of view angles
+        if batch_size >= n_sensors:
+            batch = list(range(n_sensors))
+        else:
+            steps = -(-n_sensors // batch_size)
+            batch = [(j * steps + i % steps) % n_sensors for j in range(batch_size)]
+        for idx in batch:
             img = render(scene, sensor=idx, seed=seed, spp=spp * primal_spp_mult, seed_grad=seed + 1 + n_sensors, spp_grad=spp)
             seed += 1 + n_sensors
             view_loss = loss_fn(img, _ref_for(ref_images[idx], sensors[idx].film().crop_size()[0])) / batch_size

@@ -150,9 +150,10 @@ class BoxSDF(SDFBase):
         return torch.linalg.norm(q.clamp_min(0.0), dim=-1) + q.max(-1).values.clamp_max(0.0) - self.smoothing
 
 
-def create_sphere_sdf(res, center=(0.5, 0.5, 0.5), radius=0.3, redistance=False):
-    """python/shapes.py:557-581 without noise.  The reference finishes with `redistancing.redistance` (:580); that pass needs
-    the GPU here, so it is opt-in (`redistance=True` returns a CUDA tensor), the default returns the analytic numpy grid."""
+def create_sphere_sdf(res, center=(0.5, 0.5, 0.5), radius=0.3, redistance=True):
+    """python/shapes.py:557-581 without noise.  Like the reference it finishes with `redistancing.redistance` (:580) and returns
+    the re-distanced grid (a CUDA tensor: the pass runs on the GPU); `redistance=False` is the explicit opt-out that returns the
+    analytic numpy grid (CPU-only tests)."""
     z, y, x = np.meshgrid(np.linspace(0, 1, res[0]), np.linspace(0, 1, res[1]), np.linspace(0, 1, res[2]), indexing='ij')
     pts = np.stack([x.ravel(), y.ravel(), z.ravel()], axis=1)
     sdf = np.reshape(np.linalg.norm(pts - np.asarray(center), axis=-1) - radius, res).astype(np.float32)

@@ -146,6 +146,17 @@ int sdfrt_set_prb(sdfrt_ctx* ctx, const sdfrt_prb_params* p);      /* used when 
  * wavefront lane index (python/integrators/reparam.py:51), so results do not depend on the world size. */
 int sdfrt_set_partition(sdfrt_ctx* ctx, int rank, int world);
 
+/* Validation hook: restrict adjoint sweep 2 (sdfrt_adjoint_backprop) to the wavefront lanes [lane_lo, lane_hi) -- lane =
+ * (pixel_y * (W+2b) + pixel_x) * spp + sample, python/integrators/reparam.py:141-155 -- so that the gradient contribution of a
+ * lane subsample can be compared with a reference that evaluates only those lanes.  (0, 0) = all lanes (default). */
+int sdfrt_set_lane_window(sdfrt_ctx* ctx, uint64_t lane_lo, uint64_t lane_hi);
+
+/* The conservative empty-space test (one brick-minimum DDA per film pixel; pixels whose sample rays provably never evaluate an
+ * SDF value below the hit / warp threshold are not marched) changes no result, only the work done.  enable = 0 marches every
+ * camera ray like the reference does (python/shapes.py:166-238), which makes the device counters of sdfrt_get_stats comparable
+ * with a count of the reference's evaluations.  Default: enabled. */
+int sdfrt_set_empty_space_skip(sdfrt_ctx* ctx, int enable);
+
 /* ---- rendering ---------------------------------------------------------------------- */
 /* film accumulator geometry: (H+2b, W+2b, 4) floats, b = border of the reconstruction filter */
 int sdfrt_film_dims(const sdfrt_ctx* ctx, int* height_b, int* width_b, int* border);
@@ -174,6 +185,11 @@ int sdfrt_render_view(sdfrt_ctx* ctx, uint32_t seed, int spp, float* film_primal
                       float* film_adjoint, void* stream);
 int sdfrt_adjoint_backprop(sdfrt_ctx* ctx, const float* film_accum, const float* grad_image,
                            float* grad_sdf, float* grad_albedo, float* grad_p, void* stream);
+/* The context keeps the lane records of ONE adjoint sweep 1 (the most recent sdfrt_adjoint_accumulate / sdfrt_render_view).
+ * Returns a token that changes with every such sweep and is 0 when no records are valid (no sweep yet, or a set_* call since):
+ * a caller that renders several views before back-propagating them (mi.render's CustomOp holds its inputs per view,
+ * python/shape_opt.py:78-83) compares tokens and re-runs sweep 1 of a view whose records were overwritten. */
+uint64_t sdfrt_adjoint_token(const sdfrt_ctx* ctx);
 
 /* device work counters accumulated since the last reset (synchronises `stream`) */
 int sdfrt_get_stats(sdfrt_ctx* ctx, sdfrt_stats* out, int reset, void* stream);
@@ -208,6 +224,9 @@ int sdfrt_eval_sdf(sdfrt_ctx* ctx, const float* x, int n, int order, float* out,
  * Asynchronous on `stream` unless iters_out (host int, optional: number of work lists the solver ran) is given. */
 int sdfrt_redistance(sdfrt_ctx* ctx, const float* phi, const float* lower_bound, float* out, int rx, int ry, int rz,
                      int* iters_out, void* stream);
+/* Outcome of the last asynchronous sdfrt_redistance (waits for it): SDFRT_OK, or SDFRT_ERR_CUDA if the solver aborted
+ * (grid barrier time-out / iteration cap) and `out` holds unreached nodes.  Also checked by the next sdfrt_redistance. */
+int sdfrt_redistance_status(sdfrt_ctx* ctx);
 
 /* mi.ad.Adam.step (python/shape_opt.py:53,102) for one parameter tensor of n floats with the reference's validation fused
  * in: gradient NaN scrub + clamp to [-grad_clamp, grad_clamp] (SdfVariable.validate_gradient, python/variables.py:193-199;

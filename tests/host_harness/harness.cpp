@@ -114,6 +114,12 @@ int hh_develop(const hh_scene* h, const float* film, float* image) {
     return 0;
 }
 
+// lane window of hh_backward (the host twin of sdfrt_set_lane_window); (0, 0) = all lanes
+static unsigned long long g_win_lo = 0ull, g_win_hi = ~0ull;
+void hh_set_lane_window(unsigned long long lo, unsigned long long hi) {
+    if (lo == 0ull && hi == 0ull) { g_win_lo = 0ull; g_win_hi = ~0ull; } else { g_win_lo = lo; g_win_hi = hi; }
+}
+
 int hh_backward(const hh_scene* h, unsigned seed, int spp, const float* film, const float* rec, const float* grad_image,
                 float* grad_sdf, float* grad_albedo, float* grad_p, unsigned long long* stats, int rank, int world) {
     SceneParams sc = build(h);
@@ -139,6 +145,7 @@ int hh_backward(const hh_scene* h, unsigned seed, int spp, const float* film, co
     const unsigned long long n = ps.n_items;
     for (unsigned long long k = 0; k < n; ++k) {
         const unsigned long long lane = decode_item(ps, k).lane;
+        if ((lane & ~kAntiBit) < g_win_lo || (lane & ~kAntiBit) >= g_win_hi) continue;
         SiteList sites;
         lane_backward(sc, ps, lane, adj.data(), rec + k, n, tg, gp, sites, st);
         for (int q = 0; q < sites.n; ++q) scatter_site(grad_sdf, sc.G, sites.s[q].x, sites.s[q].phi_hat, sites.s[q].g_hat);

@@ -141,7 +141,9 @@ class HostScene:
         lib().hh_develop(C.byref(self.h), fptr(film), fptr(img))
         return img
 
-    def backward(self, seed, spp, film, rec, grad_image, rank=0, world=1):
+    def backward(self, seed, spp, film, rec, grad_image, rank=0, world=1, lane_window=None):
+        lo, hi = lane_window if lane_window is not None else (0, 0)
+        lib().hh_set_lane_window(C.c_ulonglong(lo), C.c_ulonglong(hi))
         grad_image = np.ascontiguousarray(grad_image, dtype=np.float32)
         g = np.zeros_like(self.sdf)
         ga = None if self.albedo is None else np.zeros_like(self.albedo)

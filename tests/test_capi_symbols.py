@@ -56,7 +56,7 @@ def test_no_cpu_fallback(built):
     with pytest.raises(sdfrt.SdfrtError):
         sdfrt.Context(0)
     with pytest.raises(sdfrt.SdfrtError):
-        sdfrt.Grid3d(sdfrt.create_sphere_sdf((8, 8, 8)))
+        sdfrt.Grid3d(sdfrt.create_sphere_sdf((8, 8, 8), redistance=False))
 
 
 def test_facade_mirrors_reference_defaults():

@@ -153,10 +153,10 @@ def test_reconstruction_loop_moves_the_surface(sdfrt_mod):
     sdfrt = sdfrt_mod
     R, W = 16, 48
     sensors = sdfrt.get_regular_cameras(4, resx=W, resy=W)
-    target_sdf = sdfrt.Grid3d(sdfrt.create_sphere_sdf((32, 32, 32), radius=0.2), device=0)
+    target_sdf = sdfrt.Grid3d(sdfrt.create_sphere_sdf((32, 32, 32), radius=0.2, redistance=False), device=0)
     target_scene = sdfrt.Scene(sdfrt.integrators.create('sdf_direct_reparam', sdf=target_sdf), sensors)
     refs = [sdfrt.render(target_scene, sensor=i, seed=100 + i, spp=64) for i in range(4)]
-    sdf = sdfrt.Grid3d(sdfrt.create_sphere_sdf((R, R, R)), device=0)
+    sdf = sdfrt.Grid3d(sdfrt.create_sphere_sdf((R, R, R), redistance=False), device=0)
     integrator = sdfrt.integrators.create('sdf_direct_reparam', sdf=sdf)
     wf = sdfrt.WarpField2D(sdf, weight_strategy=6, edge_eps=0.01)
     wf.clamping_thresh = 0.05
@@ -173,7 +173,7 @@ def test_reconstruction_loop_moves_the_surface(sdfrt_mod):
     assert seen[5][1] == (R, R, R, 1) and seen[6][1] == (2 * R, 2 * R, 2 * R, 1)          # upsampled at iteration 6
     assert opt.t[sdfrt.shape_opt.SDF_KEY] == 1 and var.mean.shape == data.shape           # state reset by the new shape
     d = data[..., 0].detach().cpu().numpy()
-    inside_before = (sdfrt.create_sphere_sdf((2 * R,) * 3) < 0).mean()
+    inside_before = (sdfrt.create_sphere_sdf((2 * R,) * 3, redistance=False) < 0).mean()
     assert 0.2 * inside_before < (d < 0).mean() < 0.85 * inside_before   # the shape shrank towards the target (and is still there)
     box = sdfrt.synthetic.box_sdf_grid(2 * R).astype(np.float32)
     assert ((d < 0) & (box > 0)).sum() == 0               # bbox constraint holds

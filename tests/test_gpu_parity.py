@@ -150,7 +150,7 @@ def test_error_behaviour(sdfrt_mod):
     film = ctx.new_film()
     with pytest.raises(sdfrt_mod.SdfrtError):          # no SDF bound
         ctx.render_primal(0, 4, film)
-    sdf = torch.from_numpy(sdfrt_mod.create_sphere_sdf((16, 16, 16))).cuda()
+    sdf = torch.from_numpy(sdfrt_mod.create_sphere_sdf((16, 16, 16), redistance=False)).cuda()
     ctx.set_sdf(sdf)
     ctx.set_sensor(np.eye(4), 16, 16)
     film = ctx.new_film()
@@ -178,7 +178,7 @@ def test_empty_and_inside_cases(sdfrt_mod):
     film = ctx.adjoint_accumulate(1, 4)
     ctx.adjoint_backprop(film, torch.ones(16, 16, 3, device='cuda'), g)
     assert torch.isfinite(g).all()
-    ctx.set_sdf(torch.from_numpy(sdfrt_mod.create_sphere_sdf((16, 16, 16))).cuda())
+    ctx.set_sdf(torch.from_numpy(sdfrt_mod.create_sphere_sdf((16, 16, 16), redistance=False)).cuda())
     ctx.set_sensor(sdfrt_mod.look_at([0.5, 0.5, 0.02], [0.5, 0.5, 0.5], [0, 1, 0]), 16, 16)
     img = ctx.develop(ctx.render_primal(0, 4))
     assert torch.isfinite(img).all() and img[8, 8].sum() < 3.0       # the sphere is seen from inside the bbox
@@ -251,7 +251,7 @@ def test_gradient_matches_finite_differences_of_the_loss(sdfrt_mod):
     sensors = sdfrt.get_regular_cameras(6, resx=W, resy=W)
 
     def make(radius):
-        sdf = sdfrt.Grid3d(sdfrt.create_sphere_sdf((R, R, R), radius=radius), device=0)
+        sdf = sdfrt.Grid3d(sdfrt.create_sphere_sdf((R, R, R), radius=radius, redistance=False), device=0)
         integ = sdfrt.integrators.create('sdf_direct_reparam', sdf=sdf)
         wf = sdfrt.WarpField2D(sdf, weight_strategy=6, edge_eps=0.01)
         wf.clamping_thresh = 0.05
