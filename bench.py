@@ -4,7 +4,10 @@
 Step = one optimisation-loop view as python/shape_opt.py:78-83 drives it: primal render at
 spp*primal_spp_mult (256) + adjoint re-render/backprop at spp_grad (64), 256^3 SDF + 256^3x3 reflectance
 grid, 512x512 film (BASELINE.json configs[2], the configuration the metric is quoted on).
-Prints ONE JSON line (rank 0).  `--impl reference` times the CPU oracle (the restated reference) instead.
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU port of the restated reference instead.
+
+The line also carries (rank 0): `grad_check` = the metric's "grad MSE vs ref" on a fixed lane subsample against the fp64 oracle,
+`secondary` = short runs of BASELINE configs[3] (512^3) and configs[4] (sdf_prb_reparam) at the same N.
 """
 import argparse
 import json
@@ -23,15 +26,22 @@ WORKLOADS = {
     'c2_blobs128_256x256_16spp': ('blobs', 128, None, 256, 256, 16, 4, 12),
     'c1_sphere64_128x128_4spp': ('sphere', 64, None, 128, 128, 4, 4, 6),
     'c4_blobs512_512x512_64spp': ('blobs', 512, None, 512, 512, 64, 4, 12),
-    # BASELINE configs[4] (sdf_prb_reparam, 2-bounce GI): secondary line, `python bench.py --workload c5_...`
+    # BASELINE configs[4] (sdf_prb_reparam, 2-bounce GI)
     'c5_prb_blobs256_512x512_128spp': ('blobs', 256, None, 512, 512, 128, 1, 12),
 }
 PRB_WORKLOADS = {'c5_prb_blobs256_512x512_128spp': dict(max_depth=3, rr_depth=5)}  # camera hit + 2 bounces
+SECONDARY = ('c4_blobs512_512x512_64spp', 'c5_prb_blobs256_512x512_128spp')
 METRIC = "primary+adjoint Mrays/s"
 # dram__bytes_read + dram__bytes_write of the k_march launches of ONE c3 step, from the committed ncu launch list
-# (segment arrays, lane records and the L2 misses of the row-expanded grid copy; before that copy: 5.6 GB,
-# profiles/r1_final_launches_c3.csv).  Only meaningful for the default workload.
-NCU_DRAM_BYTES_PER_STEP = {'c3_blobs256_tex_512x512_64spp': 11.95e9}  # profiles/r1_launches_rows4_c3.csv: 24 k_march launches per step
+NCU_DRAM_BYTES_PER_STEP = {'c3_blobs256_tex_512x512_64spp': (11.95e9, 'profiles/r1_launches_rows4_c3.csv')}
+# what binds each kernel, from the committed `ncu --set full` captures (profiles/): unit and its % of peak
+BINDING = {
+    'k_march<0,1,1> primary segments': {"unit": "issue + L1 (l1tex__throughput)", "pct": 76, "issue_active_pct": 56, "source": "profiles/r1_final_march.md"},
+    'k_march<0,1,1> shadow segments': {"unit": "L1 tag stage (l1tex__throughput), scattered 16 B gathers", "pct": 95, "issue_active_pct": 25, "source": "profiles/r1_final_march.md"},
+    'k_march<1,0,1> primary segments (differentiable)': {"unit": "issue (smsp__issue_active)", "pct": 77, "source": "profiles/r1_wavefront_march_diff_primary_vs_shadow.md"},
+    'k_march<1,1,1> shadow segments (differentiable)': {"unit": "L1 (l1tex__throughput)", "pct": 89, "source": "profiles/r1_wavefront_march_diff_primary_vs_shadow.md"},
+    'k_backward': {"unit": "RED queue (lg_throttle), grouped transposed scatter", "pct": None, "source": "profiles/r1_backward_direct_atomics.md"},
+}
 
 
 def parse():
@@ -42,6 +52,9 @@ def parse():
     ap.add_argument('--impl', default='sdfrt', choices=['sdfrt', 'reference'])
     ap.add_argument('--workload', default='c3_blobs256_tex_512x512_64spp', choices=list(WORKLOADS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-secondary', action='store_true', help='skip the short c4 / c5 records')
+    ap.add_argument('--no-grad-check', action='store_true', help='skip the lane-subsample gradient check against the oracle')
+    ap.add_argument('--no-e2e', action='store_true', help='profiling runs: skip the host-buffer leg')
     return ap.parse_args()
 
 
@@ -91,6 +104,10 @@ class ClockSampler:
 _CPU_SCENE = {}
 
 
+def host_cores():
+    return len(os.sched_getaffinity(0))
+
+
 def cpu_scene(wl):
     if wl not in _CPU_SCENE:
         import sdfrt
@@ -104,12 +121,14 @@ def cpu_scene(wl):
 
 
 def cpu_sample(wl, n_primal, seed):
-    """`n_primal` primal + n_primal/mult adjoint lanes (the workload's 4:1 ratio) from the centre of the wavefronts."""
+    """`n_primal` primal + n_primal/mult adjoint lanes (the workload's 4:1 ratio), in chunks of 64 consecutive samples strided over
+    the WHOLE wavefronts (bounding-box misses, empty space, grazing rays and hits in the workload's proportions), on all host
+    cores of the affinity mask (set explicitly: torchrun exports OMP_NUM_THREADS=1)."""
     from oracle import cpu_port
     kind, R, AR, W, H, spp, mult, nsens = WORKLOADS[wl]
     sdf, alb, tw = cpu_scene(wl)
     r = cpu_port.time_sample(sdf, alb, tw, W, H, seed, spp * mult, spp, n_primal, max(spp, n_primal // mult),
-                             prb=PRB_WORKLOADS.get(wl))
+                             prb=PRB_WORKLOADS.get(wl), threads=host_cores())
     r['seconds'] = r['seconds_primal'] + r['seconds_adjoint']
     return r
 
@@ -123,34 +142,43 @@ def cpu_calibrated_sample(wl, target_s, seed=100):
     return n, cpu_sample(wl, n, seed)
 
 
+def cpu_record(wl, n, r, kind_note):
+    mult, spp = WORKLOADS[wl][6], WORKLOADS[wl][5]
+    return {"value": r['rays'] / r['seconds'] / 1e6, "unit": "Mrays/s", "cores": r['threads'], "kind": "port",
+            "sample": f"{n} primal + {max(spp, n // mult)} adjoint lanes, 64-sample chunks strided over the whole wavefronts, "
+                      f"{r['seconds']:.1f} s; every ray marched (no empty-space cull); {kind_note} ({r['build']})",
+            "evals_per_s": r['evals'] / r['seconds'], "hit_fraction": r['hits'] / r['rays']}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation.  Mitsuba llvm_ad_rgb cannot be installed offline, so this is
     the compiled CPU port of the restated reference algorithm on all host cores (kind = "port")."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    cores = len(os.sched_getaffinity(0))
-    os.environ.setdefault('OMP_NUM_THREADS', str(cores))
     wl = args.workload
     mult = WORKLOADS[wl][6]
     n, _ = cpu_calibrated_sample(wl, 8.0 / max(1, args.steps))   # also the warm-up
     for w in range(max(0, args.warmup - 1)):
         cpu_sample(wl, max(1 << 16, n // 8), w)
-    rays = secs = 0.0
-    threads = cores
+    rays = secs = evals = hits = 0.0
+    threads, how = host_cores(), ''
     for s in range(args.steps):
         r = cpu_sample(wl, n, 100 + s)
         rays += r['rays']
         secs += r['seconds']
-        threads = r['threads']
+        evals += r['evals']
+        hits += r['hits']
+        threads, how = r['threads'], r['build']
     val = rays / secs / 1e6
-    sample = f"{n} primal + {max(WORKLOADS[wl][5], n // mult)} adjoint lanes per step from the wavefront centre"
+    sample = (f"{n} primal + {max(WORKLOADS[wl][5], n // mult)} adjoint lanes per step, 64-sample chunks strided over the whole "
+              f"wavefronts; every ray marched; g++ {how}")
     line = {"metric": METRIC, "value": val, "unit": "Mrays/s", "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl, "note": "compiled CPU port of the restated reference (g++ -O3 -fopenmp); "
-                                               "Mitsuba llvm_ad_rgb is not installable offline"},
-            "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": sample},
+            "config": {"workload": wl, "note": "compiled CPU port of the restated reference; Mitsuba llvm_ad_rgb is not installable offline"},
+            "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": sample,
+                             "evals_per_s": evals / secs, "hit_fraction": hits / rays},
             "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -158,166 +186,236 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
-def run_gpu(args):
-    import numpy as np
-    import torch
-    import torch.distributed as dist
-    import sdfrt
-    from sdfrt import synthetic as syn
+class Job:
+    """One workload bound to a context: buffers + the step function (device buffers resident; one optimisation-loop view)."""
 
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("launch with torch.distributed.run for --gpus > 1")
-    torch.cuda.set_device(local)
-    dev = torch.device('cuda', local)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
+    def __init__(self, wl, local, rank, world):
+        import torch
+        import sdfrt
+        from sdfrt import synthetic as syn
+        self.torch, self.sdfrt = torch, sdfrt
+        self.wl, self.rank, self.world = wl, rank, world
+        kind, R, AR, W, H, spp, mult, nsens = WORKLOADS[wl]
+        self.R, self.AR, self.W, self.H, self.spp, self.mult, self.nsens = R, AR, W, H, spp, mult, nsens
+        self.dev = dev = torch.device('cuda', local)
+        self.prb = PRB_WORKLOADS.get(wl)
+        self.ctx = ctx = sdfrt.Context(local)
+        self.sdf = syn.make_sdf_device(kind, R, dev)
+        self.alb = None if AR is None else torch.from_numpy(syn.make_albedo_grid(AR)).to(dev)
+        self.sensor = sdfrt.get_regular_cameras(nsens, resx=W, resy=H)[0]
+        ctx.set_sdf(self.sdf)
+        ctx.set_albedo(self.alb)
+        ctx.set_sensor(self.sensor.to_world, W, H)
+        ctx.set_shading()
+        if self.prb:
+            ctx.set_integrator('sdf_prb_reparam')
+            ctx.set_prb(**self.prb)
+        else:
+            ctx.set_integrator('sdf_direct_reparam')
+        ctx.set_warp()
+        ctx.set_partition(rank, world)
+        Hb, Wb, b = ctx.film_dims()
+        self.n_primal, self.n_adj = Hb * Wb * spp * mult, Hb * Wb * spp
+        self.rays_per_step = self.n_primal + self.n_adj
+        self.film_p, self.film_a = ctx.new_film(), ctx.new_film()
+        self.image = torch.empty((H, W, 3), device=dev)
+        self.grad_image = torch.ones((H, W, 3), device=dev)  # loss = dr.sum(img), figures/benchmark/benchmark.py:44
+        self.grad_sdf = torch.zeros_like(self.sdf)
+        self.grad_alb = None if self.alb is None else torch.zeros_like(self.alb)
+        self.stream = torch.cuda.current_stream(dev)
+        self.pending = None
 
-    kind, R, AR, W, H, spp, mult, nsens = WORKLOADS[args.workload]
-    ctx = sdfrt.Context(local)
-    sdf = syn.make_sdf_device(kind, R, dev)
-    alb = None if AR is None else torch.from_numpy(syn.make_albedo_grid(AR)).to(dev)
-    sensor = sdfrt.get_regular_cameras(nsens, resx=W, resy=H)[0]
-    ctx.set_sdf(sdf)
-    ctx.set_albedo(alb)
-    ctx.set_sensor(sensor.to_world, W, H)
-    ctx.set_shading()
-    ctx.set_integrator('sdf_direct_reparam')
-    ctx.set_warp()
-    ctx.set_partition(rank, world)
-    Hb, Wb, b = ctx.film_dims()
-    n_primal, n_adj = Hb * Wb * spp * mult, Hb * Wb * spp
-    film_p, film_a = ctx.new_film(), ctx.new_film()
-    image = torch.empty((H, W, 3), device=dev)
-    grad_image = torch.ones((H, W, 3), device=dev)  # loss = dr.sum(img), figures/benchmark/benchmark.py:44
-    grad_sdf = torch.zeros_like(sdf)
-    grad_alb = None if alb is None else torch.zeros_like(alb)
-    stream = torch.cuda.current_stream(dev)
-
-    ev = {k: [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)] for k in ('p0', 'p1', 'a0', 'a1', 'b1')}
-
-    def step(i, seed, timed):
-        # primal render (spp * mult) and adjoint sweep 1 (spp_grad) are independent: one pipelined call (sdfrt_render_view)
-        if timed:
-            ev['p0'][i].record(stream)
-        ctx.render_view(seed, spp * mult, seed + 1 + nsens, spp, film_p, film_a)
+    def step(self, seed, ev=None):
+        """primal render (spp * mult) and adjoint sweep 1 (spp_grad) in one pipelined call, film all-reduces, develop, adjoint
+        sweep 2, gradient all-reduce (the one large collective per backward)."""
+        import torch.distributed as dist
+        ctx, world = self.ctx, self.world
+        if ev:
+            ev[0].record(self.stream)
+        ctx.render_view(seed, self.spp * self.mult, seed + 1 + self.nsens, self.spp, self.film_p, self.film_a)
         if world > 1:
-            dist.all_reduce(film_p)
-            dist.all_reduce(film_a)
-        ctx.develop(film_p, image)
-        if timed:
-            ev['p1'][i].record(stream)
-        grad_sdf.zero_()
-        if grad_alb is not None:
-            grad_alb.zero_()
-        if timed:
-            ev['a1'][i].record(stream)
-        ctx.adjoint_backprop(film_a, grad_image, grad_sdf, grad_alb)
+            dist.all_reduce(self.film_p)
+            dist.all_reduce(self.film_a)
+        ctx.develop(self.film_p, self.image)
+        if ev:
+            ev[1].record(self.stream)
+        self.grad_sdf.zero_()
+        if self.grad_alb is not None:
+            self.grad_alb.zero_()
+        ctx.adjoint_backprop(self.film_a, self.grad_image, self.grad_sdf, self.grad_alb)
         if world > 1:
-            dist.all_reduce(grad_sdf)
-            if grad_alb is not None:
-                dist.all_reduce(grad_alb)
-        if timed:
-            ev['b1'][i].record(stream)
+            dist.all_reduce(self.grad_sdf)
+            if self.grad_alb is not None:
+                dist.all_reduce(self.grad_alb)
+        if ev:
+            ev[2].record(self.stream)
 
-    for w in range(args.warmup):
-        step(0, w * (1 + nsens), False)
-    torch.cuda.synchronize(dev)
-    ctx.stats(reset=True)
-    if world > 1:
-        dist.barrier()
-    t0 = torch.cuda.Event(enable_timing=True)
-    t1 = torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clk:
-        torch.cuda.synchronize(dev)
-        t0.record(stream)
-        for s in range(args.steps):
-            step(s, 1000 + s * (1 + nsens), True)
-        t1.record(stream)
-        torch.cuda.synchronize(dev)
-    if world > 1:
-        dist.barrier()
-    ms = t0.elapsed_time(t1)
-    tt = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    ms = tt.item()
-    stats = ctx.stats(reset=True)
-    rays_per_step = n_primal + n_adj
-    value = rays_per_step * args.steps / (ms * 1e-3) / 1e6
+    def timed(self, steps, warmup, clocks=False):
+        """W untimed steps, then exactly K steps bracketed by barrier + synchronize; device time, max over ranks."""
+        torch = self.torch
+        import torch.distributed as dist
+        for w in range(warmup):
+            self.step(w * (1 + self.nsens))
+        torch.cuda.synchronize(self.dev)
+        self.ctx.stats(reset=True)
+        if self.world > 1:
+            dist.barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+        clk = ClockSampler(self.dev.index) if clocks else None
+        if clk:
+            clk.__enter__()
+        torch.cuda.synchronize(self.dev)
+        t0.record(self.stream)
+        for s in range(steps):
+            self.step(1000 + s * (1 + self.nsens), ev[s])
+        t1.record(self.stream)
+        torch.cuda.synchronize(self.dev)
+        if clk:
+            clk.__exit__()
+        if self.world > 1:
+            dist.barrier()
+        ms = t0.elapsed_time(t1)
+        tt = torch.tensor([ms], device=self.dev, dtype=torch.float64)
+        if self.world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = tt.item()
+        stats = self.ctx.stats(reset=True)
+        t_fwd = sum(e[0].elapsed_time(e[1]) for e in ev) / steps
+        t_bwd = sum(e[1].elapsed_time(e[2]) for e in ev) / steps
+        return ms, stats, {"primal+adjoint_sweep1": t_fwd, "adjoint_backprop+grad_allreduce": t_bwd}, (clk.summary() if clk else None)
 
-    # per-kernel timings (this rank; CUDA events recorded by the library on the launching stream, inside the timed
-    # region) and the roofline of the dominant kernel
-    t_forward = sum(ev['p0'][i].elapsed_time(ev['p1'][i]) for i in range(args.steps)) / args.steps
-    t_back = sum(ev['a1'][i].elapsed_time(ev['b1'][i]) for i in range(args.steps)) / args.steps
-    # second timed loop, batches serialised on the launching stream so that the per-launch CUDA-event durations are additive
-    ctx.set_overlap(False)
-    ctx.set_profiling(True)
-    ctx.timing()
-    step(0, 7, False)
-    torch.cuda.synchronize(dev)
-    ctx.timing()
-    ctx.stats(reset=True)
-    for s_ in range(args.steps):
-        step(s_, 1000 + s_ * (1 + nsens), True)
-    torch.cuda.synchronize(dev)
-    stats = ctx.stats(reset=True)
-    kt = ctx.timing()
-    ctx.set_profiling(False)
-    ctx.set_overlap(True)
-    kernel_ms = {k: v[0] / args.steps for k, v in kt.items()}
-    kernel_ms['k_march (primary+shadow segments)'] = kernel_ms.pop('march_primary') + kernel_ms.pop('march_shadow')
-    launches_per_step = sum(v[1] for v in kt.values()) / args.steps
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
-    except Exception:
-        pass
-    peak = float(peaks.get('hbm_gbs', 6650.0))
-    peak_src = 'measured' if 'hbm_gbs' in peaks else 'fallback'
-    dom = max(kernel_ms, key=kernel_ms.get)
-    # algorithmic bytes of k_march: one 4x4x4 fp32 neighbourhood = 256 B per B-spline evaluation it performs
-    march_evals = (stats['n_evals_value'] + stats['n_evals_hess']) / args.steps
-    march_bytes = 256.0 * march_evals
-    march_ms = kernel_ms['k_march (primary+shadow segments)']
+    def kernel_split(self, steps):
+        """Per-kernel CUDA-event timings (recorded by the library on the launching streams) over `steps` steps run exactly like the
+        timed region (batches overlapping on the internal streams): summed launch durations and, per class, the union of the launch
+        intervals -- the time that class was on the device."""
+        torch, ctx = self.torch, self.ctx
+        ctx.set_profiling(True)
+        ctx.timing()
+        self.step(7)
+        torch.cuda.synchronize(self.dev)
+        ctx.timing()
+        ctx.stats(reset=True)
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record(self.stream)
+        for s in range(steps):
+            self.step(1000 + s * (1 + self.nsens))
+        t1.record(self.stream)
+        torch.cuda.synchronize(self.dev)
+        stats = ctx.stats(reset=True)
+        kt = ctx.timing(union=True)
+        ctx.set_profiling(False)
+        return kt, stats, t0.elapsed_time(t1) / steps
+
+    def close(self):
+        self.ctx = None
+        for k in ('sdf', 'alb', 'grad_sdf', 'grad_alb', 'film_p', 'film_a', 'image', 'grad_image'):
+            setattr(self, k, None)
+        self.torch.cuda.empty_cache()
+
+
+def march_roofline(job, kt, stats, steps, peak, peak_src, loop_ms):
+    kernel_ms = {k: v[0] / steps for k, v in kt.items() if k != 'march_all'}
+    union_ms = {k: v[2] / steps for k, v in kt.items()}
+    march_evals = (stats['n_evals_value'] + stats['n_evals_hess']) / steps
+    march_bytes = 256.0 * march_evals          # SURVEY 8d: one 4x4x4 fp32 neighbourhood per B-spline evaluation
+    march_ms = union_ms['march_all']
     achieved = march_bytes / (march_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": NCU_DRAM_BYTES_PER_STEP.get(args.workload), "peak_source": peak_src, "kernel": "k_march (all launches of one step; batches serialised for this measurement)",
-                "dominant_kernel": dom, "kernel_ms_per_step": kernel_ms, "pass_ms": {"primal+adjoint_sweep1": t_forward, "adjoint_backprop": t_back},
-                "algorithmic_bytes_per_step": march_bytes, "evals_per_step": march_evals,
-                "note": "fetch-level bytes: 256 B per B-spline evaluation; the SDF grid is L2-resident at <= 256^3, so the fetches are "
-                        "served by L1/L2 and frac can exceed 1; `traffic` is the ncu dram__bytes of the same launches (profiles/)"}
+    traffic = NCU_DRAM_BYTES_PER_STEP.get(job.wl)
+    launches = sum(v[1] for k, v in kt.items() if k != 'march_all') / steps
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": traffic[0] if traffic else None, "traffic_source": traffic[1] if traffic else None, "peak_source": peak_src,
+            "kernel": "k_march: all launches of one step",
+            "kernel_ms": march_ms, "kernel_ms_how": "union of the k_march launch intervals (CUDA events recorded by the library around every "
+                                                    "launch), steps run as in the timed region with overlapping batches",
+            "profiled_loop_ms_per_step": loop_ms,
+            "launch_ms_sum_per_step": kernel_ms, "launch_ms_union_per_step": union_ms,
+            "algorithmic_bytes_per_step": march_bytes, "evals_per_step": march_evals,
+            "frac_vs_timed_step": None,
+            "binding": BINDING,
+            "note": "fetch-level bytes: 256 B per B-spline evaluation; the 256^3 grid is L2-resident, so the fetches are served by "
+                    "L1/L2 (43 % by the register tap cache) and the figure is NOT an HBM utilisation: `traffic` is the ncu dram__bytes "
+                    "of the same launches; `binding` names the unit that limits each kernel (ncu --set full, profiles/)"}, launches
 
-    # e2e: HOST buffers in, host buffers out, copies inside the timed region.
-    #  N = 1: the host-buffer C-ABI entry point sdfrt_render_view_host (H2D sdf; D2H image + grad_sdf every step)
-    #  N > 1: the Python mirror's multi-GPU path (sdfrt.dist.render_view): every rank uploads the grid from pinned host memory,
-    #         renders its film rows, NCCL all-reduces film and gradient, rank 0 downloads image + gradient.
-    e2e = None
-    e_steps = max(1, min(args.steps, 5))
-    sdf_h = sdf.cpu().pin_memory()
-    img_h = torch.empty((H, W, 3)).pin_memory()
-    g_h = torch.empty((R, R, R)).pin_memory()
-    if world == 1:
+
+def grad_check(job, n_lanes=16384):
+    """Metric: "...; grad MSE vs ref".  A fixed window of wavefront lanes through the middle of the film (256 pixels x 64 spp at c3):
+    sdfrt_adjoint_backprop restricted to those lanes (sdfrt_set_lane_window) under the completed film of the whole re-render, against
+    the fp64 oracle evaluating the same lanes (oracle/window_check.py).  Whole wavefront on this rank (partition 0 of 1)."""
+    import numpy as np
+    torch = job.torch
+    from oracle import sdf_oracle as O
+    from oracle import window_check as WC
+    ctx = job.ctx
+    t0 = time.time()
+    ctx.set_partition(0, 1)
+    sens = O.Sensor(to_world=job.sensor.to_world, width=job.W, height=job.H)
+    osc = O.Scene(sdf=O.Grid3d(job.sdf.cpu().double()), sensor=sens, albedo_grid=None if job.alb is None else job.alb.cpu().double())
+    owf = O.WarpField2D(osc.sdf, weight_strategy=6, edge_eps=0.01)
+    owf.clamping_thresh = 0.05
+    lo, hi = WC.centre_window(sens, job.spp, n_lanes)
+    G = np.random.default_rng(4).uniform(-1, 1, size=(job.H, job.W, 3)).astype(np.float32)
+    seed_grad = 13
+    film = ctx.adjoint_accumulate(seed_grad, job.spp)
+    ctx.set_lane_window(lo, hi)
+    g = torch.zeros_like(job.sdf)
+    ga = None if job.alb is None else torch.zeros_like(job.alb)
+    ctx.adjoint_backprop(film, torch.from_numpy(G).to(job.dev), g, ga)
+    ctx.set_lane_window(0, 0)
+    ctx.set_partition(job.rank, job.world)
+    _, g_o, ga_o = WC.window_gradient(osc, owf, 'sdf_direct_reparam', film.cpu().numpy(), G, seed_grad, job.spp, (lo, hi))
+    out = {"vs": "fp64 oracle (oracle/sdf_oracle.py, torch autograd) on the same lanes", "lanes": [lo, hi],
+           "grad_image": "uniform(-1,1), seed 4", "sdf": WC.gradient_errors(g.cpu().numpy(), g_o.numpy())}
+    if ga is not None:
+        out["reflectance"] = WC.gradient_errors(ga.cpu().numpy(), ga_o.numpy())
+    out["grad_mse_vs_oracle"] = out["sdf"]["mse"]
+    out["grad_max_rel"] = out["sdf"]["max_abs_over_ref_max"]
+    out["seconds"] = time.time() - t0
+    return out
+
+
+def e2e_leg(job, steps):
+    """Host buffers in, host buffers out, copies inside the timed region.
+      N = 1: the host-buffer C-ABI entry point (sdfrt_render_view_host_ex): H2D sdf (+ reflectance grid), D2H image + both gradients
+      N > 1: sdfrt.dist.render_view: every rank uploads the grids from pinned host memory, renders its film rows, NCCL all-reduces
+             film and gradients, rank 0 downloads image + gradients."""
+    torch, sdfrt = job.torch, job.sdfrt
+    import torch.distributed as dist
+    e_steps = max(1, min(steps, 5))
+    sdf_h = job.sdf.cpu().pin_memory()
+    alb_h = None if job.alb is None else job.alb.cpu().pin_memory()
+    img_h = torch.empty((job.H, job.W, 3)).pin_memory()
+    g_h = torch.empty(tuple(job.sdf.shape)).pin_memory()
+    ga_h = None if job.alb is None else torch.empty(tuple(job.alb.shape)).pin_memory()
+    nsens, spp, mult = job.nsens, job.spp, job.mult
+    if job.world == 1:
+        def one(seed):
+            job.ctx.render_view_host(sdf_h, seed, spp * mult, seed + 1 + nsens, spp, None, img_h, g_h, albedo_host=alb_h, grad_albedo_host=ga_h)
         for w in range(2):
-            ctx.render_view_host(sdf_h, w, spp * mult, w + 1 + nsens, spp, None, img_h, g_h)
-        torch.cuda.synchronize(dev)
+            one(w)
+        torch.cuda.synchronize(job.dev)
         tw = time.perf_counter()
         for s in range(e_steps):
-            ctx.render_view_host(sdf_h, 1000 + s, spp * mult, 1001 + s + nsens, spp, None, img_h, g_h)
+            one(1000 + s)
         tw = time.perf_counter() - tw
-        ctx.set_sdf(sdf)
+        job.ctx.set_sdf(job.sdf)
+        job.ctx.set_albedo(job.alb)
+        api = "sdfrt_render_view_host_ex"
     else:
         def one(seed):
-            sdf.copy_(sdf_h, non_blocking=True)
-            grad_sdf.zero_()
-            img = sdfrt.dist.render_view(ctx, seed, spp * mult, seed + 1 + nsens, spp, lambda im: grad_image, grad_sdf)
-            if rank == 0:
+            job.sdf.copy_(sdf_h, non_blocking=True)
+            if alb_h is not None:
+                job.alb.copy_(alb_h, non_blocking=True)
+            job.grad_sdf.zero_()
+            if job.grad_alb is not None:
+                job.grad_alb.zero_()
+            img = sdfrt.dist.render_view(job.ctx, seed, spp * mult, seed + 1 + nsens, spp, lambda im: job.grad_image, job.grad_sdf, job.grad_alb)
+            if job.rank == 0:
                 img_h.copy_(img, non_blocking=True)
-                g_h.copy_(grad_sdf, non_blocking=True)
-            torch.cuda.synchronize(dev)
+                g_h.copy_(job.grad_sdf, non_blocking=True)
+                if ga_h is not None:
+                    ga_h.copy_(job.grad_alb, non_blocking=True)
+            torch.cuda.synchronize(job.dev)
         for w in range(2):
             one(w)
         dist.barrier()
@@ -326,188 +424,181 @@ def run_gpu(args):
             one(1000 + s)
         dist.barrier()
         tw = time.perf_counter() - tw
-        twt = torch.tensor([tw], device=dev, dtype=torch.float64)
+        twt = torch.tensor([tw], device=job.dev, dtype=torch.float64)
         dist.all_reduce(twt, op=dist.ReduceOp.MAX)
         tw = twt.item()
-    e2e = {"value": rays_per_step * e_steps / tw / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": sdf_h.numel() * 4 * world,
-           "d2h_bytes_per_step": img_h.numel() * 4 + g_h.numel() * 4, "steps": e_steps,
-           "api": "sdfrt_render_view_host" if world == 1 else "sdfrt.dist.render_view"}
-
-    cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = len(os.sched_getaffinity(0))
-        os.environ.setdefault('OMP_NUM_THREADS', str(cores))
-        n, r = cpu_calibrated_sample(args.workload, 12.0)
-        cpu_baseline = {"value": r['rays'] / r['seconds'] / 1e6, "unit": "Mrays/s", "cores": r['threads'], "kind": "port",
-                        "sample": f"{n} primal + {max(spp, n // mult)} adjoint lanes from the wavefront centre, {r['seconds']:.1f} s; "
-                                  "compiled CPU port (g++ -O3 -fopenmp) of the restated reference"}
-
-    # second metric (protocol of figures/benchmark/benchmark.py:120-144): the per-iteration grid update on the
-    # workload's SDF grid -- re-distancing (mean of 5, CUDA events) and the fused Adam step; the CPU side is the C oracle
-    grid_update = None
-    if rank == 0 and world == 1:
-        gctx = sdfrt.redistancing.shared_context(local)
-        phi = (sdf.reshape(R, R, R) * 1.7).contiguous()
-        for _ in range(2):
-            gctx.redistance(phi)
-        gev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-        torch.cuda.synchronize()
-        gev[0].record()
-        for _ in range(5):
-            dist_t = gctx.redistance(phi)
-        gev[1].record()
-        torch.cuda.synchronize()
-        rd_ms = gev[0].elapsed_time(gev[1]) / 5
-        _, lists = gctx.redistance(phi, return_iters=True)
-        pp = phi.clone().reshape(-1)
-        gg, mm, vv = torch.randn_like(pp) * 0.01, torch.zeros_like(pp), torch.zeros_like(pp)
-        gctx.adam_step(pp, gg, mm, vv, 4e-2, 1, grad_clamp=0.1)
-        torch.cuda.synchronize()
-        gev[0].record()
-        for t in range(2, 7):
-            gctx.adam_step(pp, gg, mm, vv, 4e-2, t, grad_clamp=0.1)
-        gev[1].record()
-        torch.cuda.synchronize()
-        adam_ms = gev[0].elapsed_time(gev[1]) / 5
-        grid_update = {"sdf_res": R, "redistance_ms": rd_ms, "redistance_work_lists": lists, "adam_step_ms": adam_ms,
-                       "adam_step_GBps": 7 * 4 * pp.numel() / adam_ms / 1e6}
-        if not args.no_cpu_baseline:
-            from oracle import redistance_oracle as ro
-            sub = phi[:: max(1, R // 128), :: max(1, R // 128), :: max(1, R // 128)].contiguous().cpu().numpy()
-            t0 = time.time()
-            want = ro.redistance(sub)
-            grid_update["cpu_redistance_ms"] = (time.time() - t0) * 1e3
-            grid_update["cpu_sample"] = f"C oracle (1 thread) on the grid subsampled to {sub.shape[0]}^3"
-            got = gctx.redistance(torch.from_numpy(sub).cuda()).cpu().numpy()
-            grid_update["max_abs_diff_vs_oracle"] = float(np.abs(got - want).max())
-
-    if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic",
-                "config": {"workload": args.workload, "sdf_res": R, "albedo_res": AR, "film": [W, H], "spp_primal": spp * mult,
-                           "spp_adjoint": spp, "rays_per_step": rays_per_step, "partition": f"interleaved 8-row film bands x{world}",
-                           "l2": "inputs (sdf+albedo+grads+lane records > 1 GB) exceed L2; no explicit flush"},
-                "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(round(launches_per_step * args.steps)),
-                "roofline": roofline, "cpu_baseline": cpu_baseline, "stats_per_step": {k: v / args.steps for k, v in stats.items()},
-                "grid_update": grid_update}
-        print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+        api = "sdfrt.dist.render_view"
+    h2d = (sdf_h.numel() + (alb_h.numel() if alb_h is not None else 0)) * 4 * job.world
+    d2h = (img_h.numel() + g_h.numel() + (ga_h.numel() if ga_h is not None else 0)) * 4
+    return {"value": job.rays_per_step * e_steps / tw / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "steps": e_steps, "api": api}
 
 
-def run_gpu_prb(args):
-    """Secondary line: the path replay integrator in its first, one-thread-per-sample form.  Same step
-    structure and timing rules as the headline (primal + re-render in one call, then the replay/backprop), camera samples
-    counted as rays; no roofline claim yet -- the wavefront form on k_march is the next step."""
+def secondary_record(wl, local, rank, world, peak):
+    """A short run (1 warm-up + 3 timed steps, same timing rules) of another BASELINE config at the same N."""
+    job = Job(wl, local, rank, world)
+    steps = 3
+    ms, stats, passes, _ = job.timed(steps, 1)
+    evals = (stats['n_evals_value'] + stats['n_evals_grad'] + stats['n_evals_hess'] + stats['n_evals_adjoint']) / steps
+    rec = {"value": job.rays_per_step * steps / (ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": ms / steps, "steps": steps, "warmup": 1,
+           "n_gpus": world, "rays_per_step": job.rays_per_step, "evals_per_step_this_rank": evals,
+           "fetch_GBps_this_rank": 256.0 * evals / (ms / steps * 1e-3) / 1e9, "pass_ms": passes,
+           "marched_fraction": 1.0 - stats['n_skipped'] / max(1, stats['n_rays'] + stats['n_skipped']) if not job.prb else None,
+           "config": {"sdf_res": job.R, "film": [job.W, job.H], "spp_primal": job.spp * job.mult, "spp_adjoint": job.spp,
+                      **({"integrator": "sdf_prb_reparam", **job.prb} if job.prb else {"integrator": "sdf_direct_reparam"})}}
+    if not job.prb:
+        march_evals = (stats['n_evals_value'] + stats['n_evals_hess']) / steps
+        rec["roofline"] = {"bound": "hbm", "achieved": 256.0 * march_evals / (ms / steps * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                           "frac": 256.0 * march_evals / (ms / steps * 1e-3) / 1e9 / peak,
+                           "note": "this rank's k_march fetch bytes over the whole step time (lower bound of the kernel's rate)"}
+    job.close()
+    return rec
+
+
+def run_gpu(args):
     import torch
     import torch.distributed as dist
-    import sdfrt
-    from sdfrt import synthetic as syn
+
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit("launch with torch.distributed.run for --gpus > 1")
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
-    kind, R, AR, W, H, spp, mult, nsens = WORKLOADS[args.workload]
-    ctx = sdfrt.Context(local)
-    sdf = syn.make_sdf_device(kind, R, dev)
-    sensor = sdfrt.get_regular_cameras(nsens, resx=W, resy=H)[0]
-    ctx.set_sdf(sdf)
-    ctx.set_albedo(None)
-    ctx.set_sensor(sensor.to_world, W, H)
-    ctx.set_shading()
-    ctx.set_integrator('sdf_prb_reparam')
-    ctx.set_prb(**PRB_WORKLOADS[args.workload])
-    ctx.set_warp()
-    ctx.set_partition(rank, world)
-    Hb, Wb, b = ctx.film_dims()
-    rays_per_step = Hb * Wb * spp * (mult + 1)
-    film_p, film_a = ctx.new_film(), ctx.new_film()
-    image = torch.empty((H, W, 3), device=dev)
-    grad_image = torch.ones((H, W, 3), device=dev)
-    grad_sdf = torch.zeros_like(sdf)
-    stream = torch.cuda.current_stream(dev)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    peak = float(peaks.get('hbm_gbs', 6650.0))
+    peak_src = 'measured (MEASURED_PEAKS.json, burst copy)' if 'hbm_gbs' in peaks else 'fallback (B200_PROFILING.md)'
 
-    def step(seed):
-        ctx.render_view(seed, spp * mult, seed + 1 + nsens, spp, film_p, film_a)
-        if world > 1:
-            dist.all_reduce(film_p)
-            dist.all_reduce(film_a)
-        ctx.develop(film_p, image)
-        grad_sdf.zero_()
-        ctx.adjoint_backprop(film_a, grad_image, grad_sdf)
-        if world > 1:
-            dist.all_reduce(grad_sdf)
+    job = Job(args.workload, local, rank, world)
+    ms, stats, passes, clocks = job.timed(args.steps, args.warmup, clocks=True)
+    value = job.rays_per_step * args.steps / (ms * 1e-3) / 1e6
+    n_cam = stats['n_rays'] + 0   # camera samples this rank shaded (marched or culled)
+    skipped = stats['n_skipped']
 
-    for w in range(args.warmup):
-        step(w * (1 + nsens))
-    torch.cuda.synchronize(dev)
-    ctx.stats(reset=True)
+    line = {"metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "sdf_res": job.R, "albedo_res": job.AR, "film": [job.W, job.H],
+                       "spp_primal": job.spp * job.mult, "spp_adjoint": job.spp, "rays_per_step": job.rays_per_step,
+                       "partition": f"interleaved 8-row film bands x{world}",
+                       **({"integrator": "sdf_prb_reparam", **job.prb} if job.prb else {}),
+                       "l2": "inputs (sdf+albedo+grads+lane records > 1 GB) exceed L2; no explicit flush"},
+            "clocks": clocks, "pass_ms": passes}
+    # camera rays the empty-space test proved clear are counted in `value` (the reference's wavefront counts them too) but never
+    # marched; the rate over marched rays only:
+    if not job.prb:
+        frac_marched = 1.0 - skipped / max(1, stats['n_rays'])
+        line["value_marched_rays"] = value * frac_marched
+        line["marched_fraction_this_rank"] = frac_marched
+    ev_t = torch.tensor([float(stats['n_evals_value'] + stats['n_evals_grad'] + stats['n_evals_hess'] + stats['n_evals_adjoint'])],
+                        device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ev_t)
+    line["evals_per_s"] = ev_t.item() / (ms * 1e-3)     # B-spline evaluations of all ranks per second (the CPU arm prints the same)
+    line["stats_per_step_this_rank"] = {k: v / args.steps for k, v in stats.items()}
+
+    kt, kstats, loop_ms = job.kernel_split(max(2, min(args.steps, 10)))
+    ksteps = max(2, min(args.steps, 10))
+    if not job.prb:
+        roof, launches = march_roofline(job, kt, kstats, ksteps, peak, peak_src, loop_ms)
+        roof["frac_vs_timed_step"] = roof["algorithmic_bytes_per_step"] / (ms / args.steps * 1e-3) / 1e9 / peak
+        line["roofline"] = roof
+    else:
+        launches = sum(v[1] for k, v in kt.items() if k != 'march_all') / ksteps
+        evals = (kstats['n_evals_value'] + kstats['n_evals_grad'] + kstats['n_evals_hess'] + kstats['n_evals_adjoint']) / ksteps
+        line["roofline"] = {"bound": "hbm", "achieved": 256.0 * evals / (ms / args.steps * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                            "frac": 256.0 * evals / (ms / args.steps * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                            "kernel": "all lookups of one step over the step time",
+                            "launch_ms_sum_per_step": {k: v[0] / ksteps for k, v in kt.items()},
+                            "launch_ms_union_per_step": {k: v[2] / ksteps for k, v in kt.items()}}
+    line["gpu_launches"] = int(round(launches * args.steps))
+
+    line["e2e"] = None if args.no_e2e else e2e_leg(job, args.steps)
+
+    if rank == 0 and not args.no_grad_check and not job.prb:
+        try:
+            line["grad_check"] = grad_check(job)
+        except Exception as e:  # the checker must never take the measurement down
+            line["grad_check"] = {"error": repr(e)}
     if world > 1:
         dist.barrier()
-    t0, t1, tm = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-    with ClockSampler(local) as clk:
-        torch.cuda.synchronize(dev)
-        t0.record(stream)
-        for s in range(args.steps):
-            step(1000 + s * (1 + nsens))
-        t1.record(stream)
-        torch.cuda.synchronize(dev)
-    ms = t0.elapsed_time(t1)
-    tt = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    ms = tt.item()
-    stats = ctx.stats(reset=True)
-    # e2e: host buffers in, host buffers out through the host entry point of the C ABI (N = 1 only)
-    e2e = None
-    if world == 1:
-        sdf_h = sdf.cpu().pin_memory()
-        img_h = torch.empty((H, W, 3)).pin_memory()
-        g_h = torch.empty((R, R, R)).pin_memory()
-        ctx.render_view_host(sdf_h, 0, spp * mult, 1 + nsens, spp, None, img_h, g_h)
-        torch.cuda.synchronize(dev)
-        e_steps = max(1, min(args.steps, 3))
-        tw = time.perf_counter()
-        for s in range(e_steps):
-            ctx.render_view_host(sdf_h, 1000 + s, spp * mult, 1001 + s + nsens, spp, None, img_h, g_h)
-        tw = time.perf_counter() - tw
-        ctx.set_sdf(sdf)
-        e2e = {"value": rays_per_step * e_steps / tw / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": sdf_h.numel() * 4,
-               "d2h_bytes_per_step": img_h.numel() * 4 + g_h.numel() * 4, "steps": e_steps, "api": "sdfrt_render_view_host"}
-    cpu_baseline = None
+
+    line["cpu_baseline"] = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = len(os.sched_getaffinity(0))
-        os.environ.setdefault('OMP_NUM_THREADS', str(cores))
         n, r = cpu_calibrated_sample(args.workload, 12.0)
-        cpu_baseline = {"value": r['rays'] / r['seconds'] / 1e6, "unit": "Mrays/s", "cores": r['threads'], "kind": "port",
-                        "sample": f"{n} primal + {max(spp, n // mult)} adjoint lanes from the wavefront centre, {r['seconds']:.1f} s; "
-                                  "compiled CPU port (g++ -O3 -fopenmp) of the restated sdf_prb_reparam"}
+        line["cpu_baseline"] = cpu_record(args.workload, n, r, "compiled CPU port of the restated reference")
+
+    # second metric (SURVEY 8f#2, protocol of figures/benchmark/benchmark.py:120-144): the per-iteration grid update on the
+    # workload's SDF grid -- re-distancing (mean of 5, CUDA events) and the fused Adam step; the CPU side is the C oracle
+    if rank == 0 and world == 1 and not job.prb:
+        line["grid_update"] = grid_update_record(job, args)
+
+    job.close()
+    if not args.no_secondary and args.workload == 'c3_blobs256_tex_512x512_64spp':
+        sec = {}
+        for wl in SECONDARY:
+            try:
+                sec[wl] = secondary_record(wl, local, rank, world, peak)
+            except Exception as e:
+                sec[wl] = {"error": repr(e)}
+        line["secondary"] = sec
     if rank == 0:
-        evals = (stats['n_evals_value'] + stats['n_evals_grad'] + stats['n_evals_hess'] + stats['n_evals_adjoint']) / args.steps
-        line = {"metric": METRIC, "value": rays_per_step * args.steps / (ms * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": args.workload, "integrator": "sdf_prb_reparam", **PRB_WORKLOADS[args.workload], "sdf_res": R,
-                           "film": [W, H], "spp_primal": spp * mult, "spp_adjoint": spp, "rays_per_step": rays_per_step,
-                           "note": "camera samples counted as rays; every sample walks up to max_depth path segments plus "
-                                   "their shadow rays (see evals_per_step)"},
-                "clocks": clk.summary(), "e2e": e2e, "cpu_baseline": cpu_baseline, "gpu_launches": int(stats['n_launches']), "evals_per_step": evals,
-                "fetch_GBps": 256.0 * evals / (ms / args.steps * 1e-3) / 1e9,
-                "stats_per_step": {k: v / args.steps for k, v in stats.items()}}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def grid_update_record(job, args):
+    import numpy as np
+    torch, sdfrt = job.torch, job.sdfrt
+    R = job.R
+    gctx = sdfrt.redistancing.shared_context(job.dev.index)
+    phi = (job.sdf.reshape(R, R, R) * 1.7).contiguous()
+    for _ in range(2):
+        gctx.redistance(phi)
+    gev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    torch.cuda.synchronize()
+    gev[0].record()
+    for _ in range(5):
+        gctx.redistance(phi)
+    gev[1].record()
+    torch.cuda.synchronize()
+    rd_ms = gev[0].elapsed_time(gev[1]) / 5
+    _, lists = gctx.redistance(phi, return_iters=True)
+    pp = phi.clone().reshape(-1)
+    gg, mm, vv = torch.randn_like(pp) * 0.01, torch.zeros_like(pp), torch.zeros_like(pp)
+    gctx.adam_step(pp, gg, mm, vv, 4e-2, 1, grad_clamp=0.1)
+    torch.cuda.synchronize()
+    gev[0].record()
+    for t in range(2, 7):
+        gctx.adam_step(pp, gg, mm, vv, 4e-2, t, grad_clamp=0.1)
+    gev[1].record()
+    torch.cuda.synchronize()
+    adam_ms = gev[0].elapsed_time(gev[1]) / 5
+    out = {"sdf_res": R, "redistance_ms": rd_ms, "redistance_work_lists": lists, "adam_step_ms": adam_ms,
+           "adam_step_GBps": 7 * 4 * pp.numel() / adam_ms / 1e6}
+    if not args.no_cpu_baseline:
+        from oracle import redistance_oracle as ro
+        sub = phi[:: max(1, R // 128), :: max(1, R // 128), :: max(1, R // 128)].contiguous().cpu().numpy()
+        t0 = time.time()
+        want = ro.redistance(sub)
+        out["cpu_redistance_ms"] = (time.time() - t0) * 1e3
+        out["cpu_sample"] = f"C oracle (1 thread) on the grid subsampled to {sub.shape[0]}^3"
+        got = gctx.redistance(torch.from_numpy(sub).cuda()).cpu().numpy()
+        out["max_abs_diff_vs_oracle"] = float(np.abs(got - want).max())
+    return out
 
 
 if __name__ == '__main__':
     a = parse()
     if a.impl == 'reference':
         run_reference(a)
-    elif a.workload in PRB_WORKLOADS:
-        run_gpu_prb(a)
     else:
         run_gpu(a)

@@ -90,6 +90,7 @@ SIGNATURES = {
     'sdfrt_set_profiling': (C.c_int, [_P, C.c_int]),
     'sdfrt_set_overlap': (C.c_int, [_P, C.c_int]),
     'sdfrt_get_timing': (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
+    'sdfrt_get_timing_ex': (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_float)]),
     'sdfrt_trace_rays': (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.POINTER(RayOut), _P]),
     'sdfrt_eval_sdf': (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
     'sdfrt_redistance': (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), _P]),
@@ -98,6 +99,8 @@ SIGNATURES = {
     'sdfrt_laplacian_reg': (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_float, _P, _P, _P]),
     'sdfrt_render_view_host': (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_uint32, C.c_int,
                                          _P, _P, _P]),
+    'sdfrt_render_view_host_ex': (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_int,
+                                            C.c_uint32, C.c_int, _P, _P, _P, _P]),
 }
 
 _lib = None

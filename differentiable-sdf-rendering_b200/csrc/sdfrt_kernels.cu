@@ -405,7 +405,8 @@ struct sdfrt_ctx {
     int cache_mode[4] = {1, 1, 0, 1};        // tap-cache mode of [value primary, value shadow, diff primary, diff shadow]
     // buffers of the host entry point
     float *h_sdf = nullptr, *h_film = nullptr, *h_film2 = nullptr, *h_image = nullptr, *h_gimg = nullptr, *h_grad = nullptr;
-    size_t h_sdf_n = 0, h_film_n = 0, h_film2_n = 0, h_image_n = 0, h_grad_n = 0;
+    float *h_alb = nullptr, *h_galb = nullptr;
+    size_t h_sdf_n = 0, h_film_n = 0, h_film2_n = 0, h_image_n = 0, h_grad_n = 0, h_alb_n = 0, h_galb_n = 0;
 };
 
 namespace {
@@ -868,6 +869,7 @@ void sdfrt_destroy(sdfrt_ctx* ctx) {
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->rd_err_host) cudaFreeHost(ctx->rd_err_host);
     if (ctx->rd_err_event) cudaEventDestroy(ctx->rd_err_event);
+    cudaFree(ctx->h_alb); cudaFree(ctx->h_galb);
     cudaFree(ctx->h_sdf); cudaFree(ctx->h_film); cudaFree(ctx->h_film2); cudaFree(ctx->h_image); cudaFree(ctx->h_gimg); cudaFree(ctx->h_grad);
     delete ctx;
 }
@@ -1183,22 +1185,49 @@ int sdfrt_set_overlap(sdfrt_ctx* ctx, int enable) {
     return SDFRT_OK;
 }
 
-int sdfrt_get_timing(sdfrt_ctx* ctx, float* ms, int* launches) {
+int sdfrt_get_timing_ex(sdfrt_ctx* ctx, float* ms, int* launches, float* ms_union) {
     if (!ctx || !ms || !launches) return SDFRT_ERR_INVALID;
     SDFRT_CUDA(ctx, cudaSetDevice(ctx->device));
-    for (int i = 0; i < SDFRT_NUM_KERNEL_CLASSES; ++i) { ms[i] = 0.f; launches[i] = 0; }
+    for (int i = 0; i < SDFRT_NUM_KERNEL_CLASSES; ++i) { ms[i] = 0.f; launches[i] = 0; if (ms_union) ms_union[i] = 0.f; }
+    if (ms_union) ms_union[SDFRT_NUM_KERNEL_CLASSES] = 0.f;
+    // intervals relative to the first recorded event (launches of different batches overlap on the internal streams);
+    // slot [SDFRT_NUM_KERNEL_CLASSES] collects every k_march launch (classes 1 and 3)
+    std::vector<std::pair<float, float>> iv[SDFRT_NUM_KERNEL_CLASSES + 1];
+    const cudaEvent_t ref = ctx->timed.empty() ? nullptr : ctx->timed.front().second.first;
     for (auto& t : ctx->timed) {
         float e = 0.f;
         SDFRT_CUDA(ctx, cudaEventSynchronize(t.second.second));
         SDFRT_CUDA(ctx, cudaEventElapsedTime(&e, t.second.first, t.second.second));
         ms[t.first] += e;
         launches[t.first] += 1;
+        if (ms_union) {
+            float a = 0.f;
+            if (t.second.first != ref) {
+                SDFRT_CUDA(ctx, cudaEventSynchronize(t.second.first));
+                SDFRT_CUDA(ctx, cudaEventElapsedTime(&a, ref, t.second.first));
+            }
+            iv[t.first].push_back({a, a + e});
+            if (t.first == 1 || t.first == 3) iv[SDFRT_NUM_KERNEL_CLASSES].push_back({a, a + e});
+        }
+    }
+    if (ms_union)
+        for (int c = 0; c <= SDFRT_NUM_KERNEL_CLASSES; ++c) {
+            std::sort(iv[c].begin(), iv[c].end());
+            float end = -1e30f;
+            for (auto& q : iv[c]) {
+                if (q.first > end) { ms_union[c] += q.second - q.first; end = q.second; }
+                else if (q.second > end) { ms_union[c] += q.second - end; end = q.second; }
+            }
+        }
+    for (auto& t : ctx->timed) {
         ctx->event_pool.push_back(t.second.first);
         ctx->event_pool.push_back(t.second.second);
     }
     ctx->timed.clear();
     return SDFRT_OK;
 }
+
+int sdfrt_get_timing(sdfrt_ctx* ctx, float* ms, int* launches) { return sdfrt_get_timing_ex(ctx, ms, launches, nullptr); }
 
 int sdfrt_trace_rays(sdfrt_ctx* ctx, const float* o, const float* d, const float* maxt, int n, int differentiable,
                      const sdfrt_ray_out* out, void* stream) {
@@ -1332,18 +1361,23 @@ int sdfrt_laplacian_reg(sdfrt_ctx* ctx, const float* data, int rx, int ry, int r
     return SDFRT_OK;
 }
 
-int sdfrt_render_view_host(sdfrt_ctx* ctx, const float* sdf_host, int rx, int ry, int rz, uint32_t seed, int spp,
-                           uint32_t seed_grad, int spp_grad, const float* grad_image_host, float* image_host,
-                           float* grad_sdf_host) {
+int sdfrt_render_view_host_ex(sdfrt_ctx* ctx, const float* sdf_host, int rx, int ry, int rz, const float* albedo_host, int ax, int ay,
+                              int az, uint32_t seed, int spp, uint32_t seed_grad, int spp_grad, const float* grad_image_host,
+                              float* image_host, float* grad_sdf_host, float* grad_albedo_host) {
     if (!ctx || !sdf_host || !image_host || !grad_sdf_host) return SDFRT_ERR_INVALID;
+    if (grad_albedo_host && !albedo_host) return fail(ctx, SDFRT_ERR_INVALID, "grad_albedo_host needs albedo_host");
+    if (albedo_host && (ax < 1 || ay < 1 || az < 1)) return fail(ctx, SDFRT_ERR_INVALID, "bad albedo grid");
     if (ctx->world != 1) return fail(ctx, SDFRT_ERR_STATE, "host entry point is single-GPU; use the device API with a partition");
     SDFRT_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t nvox = (size_t)rx * ry * rz;
+    const size_t nalb = albedo_host ? (size_t)ax * ay * az * 3 : 0;
     const SensorParams& S = ctx->sc.S;
     const size_t nimg = (size_t)S.W * S.H * 3;
     int rc;
     if ((rc = ensure(ctx, &ctx->h_sdf, &ctx->h_sdf_n, nvox))) return rc;
     if ((rc = ensure(ctx, &ctx->h_grad, &ctx->h_grad_n, nvox))) return rc;
+    if (albedo_host && (rc = ensure(ctx, &ctx->h_alb, &ctx->h_alb_n, nalb))) return rc;
+    if (grad_albedo_host && (rc = ensure(ctx, &ctx->h_galb, &ctx->h_galb_n, nalb))) return rc;
     if ((rc = ensure(ctx, &ctx->h_film, &ctx->h_film_n, film_floats(ctx)))) return rc;
     if ((rc = ensure(ctx, &ctx->h_film2, &ctx->h_film2_n, film_floats(ctx)))) return rc;
     if (ctx->h_image_n < nimg) {
@@ -1357,6 +1391,10 @@ int sdfrt_render_view_host(sdfrt_ctx* ctx, const float* sdf_host, int rx, int ry
     SDFRT_CUDA(ctx, cudaMemcpyAsync(ctx->h_sdf, sdf_host, nvox * sizeof(float), cudaMemcpyHostToDevice, st));
     const float p0[3] = {ctx->sc.G.px, ctx->sc.G.py, ctx->sc.G.pz};
     if ((rc = sdfrt_set_sdf(ctx, ctx->h_sdf, rx, ry, rz, ctx->have_sdf ? p0 : nullptr))) return rc;
+    if (albedo_host) {
+        SDFRT_CUDA(ctx, cudaMemcpyAsync(ctx->h_alb, albedo_host, nalb * sizeof(float), cudaMemcpyHostToDevice, st));
+        if ((rc = sdfrt_set_albedo(ctx, ctx->h_alb, ax, ay, az))) return rc;
+    }
     // primal render and adjoint sweep 1 do not depend on each other: one pipelined call
     if ((rc = sdfrt_render_view(ctx, seed, spp, ctx->h_film, seed_grad, spp_grad, ctx->h_film2, st))) return rc;
     if ((rc = sdfrt_develop(ctx, ctx->h_film, ctx->h_image, st))) return rc;
@@ -1368,10 +1406,19 @@ int sdfrt_render_view_host(sdfrt_ctx* ctx, const float* sdf_host, int rx, int ry
         SDFRT_CUDA(ctx, cudaGetLastError());
     }
     SDFRT_CUDA(ctx, cudaMemsetAsync(ctx->h_grad, 0, nvox * sizeof(float), st));
-    if ((rc = sdfrt_adjoint_backprop(ctx, ctx->h_film2, ctx->h_gimg, ctx->h_grad, nullptr, nullptr, st))) return rc;
+    if (grad_albedo_host) SDFRT_CUDA(ctx, cudaMemsetAsync(ctx->h_galb, 0, nalb * sizeof(float), st));
+    if ((rc = sdfrt_adjoint_backprop(ctx, ctx->h_film2, ctx->h_gimg, ctx->h_grad, grad_albedo_host ? ctx->h_galb : nullptr, nullptr, st))) return rc;
     SDFRT_CUDA(ctx, cudaMemcpyAsync(grad_sdf_host, ctx->h_grad, nvox * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (grad_albedo_host) SDFRT_CUDA(ctx, cudaMemcpyAsync(grad_albedo_host, ctx->h_galb, nalb * sizeof(float), cudaMemcpyDeviceToHost, st));
     SDFRT_CUDA(ctx, cudaStreamSynchronize(st));
     return SDFRT_OK;
+}
+
+int sdfrt_render_view_host(sdfrt_ctx* ctx, const float* sdf_host, int rx, int ry, int rz, uint32_t seed, int spp,
+                           uint32_t seed_grad, int spp_grad, const float* grad_image_host, float* image_host,
+                           float* grad_sdf_host) {
+    return sdfrt_render_view_host_ex(ctx, sdf_host, rx, ry, rz, nullptr, 0, 0, 0, seed, spp, seed_grad, spp_grad, grad_image_host, image_host,
+                                     grad_sdf_host, nullptr);
 }
 
 }  // extern "C"

@@ -202,12 +202,19 @@ class Context:
     def set_overlap(self, enable=True):
         check(self.ctx, self.lib.sdfrt_set_overlap(self.ctx, int(enable)))
 
-    def timing(self):
-        """{class: (milliseconds, launches)} of the launches since the last call (CUDA events on the launching stream)."""
+    def timing(self, union=False):
+        """{class: (milliseconds, launches)} of the launches since the last call (CUDA events on the launching stream); with
+        union=True {class: (summed ms, launches, ms of the union of the launches' intervals)}."""
         ms = (C.c_float * 8)()
         n = (C.c_int * 8)()
-        check(self.ctx, self.lib.sdfrt_get_timing(self.ctx, ms, n))
-        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(self.KERNEL_CLASSES)}
+        if not union:
+            check(self.ctx, self.lib.sdfrt_get_timing(self.ctx, ms, n))
+            return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(self.KERNEL_CLASSES)}
+        un = (C.c_float * 9)()
+        check(self.ctx, self.lib.sdfrt_get_timing_ex(self.ctx, ms, n, un))
+        out = {k: (float(ms[i]), int(n[i]), float(un[i])) for i, k in enumerate(self.KERNEL_CLASSES)}
+        out['march_all'] = (float(ms[1] + ms[3]), int(n[1] + n[3]), float(un[8]))
+        return out
 
     # ---- test hooks -----------------------------------------------------------------------------
     def trace_rays(self, o, d, maxt=None, differentiable=True):
@@ -274,8 +281,9 @@ class Context:
         return loss
 
     def render_view_host(self, sdf_host, seed, spp, seed_grad, spp_grad, grad_image_host=None, image_host=None,
-                         grad_sdf_host=None):
-        """End-to-end call with HOST (numpy / pinned torch CPU) buffers."""
+                         grad_sdf_host=None, albedo_host=None, grad_albedo_host=None):
+        """End-to-end call with HOST (numpy / pinned torch CPU) buffers; with `albedo_host` the reflectance grid is a second
+        uploaded parameter and `grad_albedo_host` (if given) receives its gradient."""
         def hp(a):
             if a is None:
                 return None
@@ -285,7 +293,8 @@ class Context:
             image_host = torch.empty((self.sensor.height, self.sensor.width, 3), dtype=torch.float32).pin_memory()
         if grad_sdf_host is None:
             grad_sdf_host = torch.empty((rz, ry, rx), dtype=torch.float32).pin_memory()
-        check(self.ctx, self.lib.sdfrt_render_view_host(self.ctx, hp(sdf_host), rx, ry, rz, seed & 0xFFFFFFFF, spp,
-                                                        seed_grad & 0xFFFFFFFF, spp_grad, hp(grad_image_host),
-                                                        hp(image_host), hp(grad_sdf_host)))
+        az, ay, ax = (albedo_host.shape[:3] if albedo_host is not None else (0, 0, 0))
+        check(self.ctx, self.lib.sdfrt_render_view_host_ex(self.ctx, hp(sdf_host), rx, ry, rz, hp(albedo_host), ax, ay, az,
+                                                           seed & 0xFFFFFFFF, spp, seed_grad & 0xFFFFFFFF, spp_grad,
+                                                           hp(grad_image_host), hp(image_host), hp(grad_sdf_host), hp(grad_albedo_host)))
         return image_host, grad_sdf_host

@@ -205,6 +205,9 @@ int sdfrt_set_profiling(sdfrt_ctx* ctx, int enable);
  * event timings additive (used for roofline reporting). */
 int sdfrt_set_overlap(sdfrt_ctx* ctx, int enable);
 int sdfrt_get_timing(sdfrt_ctx* ctx, float* ms, int* launches);
+/* Same, plus ms_union[9] (optional; entry 8 = all k_march launches, classes 1 and 3 together): per class, the length of the UNION of its launches' [start, stop] intervals -- with overlapping
+ * batches on the internal streams the per-launch durations are not additive, the union is the time the class was on the device. */
+int sdfrt_get_timing_ex(sdfrt_ctx* ctx, float* ms, int* launches, float* ms_union);
 
 /* ---- test hooks / helpers used by the reference's callers ------------------------------ */
 /* SDFBase.ray_intersect / ray_intersect_non_diff, python/shapes.py:115-339; o, d: [n*3], maxt: [n] or NULL */
@@ -249,6 +252,13 @@ int sdfrt_laplacian_reg(sdfrt_ctx* ctx, const float* data, int rx, int ry, int r
 int sdfrt_render_view_host(sdfrt_ctx* ctx, const float* sdf_host, int rx, int ry, int rz,
                            uint32_t seed, int spp, uint32_t seed_grad, int spp_grad,
                            const float* grad_image_host, float* image_host, float* grad_sdf_host);
+
+/* Same with the reflectance grid as a second parameter (`main-bsdf.reflectance.volume.data`, python/opt_configs.py:286):
+ * albedo_host (az*ay*ax*3 floats, or NULL to keep the bound grid) is uploaded too and, if grad_albedo_host is given,
+ * dLoss/d(reflectance) comes back with the SDF gradient -- one textured optimisation-loop view, host buffers in and out. */
+int sdfrt_render_view_host_ex(sdfrt_ctx* ctx, const float* sdf_host, int rx, int ry, int rz, const float* albedo_host, int ax, int ay,
+                              int az, uint32_t seed, int spp, uint32_t seed_grad, int spp_grad, const float* grad_image_host,
+                              float* image_host, float* grad_sdf_host, float* grad_albedo_host);
 
 #ifdef __cplusplus
 }

@@ -63,10 +63,24 @@ void cp_defaults(cp_scene* h) {
 }
 
 int cp_threads() { return omp_get_max_threads(); }
+void cp_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+
+// Sample k of `n_sample` -> work item: chunks of 64 consecutive items (the samples of a pixel stay together, as they would in a
+// full render) spread evenly over the WHOLE wavefront of `n_items`, so that the sample sees the workload's mix of rays that miss
+// the bounding box, cross empty space, graze and hit.
+static inline unsigned long long strided_item(long long k, unsigned long long n_items, long long n_sample) {
+    const long long chunk = 64;
+    const unsigned long long total_chunks = (n_items + chunk - 1) / chunk;
+    const unsigned long long sample_chunks = (unsigned long long)((n_sample + chunk - 1) / chunk);
+    if (sample_chunks >= total_chunks) return (unsigned long long)k < n_items ? (unsigned long long)k : n_items - 1;
+    const unsigned long long c = (unsigned long long)(k / chunk);
+    const unsigned long long it = (c * total_chunks / sample_chunks) * chunk + (unsigned long long)(k % chunk);
+    return it < n_items ? it : n_items - 1;
+}
 
 // Times `n_primal` primal lanes (seed, spp*mult) and `n_adjoint` adjoint lanes (forward with the differentiable tracer +
-// closed-form backward with grad_image = 1) taken from the middle of the respective wavefronts.
-// out[0] = seconds primal, out[1] = seconds adjoint, out[2] = value evals, out[3] = hess evals
+// closed-form backward with grad_image = 1) strided over the whole of the respective wavefronts (strided_item).
+// out[0] = seconds primal, out[1] = seconds adjoint, out[2] = value evals, out[3] = hess evals, out[4] = camera rays that hit
 int cp_time_sample(const cp_scene* h, unsigned seed, int spp_primal, int spp_adjoint, long long n_primal, long long n_adjoint,
                    float* grad_sdf /* rz*ry*rx, accumulated */, double* out) {
     SceneParams sc;
@@ -80,14 +94,13 @@ int cp_time_sample(const cp_scene* h, unsigned seed, int spp_primal, int spp_adj
     const bool prb = sc.integrator == INTEGRATOR_PRB;
     const size_t nf = (size_t)(sc.S.W + 2 * sc.S.border) * (sc.S.H + 2 * sc.S.border) * 4;
     std::vector<float> film(nf, 0.f), film_adj(nf, 0.f);
-    double nv = 0, nh = 0;
+    double nv = 0, nh = 0, nhit = 0;
     // ---- primal sample
     PassParams pp = make_pass(sc.S, seed, spp_primal, 0, 1);
-    long long lo = (long long)(pp.n_items / 2) - n_primal / 2;
-    if (lo < 0) lo = 0;
     auto t0 = std::chrono::steady_clock::now();
-#pragma omp parallel for schedule(dynamic, 512) reduction(+ : nv, nh)
-    for (long long l = lo; l < lo + n_primal; ++l) {
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : nv, nh, nhit)
+    for (long long k = 0; k < n_primal; ++k) {
+        const long long l = (long long)strided_item(k, pp.n_items, n_primal);
         LaneStats st = {0, 0, 0, 0, 0, 0, 0};
         if (prb) {
             const WorkItem w = decode_item(pp, (unsigned long long)l);
@@ -96,30 +109,31 @@ int cp_time_sample(const cp_scene* h, unsigned seed, int spp_primal, int spp_adj
         } else {
             lane_forward<false>(sc, pp, decode_item(pp, (unsigned long long)l).lane, film.data(), nullptr, 0, st);
         }
-        nv += st.n_value; nh += st.n_hess;
+        nv += st.n_value + st.n_grad; nh += st.n_hess; nhit += st.n_hit;
     }
     auto t1 = std::chrono::steady_clock::now();
     // ---- adjoint sample: forward (records) + backward
     PassParams pa = make_pass(sc.S, seed + 13, spp_adjoint, 0, 1);
-    long long la = (long long)(pa.n_items / 2) - n_adjoint / 2;
-    if (la < 0) la = 0;
+    const long long la = 0;   // records are indexed by the sample index k
     const PassParams& sub = pa;
     std::vector<float> rec((size_t)REC_COUNT * (size_t)n_adjoint, 0.f);
     std::fill(film.begin(), film.end(), 0.f);
-#pragma omp parallel for schedule(dynamic, 512) reduction(+ : nv, nh)
-    for (long long l = la; l < la + n_adjoint; ++l) {
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : nv, nh, nhit)
+    for (long long k = 0; k < n_adjoint; ++k) {
+        const long long l = k;
+        const unsigned long long item = strided_item(k, sub.n_items, n_adjoint);
         LaneStats st = {0, 0, 0, 0, 0, 0, 0};
         if (prb) {  // re-render of render_backward: keeps L per sample (rows 0..2 of the records)
-            const WorkItem w = decode_item(sub, (unsigned long long)l);
+            const WorkItem w = decode_item(sub, item);
             NoEmit ne; V3 gp = v3(0.f);
             const V3 L = lane_prb<false>(sc, sub, w.lane, nullptr, v3(0.f), ne, gp, st);
             float* r = rec.data() + (l - la);
             r[0] = L.x; r[n_adjoint] = L.y; r[2 * n_adjoint] = L.z;
             splat_at(sc, sub, w, L, film.data());
         } else {
-            lane_forward<true>(sc, sub, decode_item(sub, (unsigned long long)l).lane, film.data(), rec.data() + (l - la), (unsigned long long)n_adjoint, st);
+            lane_forward<true>(sc, sub, decode_item(sub, item).lane, film.data(), rec.data() + (l - la), (unsigned long long)n_adjoint, st);
         }
-        nv += st.n_value; nh += st.n_hess;
+        nv += st.n_value + st.n_grad; nh += st.n_hess; nhit += st.n_hit;
     }
     const int Wb = sc.S.W + 2 * sc.S.border, Hb = sc.S.H + 2 * sc.S.border;
     for (int i = 0; i < Wb * Hb; ++i) {  // grad_image = 1 (figures/benchmark/benchmark.py:44)
@@ -131,26 +145,28 @@ int cp_time_sample(const cp_scene* h, unsigned seed, int spp_primal, int spp_adj
         o[3] = -(a[0] + a[1] + a[2]) * iw * iw;
     }
     BackwardTargets tg; tg.grad_sdf = grad_sdf; tg.grad_albedo = nullptr;
-#pragma omp parallel for schedule(dynamic, 512) reduction(+ : nh)
-    for (long long l = la; l < la + n_adjoint; ++l) {
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : nh)
+    for (long long k = 0; k < n_adjoint; ++k) {
+        const long long l = k;
+        const unsigned long long item = strided_item(k, sub.n_items, n_adjoint);
         LaneStats st = {0, 0, 0, 0, 0, 0, 0};
         V3 gp = v3(0.f);
         if (prb) {
             const float* r = rec.data() + (l - la);
             DirectEmit em{grad_sdf, nullptr, sc.G};
-            (void)lane_prb<true>(sc, sub, decode_item(sub, (unsigned long long)l).lane, film_adj.data(), V3{r[0], r[n_adjoint], r[2 * n_adjoint]}, em, gp, st);
+            (void)lane_prb<true>(sc, sub, decode_item(sub, item).lane, film_adj.data(), V3{r[0], r[n_adjoint], r[2 * n_adjoint]}, em, gp, st);
             nh += st.n_hess;
             continue;
         }
         SiteList sites;
-        lane_backward(sc, sub, decode_item(sub, (unsigned long long)l).lane, film_adj.data(), rec.data() + (l - la), (unsigned long long)n_adjoint, tg, gp, sites, st);
+        lane_backward(sc, sub, decode_item(sub, item).lane, film_adj.data(), rec.data() + (l - la), (unsigned long long)n_adjoint, tg, gp, sites, st);
         for (int q = 0; q < sites.n; ++q) scatter_site(grad_sdf, sc.G, sites.s[q].x, sites.s[q].phi_hat, sites.s[q].g_hat);
         nh += st.n_hess;
     }
     auto t2 = std::chrono::steady_clock::now();
     out[0] = std::chrono::duration<double>(t1 - t0).count();
     out[1] = std::chrono::duration<double>(t2 - t1).count();
-    out[2] = nv; out[3] = nh;
+    out[2] = nv; out[3] = nh; out[4] = nhit;
     return 0;
 }
 }

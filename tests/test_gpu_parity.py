@@ -400,3 +400,55 @@ def test_direct_integrator_shadow_origin_variants(sdfrt_mod, prop):
     integ.render_backward(scene, None, torch.from_numpy(g_in).float().cuda(), sensor=0, seed=11, spp=spp)
     gs = sdf.data.grad[..., 0].cpu().numpy()
     assert np.abs(gs - g_o).max() < 2e-2 * np.abs(g_o).max() and np.linalg.norm(gs - g_o) < 5e-3 * np.linalg.norm(g_o)
+
+
+def test_render_op_holds_several_views_and_reflectance_only_gradients(sdfrt_mod):
+    """`render()` is the mi.render replacement (python/shape_opt.py:78-83).  (i) A loss summed over two views rendered before one
+    backward: the context keeps the lane records of the LAST adjoint sweep only, the op re-runs sweep 1 of the view whose records
+    were overwritten (sdfrt_adjoint_token) -- the gradient equals the sum of the per-view gradients.  (ii) Texture-only
+    optimisation (SDF frozen): the reflectance grid is a differentiable input of the op and gets its gradient."""
+    sdfrt = sdfrt_mod
+    from oracle import sdf_oracle as O
+    W, spp = 24, 8
+    osc = O.make_scene('blobs', res=32, width=W, height=W, albedo_grid_res=8)
+    sdf = sdfrt.Grid3d(osc.sdf.data.float().numpy(), device=0)
+    integ = sdfrt.integrators.create('sdf_direct_reparam', sdf=sdf)
+    wf = sdfrt.WarpField2D(sdf, weight_strategy=6, edge_eps=0.01)
+    wf.clamping_thresh = 0.05
+    integ.warp_field = wf
+    cams = sdfrt.get_regular_cameras(6, resx=W, resy=W)
+    alb = osc.albedo_grid.float().cuda().contiguous()
+    scene = sdfrt.Scene(integ, cams[:2], albedo_grid=alb)
+    w0 = torch.from_numpy(np.random.default_rng(0).uniform(-1, 1, (W, W, 3))).float().cuda()
+    w1 = torch.from_numpy(np.random.default_rng(1).uniform(-1, 1, (W, W, 3))).float().cuda()
+
+    def grads(order):
+        sdf.data.grad = None
+        alb.grad = None
+        sdf.data.requires_grad_(True)
+        alb.requires_grad_(True)
+        if order == 'per_view':
+            for i, w in ((0, w0), (1, w1)):
+                (sdfrt.render(scene, sensor=i, seed=3 + i, spp=spp, seed_grad=11 + i, spp_grad=spp) * w).sum().backward()
+        else:
+            a = sdfrt.render(scene, sensor=0, seed=3, spp=spp, seed_grad=11, spp_grad=spp)
+            b = sdfrt.render(scene, sensor=1, seed=4, spp=spp, seed_grad=12, spp_grad=spp)
+            ((a * w0).sum() + (b * w1).sum()).backward()
+        return sdf.data.grad.clone(), alb.grad.clone()
+
+    g1, a1 = grads('per_view')
+    g2, a2 = grads('summed')
+    assert g1.abs().max() > 0 and (g1 - g2).abs().max() < 1e-4 * g1.abs().max()       # atomics order only
+    assert (a1 - a2).abs().max() < 1e-4 * a1.abs().max()
+    # (ii) SDF frozen, reflectance grid optimised
+    sdf.data.grad = None
+    alb.grad = None
+    sdf.data.requires_grad_(False)
+    alb.requires_grad_(True)
+    (sdfrt.render(scene, sensor=0, seed=3, spp=spp, seed_grad=11, spp_grad=spp) * w0).sum().backward()
+    only = alb.grad.clone()
+    assert sdf.data.grad is None
+    sdf.data.requires_grad_(True)
+    alb.grad = None
+    (sdfrt.render(scene, sensor=0, seed=3, spp=spp, seed_grad=11, spp_grad=spp) * w0).sum().backward()
+    assert only.abs().max() > 0 and (only - alb.grad).abs().max() < 1e-4 * only.abs().max()
