@@ -55,6 +55,8 @@ def parse():
     ap.add_argument('--no-secondary', action='store_true', help='skip the short c4 / c5 records')
     ap.add_argument('--no-grad-check', action='store_true', help='skip the lane-subsample gradient check against the oracle')
     ap.add_argument('--no-e2e', action='store_true', help='profiling runs: skip the host-buffer leg')
+    ap.add_argument('--views-in-flight', type=int, default=2, help='independent views (steps) enqueued concurrently on separate streams / view slots')
+    ap.add_argument('--partition-of', type=int, default=0, help='tuning: render rank 0 of a partition into this many ranks on one GPU (no collectives)')
     return ap.parse_args()
 
 
@@ -189,7 +191,7 @@ def run_reference(args):
 class Job:
     """One workload bound to a context: buffers + the step function (device buffers resident; one optimisation-loop view)."""
 
-    def __init__(self, wl, local, rank, world):
+    def __init__(self, wl, local, rank, world, inflight=2, partition_of=0):
         import torch
         import sdfrt
         from sdfrt import synthetic as syn
@@ -213,49 +215,81 @@ class Job:
         else:
             ctx.set_integrator('sdf_direct_reparam')
         ctx.set_warp()
-        ctx.set_partition(rank, world)
+        if partition_of > 1:
+            ctx.set_partition(0, partition_of)
+        else:
+            ctx.set_partition(rank, world)
         Hb, Wb, b = ctx.film_dims()
         self.n_primal, self.n_adj = Hb * Wb * spp * mult, Hb * Wb * spp
         self.rays_per_step = self.n_primal + self.n_adj
-        self.film_p, self.film_a = ctx.new_film(), ctx.new_film()
-        self.image = torch.empty((H, W, 3), device=dev)
         self.grad_image = torch.ones((H, W, 3), device=dev)  # loss = dr.sum(img), figures/benchmark/benchmark.py:44
-        self.grad_sdf = torch.zeros_like(self.sdf)
-        self.grad_alb = None if self.alb is None else torch.zeros_like(self.alb)
         self.stream = torch.cuda.current_stream(dev)
-        self.pending = None
+        # Views in flight: the views of an optimisation iteration are independent (python/shape_opt.py:77-83), so consecutive steps
+        # are enqueued on alternating streams with their own view slot (sdfrt_set_view_slot), film, image and gradient buffers: the
+        # persistent kernels of one view fill the latency tails of the other.  Every step still produces its own image + gradients.
+        self.inflight = max(1, min(inflight, ctx.num_view_slots()))
+        self.lanes = []
+        for k in range(self.inflight):
+            self.lanes.append(dict(stream=self.stream if self.inflight == 1 else torch.cuda.Stream(dev), film_p=ctx.new_film(), film_a=ctx.new_film(),
+                                   image=torch.empty((H, W, 3), device=dev), grad_sdf=torch.zeros_like(self.sdf),
+                                   grad_alb=None if self.alb is None else torch.zeros_like(self.alb)))
+        self.grad_sdf, self.grad_alb = self.lanes[0]['grad_sdf'], self.lanes[0]['grad_alb']
+        self.n_step = 0
 
     def step(self, seed, ev=None):
         """primal render (spp * mult) and adjoint sweep 1 (spp_grad) in one pipelined call, film all-reduces, develop, adjoint
-        sweep 2, gradient all-reduce (the one large collective per backward)."""
+        sweep 2, gradient all-reduce (the one large collective per backward) -- on the stream / view slot of this step's lane."""
         import torch.distributed as dist
-        ctx, world = self.ctx, self.world
-        if ev:
-            ev[0].record(self.stream)
-        ctx.render_view(seed, self.spp * self.mult, seed + 1 + self.nsens, self.spp, self.film_p, self.film_a)
-        if world > 1:
-            dist.all_reduce(self.film_p)
-            dist.all_reduce(self.film_a)
-        ctx.develop(self.film_p, self.image)
-        if ev:
-            ev[1].record(self.stream)
-        self.grad_sdf.zero_()
-        if self.grad_alb is not None:
-            self.grad_alb.zero_()
-        ctx.adjoint_backprop(self.film_a, self.grad_image, self.grad_sdf, self.grad_alb)
-        if world > 1:
-            dist.all_reduce(self.grad_sdf)
-            if self.grad_alb is not None:
-                dist.all_reduce(self.grad_alb)
-        if ev:
-            ev[2].record(self.stream)
+        torch, ctx, world = self.torch, self.ctx, self.world
+        L = self.lanes[self.n_step % self.inflight]
+        k = self.n_step % self.inflight
+        self.n_step += 1
+        with torch.cuda.stream(L['stream']):
+            if ev:
+                ev[0].record()
+            ctx.set_view_slot(k)
+            ctx.render_view(seed, self.spp * self.mult, seed + 1 + self.nsens, self.spp, L['film_p'], L['film_a'])
+            if world > 1:
+                dist.all_reduce(L['film_p'])
+                dist.all_reduce(L['film_a'])
+            ctx.develop(L['film_p'], L['image'])
+            if ev:
+                ev[1].record()
+            L['grad_sdf'].zero_()
+            if L['grad_alb'] is not None:
+                L['grad_alb'].zero_()
+            ctx.adjoint_backprop(L['film_a'], self.grad_image, L['grad_sdf'], L['grad_alb'])
+            if world > 1:
+                dist.all_reduce(L['grad_sdf'])
+                if L['grad_alb'] is not None:
+                    dist.all_reduce(L['grad_alb'])
+            if ev:
+                ev[2].record()
+
+    def fork(self):
+        """the lanes' streams start after everything queued on the main stream ..."""
+        if self.inflight > 1:
+            e = self.torch.cuda.Event()
+            e.record(self.stream)
+            for L in self.lanes:
+                L['stream'].wait_event(e)
+
+    def join(self):
+        """... and the main stream continues after all of them"""
+        if self.inflight > 1:
+            for L in self.lanes:
+                e = self.torch.cuda.Event()
+                e.record(L['stream'])
+                self.stream.wait_event(e)
 
     def timed(self, steps, warmup, clocks=False):
         """W untimed steps, then exactly K steps bracketed by barrier + synchronize; device time, max over ranks."""
         torch = self.torch
         import torch.distributed as dist
+        self.fork()
         for w in range(warmup):
             self.step(w * (1 + self.nsens))
+        self.join()
         torch.cuda.synchronize(self.dev)
         self.ctx.stats(reset=True)
         if self.world > 1:
@@ -267,8 +301,10 @@ class Job:
             clk.__enter__()
         torch.cuda.synchronize(self.dev)
         t0.record(self.stream)
+        self.fork()
         for s in range(steps):
             self.step(1000 + s * (1 + self.nsens), ev[s])
+        self.join()
         t1.record(self.stream)
         torch.cuda.synchronize(self.dev)
         if clk:
@@ -292,14 +328,18 @@ class Job:
         torch, ctx = self.torch, self.ctx
         ctx.set_profiling(True)
         ctx.timing()
+        self.fork()
         self.step(7)
+        self.join()
         torch.cuda.synchronize(self.dev)
         ctx.timing()
         ctx.stats(reset=True)
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0.record(self.stream)
+        self.fork()
         for s in range(steps):
             self.step(1000 + s * (1 + self.nsens))
+        self.join()
         t1.record(self.stream)
         torch.cuda.synchronize(self.dev)
         stats = ctx.stats(reset=True)
@@ -309,7 +349,7 @@ class Job:
 
     def close(self):
         self.ctx = None
-        for k in ('sdf', 'alb', 'grad_sdf', 'grad_alb', 'film_p', 'film_a', 'image', 'grad_image'):
+        for k in ('sdf', 'alb', 'grad_sdf', 'grad_alb', 'grad_image', 'lanes'):
             setattr(self, k, None)
         self.torch.cuda.empty_cache()
 
@@ -348,6 +388,7 @@ def grad_check(job, n_lanes=16384):
     from oracle import window_check as WC
     ctx = job.ctx
     t0 = time.time()
+    ctx.set_view_slot(0)
     ctx.set_partition(0, 1)
     sens = O.Sensor(to_world=job.sensor.to_world, width=job.W, height=job.H)
     osc = O.Scene(sdf=O.Grid3d(job.sdf.cpu().double()), sensor=sens, albedo_grid=None if job.alb is None else job.alb.cpu().double())
@@ -434,11 +475,11 @@ def e2e_leg(job, steps):
             "steps": e_steps, "api": api}
 
 
-def secondary_record(wl, local, rank, world, peak):
-    """A short run (1 warm-up + 3 timed steps, same timing rules) of another BASELINE config at the same N."""
-    job = Job(wl, local, rank, world)
-    steps = 3
-    ms, stats, passes, _ = job.timed(steps, 1)
+def secondary_record(wl, local, rank, world, peak, inflight=2):
+    """A short run (2 warm-up + 4 timed steps, same timing rules) of another BASELINE config at the same N."""
+    job = Job(wl, local, rank, world, inflight)
+    steps = 4
+    ms, stats, passes, _ = job.timed(steps, 2)
     evals = (stats['n_evals_value'] + stats['n_evals_grad'] + stats['n_evals_hess'] + stats['n_evals_adjoint']) / steps
     rec = {"value": job.rays_per_step * steps / (ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": ms / steps, "steps": steps, "warmup": 1,
            "n_gpus": world, "rays_per_step": job.rays_per_step, "evals_per_step_this_rank": evals,
@@ -476,7 +517,7 @@ def run_gpu(args):
     peak = float(peaks.get('hbm_gbs', 6650.0))
     peak_src = 'measured (MEASURED_PEAKS.json, burst copy)' if 'hbm_gbs' in peaks else 'fallback (B200_PROFILING.md)'
 
-    job = Job(args.workload, local, rank, world)
+    job = Job(args.workload, local, rank, world, args.views_in_flight, args.partition_of)
     ms, stats, passes, clocks = job.timed(args.steps, args.warmup, clocks=True)
     value = job.rays_per_step * args.steps / (ms * 1e-3) / 1e6
     n_cam = stats['n_rays'] + 0   # camera samples this rank shaded (marched or culled)
@@ -487,7 +528,8 @@ def run_gpu(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "sdf_res": job.R, "albedo_res": job.AR, "film": [job.W, job.H],
                        "spp_primal": job.spp * job.mult, "spp_adjoint": job.spp, "rays_per_step": job.rays_per_step,
-                       "partition": f"interleaved 8-row film bands x{world}",
+                       "partition": f"interleaved 8-row film bands x{world}" + (f" (tuning: rank 0 of {args.partition_of} on one GPU, no collectives)" if args.partition_of > 1 else ""),
+                       "views_in_flight": job.inflight,
                        **({"integrator": "sdf_prb_reparam", **job.prb} if job.prb else {}),
                        "l2": "inputs (sdf+albedo+grads+lane records > 1 GB) exceed L2; no explicit flush"},
             "clocks": clocks, "pass_ms": passes}
@@ -545,7 +587,7 @@ def run_gpu(args):
         sec = {}
         for wl in SECONDARY:
             try:
-                sec[wl] = secondary_record(wl, local, rank, world, peak)
+                sec[wl] = secondary_record(wl, local, rank, world, peak, args.views_in_flight)
             except Exception as e:
                 sec[wl] = {"error": repr(e)}
         line["secondary"] = sec

@@ -77,6 +77,8 @@ SIGNATURES = {
     'sdfrt_set_partition': (C.c_int, [_P, C.c_int, C.c_int]),
     'sdfrt_set_lane_window': (C.c_int, [_P, C.c_uint64, C.c_uint64]),
     'sdfrt_set_empty_space_skip': (C.c_int, [_P, C.c_int]),
+    'sdfrt_set_view_slot': (C.c_int, [_P, C.c_int]),
+    'sdfrt_num_view_slots': (C.c_int, []),
     'sdfrt_adjoint_token': (C.c_uint64, [_P]),
     'sdfrt_redistance_status': (C.c_int, [_P]),
     'sdfrt_film_dims': (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),

@@ -89,6 +89,10 @@ struct GridView {
     // optional row-expanded copy for the marchers: rows4[(z * ry + y) * rx + x] = data[z][y][x .. x+3] (x <= rx - 4),
     // so that one 16-byte load fetches a whole x-row of a 4x4x4 block.  nullptr = read `data`.
     const float4* rows4;
+    // ... or 8x expanded: rows8[((z * ry + y) * rx + x) * 8 + 0..7] = data[z][y][x .. x+3], data[z][y+1][x .. x+3], 32-byte aligned, so
+    // that one 256-bit load (LDG.E.256, sm_100) fetches TWO x-rows of a block: 8 load instructions per lookup instead of 16.  For
+    // incoherent (shadow) rays the L1 tag stage does one lookup per lane and load instruction, so this halves its work.
+    const float* rows8;
     // Grid3d(data, transform) (python/shapes.py:378-392): lookups use x_local = A (x - p) + tl (`to_local`), gradients and
     // Hessians are pulled back with A^T (python/shapes.py:423-448).  has_transform == 0: identity (the reference's fast path).
     int has_transform;
@@ -276,12 +280,27 @@ SDFRT_HD void cell_setup(const GridView& G, V3 x, CellSetup<ORDER>& s) {
         if (ORDER >= 2) { fold_weights(c.ix, s.bx, G.rx, s.ex); fold_weights(c.iy, s.by, G.ry, s.ey); fold_weights(c.iz, s.bz, G.rz, s.ez); }
     }
 }
-template <bool ROWS4 = false>
+template <int ROWS = 0>  // 0: plain grid, 4: row-expanded copy (float4 per row), 8: two rows per 256-bit load
 SDFRT_HD void load_taps(const GridView& G, int bx, int by, int bz, float f[64]) {
     // 32-bit element offsets (grids up to 2^32 texels): one address computation per row, taps at +0..+3
     const unsigned sy = (unsigned)G.rx, sz = (unsigned)G.rx * (unsigned)G.ry;
     const unsigned o = (unsigned)bz * sz + (unsigned)by * sy + (unsigned)bx;
-    if (ROWS4) {
+#if defined(__CUDA_ARCH__)
+    if (ROWS == 8) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int j = 0; j < 4; j += 2) {
+                const float* q = G.rows8 + (size_t)(o + (unsigned)k * sz + (unsigned)j * sy) * 8u;
+                float* d = f + (k * 4 + j) * 4;
+                asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                             : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3]), "=f"(d[4]), "=f"(d[5]), "=f"(d[6]), "=f"(d[7])
+                             : "l"(q));
+            }
+        return;
+    }
+#endif
+    if (ROWS == 4) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
 #pragma unroll

@@ -331,6 +331,8 @@ __global__ void __launch_bounds__(kBlock, MIN_BLOCKS) k_prb_backward(const __gri
 // ----------------------------------------------------------------------------------------------------
 // context
 // ----------------------------------------------------------------------------------------------------
+constexpr int kViewSlots = 4;  // views in flight (adjoint-state slots)
+#define VS(c) ((c)->view[(c)->cur_view])
 constexpr int kSlots = 8;  // pipeline slots (internal streams + scratch sets) available to a forward sweep
 
 struct sdfrt_ctx {
@@ -348,19 +350,32 @@ struct sdfrt_ctx {
     int shadow_origin = 0;   // sdf_direct_reparam props detach_indirect_si (1) / decouple_reparam (2)
     int antithetic = 0;  // ReparamIntegrator.antithetic_sampling (python/integrators/reparam.py:19); not used by sdf_prb_reparam
     bool have_sdf = false;
-    // adjoint state
-    float* rec = nullptr;
-    size_t rec_capacity = 0;  // floats
-    unsigned long long rec_stride = 0;
-    PassParams adj_pass;
-    bool adj_ready = false;
+    // Adjoint state of a VIEW: the lane records of adjoint sweep 1, the scene it was rendered with and the per-view scratch of the
+    // empty-space test.  kViewSlots views can be in flight (sdfrt_set_view_slot): the views of one optimisation iteration are
+    // independent (python/shape_opt.py:77-83), so a caller may enqueue the sweeps of the next view on another stream before the
+    // previous view's backprop -- the persistent kernels of one view then fill the latency tails of the other.
+    struct ViewSlot {
+        float* rec = nullptr;
+        size_t rec_capacity = 0;  // floats
+        unsigned long long rec_stride = 0;
+        PassParams adj_pass;
+        bool adj_ready = false;
+        unsigned long long generation = 0;
+        SceneParams sc;               // snapshot taken by adjoint sweep 1, used by sweep 2
+        float* film_adj = nullptr;
+        size_t film_adj_capacity = 0;
+        float* prb_rec = nullptr;     // sdf_prb_reparam, DIFF sweep: per-vertex march records [max_depth * 18][n_items]
+        size_t prb_rec_n = 0;
+        float *brick_a = nullptr, *brick_b = nullptr, *pix_mask = nullptr;  // dilated brick minima (ping-pong) + per-pixel masks
+        size_t brick_a_n = 0, brick_b_n = 0, pix_mask_n = 0;
+    } view[kViewSlots];
+    int cur_view = 0;
     unsigned long long adj_generation = 0;   // bumped by every adjoint sweep 1; sdfrt_adjoint_token
+    bool grid_dirty = true, rows4_valid = false, rows8_valid = false, brick_raw_valid = false;                  // sdfrt_set_sdf since the derived copies (rows4 / rows8 / brick minima) were built
     unsigned long long win_lo = 0ull, win_hi = ~0ull;  // sdfrt_set_lane_window
     unsigned* rd_err_host = nullptr;         // pinned copy of the re-distancing solver's error word (async callers)
     cudaEvent_t rd_err_event = nullptr;
     bool rd_err_pending = false;
-    float* film_adj = nullptr;
-    size_t film_adj_capacity = 0;
     Counters* counters = nullptr;
     unsigned* work = nullptr;  // WQ_COUNT counters
     unsigned long long n_launches = 0;
@@ -375,8 +390,8 @@ struct sdfrt_ctx {
     } scratch[kSlots];            // one per pipeline slot
     cudaStream_t aux[kSlots] = {};   // batches rotate over internal streams so that the tail of one batch's persistent
     cudaEvent_t ev_fork = nullptr, ev_join[kSlots] = {};  // kernels overlaps the following batches
-    float *brick_raw = nullptr, *brick = nullptr, *pix_mask = nullptr;  // per-brick SDF minima (two ping-pong buffers) and the
-    size_t brick_raw_n = 0, brick_n = 0, pix_mask_n = 0;                // per-pixel result of the empty-space test
+    float* brick_raw = nullptr;   // per-brick SDF minima (undilated; rebuilt when the grid changes)
+    size_t brick_raw_n = 0;
     bool skip_empty = true;
     int min_live = kMinActive;  // slots that must be stepping for a warp to stay in the stepping loop
     int max_slots = 4;
@@ -395,11 +410,13 @@ struct sdfrt_ctx {
     size_t lap_r_n = 0;
     float4* rows4 = nullptr;
     size_t rows4_n = 0;
+    float* rows8 = nullptr;                  // two-rows-per-256-bit-load copy (GridView::rows8), 8x the grid
+    size_t rows8_n = 0;
+    int rows8_roles = 0;                     // role mask (SDFRT_ROWS8); 0 = off
+    bool rows8_on = false;
     int rows4_roles = -1, march_role = 0;
     bool rows4_on = false;
     bool prb_wavefront = true;               // sdf_prb_reparam bounce by bounce through k_march (SDFRT_PRB_WAVEFRONT=0: per-lane walker)
-    float* prb_rec = nullptr;                // DIFF sweep: per-vertex march records [max_depth * 18][n_items]
-    size_t prb_rec_n = 0;
     bool prb_primary_wavefront = true;       // camera rays of sdf_prb_reparam through k_march (SDFRT_PRB_PRIMARY=0: per lane)
     int prb_min_blocks = 2;                  // register-allocation variant of k_prb_backward (SDFRT_PRB_OCC)
     int cache_mode[4] = {1, 1, 0, 1};        // tap-cache mode of [value primary, value shadow, diff primary, diff shadow]
@@ -473,13 +490,20 @@ template <bool DIFF, int CACHE>
 void launch_march(sdfrt_ctx* ctx, unsigned grid, cudaStream_t st, const SegIn* segs, const unsigned* region_fill, unsigned n_slots, unsigned region,
                   int do_refine, float* out_its, float* rec_out, unsigned long long rec_stride, unsigned* region_counter) {
     GridView G = ctx->sc.G;
-    G.rows4 = (ctx->rows4_on && ((ctx->rows4_roles < 0 ? 15 : ctx->rows4_roles) >> ctx->march_role & 1)) ? ctx->rows4 : nullptr;
-    if (G.rows4)
-        k_march<DIFF, CACHE, true><<<grid, kMarchBlock, 0, st>>>(G, ctx->sc.T, segs, region_fill, n_slots, region, do_refine, ctx->min_live, out_its, rec_out,
-                                                                 rec_stride, region_counter, ctx->counters);
+    const int role = ctx->march_role;
+    const bool use8 = ctx->rows8_on && (ctx->rows8_roles >> role & 1);
+    const bool use4 = !use8 && ctx->rows4_on && ((ctx->rows4_roles < 0 ? 15 : ctx->rows4_roles) >> role & 1);
+    G.rows4 = use4 ? ctx->rows4 : nullptr;
+    G.rows8 = use8 ? ctx->rows8 : nullptr;
+    if (use8)
+        k_march<DIFF, CACHE, 8><<<grid, kMarchBlock, 0, st>>>(G, ctx->sc.T, segs, region_fill, n_slots, region, do_refine, ctx->min_live, out_its, rec_out,
+                                                              rec_stride, region_counter, ctx->counters);
+    else if (use4)
+        k_march<DIFF, CACHE, 4><<<grid, kMarchBlock, 0, st>>>(G, ctx->sc.T, segs, region_fill, n_slots, region, do_refine, ctx->min_live, out_its, rec_out,
+                                                              rec_stride, region_counter, ctx->counters);
     else
-    k_march<DIFF, CACHE, false><<<grid, kMarchBlock, 0, st>>>(G, ctx->sc.T, segs, region_fill, n_slots, region, do_refine, ctx->min_live, out_its, rec_out,
-                                                       rec_stride, region_counter, ctx->counters);
+        k_march<DIFF, CACHE, 0><<<grid, kMarchBlock, 0, st>>>(G, ctx->sc.T, segs, region_fill, n_slots, region, do_refine, ctx->min_live, out_its, rec_out,
+                                                              rec_stride, region_counter, ctx->counters);
 }
 template <bool DIFF>
 void launch_march_mode(sdfrt_ctx* ctx, int role /* index into cache_mode */, unsigned need, cudaStream_t st, const SegIn* segs, const unsigned* region_fill,
@@ -528,14 +552,14 @@ int enqueue_batch(sdfrt_ctx* ctx, const Sweep& sw, unsigned long long item0, int
     SDFRT_CUDA(ctx, cudaMemsetAsync(work, 0, WQ_COUNT * sizeof(unsigned), bs));
     { LaunchScope ls(ctx, 0, bs); k_gen_primary<<<blocks256, 256, 0, bs>>>(ctx->sc, ps, item0, cnt, reinterpret_cast<SegIn*>(sc.segs), sw.mask, ctx->counters); }
     // primary march (+ refine); DIFF writes its_t into row 0 of the lane records
-    float* rec_b = DIFF ? ctx->rec + item0 : nullptr;
-    unsigned long long rec_stride = ctx->rec_stride;
+    float* rec_b = DIFF ? VS(ctx).rec + item0 : nullptr;
+    unsigned long long rec_stride = VS(ctx).rec_stride;
     float* its_out = sc.its;
     // sdf_prb_reparam, wavefront form: every segment's march lands in the per-vertex records (PrbRecords layout)
     const bool prb_wf = ctx->sc.integrator == INTEGRATOR_PRB && ctx->prb_wavefront;
     PrbRecords prec{nullptr, 0, 9};
     if (prb_wf) {
-        if (DIFF) { prec.base = ctx->prb_rec + item0; prec.stride = ps.n_items; prec.rows = 9; }
+        if (DIFF) { prec.base = VS(ctx).prb_rec + item0; prec.stride = ps.n_items; prec.rows = 9; }
         else { prec.base = sc.prb_rec; prec.stride = B; prec.rows = 1; }
         rec_b = const_cast<float*>(prec.base);
         rec_stride = prec.stride;
@@ -581,8 +605,8 @@ int enqueue_batch(sdfrt_ctx* ctx, const Sweep& sw, unsigned long long item0, int
         }
         { LaunchScope ls(ctx, 4, bs);
           k_prb_primal<<<(cnt + kBlock - 1) / kBlock, kBlock, 0, bs>>>(ctx->sc, ps, item0, (unsigned long long)cnt, nullptr, prec, film,
-                                                                        DIFF ? ctx->rec + item0 + (size_t)REC_S_STATE * ctx->rec_stride : nullptr,
-                                                                        ctx->rec_stride, ctx->counters); }
+                                                                        DIFF ? VS(ctx).rec + item0 + (size_t)REC_S_STATE * VS(ctx).rec_stride : nullptr,
+                                                                        VS(ctx).rec_stride, ctx->counters); }
         SDFRT_CUDA(ctx, cudaGetLastError());
         return SDFRT_OK;
     }
@@ -591,13 +615,13 @@ int enqueue_batch(sdfrt_ctx* ctx, const Sweep& sw, unsigned long long item0, int
         // included); the rest of the path is walked per sample.  The re-render of render_backward (DIFF) keeps L in rows 9..11.
         LaunchScope ls(ctx, 2, bs);
         k_prb_primal<<<(cnt + kBlock - 1) / kBlock, kBlock, 0, bs>>>(ctx->sc, ps, item0, (unsigned long long)cnt, its, PrbRecords{nullptr, 0, 9}, film,
-                                                                      DIFF ? rec_b + (size_t)REC_S_STATE * ctx->rec_stride : nullptr, ctx->rec_stride, ctx->counters);
+                                                                      DIFF ? rec_b + (size_t)REC_S_STATE * VS(ctx).rec_stride : nullptr, VS(ctx).rec_stride, ctx->counters);
         SDFRT_CUDA(ctx, cudaGetLastError());
         return SDFRT_OK;
     }
     { LaunchScope ls(ctx, 2, bs);
       k_shade<DIFF><<<regions, 256, 0, bs>>>(ctx->sc, ps, item0, cnt, region, reinterpret_cast<const SegIn*>(sc.segs), its, q, film,
-                                             DIFF ? rec_b + REC_S_STATE * ctx->rec_stride : nullptr, ctx->counters); }
+                                             DIFF ? rec_b + REC_S_STATE * VS(ctx).rec_stride : nullptr, ctx->counters); }
     if (ctx->sc.integrator == INTEGRATOR_DIRECT) {
         // shadow march over the region-compacted queue.  The differentiable tracer is only needed if shadow rays are
         // reparameterised (python/warp.py:103: max_reparam_depth); otherwise the value tracer's its_t is all the pass uses.
@@ -613,7 +637,7 @@ int enqueue_batch(sdfrt_ctx* ctx, const Sweep& sw, unsigned long long item0, int
         { LaunchScope ls(ctx, 4, bs);
           k_shadow_splat<DIFF><<<regions, 256, 0, bs>>>(ctx->sc, ps, item0, region, reinterpret_cast<const SegIn*>(sc.segs), q.count,
                                                         reinterpret_cast<const float4*>(sc.sinfo), shadow_its, sc.srec, B, film, rec_b,
-                                                        ctx->rec_stride); }
+                                                        VS(ctx).rec_stride); }
     }
     SDFRT_CUDA(ctx, cudaGetLastError());
     return SDFRT_OK;
@@ -657,8 +681,12 @@ int run_sweeps(sdfrt_ctx* ctx, Sweep* sweeps, int ns, cudaStream_t st) {
         if (any_value && ctx->sc.integrator == INTEGRATOR_PRB && ctx->prb_wavefront &&
             (rc = ensure(ctx, &sc.prb_rec, &sc.prb_rec_n, (size_t)Bmax * 2 * (size_t)ctx->sc.prb.max_depth))) return rc;
     }
-    // empty-space test (rebuilt every call: the caller may have updated the grid in place): brick minima -> dilation -> one
-    // DDA per film pixel and sweep -> masks consumed by k_gen_primary
+    // Derived copies of the grid (row-expanded copies for the marchers, per-brick minima) are rebuilt when the grid was (re)bound
+    // since they were built -- sdfrt_set_sdf is the `parameters_changed` of this boundary (python/shapes.py:477-479) and must follow
+    // every change of the grid's values.  They are shared by all views in flight; everything per view lives in its ViewSlot.
+    const bool dirty = ctx->grid_dirty;
+    sdfrt_ctx::ViewSlot& V = VS(ctx);
+    // empty-space test: brick minima -> dilation -> one DDA per film pixel and sweep -> masks consumed by k_gen_primary
     if (ctx->skip_empty && !ctx->sc.G.has_transform) {  // the brick DDA walks grid space = world space: identity to_world only
         const GridView& G = ctx->sc.G;
         const int npix = (S.W + 2 * S.border) * (S.H + 2 * S.border);
@@ -679,41 +707,64 @@ int run_sweeps(sdfrt_ctx* ctx, Sweep* sweeps, int ns, cudaStream_t st) {
             if (e.skip_eps < 0.f) continue;
             if (!bricks_ready) {
                 const size_t nb = (size_t)bricks.nx * bricks.ny * bricks.nz;
+                const bool fresh = ctx->brick_raw_n < nb;
                 if ((rc = ensure(ctx, &ctx->brick_raw, &ctx->brick_raw_n, nb))) return rc;
-                if ((rc = ensure(ctx, &ctx->brick, &ctx->brick_n, nb))) return rc;
-                if ((rc = ensure(ctx, &ctx->pix_mask, &ctx->pix_mask_n, 2 * mask_words))) return rc;
+                if ((rc = ensure(ctx, &V.brick_a, &V.brick_a_n, nb))) return rc;
+                if ((rc = ensure(ctx, &V.brick_b, &V.brick_b_n, nb))) return rc;
+                if ((rc = ensure(ctx, &V.pix_mask, &V.pix_mask_n, 2 * mask_words))) return rc;
                 const unsigned gb = (unsigned)((nb + 255) / 256);
                 LaunchScope ls(ctx, 0, st);
-                k_brick_min<<<gb, 256, 0, st>>>(G, ctx->brick_raw, bricks.nx, bricks.ny, bricks.nz);
-                k_brick_dilate<<<gb, 256, 0, st>>>(ctx->brick_raw, ctx->brick, bricks.nx, bricks.ny, bricks.nz, e.dilation, 0);
-                k_brick_dilate<<<gb, 256, 0, st>>>(ctx->brick, ctx->brick_raw, bricks.nx, bricks.ny, bricks.nz, e.dilation, 1);
-                k_brick_dilate<<<gb, 256, 0, st>>>(ctx->brick_raw, ctx->brick, bricks.nx, bricks.ny, bricks.nz, e.dilation, 2);
-                ctx->n_launches += 3;
-                bricks.data = ctx->brick;
+                if (dirty || fresh || !ctx->brick_raw_valid) {
+                    k_brick_min<<<gb, 256, 0, st>>>(G, ctx->brick_raw, bricks.nx, bricks.ny, bricks.nz);
+                    ctx->brick_raw_valid = true;
+                    ctx->n_launches += 1;
+                }
+                k_brick_dilate<<<gb, 256, 0, st>>>(ctx->brick_raw, V.brick_a, bricks.nx, bricks.ny, bricks.nz, e.dilation, 0);
+                k_brick_dilate<<<gb, 256, 0, st>>>(V.brick_a, V.brick_b, bricks.nx, bricks.ny, bricks.nz, e.dilation, 1);
+                k_brick_dilate<<<gb, 256, 0, st>>>(V.brick_b, V.brick_a, bricks.nx, bricks.ny, bricks.nz, e.dilation, 2);
+                ctx->n_launches += 2;
+                bricks.data = V.brick_a;
                 bricks_ready = true;
             }
-            unsigned char* m = reinterpret_cast<unsigned char*>(ctx->pix_mask + (sw.diff ? mask_words : 0));
+            unsigned char* m = reinterpret_cast<unsigned char*>(V.pix_mask + (sw.diff ? mask_words : 0));
             { LaunchScope ls(ctx, 0, st); k_pixel_clear<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(ctx->sc, bricks, e, m); }
             sw.mask = m;
         }
     }
-    ctx->rows4_on = false;
-    if (ctx->rows4_roles != 0) {
+    {
         const GridView& G = ctx->sc.G;
         const size_t nt = (size_t)G.rx * G.ry * G.rz;
-        ctx->rows4_on = ctx->rows4_roles > 0 || nt <= kRows4MaxTexels;
-    }
-    if (ctx->rows4_on) {
-        const GridView& G = ctx->sc.G;
-        const size_t nt = (size_t)G.rx * G.ry * G.rz;
-        if (ctx->rows4_n < nt) {
-            cudaFree(ctx->rows4); ctx->rows4 = nullptr; ctx->rows4_n = 0;
-            SDFRT_CUDA(ctx, cudaMalloc(&ctx->rows4, nt * sizeof(float4)));
-            ctx->rows4_n = nt;
+        ctx->rows4_on = ctx->rows4_roles != 0 && (ctx->rows4_roles > 0 || nt <= kRows4MaxTexels);
+        ctx->rows8_on = ctx->rows8_roles != 0 && nt <= kRows4MaxTexels;
+        if (ctx->rows8_on && (ctx->rows8_roles & 15) == 15) ctx->rows4_on = false;   // every role on the 8x copy
+        if (ctx->rows8_on) {
+            const bool fresh = ctx->rows8_n < nt;
+            if (fresh) {
+                cudaFree(ctx->rows8); ctx->rows8 = nullptr; ctx->rows8_n = 0;
+                SDFRT_CUDA(ctx, cudaMalloc(&ctx->rows8, nt * 8 * sizeof(float)));
+                ctx->rows8_n = nt;
+            }
+            if (dirty || fresh || !ctx->rows8_valid) {
+                LaunchScope ls(ctx, 0, st);
+                k_expand_rows8<<<(unsigned)ctx->num_sms * 8, 256, 0, st>>>(G, ctx->rows8);
+                ctx->rows8_valid = true;
+            }
         }
-        { LaunchScope ls(ctx, 0, st); k_expand_rows<<<(unsigned)ctx->num_sms * 8, 256, 0, st>>>(G, ctx->rows4); }
-        ctx->n_launches += 1;
+        if (ctx->rows4_on) {
+            const bool fresh = ctx->rows4_n < nt;
+            if (fresh) {
+                cudaFree(ctx->rows4); ctx->rows4 = nullptr; ctx->rows4_n = 0;
+                SDFRT_CUDA(ctx, cudaMalloc(&ctx->rows4, nt * sizeof(float4)));
+                ctx->rows4_n = nt;
+            }
+            if (dirty || fresh || !ctx->rows4_valid) {
+                LaunchScope ls(ctx, 0, st);
+                k_expand_rows<<<(unsigned)ctx->num_sms * 8, 256, 0, st>>>(G, ctx->rows4);
+                ctx->rows4_valid = true;
+            }
+        }
     }
+    ctx->grid_dirty = false;
     // fork: the internal streams wait for everything queued on the caller's stream (film memsets, masks)
     if (nslots > 1) {
         SDFRT_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
@@ -817,6 +868,7 @@ sdfrt_ctx* sdfrt_create(int device, int* status) {
     ctx->num_sms = prop.multiProcessorCount;
     bool ok = cudaMalloc((void**)&ctx->work, kSlots * WQ_COUNT * sizeof(unsigned)) == cudaSuccess;
     if (const char* e = std::getenv("SDFRT_ROWS4")) ctx->rows4_roles = std::atoi(e) & 15;   // developer override: 0 = off, else role mask
+    if (const char* e = std::getenv("SDFRT_ROWS8")) ctx->rows8_roles = std::atoi(e) & 15;  // developer override: role mask of the 8x copy
     if (const char* e = std::getenv("SDFRT_SLOTS")) ctx->max_slots = std::max(1, std::min(kSlots, std::atoi(e)));          // developer overrides
     if (const char* e = std::getenv("SDFRT_MIN_LIVE")) ctx->min_live = std::max(1, std::min(32, std::atoi(e)));
     if (const char* e = std::getenv("SDFRT_PRB_OCC")) ctx->prb_min_blocks = std::atoi(e);
@@ -829,12 +881,12 @@ sdfrt_ctx* sdfrt_create(int device, int* status) {
         ok = ok && cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
     }
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
-    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->march_blocks[0], k_march<false, 0, false>, kMarchBlock, 0) == cudaSuccess;
-    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->march_blocks[1], k_march<false, 1, false>, kMarchBlock, 0) == cudaSuccess;
-    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->march_blocks[2], k_march<false, 2, false>, kMarchBlock, 0) == cudaSuccess;
-    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->march_blocks[3], k_march<true, 0, false>, kMarchBlock, 0) == cudaSuccess;
-    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->march_blocks[4], k_march<true, 1, false>, kMarchBlock, 0) == cudaSuccess;
-    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->march_blocks[5], k_march<true, 2, false>, kMarchBlock, 0) == cudaSuccess;
+    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->march_blocks[0], k_march<false, 0, 0>, kMarchBlock, 0) == cudaSuccess;
+    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->march_blocks[1], k_march<false, 1, 0>, kMarchBlock, 0) == cudaSuccess;
+    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->march_blocks[2], k_march<false, 2, 0>, kMarchBlock, 0) == cudaSuccess;
+    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->march_blocks[3], k_march<true, 0, 0>, kMarchBlock, 0) == cudaSuccess;
+    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->march_blocks[4], k_march<true, 1, 0>, kMarchBlock, 0) == cudaSuccess;
+    ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->march_blocks[5], k_march<true, 2, 0>, kMarchBlock, 0) == cudaSuccess;
     for (int i = 0; i < 6; ++i) ok = ok && ctx->march_blocks[i] >= 1;
     if (const char* e = std::getenv("SDFRT_CACHE_MODES")) {  // developer override, e.g. "1102"
         for (int i = 0; i < 4 && e[i]; ++i) ctx->cache_mode[i] = (e[i] - '0') % 3;
@@ -853,12 +905,11 @@ void sdfrt_destroy(sdfrt_ctx* ctx) {
     cudaSetDevice(ctx->device);
     for (auto& t : ctx->timed) { cudaEventDestroy(t.second.first); cudaEventDestroy(t.second.second); }
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
-    cudaFree(ctx->rec);
-    cudaFree(ctx->film_adj);
+    for (auto& v : ctx->view) { cudaFree(v.rec); cudaFree(v.film_adj); cudaFree(v.prb_rec); cudaFree(v.brick_a); cudaFree(v.brick_b); cudaFree(v.pix_mask); }
     cudaFree(ctx->counters);
     cudaFree(ctx->work);
-    cudaFree(ctx->rows4); cudaFree(ctx->brick_raw); cudaFree(ctx->brick); cudaFree(ctx->pix_mask);
-    cudaFree(ctx->rd_work); cudaFree(ctx->rd_state); cudaFree(ctx->lap_r); cudaFree(ctx->prb_rec);
+    cudaFree(ctx->rows4); cudaFree(ctx->rows8); cudaFree(ctx->brick_raw);
+    cudaFree(ctx->rd_work); cudaFree(ctx->rd_state); cudaFree(ctx->lap_r);
     for (auto& sc : ctx->scratch) {
         cudaFree(sc.prb_rec); cudaFree(sc.segs); cudaFree(sc.its); cudaFree(sc.ssegs); cudaFree(sc.sinfo); cudaFree(sc.s_its); cudaFree(sc.srec); cudaFree(sc.scount);
     }
@@ -881,10 +932,13 @@ int sdfrt_set_sdf(sdfrt_ctx* ctx, const float* sdf, int rx, int ry, int rz, cons
     if (!sdf || rx < 4 || ry < 4 || rz < 4) return fail(ctx, SDFRT_ERR_INVALID, "bad SDF grid (need >= 4 texels per axis)");
     ctx->sc.G.data = sdf;
     ctx->sc.G.rows4 = nullptr;
+    ctx->sc.G.rows8 = nullptr;
     ctx->sc.G.rx = rx; ctx->sc.G.ry = ry; ctx->sc.G.rz = rz;
     ctx->sc.G.px = p ? p[0] : 0.f; ctx->sc.G.py = p ? p[1] : 0.f; ctx->sc.G.pz = p ? p[2] : 0.f;
     ctx->have_sdf = true;
-    ctx->adj_ready = false;
+    ctx->grid_dirty = true;
+    ctx->rows4_valid = ctx->rows8_valid = ctx->brick_raw_valid = false;
+    VS(ctx).adj_ready = false;
     return SDFRT_OK;
 }
 
@@ -893,7 +947,7 @@ int sdfrt_set_albedo(sdfrt_ctx* ctx, const float* rgb_grid, int rx, int ry, int 
     if (rgb_grid && (rx < 1 || ry < 1 || rz < 1)) return fail(ctx, SDFRT_ERR_INVALID, "bad albedo grid");
     ctx->sc.A.data = rgb_grid;
     ctx->sc.A.rx = rx; ctx->sc.A.ry = ry; ctx->sc.A.rz = rz;
-    ctx->adj_ready = false;
+    VS(ctx).adj_ready = false;
     return SDFRT_OK;
 }
 
@@ -903,7 +957,7 @@ int sdfrt_set_tracer(sdfrt_ctx* ctx, const sdfrt_tracer_params* p) {
     ctx->tracer_pub = *p;
     ctx->sc.T = make_tracer(*p);
     set_grid_transform(ctx->sc.G, ctx->sc.T, ctx->has_xf ? ctx->to_world : nullptr);  // the bbox travels with the tracer block
-    ctx->adj_ready = false;
+    VS(ctx).adj_ready = false;
     return SDFRT_OK;
 }
 
@@ -912,7 +966,7 @@ int sdfrt_set_warp(sdfrt_ctx* ctx, const sdfrt_warp_params* p) {
     if (p->kind < SDFRT_WARP_NONE || p->kind > SDFRT_WARP_2D) return fail(ctx, SDFRT_ERR_INVALID, "unknown warp kind");
     ctx->warp_pub = *p;
     ctx->sc.W = make_warp(*p);
-    ctx->adj_ready = false;
+    VS(ctx).adj_ready = false;
     return SDFRT_OK;
 }
 
@@ -922,7 +976,7 @@ int sdfrt_set_sensor(sdfrt_ctx* ctx, const sdfrt_sensor* s) {
         return fail(ctx, SDFRT_ERR_INVALID, "bad sensor");
     ctx->sensor_pub = *s;
     ctx->sc.S = make_sensor(*s);
-    ctx->adj_ready = false;
+    VS(ctx).adj_ready = false;
     return SDFRT_OK;
 }
 
@@ -932,7 +986,7 @@ int sdfrt_set_shading(sdfrt_ctx* ctx, const sdfrt_shading* s) {
     ctx->sc.Sh = make_shading(*s);
     ctx->sc.Sh.shadow_origin = ctx->shadow_origin;
     ctx->sc.A.cr = s->albedo[0]; ctx->sc.A.cg = s->albedo[1]; ctx->sc.A.cb = s->albedo[2];
-    ctx->adj_ready = false;
+    VS(ctx).adj_ready = false;
     return SDFRT_OK;
 }
 
@@ -941,7 +995,7 @@ int sdfrt_set_integrator(sdfrt_ctx* ctx, int integrator) {
     if (integrator < SDFRT_INTEGRATOR_SILHOUETTE || integrator > SDFRT_INTEGRATOR_PRB)
         return fail(ctx, SDFRT_ERR_INVALID, "unknown integrator");
     ctx->sc.integrator = integrator;
-    ctx->adj_ready = false;
+    VS(ctx).adj_ready = false;
     return SDFRT_OK;
 }
 
@@ -960,7 +1014,7 @@ int sdfrt_set_sdf_transform(sdfrt_ctx* ctx, const float* to_world) {
     ctx->sc.T = T;
     ctx->has_xf = to_world != nullptr;
     if (to_world) std::memcpy(ctx->to_world, to_world, sizeof(ctx->to_world));
-    ctx->adj_ready = false;
+    VS(ctx).adj_ready = false;
     return SDFRT_OK;
 }
 
@@ -969,14 +1023,14 @@ int sdfrt_set_shadow_origin(sdfrt_ctx* ctx, int mode) {
     if (mode < 0 || mode > 2) return fail(ctx, SDFRT_ERR_INVALID, "shadow origin mode must be 0 (si), 1 (detach_indirect_si) or 2 (decouple_reparam)");
     ctx->shadow_origin = mode;
     ctx->sc.Sh.shadow_origin = mode;
-    ctx->adj_ready = false;
+    VS(ctx).adj_ready = false;
     return SDFRT_OK;
 }
 
 int sdfrt_set_antithetic(sdfrt_ctx* ctx, int enable) {
     if (!ctx) return SDFRT_ERR_INVALID;
     ctx->antithetic = enable ? 1 : 0;
-    ctx->adj_ready = false;
+    VS(ctx).adj_ready = false;
     return SDFRT_OK;
 }
 
@@ -985,7 +1039,7 @@ int sdfrt_set_prb(sdfrt_ctx* ctx, const sdfrt_prb_params* p) {
     if (p->max_depth < 1 || p->max_depth > 1024 || p->rr_depth < 0) return fail(ctx, SDFRT_ERR_INVALID, "bad PRB parameters (need 1 <= max_depth <= 1024, rr_depth >= 0)");
     ctx->prb_pub = *p;
     ctx->sc.prb = make_prb(*p);
-    ctx->adj_ready = false;
+    VS(ctx).adj_ready = false;
     return SDFRT_OK;
 }
 
@@ -994,7 +1048,7 @@ int sdfrt_set_partition(sdfrt_ctx* ctx, int rank, int world) {
     if (world < 1 || rank < 0 || rank >= world) return fail(ctx, SDFRT_ERR_INVALID, "bad partition");
     ctx->rank = rank;
     ctx->world = world;
-    ctx->adj_ready = false;
+    VS(ctx).adj_ready = false;
     return SDFRT_OK;
 }
 
@@ -1013,7 +1067,15 @@ int sdfrt_set_empty_space_skip(sdfrt_ctx* ctx, int enable) {
     return SDFRT_OK;
 }
 
-uint64_t sdfrt_adjoint_token(const sdfrt_ctx* ctx) { return (ctx && ctx->adj_ready) ? ctx->adj_generation : 0ull; }
+uint64_t sdfrt_adjoint_token(const sdfrt_ctx* ctx) { return (ctx && VS(ctx).adj_ready) ? VS(ctx).generation : 0ull; }
+
+int sdfrt_set_view_slot(sdfrt_ctx* ctx, int slot) {
+    if (!ctx) return SDFRT_ERR_INVALID;
+    if (slot < 0 || slot >= kViewSlots) return fail(ctx, SDFRT_ERR_INVALID, "view slot out of range");
+    ctx->cur_view = slot;
+    return SDFRT_OK;
+}
+int sdfrt_num_view_slots(void) { return kViewSlots; }
 
 int sdfrt_film_dims(const sdfrt_ctx* ctx, int* height_b, int* width_b, int* border) {
     if (!ctx) return SDFRT_ERR_INVALID;
@@ -1063,19 +1125,20 @@ int sdfrt_adjoint_accumulate(sdfrt_ctx* ctx, uint32_t seed_grad, int spp_grad, f
     sw.diff = true;
     sw.ps = make_pass(ctx->sc.S, seed_grad, spp_grad, ctx->rank, ctx->world, ctx->sc.integrator == INTEGRATOR_PRB ? 0 : ctx->antithetic);
     sw.film = film_accum;
-    rc = ensure(ctx, &ctx->rec, &ctx->rec_capacity, (size_t)sw.ps.n_items * REC_COUNT + 1);
+    rc = ensure(ctx, &VS(ctx).rec, &VS(ctx).rec_capacity, (size_t)sw.ps.n_items * REC_COUNT + 1);
     if (rc) return rc;
-    ctx->rec_stride = sw.ps.n_items;
+    VS(ctx).rec_stride = sw.ps.n_items;
     if (ctx->sc.integrator == INTEGRATOR_PRB && ctx->prb_wavefront &&
-        (rc = ensure(ctx, &ctx->prb_rec, &ctx->prb_rec_n, (size_t)sw.ps.n_items * kPrbRecFloats * (size_t)ctx->sc.prb.max_depth + 1))) return rc;
+        (rc = ensure(ctx, &VS(ctx).prb_rec, &VS(ctx).prb_rec_n, (size_t)sw.ps.n_items * kPrbRecFloats * (size_t)ctx->sc.prb.max_depth + 1))) return rc;
     if (ctx->sc.integrator == INTEGRATOR_PRB && !ctx->prb_primary_wavefront && !ctx->prb_wavefront)  // re-render of render_backward (:204-206), keeps L per sample
-        rc = run_prb_sweep(ctx, sw.ps, film_accum, ctx->rec + (size_t)REC_S_STATE * ctx->rec_stride, ctx->rec_stride, (cudaStream_t)stream);
+        rc = run_prb_sweep(ctx, sw.ps, film_accum, VS(ctx).rec + (size_t)REC_S_STATE * VS(ctx).rec_stride, VS(ctx).rec_stride, (cudaStream_t)stream);
     else
         rc = run_sweeps(ctx, &sw, 1, (cudaStream_t)stream);
     if (rc) return rc;
-    ctx->adj_pass = sw.ps;
-    ctx->adj_ready = true;
-    ++ctx->adj_generation;
+    VS(ctx).adj_pass = sw.ps;
+    VS(ctx).sc = ctx->sc;
+    VS(ctx).adj_ready = true;
+    VS(ctx).generation = ++ctx->adj_generation;
     return SDFRT_OK;
 }
 
@@ -1094,39 +1157,41 @@ int sdfrt_render_view(sdfrt_ctx* ctx, uint32_t seed, int spp, float* film_primal
     sw[1].diff = true;
     sw[1].ps = make_pass(ctx->sc.S, seed_grad, spp_grad, ctx->rank, ctx->world, anti);
     sw[1].film = film_adjoint;
-    rc = ensure(ctx, &ctx->rec, &ctx->rec_capacity, (size_t)sw[1].ps.n_items * REC_COUNT + 1);
+    rc = ensure(ctx, &VS(ctx).rec, &VS(ctx).rec_capacity, (size_t)sw[1].ps.n_items * REC_COUNT + 1);
     if (rc) return rc;
-    ctx->rec_stride = sw[1].ps.n_items;
+    VS(ctx).rec_stride = sw[1].ps.n_items;
     if (ctx->sc.integrator == INTEGRATOR_PRB && ctx->prb_wavefront &&
-        (rc = ensure(ctx, &ctx->prb_rec, &ctx->prb_rec_n, (size_t)sw[1].ps.n_items * kPrbRecFloats * (size_t)ctx->sc.prb.max_depth + 1))) return rc;
+        (rc = ensure(ctx, &VS(ctx).prb_rec, &VS(ctx).prb_rec_n, (size_t)sw[1].ps.n_items * kPrbRecFloats * (size_t)ctx->sc.prb.max_depth + 1))) return rc;
     if (ctx->sc.integrator == INTEGRATOR_PRB && !ctx->prb_primary_wavefront && !ctx->prb_wavefront) {
         rc = run_prb_sweep(ctx, sw[0].ps, film_primal, nullptr, 0, (cudaStream_t)stream);
-        if (!rc) rc = run_prb_sweep(ctx, sw[1].ps, film_adjoint, ctx->rec + (size_t)REC_S_STATE * ctx->rec_stride, ctx->rec_stride, (cudaStream_t)stream);
+        if (!rc) rc = run_prb_sweep(ctx, sw[1].ps, film_adjoint, VS(ctx).rec + (size_t)REC_S_STATE * VS(ctx).rec_stride, VS(ctx).rec_stride, (cudaStream_t)stream);
     } else {
         rc = run_sweeps(ctx, sw, 2, (cudaStream_t)stream);
     }
     if (rc) return rc;
-    ctx->adj_pass = sw[1].ps;
-    ctx->adj_ready = true;
-    ++ctx->adj_generation;
+    VS(ctx).adj_pass = sw[1].ps;
+    VS(ctx).sc = ctx->sc;
+    VS(ctx).adj_ready = true;
+    VS(ctx).generation = ++ctx->adj_generation;
     return SDFRT_OK;
 }
 
 int sdfrt_adjoint_backprop(sdfrt_ctx* ctx, const float* film_accum, const float* grad_image, float* grad_sdf,
                            float* grad_albedo, float* grad_p, void* stream) {
     if (!ctx) return SDFRT_ERR_INVALID;
-    if (!ctx->adj_ready) return fail(ctx, SDFRT_ERR_STATE, "sdfrt_adjoint_accumulate must run first (and no set_* in between)");
+    if (!VS(ctx).adj_ready) return fail(ctx, SDFRT_ERR_STATE, "sdfrt_adjoint_accumulate must run first (and no set_* in between)");
     if (!film_accum || !grad_image) return fail(ctx, SDFRT_ERR_INVALID, "null buffer");
     if (!grad_sdf && !grad_albedo && !grad_p) return fail(ctx, SDFRT_ERR_INVALID, "no gradient target");
     SDFRT_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
-    const SensorParams& S = ctx->sc.S;
-    int rc = ensure(ctx, &ctx->film_adj, &ctx->film_adj_capacity, film_floats(ctx));
+    const SceneParams& vsc = VS(ctx).sc;   // the scene adjoint sweep 1 of this view was rendered with
+    const SensorParams& S = vsc.S;
+    int rc = ensure(ctx, &VS(ctx).film_adj, &VS(ctx).film_adj_capacity, (size_t)(S.W + 2 * S.border) * (size_t)(S.H + 2 * S.border) * 4);
     if (rc) return rc;
     const int npix = (S.W + 2 * S.border) * (S.H + 2 * S.border);
-    { LaunchScope ls(ctx, 5, st); k_film_adjoint<<<(npix + 255) / 256, 256, 0, st>>>(film_accum, grad_image, ctx->film_adj, S.W, S.H, S.border); }
+    { LaunchScope ls(ctx, 5, st); k_film_adjoint<<<(npix + 255) / 256, 256, 0, st>>>(film_accum, grad_image, VS(ctx).film_adj, S.W, S.H, S.border); }
     SDFRT_CUDA(ctx, cudaGetLastError());
-    PassParams ps = ctx->adj_pass;
+    PassParams ps = VS(ctx).adj_pass;
     ps.win_lo = ctx->win_lo;
     ps.win_hi = ctx->win_hi;
     const unsigned long long n = ps.n_items;
@@ -1135,18 +1200,18 @@ int sdfrt_adjoint_backprop(sdfrt_ctx* ctx, const float* film_accum, const float*
     tg.grad_sdf = grad_sdf;
     tg.grad_albedo = grad_albedo;
     const unsigned long long blocks = (n + kBlock - 1) / kBlock;
-    if (ctx->sc.integrator == INTEGRATOR_PRB) {
+    if (vsc.integrator == INTEGRATOR_PRB) {
         LaunchScope ls(ctx, 6, st);
-        const float* L_rec = ctx->rec + (size_t)REC_S_STATE * ctx->rec_stride;   // rows 9..11: L of the re-render
-        const float* prim = (ctx->prb_primary_wavefront && !ctx->prb_wavefront) ? ctx->rec : nullptr;  // rows 0..8: camera ray's march by k_march
-        const PrbRecords recs = ctx->prb_wavefront ? PrbRecords{ctx->prb_rec, ps.n_items, 9} : PrbRecords{nullptr, 0, 9};
+        const float* L_rec = VS(ctx).rec + (size_t)REC_S_STATE * VS(ctx).rec_stride;   // rows 9..11: L of the re-render
+        const float* prim = (ctx->prb_primary_wavefront && !ctx->prb_wavefront) ? VS(ctx).rec : nullptr;  // rows 0..8: camera ray's march by k_march
+        const PrbRecords recs = ctx->prb_wavefront ? PrbRecords{VS(ctx).prb_rec, ps.n_items, 9} : PrbRecords{nullptr, 0, 9};
         if (ctx->prb_min_blocks >= 3)
-            k_prb_backward<3><<<(unsigned)blocks, kBlock, 0, st>>>(ctx->sc, ps, ctx->film_adj, L_rec, prim, recs, ctx->rec_stride, tg, grad_p, ctx->counters);
+            k_prb_backward<3><<<(unsigned)blocks, kBlock, 0, st>>>(vsc, ps, VS(ctx).film_adj, L_rec, prim, recs, VS(ctx).rec_stride, tg, grad_p, ctx->counters);
         else
-            k_prb_backward<2><<<(unsigned)blocks, kBlock, 0, st>>>(ctx->sc, ps, ctx->film_adj, L_rec, prim, recs, ctx->rec_stride, tg, grad_p, ctx->counters);
+            k_prb_backward<2><<<(unsigned)blocks, kBlock, 0, st>>>(vsc, ps, VS(ctx).film_adj, L_rec, prim, recs, VS(ctx).rec_stride, tg, grad_p, ctx->counters);
     } else {
         LaunchScope ls(ctx, 6, st);
-        k_backward<<<(unsigned)blocks, kBlock, 0, st>>>(ctx->sc, ps, ctx->film_adj, ctx->rec, ctx->rec_stride, tg, grad_p, ctx->counters);
+        k_backward<<<(unsigned)blocks, kBlock, 0, st>>>(vsc, ps, VS(ctx).film_adj, VS(ctx).rec, VS(ctx).rec_stride, tg, grad_p, ctx->counters);
     }
     SDFRT_CUDA(ctx, cudaGetLastError());
     return SDFRT_OK;

@@ -101,6 +101,20 @@ __global__ void k_expand_rows(GridView G, float4* __restrict__ out) {
     }
 }
 
+// rows8[i * 8 + 0..3] = data[i .. i+3], [4..7] = data[i + rx .. i + rx + 3]; only bases with x <= rx - 4 and y <= ry - 2 are ever read
+// with an even row offset j in {0, 2} from by <= ry - 4, i.e. y + 1 <= ry - 1 (fold_base); the rest stays unwritten
+__global__ void k_expand_rows8(GridView G, float* __restrict__ out) {
+    const size_t n = (size_t)G.rx * G.ry * G.rz;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i % (size_t)G.rx), y = (int)((i / (size_t)G.rx) % (size_t)G.ry);
+        if (x > G.rx - 4 || y > G.ry - 2) continue;
+        float4* o = reinterpret_cast<float4*>(out + i * 8);
+        o[0] = make_float4(G.data[i], G.data[i + 1], G.data[i + 2], G.data[i + 3]);
+        const size_t u = i + (size_t)G.rx;
+        o[1] = make_float4(G.data[u], G.data[u + 1], G.data[u + 2], G.data[u + 3]);
+    }
+}
+
 __global__ void k_brick_min(GridView G, float* __restrict__ out, int nx, int ny, int nz) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;  // one thread per brick (kBrick^3 = 64 texels)
     if (i >= nx * ny * nz) return;
@@ -280,7 +294,7 @@ enum { SLOT_IDLE = 0, SLOT_MARCH = 1, SLOT_REFINE = 2, SLOT_DONE = 3 };
 
 // rec_out (DIFF): 9 rows [its_t, warp_t, warp_t_d xyz, warp_weight, warp_weight_d xyz] of stride rec_stride.
 // CACHE: 0 = gather every evaluation, 1 = tap cache in registers, 2 = tap cache in shared memory
-template <bool DIFF, int CACHE, bool ROWS4>
+template <bool DIFF, int CACHE, int ROWS>
 __global__ void __launch_bounds__(kMarchBlock, DIFF ? (CACHE == 1 ? 3 : 4) : (CACHE == 1 ? 4 : 7)) k_march(const GridView G, const TracerParams T, const SegIn* __restrict__ segs,
                                                         const unsigned* __restrict__ region_count, unsigned n_slots, unsigned region, int do_refine, int min_live,
                                                         float* __restrict__ out_its, float* __restrict__ rec_out,
@@ -373,7 +387,7 @@ __global__ void __launch_bounds__(kMarchBlock, DIFF ? (CACHE == 1 ? 3 : 4) : (CA
                 const int key = (cs.bz * G.ry + cs.by) * G.rx + cs.bx;
                 if constexpr (CACHE == 1) {          // block of the last cell kept in registers
                     if (key != tap_key) {
-                        load_taps<ROWS4>(G, cs.bx, cs.by, cs.bz, taps);
+                        load_taps<ROWS>(G, cs.bx, cs.by, cs.bz, taps);
                         tap_key = key;
                         ++n_loads;
                     }
@@ -382,7 +396,7 @@ __global__ void __launch_bounds__(kMarchBlock, DIFF ? (CACHE == 1 ? 3 : 4) : (CA
                     float f[64];
                     float* st = s_taps + threadIdx.x;
                     if (key != tap_key) {
-                        load_taps<ROWS4>(G, cs.bx, cs.by, cs.bz, f);
+                        load_taps<ROWS>(G, cs.bx, cs.by, cs.bz, f);
 #pragma unroll
                         for (int q = 0; q < 64; ++q) st[q * kMarchBlock] = f[q];
                         tap_key = key;
@@ -394,7 +408,7 @@ __global__ void __launch_bounds__(kMarchBlock, DIFF ? (CACHE == 1 ? 3 : 4) : (CA
                     reduce_taps<ORD>(f, cs, G, v, g, H);
                 } else {
                     float f[64];
-                    load_taps<ROWS4>(G, cs.bx, cs.by, cs.bz, f);
+                    load_taps<ROWS>(G, cs.bx, cs.by, cs.bz, f);
                     ++n_loads;
                     reduce_taps<ORD>(f, cs, G, v, g, H);
                 }

@@ -138,6 +138,13 @@ class Context:
         """enable=False marches every camera ray (reference behaviour); results are identical, only the work counters change."""
         check(self.ctx, self.lib.sdfrt_set_empty_space_skip(self.ctx, int(bool(enable))))
 
+    def set_view_slot(self, slot):
+        """Select the adjoint-state slot (view in flight) used by the following sweep / backprop / token calls."""
+        check(self.ctx, self.lib.sdfrt_set_view_slot(self.ctx, int(slot)))
+
+    def num_view_slots(self):
+        return int(self.lib.sdfrt_num_view_slots())
+
     def adjoint_token(self):
         """Identifies the adjoint sweep 1 whose lane records the context holds (0: none valid)."""
         return int(self.lib.sdfrt_adjoint_token(self.ctx))

@@ -53,6 +53,9 @@ class ReparamIntegrator:
         if isinstance(sensor, int):
             sensor = scene.sensors()[sensor]
         ctx = self.sdf.ctx
+        # the grid tensor may have been updated in place since the last view (optimiser step): rebind it so that the library rebuilds
+        # its derived copies -- the `parameters_changed` -> `set_tensor` of python/shapes.py:477-479
+        ctx.set_sdf(self.sdf.data, self.sdf.p)
         film = sensor.film()
         ctx.set_sensor(sensor.to_world, film.width, film.height, sensor.fov, sensor.near_clip, sensor.far_clip,
                        film.filter_radius, film.filter_stddev, film.sample_border)
@@ -81,6 +84,10 @@ class ReparamIntegrator:
         """Primal image plus the film of adjoint sweep 1, from ONE pipelined call (sdfrt_render_view): what `mi.render`
         does when gradients are enabled, with the re-render of render_backward hoisted next to the primal render (it does
         not depend on the loss).  `backprop_adjoint_sweep` then plays the role of render_backward."""
+        ctx = self.sdf.ctx
+        # adjoint state goes to the next view slot (round robin): up to num_view_slots() views can be rendered before their backward
+        self._view_slot = (getattr(self, '_view_slot', -1) + 1) % ctx.num_view_slots()
+        ctx.set_view_slot(self._view_slot)
         ctx = self._bind(scene, sensor)
         self._check_wavefront(ctx, spp)
         self._check_wavefront(ctx, spp_grad)
@@ -90,7 +97,7 @@ class ReparamIntegrator:
 
     def adjoint_sweep(self, scene, sensor, seed_grad, spp_grad):
         """Adjoint sweep 1 alone (the re-render of render_backward): rebinds the view and refills the context's lane records."""
-        ctx = self._bind(scene, sensor)
+        ctx = self._bind(scene, sensor)   # (into the currently selected view slot)
         self._check_wavefront(ctx, spp_grad)
         self.last_film = ctx.adjoint_accumulate(seed_grad, spp_grad)
         return self.last_film

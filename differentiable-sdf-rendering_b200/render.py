@@ -8,23 +8,25 @@ class _RenderOp(torch.autograd.Function):
     """Mitsuba's `_RenderOp` (python/shape_opt.py:78-83 calls it through mi.render): `eval` = primal render, `backward` =
     integrator.render_backward.  Here the re-render of render_backward (adjoint sweep 1) is hoisted next to the primal render (it
     does not depend on the loss) and its per-lane tracer records stay inside the sdfrt context until `backward`.  The context
-    holds the records of ONE sweep: the op remembers that sweep's token and, if another view was rendered in between (a loss summed
-    over several views), re-runs sweep 1 of its own view before back-propagating -- the result is the same either way."""
+    has a few view slots (sdfrt_set_view_slot), used round robin: the op remembers its slot and that sweep's token and, if the slot was
+    reused in the meantime (a loss summed over more views than there are slots), re-runs sweep 1 of its own view before
+    back-propagating -- the result is the same either way."""
 
     @staticmethod
     def forward(ctx, sdf_data, albedo, scene, sensor, seed, spp, seed_grad, spp_grad):
         integrator = scene.integrator()
         with torch.no_grad():
             image, film_a = integrator.render_with_adjoint_sweep(scene, sensor, seed, spp, seed_grad, spp_grad)
-        ctx.view = (scene, sensor, seed_grad, spp_grad, film_a, integrator.sdf.ctx.adjoint_token())
+        ctx.view = (scene, sensor, seed_grad, spp_grad, film_a, integrator._view_slot, integrator.sdf.ctx.adjoint_token())
         ctx.shapes = (sdf_data.shape, None if albedo is None else albedo.shape)
         return image
 
     @staticmethod
     def backward(ctx, grad_out):
-        scene, sensor, seed_grad, spp_grad, film_a, token = ctx.view
+        scene, sensor, seed_grad, spp_grad, film_a, slot, token = ctx.view
         integrator = scene.integrator()
         c = integrator.sdf.ctx
+        c.set_view_slot(slot)
         if token == 0 or c.adjoint_token() != token:
             film_a = integrator.adjoint_sweep(scene, sensor, seed_grad, spp_grad)
         dev = grad_out.device

@@ -121,6 +121,9 @@ void sdfrt_shading_defaults(sdfrt_shading* s);
 /* Grid3d(data) + traverse()'s `sdf.data` / `sdf.p`: python/shapes.py:378-392,469-479.
  * sdf is (rz, ry, rx) C-order, x fastest; to_world: sdfrt_set_sdf_transform (identity unless set). */
 int sdfrt_set_sdf(sdfrt_ctx* ctx, const float* sdf, int rx, int ry, int rz, const float p[3]);
+/* NOTE: like Grid3d.parameters_changed -> texture.set_tensor (python/shapes.py:477-479), sdfrt_set_sdf must be called again after
+ * the grid's VALUES change (e.g. an optimiser step in place): the marchers read derived copies of the grid (row-expanded copies,
+ * per-brick minima) that are rebuilt by the first sweep after a sdfrt_set_sdf. */
 /* Grid3d(data, transform) / integrator prop `sdf_to_world` (python/shapes.py:378-403, python/integrators/reparam.py:21-24):
  * affine to_world as a row-major 4x4 (last row 0 0 0 1), or NULL for the identity.  Lookups use to_local @ (x - p), gradients
  * and Hessians are pulled back with to_local^T, the bounding box becomes the AABB of the transformed unit cube +- 0.05. */
@@ -190,6 +193,15 @@ int sdfrt_adjoint_backprop(sdfrt_ctx* ctx, const float* film_accum, const float*
  * a caller that renders several views before back-propagating them (mi.render's CustomOp holds its inputs per view,
  * python/shape_opt.py:78-83) compares tokens and re-runs sweep 1 of a view whose records were overwritten. */
 uint64_t sdfrt_adjoint_token(const sdfrt_ctx* ctx);
+/* Views in flight.  The adjoint state of a view (lane records of sweep 1, the scene parameters it was rendered with, the film
+ * adjoint, the per-view scratch of the empty-space test) lives in one of sdfrt_num_view_slots() slots; sdfrt_set_view_slot selects
+ * the slot that the following sdfrt_adjoint_accumulate / sdfrt_render_view / sdfrt_adjoint_backprop / sdfrt_adjoint_token calls use
+ * (default 0).  The views of one optimisation iteration are independent (python/shape_opt.py:77-83): a caller may enqueue the sweeps
+ * of view v+1 (slot B, stream B) before the backprop of view v (slot A, stream A) so that the persistent kernels of one view fill
+ * the latency tails of the other.  set_* calls only invalidate the selected slot; a slot back-propagates with the scene parameters
+ * its sweep 1 saw.  The grid's derived copies are shared: do not rebind the SDF (sdfrt_set_sdf) while a view is in flight. */
+int sdfrt_set_view_slot(sdfrt_ctx* ctx, int slot);
+int sdfrt_num_view_slots(void);
 
 /* device work counters accumulated since the last reset (synchronises `stream`) */
 int sdfrt_get_stats(sdfrt_ctx* ctx, sdfrt_stats* out, int reset, void* stream);

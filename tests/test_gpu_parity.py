@@ -403,9 +403,9 @@ def test_direct_integrator_shadow_origin_variants(sdfrt_mod, prop):
 
 
 def test_render_op_holds_several_views_and_reflectance_only_gradients(sdfrt_mod):
-    """`render()` is the mi.render replacement (python/shape_opt.py:78-83).  (i) A loss summed over two views rendered before one
-    backward: the context keeps the lane records of the LAST adjoint sweep only, the op re-runs sweep 1 of the view whose records
-    were overwritten (sdfrt_adjoint_token) -- the gradient equals the sum of the per-view gradients.  (ii) Texture-only
+    """`render()` is the mi.render replacement (python/shape_opt.py:78-83).  (i) A loss summed over five views rendered before one
+    backward: the context keeps the lane records of a few views (view slots), the op re-runs sweep 1 of a view whose slot was
+    reused (sdfrt_adjoint_token) -- the gradient equals the sum of the per-view gradients.  (ii) Texture-only
     optimisation (SDF frozen): the reflectance grid is a differentiable input of the op and gets its gradient."""
     sdfrt = sdfrt_mod
     from oracle import sdf_oracle as O
@@ -418,9 +418,10 @@ def test_render_op_holds_several_views_and_reflectance_only_gradients(sdfrt_mod)
     integ.warp_field = wf
     cams = sdfrt.get_regular_cameras(6, resx=W, resy=W)
     alb = osc.albedo_grid.float().cuda().contiguous()
-    scene = sdfrt.Scene(integ, cams[:2], albedo_grid=alb)
-    w0 = torch.from_numpy(np.random.default_rng(0).uniform(-1, 1, (W, W, 3))).float().cuda()
-    w1 = torch.from_numpy(np.random.default_rng(1).uniform(-1, 1, (W, W, 3))).float().cuda()
+    scene = sdfrt.Scene(integ, cams[:5], albedo_grid=alb)
+    ws = [torch.from_numpy(np.random.default_rng(i).uniform(-1, 1, (W, W, 3))).float().cuda() for i in range(5)]
+    w0 = ws[0]
+    assert sdf.ctx.num_view_slots() < 5   # five views before one backward: more than there are view slots -> one sweep is re-run
 
     def grads(order):
         sdf.data.grad = None
@@ -428,12 +429,11 @@ def test_render_op_holds_several_views_and_reflectance_only_gradients(sdfrt_mod)
         sdf.data.requires_grad_(True)
         alb.requires_grad_(True)
         if order == 'per_view':
-            for i, w in ((0, w0), (1, w1)):
+            for i, w in enumerate(ws):
                 (sdfrt.render(scene, sensor=i, seed=3 + i, spp=spp, seed_grad=11 + i, spp_grad=spp) * w).sum().backward()
         else:
-            a = sdfrt.render(scene, sensor=0, seed=3, spp=spp, seed_grad=11, spp_grad=spp)
-            b = sdfrt.render(scene, sensor=1, seed=4, spp=spp, seed_grad=12, spp_grad=spp)
-            ((a * w0).sum() + (b * w1).sum()).backward()
+            imgs = [sdfrt.render(scene, sensor=i, seed=3 + i, spp=spp, seed_grad=11 + i, spp_grad=spp) for i in range(5)]
+            sum((im * w).sum() for im, w in zip(imgs, ws)).backward()
         return sdf.data.grad.clone(), alb.grad.clone()
 
     g1, a1 = grads('per_view')
