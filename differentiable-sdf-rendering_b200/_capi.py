@@ -40,7 +40,7 @@ class PrbParams(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [(k, C.c_uint64) for k in ('n_rays', 'n_evals_value', 'n_evals_grad', 'n_evals_hess', 'n_scatter_sites',
-                                          'n_albedo_lookups', 'n_steps_max', 'n_hits', 'n_evals_adjoint', 'n_tap_loads', 'n_skipped', 'n_launches')]
+                                          'n_albedo_lookups', 'n_steps_max', 'n_hits', 'n_evals_adjoint', 'n_tap_loads', 'n_skipped', 'n_launches', 'n_box_loads')]
 
     def as_dict(self):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}

@@ -137,7 +137,7 @@ struct ShadingParams {
 };
 struct Counters {  // device work counters (unsigned long long for atomicAdd)
     unsigned long long n_rays, n_evals_value, n_evals_grad, n_evals_hess, n_scatter_sites, n_albedo_lookups,
-        n_steps_max, n_hits, n_evals_adjoint, n_tap_loads, n_skipped;
+        n_steps_max, n_hits, n_evals_adjoint, n_tap_loads, n_skipped, n_box_loads;
 };
 
 constexpr float kBBoxDelta = 0.05f;     // python/shapes.py:416-418

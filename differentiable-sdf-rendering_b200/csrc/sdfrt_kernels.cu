@@ -8,6 +8,7 @@
 //   k_backward        one lane per thread: closed-form adjoint + 64-tap atomic scatter into dL/d(sdf).
 //   k_develop, k_trace_rays, k_eval_sdf  small helpers / test hooks.
 // No CPU fallback exists: every entry point launches device work or fails.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -385,8 +386,8 @@ struct sdfrt_ctx {
     std::vector<cudaEvent_t> event_pool;
     // per-batch scratch of the wavefront pipeline
     struct Scratch {
-        float *segs = nullptr, *its = nullptr, *ssegs = nullptr, *sinfo = nullptr, *s_its = nullptr, *srec = nullptr, *scount = nullptr, *prb_rec = nullptr;
-        size_t segs_n = 0, its_n = 0, ssegs_n = 0, sinfo_n = 0, s_its_n = 0, srec_n = 0, scount_n = 0, prb_rec_n = 0;
+        float *segs = nullptr, *its = nullptr, *ssegs = nullptr, *sinfo = nullptr, *s_its = nullptr, *srec = nullptr, *scount = nullptr, *prb_rec = nullptr, *sbox = nullptr;
+        size_t segs_n = 0, its_n = 0, ssegs_n = 0, sinfo_n = 0, s_its_n = 0, srec_n = 0, scount_n = 0, prb_rec_n = 0, sbox_n = 0;
     } scratch[kSlots];            // one per pipeline slot
     cudaStream_t aux[kSlots] = {};   // batches rotate over internal streams so that the tail of one batch's persistent
     cudaEvent_t ev_fork = nullptr, ev_join[kSlots] = {};  // kernels overlaps the following batches
@@ -410,6 +411,11 @@ struct sdfrt_ctx {
     size_t lap_r_n = 0;
     float4* rows4 = nullptr;
     size_t rows4_n = 0;
+    TmaMap tmap;                             // 3-D tensor map of the SDF grid, box (kBoxX, kBoxY, kBoxZ): SMEM box staging of the shadow marchers
+    const float* tmap_grid = nullptr;        // grid the map was encoded for
+    int tmap_dims[3] = {0, 0, 0};
+    int box_roles = 0;                       // role mask of the SMEM box staging (SDFRT_BOX; roles 1 and 3 = shadow segments), 0 = off
+    bool box_on = false;
     float* rows8 = nullptr;                  // two-rows-per-256-bit-load copy (GridView::rows8), 8x the grid
     size_t rows8_n = 0;
     int rows8_roles = 0;                     // role mask (SDFRT_ROWS8); 0 = off
@@ -486,37 +492,75 @@ int check_ready(sdfrt_ctx* ctx, int spp) {
 }
 
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+int encode_grid_tmap(sdfrt_ctx* ctx) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !p)
+            return fail(ctx, SDFRT_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+        fn = (EncodeFn)p;
+    }
+    const GridView& G = ctx->sc.G;
+    static_assert(sizeof(CUtensorMap) == sizeof(TmaMap), "tensor map size");
+    const cuuint64_t dims[3] = {(cuuint64_t)G.rx, (cuuint64_t)G.ry, (cuuint64_t)G.rz};
+    const cuuint64_t strides[2] = {(cuuint64_t)G.rx * 4ull, (cuuint64_t)G.rx * (cuuint64_t)G.ry * 4ull};
+    const cuuint32_t box[3] = {(cuuint32_t)kBoxX, (cuuint32_t)kBoxY, (cuuint32_t)kBoxZ};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = fn(reinterpret_cast<CUtensorMap*>(&ctx->tmap), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(G.data), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, SDFRT_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    ctx->tmap_grid = G.data;
+    ctx->tmap_dims[0] = G.rx; ctx->tmap_dims[1] = G.ry; ctx->tmap_dims[2] = G.rz;
+    return SDFRT_OK;
+}
+
 template <bool DIFF, int CACHE>
 void launch_march(sdfrt_ctx* ctx, unsigned grid, cudaStream_t st, const SegIn* segs, const unsigned* region_fill, unsigned n_slots, unsigned region,
-                  int do_refine, float* out_its, float* rec_out, unsigned long long rec_stride, unsigned* region_counter) {
+                  int do_refine, float* out_its, float* rec_out, unsigned long long rec_stride, unsigned* region_counter,
+                  const int4* region_box = nullptr) {
     GridView G = ctx->sc.G;
     const int role = ctx->march_role;
     const bool use8 = ctx->rows8_on && (ctx->rows8_roles >> role & 1);
     const bool use4 = !use8 && ctx->rows4_on && ((ctx->rows4_roles < 0 ? 15 : ctx->rows4_roles) >> role & 1);
     G.rows4 = use4 ? ctx->rows4 : nullptr;
     G.rows8 = use8 ? ctx->rows8 : nullptr;
+    if (region_box != nullptr && CACHE != 2) {   // shadow segments with a staged SMEM box per region (TMA)
+        const size_t smem = sizeof(BoxShared) + 128;
+        if (use8)
+            k_march<DIFF, CACHE, 8, true><<<grid, kMarchBlock, smem, st>>>(G, ctx->sc.T, segs, region_fill, n_slots, region, do_refine, ctx->min_live, out_its,
+                                                                         rec_out, rec_stride, region_counter, ctx->counters, ctx->tmap, region_box);
+        else
+            k_march<DIFF, CACHE, 4, true><<<grid, kMarchBlock, smem, st>>>(G, ctx->sc.T, segs, region_fill, n_slots, region, do_refine, ctx->min_live, out_its,
+                                                                         rec_out, rec_stride, region_counter, ctx->counters, ctx->tmap, region_box);
+        return;
+    }
     if (use8)
         k_march<DIFF, CACHE, 8><<<grid, kMarchBlock, 0, st>>>(G, ctx->sc.T, segs, region_fill, n_slots, region, do_refine, ctx->min_live, out_its, rec_out,
-                                                              rec_stride, region_counter, ctx->counters);
+                                                              rec_stride, region_counter, ctx->counters, ctx->tmap, nullptr);
     else if (use4)
         k_march<DIFF, CACHE, 4><<<grid, kMarchBlock, 0, st>>>(G, ctx->sc.T, segs, region_fill, n_slots, region, do_refine, ctx->min_live, out_its, rec_out,
-                                                              rec_stride, region_counter, ctx->counters);
+                                                              rec_stride, region_counter, ctx->counters, ctx->tmap, nullptr);
     else
         k_march<DIFF, CACHE, 0><<<grid, kMarchBlock, 0, st>>>(G, ctx->sc.T, segs, region_fill, n_slots, region, do_refine, ctx->min_live, out_its, rec_out,
-                                                              rec_stride, region_counter, ctx->counters);
+                                                              rec_stride, region_counter, ctx->counters, ctx->tmap, nullptr);
 }
 template <bool DIFF>
 void launch_march_mode(sdfrt_ctx* ctx, int role /* index into cache_mode */, unsigned need, cudaStream_t st, const SegIn* segs, const unsigned* region_fill,
                        unsigned n_slots, unsigned region, int do_refine, float* out_its, float* rec_out, unsigned long long rec_stride,
-                       unsigned* region_counter) {
+                       unsigned* region_counter, const int4* region_box = nullptr) {
     const int mode = ctx->cache_mode[role];
     ctx->march_role = role;
-    const int bps = ctx->march_blocks[(DIFF ? 3 : 0) + mode];
+    int bps = ctx->march_blocks[(DIFF ? 3 : 0) + mode];
+    if (region_box != nullptr && mode != 2) bps = std::min(bps, 3);   // 58 KB of shared memory per block
     unsigned grid = (unsigned)ctx->num_sms * (unsigned)bps;
     if (grid > need) grid = need;
-    if (mode == 0) launch_march<DIFF, 0>(ctx, grid, st, segs, region_fill, n_slots, region, do_refine, out_its, rec_out, rec_stride, region_counter);
-    else if (mode == 1) launch_march<DIFF, 1>(ctx, grid, st, segs, region_fill, n_slots, region, do_refine, out_its, rec_out, rec_stride, region_counter);
-    else launch_march<DIFF, 2>(ctx, grid, st, segs, region_fill, n_slots, region, do_refine, out_its, rec_out, rec_stride, region_counter);
+    if (mode == 0) launch_march<DIFF, 0>(ctx, grid, st, segs, region_fill, n_slots, region, do_refine, out_its, rec_out, rec_stride, region_counter, region_box);
+    else if (mode == 1) launch_march<DIFF, 1>(ctx, grid, st, segs, region_fill, n_slots, region, do_refine, out_its, rec_out, rec_stride, region_counter, region_box);
+    else launch_march<DIFF, 2>(ctx, grid, st, segs, region_fill, n_slots, region, do_refine, out_its, rec_out, rec_stride, region_counter, region_box);
 }  // camera samples per batch of the wavefront pipeline
 
 // One forward sweep over this rank's camera samples: the primal render (value tracers) or adjoint sweep 1 (differentiable
@@ -543,6 +587,9 @@ int enqueue_batch(sdfrt_ctx* ctx, const Sweep& sw, unsigned long long item0, int
     q.segs = reinterpret_cast<SegIn*>(sc.ssegs);
     q.info = reinterpret_cast<float4*>(sc.sinfo);
     q.count = reinterpret_cast<unsigned*>(sc.scount);
+    const int shadow_role = (DIFF && reparam_at_depth(ctx->sc.W, 1)) ? 3 : 1;   // which marcher walks this batch's shadow segments
+    const bool box_shadow = ctx->box_on && ctx->sc.integrator == INTEGRATOR_DIRECT && ((ctx->box_roles >> shadow_role) & 1);
+    q.box = box_shadow ? reinterpret_cast<int4*>(sc.sbox) : nullptr;
     const unsigned cnt = (unsigned)((n - item0 < B) ? (n - item0) : B);
     const unsigned blocks256 = (cnt + 255u) / 256u;
     // region size: large enough to keep a block's rays on one film column, small enough to balance the persistent grid
@@ -629,10 +676,10 @@ int enqueue_batch(sdfrt_ctx* ctx, const Sweep& sw, unsigned long long item0, int
         { LaunchScope ls(ctx, 3, bs);
           if (shadow_diff)
               launch_march_mode<true>(ctx, 3, need, bs, reinterpret_cast<const SegIn*>(sc.ssegs), q.count,
-                                      regions * region, region, 0, nullptr, sc.srec, B, work + WQ_SHADOW_CHUNK);
+                                      regions * region, region, 0, nullptr, sc.srec, B, work + WQ_SHADOW_CHUNK, q.box);
           else
               launch_march_mode<false>(ctx, 1, need, bs, reinterpret_cast<const SegIn*>(sc.ssegs), q.count,
-                                       regions * region, region, 0, sc.s_its, nullptr, 0, work + WQ_SHADOW_CHUNK); }
+                                       regions * region, region, 0, sc.s_its, nullptr, 0, work + WQ_SHADOW_CHUNK, q.box); }
         const float* shadow_its = shadow_diff ? sc.srec : sc.s_its;
         { LaunchScope ls(ctx, 4, bs);
           k_shadow_splat<DIFF><<<regions, 256, 0, bs>>>(ctx->sc, ps, item0, region, reinterpret_cast<const SegIn*>(sc.segs), q.count,
@@ -675,6 +722,7 @@ int run_sweeps(sdfrt_ctx* ctx, Sweep* sweeps, int ns, cudaStream_t st) {
         if ((rc = ensure(ctx, &sc.ssegs, &sc.ssegs_n, (size_t)Bmax * 8))) return rc;
         if ((rc = ensure(ctx, &sc.sinfo, &sc.sinfo_n, (size_t)Bmax * 4))) return rc;
         if ((rc = ensure(ctx, &sc.scount, &sc.scount_n, (size_t)(Bmax / 256) + 1))) return rc;
+        if ((rc = ensure(ctx, &sc.sbox, &sc.sbox_n, 4 * ((size_t)(Bmax / 256) + 1)))) return rc;
         if ((rc = ensure(ctx, &sc.s_its, &sc.s_its_n, (size_t)Bmax))) return rc;
         if (any_diff && (rc = ensure(ctx, &sc.srec, &sc.srec_n, (size_t)Bmax * 9))) return rc;
         if (any_value && (rc = ensure(ctx, &sc.its, &sc.its_n, (size_t)Bmax))) return rc;
@@ -763,6 +811,16 @@ int run_sweeps(sdfrt_ctx* ctx, Sweep* sweeps, int ns, cudaStream_t st) {
                 ctx->rows4_valid = true;
             }
         }
+    }
+    // tensor map of the grid for the SMEM box staging (TMA): needs 16-byte row pitch and an identity to_world
+    ctx->box_on = false;
+    if (ctx->box_roles != 0 && !ctx->sc.G.has_transform && (ctx->sc.G.rx % 4) == 0 && ctx->sc.G.rx >= kBoxBase + 4 &&
+        ctx->sc.G.ry >= kBoxBase + 3 && ctx->sc.G.rz >= kBoxBase + 3) {
+        const GridView& G = ctx->sc.G;
+        if (ctx->tmap_grid != G.data || ctx->tmap_dims[0] != G.rx || ctx->tmap_dims[1] != G.ry || ctx->tmap_dims[2] != G.rz) {
+            if ((rc = encode_grid_tmap(ctx))) return rc;
+        }
+        ctx->box_on = true;
     }
     ctx->grid_dirty = false;
     // fork: the internal streams wait for everything queued on the caller's stream (film memsets, masks)
@@ -868,6 +926,19 @@ sdfrt_ctx* sdfrt_create(int device, int* status) {
     ctx->num_sms = prop.multiProcessorCount;
     bool ok = cudaMalloc((void**)&ctx->work, kSlots * WQ_COUNT * sizeof(unsigned)) == cudaSuccess;
     if (const char* e = std::getenv("SDFRT_ROWS4")) ctx->rows4_roles = std::atoi(e) & 15;   // developer override: 0 = off, else role mask
+    std::memset(&ctx->tmap, 0, sizeof(ctx->tmap));
+    if (const char* e = std::getenv("SDFRT_BOX")) ctx->box_roles = std::atoi(e) & 10;      // developer override: SMEM box staging, roles 1 / 3
+    {
+        const int smem = (int)sizeof(BoxShared) + 128;
+        ok = ok && cudaFuncSetAttribute(k_march<false, 0, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(k_march<false, 1, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(k_march<true, 0, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(k_march<true, 1, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(k_march<false, 0, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(k_march<false, 1, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(k_march<true, 0, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(k_march<true, 1, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess;
+    }
     if (const char* e = std::getenv("SDFRT_ROWS8")) ctx->rows8_roles = std::atoi(e) & 15;  // developer override: role mask of the 8x copy
     if (const char* e = std::getenv("SDFRT_SLOTS")) ctx->max_slots = std::max(1, std::min(kSlots, std::atoi(e)));          // developer overrides
     if (const char* e = std::getenv("SDFRT_MIN_LIVE")) ctx->min_live = std::max(1, std::min(32, std::atoi(e)));
@@ -911,7 +982,7 @@ void sdfrt_destroy(sdfrt_ctx* ctx) {
     cudaFree(ctx->rows4); cudaFree(ctx->rows8); cudaFree(ctx->brick_raw);
     cudaFree(ctx->rd_work); cudaFree(ctx->rd_state); cudaFree(ctx->lap_r);
     for (auto& sc : ctx->scratch) {
-        cudaFree(sc.prb_rec); cudaFree(sc.segs); cudaFree(sc.its); cudaFree(sc.ssegs); cudaFree(sc.sinfo); cudaFree(sc.s_its); cudaFree(sc.srec); cudaFree(sc.scount);
+        cudaFree(sc.prb_rec); cudaFree(sc.segs); cudaFree(sc.its); cudaFree(sc.ssegs); cudaFree(sc.sinfo); cudaFree(sc.s_its); cudaFree(sc.srec); cudaFree(sc.scount); cudaFree(sc.sbox);
     }
     for (int i = 0; i < kSlots; ++i) {
         if (ctx->aux[i]) cudaStreamDestroy(ctx->aux[i]);
@@ -1230,6 +1301,7 @@ int sdfrt_get_stats(sdfrt_ctx* ctx, sdfrt_stats* out, int reset, void* stream) {
     out->n_evals_adjoint = c.n_evals_adjoint;
     out->n_tap_loads = c.n_tap_loads;
     out->n_skipped = c.n_skipped;
+    out->n_box_loads = c.n_box_loads;
     out->n_launches = ctx->n_launches;
     if (reset) {
         SDFRT_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, sizeof(Counters), st));

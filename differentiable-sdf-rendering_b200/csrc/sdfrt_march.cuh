@@ -257,6 +257,102 @@ __device__ __forceinline__ void warp_splat(const SensorParams& S, float* film, S
 // ---------------------------------------------------------------------------------------------------------------
 // k_march: persistent sphere tracer over segments
 // ---------------------------------------------------------------------------------------------------------------
+
+// ---------------------------------------------------------------------------------------------------------------
+// SMEM box staging for the shadow marchers (north star: "TMA-stages SDF bricks into shared memory").
+// The shadow rays of one region (= the samples of one 8-pixel film column) start on a small surface patch.  k_shade records the
+// patch's position, and the marcher block that takes the region asks the TMA unit for the box of kBoxBase^3 block bases
+// ((kBoxBase + 3)^3 texels) around it: one `cp.async.bulk.tensor.3d` from the SDF grid into one of two shared-memory buffers,
+// completion signalled on an mbarrier.  A lookup whose 4x4x4 block lies inside the box of its region reads its 64 taps from shared
+// memory (no L1 tag work: the shadow marcher's limit, profiles/); everything else -- rays that left the box, regions whose box is
+// still in flight -- takes the global (L1/L2) path as before.  Nobody ever waits for a box.
+//   buffer b holds region s_box_region[b] once s_ready[b] == s_fill[b]; a reader re-checks s_fill[b] after its loads (seqlock): the
+//   installer bumps s_fill[b] BEFORE it hands the buffer to the TMA unit, so an unchanged value proves the data was intact.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kBoxBase = 16;                 // block bases per axis covered by a box
+constexpr int kBoxY = kBoxBase + 3, kBoxZ = kBoxBase + 3;
+constexpr int kBoxX = kBoxBase + 4;          // inner extent rounded up to a multiple of 16 bytes (TMA box rule)
+constexpr int kBoxFloats = kBoxX * kBoxY * kBoxZ;
+constexpr unsigned kBoxBytes = (unsigned)kBoxFloats * 4u;
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0u;
+}
+// 3-D tiled TMA load: box of the tensor map at element coordinates (x, y, z) -> shared memory, bytes counted on `bar`
+__device__ __forceinline__ void tma_load_3d(void* dst, const void* tmap, int x, int y, int z, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<unsigned long long>(tmap)), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+struct TmaMap { alignas(64) unsigned long long opaque[16]; };  // CUtensorMap (128 bytes), filled by the host with cuTensorMapEncodeTiled
+
+struct BoxShared {
+    alignas(128) float data[2][kBoxFloats];
+    unsigned long long mbar[2];
+    int region[2];        // region id held by (or being loaded into) the buffer, -1 = none
+    int ox[2], oy[2], oz[2];
+    unsigned fill[2];     // fills handed to the TMA unit
+    unsigned ready[2];    // fills known to have landed
+    unsigned seq;         // regions installed by this block
+};
+
+// Hand buffer (seq & 1) to the TMA unit for region `id` (box origin from k_shade, w = 0: the region has no shadow rays / no box).
+// One thread.  If the buffer's previous fill is still in flight it is waited for (microseconds; a block installs a region only
+// after handing out all slots of the previous one).
+__device__ __forceinline__ void box_install(BoxShared& B, const TmaMap* tmap, const int4* __restrict__ region_box, unsigned id) {
+    const unsigned b = atomicAdd(&B.seq, 1u) & 1u;
+    const int4 org = region_box[id];
+    if (B.fill[b] != B.ready[b]) {
+        const unsigned par = (B.fill[b] - 1u) & 1u;
+        while (!mbar_test(&B.mbar[b], par)) __nanosleep(20);
+        B.ready[b] = B.fill[b];
+    }
+    *(volatile int*)&B.region[b] = -1;
+    if (org.w == 0) return;
+    *(volatile unsigned*)&B.fill[b] = B.fill[b] + 1u;        // readers of the old contents fail their re-check from here on
+    __threadfence_block();
+    B.ox[b] = org.x; B.oy[b] = org.y; B.oz[b] = org.z;
+    __threadfence_block();
+    *(volatile int*)&B.region[b] = (int)id;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx(&B.mbar[b], kBoxBytes);
+    tma_load_3d(&B.data[b][0], tmap, org.x, org.y, org.z, &B.mbar[b]);
+}
+
+// Try to serve the 4x4x4 block at (bx, by, bz) of a ray of region `my_region` from shared memory.  Returns false (f untouched or
+// garbage) if the region has no ready box, the block is outside it, or the buffer was re-used while reading.
+__device__ __forceinline__ bool box_lookup(BoxShared& B, int my_region, int bx, int by, int bz, float f[64]) {
+    const int b = (*(volatile int*)&B.region[0] == my_region) ? 0 : ((*(volatile int*)&B.region[1] == my_region) ? 1 : -1);
+    if (b < 0) return false;
+    const unsigned fill = *(volatile unsigned*)&B.fill[b];
+    if (*(volatile unsigned*)&B.ready[b] != fill) {
+        if (!mbar_test(&B.mbar[b], (fill - 1u) & 1u)) return false;   // still in flight: global path, no waiting
+        *(volatile unsigned*)&B.ready[b] = fill;
+    }
+    const int lx = bx - B.ox[b], ly = by - B.oy[b], lz = bz - B.oz[b];
+    if ((unsigned)lx >= (unsigned)kBoxBase || (unsigned)ly >= (unsigned)kBoxBase || (unsigned)lz >= (unsigned)kBoxBase) return false;
+    const float* src = &B.data[b][(lz * kBoxY + ly) * kBoxX + lx];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) f[(k * 4 + j) * 4 + i] = src[(k * kBoxY + j) * kBoxX + i];
+    // seqlock re-check (same thread, shared loads in program order): unchanged => the TMA unit did not get the buffer meanwhile
+    return *(volatile unsigned*)&B.fill[b] == fill && *(volatile int*)&B.region[b] == my_region;
+}
+
 constexpr unsigned long long kQueueExhausted = 0xFFFFFFFFull << 32;
 
 // Segments live in REGIONS of `region` slots; region r holds fill(r) valid segments at its start (primary segments: all
@@ -268,8 +364,10 @@ __device__ __forceinline__ unsigned region_fill(const unsigned* region_count, un
     const unsigned long long base = (unsigned long long)id * region;
     return (base + region <= n_slots) ? region : (unsigned)(n_slots - base);
 }
+template <bool BOX>
 __device__ __forceinline__ int fetch_items(unsigned long long* word, unsigned* region_counter, const unsigned* region_count,
-                                           unsigned n_slots, unsigned region, int n, unsigned& pos) {
+                                           unsigned n_slots, unsigned region, int n, unsigned& pos, BoxShared* box, const TmaMap* tmap,
+                                           const int4* region_box) {
     for (;;) {
         const unsigned long long old = atomicAdd(word, (unsigned long long)n);
         const unsigned id = (unsigned)(old >> 32), off = (unsigned)old;
@@ -281,6 +379,7 @@ __device__ __forceinline__ int fetch_items(unsigned long long* word, unsigned* r
                 const unsigned nid = atomicAdd(region_counter, 1u);
                 const unsigned long long nw = ((unsigned long long)nid * region >= n_slots) ? kQueueExhausted
                                                                                           : ((unsigned long long)nid << 32);
+                if (BOX && nw != kQueueExhausted) box_install(*box, tmap, region_box, nid);   // before the region becomes visible
                 atomicExch(word, nw);
             }
             pos = id * region + off;
@@ -294,13 +393,17 @@ enum { SLOT_IDLE = 0, SLOT_MARCH = 1, SLOT_REFINE = 2, SLOT_DONE = 3 };
 
 // rec_out (DIFF): 9 rows [its_t, warp_t, warp_t_d xyz, warp_weight, warp_weight_d xyz] of stride rec_stride.
 // CACHE: 0 = gather every evaluation, 1 = tap cache in registers, 2 = tap cache in shared memory
-template <bool DIFF, int CACHE, int ROWS>
-__global__ void __launch_bounds__(kMarchBlock, DIFF ? (CACHE == 1 ? 3 : 4) : (CACHE == 1 ? 4 : 7)) k_march(const GridView G, const TracerParams T, const SegIn* __restrict__ segs,
+template <bool DIFF, int CACHE, int ROWS, bool BOX = false>
+__global__ void __launch_bounds__(kMarchBlock, BOX ? 3 : (DIFF ? (CACHE == 1 ? 3 : 4) : (CACHE == 1 ? 4 : 7))) k_march(const GridView G, const TracerParams T, const SegIn* __restrict__ segs,
                                                         const unsigned* __restrict__ region_count, unsigned n_slots, unsigned region, int do_refine, int min_live,
                                                         float* __restrict__ out_its, float* __restrict__ rec_out,
                                                         unsigned long long rec_stride, unsigned* __restrict__ region_counter,
-                                                        Counters* __restrict__ counters) {
+                                                        Counters* __restrict__ counters, const __grid_constant__ TmaMap tmap,
+                                                        const int4* __restrict__ region_box) {
     __shared__ unsigned long long s_word;
+    extern __shared__ unsigned char s_dyn[];   // BOX: one BoxShared (128-byte aligned by the launch)
+    BoxShared* box = BOX ? reinterpret_cast<BoxShared*>((reinterpret_cast<size_t>(s_dyn) + 127) & ~(size_t)127) : nullptr;
+    unsigned n_box = 0;
     // Tap cache: the 4x4x4 block of the cell a slot evaluated last.  Near a surface the sphere-tracing steps are far
     // smaller than a voxel, so consecutive evaluations mostly fall into the same cell and skip the 64-tap gather.
     // The value-only marcher keeps the block in registers; the differentiable marcher (register-bound) in shared memory,
@@ -311,9 +414,16 @@ __global__ void __launch_bounds__(kMarchBlock, DIFF ? (CACHE == 1 ? 3 : 4) : (CA
     if (threadIdx.x == 0) {
         const unsigned id = atomicAdd(region_counter, 1u);
         s_word = ((unsigned long long)id * region >= n_slots) ? kQueueExhausted : ((unsigned long long)id << 32);
+        if (BOX) {
+            box->seq = 0u;
+            for (int b = 0; b < 2; ++b) { mbar_init(&box->mbar[b], 1u); box->region[b] = -1; box->fill[b] = 0u; box->ready[b] = 0u; }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            if (s_word != kQueueExhausted) box_install(*box, &tmap, region_box, id);
+        }
     }
     __syncthreads();
     const unsigned FULL = 0xffffffffu;
+    int my_region = -1;
     const int lane_id = threadIdx.x & 31;
     int state = SLOT_IDLE;
     unsigned item = 0;
@@ -344,13 +454,14 @@ __global__ void __launch_bounds__(kMarchBlock, DIFF ? (CACHE == 1 ? 3 : 4) : (CA
         if (idle != 0u && !exhausted) {
             unsigned pos = 0;
             int got = 0;
-            if (lane_id == 0) got = fetch_items(&s_word, region_counter, region_count, n_slots, region, __popc(idle), pos);
+            if (lane_id == 0) got = fetch_items<BOX>(&s_word, region_counter, region_count, n_slots, region, __popc(idle), pos, box, &tmap, region_box);
             got = __shfl_sync(FULL, got, 0);
             pos = __shfl_sync(FULL, pos, 0);
             if (got < 0) exhausted = true;
             const int my = __popc(idle & ((1u << lane_id) - 1u));
             if (state == SLOT_IDLE && my < got) {
                 item = pos + (unsigned)my;
+                if (BOX) my_region = (int)(item / region);
                 const float4 a = __ldg(&segs[item].a), b = __ldg(&segs[item].b);
                 seg.o = V3{a.x, a.y, a.z}; seg.d = V3{b.x, b.y, b.z};
                 seg.t = a.w; seg.maxt = b.w;
@@ -387,7 +498,9 @@ __global__ void __launch_bounds__(kMarchBlock, DIFF ? (CACHE == 1 ? 3 : 4) : (CA
                 const int key = (cs.bz * G.ry + cs.by) * G.rx + cs.bx;
                 if constexpr (CACHE == 1) {          // block of the last cell kept in registers
                     if (key != tap_key) {
-                        load_taps<ROWS>(G, cs.bx, cs.by, cs.bz, taps);
+                        bool from_box = false;
+                        if (BOX) { from_box = box_lookup(*box, my_region, cs.bx, cs.by, cs.bz, taps); n_box += from_box; }
+                        if (!from_box) load_taps<ROWS>(G, cs.bx, cs.by, cs.bz, taps);
                         tap_key = key;
                         ++n_loads;
                     }
@@ -408,7 +521,9 @@ __global__ void __launch_bounds__(kMarchBlock, DIFF ? (CACHE == 1 ? 3 : 4) : (CA
                     reduce_taps<ORD>(f, cs, G, v, g, H);
                 } else {
                     float f[64];
-                    load_taps<ROWS>(G, cs.bx, cs.by, cs.bz, f);
+                    bool from_box = false;
+                    if (BOX) { from_box = box_lookup(*box, my_region, cs.bx, cs.by, cs.bz, f); n_box += from_box; }
+                    if (!from_box) load_taps<ROWS>(G, cs.bx, cs.by, cs.bz, f);
                     ++n_loads;
                     reduce_taps<ORD>(f, cs, G, v, g, H);
                 }
@@ -432,12 +547,21 @@ __global__ void __launch_bounds__(kMarchBlock, DIFF ? (CACHE == 1 ? 3 : 4) : (CA
     for (int o = 16; o > 0; o >>= 1) {
         n_evals += __shfl_xor_sync(FULL, n_evals, o);
         n_loads += __shfl_xor_sync(FULL, n_loads, o);
+        if (BOX) n_box += __shfl_xor_sync(FULL, n_box, o);
         n_steps_max = max(n_steps_max, __shfl_xor_sync(FULL, n_steps_max, o));
     }
     if (lane_id == 0) {
         if (n_evals) atomicAdd(DIFF ? &counters->n_evals_hess : &counters->n_evals_value, (unsigned long long)n_evals);
         if (n_loads) atomicAdd(&counters->n_tap_loads, (unsigned long long)n_loads);
+        if (BOX && n_box) atomicAdd(&counters->n_box_loads, (unsigned long long)n_box);
         atomicMax(&counters->n_steps_max, (unsigned long long)n_steps_max);
+    }
+    if (BOX) {   // a block must not exit while the TMA unit may still write into its shared memory
+        __syncthreads();
+        if (threadIdx.x == 0)
+            for (int b = 0; b < 2; ++b)
+                if (box->fill[b] != box->ready[b])
+                    while (!mbar_test(&box->mbar[b], (box->fill[b] - 1u) & 1u)) __nanosleep(20);
     }
 }
 
@@ -452,6 +576,7 @@ struct ShadowQueue {
     SegIn* segs;      // [n_slots] shadow segments, region-compacted
     float4* info;     // [n_slots] rgb added if unoccluded, item index (bit pattern) in .w
     unsigned* count;  // [n_regions] valid segments per region
+    int4* box;        // [n_regions] or nullptr: origin (block-base texel coordinates) of the SMEM box of the region's shadow rays, w = valid
 };
 
 template <bool DIFF>
@@ -461,12 +586,17 @@ __global__ void __launch_bounds__(256, 3) k_shade(const __grid_constant__ SceneP
                                                 Counters* __restrict__ counters) {
     __shared__ SplatSmem s_splat[8];
     __shared__ unsigned s_count;
-    if (threadIdx.x == 0) s_count = 0;
+    __shared__ int s_lo[3], s_hi[3];   // block bases of the shadow origins (for the marcher's SMEM box)
+    if (threadIdx.x == 0) {
+        s_count = 0;
+        for (int a = 0; a < 3; ++a) { s_lo[a] = 0x7fffffff; s_hi[a] = -0x7fffffff; }
+    }
     __syncthreads();
     const unsigned FULL = 0xffffffffu;
     const int lane_id = threadIdx.x & 31;
     const unsigned region_base = blockIdx.x * region;
     unsigned n_grad = 0, n_alb = 0, n_hit = 0, n_rays = 0;
+    int my_lo[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, my_hi[3] = {-0x7fffffff, -0x7fffffff, -0x7fffffff};
     for (unsigned it = 0; it < region / 256u; ++it) {
         const unsigned i = region_base + it * 256u + threadIdx.x;
         if (region_base + it * 256u >= n) break;  // block-uniform
@@ -514,6 +644,11 @@ __global__ void __launch_bounds__(256, 3) k_shade(const __grid_constant__ SceneP
                         info = make_float4(rho.x * k * sc.Sh.Le[0], rho.y * k * sc.Sh.Le[1], rho.z * k * sc.Sh.Le[2], __uint_as_float(i));
                         sseg = make_seg(sc.T, sr.o, sr.d, sr.maxt);
                         push = true;
+                        if (q.box != nullptr) {
+                            const CellCoord cc = cell_coord(sc.G, sr.o);
+                            my_lo[0] = min(my_lo[0], cc.ix); my_lo[1] = min(my_lo[1], cc.iy); my_lo[2] = min(my_lo[2], cc.iz);
+                            my_hi[0] = max(my_hi[0], cc.ix); my_hi[1] = max(my_hi[1], cc.iy); my_hi[2] = max(my_hi[2], cc.iz);
+                        }
                     }
                 }
             }
@@ -532,8 +667,33 @@ __global__ void __launch_bounds__(256, 3) k_shade(const __grid_constant__ SceneP
             }
         }
     }
+    if (q.box != nullptr) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            int lo = my_lo[a], hi = my_hi[a];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { lo = min(lo, __shfl_xor_sync(FULL, lo, o)); hi = max(hi, __shfl_xor_sync(FULL, hi, o)); }
+            if (lane_id == 0 && hi >= lo) { atomicMin(&s_lo[a], lo); atomicMax(&s_hi[a], hi); }
+        }
+    }
     __syncthreads();
-    if (threadIdx.x == 0) q.count[blockIdx.x] = s_count;
+    if (threadIdx.x == 0) {
+        q.count[blockIdx.x] = s_count;
+        if (q.box != nullptr) {   // box of kBoxBase^3 block bases centred on the origin patch, kept inside the grid
+            int4 b = make_int4(0, 0, 0, 0);
+            if (s_count > 0u) {
+                const int r[3] = {sc.G.rx, sc.G.ry, sc.G.rz};
+                int o3[3];
+                for (int a = 0; a < 3; ++a) {
+                    int c = (s_lo[a] + s_hi[a]) / 2 - kBoxBase / 2;
+                    c = max(0, min(c, r[a] - (kBoxBase + 3)));
+                    o3[a] = c;
+                }
+                b = make_int4(o3[0], o3[1], o3[2], 1);
+            }
+            q.box[blockIdx.x] = b;
+        }
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         n_grad += __shfl_xor_sync(FULL, n_grad, o);

@@ -94,6 +94,7 @@ typedef struct sdfrt_stats {
     uint64_t n_tap_loads;     /* marcher evaluations that actually gathered their 4x4x4 block (tap-cache misses) */
     uint64_t n_skipped;       /* camera rays proven clear of the surface by the brick lower bound (never marched) */
     uint64_t n_launches;      /* kernels launched by the library (host-side count) */
+    uint64_t n_box_loads;     /* tap loads served from a TMA-staged shared-memory box instead of L1/L2 (shadow marchers, SDFRT_BOX) */
 } sdfrt_stats;
 
 /* per-ray tracer outputs of SDFBase.ray_intersect, python/shapes.py:288 (test hook) */

@@ -452,3 +452,49 @@ def test_render_op_holds_several_views_and_reflectance_only_gradients(sdfrt_mod)
     alb.grad = None
     (sdfrt.render(scene, sensor=0, seed=3, spp=spp, seed_grad=11, spp_grad=spp) * w0).sum().backward()
     assert only.abs().max() > 0 and (only - alb.grad).abs().max() < 1e-4 * only.abs().max()
+
+
+@pytest.mark.parametrize('env', [{'SDFRT_ROWS8': '15'}, {'SDFRT_BOX': '10'}, {'SDFRT_BOX': '10', 'SDFRT_ROWS8': '10'}])
+def test_marcher_variants_give_the_same_films_and_gradients(sdfrt_mod, env):
+    """Developer variants of k_march read the SAME taps by other routes -- the 8x row-expanded copy with 256-bit loads (SDFRT_ROWS8)
+    and TMA-staged shared-memory boxes for the shadow segments (SDFRT_BOX) -- so films, gradients and evaluation counts must not
+    change (films/gradients up to the order of the atomics)."""
+    import baseline_cases as B
+    sdfrt = sdfrt_mod
+    kind, R, AR, W, spp, mult, ns = B.CONFIGS['c2']
+    sdf = torch.from_numpy(B.grid(kind, R)).cuda()
+    cam = sdfrt.get_regular_cameras(ns, resx=W, resy=W)[0]
+    G = torch.ones((W, W, 3), device='cuda')
+
+    def run(e):
+        old = {k: os.environ.get(k) for k in e}
+        os.environ.update(e)
+        try:
+            ctx = sdfrt.Context(0)
+        finally:
+            for k, v in old.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+        ctx.set_sdf(sdf)
+        ctx.set_sensor(cam.to_world, W, W)
+        ctx.set_shading()
+        ctx.set_integrator('sdf_direct_reparam')
+        ctx.set_warp()
+        ctx.stats(reset=True)
+        fp, fa = ctx.render_view(5, spp * mult, 18, spp)
+        g = torch.zeros_like(sdf)
+        ctx.adjoint_backprop(fa, G, g)
+        return fp.clone(), fa.clone(), g, ctx.stats(reset=True)
+
+    fp0, fa0, g0, st0 = run({})
+    fp1, fa1, g1, st1 = run(env)
+    for k in ('n_evals_value', 'n_evals_hess', 'n_evals_grad', 'n_tap_loads', 'n_hits', 'n_scatter_sites'):
+        assert st0[k] == st1[k], (k, st0[k], st1[k])
+    assert (fp0 - fp1).abs().max() < 1e-5 * fp0.abs().max() and (fa0 - fa1).abs().max() < 1e-5 * fa0.abs().max()
+    assert (g0 - g1).abs().max() < 1e-4 * g0.abs().max()
+    if 'SDFRT_BOX' in env:
+        assert st1['n_box_loads'] > 0.05 * st1['n_tap_loads'], st1
+    else:
+        assert st1['n_box_loads'] == 0
