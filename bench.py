@@ -107,7 +107,22 @@ _CPU_SCENE = {}
 
 
 def host_cores():
-    return len(os.sched_getaffinity(0))
+    """Usable host cores: the affinity mask, capped by the cgroup CPU quota (a container may see 128 CPUs and be allowed 16)."""
+    n = len(os.sched_getaffinity(0))
+    try:
+        with open('/sys/fs/cgroup/cpu.max') as f:
+            q, p = f.read().split()[:2]
+        if q != 'max':
+            n = max(1, min(n, int(float(q) / float(p) + 0.5)))
+    except Exception:
+        try:
+            q = int(open('/sys/fs/cgroup/cpu/cpu.cfs_quota_us').read())
+            p = int(open('/sys/fs/cgroup/cpu/cpu.cfs_period_us').read())
+            if q > 0:
+                n = max(1, min(n, int(q / p + 0.5)))
+        except Exception:
+            pass
+    return n
 
 
 def cpu_scene(wl):
@@ -130,14 +145,29 @@ def cpu_sample(wl, n_primal, seed):
     kind, R, AR, W, H, spp, mult, nsens = WORKLOADS[wl]
     sdf, alb, tw = cpu_scene(wl)
     r = cpu_port.time_sample(sdf, alb, tw, W, H, seed, spp * mult, spp, n_primal, max(spp, n_primal // mult),
-                             prb=PRB_WORKLOADS.get(wl), threads=host_cores())
+                             prb=PRB_WORKLOADS.get(wl), threads=_CPU_THREADS.get('n', host_cores()))
     r['seconds'] = r['seconds_primal'] + r['seconds_adjoint']
     return r
+
+
+_CPU_THREADS = {}
 
 
 def cpu_calibrated_sample(wl, target_s, seed=100):
     kind, R, AR, W, H, spp, mult, nsens = WORKLOADS[wl]
     full = (W + 4) * (H + 4) * spp * mult
+    # "all the host threads it can use": more threads are not always faster on a shared host (SMT siblings, CPU quota), so probe
+    # the full affinity count and its half / quarter once and keep the fastest
+    if 'n' not in _CPU_THREADS:
+        best = None
+        for t in sorted({host_cores(), max(1, host_cores() // 2), max(1, host_cores() // 4)}, reverse=True):
+            _CPU_THREADS['n'] = t
+            cpu_sample(wl, min(full, 1 << 17), seed)          # warm the thread pool
+            p = cpu_sample(wl, min(full, 1 << 19), seed)
+            r = p['rays'] / p['seconds']
+            if best is None or r > best[0]:
+                best = (r, t)
+        _CPU_THREADS['n'] = best[1]
     probe = cpu_sample(wl, min(full, 1 << 19), seed)
     rate = probe['rays'] / probe['seconds']
     n = int(min(full, max(1 << 19, target_s * rate * mult / (mult + 1))))

@@ -170,7 +170,7 @@ def test_device_counters_equal_the_oracle_count(sdfrt_mod):
         counts[skip] = st['n_evals_value'] + st['n_evals_grad'] + st['n_evals_hess']
     assert n_oracle > 10000 and abs(counts[0] - n_oracle) <= 2e-3 * n_oracle, (counts, n_oracle)
     assert counts[1] <= counts[0]
-    assert torch.equal(films[0][..., 3], films[1][..., 3]) and (films[0] - films[1]).abs().max() < 1e-5   # skipping changes no result
+    assert (films[0] - films[1]).abs().max() < 1e-5 * films[0].abs().max()   # skipping changes no result (up to the order of the atomics)
     # (ii) the middle band of C2 at the adjoint spp, primal silhouette render: oracle restricted to the band's lanes
     name = 'c2'
     kind, R, AR, Wc, sppc, mult, ns = B.CONFIGS[name]
