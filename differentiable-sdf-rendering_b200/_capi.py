@@ -71,6 +71,7 @@ SIGNATURES = {
     'sdfrt_set_shading': (C.c_int, [_P, C.POINTER(ShadingParams)]),
     'sdfrt_set_integrator': (C.c_int, [_P, C.c_int]),
     'sdfrt_set_antithetic': (C.c_int, [_P, C.c_int]),
+    'sdfrt_set_use_mis': (C.c_int, [_P, C.c_int]),
     'sdfrt_set_shadow_origin': (C.c_int, [_P, C.c_int]),
     'sdfrt_prb_defaults': (None, [C.POINTER(PrbParams)]),
     'sdfrt_set_prb': (C.c_int, [_P, C.POINTER(PrbParams)]),

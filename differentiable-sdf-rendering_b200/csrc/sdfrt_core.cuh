@@ -134,6 +134,9 @@ struct ShadingParams {
     // 0 = si (attached, default), 1 = detach(si) (`detach_indirect_si`), 2 = si_d0 (`decouple_reparam`: the interaction of the
     // detached primary ray -- it still moves with the SDF, but not with the primary ray's warp)
     int shadow_origin;
+    // ReparamIntegrator prop `use_mis` (python/integrators/reparam.py:17): sdf_direct_reparam combines the emitter sample with a
+    // BSDF sample by the power heuristic (python/integrators/sdf_direct_reparam.py:76-79,87-107)
+    int use_mis;
 };
 struct Counters {  // device work counters (unsigned long long for atomicAdd)
     unsigned long long n_rays, n_evals_value, n_evals_grad, n_evals_hess, n_scatter_sites, n_albedo_lookups,

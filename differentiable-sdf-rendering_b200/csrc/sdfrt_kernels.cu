@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(kBlock) k_backward(const __grid_constant__ Sce
         const unsigned long long wl = w.lane & ~kAntiBit;
         if (wl >= ps.win_lo && wl < ps.win_hi) lane_backward(sc, ps, w.lane, film_adj, rec + item, rec_stride, tg, gp, sites, st);
     }
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < 5; ++q) {
         const bool has = q < sites.n;
         unsigned rem = __ballot_sync(FULL, has);
         if (rem == 0u) break;
@@ -349,6 +349,7 @@ struct sdfrt_ctx {
     float to_world[16];      // Grid3d's transform (row-major) when has_xf
     bool has_xf = false;
     int shadow_origin = 0;   // sdf_direct_reparam props detach_indirect_si (1) / decouple_reparam (2)
+    int use_mis = 0;         // ReparamIntegrator prop use_mis (python/integrators/reparam.py:17)
     int antithetic = 0;  // ReparamIntegrator.antithetic_sampling (python/integrators/reparam.py:19); not used by sdf_prb_reparam
     bool have_sdf = false;
     // Adjoint state of a VIEW: the lane records of adjoint sweep 1, the scene it was rendered with and the per-view scratch of the
@@ -386,8 +387,9 @@ struct sdfrt_ctx {
     std::vector<cudaEvent_t> event_pool;
     // per-batch scratch of the wavefront pipeline
     struct Scratch {
-        float *segs = nullptr, *its = nullptr, *ssegs = nullptr, *sinfo = nullptr, *s_its = nullptr, *srec = nullptr, *scount = nullptr, *prb_rec = nullptr, *sbox = nullptr;
-        size_t segs_n = 0, its_n = 0, ssegs_n = 0, sinfo_n = 0, s_its_n = 0, srec_n = 0, scount_n = 0, prb_rec_n = 0, sbox_n = 0;
+        float *segs = nullptr, *its = nullptr, *ssegs = nullptr, *sinfo = nullptr, *s_its = nullptr, *srec = nullptr, *scount = nullptr, *prb_rec = nullptr, *sbox = nullptr,
+              *bsegs = nullptr, *binfo = nullptr, *b_its = nullptr, *brec = nullptr, *bcount = nullptr;   // use_mis: BSDF-sampled rays
+        size_t segs_n = 0, its_n = 0, ssegs_n = 0, sinfo_n = 0, s_its_n = 0, srec_n = 0, scount_n = 0, prb_rec_n = 0, sbox_n = 0, bsegs_n = 0, binfo_n = 0, b_its_n = 0, brec_n = 0, bcount_n = 0;
     } scratch[kSlots];            // one per pipeline slot
     cudaStream_t aux[kSlots] = {};   // batches rotate over internal streams so that the tail of one batch's persistent
     cudaEvent_t ev_fork = nullptr, ev_join[kSlots] = {};  // kernels overlaps the following batches
@@ -478,6 +480,10 @@ struct LaunchScope {
 size_t film_floats(const sdfrt_ctx* ctx) {
     const SensorParams& S = ctx->sc.S;
     return (size_t)(S.W + 2 * S.border) * (size_t)(S.H + 2 * S.border) * 4;
+}
+
+int rec_rows(const sdfrt_ctx* ctx) {   // rows of a lane record: the BSDF-sampled ray of the MIS branch adds nine
+    return (ctx->sc.Sh.use_mis && ctx->sc.integrator == INTEGRATOR_DIRECT) ? (int)REC_COUNT_MIS : (int)REC_COUNT;
 }
 
 int check_ready(sdfrt_ctx* ctx, int spp) {
@@ -590,6 +596,12 @@ int enqueue_batch(sdfrt_ctx* ctx, const Sweep& sw, unsigned long long item0, int
     const int shadow_role = (DIFF && reparam_at_depth(ctx->sc.W, 1)) ? 3 : 1;   // which marcher walks this batch's shadow segments
     const bool box_shadow = ctx->box_on && ctx->sc.integrator == INTEGRATOR_DIRECT && ((ctx->box_roles >> shadow_role) & 1);
     q.box = box_shadow ? reinterpret_cast<int4*>(sc.sbox) : nullptr;
+    const bool mis = ctx->sc.Sh.use_mis && ctx->sc.integrator == INTEGRATOR_DIRECT;
+    ShadowQueue qb;   // use_mis: the BSDF-sampled rays of the batch, region-compacted like the shadow segments
+    qb.segs = reinterpret_cast<SegIn*>(sc.bsegs);
+    qb.info = reinterpret_cast<float4*>(sc.binfo);
+    qb.count = reinterpret_cast<unsigned*>(sc.bcount);
+    qb.box = nullptr;
     const unsigned cnt = (unsigned)((n - item0 < B) ? (n - item0) : B);
     const unsigned blocks256 = (cnt + 255u) / 256u;
     // region size: large enough to keep a block's rays on one film column, small enough to balance the persistent grid
@@ -667,8 +679,9 @@ int enqueue_batch(sdfrt_ctx* ctx, const Sweep& sw, unsigned long long item0, int
         return SDFRT_OK;
     }
     { LaunchScope ls(ctx, 2, bs);
-      k_shade<DIFF><<<regions, 256, 0, bs>>>(ctx->sc, ps, item0, cnt, region, reinterpret_cast<const SegIn*>(sc.segs), its, q, film,
-                                             DIFF ? rec_b + REC_S_STATE * VS(ctx).rec_stride : nullptr, ctx->counters); }
+      k_shade<DIFF><<<regions, 256, 0, bs>>>(ctx->sc, ps, item0, cnt, region, reinterpret_cast<const SegIn*>(sc.segs), its, q, qb, film,
+                                             DIFF ? rec_b + REC_S_STATE * VS(ctx).rec_stride : nullptr,
+                                             (DIFF && mis) ? rec_b + REC_B_STATE * VS(ctx).rec_stride : nullptr, ctx->counters); }
     if (ctx->sc.integrator == INTEGRATOR_DIRECT) {
         // shadow march over the region-compacted queue.  The differentiable tracer is only needed if shadow rays are
         // reparameterised (python/warp.py:103: max_reparam_depth); otherwise the value tracer's its_t is all the pass uses.
@@ -685,6 +698,21 @@ int enqueue_batch(sdfrt_ctx* ctx, const Sweep& sw, unsigned long long item0, int
           k_shadow_splat<DIFF><<<regions, 256, 0, bs>>>(ctx->sc, ps, item0, region, reinterpret_cast<const SegIn*>(sc.segs), q.count,
                                                         reinterpret_cast<const float4*>(sc.sinfo), shadow_its, sc.srec, B, film, rec_b,
                                                         VS(ctx).rec_stride); }
+        if (mis) {   // BSDF-sampled rays: same marchers (no refinement: only hit / escape and the warp record matter), second splat
+            SDFRT_CUDA(ctx, cudaMemsetAsync(work + WQ_SHADOW_CHUNK, 0, sizeof(unsigned), bs));
+            { LaunchScope ls(ctx, 3, bs);
+              if (shadow_diff)
+                  launch_march_mode<true>(ctx, 3, need, bs, reinterpret_cast<const SegIn*>(sc.bsegs), qb.count,
+                                          regions * region, region, 0, nullptr, sc.brec, B, work + WQ_SHADOW_CHUNK);
+              else
+                  launch_march_mode<false>(ctx, 1, need, bs, reinterpret_cast<const SegIn*>(sc.bsegs), qb.count,
+                                           regions * region, region, 0, sc.b_its, nullptr, 0, work + WQ_SHADOW_CHUNK); }
+            const float* b_its = shadow_diff ? sc.brec : sc.b_its;
+            { LaunchScope ls(ctx, 4, bs);
+              k_shadow_splat<DIFF, true><<<regions, 256, 0, bs>>>(ctx->sc, ps, item0, region, reinterpret_cast<const SegIn*>(sc.segs), qb.count,
+                                                                  reinterpret_cast<const float4*>(sc.binfo), b_its, sc.brec, B, film, rec_b,
+                                                                  VS(ctx).rec_stride); }
+        }
     }
     SDFRT_CUDA(ctx, cudaGetLastError());
     return SDFRT_OK;
@@ -725,6 +753,13 @@ int run_sweeps(sdfrt_ctx* ctx, Sweep* sweeps, int ns, cudaStream_t st) {
         if ((rc = ensure(ctx, &sc.sbox, &sc.sbox_n, 4 * ((size_t)(Bmax / 256) + 1)))) return rc;
         if ((rc = ensure(ctx, &sc.s_its, &sc.s_its_n, (size_t)Bmax))) return rc;
         if (any_diff && (rc = ensure(ctx, &sc.srec, &sc.srec_n, (size_t)Bmax * 9))) return rc;
+        if (ctx->sc.Sh.use_mis && ctx->sc.integrator == INTEGRATOR_DIRECT) {
+            if ((rc = ensure(ctx, &sc.bsegs, &sc.bsegs_n, (size_t)Bmax * 8))) return rc;
+            if ((rc = ensure(ctx, &sc.binfo, &sc.binfo_n, (size_t)Bmax * 4))) return rc;
+            if ((rc = ensure(ctx, &sc.bcount, &sc.bcount_n, (size_t)(Bmax / 256) + 1))) return rc;
+            if ((rc = ensure(ctx, &sc.b_its, &sc.b_its_n, (size_t)Bmax))) return rc;
+            if (any_diff && (rc = ensure(ctx, &sc.brec, &sc.brec_n, (size_t)Bmax * 9))) return rc;
+        }
         if (any_value && (rc = ensure(ctx, &sc.its, &sc.its_n, (size_t)Bmax))) return rc;
         if (any_value && ctx->sc.integrator == INTEGRATOR_PRB && ctx->prb_wavefront &&
             (rc = ensure(ctx, &sc.prb_rec, &sc.prb_rec_n, (size_t)Bmax * 2 * (size_t)ctx->sc.prb.max_depth))) return rc;
@@ -983,6 +1018,7 @@ void sdfrt_destroy(sdfrt_ctx* ctx) {
     cudaFree(ctx->rd_work); cudaFree(ctx->rd_state); cudaFree(ctx->lap_r);
     for (auto& sc : ctx->scratch) {
         cudaFree(sc.prb_rec); cudaFree(sc.segs); cudaFree(sc.its); cudaFree(sc.ssegs); cudaFree(sc.sinfo); cudaFree(sc.s_its); cudaFree(sc.srec); cudaFree(sc.scount); cudaFree(sc.sbox);
+        cudaFree(sc.bsegs); cudaFree(sc.binfo); cudaFree(sc.b_its); cudaFree(sc.brec); cudaFree(sc.bcount);
     }
     for (int i = 0; i < kSlots; ++i) {
         if (ctx->aux[i]) cudaStreamDestroy(ctx->aux[i]);
@@ -1056,6 +1092,7 @@ int sdfrt_set_shading(sdfrt_ctx* ctx, const sdfrt_shading* s) {
     ctx->shading_pub = *s;
     ctx->sc.Sh = make_shading(*s);
     ctx->sc.Sh.shadow_origin = ctx->shadow_origin;
+    ctx->sc.Sh.use_mis = ctx->use_mis;
     ctx->sc.A.cr = s->albedo[0]; ctx->sc.A.cg = s->albedo[1]; ctx->sc.A.cb = s->albedo[2];
     VS(ctx).adj_ready = false;
     return SDFRT_OK;
@@ -1094,6 +1131,14 @@ int sdfrt_set_shadow_origin(sdfrt_ctx* ctx, int mode) {
     if (mode < 0 || mode > 2) return fail(ctx, SDFRT_ERR_INVALID, "shadow origin mode must be 0 (si), 1 (detach_indirect_si) or 2 (decouple_reparam)");
     ctx->shadow_origin = mode;
     ctx->sc.Sh.shadow_origin = mode;
+    VS(ctx).adj_ready = false;
+    return SDFRT_OK;
+}
+
+int sdfrt_set_use_mis(sdfrt_ctx* ctx, int enable) {
+    if (!ctx) return SDFRT_ERR_INVALID;
+    ctx->use_mis = enable ? 1 : 0;
+    ctx->sc.Sh.use_mis = ctx->use_mis;
     VS(ctx).adj_ready = false;
     return SDFRT_OK;
 }
@@ -1196,7 +1241,7 @@ int sdfrt_adjoint_accumulate(sdfrt_ctx* ctx, uint32_t seed_grad, int spp_grad, f
     sw.diff = true;
     sw.ps = make_pass(ctx->sc.S, seed_grad, spp_grad, ctx->rank, ctx->world, ctx->sc.integrator == INTEGRATOR_PRB ? 0 : ctx->antithetic);
     sw.film = film_accum;
-    rc = ensure(ctx, &VS(ctx).rec, &VS(ctx).rec_capacity, (size_t)sw.ps.n_items * REC_COUNT + 1);
+    rc = ensure(ctx, &VS(ctx).rec, &VS(ctx).rec_capacity, (size_t)sw.ps.n_items * (size_t)rec_rows(ctx) + 1);
     if (rc) return rc;
     VS(ctx).rec_stride = sw.ps.n_items;
     if (ctx->sc.integrator == INTEGRATOR_PRB && ctx->prb_wavefront &&
@@ -1228,7 +1273,7 @@ int sdfrt_render_view(sdfrt_ctx* ctx, uint32_t seed, int spp, float* film_primal
     sw[1].diff = true;
     sw[1].ps = make_pass(ctx->sc.S, seed_grad, spp_grad, ctx->rank, ctx->world, anti);
     sw[1].film = film_adjoint;
-    rc = ensure(ctx, &VS(ctx).rec, &VS(ctx).rec_capacity, (size_t)sw[1].ps.n_items * REC_COUNT + 1);
+    rc = ensure(ctx, &VS(ctx).rec, &VS(ctx).rec_capacity, (size_t)sw[1].ps.n_items * (size_t)rec_rows(ctx) + 1);
     if (rc) return rc;
     VS(ctx).rec_stride = sw[1].ps.n_items;
     if (ctx->sc.integrator == INTEGRATOR_PRB && ctx->prb_wavefront &&

@@ -85,7 +85,11 @@ enum {
     REC_ITS_T = 0, REC_TAU, REC_TAU_DX, REC_TAU_DY, REC_TAU_DZ, REC_OMEGA, REC_OMEGA_DX, REC_OMEGA_DY, REC_OMEGA_DZ,
     REC_S_STATE,  // shadow ray: 0 = no NEE contribution, 1 = unoccluded and gates passed
     REC_S_TAU, REC_S_TAU_DX, REC_S_TAU_DY, REC_S_TAU_DZ, REC_S_OMEGA, REC_S_OMEGA_DX, REC_S_OMEGA_DY, REC_S_OMEGA_DZ,
-    REC_COUNT
+    REC_COUNT,         // rows of a record without the BSDF-sampled ray
+    // use_mis: the BSDF-sampled ray (python/integrators/sdf_direct_reparam.py:87-107): 0 = no contribution, 1 = escaped to the emitter
+    REC_B_STATE = REC_COUNT,
+    REC_B_TAU, REC_B_TAU_DX, REC_B_TAU_DY, REC_B_TAU_DZ, REC_B_OMEGA, REC_B_OMEGA_DX, REC_B_OMEGA_DY, REC_B_OMEGA_DZ,
+    REC_COUNT_MIS
 };
 
 struct LaneStats {
@@ -146,6 +150,62 @@ SDFRT_HD ShadowRay make_shadow_ray(const ShadingParams& Sh, V3 p, V3 n, float u0
     return s;
 }
 
+constexpr float kInv4Pi = 0.07957747154594767f;
+
+// mitsuba `coordinate_system` (Duff et al. 2017) -- the frame initialize_sh_frame builds when dp_du == 0
+// (python/shapes.py:360); s = first vector, t = cross(n, s).  oracle/ref_semantics.md S14
+SDFRT_HD void sh_frame(V3 n, V3& s, V3& t) {
+    const float sign = n.z >= 0.f ? 1.f : -1.f;
+    const float a = -1.f / (sign + n.z);
+    const float b = n.x * n.y * a;
+    s = V3{sign * n.x * n.x * a + 1.f, sign * b, -sign * n.x};
+    t = V3{n.y * s.z - n.z * s.y, n.z * s.x - n.x * s.z, n.x * s.y - n.y * s.x};
+}
+// warp::square_to_cosine_hemisphere through the concentric disk mapping.  S15
+SDFRT_HD V3 square_to_cosine_hemisphere(float u0, float u1) {
+    const float x = 2.f * u0 - 1.f, y = 2.f * u1 - 1.f;
+    const bool is_zero = (x == 0.f) & (y == 0.f);
+    const bool q13 = fabsf(x) < fabsf(y);
+    const float r = q13 ? y : x, rp = q13 ? x : y;
+    float phi = 0.25f * kPi * rp / (is_zero ? 1.f : r);
+    if (q13) phi = 0.5f * kPi - phi;
+    if (is_zero) phi = 0.f;
+    const float px = r * cosf(phi), py = r * sinf(phi);
+    return V3{px, py, sqrtf(fmaxf(0.f, 1.f - (px * px + py * py)))};
+}
+// mitsuba.ad.integrators.common.mis_weight (power heuristic, 0 where undefined)
+SDFRT_HD float mis_weight(float pdf_a, float pdf_b) {
+    const float a2 = pdf_a * pdf_a, den = a2 + pdf_b * pdf_b;
+    return den > 0.f ? a2 / den : 0.f;
+}
+// Interaction.offset_p (spawn_ray): p + n * mulsign((1 + max|p|) * RayEpsilon, n . d).  S6
+SDFRT_HD V3 spawn_offset(V3 p, V3 n, V3 d) {
+    const float mag = (1.f + fmaxf(fabsf(p.x), fmaxf(fabsf(p.y), fabsf(p.z)))) * kRayEpsilon;
+    return p + (mag * sign1(dot(n, d))) * n;
+}
+
+// BSDF sample of the MIS branch of sdf_direct_reparam (python/integrators/sdf_direct_reparam.py:87-94): cosine-hemisphere direction
+// in the shading frame of the detached interaction, ray spawned from the attached interaction with a detached direction.
+struct BsdfRay {
+    bool active;   // cos_i > 0 and pdf > 0
+    V3 o, d;
+    float pdf;     // cos / pi
+};
+SDFRT_HD BsdfRay make_bsdf_ray(V3 p, V3 n, float cos_i, float u0, float u1) {
+    BsdfRay r;
+    const V3 wo = square_to_cosine_hemisphere(u0, u1);
+    r.pdf = wo.z * (1.f / kPi);
+    r.active = (cos_i > 0.f) & (r.pdf > 0.f);
+    V3 fs, ft;
+    sh_frame(n, fs, ft);
+    r.d = fs * wo.x + ft * wo.y + n * wo.z;
+    r.o = spawn_offset(p, n, r.d);
+    return r;
+}
+// weights of the two strategies for the constant emitter (pdf 1 / 4 pi) and the diffuse BSDF (pdf cos / pi); both detached
+SDFRT_HD float mis_weight_nee(float cos_o) { return mis_weight(kInv4Pi, cos_o * (1.f / kPi)); }
+SDFRT_HD float mis_weight_bsdf(float pdf) { return mis_weight(pdf, kInv4Pi); }
+
 // ------------------------------------------------------------------------------------------------
 // forward lane
 // ------------------------------------------------------------------------------------------------
@@ -165,9 +225,10 @@ SDFRT_HD void lane_forward(const SceneParams& sc, const PassParams& ps, unsigned
     }
     const bool hit = isfinite(tr.its_t);
     V3 rgb = v3(0.f);
-    float s_state = 0.f;
-    TraceOut ts;
+    float s_state = 0.f, b_state = 0.f;
+    TraceOut ts, tb;
     ts.warp_t = INFINITY; ts.warp_t_d = v3(0.f); ts.warp_weight = 0.f; ts.warp_weight_d = v3(0.f);
+    tb = ts;
     if (sc.integrator == INTEGRATOR_SILHOUETTE) {
         rgb = v3(hit ? 1.f : 0.f);
     } else if (sc.integrator == INTEGRATOR_SIMPLE_SHADING) {
@@ -208,8 +269,33 @@ SDFRT_HD void lane_forward(const SceneParams& sc, const PassParams& ps, unsigned
                     s_state = 1.f;
                     const V3 rho = eval_albedo(sc.A, p, nullptr, nullptr);
                     st.n_albedo += (sc.A.data != nullptr);
-                    const float k = cos_o * 4.f;  // (rho / pi) * cos_o * Le / (1 / (4 pi))
+                    float k = cos_o * 4.f;  // (rho / pi) * cos_o * Le / (1 / (4 pi))
+                    if (sc.Sh.use_mis) k *= mis_weight_nee(cos_o);   // power heuristic against the detached BSDF pdf (:76-79)
                     rgb = V3{rho.x * k * sc.Sh.Le[0], rho.y * k * sc.Sh.Le[1], rho.z * k * sc.Sh.Le[2]};
+                }
+            }
+            if (sc.Sh.use_mis) {   // BSDF sampling (python/integrators/sdf_direct_reparam.py:87-107)
+                (void)pcg_next_f32(cs.rng);  // component sample
+                const float b0 = pcg_next_f32(cs.rng), b1 = pcg_next_f32(cs.rng);
+                const BsdfRay br = make_bsdf_ray(p, n, cos_i, b0, b1);
+                if (br.active) {
+                    float its_b;
+                    int nb = 0;
+                    if (DIFF && reparam_at_depth(sc.W, 1)) {
+                        trace_diff(sc.G, sc.T, br.o, br.d, INFINITY, false, tb, nh, nv);
+                        its_b = tb.its_t;
+                        nb = tb.n_steps;
+                    } else {
+                        its_b = trace_non_diff(sc.G, sc.T, br.o, br.d, INFINITY, false, nb, nv);
+                    }
+                    nsteps = nsteps > nb ? nsteps : nb;
+                    if (!isfinite(its_b)) {   // escaped: the environment emitter; bsdf_val / pdf = rho
+                        b_state = 1.f;
+                        const V3 rho = eval_albedo(sc.A, p, nullptr, nullptr);
+                        st.n_albedo += (sc.A.data != nullptr);
+                        const float wb = mis_weight_bsdf(br.pdf);
+                        rgb += V3{rho.x * wb * sc.Sh.Le[0], rho.y * wb * sc.Sh.Le[1], rho.z * wb * sc.Sh.Le[2]};
+                    }
                 }
             }
         }
@@ -231,6 +317,13 @@ SDFRT_HD void lane_forward(const SceneParams& sc, const PassParams& ps, unsigned
         r[REC_S_TAU_DX * rec_stride] = ts.warp_t_d.x; r[REC_S_TAU_DY * rec_stride] = ts.warp_t_d.y; r[REC_S_TAU_DZ * rec_stride] = ts.warp_t_d.z;
         r[REC_S_OMEGA * rec_stride] = ts.warp_weight;
         r[REC_S_OMEGA_DX * rec_stride] = ts.warp_weight_d.x; r[REC_S_OMEGA_DY * rec_stride] = ts.warp_weight_d.y; r[REC_S_OMEGA_DZ * rec_stride] = ts.warp_weight_d.z;
+        if (sc.Sh.use_mis && sc.integrator == INTEGRATOR_DIRECT) {
+            r[REC_B_STATE * rec_stride] = b_state;
+            r[REC_B_TAU * rec_stride] = tb.warp_t;
+            r[REC_B_TAU_DX * rec_stride] = tb.warp_t_d.x; r[REC_B_TAU_DY * rec_stride] = tb.warp_t_d.y; r[REC_B_TAU_DZ * rec_stride] = tb.warp_t_d.z;
+            r[REC_B_OMEGA * rec_stride] = tb.warp_weight;
+            r[REC_B_OMEGA_DX * rec_stride] = tb.warp_weight_d.x; r[REC_B_OMEGA_DY * rec_stride] = tb.warp_weight_d.y; r[REC_B_OMEGA_DZ * rec_stride] = tb.warp_weight_d.z;
+        }
     }
 
     // re-projection + splat (python/integrators/reparam.py:100-118; ImageBlock::put)
@@ -330,7 +423,7 @@ struct Site {
 };
 struct SiteList {
     int n;
-    Site s[4];  // shadow warp site, (decouple_reparam: detached-ray interaction), surface interaction, primary warp site
+    Site s[5];  // (use_mis: BSDF ray's warp site), shadow warp site, (decouple_reparam: detached-ray interaction), surface interaction, primary warp site
 };
 SDFRT_HD void push_site(SiteList& L, V3 x, float phi_hat, V3 g_hat) {
     L.s[L.n].x = x; L.s[L.n].phi_hat = phi_hat; L.s[L.n].g_hat = g_hat;
@@ -368,8 +461,11 @@ SDFRT_HD void lane_backward(const SceneParams& sc, const PassParams& ps, unsigne
     V3 rho = v3(0.f);
     V3 drho[3];
     AlbedoTaps taps;
-    bool nee = false;
-    float shade = 0.f;
+    bool nee = false, bsdf_hit_env = false;
+    float shade = 0.f, w_nee = 1.f, w_b = 0.f;
+    V3 rgb_b = v3(0.f);
+    BsdfRay br; br.active = false; br.o = v3(0.f); br.d = v3(0.f, 0.f, 1.f); br.pdf = 0.f;
+    const bool mis = sc.Sh.use_mis && sc.integrator == INTEGRATOR_DIRECT;
     if (hit && sc.integrator != INTEGRATOR_SILHOUETTE) {
         p = o + its_t * d0;
         float phi;
@@ -387,14 +483,28 @@ SDFRT_HD void lane_backward(const SceneParams& sc, const PassParams& ps, unsigne
     } else {
         if (!hit) {
             if (!sc.Sh.hide_emitters) rgb = V3{sc.Sh.Le[0], sc.Sh.Le[1], sc.Sh.Le[2]};
-        } else if (r[REC_S_STATE * rec_stride] != 0.f) {
-            nee = true;
-            const float u0 = pcg_next_f32(cs.rng), u1 = pcg_next_f32(cs.rng);
-            sr = make_shadow_ray(sc.Sh, p, n, u0, u1);
-            cos_o = dot(n, sr.d);
-            rho = eval_albedo(sc.A, p, &taps, drho);
-            const float k = cos_o * 4.f;
-            rgb = V3{rho.x * k * sc.Sh.Le[0], rho.y * k * sc.Sh.Le[1], rho.z * k * sc.Sh.Le[2]};
+        } else {
+            nee = r[REC_S_STATE * rec_stride] != 0.f;
+            bsdf_hit_env = mis && r[REC_B_STATE * rec_stride] != 0.f;
+            if (nee | bsdf_hit_env) {
+                const float u0 = pcg_next_f32(cs.rng), u1 = pcg_next_f32(cs.rng);
+                sr = make_shadow_ray(sc.Sh, p, n, u0, u1);
+                cos_o = dot(n, sr.d);
+                rho = eval_albedo(sc.A, p, &taps, drho);
+            }
+            if (nee) {
+                if (mis) w_nee = mis_weight_nee(cos_o);
+                const float k = cos_o * 4.f * w_nee;
+                rgb = V3{rho.x * k * sc.Sh.Le[0], rho.y * k * sc.Sh.Le[1], rho.z * k * sc.Sh.Le[2]};
+            }
+            if (bsdf_hit_env) {
+                (void)pcg_next_f32(cs.rng);
+                const float b0 = pcg_next_f32(cs.rng), b1 = pcg_next_f32(cs.rng);
+                br = make_bsdf_ray(p, n, -dot(n, d0), b0, b1);
+                w_b = mis_weight_bsdf(br.pdf);
+                rgb_b = V3{rho.x * w_b * sc.Sh.Le[0], rho.y * w_b * sc.Sh.Le[1], rho.z * w_b * sc.Sh.Le[2]};
+                rgb += rgb_b;
+            }
         }
     }
 
@@ -468,15 +578,16 @@ SDFRT_HD void lane_backward(const SceneParams& sc, const PassParams& ps, unsigne
         V3 n_hat = v3(0.f), p_hat = v3(0.f);
         if (sc.integrator == INTEGRATOR_SIMPLE_SHADING) {
             if (shade > 0.f) n_hat = v3((c_hat.x + c_hat.y + c_hat.z) * 0.57735026918962576f);
-        } else if (nee) {
-            // rgb_c = div * div_s * rho_c * cos_o * 4 Le_c
-            const V3 K = V3{4.f * sc.Sh.Le[0], 4.f * sc.Sh.Le[1], 4.f * sc.Sh.Le[2]};
+        } else if (nee | bsdf_hit_env) {
+            // rgb_c = div * (div_s * rho_c * cos_o * 4 Le_c * w_nee  +  div_b * rho_c * Le_c * w_b); the MIS weights are detached
+            const V3 K = nee ? V3{4.f * w_nee * sc.Sh.Le[0], 4.f * w_nee * sc.Sh.Le[1], 4.f * w_nee * sc.Sh.Le[2]} : v3(0.f);
             const float cos_hat = c_hat.x * rho.x * K.x + c_hat.y * rho.y * K.y + c_hat.z * rho.z * K.z;
             n_hat = cos_hat * sr.d;
             const V3 ds_hat = cos_hat * n;
-            const float div_s_hat = crgb;
-            // albedo
-            const V3 rho_hat = V3{c_hat.x * K.x * cos_o, c_hat.y * K.y * cos_o, c_hat.z * K.z * cos_o};
+            const float div_s_hat = crgb - dot(c_hat, rgb_b);   // the emitter-sampled part only
+            // albedo (both strategies)
+            const V3 rho_hat = V3{c_hat.x * (K.x * cos_o + w_b * sc.Sh.Le[0]), c_hat.y * (K.y * cos_o + w_b * sc.Sh.Le[1]),
+                                  c_hat.z * (K.z * cos_o + w_b * sc.Sh.Le[2])};
             if (sc.A.data != nullptr) {
                 st.n_albedo += 1;
                 p_hat += rho_hat.x * drho[0] + rho_hat.y * drho[1] + rho_hat.z * drho[2];
@@ -489,8 +600,29 @@ SDFRT_HD void lane_backward(const SceneParams& sc, const PassParams& ps, unsigne
                     }
                 }
             }
+            // BSDF-sampled ray's warp site: spawned from the attached interaction (si.spawn_ray, :93), direction detached -- only its
+            // divergence carries a derivative
+            if (bsdf_hit_env && reparam_at_depth(sc.W, 1)) {
+                const V3 tau_d = V3{r[REC_B_TAU_DX * rec_stride], r[REC_B_TAU_DY * rec_stride], r[REC_B_TAU_DZ * rec_stride]};
+                const V3 om_d = V3{r[REC_B_OMEGA_DX * rec_stride], r[REC_B_OMEGA_DY * rec_stride], r[REC_B_OMEGA_DZ * rec_stride]};
+                const float tau = r[REC_B_TAU * rec_stride];
+                const WarpSite ws = warp_site(sc.G, sc.W, sc.T, br.o, br.d, tau, tau_d, r[REC_B_OMEGA * rec_stride], om_d);
+                st.n_hess += isfinite(tau);
+                if (ws.active) {
+                    const float div_b_hat = dot(c_hat, rgb_b);
+                    const float phi_hat = div_b_hat * ws.cphi_div;
+                    const V3 g_hat = div_b_hat * ws.cg_div;
+                    if (isfinite(phi_hat) & isfinite(g_hat.x + g_hat.y + g_hat.z)) {
+                        push_site(sites, br.o + tau * br.d, phi_hat, g_hat);
+                        st.n_sites += 1;
+                        const V3 ob_hat = phi_hat * ws.g + mul(ws.H, g_hat);
+                        grad_p = grad_p - ob_hat;
+                        p_hat += ob_hat;
+                    }
+                }
+            }
             // shadow-ray warp site (attached through its origin o_s = p + const)
-            if (reparam_at_depth(sc.W, 1)) {
+            if (nee && reparam_at_depth(sc.W, 1)) {
                 const V3 tau_d = V3{r[REC_S_TAU_DX * rec_stride], r[REC_S_TAU_DY * rec_stride], r[REC_S_TAU_DZ * rec_stride]};
                 const V3 om_d = V3{r[REC_S_OMEGA_DX * rec_stride], r[REC_S_OMEGA_DY * rec_stride], r[REC_S_OMEGA_DZ * rec_stride]};
                 const float tau = r[REC_S_TAU * rec_stride];

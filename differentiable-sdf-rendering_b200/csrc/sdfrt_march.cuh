@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(256) k_gen_primary(const __grid_constant__ Sce
 // ---------------------------------------------------------------------------------------------------------------
 // film splat (ImageBlock::put, oracle/ref_semantics.md S4)
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void splat(const SensorParams& S, float* film, float pfx, float pfy, V3 rgb) {
+__device__ __forceinline__ void splat(const SensorParams& S, float* film, float pfx, float pfy, V3 rgb, float wgt = 1.f) {
     const int Wb = S.W + 2 * S.border, Hb = S.H + 2 * S.border;
     const float rad = S.filter_radius;
     const int x0 = (int)ceilf(pfx - rad), y0 = (int)ceilf(pfy - rad);
@@ -185,7 +185,7 @@ __device__ __forceinline__ void splat(const SensorParams& S, float* film, float 
             if (rgb.x != 0.f) atomicAdd(px + 0, rgb.x * w);
             if (rgb.y != 0.f) atomicAdd(px + 1, rgb.y * w);
             if (rgb.z != 0.f) atomicAdd(px + 2, rgb.z * w);
-            atomicAdd(px + 3, w);
+            if (wgt != 0.f) atomicAdd(px + 3, w * wgt);
         }
     }
 }
@@ -200,7 +200,9 @@ struct SplatSmem {
     float fy[32][16];
     float4 c[32];
 };
-__device__ __forceinline__ void warp_splat(const SensorParams& S, float* film, SplatSmem& sm, bool active, float pfx, float pfy, V3 rgb) {
+// `wgt`: what the sample adds to the weight channel (1; 0 for the second partial splat of a sample that is splatted in two parts)
+__device__ __forceinline__ void warp_splat(const SensorParams& S, float* film, SplatSmem& sm, bool active, float pfx, float pfy, V3 rgb,
+                                           float wgt = 1.f) {
     const unsigned FULL = 0xffffffffu;
     const int lane_id = threadIdx.x & 31;
     const float rad = S.filter_radius;
@@ -218,7 +220,7 @@ __device__ __forceinline__ void warp_splat(const SensorParams& S, float* film, S
     if (wx1 < wx0) return;  // no active lane
     const int Wx = wx1 - wx0 + 1, Wy = wy1 - wy0 + 1;
     if (Wx > 8 || Wy > 16) {
-        if (active) splat(S, film, pfx, pfy, rgb);
+        if (active) splat(S, film, pfx, pfy, rgb, wgt);
         return;
     }
 #pragma unroll
@@ -230,7 +232,7 @@ __device__ __forceinline__ void warp_splat(const SensorParams& S, float* film, S
         const int by = wy0 + i;
         sm.fy[lane_id][i] = (active && by >= y0 && by <= y1) ? filter_eval(S, (float)by - pfy) : 0.f;
     }
-    sm.c[lane_id] = make_float4(rgb.x, rgb.y, rgb.z, active ? 1.f : 0.f);
+    sm.c[lane_id] = make_float4(rgb.x, rgb.y, rgb.z, active ? wgt : 0.f);
     __syncwarp();
     const int Wb = S.W + 2 * S.border, Hb = S.H + 2 * S.border;
     for (int cell = lane_id; cell < Wx * Wy; cell += 32) {
@@ -243,12 +245,12 @@ __device__ __forceinline__ void warp_splat(const SensorParams& S, float* film, S
             acc.x += w * c.x; acc.y += w * c.y; acc.z += w * c.z; acc.w += w * c.w;
         }
         const int bx = wx0 + cx, by = wy0 + cy;
-        if (bx >= 0 && bx < Wb && by >= 0 && by < Hb && acc.w != 0.f) {
+        if (bx >= 0 && bx < Wb && by >= 0 && by < Hb) {
             float* px = film + ((size_t)by * Wb + bx) * 4;
             if (acc.x != 0.f) atomicAdd(px + 0, acc.x);
             if (acc.y != 0.f) atomicAdd(px + 1, acc.y);
             if (acc.z != 0.f) atomicAdd(px + 2, acc.z);
-            atomicAdd(px + 3, acc.w);
+            if (acc.w != 0.f) atomicAdd(px + 3, acc.w);
         }
     }
     __syncwarp();
@@ -582,13 +584,16 @@ struct ShadowQueue {
 template <bool DIFF>
 __global__ void __launch_bounds__(256, 3) k_shade(const __grid_constant__ SceneParams sc, const __grid_constant__ PassParams ps,
                                                 unsigned long long item0, unsigned n, unsigned region, const SegIn* __restrict__ psegs,
-                                                const float* __restrict__ its, ShadowQueue q, float* __restrict__ film, float* __restrict__ rec_state,
+                                                const float* __restrict__ its, ShadowQueue q, ShadowQueue qb /* use_mis: BSDF-sampled rays */,
+                                                float* __restrict__ film, float* __restrict__ rec_state, float* __restrict__ rec_bstate,
                                                 Counters* __restrict__ counters) {
     __shared__ SplatSmem s_splat[8];
-    __shared__ unsigned s_count;
+    __shared__ unsigned s_count, s_count_b;
     __shared__ int s_lo[3], s_hi[3];   // block bases of the shadow origins (for the marcher's SMEM box)
+    const bool mis = sc.Sh.use_mis && sc.integrator == INTEGRATOR_DIRECT;
     if (threadIdx.x == 0) {
         s_count = 0;
+        s_count_b = 0;
         for (int a = 0; a < 3; ++a) { s_lo[a] = 0x7fffffff; s_hi[a] = -0x7fffffff; }
     }
     __syncthreads();
@@ -601,9 +606,9 @@ __global__ void __launch_bounds__(256, 3) k_shade(const __grid_constant__ SceneP
         const unsigned i = region_base + it * 256u + threadIdx.x;
         if (region_base + it * 256u >= n) break;  // block-uniform
         const bool live = i < n;
-        bool push = false;
-        SegIn sseg;
-        float4 info = make_float4(0.f, 0.f, 0.f, 0.f);
+        bool push = false, push_b = false;
+        SegIn sseg, bseg;
+        float4 info = make_float4(0.f, 0.f, 0.f, 0.f), info_b = make_float4(0.f, 0.f, 0.f, 0.f);
         float pfx = 0.f, pfy = 0.f;
         V3 rgb = v3(0.f);
         if (live) {
@@ -640,21 +645,50 @@ __global__ void __launch_bounds__(256, 3) k_shade(const __grid_constant__ SceneP
                     if ((cos_i > 0.f) & (cos_o > 0.f)) {
                         const V3 rho = eval_albedo(sc.A, p, nullptr, nullptr);
                         n_alb += (sc.A.data != nullptr);
-                        const float k = cos_o * 4.f;  // (rho / pi) cos_o Le / (1 / 4 pi)
+                        float k = cos_o * 4.f;  // (rho / pi) cos_o Le / (1 / 4 pi)
+                        if (mis) k *= mis_weight_nee(cos_o);
                         info = make_float4(rho.x * k * sc.Sh.Le[0], rho.y * k * sc.Sh.Le[1], rho.z * k * sc.Sh.Le[2], __uint_as_float(i));
                         sseg = make_seg(sc.T, sr.o, sr.d, sr.maxt);
                         push = true;
-                        if (q.box != nullptr) {
+                        if (q.box != nullptr) {   // (boxes are staged for the emitter-sampled rays only)
                             const CellCoord cc = cell_coord(sc.G, sr.o);
                             my_lo[0] = min(my_lo[0], cc.ix); my_lo[1] = min(my_lo[1], cc.iy); my_lo[2] = min(my_lo[2], cc.iz);
                             my_hi[0] = max(my_hi[0], cc.ix); my_hi[1] = max(my_hi[1], cc.iy); my_hi[2] = max(my_hi[2], cc.iz);
                         }
                     }
+                    if (mis) {   // BSDF sampling (python/integrators/sdf_direct_reparam.py:87-107): escaped rays see the emitter
+                        (void)pcg_next_u32(rng);
+                        const float b0 = pcg_next_f32(rng), b1 = pcg_next_f32(rng);
+                        const BsdfRay br = make_bsdf_ray(p, nrm, cos_i, b0, b1);
+                        if (br.active) {
+                            const V3 rho = eval_albedo(sc.A, p, nullptr, nullptr);
+                            n_alb += (sc.A.data != nullptr);
+                            const float wb = mis_weight_bsdf(br.pdf);
+                            // bit 31 of the item word: the sample's weight channel is splatted with its emitter-sampled part
+                            info_b = make_float4(rho.x * wb * sc.Sh.Le[0], rho.y * wb * sc.Sh.Le[1], rho.z * wb * sc.Sh.Le[2],
+                                                 __uint_as_float(i | (push ? 0x80000000u : 0u)));
+                            bseg = make_seg(sc.T, br.o, br.d, INFINITY);
+                            push_b = true;
+                        }
+                    }
                 }
             }
-            if (DIFF) rec_state[i] = 0.f;
+            if (DIFF) { rec_state[i] = 0.f; if (mis) rec_bstate[i] = 0.f; }
         }
-        warp_splat(sc.S, film, s_splat[threadIdx.x >> 5], live && !push, pfx, pfy, rgb);
+        warp_splat(sc.S, film, s_splat[threadIdx.x >> 5], live && !push && !push_b, pfx, pfy, rgb);
+        if (mis) {
+            const unsigned mb = __ballot_sync(FULL, push_b);
+            if (mb) {
+                unsigned base = 0;
+                if (lane_id == (__ffs(mb) - 1)) base = atomicAdd(&s_count_b, (unsigned)__popc(mb));
+                base = __shfl_sync(FULL, base, __ffs(mb) - 1);
+                if (push_b) {
+                    const unsigned slot = region_base + base + (unsigned)__popc(mb & ((1u << lane_id) - 1u));
+                    qb.segs[slot] = bseg;
+                    qb.info[slot] = info_b;
+                }
+            }
+        }
         const unsigned m = __ballot_sync(FULL, push);
         if (m) {
             unsigned base = 0;
@@ -679,6 +713,7 @@ __global__ void __launch_bounds__(256, 3) k_shade(const __grid_constant__ SceneP
     __syncthreads();
     if (threadIdx.x == 0) {
         q.count[blockIdx.x] = s_count;
+        if (mis) qb.count[blockIdx.x] = s_count_b;
         if (q.box != nullptr) {   // box of kBoxBase^3 block bases centred on the origin patch, kept inside the grid
             int4 b = make_int4(0, 0, 0, 0);
             if (s_count > 0u) {
@@ -710,7 +745,9 @@ __global__ void __launch_bounds__(256, 3) k_shade(const __grid_constant__ SceneP
 }
 
 // one block per region: visibility -> splat; DIFF: scatter the shadow tracer record to the lane records
-template <bool DIFF>
+// BQ: the queue of BSDF-sampled rays (use_mis): escaped = contribution, records go to the REC_B_* rows, and the weight channel is
+// only added for samples that have no emitter-sampled part (bit 31 of the item word)
+template <bool DIFF, bool BQ = false>
 __global__ void __launch_bounds__(256) k_shadow_splat(const __grid_constant__ SceneParams sc, const __grid_constant__ PassParams ps,
                                                        unsigned long long item0, unsigned region, const SegIn* __restrict__ psegs,
                                                        const unsigned* __restrict__ region_count, const float4* __restrict__ info, const float* __restrict__ s_its,
@@ -723,12 +760,14 @@ __global__ void __launch_bounds__(256) k_shadow_splat(const __grid_constant__ Sc
     for (unsigned j0 = 0; j0 < cnt; j0 += 256u) {
         const unsigned j = j0 + threadIdx.x;
         const bool live = j < cnt;
-        float pfx = 0.f, pfy = 0.f;
+        float pfx = 0.f, pfy = 0.f, wgt = 1.f;
         V3 rgb = v3(0.f);
         if (live) {
             const unsigned slot = region_base + j;
             const float4 inf = info[slot];
-            const unsigned i = __float_as_uint(inf.w);
+            const unsigned iw = __float_as_uint(inf.w);
+            const unsigned i = BQ ? (iw & 0x7fffffffu) : iw;
+            if (BQ && (iw & 0x80000000u)) wgt = 0.f;
             const float its_s = s_its[slot];  // its_t of the shadow segment (value tracer's output, or row 0 of the DIFF records)
             const bool occluded = isfinite(its_s);
             const float4 sb = __ldg(&psegs[i].b);
@@ -736,12 +775,12 @@ __global__ void __launch_bounds__(256) k_shadow_splat(const __grid_constant__ Sc
             if (!occluded) rgb = V3{inf.x, inf.y, inf.z};
             if (DIFF && !occluded) {
                 float* d = rec + i;
-                d[REC_S_STATE * rec_stride] = 1.f;
+                d[(BQ ? REC_B_STATE : REC_S_STATE) * rec_stride] = 1.f;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) d[(REC_S_TAU + k) * rec_stride] = srec[(1 + k) * srec_stride + slot];
+                for (int k = 0; k < 8; ++k) d[((BQ ? REC_B_TAU : REC_S_TAU) + k) * rec_stride] = srec[(1 + k) * srec_stride + slot];
             }
         }
-        warp_splat(sc.S, film, s_splat[threadIdx.x >> 5], live, pfx, pfy, rgb);
+        warp_splat(sc.S, film, s_splat[threadIdx.x >> 5], live, pfx, pfy, rgb, wgt);
     }
 }
 

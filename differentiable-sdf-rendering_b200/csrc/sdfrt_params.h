@@ -138,6 +138,7 @@ inline ShadingParams make_shading(const sdfrt_shading& s) {
     o.env_dist = s.env_dist;
     o.hide_emitters = s.hide_emitters;
     o.shadow_origin = 0;
+    o.use_mis = 0;
     return o;
 }
 inline PassParams make_pass(const SensorParams& S, uint32_t seed, int spp, int rank, int world, int antithetic = 0) {

@@ -24,7 +24,6 @@
 
 namespace sdfrt {
 
-constexpr float kInv4Pi = 0.07957747154594767f;
 
 // The path walker marches up to three kinds of segment per vertex and evaluates up to three warp sites.  Inlining every
 // call site made k_prb_backward instruction-fetch bound (ncu: `no_instruction` 5.6 stall cycles per issued instruction, 255
@@ -80,38 +79,6 @@ SDFRT_HD_NOINLINE void prb_scatter_site(float* grad, const GridView& G, V3 x, fl
 }
 SDFRT_HD_NOINLINE WarpSite prb_warp_site(const GridView& G, const WarpParams& W, const TracerParams& T, V3 o, V3 d0, const TraceOut& tr) {
     return warp_site(G, W, T, o, d0, tr.warp_t, tr.warp_t_d, tr.warp_weight, tr.warp_weight_d);
-}
-
-// mitsuba `coordinate_system` (Duff et al. 2017) -- the frame initialize_sh_frame builds when dp_du == 0
-// (python/shapes.py:360); s = first vector, t = cross(n, s).  oracle/ref_semantics.md S14
-SDFRT_HD void sh_frame(V3 n, V3& s, V3& t) {
-    const float sign = n.z >= 0.f ? 1.f : -1.f;
-    const float a = -1.f / (sign + n.z);
-    const float b = n.x * n.y * a;
-    s = V3{sign * n.x * n.x * a + 1.f, sign * b, -sign * n.x};
-    t = V3{n.y * s.z - n.z * s.y, n.z * s.x - n.x * s.z, n.x * s.y - n.y * s.x};
-}
-// warp::square_to_cosine_hemisphere through the concentric disk mapping.  S15
-SDFRT_HD V3 square_to_cosine_hemisphere(float u0, float u1) {
-    const float x = 2.f * u0 - 1.f, y = 2.f * u1 - 1.f;
-    const bool is_zero = (x == 0.f) & (y == 0.f);
-    const bool q13 = fabsf(x) < fabsf(y);
-    const float r = q13 ? y : x, rp = q13 ? x : y;
-    float phi = 0.25f * kPi * rp / (is_zero ? 1.f : r);
-    if (q13) phi = 0.5f * kPi - phi;
-    if (is_zero) phi = 0.f;
-    const float px = r * cosf(phi), py = r * sinf(phi);
-    return V3{px, py, sqrtf(fmaxf(0.f, 1.f - (px * px + py * py)))};
-}
-// mitsuba.ad.integrators.common.mis_weight (power heuristic, 0 where undefined)
-SDFRT_HD float mis_weight(float pdf_a, float pdf_b) {
-    const float a2 = pdf_a * pdf_a, den = a2 + pdf_b * pdf_b;
-    return den > 0.f ? a2 / den : 0.f;
-}
-// Interaction.offset_p (spawn_ray): p + n * mulsign((1 + max|p|) * RayEpsilon, n . d).  S6
-SDFRT_HD V3 spawn_offset(V3 p, V3 n, V3 d) {
-    const float mag = (1.f + fmaxf(fabsf(p.x), fmaxf(fabsf(p.y), fabsf(p.z)))) * kRayEpsilon;
-    return p + (mag * sign1(dot(n, d))) * n;
 }
 
 // adjoint of the film splat of one sample whose splatted value is `rgb` with weight channel 1:

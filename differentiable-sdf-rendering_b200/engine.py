@@ -120,6 +120,9 @@ class Context:
     def set_antithetic(self, enable):
         check(self.ctx, self.lib.sdfrt_set_antithetic(self.ctx, int(bool(enable))))
 
+    def set_use_mis(self, enable):
+        check(self.ctx, self.lib.sdfrt_set_use_mis(self.ctx, int(bool(enable))))
+
     def set_shadow_origin(self, mode):
         check(self.ctx, self.lib.sdfrt_set_shadow_origin(self.ctx, int(mode)))
 

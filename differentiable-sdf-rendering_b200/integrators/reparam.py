@@ -22,9 +22,7 @@ class ReparamIntegrator:
         self.max_depth = props.get('max_depth', 4)
         self.weight_by_spp = props.get('weight_by_spp', False)
         assert not self.weight_by_spp, "Not supported"  # python/integrators/reparam.py:16
-        self.use_mis = props.get('use_mis', False)
-        if self.use_mis:
-            raise NotImplementedError("the BSDF-sampling MIS branch (sdf_direct_reparam.py:87-107) is not on the hot path")
+        self.use_mis = props.get('use_mis', False)   # python/integrators/reparam.py:17; used by sdf_direct_reparam (:76-79,87-107)
         self.antithetic_sampling = props.get('antithetic_sampling', False)   # python/integrators/reparam.py:19,167-178
         self.use_aovs = props.get('use_aovs', False)
         self.hide_emitters = props.get('hide_emitters', False)
@@ -63,6 +61,7 @@ class ReparamIntegrator:
         ctx.set_albedo(scene.albedo_grid)
         ctx.set_integrator(self.integrator_name)
         ctx.set_antithetic(self.antithetic_sampling)
+        ctx.set_use_mis(self.use_mis and self.integrator_name == 'sdf_direct_reparam')
         ctx.set_warp(**warp_params_of(self.warp_field))
         ctx.set_tracer(**self.sdf.tracer_params())
         return ctx

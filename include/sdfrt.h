@@ -143,6 +143,11 @@ int sdfrt_set_antithetic(sdfrt_ctx* ctx, int enable);
 /* props `detach_indirect_si` / `decouple_reparam` of sdf_direct_reparam (python/integrators/sdf_direct_reparam.py:13-14,44-49): the
  * interaction the shadow ray is spawned from -- 0 = si (default), 1 = detach(si), 2 = si_d0 (interaction of the detached primary ray) */
 int sdfrt_set_shadow_origin(sdfrt_ctx* ctx, int mode);
+/* prop `use_mis` of ReparamIntegrator (python/integrators/reparam.py:17) as sdf_direct_reparam uses it
+ * (python/integrators/sdf_direct_reparam.py:76-79,87-107): the emitter sample is weighted by the power heuristic against the BSDF's pdf
+ * and a second, BSDF-sampled (cosine-hemisphere) ray is traced from every hit; rays that escape see the environment emitter.  Its warp
+ * record (reparameterised like the shadow ray, depth 1) goes to nine more rows of the lane records.  Default off (the reference's). */
+int sdfrt_set_use_mis(sdfrt_ctx* ctx, int enable);
 void sdfrt_prb_defaults(sdfrt_prb_params* p);
 int sdfrt_set_prb(sdfrt_ctx* ctx, const sdfrt_prb_params* p);      /* used when the integrator is SDFRT_INTEGRATOR_PRB */
 /* multi-GPU ray partition: the film rows (border included) are cut into bands of 8 rows; this context renders the

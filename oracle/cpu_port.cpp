@@ -116,7 +116,7 @@ int cp_time_sample(const cp_scene* h, unsigned seed, int spp_primal, int spp_adj
     PassParams pa = make_pass(sc.S, seed + 13, spp_adjoint, 0, 1);
     const long long la = 0;   // records are indexed by the sample index k
     const PassParams& sub = pa;
-    std::vector<float> rec((size_t)REC_COUNT * (size_t)n_adjoint, 0.f);
+    std::vector<float> rec((size_t)REC_COUNT_MIS * (size_t)n_adjoint, 0.f);
     std::fill(film.begin(), film.end(), 0.f);
 #pragma omp parallel for schedule(dynamic, 64) reduction(+ : nv, nh, nhit)
     for (long long k = 0; k < n_adjoint; ++k) {

@@ -23,6 +23,7 @@ struct hh_scene {
     int has_transform;   // Grid3d(data, transform): row-major 4x4 to_world
     float to_world[16];
     int shadow_origin;   // sdf_direct_reparam: 0 si, 1 detach_indirect_si, 2 decouple_reparam
+    int use_mis;         // ReparamIntegrator prop use_mis (sdf_direct_reparam's BSDF-sampling branch)
 };
 
 static SceneParams build(const hh_scene* h) {
@@ -37,6 +38,7 @@ static SceneParams build(const hh_scene* h) {
     sc.S = make_sensor(h->sensor);
     sc.Sh = make_shading(h->shading);
     sc.Sh.shadow_origin = h->shadow_origin;
+    sc.Sh.use_mis = h->use_mis;
     sc.integrator = h->integrator;
     sc.prb = make_prb(h->prb);
     set_grid_transform(sc.G, sc.T, h->has_transform ? h->to_world : nullptr);
@@ -326,7 +328,7 @@ int hh_prb_wf_backward(const hh_scene* h, unsigned seed, int spp, const float* f
     return 0;
 }
 
-int hh_rec_count() { return REC_COUNT; }
+int hh_rec_count() { return REC_COUNT_MIS; }
 unsigned long long hh_local_lanes(const hh_scene* h, int spp, int rank, int world) {
     SensorParams S = make_sensor(h->sensor);
     PassParams ps = make_pass(S, 0, spp, rank, world, h->antithetic);

@@ -46,7 +46,7 @@ class HHScene(C.Structure):
                 ('albedo', C.c_void_p), ('ax', C.c_int), ('ay', C.c_int), ('az', C.c_int),
                 ('tracer', TracerParams), ('warp', WarpParams), ('sensor', SensorParams), ('shading', ShadingParams),
                 ('integrator', C.c_int), ('prb', PrbParams), ('antithetic', C.c_int), ('has_transform', C.c_int),
-                ('to_world', C.c_float * 16), ('shadow_origin', C.c_int)]
+                ('to_world', C.c_float * 16), ('shadow_origin', C.c_int), ('use_mis', C.c_int)]
 
 
 def build():

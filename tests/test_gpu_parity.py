@@ -498,3 +498,37 @@ def test_marcher_variants_give_the_same_films_and_gradients(sdfrt_mod, env):
         assert st1['n_box_loads'] > 0.05 * st1['n_tap_loads'], st1
     else:
         assert st1['n_box_loads'] == 0
+
+
+@pytest.mark.parametrize('kind,albedo_res', [('sphere', None), ('knot', 8)])
+def test_use_mis_against_oracle(sdfrt_mod, kind, albedo_res):
+    """`use_mis=True` (python/integrators/reparam.py:17; sdf_direct_reparam.py:76-79,87-107) through the wavefront pipeline: second
+    region-compacted queue of BSDF-sampled rays, the weight channel splatted once per sample, nine more record rows."""
+    from oracle import sdf_oracle as O
+    sdfrt = sdfrt_mod
+    W, spp = 20, 4
+    osc = O.make_scene(kind, res=32, width=W, height=W, albedo_grid_res=albedo_res)
+    osc.use_mis = True
+    owf = O.WarpField2D(osc.sdf, weight_strategy=6, edge_eps=0.01)
+    owf.clamping_thresh = 0.05
+    sdf = sdfrt.Grid3d(osc.sdf.data.float().numpy(), device=0)
+    integ = sdfrt.integrators.create('sdf_direct_reparam', {'use_mis': True}, sdf)
+    wf = sdfrt.WarpField2D(sdf, weight_strategy=6, edge_eps=0.01)
+    wf.clamping_thresh = 0.05
+    integ.warp_field = wf
+    alb = None if albedo_res is None else osc.albedo_grid.float().cuda().contiguous().requires_grad_(True)
+    scene = sdfrt.Scene(integ, [sdfrt.Sensor(osc.sensor.to_world, W, W)], albedo_grid=alb)
+    g_in = np.random.default_rng(7).uniform(-1, 1, size=(W, W, 3))
+    img_o, g_o, _, ga_o = O.render_backward(osc, owf, 'sdf_direct_reparam', torch.from_numpy(g_in), seed=11, spp=spp)
+    with torch.no_grad():
+        img_p = O.render(osc, owf, 'sdf_direct_reparam', seed=5, spp=spp)
+    sdf.data.requires_grad_(True)
+    img = sdfrt.render(scene, sensor=0, seed=5, spp=spp, seed_grad=11, spp_grad=spp)
+    assert (img.detach().cpu().double() - img_p).abs().max() < 2e-5
+    (img * torch.from_numpy(g_in).float().cuda()).sum().backward()
+    img_adj = sdf.ctx.develop(integ.last_film).cpu().double()
+    assert (img_adj - img_o).abs().max() < 2e-5
+    gs = sdf.data.grad[..., 0].cpu().double()
+    assert (gs - g_o).abs().max() < 2e-2 * g_o.abs().max() and (gs - g_o).norm() < 5e-3 * g_o.norm()
+    if alb is not None:
+        assert (alb.grad.cpu().double() - ga_o).abs().max() < 1e-3 * ga_o.abs().max()
