@@ -368,6 +368,9 @@ struct sdfrt_ctx {
         size_t film_adj_capacity = 0;
         float* prb_rec = nullptr;     // sdf_prb_reparam, DIFF sweep: per-vertex march records [max_depth * 18][n_items]
         size_t prb_rec_n = 0;
+        float *flag_segs = nullptr, *flag_dest = nullptr;   // deferred differentiable march: segments + record offsets, and
+        size_t flag_segs_n = 0, flag_dest_n = 0;           // [0] their count, [1] the marcher's region counter
+        unsigned* flag_count = nullptr;
         float *brick_a = nullptr, *brick_b = nullptr, *pix_mask = nullptr;  // dilated brick minima (ping-pong) + per-pixel masks
         size_t brick_a_n = 0, brick_b_n = 0, pix_mask_n = 0;
     } view[kViewSlots];
@@ -396,6 +399,7 @@ struct sdfrt_ctx {
     float* brick_raw = nullptr;   // per-brick SDF minima (undilated; rebuilt when the grid changes)
     size_t brick_raw_n = 0;
     bool skip_empty = true;
+    bool defer_diff = true;     // deferred differentiable march of the shadow segments (SDFRT_DEFER=0: march them differentiably per batch)
     int min_live = kMinActive;  // slots that must be stepping for a warp to stay in the stepping loop
     int max_slots = 4;
     unsigned long long batch_target = 0;  // camera samples per batch; 0 = n / 6 clamped to [2^20, 2^24] (measured best at c3)
@@ -524,49 +528,56 @@ int encode_grid_tmap(sdfrt_ctx* ctx) {
     return SDFRT_OK;
 }
 
+struct MarchExtra {   // optional arguments of a k_march launch
+    const int4* region_box = nullptr;     // SMEM box staging (shadow segments)
+    bool approach = false;                // value marcher: report misses whose |phi| stopped growing as -inf
+    const unsigned* dest = nullptr;       // DIFF: record offset per segment
+    const unsigned* n_slots_dev = nullptr;
+};
+
 template <bool DIFF, int CACHE>
 void launch_march(sdfrt_ctx* ctx, unsigned grid, cudaStream_t st, const SegIn* segs, const unsigned* region_fill, unsigned n_slots, unsigned region,
                   int do_refine, float* out_its, float* rec_out, unsigned long long rec_stride, unsigned* region_counter,
-                  const int4* region_box = nullptr) {
+                  const MarchExtra& ex = MarchExtra()) {
     GridView G = ctx->sc.G;
     const int role = ctx->march_role;
     const bool use8 = ctx->rows8_on && (ctx->rows8_roles >> role & 1);
     const bool use4 = !use8 && ctx->rows4_on && ((ctx->rows4_roles < 0 ? 15 : ctx->rows4_roles) >> role & 1);
     G.rows4 = use4 ? ctx->rows4 : nullptr;
     G.rows8 = use8 ? ctx->rows8 : nullptr;
-    if (region_box != nullptr && CACHE != 2) {   // shadow segments with a staged SMEM box per region (TMA)
+#define SDFRT_MARCH_ARGS G, ctx->sc.T, segs, region_fill, n_slots, region, do_refine, ctx->min_live, out_its, rec_out, rec_stride, region_counter, ctx->counters, ctx->tmap
+    if (ex.region_box != nullptr && CACHE != 2) {   // shadow segments with a staged SMEM box per region (TMA)
         const size_t smem = sizeof(BoxShared) + 128;
-        if (use8)
-            k_march<DIFF, CACHE, 8, true><<<grid, kMarchBlock, smem, st>>>(G, ctx->sc.T, segs, region_fill, n_slots, region, do_refine, ctx->min_live, out_its,
-                                                                         rec_out, rec_stride, region_counter, ctx->counters, ctx->tmap, region_box);
-        else
-            k_march<DIFF, CACHE, 4, true><<<grid, kMarchBlock, smem, st>>>(G, ctx->sc.T, segs, region_fill, n_slots, region, do_refine, ctx->min_live, out_its,
-                                                                         rec_out, rec_stride, region_counter, ctx->counters, ctx->tmap, region_box);
+        if (use8) k_march<DIFF, CACHE, 8, true><<<grid, kMarchBlock, smem, st>>>(SDFRT_MARCH_ARGS, ex.region_box, ex.dest, ex.n_slots_dev);
+        else k_march<DIFF, CACHE, 4, true><<<grid, kMarchBlock, smem, st>>>(SDFRT_MARCH_ARGS, ex.region_box, ex.dest, ex.n_slots_dev);
         return;
     }
-    if (use8)
-        k_march<DIFF, CACHE, 8><<<grid, kMarchBlock, 0, st>>>(G, ctx->sc.T, segs, region_fill, n_slots, region, do_refine, ctx->min_live, out_its, rec_out,
-                                                              rec_stride, region_counter, ctx->counters, ctx->tmap, nullptr);
-    else if (use4)
-        k_march<DIFF, CACHE, 4><<<grid, kMarchBlock, 0, st>>>(G, ctx->sc.T, segs, region_fill, n_slots, region, do_refine, ctx->min_live, out_its, rec_out,
-                                                              rec_stride, region_counter, ctx->counters, ctx->tmap, nullptr);
-    else
-        k_march<DIFF, CACHE, 0><<<grid, kMarchBlock, 0, st>>>(G, ctx->sc.T, segs, region_fill, n_slots, region, do_refine, ctx->min_live, out_its, rec_out,
-                                                              rec_stride, region_counter, ctx->counters, ctx->tmap, nullptr);
+    if constexpr (!DIFF && CACHE == 1) {
+        if (ex.approach) {   // (only the register-cached value marcher is instantiated with APPROACH: the shadow role's mode)
+            if (use8) k_march<false, 1, 8, false, true><<<grid, kMarchBlock, 0, st>>>(SDFRT_MARCH_ARGS, nullptr, ex.dest, ex.n_slots_dev);
+            else if (use4) k_march<false, 1, 4, false, true><<<grid, kMarchBlock, 0, st>>>(SDFRT_MARCH_ARGS, nullptr, ex.dest, ex.n_slots_dev);
+            else k_march<false, 1, 0, false, true><<<grid, kMarchBlock, 0, st>>>(SDFRT_MARCH_ARGS, nullptr, ex.dest, ex.n_slots_dev);
+            return;
+        }
+    }
+    if (use8) k_march<DIFF, CACHE, 8><<<grid, kMarchBlock, 0, st>>>(SDFRT_MARCH_ARGS, nullptr, ex.dest, ex.n_slots_dev);
+    else if (use4) k_march<DIFF, CACHE, 4><<<grid, kMarchBlock, 0, st>>>(SDFRT_MARCH_ARGS, nullptr, ex.dest, ex.n_slots_dev);
+    else k_march<DIFF, CACHE, 0><<<grid, kMarchBlock, 0, st>>>(SDFRT_MARCH_ARGS, nullptr, ex.dest, ex.n_slots_dev);
+#undef SDFRT_MARCH_ARGS
 }
 template <bool DIFF>
 void launch_march_mode(sdfrt_ctx* ctx, int role /* index into cache_mode */, unsigned need, cudaStream_t st, const SegIn* segs, const unsigned* region_fill,
                        unsigned n_slots, unsigned region, int do_refine, float* out_its, float* rec_out, unsigned long long rec_stride,
-                       unsigned* region_counter, const int4* region_box = nullptr) {
+                       unsigned* region_counter, const MarchExtra& ex = MarchExtra()) {
     const int mode = ctx->cache_mode[role];
     ctx->march_role = role;
     int bps = ctx->march_blocks[(DIFF ? 3 : 0) + mode];
-    if (region_box != nullptr && mode != 2) bps = std::min(bps, 3);   // 58 KB of shared memory per block
+    if (ex.region_box != nullptr && mode != 2) bps = std::min(bps, 3);   // 58 KB of shared memory per block
     unsigned grid = (unsigned)ctx->num_sms * (unsigned)bps;
     if (grid > need) grid = need;
-    if (mode == 0) launch_march<DIFF, 0>(ctx, grid, st, segs, region_fill, n_slots, region, do_refine, out_its, rec_out, rec_stride, region_counter, region_box);
-    else if (mode == 1) launch_march<DIFF, 1>(ctx, grid, st, segs, region_fill, n_slots, region, do_refine, out_its, rec_out, rec_stride, region_counter, region_box);
-    else launch_march<DIFF, 2>(ctx, grid, st, segs, region_fill, n_slots, region, do_refine, out_its, rec_out, rec_stride, region_counter, region_box);
+    if (mode == 0) launch_march<DIFF, 0>(ctx, grid, st, segs, region_fill, n_slots, region, do_refine, out_its, rec_out, rec_stride, region_counter, ex);
+    else if (mode == 1) launch_march<DIFF, 1>(ctx, grid, st, segs, region_fill, n_slots, region, do_refine, out_its, rec_out, rec_stride, region_counter, ex);
+    else launch_march<DIFF, 2>(ctx, grid, st, segs, region_fill, n_slots, region, do_refine, out_its, rec_out, rec_stride, region_counter, ex);
 }  // camera samples per batch of the wavefront pipeline
 
 // One forward sweep over this rank's camera samples: the primal render (value tracers) or adjoint sweep 1 (differentiable
@@ -580,6 +591,7 @@ struct Sweep {
     float* film;
     const unsigned char* mask;  // per-pixel result of the empty-space test (or nullptr)
     unsigned long long B;       // camera samples per batch
+    FlagList flag;              // DIFF sweep: list for the deferred differentiable march of shadow / BSDF segments (segs == nullptr: off)
 };
 
 template <bool DIFF>
@@ -686,32 +698,44 @@ int enqueue_batch(sdfrt_ctx* ctx, const Sweep& sw, unsigned long long item0, int
         // shadow march over the region-compacted queue.  The differentiable tracer is only needed if shadow rays are
         // reparameterised (python/warp.py:103: max_reparam_depth); otherwise the value tracer's its_t is all the pass uses.
         const bool shadow_diff = DIFF && reparam_at_depth(ctx->sc.W, 1);
+        // Deferred differentiable march (sw.flag): the shadow segments of a DIFF sweep are first marched by the VALUE tracer, which
+        // also reports whether |phi| ever stopped growing along the segment; only those (about 1 in 10, and only if unoccluded) can
+        // end with a valid warp record and are collected for one differentiable march at the end of the sweep (run_sweeps).
+        const bool deferred = shadow_diff && sw.flag.segs != nullptr && ctx->cache_mode[1] == 1;
+        const bool shadow_diff_now = shadow_diff && !deferred;
+        MarchExtra ex;
+        ex.region_box = q.box;
+        ex.approach = deferred;
         { LaunchScope ls(ctx, 3, bs);
-          if (shadow_diff)
+          if (shadow_diff_now)
               launch_march_mode<true>(ctx, 3, need, bs, reinterpret_cast<const SegIn*>(sc.ssegs), q.count,
-                                      regions * region, region, 0, nullptr, sc.srec, B, work + WQ_SHADOW_CHUNK, q.box);
+                                      regions * region, region, 0, nullptr, sc.srec, B, work + WQ_SHADOW_CHUNK, ex);
           else
               launch_march_mode<false>(ctx, 1, need, bs, reinterpret_cast<const SegIn*>(sc.ssegs), q.count,
-                                       regions * region, region, 0, sc.s_its, nullptr, 0, work + WQ_SHADOW_CHUNK, q.box); }
-        const float* shadow_its = shadow_diff ? sc.srec : sc.s_its;
+                                       regions * region, region, 0, sc.s_its, nullptr, 0, work + WQ_SHADOW_CHUNK, ex); }
+        const float* shadow_its = shadow_diff_now ? sc.srec : sc.s_its;
         { LaunchScope ls(ctx, 4, bs);
           k_shadow_splat<DIFF><<<regions, 256, 0, bs>>>(ctx->sc, ps, item0, region, reinterpret_cast<const SegIn*>(sc.segs), q.count,
                                                         reinterpret_cast<const float4*>(sc.sinfo), shadow_its, sc.srec, B, film, rec_b,
-                                                        VS(ctx).rec_stride); }
+                                                        VS(ctx).rec_stride, reinterpret_cast<const SegIn*>(sc.ssegs),
+                                                        deferred ? sw.flag : FlagList{nullptr, nullptr, nullptr, 0u}); }
         if (mis) {   // BSDF-sampled rays: same marchers (no refinement: only hit / escape and the warp record matter), second splat
             SDFRT_CUDA(ctx, cudaMemsetAsync(work + WQ_SHADOW_CHUNK, 0, sizeof(unsigned), bs));
+            MarchExtra exb;
+            exb.approach = deferred;
             { LaunchScope ls(ctx, 3, bs);
-              if (shadow_diff)
+              if (shadow_diff_now)
                   launch_march_mode<true>(ctx, 3, need, bs, reinterpret_cast<const SegIn*>(sc.bsegs), qb.count,
-                                          regions * region, region, 0, nullptr, sc.brec, B, work + WQ_SHADOW_CHUNK);
+                                          regions * region, region, 0, nullptr, sc.brec, B, work + WQ_SHADOW_CHUNK, exb);
               else
                   launch_march_mode<false>(ctx, 1, need, bs, reinterpret_cast<const SegIn*>(sc.bsegs), qb.count,
-                                           regions * region, region, 0, sc.b_its, nullptr, 0, work + WQ_SHADOW_CHUNK); }
-            const float* b_its = shadow_diff ? sc.brec : sc.b_its;
+                                           regions * region, region, 0, sc.b_its, nullptr, 0, work + WQ_SHADOW_CHUNK, exb); }
+            const float* b_its = shadow_diff_now ? sc.brec : sc.b_its;
             { LaunchScope ls(ctx, 4, bs);
               k_shadow_splat<DIFF, true><<<regions, 256, 0, bs>>>(ctx->sc, ps, item0, region, reinterpret_cast<const SegIn*>(sc.segs), qb.count,
                                                                   reinterpret_cast<const float4*>(sc.binfo), b_its, sc.brec, B, film, rec_b,
-                                                                  VS(ctx).rec_stride); }
+                                                                  VS(ctx).rec_stride, reinterpret_cast<const SegIn*>(sc.bsegs),
+                                                                  deferred ? sw.flag : FlagList{nullptr, nullptr, nullptr, 0u}); }
         }
     }
     SDFRT_CUDA(ctx, cudaGetLastError());
@@ -729,6 +753,7 @@ int run_sweeps(sdfrt_ctx* ctx, Sweep* sweeps, int ns, cudaStream_t st) {
         SDFRT_CUDA(ctx, cudaMemsetAsync(sw.film, 0, film_floats(ctx) * sizeof(float), st));
         sw.mask = nullptr;
         sw.B = 0;
+        sw.flag = FlagList{nullptr, nullptr, nullptr, 0u};
         const unsigned long long n = sw.ps.n_items;
         if (n == 0) continue;
         if ((unsigned long long)kBandRows * (unsigned long long)(S.W + 2 * S.border) * (unsigned long long)sw.ps.spp * (1ull + sw.ps.antithetic) > 0xffffffffull)
@@ -743,6 +768,23 @@ int run_sweeps(sdfrt_ctx* ctx, Sweep* sweeps, int ns, cudaStream_t st) {
         (sw.diff ? any_diff : any_value) = true;
     }
     if (total_batches == 0) return SDFRT_OK;
+    // list of the deferred differentiable march (per view slot; one DIFF sweep per call)
+    for (int k = 0; k < ns; ++k) {
+        Sweep& sw = sweeps[k];
+        const unsigned long long n = sw.ps.n_items;
+        if (!sw.diff || n == 0 || !ctx->defer_diff || ctx->sc.integrator != INTEGRATOR_DIRECT || !reparam_at_depth(ctx->sc.W, 1)) continue;
+        const unsigned long long rows = (unsigned long long)rec_rows(ctx);
+        if (n * rows > 0xffffffffull) continue;                       // record offsets are 32-bit
+        const bool mis = ctx->sc.Sh.use_mis;
+        const unsigned long long cap = n * (mis ? 2ull : 1ull);       // every sample could contribute a shadow (and a BSDF) segment
+        if (cap > 0xffffffffull) continue;
+        sdfrt_ctx::ViewSlot& V = VS(ctx);
+        if ((rc = ensure(ctx, &V.flag_segs, &V.flag_segs_n, (size_t)cap * 8))) return rc;
+        if ((rc = ensure(ctx, &V.flag_dest, &V.flag_dest_n, (size_t)cap))) return rc;
+        if (!V.flag_count) SDFRT_CUDA(ctx, cudaMalloc((void**)&V.flag_count, 4 * sizeof(unsigned)));
+        SDFRT_CUDA(ctx, cudaMemsetAsync(V.flag_count, 0, 4 * sizeof(unsigned), st));
+        sw.flag = FlagList{reinterpret_cast<SegIn*>(V.flag_segs), reinterpret_cast<unsigned*>(V.flag_dest), V.flag_count, (unsigned)cap};
+    }
     const int nslots = (total_batches > 1 && ctx->overlap) ? (int)std::min<unsigned long long>(total_batches, (unsigned long long)ctx->max_slots) : 1;
     for (int sl = 0; sl < nslots; ++sl) {
         sdfrt_ctx::Scratch& sc = ctx->scratch[sl];
@@ -887,6 +929,20 @@ int run_sweeps(sdfrt_ctx* ctx, Sweep* sweeps, int ns, cudaStream_t st) {
             SDFRT_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join[sl], 0));
         }
     }
+    // the deferred differentiable march: every flagged shadow / BSDF segment of the sweep in ONE persistent launch; the records go
+    // straight to the lanes' rows (row 0 = its_t lands in the state row: non-zero for an unoccluded segment, as the adjoint expects)
+    for (int k = 0; k < ns; ++k) {
+        Sweep& sw = sweeps[k];
+        if (sw.flag.segs == nullptr) continue;
+        MarchExtra ex;
+        ex.dest = sw.flag.dest;
+        ex.n_slots_dev = sw.flag.count;
+        const unsigned region = 256u;
+        LaunchScope ls(ctx, 3, st);
+        launch_march_mode<true>(ctx, 3, 0xffffffffu, st, sw.flag.segs, nullptr, sw.flag.capacity, region, 0, nullptr, VS(ctx).rec, VS(ctx).rec_stride,
+                                sw.flag.count + 1, ex);
+        SDFRT_CUDA(ctx, cudaGetLastError());
+    }
     return SDFRT_OK;
 }
 
@@ -980,6 +1036,7 @@ sdfrt_ctx* sdfrt_create(int device, int* status) {
     if (const char* e = std::getenv("SDFRT_PRB_OCC")) ctx->prb_min_blocks = std::atoi(e);
     if (const char* e = std::getenv("SDFRT_PRB_WAVEFRONT")) ctx->prb_wavefront = std::atoi(e) != 0;
     if (const char* e = std::getenv("SDFRT_PRB_PRIMARY")) ctx->prb_primary_wavefront = std::atoi(e) != 0;
+    if (const char* e = std::getenv("SDFRT_DEFER")) ctx->defer_diff = std::atoi(e) != 0;
     if (const char* e = std::getenv("SDFRT_SKIP_EMPTY")) ctx->skip_empty = std::atoi(e) != 0;
     if (const char* e = std::getenv("SDFRT_BATCH_LOG2")) ctx->batch_target = 1ull << std::max(16, std::min(28, std::atoi(e)));
     for (int i = 0; i < kSlots; ++i) {
@@ -1011,7 +1068,7 @@ void sdfrt_destroy(sdfrt_ctx* ctx) {
     cudaSetDevice(ctx->device);
     for (auto& t : ctx->timed) { cudaEventDestroy(t.second.first); cudaEventDestroy(t.second.second); }
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
-    for (auto& v : ctx->view) { cudaFree(v.rec); cudaFree(v.film_adj); cudaFree(v.prb_rec); cudaFree(v.brick_a); cudaFree(v.brick_b); cudaFree(v.pix_mask); }
+    for (auto& v : ctx->view) { cudaFree(v.rec); cudaFree(v.film_adj); cudaFree(v.prb_rec); cudaFree(v.brick_a); cudaFree(v.brick_b); cudaFree(v.pix_mask); cudaFree(v.flag_segs); cudaFree(v.flag_dest); cudaFree(v.flag_count); }
     cudaFree(ctx->counters);
     cudaFree(ctx->work);
     cudaFree(ctx->rows4); cudaFree(ctx->rows8); cudaFree(ctx->brick_raw);

@@ -275,7 +275,8 @@ constexpr int kBoxBase = 16;                 // block bases per axis covered by 
 constexpr int kBoxY = kBoxBase + 3, kBoxZ = kBoxBase + 3;
 constexpr int kBoxX = kBoxBase + 4;          // inner extent rounded up to a multiple of 16 bytes (TMA box rule)
 constexpr int kBoxFloats = kBoxX * kBoxY * kBoxZ;
-constexpr unsigned kBoxBytes = (unsigned)kBoxFloats * 4u;
+constexpr unsigned kBoxBytes = (unsigned)kBoxFloats * 4u;          // bytes one TMA fill delivers
+constexpr int kBoxStride = (kBoxFloats + 31) / 32 * 32;            // buffer stride: every TMA destination must be 128-byte aligned
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
@@ -300,7 +301,7 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const void* tmap, int x, 
 struct TmaMap { alignas(64) unsigned long long opaque[16]; };  // CUtensorMap (128 bytes), filled by the host with cuTensorMapEncodeTiled
 
 struct BoxShared {
-    alignas(128) float data[2][kBoxFloats];
+    alignas(128) float data[2][kBoxStride];
     unsigned long long mbar[2];
     int region[2];        // region id held by (or being loaded into) the buffer, -1 = none
     int ox[2], oy[2], oz[2];
@@ -395,13 +396,21 @@ enum { SLOT_IDLE = 0, SLOT_MARCH = 1, SLOT_REFINE = 2, SLOT_DONE = 3 };
 
 // rec_out (DIFF): 9 rows [its_t, warp_t, warp_t_d xyz, warp_weight, warp_weight_d xyz] of stride rec_stride.
 // CACHE: 0 = gather every evaluation, 1 = tap cache in registers, 2 = tap cache in shared memory
-template <bool DIFF, int CACHE, int ROWS, bool BOX = false>
+// APPROACH (value marcher only): a miss is reported as -inf instead of +inf if |phi| ever failed to grow from one step to the next.
+//   The differentiable tracer only accumulates silhouette weight once that has happened (`extra_weight_sum`, python/shapes.py:195-201),
+//   so a +inf segment provably ends with an invalid warp record and never needs the differentiable march (shadow segments of
+//   adjoint sweep 1: 9 in 10).
+// dest (DIFF, optional): record of segment `item` goes to rec_out + dest[item] instead of rec_out + item.
+// n_slots_dev (optional): the number of valid slots is read from device memory (a list filled by earlier kernels of the stream).
+template <bool DIFF, int CACHE, int ROWS, bool BOX = false, bool APPROACH = false>
 __global__ void __launch_bounds__(kMarchBlock, BOX ? 3 : (DIFF ? (CACHE == 1 ? 3 : 4) : (CACHE == 1 ? 4 : 7))) k_march(const GridView G, const TracerParams T, const SegIn* __restrict__ segs,
                                                         const unsigned* __restrict__ region_count, unsigned n_slots, unsigned region, int do_refine, int min_live,
                                                         float* __restrict__ out_its, float* __restrict__ rec_out,
                                                         unsigned long long rec_stride, unsigned* __restrict__ region_counter,
                                                         Counters* __restrict__ counters, const __grid_constant__ TmaMap tmap,
-                                                        const int4* __restrict__ region_box) {
+                                                        const int4* __restrict__ region_box, const unsigned* __restrict__ dest = nullptr,
+                                                        const unsigned* __restrict__ n_slots_dev = nullptr) {
+    if (n_slots_dev != nullptr) n_slots = *n_slots_dev;
     __shared__ unsigned long long s_word;
     extern __shared__ unsigned char s_dyn[];   // BOX: one BoxShared (128-byte aligned by the launch)
     BoxShared* box = BOX ? reinterpret_cast<BoxShared*>((reinterpret_cast<size_t>(s_dyn) + 127) & ~(size_t)127) : nullptr;
@@ -437,13 +446,15 @@ __global__ void __launch_bounds__(kMarchBlock, BOX ? 3 : (DIFF ? (CACHE == 1 ? 3
                 acc.mixed_sum_d = v3(0.f); acc.weight_d_sum = v3(0.f); acc.extra_weight_sum_d = v3(0.f); acc.t_d = v3(0.f); }
     unsigned n_evals = 0, n_steps_max = 0, n_loads = 0;
     bool exhausted = false;
+    float prev_surf = 0.f;      // APPROACH: |phi| of the previous march step of this slot's segment
+    bool approached = false;
 
     while (true) {
         // ---- finish (DIFF): tracer outputs of completed segments ----------------------------------------------
         if (DIFF && state == SLOT_DONE) {
             TraceOut tr;
             diff_finalize(seg, acc, T, tr);
-            float* r = rec_out + item;
+            float* r = rec_out + (dest != nullptr ? dest[item] : item);
             r[0 * rec_stride] = tr.its_t;
             r[1 * rec_stride] = tr.warp_t;
             r[2 * rec_stride] = tr.warp_t_d.x; r[3 * rec_stride] = tr.warp_t_d.y; r[4 * rec_stride] = tr.warp_t_d.z;
@@ -473,6 +484,7 @@ __global__ void __launch_bounds__(kMarchBlock, BOX ? 3 : (DIFF ? (CACHE == 1 ? 3
                 seg.its_t = INFINITY;
                 seg.i = 0;
                 if (DIFF) diff_begin(acc, seg, T);
+                if (APPROACH) { prev_surf = 0.f; approached = false; }
                 state = seg.intersects ? SLOT_MARCH : SLOT_DONE;
                 if (!DIFF && state == SLOT_DONE) { out_its[item] = INFINITY; state = SLOT_IDLE; }
             }
@@ -530,7 +542,14 @@ __global__ void __launch_bounds__(kMarchBlock, BOX ? 3 : (DIFF ? (CACHE == 1 ? 3
                     reduce_taps<ORD>(f, cs, G, v, g, H);
                 }
                 if (DIFF) cont = (state == SLOT_MARCH) ? diff_step(seg, acc, T, v, g, H) : refine_step(seg, v);
-                else cont = (state == SLOT_MARCH) ? value_step(seg, T, v) : refine_step(seg, v);
+                else {
+                    if (APPROACH && state == SLOT_MARCH) {   // dist_difference >= 0 of python/shapes.py:199-200 (conservatively: incl. 0)
+                        const float surf = fabsf(T.step_scale != 1.f ? v * T.step_scale : v);
+                        approached = approached | (prev_surf - surf >= 0.f);
+                        prev_surf = surf;
+                    }
+                    cont = (state == SLOT_MARCH) ? value_step(seg, T, v) : refine_step(seg, v);
+                }
                 if (!cont) {
                     if (state == SLOT_MARCH) {
                         n_steps_max = max(n_steps_max, (unsigned)seg.i);
@@ -539,7 +558,10 @@ __global__ void __launch_bounds__(kMarchBlock, BOX ? 3 : (DIFF ? (CACHE == 1 ? 3
                     } else {
                         state = SLOT_DONE;
                     }
-                    if (!DIFF && state == SLOT_DONE) { out_its[item] = seg.its_t; state = SLOT_IDLE; }
+                    if (!DIFF && state == SLOT_DONE) {
+                        out_its[item] = (APPROACH && approached && !isfinite(seg.its_t)) ? -INFINITY : seg.its_t;
+                        state = SLOT_IDLE;
+                    }
                 }
             }
         }
@@ -747,13 +769,22 @@ __global__ void __launch_bounds__(256, 3) k_shade(const __grid_constant__ SceneP
 // one block per region: visibility -> splat; DIFF: scatter the shadow tracer record to the lane records
 // BQ: the queue of BSDF-sampled rays (use_mis): escaped = contribution, records go to the REC_B_* rows, and the weight channel is
 // only added for samples that have no emitter-sampled part (bit 31 of the item word)
+// Deferred differentiable march (DIFF, `flag` given): the segments were marched by the value tracer with APPROACH; unoccluded ones
+// get state 1 and an invalid warp record (tau = inf), and those reported as -inf are appended to the sweep's list `flag` for the one
+// differentiable march at the end of the sweep, which overwrites their record rows in place.
+struct FlagList {
+    SegIn* segs;        // [capacity]
+    unsigned* dest;     // [capacity] record offset of the segment's lane: row_base * stride + lane item (the marcher adds row * stride)
+    unsigned* count;    // device counter
+    unsigned capacity;
+};
 template <bool DIFF, bool BQ = false>
 __global__ void __launch_bounds__(256) k_shadow_splat(const __grid_constant__ SceneParams sc, const __grid_constant__ PassParams ps,
                                                        unsigned long long item0, unsigned region, const SegIn* __restrict__ psegs,
                                                        const unsigned* __restrict__ region_count, const float4* __restrict__ info, const float* __restrict__ s_its,
                                                        const float* __restrict__ srec, unsigned long long srec_stride,
                                                        float* __restrict__ film, float* __restrict__ rec,
-                                                       unsigned long long rec_stride) {
+                                                       unsigned long long rec_stride, const SegIn* __restrict__ ssegs = nullptr, FlagList flag = FlagList{nullptr, nullptr, nullptr, 0u}) {
     __shared__ SplatSmem s_splat[8];
     const unsigned cnt = region_count[blockIdx.x];
     const unsigned region_base = blockIdx.x * region;
@@ -762,12 +793,15 @@ __global__ void __launch_bounds__(256) k_shadow_splat(const __grid_constant__ Sc
         const bool live = j < cnt;
         float pfx = 0.f, pfy = 0.f, wgt = 1.f;
         V3 rgb = v3(0.f);
+        bool want_flag = false;
+        unsigned flag_item = 0u;
         if (live) {
             const unsigned slot = region_base + j;
             const float4 inf = info[slot];
             const unsigned iw = __float_as_uint(inf.w);
             const unsigned i = BQ ? (iw & 0x7fffffffu) : iw;
             if (BQ && (iw & 0x80000000u)) wgt = 0.f;
+            flag_item = (unsigned)item0 + i;   // lane item within the sweep (records are indexed by it)
             const float its_s = s_its[slot];  // its_t of the shadow segment (value tracer's output, or row 0 of the DIFF records)
             const bool occluded = isfinite(its_s);
             const float4 sb = __ldg(&psegs[i].b);
@@ -776,8 +810,29 @@ __global__ void __launch_bounds__(256) k_shadow_splat(const __grid_constant__ Sc
             if (DIFF && !occluded) {
                 float* d = rec + i;
                 d[(BQ ? REC_B_STATE : REC_S_STATE) * rec_stride] = 1.f;
+                if (flag.segs != nullptr) {
+                    d[(BQ ? REC_B_TAU : REC_S_TAU) * rec_stride] = INFINITY;   // invalid warp record unless the deferred march says otherwise
+                    want_flag = its_s < 0.f;                                  // -inf: |phi| stopped growing somewhere along the segment
+                } else {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) d[((BQ ? REC_B_TAU : REC_S_TAU) + k) * rec_stride] = srec[(1 + k) * srec_stride + slot];
+                    for (int k = 0; k < 8; ++k) d[((BQ ? REC_B_TAU : REC_S_TAU) + k) * rec_stride] = srec[(1 + k) * srec_stride + slot];
+                }
+            }
+        }
+        if (DIFF && flag.segs != nullptr) {   // warp-aggregated append to the sweep's list
+            const unsigned m = __ballot_sync(0xffffffffu, want_flag);
+            if (m) {
+                const int lane_id = threadIdx.x & 31;
+                unsigned base = 0;
+                if (lane_id == (__ffs(m) - 1)) base = atomicAdd(flag.count, (unsigned)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+                if (want_flag) {
+                    const unsigned k = base + (unsigned)__popc(m & ((1u << lane_id) - 1u));
+                    if (k < flag.capacity) {
+                        flag.segs[k] = ssegs[region_base + j];
+                        flag.dest[k] = (unsigned)((BQ ? REC_B_STATE : REC_S_STATE) * rec_stride) + flag_item;
+                    }
+                }
             }
         }
         warp_splat(sc.S, film, s_splat[threadIdx.x >> 5], live, pfx, pfy, rgb, wgt);
