@@ -460,18 +460,44 @@ def e2e_leg(job, steps):
     ga_h = None if job.alb is None else torch.empty(tuple(job.alb.shape)).pin_memory()
     nsens, spp, mult = job.nsens, job.spp, job.mult
     if job.world == 1:
-        def one(seed):
-            job.ctx.render_view_host(sdf_h, seed, spp * mult, seed + 1 + nsens, spp, None, img_h, g_h, albedo_host=alb_h, grad_albedo_host=ga_h)
-        for w in range(2):
-            one(w)
+        # Views in flight on the host API too: `inflight` contexts, one host thread each (the C call releases the GIL), every one with
+        # its own pinned host buffers; the copies of one view overlap the kernels of the other (PCIe is full duplex).
+        import threading
+        nctx = job.inflight
+        ctxs = [job.ctx] + [sdfrt.Context(job.dev.index) for _ in range(nctx - 1)]
+        for c in ctxs[1:]:
+            c.set_sensor(job.sensor.to_world, job.W, job.H)
+            c.set_shading()
+            c.set_integrator('sdf_prb_reparam' if job.prb else 'sdf_direct_reparam')
+            if job.prb:
+                c.set_prb(**job.prb)
+            c.set_warp()
+        bufs = [(img_h, g_h, ga_h)] + [(torch.empty_like(img_h).pin_memory(), torch.empty_like(g_h).pin_memory(),
+                                        None if ga_h is None else torch.empty_like(ga_h).pin_memory()) for _ in range(nctx - 1)]
+
+        def one(k, seed):
+            im, g, ga = bufs[k]
+            ctxs[k].render_view_host(sdf_h, seed, spp * mult, seed + 1 + nsens, spp, None, im, g, albedo_host=alb_h, grad_albedo_host=ga)
+
+        def run(n_steps, seed0):
+            def worker(k):
+                for s in range(k, n_steps, nctx):
+                    one(k, seed0 + s)
+            th = [threading.Thread(target=worker, args=(k,)) for k in range(nctx)]
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+        run(2 * nctx, 0)
         torch.cuda.synchronize(job.dev)
+        e_steps = max(e_steps, 2 * nctx)
         tw = time.perf_counter()
-        for s in range(e_steps):
-            one(1000 + s)
+        run(e_steps, 1000)
         tw = time.perf_counter() - tw
         job.ctx.set_sdf(job.sdf)
         job.ctx.set_albedo(job.alb)
-        api = "sdfrt_render_view_host_ex"
+        del ctxs
+        api = f"sdfrt_render_view_host_ex ({nctx} contexts / host threads, one view each in flight)" if nctx > 1 else "sdfrt_render_view_host_ex"
     else:
         def one(seed):
             job.sdf.copy_(sdf_h, non_blocking=True)

@@ -394,6 +394,7 @@ struct sdfrt_ctx {
               *bsegs = nullptr, *binfo = nullptr, *b_its = nullptr, *brec = nullptr, *bcount = nullptr;   // use_mis: BSDF-sampled rays
         size_t segs_n = 0, its_n = 0, ssegs_n = 0, sinfo_n = 0, s_its_n = 0, srec_n = 0, scount_n = 0, prb_rec_n = 0, sbox_n = 0, bsegs_n = 0, binfo_n = 0, b_its_n = 0, brec_n = 0, bcount_n = 0;
     } scratch[kSlots];            // one per pipeline slot
+    cudaStream_t host_stream = nullptr;   // stream of the host-buffer entry points
     cudaStream_t aux[kSlots] = {};   // batches rotate over internal streams so that the tail of one batch's persistent
     cudaEvent_t ev_fork = nullptr, ev_join[kSlots] = {};  // kernels overlaps the following batches
     float* brick_raw = nullptr;   // per-brick SDF minima (undilated; rebuilt when the grid changes)
@@ -1044,6 +1045,7 @@ sdfrt_ctx* sdfrt_create(int device, int* status) {
         ok = ok && cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
     }
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&ctx->host_stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->march_blocks[0], k_march<false, 0, 0>, kMarchBlock, 0) == cudaSuccess;
     ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->march_blocks[1], k_march<false, 1, 0>, kMarchBlock, 0) == cudaSuccess;
     ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->march_blocks[2], k_march<false, 2, 0>, kMarchBlock, 0) == cudaSuccess;
@@ -1082,6 +1084,7 @@ void sdfrt_destroy(sdfrt_ctx* ctx) {
         if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
     }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->host_stream) cudaStreamDestroy(ctx->host_stream);
     if (ctx->rd_err_host) cudaFreeHost(ctx->rd_err_host);
     if (ctx->rd_err_event) cudaEventDestroy(ctx->rd_err_event);
     cudaFree(ctx->h_alb); cudaFree(ctx->h_galb);
@@ -1626,7 +1629,8 @@ int sdfrt_render_view_host_ex(sdfrt_ctx* ctx, const float* sdf_host, int rx, int
         if ((rc = ensure(ctx, &ctx->h_gimg, &cap, nimg))) return rc;
         ctx->h_image_n = nimg;
     }
-    cudaStream_t st = 0;
+    // the context's own non-blocking stream: calls on DIFFERENT contexts (one per host thread) overlap their copies and kernels
+    cudaStream_t st = ctx->host_stream;
     SDFRT_CUDA(ctx, cudaMemcpyAsync(ctx->h_sdf, sdf_host, nvox * sizeof(float), cudaMemcpyHostToDevice, st));
     const float p0[3] = {ctx->sc.G.px, ctx->sc.G.py, ctx->sc.G.pz};
     if ((rc = sdfrt_set_sdf(ctx, ctx->h_sdf, rx, ry, rz, ctx->have_sdf ? p0 : nullptr))) return rc;

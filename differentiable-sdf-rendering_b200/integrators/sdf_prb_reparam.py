@@ -29,10 +29,14 @@ class SdfPrbReparamIntegrator(ReparamIntegrator):
         if isinstance(self.warp_field, DummyWarpField):
             # the reference calls warp_field.reparam (sdf_prb_reparam.py:181), which DummyWarpField lacks (python/warp.py:179-196)
             raise AttributeError("'DummyWarpField' object has no attribute 'reparam'")
-        if self.max_depth < 1:
-            raise ValueError("max_depth must be >= 1 (unbounded paths, max_depth = -1, are not supported)")
+        # max_depth = -1: the reference passes the prop through unchanged (python/integrators/reparam.py:14) -- unlike Mitsuba's own
+        # prb there is no "-1 means unbounded" conversion.  `loop.set_max_iterations(-1)` wraps to a huge count, but
+        # `active_next = (depth + 1 < self.max_depth)` (sdf_prb_reparam.py:307) is then false at the first vertex, so the path ends
+        # there: exactly the behaviour of max_depth = 1, which is what is rendered here (oracle/ref_semantics.md S17).
+        if self.max_depth == 0 or self.max_depth < -1:
+            raise ValueError("max_depth must be >= 1 (or -1)")
         ctx = super()._bind(scene, sensor)
-        ctx.set_prb(self.max_depth, self.rr_depth)
+        ctx.set_prb(1 if self.max_depth == -1 else self.max_depth, self.rr_depth)
         if self.warp_field is not None:  # :267-272
             m = self.warp_field.max_reparam_depth
             self.reparam_max_depth = m if m >= 0 else 100000

@@ -266,7 +266,10 @@ int sdfrt_laplacian_reg(sdfrt_ctx* ctx, const float* data, int rx, int ry, int r
  * One optimisation-loop view: upload sdf (host, rz*ry*rx floats), render primal at (seed, spp),
  * re-render + backprop at (seed_grad, spp_grad) against grad_image_host (H*W*3; if NULL the
  * reference benchmark's loss dr.sum(img) is used, figures/benchmark/benchmark.py:44), download
- * image_host (H*W*3) and grad_sdf_host (rz*ry*rx).  Synchronous. */
+ * image_host (H*W*3) and grad_sdf_host (rz*ry*rx).  Synchronous for the caller; the work runs on a non-blocking stream owned by the
+ * context, so host threads driving DIFFERENT contexts (one per thread; a context is not thread-safe) overlap each other's copies
+ * and kernels -- e.g. the views of one optimisation iteration, which are independent (python/shape_opt.py:77-83).  Use pinned host
+ * memory for asynchronous copies. */
 int sdfrt_render_view_host(sdfrt_ctx* ctx, const float* sdf_host, int rx, int ry, int rz,
                            uint32_t seed, int spp, uint32_t seed_grad, int spp_grad,
                            const float* grad_image_host, float* image_host, float* grad_sdf_host);
