@@ -402,8 +402,8 @@ struct sdfrt_ctx {
     bool skip_empty = true;
     bool defer_diff = true;     // deferred differentiable march of the shadow segments (SDFRT_DEFER=0: march them differentiably per batch)
     int min_live = kMinActive;  // slots that must be stepping for a warp to stay in the stepping loop
-    int max_slots = 4;
-    unsigned long long batch_target = 0;  // camera samples per batch; 0 = n / 6 clamped to [2^20, 2^24] (measured best at c3)
+    int max_slots = 6;
+    unsigned long long batch_target = 0;  // camera samples per batch; 0 = n / 6 clamped to [2^23, 2^24]
     int num_sms = 0;
     int march_blocks[6] = {0, 0, 0, 0, 0, 0};  // resident blocks per SM of k_march<DIFF, CACHE> at [3*DIFF + CACHE]
     // Row-expanded copy of the SDF grid for the marchers (GridView::rows4): 4x the memory, one 16-byte load per x-row of a
@@ -702,7 +702,7 @@ int enqueue_batch(sdfrt_ctx* ctx, const Sweep& sw, unsigned long long item0, int
         // Deferred differentiable march (sw.flag): the shadow segments of a DIFF sweep are first marched by the VALUE tracer, which
         // also reports whether |phi| ever stopped growing along the segment; only those (about 1 in 10, and only if unoccluded) can
         // end with a valid warp record and are collected for one differentiable march at the end of the sweep (run_sweeps).
-        const bool deferred = shadow_diff && sw.flag.segs != nullptr && ctx->cache_mode[1] == 1;
+        const bool deferred = shadow_diff && sw.flag.segs != nullptr && ctx->cache_mode[1] == 1 && !box_shadow;
         const bool shadow_diff_now = shadow_diff && !deferred;
         MarchExtra ex;
         ex.region_box = q.box;
@@ -760,7 +760,8 @@ int run_sweeps(sdfrt_ctx* ctx, Sweep* sweeps, int ns, cudaStream_t st) {
         if ((unsigned long long)kBandRows * (unsigned long long)(S.W + 2 * S.border) * (unsigned long long)sw.ps.spp * (1ull + sw.ps.antithetic) > 0xffffffffull)
             return fail(ctx, SDFRT_ERR_INVALID, "film row band exceeds 2^32 samples");
         unsigned long long target = ctx->batch_target;
-        if (target == 0) target = std::max<unsigned long long>(1ull << 20, std::min<unsigned long long>(1ull << 24, n / 6));
+        if (target == 0) target = std::max<unsigned long long>(1ull << 23, std::min<unsigned long long>(1ull << 24, n / 6));   // measured: fewer, larger batches
+                                                                        // win once a rank holds < 50 M samples (profiles/r2_call4)
         const unsigned long long nbatch = (n + target - 1) / target;
         unsigned long long B = (n + nbatch - 1) / nbatch;
         sw.B = (B + kMaxRegion - 1) / kMaxRegion * kMaxRegion;  // whole regions per batch
