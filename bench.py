@@ -630,7 +630,7 @@ def run_gpu(args):
 
     line["cpu_baseline"] = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        n, r = cpu_calibrated_sample(args.workload, 12.0)
+        n, r = cpu_calibrated_sample(args.workload, 5.0)
         line["cpu_baseline"] = cpu_record(args.workload, n, r, "compiled CPU port of the restated reference")
 
     # second metric (protocol of figures/benchmark/benchmark.py:120-144): the per-iteration grid update on the

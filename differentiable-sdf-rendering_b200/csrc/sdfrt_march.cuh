@@ -744,6 +744,7 @@ __global__ void __launch_bounds__(256, 3) k_shade(const __grid_constant__ SceneP
                 for (int a = 0; a < 3; ++a) {
                     int c = (s_lo[a] + s_hi[a]) / 2 - kBoxBase / 2;
                     c = max(0, min(c, r[a] - (kBoxBase + 3)));
+                    if (a == 0) c &= ~3;   // the TMA unit faults on a box whose first row does not start on a 16-byte boundary
                     o3[a] = c;
                 }
                 b = make_int4(o3[0], o3[1], o3[2], 1);
