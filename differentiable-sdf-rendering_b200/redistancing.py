@@ -28,10 +28,8 @@ def redistance(phi, method='fastsweep', lower_bound=None, context=None):
         raise ValueError("Invalid re-distancing method")
     if not torch.is_tensor(phi):
         phi = torch.from_numpy(np.ascontiguousarray(np.asarray(phi, dtype=np.float32)))
-    if not phi.is_cuda:
-        phi = phi.cuda(context.device if context is not None else 0)
     ctx = context if context is not None else shared_context(phi.device.index or 0)
-    phi = phi.to(torch.float32).contiguous()
+    phi = phi.to(ctx.device, torch.float32).contiguous()
     if lower_bound is not None:
         lower_bound = torch.as_tensor(lower_bound, dtype=torch.float32).to(phi.device).contiguous()
     # synchronous on purpose: the solver's error word (barrier time-out / iteration cap) is checked before the grid is handed

@@ -27,8 +27,9 @@ class _LaplacianReg(torch.autograd.Function):
 def eval_discrete_laplacian_reg(data, _=None):
     """Sum over voxels of (c - mean of the 6 axis neighbours)^2 with clamped neighbour indices (python/regularizations.py:5-25).
     data: (Z, Y, X[, 1]) float32 CUDA tensor."""
-    if not (torch.is_tensor(data) and data.is_cuda and data.dtype == torch.float32):
-        raise SdfrtError("eval_discrete_laplacian_reg expects a float32 CUDA tensor (no CPU path)")
+    from . import redistancing
+    if not (torch.is_tensor(data) and data.dtype == torch.float32 and data.device == redistancing.shared_context(data.device.index or 0).device):
+        raise SdfrtError("eval_discrete_laplacian_reg expects a float32 tensor on the rendering device (no CPU path)")
     return _LaplacianReg.apply(data)
 
 

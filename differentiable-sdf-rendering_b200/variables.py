@@ -127,7 +127,7 @@ class VolumeVariable(Variable):
         self.shape = np.array(shape)
         self.init_value = init_value
         self.upsample_iter = upsample_iter
-        self.device = torch.device('cuda', device)
+        self.device = redistancing.shared_context(device).device   # the rendering device (cuda:<device>)
         if self.upsample_iter is not None:
             self.upsample_iter = list(self.upsample_iter)
             for i in range(3):
