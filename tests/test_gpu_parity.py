@@ -488,8 +488,9 @@ def test_marcher_variants_give_the_same_films_and_gradients(sdfrt_mod, env):
         ctx.adjoint_backprop(fa, G, g)
         return fp.clone(), fa.clone(), g, ctx.stats(reset=True)
 
-    fp0, fa0, g0, st0 = run({})
-    fp1, fa1, g1, st1 = run(env)
+    base = {'SDFRT_DEFER': '0'}     # (the staged boxes and the deferred differentiable march exclude each other: compare like with like)
+    fp0, fa0, g0, st0 = run(base)
+    fp1, fa1, g1, st1 = run({**base, **env})
     for k in ('n_evals_value', 'n_evals_hess', 'n_evals_grad', 'n_hits', 'n_scatter_sites'):   # (n_tap_loads depends on which segment a slot held before)
         assert st0[k] == st1[k], (k, st0[k], st1[k])
     assert (fp0 - fp1).abs().max() < 1e-5 * fp0.abs().max() and (fa0 - fa1).abs().max() < 1e-5 * fa0.abs().max()
