@@ -499,32 +499,73 @@ def e2e_leg(job, steps):
         del ctxs
         api = f"sdfrt_render_view_host_ex ({nctx} contexts / host threads, one view each in flight)" if nctx > 1 else "sdfrt_render_view_host_ex"
     else:
-        def one(seed):
-            job.sdf.copy_(sdf_h, non_blocking=True)
-            if alb_h is not None:
-                job.alb.copy_(alb_h, non_blocking=True)
-            job.grad_sdf.zero_()
-            if job.grad_alb is not None:
-                job.grad_alb.zero_()
-            img = sdfrt.dist.render_view(job.ctx, seed, spp * mult, seed + 1 + nsens, spp, lambda im: job.grad_image, job.grad_sdf, job.grad_alb)
+        # N > 1: sdfrt.dist.render_view per view (set_partition, film all-reduces, backprop, gradient all-reduce over NCCL).  The host
+        # copies are double-buffered around it: the grids of view v+1 are uploaded on a copy stream into the other pair of device
+        # buffers while view v renders, and rank 0's downloads of view v run on the copy stream behind the next view's kernels.
+        copy_s = torch.cuda.Stream(job.dev)
+        sdf_d = [job.sdf, torch.empty_like(job.sdf)]
+        alb_d = [job.alb, None if job.alb is None else torch.empty_like(job.alb)]
+        gs_d = [job.grad_sdf, torch.empty_like(job.grad_sdf)]
+        ga_d = [job.grad_alb, None if job.grad_alb is None else torch.empty_like(job.grad_alb)]
+        outs = [(img_h, g_h, ga_h), (torch.empty_like(img_h).pin_memory(), torch.empty_like(g_h).pin_memory(),
+                                     None if ga_h is None else torch.empty_like(ga_h).pin_memory())]
+        up_done = [torch.cuda.Event(), torch.cuda.Event()]
+        free = [torch.cuda.Event(), torch.cuda.Event()]      # device buffers k may be overwritten (their view's kernels are done)
+        main = torch.cuda.current_stream(job.dev)
+        job.ctx.set_view_slot(0)
+
+        def upload(k):
+            with torch.cuda.stream(copy_s):
+                copy_s.wait_event(free[k])
+                sdf_d[k].copy_(sdf_h, non_blocking=True)
+                if alb_h is not None:
+                    alb_d[k].copy_(alb_h, non_blocking=True)
+                up_done[k].record(copy_s)
+
+        def view(k, seed):
+            main.wait_event(up_done[k])
+            job.ctx.set_sdf(sdf_d[k])
+            job.ctx.set_albedo(alb_d[k])
+            gs_d[k].zero_()
+            if ga_d[k] is not None:
+                ga_d[k].zero_()
+            img = sdfrt.dist.render_view(job.ctx, seed, spp * mult, seed + 1 + nsens, spp, lambda im: job.grad_image, gs_d[k], ga_d[k], buffers_are_zero=True)
+            done = torch.cuda.Event()
+            done.record(main)
             if job.rank == 0:
-                img_h.copy_(img, non_blocking=True)
-                g_h.copy_(job.grad_sdf, non_blocking=True)
-                if ga_h is not None:
-                    ga_h.copy_(job.grad_alb, non_blocking=True)
+                with torch.cuda.stream(copy_s):
+                    copy_s.wait_event(done)
+                    outs[k][0].copy_(img, non_blocking=True)
+                    outs[k][1].copy_(gs_d[k], non_blocking=True)
+                    if ga_d[k] is not None:
+                        outs[k][2].copy_(ga_d[k], non_blocking=True)
+                    img.record_stream(copy_s)
+                    free[k].record(copy_s)
+            else:
+                free[k].record(main)
+
+        def run(n_steps, seed0):
+            for k in range(2):
+                free[k].record(main)
+            upload(0)
+            for s_ in range(n_steps):
+                if s_ + 1 < n_steps:
+                    upload((s_ + 1) % 2)
+                view(s_ % 2, seed0 + s_)
             torch.cuda.synchronize(job.dev)
-        for w in range(2):
-            one(w)
+        run(2, 0)
         dist.barrier()
+        e_steps = max(e_steps, 4)
         tw = time.perf_counter()
-        for s in range(e_steps):
-            one(1000 + s)
+        run(e_steps, 1000)
         dist.barrier()
         tw = time.perf_counter() - tw
         twt = torch.tensor([tw], device=job.dev, dtype=torch.float64)
         dist.all_reduce(twt, op=dist.ReduceOp.MAX)
         tw = twt.item()
-        api = "sdfrt.dist.render_view"
+        job.ctx.set_sdf(job.sdf)
+        job.ctx.set_albedo(job.alb)
+        api = "sdfrt.dist.render_view (uploads / downloads double-buffered on a copy stream)"
     h2d = (sdf_h.numel() + (alb_h.numel() if alb_h is not None else 0)) * 4 * job.world
     d2h = (img_h.numel() + g_h.numel() + (ga_h.numel() if ga_h is not None else 0)) * 4
     return {"value": job.rays_per_step * e_steps / tw / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

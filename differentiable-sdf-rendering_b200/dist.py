@@ -18,12 +18,14 @@ def _world(group):
 
 
 def render_view(backend, seed, spp, seed_grad, spp_grad, grad_image_fn, grad_sdf, grad_albedo=None, group=None,
-                async_grad_reduce=False):
+                async_grad_reduce=False, buffers_are_zero=False):
     """One optimisation-loop view (python/shape_opt.py:78-83) across the ranks of `group`.
 
     grad_image_fn(image) -> dLoss/dImage, evaluated redundantly on every rank from the all-reduced image.
     Gradients are ACCUMULATED into grad_sdf / grad_albedo (like dr.backward) and are complete (summed over
     ranks) on return unless async_grad_reduce=True, in which case the pending work handles are returned.
+    buffers_are_zero=True: the caller has just zeroed grad_sdf / grad_albedo, so this view's contribution is written and all-reduced
+    in place (no temporary grids).
     """
     rank, world = _world(group)
     backend.set_partition(rank, world)
@@ -44,8 +46,8 @@ def render_view(backend, seed, spp, seed_grad, spp_grad, grad_image_fn, grad_sdf
         film_a = backend.adjoint_accumulate(seed_grad, spp_grad)
         if world > 1:
             dist.all_reduce(film_a, group=group)
-    local = torch.zeros_like(grad_sdf)
-    local_alb = None if grad_albedo is None else torch.zeros_like(grad_albedo)
+    local = grad_sdf if buffers_are_zero else torch.zeros_like(grad_sdf)
+    local_alb = None if grad_albedo is None else (grad_albedo if buffers_are_zero else torch.zeros_like(grad_albedo))
     backend.adjoint_backprop(film_a, grad_image.contiguous(), local, local_alb)
     handles = []
     if world > 1:
@@ -56,9 +58,10 @@ def render_view(backend, seed, spp, seed_grad, spp_grad, grad_image_fn, grad_sdf
     def finish():
         for h in handles:
             h.wait()
-        grad_sdf.add_(local)
-        if local_alb is not None:
-            grad_albedo.add_(local_alb)
+        if not buffers_are_zero:
+            grad_sdf.add_(local)
+            if local_alb is not None:
+                grad_albedo.add_(local_alb)
 
     if async_grad_reduce:
         return image, finish
