@@ -138,6 +138,16 @@ struct ShadingParams {
     // BSDF sample by the power heuristic (python/integrators/sdf_direct_reparam.py:76-79,87-107)
     int use_mis;
 };
+// `envmap` emitter (lat-long bitmap, identity to_world; oracle/ref_semantics.md S18).  data == nullptr: the `constant` emitter of
+// ShadingParams.  The bitmap is stored with its first column repeated at the end (W1 = width + 1); the sampling tables describe a
+// piecewise-constant distribution over the (W1 - 1) x (H - 1) bilinear cells, weight = mean corner luminance * sin(theta_centre).
+struct EnvView {
+    const float* data;       // (H, W1, 3)
+    const float* marg_cdf;   // [H - 1] inclusive CDF over cell rows
+    const float* cond_cdf;   // [(H - 1) * (W1 - 1)] inclusive CDF inside each row
+    const float* cell_prob;  // [(H - 1) * (W1 - 1)]
+    int W1, H;
+};
 struct Counters {  // device work counters (unsigned long long for atomicAdd)
     unsigned long long n_rays, n_evals_value, n_evals_grad, n_evals_hess, n_scatter_sites, n_albedo_lookups,
         n_steps_max, n_hits, n_evals_adjoint, n_tap_loads, n_skipped, n_box_loads;
@@ -239,6 +249,7 @@ SDFRT_HD CellCoord cell_coord(const GridView& G, V3 x) {
     return c;
 }
 SDFRT_HD int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+SDFRT_HD int min_i(int a, int b) { return a < b ? a : b; }
 
 // Clamp-to-edge addressing (WrapMode::Clamp) folded into the WEIGHTS: the interpolant is linear in the taps, so
 // taps i-1..i+2 clamped to [0, r-1] equal the 4 in-range taps b..b+3 (b = clamp(i, 0, r-4)) with the weights of
@@ -793,6 +804,77 @@ SDFRT_HD V3 square_to_uniform_sphere(float u0, float u1) {
     const float r = sqrtf(fmaxf(0.f, 1.f - z * z));
     const float phi = 2.f * kPi * u0;
     return V3{r * cosf(phi), r * sinf(phi), z};
+}
+
+// ------------------------------------------------------------------------------------
+// envmap emitter: lookup (+ derivative w.r.t. the direction), importance sampling, pdf
+// ------------------------------------------------------------------------------------
+SDFRT_HD void env_coord(const EnvView& E, V3 d, float& cx, float& cy) {
+    float u = atan2f(d.x, -d.z) * (0.5f / kPi) - 0.5f / (float)(E.W1 - 1);
+    float v = acosf(fminf(fmaxf(d.y, -1.f), 1.f)) * (1.f / kPi);
+    u -= floorf(u);
+    v -= floorf(v);
+    cx = u * (float)(E.W1 - 1);
+    cy = v * (float)(E.H - 1);
+}
+// radiance from the unit direction d; dLe (optional): dLe[c] = gradient of channel c w.r.t. d
+SDFRT_HD V3 env_eval(const EnvView& E, V3 d, V3* dLe) {
+    float cx, cy;
+    env_coord(E, d, cx, cy);
+    const int ix = min_i((int)floorf(cx), E.W1 - 2), iy = min_i((int)floorf(cy), E.H - 2);
+    const float wx1 = cx - (float)ix, wy1 = cy - (float)iy, wx0 = 1.f - wx1, wy0 = 1.f - wy1;
+    const float* r0 = E.data + ((size_t)iy * E.W1 + ix) * 3;
+    const float* r1 = r0 + (size_t)E.W1 * 3;
+    const V3 v00 = V3{r0[0], r0[1], r0[2]}, v10 = V3{r0[3], r0[4], r0[5]}, v01 = V3{r1[0], r1[1], r1[2]}, v11 = V3{r1[3], r1[4], r1[5]};
+    const V3 Le = (wx0 * wy0) * v00 + (wx1 * wy0) * v10 + (wx0 * wy1) * v01 + (wx1 * wy1) * v11;
+    if (dLe) {
+        const V3 dcx = wy0 * (v10 - v00) + wy1 * (v11 - v01);   // d Le / d cx
+        const V3 dcy = wx0 * (v01 - v00) + wx1 * (v11 - v10);   // d Le / d cy
+        const float r2 = d.x * d.x + d.z * d.z;
+        const float kx = r2 > 0.f ? (float)(E.W1 - 1) * (0.5f / kPi) / r2 : 0.f;
+        const V3 gx = V3{-d.z * kx, 0.f, d.x * kx};             // grad cx
+        const float s2 = 1.f - d.y * d.y;
+        const float ky = s2 > 0.f ? -(float)(E.H - 1) * (1.f / kPi) / sqrtf(s2) : 0.f;
+        const V3 gy = V3{0.f, ky, 0.f};                         // grad cy
+        dLe[0] = dcx.x * gx + dcy.x * gy;
+        dLe[1] = dcx.y * gx + dcy.y * gy;
+        dLe[2] = dcx.z * gx + dcy.z * gy;
+    }
+    return Le;
+}
+SDFRT_HD float env_pdf(const EnvView& E, V3 d) {
+    float cx, cy;
+    env_coord(E, d, cx, cy);
+    const int ix = min_i((int)floorf(cx), E.W1 - 2), iy = min_i((int)floorf(cy), E.H - 2);
+    const float sin_t = sqrtf(fmaxf(0.f, 1.f - d.y * d.y));
+    if (!(sin_t > 0.f)) return 0.f;
+    return E.cell_prob[(size_t)iy * (E.W1 - 1) + ix] * (float)((E.W1 - 1) * (E.H - 1)) / (2.f * kPi * kPi * sin_t);
+}
+// first index with cdf[i] > u  (inclusive CDF, n entries), clamped to n - 1
+SDFRT_HD int cdf_search(const float* cdf, int n, float u) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (cdf[mid] > u) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+SDFRT_HD V3 env_sample(const EnvView& E, float u0, float u1, float& pdf) {
+    const int nx = E.W1 - 1, ny = E.H - 1;
+    const int iy = cdf_search(E.marg_cdf, ny, u1);
+    const float ylo = iy > 0 ? E.marg_cdf[iy - 1] : 0.f;
+    const float fy = fminf(fmaxf((u1 - ylo) / fmaxf(E.marg_cdf[iy] - ylo, 1e-30f), 0.f), 1.f);
+    const float* row = E.cond_cdf + (size_t)iy * nx;
+    const int ix = cdf_search(row, nx, u0);
+    const float xlo = ix > 0 ? row[ix - 1] : 0.f;
+    const float fx = fminf(fmaxf((u0 - xlo) / fmaxf(row[ix] - xlo, 1e-30f), 0.f), 1.f);
+    const float uu = ((float)ix + fx) / (float)nx + 0.5f / (float)nx;
+    const float vv = ((float)iy + fy) / (float)ny;
+    const float theta = vv * kPi, phi = uu * 2.f * kPi;
+    const float st = sinf(theta);
+    const V3 d = V3{sinf(phi) * st, cosf(theta), -cosf(phi) * st};
+    pdf = env_pdf(E, d);
+    return d;
 }
 
 // diffuse reflectance: constant or trilinear gridvolume on [0,1]^3 (clamp); optional gradient wrt p

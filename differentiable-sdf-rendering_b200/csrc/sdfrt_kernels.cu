@@ -350,6 +350,7 @@ struct sdfrt_ctx {
     bool has_xf = false;
     int shadow_origin = 0;   // sdf_direct_reparam props detach_indirect_si (1) / decouple_reparam (2)
     int use_mis = 0;         // ReparamIntegrator prop use_mis (python/integrators/reparam.py:17)
+    float* env_buf = nullptr;   // `envmap` emitter: bitmap + sampling tables in one allocation (sc.E points into it)
     int antithetic = 0;  // ReparamIntegrator.antithetic_sampling (python/integrators/reparam.py:19); not used by sdf_prb_reparam
     bool have_sdf = false;
     // Adjoint state of a VIEW: the lane records of adjoint sweep 1, the scene it was rendered with and the per-view scratch of the
@@ -745,6 +746,8 @@ int enqueue_batch(sdfrt_ctx* ctx, const Sweep& sw, unsigned long long item0, int
 
 int run_sweeps(sdfrt_ctx* ctx, Sweep* sweeps, int ns, cudaStream_t st) {
     SDFRT_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ctx->sc.E.data != nullptr && ctx->sc.integrator == INTEGRATOR_PRB)
+        return fail(ctx, SDFRT_ERR_INVALID, "the envmap emitter is implemented for sdf_direct_reparam only (sdf_prb_reparam: constant emitter)");
     const SensorParams& S = ctx->sc.S;
     int rc;
     unsigned long long Bmax = 0, total_batches = 0;
@@ -1074,7 +1077,7 @@ void sdfrt_destroy(sdfrt_ctx* ctx) {
     for (auto& v : ctx->view) { cudaFree(v.rec); cudaFree(v.film_adj); cudaFree(v.prb_rec); cudaFree(v.brick_a); cudaFree(v.brick_b); cudaFree(v.pix_mask); cudaFree(v.flag_segs); cudaFree(v.flag_dest); cudaFree(v.flag_count); }
     cudaFree(ctx->counters);
     cudaFree(ctx->work);
-    cudaFree(ctx->rows4); cudaFree(ctx->rows8); cudaFree(ctx->brick_raw);
+    cudaFree(ctx->rows4); cudaFree(ctx->rows8); cudaFree(ctx->brick_raw); cudaFree(ctx->env_buf);
     cudaFree(ctx->rd_work); cudaFree(ctx->rd_state); cudaFree(ctx->lap_r);
     for (auto& sc : ctx->scratch) {
         cudaFree(sc.prb_rec); cudaFree(sc.segs); cudaFree(sc.its); cudaFree(sc.ssegs); cudaFree(sc.sinfo); cudaFree(sc.s_its); cudaFree(sc.srec); cudaFree(sc.scount); cudaFree(sc.sbox);
@@ -1201,6 +1204,31 @@ int sdfrt_set_use_mis(sdfrt_ctx* ctx, int enable) {
     ctx->use_mis = enable ? 1 : 0;
     ctx->sc.Sh.use_mis = ctx->use_mis;
     VS(ctx).adj_ready = false;
+    return SDFRT_OK;
+}
+
+int sdfrt_set_envmap_host(sdfrt_ctx* ctx, const float* rgb_host, int width, int height, float scale) {
+    if (!ctx) return SDFRT_ERR_INVALID;
+    SDFRT_CUDA(ctx, cudaSetDevice(ctx->device));
+    SDFRT_CUDA(ctx, cudaDeviceSynchronize());   // views in flight may still read the previous tables
+    cudaFree(ctx->env_buf);
+    ctx->env_buf = nullptr;
+    std::memset(&ctx->sc.E, 0, sizeof(ctx->sc.E));
+    for (auto& v : ctx->view) v.adj_ready = false;
+    if (rgb_host == nullptr) return SDFRT_OK;
+    EnvTables t;
+    if (!build_envmap(rgb_host, width, height, scale, t))
+        return fail(ctx, SDFRT_ERR_INVALID, "bad envmap (need width >= 1, height >= 2, non-negative finite radiance, not all black)");
+    const size_t n_data = t.data.size(), n_m = t.marg_cdf.size(), n_c = t.cond_cdf.size();
+    const size_t total = n_data + n_m + 2 * n_c;
+    SDFRT_CUDA(ctx, cudaMalloc((void**)&ctx->env_buf, total * sizeof(float)));
+    float* d = ctx->env_buf;
+    SDFRT_CUDA(ctx, cudaMemcpy(d, t.data.data(), n_data * sizeof(float), cudaMemcpyHostToDevice));
+    SDFRT_CUDA(ctx, cudaMemcpy(d + n_data, t.marg_cdf.data(), n_m * sizeof(float), cudaMemcpyHostToDevice));
+    SDFRT_CUDA(ctx, cudaMemcpy(d + n_data + n_m, t.cond_cdf.data(), n_c * sizeof(float), cudaMemcpyHostToDevice));
+    SDFRT_CUDA(ctx, cudaMemcpy(d + n_data + n_m + n_c, t.cell_prob.data(), n_c * sizeof(float), cudaMemcpyHostToDevice));
+    ctx->sc.E.data = d; ctx->sc.E.marg_cdf = d + n_data; ctx->sc.E.cond_cdf = d + n_data + n_m; ctx->sc.E.cell_prob = d + n_data + n_m + n_c;
+    ctx->sc.E.W1 = t.W1; ctx->sc.E.H = t.H;
     return SDFRT_OK;
 }
 

@@ -28,6 +28,7 @@ struct SceneParams {
     ShadingParams Sh;
     int integrator;
     PrbParams prb;
+    EnvView E;   // `envmap` emitter (data == nullptr: the constant emitter of Sh)
 };
 
 struct PassParams {
@@ -136,8 +137,21 @@ struct ShadowRay {
     V3 o, d;
     float maxt;
 };
+SDFRT_HD ShadowRay make_shadow_ray_dir(const ShadingParams& Sh, V3 p, V3 n, V3 d_e);
 SDFRT_HD ShadowRay make_shadow_ray(const ShadingParams& Sh, V3 p, V3 n, float u0, float u1) {
-    const V3 d_e = square_to_uniform_sphere(u0, u1);
+    return make_shadow_ray_dir(Sh, p, n, square_to_uniform_sphere(u0, u1));
+}
+// emitter sample of the direct integrator (scene.sample_emitter_direction, python/integrators/sdf_direct_reparam.py:40): uniform sphere
+// for the constant emitter (pdf 1 / 4 pi), importance sampling of the envmap otherwise
+SDFRT_HD ShadowRay sample_emitter_ray(const SceneParams& sc, V3 p, V3 n, float u0, float u1, float& pdf) {
+    if (sc.E.data == nullptr) {
+        pdf = 0.07957747154594767f;
+        return make_shadow_ray(sc.Sh, p, n, u0, u1);
+    }
+    const V3 d_e = env_sample(sc.E, u0, u1, pdf);
+    return make_shadow_ray_dir(sc.Sh, p, n, d_e);
+}
+SDFRT_HD ShadowRay make_shadow_ray_dir(const ShadingParams& Sh, V3 p, V3 n, V3 d_e) {
     const V3 ds_p = p + Sh.env_dist * d_e;
     const float mag = (1.f + fmaxf(fabsf(p.x), fmaxf(fabsf(p.y), fabsf(p.z)))) * kRayEpsilon;
     const float sgn = sign1(dot(n, ds_p - p));
@@ -206,6 +220,34 @@ SDFRT_HD BsdfRay make_bsdf_ray(V3 p, V3 n, float cos_i, float u0, float u1) {
 SDFRT_HD float mis_weight_nee(float cos_o) { return mis_weight(kInv4Pi, cos_o * (1.f / kPi)); }
 SDFRT_HD float mis_weight_bsdf(float pdf) { return mis_weight(pdf, kInv4Pi); }
 
+// The three places radiance enters sdf_direct_reparam, for the constant emitter (Sh.Le) or the envmap (sc.E):
+// an escaped camera ray (python/integrators/sdf_direct_reparam.py:31), the emitter sample (:68-80; emitter_val / ds.pdf, optional
+// power-heuristic weight against the detached BSDF pdf) and an escaped BSDF-sampled ray (:105-107; bsdf_val / bs.pdf = rho).
+SDFRT_HD V3 miss_rgb(const SceneParams& sc, V3 d) {
+    if (sc.E.data == nullptr) return V3{sc.Sh.Le[0], sc.Sh.Le[1], sc.Sh.Le[2]};
+    return env_eval(sc.E, d, nullptr);
+}
+SDFRT_HD V3 nee_rgb(const SceneParams& sc, V3 rho, float cos_o, V3 d_s, float pdf, bool mis) {
+    if (sc.E.data == nullptr) {
+        float k = cos_o * 4.f;  // (rho / pi) * cos_o * Le / (1 / (4 pi))
+        if (mis) k *= mis_weight_nee(cos_o);
+        return V3{rho.x * k * sc.Sh.Le[0], rho.y * k * sc.Sh.Le[1], rho.z * k * sc.Sh.Le[2]};
+    }
+    float k = cos_o * (1.f / kPi) / pdf;
+    if (mis) k *= mis_weight(pdf, cos_o * (1.f / kPi));
+    const V3 Le = env_eval(sc.E, d_s, nullptr);
+    return V3{rho.x * k * Le.x, rho.y * k * Le.y, rho.z * k * Le.z};
+}
+SDFRT_HD V3 bsdf_rgb(const SceneParams& sc, V3 rho, V3 d_b, float bs_pdf) {
+    if (sc.E.data == nullptr) {
+        const float wb = mis_weight_bsdf(bs_pdf);
+        return V3{rho.x * wb * sc.Sh.Le[0], rho.y * wb * sc.Sh.Le[1], rho.z * wb * sc.Sh.Le[2]};
+    }
+    const float wb = mis_weight(bs_pdf, env_pdf(sc.E, d_b));
+    const V3 Le = env_eval(sc.E, d_b, nullptr);
+    return V3{rho.x * wb * Le.x, rho.y * wb * Le.y, rho.z * wb * Le.z};
+}
+
 // ------------------------------------------------------------------------------------------------
 // forward lane
 // ------------------------------------------------------------------------------------------------
@@ -241,7 +283,7 @@ SDFRT_HD void lane_forward(const SceneParams& sc, const PassParams& ps, unsigned
         }
     } else {
         if (!hit) {
-            if (!sc.Sh.hide_emitters) rgb = V3{sc.Sh.Le[0], sc.Sh.Le[1], sc.Sh.Le[2]};
+            if (!sc.Sh.hide_emitters) rgb = miss_rgb(sc, d0);
         } else {
             const V3 p = o + tr.its_t * d0;
             float phi; V3 g; S3 H;
@@ -250,11 +292,12 @@ SDFRT_HD void lane_forward(const SceneParams& sc, const PassParams& ps, unsigned
             const V3 n = normalize(g);
             const float cos_i = -dot(n, d0);
             const float u0 = pcg_next_f32(cs.rng), u1 = pcg_next_f32(cs.rng);
-            const ShadowRay sr = make_shadow_ray(sc.Sh, p, n, u0, u1);
+            float pdf_e;
+            const ShadowRay sr = sample_emitter_ray(sc, p, n, u0, u1, pdf_e);
             const float cos_o = dot(n, sr.d);
             // the reference marches every shadow ray; a lane whose BSDF gate is closed contributes
             // exactly zero whatever the march returns, so it is skipped here.
-            if ((cos_i > 0.f) & (cos_o > 0.f)) {
+            if ((cos_i > 0.f) & (cos_o > 0.f) & (pdf_e > 0.f)) {
                 float its_s;
                 int ns = 0;
                 if (DIFF && reparam_at_depth(sc.W, 1)) {
@@ -269,9 +312,7 @@ SDFRT_HD void lane_forward(const SceneParams& sc, const PassParams& ps, unsigned
                     s_state = 1.f;
                     const V3 rho = eval_albedo(sc.A, p, nullptr, nullptr);
                     st.n_albedo += (sc.A.data != nullptr);
-                    float k = cos_o * 4.f;  // (rho / pi) * cos_o * Le / (1 / (4 pi))
-                    if (sc.Sh.use_mis) k *= mis_weight_nee(cos_o);   // power heuristic against the detached BSDF pdf (:76-79)
-                    rgb = V3{rho.x * k * sc.Sh.Le[0], rho.y * k * sc.Sh.Le[1], rho.z * k * sc.Sh.Le[2]};
+                    rgb = nee_rgb(sc, rho, cos_o, sr.d, pdf_e, sc.Sh.use_mis != 0);
                 }
             }
             if (sc.Sh.use_mis) {   // BSDF sampling (python/integrators/sdf_direct_reparam.py:87-107)
@@ -293,8 +334,7 @@ SDFRT_HD void lane_forward(const SceneParams& sc, const PassParams& ps, unsigned
                         b_state = 1.f;
                         const V3 rho = eval_albedo(sc.A, p, nullptr, nullptr);
                         st.n_albedo += (sc.A.data != nullptr);
-                        const float wb = mis_weight_bsdf(br.pdf);
-                        rgb += V3{rho.x * wb * sc.Sh.Le[0], rho.y * wb * sc.Sh.Le[1], rho.z * wb * sc.Sh.Le[2]};
+                        rgb += bsdf_rgb(sc, rho, br.d, br.pdf);
                     }
                 }
             }
@@ -466,6 +506,10 @@ SDFRT_HD void lane_backward(const SceneParams& sc, const PassParams& ps, unsigne
     V3 rgb_b = v3(0.f);
     BsdfRay br; br.active = false; br.o = v3(0.f); br.d = v3(0.f, 0.f, 1.f); br.pdf = 0.f;
     const bool mis = sc.Sh.use_mis && sc.integrator == INTEGRATOR_DIRECT;
+    const bool env = sc.E.data != nullptr && sc.integrator == INTEGRATOR_DIRECT;
+    V3 K = v3(0.f), Kb = v3(0.f);          // rgb_c = rho_c * (cos_o * K_c + Kb_c)
+    V3 dLe_0[3], dLe_s[3], dLe_b[3];       // envmap: d Le_c / d direction for the camera / emitter-sampled / BSDF-sampled ray
+    float pdf_e = 0.f, k_env = 0.f;
     if (hit && sc.integrator != INTEGRATOR_SILHOUETTE) {
         p = o + its_t * d0;
         float phi;
@@ -482,27 +526,45 @@ SDFRT_HD void lane_backward(const SceneParams& sc, const PassParams& ps, unsigne
         }
     } else {
         if (!hit) {
-            if (!sc.Sh.hide_emitters) rgb = V3{sc.Sh.Le[0], sc.Sh.Le[1], sc.Sh.Le[2]};
+            if (!sc.Sh.hide_emitters) {
+                rgb = miss_rgb(sc, d0);
+                if (env) (void)env_eval(sc.E, d0, dLe_0);
+            }
         } else {
             nee = r[REC_S_STATE * rec_stride] != 0.f;
             bsdf_hit_env = mis && r[REC_B_STATE * rec_stride] != 0.f;
             if (nee | bsdf_hit_env) {
                 const float u0 = pcg_next_f32(cs.rng), u1 = pcg_next_f32(cs.rng);
-                sr = make_shadow_ray(sc.Sh, p, n, u0, u1);
+                sr = sample_emitter_ray(sc, p, n, u0, u1, pdf_e);
                 cos_o = dot(n, sr.d);
                 rho = eval_albedo(sc.A, p, &taps, drho);
             }
             if (nee) {
-                if (mis) w_nee = mis_weight_nee(cos_o);
-                const float k = cos_o * 4.f * w_nee;
-                rgb = V3{rho.x * k * sc.Sh.Le[0], rho.y * k * sc.Sh.Le[1], rho.z * k * sc.Sh.Le[2]};
+                // rgb_c = rho_c * cos_o * K_c;  K = 4 w Le (constant emitter) or w Le(d_s) / (pi pdf) (envmap), w detached
+                if (!env) {
+                    if (mis) w_nee = mis_weight_nee(cos_o);
+                    const float k = cos_o * 4.f * w_nee;
+                    rgb = V3{rho.x * k * sc.Sh.Le[0], rho.y * k * sc.Sh.Le[1], rho.z * k * sc.Sh.Le[2]};
+                    K = V3{4.f * w_nee * sc.Sh.Le[0], 4.f * w_nee * sc.Sh.Le[1], 4.f * w_nee * sc.Sh.Le[2]};
+                } else {
+                    if (mis) w_nee = mis_weight(pdf_e, cos_o * (1.f / kPi));
+                    k_env = (1.f / kPi) / pdf_e * w_nee;
+                    K = k_env * env_eval(sc.E, sr.d, dLe_s);
+                    rgb = V3{rho.x * cos_o * K.x, rho.y * cos_o * K.y, rho.z * cos_o * K.z};
+                }
             }
             if (bsdf_hit_env) {
                 (void)pcg_next_f32(cs.rng);
                 const float b0 = pcg_next_f32(cs.rng), b1 = pcg_next_f32(cs.rng);
                 br = make_bsdf_ray(p, n, -dot(n, d0), b0, b1);
-                w_b = mis_weight_bsdf(br.pdf);
-                rgb_b = V3{rho.x * w_b * sc.Sh.Le[0], rho.y * w_b * sc.Sh.Le[1], rho.z * w_b * sc.Sh.Le[2]};
+                if (!env) {
+                    w_b = mis_weight_bsdf(br.pdf);
+                    Kb = V3{w_b * sc.Sh.Le[0], w_b * sc.Sh.Le[1], w_b * sc.Sh.Le[2]};
+                } else {
+                    w_b = mis_weight(br.pdf, env_pdf(sc.E, br.d));
+                    Kb = w_b * env_eval(sc.E, br.d, dLe_b);
+                }
+                rgb_b = V3{rho.x * Kb.x, rho.y * Kb.y, rho.z * Kb.z};
                 rgb += rgb_b;
             }
         }
@@ -572,6 +634,8 @@ SDFRT_HD void lane_backward(const SceneParams& sc, const PassParams& ps, unsigne
     V3 d_hat = V3{sc.S.R[0][0] * ref_hat.x + sc.S.R[0][1] * ref_hat.y + sc.S.R[0][2] * ref_hat.z,
                   sc.S.R[1][0] * ref_hat.x + sc.S.R[1][1] * ref_hat.y + sc.S.R[1][2] * ref_hat.z,
                   sc.S.R[2][0] * ref_hat.x + sc.S.R[2][1] * ref_hat.y + sc.S.R[2][2] * ref_hat.z};
+    if (env && !hit && !sc.Sh.hide_emitters)   // escaped camera ray: the envmap lookup follows the reparameterised direction
+        d_hat += c_hat.x * dLe_0[0] + c_hat.y * dLe_0[1] + c_hat.z * dLe_0[2];
 
     // ---- shading -> surface interaction -------------------------------------------------------------
     if (hit && sc.integrator != INTEGRATOR_SILHOUETTE) {
@@ -580,14 +644,17 @@ SDFRT_HD void lane_backward(const SceneParams& sc, const PassParams& ps, unsigne
             if (shade > 0.f) n_hat = v3((c_hat.x + c_hat.y + c_hat.z) * 0.57735026918962576f);
         } else if (nee | bsdf_hit_env) {
             // rgb_c = div * (div_s * rho_c * cos_o * 4 Le_c * w_nee  +  div_b * rho_c * Le_c * w_b); the MIS weights are detached
-            const V3 K = nee ? V3{4.f * w_nee * sc.Sh.Le[0], 4.f * w_nee * sc.Sh.Le[1], 4.f * w_nee * sc.Sh.Le[2]} : v3(0.f);
             const float cos_hat = c_hat.x * rho.x * K.x + c_hat.y * rho.y * K.y + c_hat.z * rho.z * K.z;
             n_hat = cos_hat * sr.d;
-            const V3 ds_hat = cos_hat * n;
+            V3 ds_hat = cos_hat * n;
+            V3 db_hat = v3(0.f);
+            if (env) {   // the envmap is looked up with the attached (reparameterised) directions
+                if (nee) ds_hat += (cos_o * k_env) * ((c_hat.x * rho.x) * dLe_s[0] + (c_hat.y * rho.y) * dLe_s[1] + (c_hat.z * rho.z) * dLe_s[2]);
+                if (bsdf_hit_env) db_hat = w_b * ((c_hat.x * rho.x) * dLe_b[0] + (c_hat.y * rho.y) * dLe_b[1] + (c_hat.z * rho.z) * dLe_b[2]);
+            }
             const float div_s_hat = crgb - dot(c_hat, rgb_b);   // the emitter-sampled part only
             // albedo (both strategies)
-            const V3 rho_hat = V3{c_hat.x * (K.x * cos_o + w_b * sc.Sh.Le[0]), c_hat.y * (K.y * cos_o + w_b * sc.Sh.Le[1]),
-                                  c_hat.z * (K.z * cos_o + w_b * sc.Sh.Le[2])};
+            const V3 rho_hat = V3{c_hat.x * (K.x * cos_o + Kb.x), c_hat.y * (K.y * cos_o + Kb.y), c_hat.z * (K.z * cos_o + Kb.z)};
             if (sc.A.data != nullptr) {
                 st.n_albedo += 1;
                 p_hat += rho_hat.x * drho[0] + rho_hat.y * drho[1] + rho_hat.z * drho[2];
@@ -610,7 +677,7 @@ SDFRT_HD void lane_backward(const SceneParams& sc, const PassParams& ps, unsigne
                 st.n_hess += isfinite(tau);
                 if (ws.active) {
                     const float div_b_hat = dot(c_hat, rgb_b);
-                    const float phi_hat = div_b_hat * ws.cphi_div;
+                    const float phi_hat = div_b_hat * ws.cphi_div + dot(db_hat, ws.cphi_dir);
                     const V3 g_hat = div_b_hat * ws.cg_div;
                     if (isfinite(phi_hat) & isfinite(g_hat.x + g_hat.y + g_hat.z)) {
                         push_site(sites, br.o + tau * br.d, phi_hat, g_hat);

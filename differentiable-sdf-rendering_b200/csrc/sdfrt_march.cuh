@@ -647,7 +647,7 @@ __global__ void __launch_bounds__(256, 3) k_shade(const __grid_constant__ SceneP
             if (sc.integrator == INTEGRATOR_SILHOUETTE) {
                 rgb = v3(hit ? 1.f : 0.f);
             } else if (!hit) {
-                if (sc.integrator == INTEGRATOR_DIRECT && !sc.Sh.hide_emitters) rgb = V3{sc.Sh.Le[0], sc.Sh.Le[1], sc.Sh.Le[2]};
+                if (sc.integrator == INTEGRATOR_DIRECT && !sc.Sh.hide_emitters) rgb = miss_rgb(sc, r.d);
             } else {
                 const V3 p = r.o + its_t * r.d;
                 float phi; V3 g; S3 H;
@@ -661,15 +661,15 @@ __global__ void __launch_bounds__(256, 3) k_shade(const __grid_constant__ SceneP
                     Pcg32 rng = sampler_seed(ps.seed, (uint32_t)decode_item(ps, item0 + i).lane);
                     (void)pcg_next_u32(rng); (void)pcg_next_u32(rng); (void)pcg_next_u32(rng);
                     const float u0 = pcg_next_f32(rng), u1 = pcg_next_f32(rng);
-                    const ShadowRay sr = make_shadow_ray(sc.Sh, p, nrm, u0, u1);
+                    float pdf_e;
+                    const ShadowRay sr = sample_emitter_ray(sc, p, nrm, u0, u1, pdf_e);
                     const float cos_o = dot(nrm, sr.d);
                     // a shadow ray whose BSDF gate is closed contributes exactly zero whatever it hits: not traced
-                    if ((cos_i > 0.f) & (cos_o > 0.f)) {
+                    if ((cos_i > 0.f) & (cos_o > 0.f) & (pdf_e > 0.f)) {
                         const V3 rho = eval_albedo(sc.A, p, nullptr, nullptr);
                         n_alb += (sc.A.data != nullptr);
-                        float k = cos_o * 4.f;  // (rho / pi) cos_o Le / (1 / 4 pi)
-                        if (mis) k *= mis_weight_nee(cos_o);
-                        info = make_float4(rho.x * k * sc.Sh.Le[0], rho.y * k * sc.Sh.Le[1], rho.z * k * sc.Sh.Le[2], __uint_as_float(i));
+                        const V3 c = nee_rgb(sc, rho, cos_o, sr.d, pdf_e, mis);
+                        info = make_float4(c.x, c.y, c.z, __uint_as_float(i));
                         sseg = make_seg(sc.T, sr.o, sr.d, sr.maxt);
                         push = true;
                         if (q.box != nullptr) {   // (boxes are staged for the emitter-sampled rays only)
@@ -685,10 +685,9 @@ __global__ void __launch_bounds__(256, 3) k_shade(const __grid_constant__ SceneP
                         if (br.active) {
                             const V3 rho = eval_albedo(sc.A, p, nullptr, nullptr);
                             n_alb += (sc.A.data != nullptr);
-                            const float wb = mis_weight_bsdf(br.pdf);
+                            const V3 c = bsdf_rgb(sc, rho, br.d, br.pdf);
                             // bit 31 of the item word: the sample's weight channel is splatted with its emitter-sampled part
-                            info_b = make_float4(rho.x * wb * sc.Sh.Le[0], rho.y * wb * sc.Sh.Le[1], rho.z * wb * sc.Sh.Le[2],
-                                                 __uint_as_float(i | (push ? 0x80000000u : 0u)));
+                            info_b = make_float4(c.x, c.y, c.z, __uint_as_float(i | (push ? 0x80000000u : 0u)));
                             bseg = make_seg(sc.T, br.o, br.d, INFINITY);
                             push_b = true;
                         }

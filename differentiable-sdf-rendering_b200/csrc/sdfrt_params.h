@@ -3,6 +3,7 @@
 #pragma once
 #include <algorithm>
 #include <cmath>
+#include <vector>
 #include <cstring>
 
 #include "../../include/sdfrt.h"
@@ -140,6 +141,51 @@ inline ShadingParams make_shading(const sdfrt_shading& s) {
     o.shadow_origin = 0;
     o.use_mis = 0;
     return o;
+}
+// host tables of the `envmap` emitter (oracle/ref_semantics.md S18; oracle/sdf_oracle.py EnvMap): the bitmap with its first column
+// repeated, and the piecewise-constant sampling distribution over the bilinear cells (computed in double, stored as float)
+struct EnvTables {
+    std::vector<float> data, marg_cdf, cond_cdf, cell_prob;
+    int W1 = 0, H = 0;
+};
+inline bool build_envmap(const float* rgb, int w, int h, float scale, EnvTables& t) {
+    if (rgb == nullptr || w < 1 || h < 2) return false;
+    t.W1 = w + 1; t.H = h;
+    t.data.resize((size_t)h * t.W1 * 3);
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < t.W1; ++x)
+            for (int c = 0; c < 3; ++c) t.data[((size_t)y * t.W1 + x) * 3 + c] = rgb[((size_t)y * w + (x % w)) * 3 + c] * scale;
+    const int nx = w, ny = h - 1;
+    std::vector<double> wgt((size_t)nx * ny), rows(ny, 0.0);
+    auto lum = [&](int y, int x) {
+        const float* q = &t.data[((size_t)y * t.W1 + x) * 3];
+        return 0.212671 * (double)q[0] + 0.715160 * (double)q[1] + 0.072169 * (double)q[2];
+    };
+    double total = 0.0;
+    for (int y = 0; y < ny; ++y) {
+        const double st = std::sin(((double)y + 0.5) / (double)ny * 3.14159265358979323846);
+        for (int x = 0; x < nx; ++x) {
+            const double v = 0.25 * (lum(y, x) + lum(y, x + 1) + lum(y + 1, x) + lum(y + 1, x + 1)) * st;
+            if (!(v >= 0.0)) return false;   // negative or NaN radiance
+            wgt[(size_t)y * nx + x] = v;
+            rows[y] += v;
+        }
+        total += rows[y];
+    }
+    if (!(total > 0.0)) return false;
+    t.cell_prob.resize((size_t)nx * ny); t.cond_cdf.resize((size_t)nx * ny); t.marg_cdf.resize(ny);
+    double acc = 0.0;
+    for (int y = 0; y < ny; ++y) {
+        acc += rows[y] / total;
+        t.marg_cdf[y] = (float)acc;
+        double a = 0.0;
+        for (int x = 0; x < nx; ++x) {
+            t.cell_prob[(size_t)y * nx + x] = (float)(wgt[(size_t)y * nx + x] / total);
+            a += wgt[(size_t)y * nx + x] / std::max(rows[y], 1e-300);
+            t.cond_cdf[(size_t)y * nx + x] = (float)a;
+        }
+    }
+    return true;
 }
 inline PassParams make_pass(const SensorParams& S, uint32_t seed, int spp, int rank, int world, int antithetic = 0) {
     PassParams p;

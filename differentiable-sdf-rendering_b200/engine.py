@@ -123,6 +123,17 @@ class Context:
     def set_use_mis(self, enable):
         check(self.ctx, self.lib.sdfrt_set_use_mis(self.ctx, int(bool(enable))))
 
+    def set_envmap(self, rgb=None, scale=1.0):
+        """`envmap` emitter from an (H, W, 3) lat-long bitmap (numpy / CPU tensor; row 0 = +y pole), or None for the constant emitter
+        of set_shading.  sdf_direct_reparam only.  Copies the bitmap; synchronises the device."""
+        if rgb is None:
+            check(self.ctx, self.lib.sdfrt_set_envmap_host(self.ctx, None, 0, 0, 1.0))
+            return
+        a = np.ascontiguousarray(rgb.detach().cpu().numpy() if torch.is_tensor(rgb) else rgb, dtype=np.float32)
+        if a.ndim != 3 or a.shape[2] != 3:
+            raise ValueError("envmap must have shape (H, W, 3)")
+        check(self.ctx, self.lib.sdfrt_set_envmap_host(self.ctx, a.ctypes.data_as(C.c_void_p), a.shape[1], a.shape[0], float(scale)))
+
     def set_shadow_origin(self, mode):
         check(self.ctx, self.lib.sdfrt_set_shadow_origin(self.ctx, int(mode)))
 

@@ -148,6 +148,16 @@ int sdfrt_set_shadow_origin(sdfrt_ctx* ctx, int mode);
  * and a second, BSDF-sampled (cosine-hemisphere) ray is traced from every hit; rays that escape see the environment emitter.  Its warp
  * record (reparameterised like the shadow ray, depth 1) goes to nine more rows of the lane records.  Default off (the reference's). */
 int sdfrt_set_use_mis(sdfrt_ctx* ctx, int enable);
+
+/* `envmap` emitter instead of the constant one (the scenes of the reference's figures light the object with a lat-long bitmap,
+ * <emitter type="envmap"> with the identity to_world; here the bitmap comes as an array).  rgb_host: (height, width, 3) floats in
+ * HOST memory, row 0 = +y pole, copied (and scaled by `scale`) into context-owned device memory; NULL: back to the constant emitter
+ * of sdfrt_set_shading.  Lookup: Mitsuba's envmap eval (uv = (atan2(d.x, -d.z) / 2pi, acos(d.y) / pi), bilinear, first column
+ * repeated), followed with the reparameterised directions, so dLe/dd enters the adjoint (python/integrators/sdf_direct_reparam.py:31,
+ * 62-70,105).  Emitter sampling: piecewise-constant over the bilinear cells by luminance x sin(theta) (oracle/ref_semantics.md S18 --
+ * Mitsuba's hierarchical sample warp is not restated; the estimator is unbiased either way).  sdf_direct_reparam only: a render with
+ * sdf_prb_reparam fails with SDFRT_ERR_INVALID while an envmap is bound.  Synchronises the device. */
+int sdfrt_set_envmap_host(sdfrt_ctx* ctx, const float* rgb_host, int width, int height, float scale);
 void sdfrt_prb_defaults(sdfrt_prb_params* p);
 int sdfrt_set_prb(sdfrt_ctx* ctx, const sdfrt_prb_params* p);      /* used when the integrator is SDFRT_INTEGRATOR_PRB */
 /* multi-GPU ray partition: the film rows (border included) are cut into bands of 8 rows; this context renders the

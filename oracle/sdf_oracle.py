@@ -738,6 +738,78 @@ def square_to_uniform_sphere(u):
     return torch.stack([r * torch.cos(phi), r * torch.sin(phi), z], -1)
 
 
+class EnvMap:
+    """Mitsuba's `envmap` emitter (lat-long bitmap, identity to_world), restated -- oracle/ref_semantics.md S18.
+
+    eval: direction d -> uv = (atan2(d.x, -d.z) / 2pi, acos(d.y) / pi); the bitmap is stored with its first column repeated at the end
+    (res = (W + 1, H)); uv.x -= 0.5 / (res.x - 1); uv -= floor(uv); uv *= res - 1; bilinear interpolation of the four texels around it.
+    sample_direction: Mitsuba importance-samples luminance * sin(theta) with a hierarchical sample warp (`Hierarchical2D`); restated
+    here as a PIECEWISE-CONSTANT distribution over the (res.x - 1) x (res.y - 1) bilinear cells (cell weight = mean luminance of its
+    four corners * sin(theta) at the cell centre), uniform inside a cell -- the same target density up to the interpolation inside a
+    cell, a different sample warp (deliberate deviation, the reference's estimator is unbiased either way).
+    pdf over solid angle = cell probability * (res.x - 1)(res.y - 1) / (2 pi^2 sin theta)."""
+
+    def __init__(self, rgb, scale=1.0):
+        rgb = torch.as_tensor(rgb, dtype=torch.float64) * scale          # (H, W, 3)
+        self.data = torch.cat([rgb, rgb[:, :1]], 1).contiguous()       # (H, W + 1, 3)
+        self.H, self.W1 = self.data.shape[0], self.data.shape[1]
+        lum = (self.data * torch.tensor([0.212671, 0.715160, 0.072169], dtype=torch.float64)).sum(-1)
+        cell = 0.25 * (lum[:-1, :-1] + lum[:-1, 1:] + lum[1:, :-1] + lum[1:, 1:])       # (H - 1, W)
+        theta = (torch.arange(self.H - 1, dtype=torch.float64) + 0.5) / (self.H - 1) * math.pi
+        w = cell * torch.sin(theta)[:, None]
+        w = w / w.sum()
+        self.cell_prob = w                                               # (H - 1, W)
+        self.marg_cdf = torch.cumsum(w.sum(1), 0)                        # rows
+        self.cond_cdf = torch.cumsum(w / w.sum(1, keepdim=True).clamp_min(1e-300), 1)
+
+    def _coord(self, d):
+        """direction (unit) -> lookup coordinate c in [0, W) x [0, H - 1]."""
+        u = torch.atan2(d[:, 0], -d[:, 2]) * (0.5 / math.pi)
+        v = torch.acos(d[:, 1].clamp(-1.0, 1.0)) * (1.0 / math.pi)
+        u = u - 0.5 / (self.W1 - 1)
+        u = u - torch.floor(u)
+        v = v - torch.floor(v)
+        return u * (self.W1 - 1), v * (self.H - 1)
+
+    def eval(self, d):
+        """Radiance arriving from direction d (N, 3) (unit vectors; differentiable w.r.t. d)."""
+        cx, cy = self._coord(d)
+        ix = torch.minimum(torch.floor(cx.detach()), torch.full_like(cx, self.W1 - 2)).long()
+        iy = torch.minimum(torch.floor(cy.detach()), torch.full_like(cy, self.H - 2)).long()
+        wx1, wy1 = cx - ix, cy - iy
+        wx0, wy0 = 1 - wx1, 1 - wy1
+        D = self.data.to(d.dtype)
+        return (D[iy, ix] * (wx0 * wy0)[:, None] + D[iy, ix + 1] * (wx1 * wy0)[:, None] +
+                D[iy + 1, ix] * (wx0 * wy1)[:, None] + D[iy + 1, ix + 1] * (wx1 * wy1)[:, None])
+
+    def pdf(self, d):
+        cx, cy = self._coord(d.detach())
+        ix = torch.minimum(torch.floor(cx), torch.full_like(cx, self.W1 - 2)).long()
+        iy = torch.minimum(torch.floor(cy), torch.full_like(cy, self.H - 2)).long()
+        sin_t = torch.sqrt((1 - d[:, 1].detach() ** 2).clamp_min(0.0))
+        p = self.cell_prob.to(d.dtype)[iy, ix] * ((self.W1 - 1) * (self.H - 1)) / (2 * math.pi ** 2 * sin_t.clamp_min(1e-30))
+        return torch.where(sin_t > 0, p, torch.zeros_like(p))
+
+    def sample(self, u):
+        """u (N, 2) -> (direction, pdf over solid angle)."""
+        dt = u.dtype
+        iy = torch.searchsorted(self.marg_cdf.to(dt), u[:, 1].contiguous(), right=True).clamp_max(self.H - 2)
+        lo = torch.where(iy > 0, self.marg_cdf.to(dt)[(iy - 1).clamp_min(0)], torch.zeros_like(u[:, 1]))
+        fy = (u[:, 1] - lo) / (self.marg_cdf.to(dt)[iy] - lo).clamp_min(1e-300)
+        cc = self.cond_cdf.to(dt)[iy]                                    # (N, W)
+        ix = torch.searchsorted(cc, u[:, 0:1].contiguous(), right=True).squeeze(1).clamp_max(self.W1 - 2)
+        lo = torch.where(ix > 0, cc.gather(1, (ix - 1).clamp_min(0)[:, None]).squeeze(1), torch.zeros_like(u[:, 0]))
+        hi = cc.gather(1, ix[:, None]).squeeze(1)
+        fx = (u[:, 0] - lo) / (hi - lo).clamp_min(1e-300)
+        cx, cy = ix.to(dt) + fx.clamp(0, 1), iy.to(dt) + fy.clamp(0, 1)
+        uu = cx / (self.W1 - 1) + 0.5 / (self.W1 - 1)
+        vv = cy / (self.H - 1)
+        theta, phi = vv * math.pi, uu * 2 * math.pi
+        st = torch.sin(theta)
+        d = torch.stack([torch.sin(phi) * st, torch.cos(theta), -torch.cos(phi) * st], -1)
+        return d, self.pdf(d)
+
+
 @dataclass
 class Scene:
     """Minimal stand-in for the Mitsuba scene the integrators query."""
@@ -751,6 +823,7 @@ class Scene:
     use_mis: bool = False                     # ReparamIntegrator prop (python/integrators/reparam.py:17): BSDF-sampling MIS branch
     detach_indirect_si: bool = False          # sdf_direct_reparam props (python/integrators/sdf_direct_reparam.py:13-14,44-49)
     decouple_reparam: bool = False
+    envmap: 'EnvMap' = None                   # `envmap` emitter instead of the constant one (direct integrator only)
 
 
 def eval_albedo(scene, p):
@@ -828,9 +901,12 @@ def sample_direct(scene, warp_field, sampler, o, d, maxt, reparam_mode):
     its_t, d_att, det, _ = _ray_intersect(scene, warp_field, o, d, maxt, 0, reparametrize)
     valid = torch.isfinite(its_t)
     Le = torch.as_tensor(scene.env_radiance, dtype=dtype)
-    # result += throughput * si.emitter(scene).eval(si): environment for misses (:24-31)
+    env = scene.envmap
+    # result += throughput * si.emitter(scene).eval(si): environment for misses (:24-31); si.wi = -ray.d of the (attached) primary
+    # direction (python/shapes.py:362), so an `envmap` emitter is evaluated differentiably w.r.t. the warped direction
     miss_vis = (~valid) & (not scene.hide_emitters)
-    result = det[:, None] * torch.where(miss_vis[:, None], Le.expand(N, 3), torch.zeros(N, 3, dtype=dtype))
+    Le_miss = Le.expand(N, 3) if env is None else env.eval(d_att)
+    result = det[:, None] * torch.where(miss_vis[:, None], Le_miss, torch.zeros(N, 3, dtype=dtype))
 
     # ---- emitter sampling (:36-84), on the lanes with a valid si ----
     u = sampler.next_2d()
@@ -841,9 +917,12 @@ def sample_direct(scene, warp_field, sampler, o, d, maxt, reparam_mode):
     # si_d = compute_surface_interaction(detach(ray), detach(its_t)) has the same values (python/warp.py:121)
     p, n = si['p'], si['n']
     with torch.no_grad():
-        d_e = square_to_uniform_sphere(u[h])
+        if env is None:
+            d_e = square_to_uniform_sphere(u[h])
+            ds_pdf = torch.full((h.numel(),), 1.0 / (4 * math.pi), dtype=dtype)
+        else:                          # scene.sample_emitter_direction -> envmap.sample_direction (:40)
+            d_e, ds_pdf = env.sample(u[h])
         ds_p = p.detach() + d_e * scene.env_dist
-        ds_pdf = 1.0 / (4 * math.pi)
         # si.spawn_ray_to(ds.p): offset along detached n, maxt shortened
         mag = (1 + p.detach().abs().max(-1).values) * RAY_EPSILON
         sgn = dr_sign(dot(n.detach(), ds_p - p.detach()))
@@ -863,14 +942,17 @@ def sample_direct(scene, warp_field, sampler, o, d, maxt, reparam_mode):
     occluded = torch.isfinite(its_s)
     cos_o = dot(n, d_s_att)           # wo = si.to_local(shadow_ray.d); only z enters the diffuse BSDF
     cos_i = si['wi_z']
-    emitter_val = Le / ds_pdf         # constant emitter eval / pdf (:68-74)
+    # ds.emitter.eval(si_e) with si_e.wi = -shadow_ray.d (:61-68): for an envmap this follows the warped shadow direction; / ds.pdf (:74)
+    Le_s = Le.expand(h.numel(), 3) if env is None else env.eval(d_s_att)
+    pdf_ok = ds_pdf > 0
+    emitter_val = torch.where(pdf_ok[:, None], Le_s / torch.where(pdf_ok, ds_pdf, torch.ones_like(ds_pdf))[:, None], torch.zeros_like(Le_s))
     rho = eval_albedo(scene, p)
-    gate = (~occluded) & (cos_i > 0) & (cos_o > 0)
+    gate = (~occluded) & (cos_i > 0) & (cos_o > 0) & pdf_ok
     bsdf_val = rho / math.pi * cos_o[:, None]
     nee = bsdf_val * emitter_val
     if scene.use_mis:  # :77-79: power heuristic against the (detached) BSDF pdf of the sampled direction
         bsdf_pdf = torch.where((cos_i > 0) & (cos_o > 0), cos_o.detach() / math.pi, torch.zeros_like(cos_o)).detach()
-        nee = nee * mis_weight(torch.full_like(bsdf_pdf, ds_pdf), bsdf_pdf)[:, None]
+        nee = nee * mis_weight(ds_pdf, bsdf_pdf)[:, None]
     contrib = det[h, None] * nee * det_e[:, None]
     contrib = torch.where(gate[:, None], contrib, torch.zeros_like(contrib))
     result = result.index_add(0, h, contrib)
@@ -886,14 +968,17 @@ def sample_direct(scene, warp_field, sampler, o, d, maxt, reparam_mode):
             fs, ft = sh_frame(nd)
             wo_w = fs * wo_l[:, 0:1] + ft * wo_l[:, 1:2] + nd * wo_l[:, 2:3]   # si_d.to_world(bs.wo)
         o_b = _spawn_offset(p, n, wo_w)                              # si.spawn_ray (attached origin), d detached (:93-94)
-        its_b, _d_b, det_b, _ = _ray_intersect(scene, warp_field, o_b, wo_w, torch.full_like(bs_pdf, INF), 1, reparametrize, active=act)
+        its_b, d_b_att, det_b, _ = _ray_intersect(scene, warp_field, o_b, wo_w, torch.full_like(bs_pdf, INF), 1, reparametrize, active=act)
         escaped = ~torch.isfinite(its_b)
         # bsdf.eval(ctx, si, bs.wo): local direction, so only rho(p) carries a derivative (:97)
         bsdf_val_b = torch.where(act[:, None], rho / math.pi * wo_l[:, 2:3], torch.zeros_like(rho))
-        emitter_pdf = torch.where(escaped, torch.full_like(bs_pdf, 1.0 / (4 * math.pi)), torch.zeros_like(bs_pdf))
+        env_pdf = torch.full_like(bs_pdf, 1.0 / (4 * math.pi)) if env is None else env.pdf(wo_w)   # scene.pdf_emitter_direction (:101-103)
+        emitter_pdf = torch.where(escaped, env_pdf, torch.zeros_like(bs_pdf))
         w_b = mis_weight(bs_pdf, emitter_pdf)
         inv_pdf = torch.where(bs_pdf > 0, 1 / torch.where(bs_pdf > 0, bs_pdf, torch.ones_like(bs_pdf)), torch.zeros_like(bs_pdf))
-        contrib_b = det[h, None] * bsdf_val_b * inv_pdf[:, None] * Le * w_b[:, None] * det_b[:, None]
+        # si_bsdf.emitter(scene).eval(si_bsdf) (:105): si_bsdf.wi = -bsdf_ray.d of the escaped, reparameterised ray
+        Le_b = Le.expand(h.numel(), 3) if env is None else env.eval(d_b_att)
+        contrib_b = det[h, None] * bsdf_val_b * inv_pdf[:, None] * Le_b * w_b[:, None] * det_b[:, None]
         contrib_b = torch.where((act & escaped)[:, None], contrib_b, torch.zeros_like(contrib_b))
         result = result.index_add(0, h, contrib_b)
     return result, d_att, det

@@ -33,6 +33,7 @@ class HostContext:
         self.integrator = 2
         self.antithetic = False
         self.use_mis = False
+        self.envmap = None
         self.shadow_origin = 0
         self.prb = dict(max_depth=4, rr_depth=5)
         self.rank, self.world = 0, 1
@@ -82,6 +83,9 @@ class HostContext:
     def set_shadow_origin(self, mode):
         self.shadow_origin = int(mode)
 
+    def set_envmap(self, rgb=None, scale=1.0):
+        self.envmap = None if rgb is None else (np.array(rgb.detach().cpu().numpy() if torch.is_tensor(rgb) else rgb, dtype=np.float32), float(scale))
+
     def set_prb(self, max_depth=4, rr_depth=5):
         self.prb = dict(max_depth=int(max_depth), rr_depth=int(rr_depth))
 
@@ -128,6 +132,10 @@ class HostContext:
         h.shading.hide_emitters = int(self.shading['hide_emitters'])
         h.antithetic = int(self.antithetic)
         h.use_mis = int(self.use_mis)
+        if self.envmap is not None:
+            if self.integrator == 3:
+                raise RuntimeError("the envmap emitter is implemented for sdf_direct_reparam only")
+            hs.set_envmap(*self.envmap)
         h.shadow_origin = self.shadow_origin
         h.prb.max_depth, h.prb.rr_depth = self.prb['max_depth'], self.prb['rr_depth']
         return hs

@@ -24,6 +24,7 @@ struct hh_scene {
     float to_world[16];
     int shadow_origin;   // sdf_direct_reparam: 0 si, 1 detach_indirect_si, 2 decouple_reparam
     int use_mis;         // ReparamIntegrator prop use_mis (sdf_direct_reparam's BSDF-sampling branch)
+    const void* envmap;  // hh_envmap_create handle or NULL (constant emitter)
 };
 
 static SceneParams build(const hh_scene* h) {
@@ -42,10 +43,39 @@ static SceneParams build(const hh_scene* h) {
     sc.integrator = h->integrator;
     sc.prb = make_prb(h->prb);
     set_grid_transform(sc.G, sc.T, h->has_transform ? h->to_world : nullptr);
+    if (h->envmap != nullptr) {
+        const EnvTables* t = (const EnvTables*)h->envmap;
+        sc.E.data = t->data.data(); sc.E.marg_cdf = t->marg_cdf.data(); sc.E.cond_cdf = t->cond_cdf.data();
+        sc.E.cell_prob = t->cell_prob.data(); sc.E.W1 = t->W1; sc.E.H = t->H;
+    }
     return sc;
 }
 
 extern "C" {
+
+// `envmap` emitter tables (the same builder sdfrt_set_envmap_host uses)
+void* hh_envmap_create(const float* rgb, int w, int h, float scale) {
+    EnvTables* t = new EnvTables();
+    if (!build_envmap(rgb, w, h, scale, *t)) { delete t; return nullptr; }
+    return t;
+}
+void hh_envmap_destroy(void* t) { delete (EnvTables*)t; }
+// lookup / sampling of the emitter alone: out (n, 8) = Le rgb, pdf(d), sampled direction, its pdf
+int hh_envmap_query(const void* e, const float* d, const float* u, int n, float* out) {
+    const EnvTables* t = (const EnvTables*)e;
+    EnvView E;
+    E.data = t->data.data(); E.marg_cdf = t->marg_cdf.data(); E.cond_cdf = t->cond_cdf.data(); E.cell_prob = t->cell_prob.data();
+    E.W1 = t->W1; E.H = t->H;
+    for (int i = 0; i < n; ++i) {
+        const V3 di = V3{d[3 * i], d[3 * i + 1], d[3 * i + 2]};
+        const V3 Le = env_eval(E, di, nullptr);
+        float pdf;
+        const V3 s = env_sample(E, u[2 * i], u[2 * i + 1], pdf);
+        float* o = out + (size_t)i * 8;
+        o[0] = Le.x; o[1] = Le.y; o[2] = Le.z; o[3] = env_pdf(E, di); o[4] = s.x; o[5] = s.y; o[6] = s.z; o[7] = pdf;
+    }
+    return 0;
+}
 
 void hh_defaults(hh_scene* h) {
     std::memset(h, 0, sizeof(*h));

@@ -46,7 +46,7 @@ class HHScene(C.Structure):
                 ('albedo', C.c_void_p), ('ax', C.c_int), ('ay', C.c_int), ('az', C.c_int),
                 ('tracer', TracerParams), ('warp', WarpParams), ('sensor', SensorParams), ('shading', ShadingParams),
                 ('integrator', C.c_int), ('prb', PrbParams), ('antithetic', C.c_int), ('has_transform', C.c_int),
-                ('to_world', C.c_float * 16), ('shadow_origin', C.c_int), ('use_mis', C.c_int)]
+                ('to_world', C.c_float * 16), ('shadow_origin', C.c_int), ('use_mis', C.c_int), ('envmap', C.c_void_p)]
 
 
 def build():
@@ -96,6 +96,28 @@ class HostScene:
             self.h.has_transform = 1
             self.h.to_world[:] = [float(v) for v in np.asarray(sdf_to_world, dtype=np.float64).reshape(16)]
         self.border = 2
+        self._env = None
+
+    def set_envmap(self, rgb, scale=1.0):
+        """`envmap` emitter from an (H, W, 3) bitmap (None: back to the constant emitter)."""
+        L = lib()
+        L.hh_envmap_create.restype = C.c_void_p
+        if self._env is not None:
+            L.hh_envmap_destroy(C.c_void_p(self._env))
+            self._env = None
+        if rgb is not None:
+            a = np.ascontiguousarray(rgb, dtype=np.float32)
+            self._env = L.hh_envmap_create(fptr(a), a.shape[1], a.shape[0], C.c_float(scale))
+            if not self._env:
+                raise ValueError('invalid envmap')
+        self.h.envmap = self._env
+
+    def envmap_query(self, d, u):
+        d = np.ascontiguousarray(d, dtype=np.float32)
+        u = np.ascontiguousarray(u, dtype=np.float32)
+        out = np.zeros((d.shape[0], 8), np.float32)
+        lib().hh_envmap_query(C.c_void_p(self._env), fptr(d), fptr(u), d.shape[0], fptr(out))
+        return dict(Le=out[:, :3], pdf=out[:, 3], d=out[:, 4:7], d_pdf=out[:, 7])
 
     @property
     def film_shape(self):
