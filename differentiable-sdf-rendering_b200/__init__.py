@@ -11,4 +11,4 @@ from .engine import Context  # noqa: F401
 from .render import render  # noqa: F401
 from .scene import Scene, Sensor, get_regular_cameras, look_at, set_sensor_res  # noqa: F401
 from .shapes import BoxSDF, Grid3d, Ray3f, create_block_sdf, create_sphere_sdf  # noqa: F401
-from .warp import DummyWarpField, WarpField2D  # noqa: F401
+from .warp import DummyWarpField, WarpField2D, WarpFieldConvolution  # noqa: F401

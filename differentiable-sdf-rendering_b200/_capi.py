@@ -8,7 +8,7 @@ LIB_PATH = os.path.join(_HERE, 'libsdfrt.so')
 
 SDFRT_OK = 0
 INTEGRATOR_SILHOUETTE, INTEGRATOR_SIMPLE_SHADING, INTEGRATOR_DIRECT, INTEGRATOR_PRB = 0, 1, 2, 3
-WARP_NONE, WARP_DUMMY, WARP_2D = 0, 1, 2
+WARP_NONE, WARP_DUMMY, WARP_2D, WARP_CONV = 0, 1, 2, 3
 
 
 class TracerParams(C.Structure):
@@ -20,7 +20,8 @@ class TracerParams(C.Structure):
 
 class WarpParams(C.Structure):
     _fields_ = [('kind', C.c_int32), ('edge_eps', C.c_float), ('weight_strategy', C.c_int32),
-                ('clamping_thresh', C.c_float), ('normalize_warp_field', C.c_int32), ('max_reparam_depth', C.c_int32)]
+                ('clamping_thresh', C.c_float), ('normalize_warp_field', C.c_int32), ('max_reparam_depth', C.c_int32),
+                ('n_aux_rays', C.c_int32), ('kappa', C.c_float), ('power', C.c_float)]
 
 
 class SensorParams(C.Structure):

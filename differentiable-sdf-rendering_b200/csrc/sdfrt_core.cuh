@@ -118,6 +118,8 @@ struct WarpParams {
     int weight_strategy;
     float clamping_thresh;
     int normalize_warp_field, max_reparam_depth;
+    int n_aux_rays;      // WARP_CONV (python/warp.py:129-136)
+    float kappa, power;
 };
 struct SensorParams {
     float R[3][3];  // camera -> world rotation (columns left, up, dir)

@@ -53,6 +53,7 @@ struct RowStore {
     __device__ __forceinline__ void operator()(int t, float v) const { row[t] = v; }
 };
 
+template <bool CONV>
 __global__ void __launch_bounds__(kBlock) k_backward(const __grid_constant__ SceneParams sc, const __grid_constant__ PassParams ps,
                                                       const float* __restrict__ film_adj, const float* __restrict__ rec,
                                                       unsigned long long rec_stride, BackwardTargets tg, float* grad_p,
@@ -70,7 +71,7 @@ __global__ void __launch_bounds__(kBlock) k_backward(const __grid_constant__ Sce
     if (item < ps.n_items) {
         const WorkItem w = decode_item(ps, item);
         const unsigned long long wl = w.lane & ~kAntiBit;
-        if (wl >= ps.win_lo && wl < ps.win_hi) lane_backward(sc, ps, w.lane, film_adj, rec + item, rec_stride, tg, gp, sites, st);
+        if (wl >= ps.win_lo && wl < ps.win_hi) lane_backward<CONV>(sc, ps, w.lane, film_adj, rec + item, rec_stride, tg, gp, sites, st);
     }
     for (int q = 0; q < 5; ++q) {
         const bool has = q < sites.n;
@@ -102,7 +103,7 @@ __global__ void __launch_bounds__(kBlock) k_backward(const __grid_constant__ Sce
         __syncwarp();
     }
     {   // the adjoint sweep's evaluations are counted separately from the marchers'
-        const unsigned h = warp_sum(st.n_hess), nsites = warp_sum(st.n_sites), al = warp_sum(st.n_albedo);
+        const unsigned h = warp_sum(st.n_hess + (CONV ? st.n_value + st.n_grad : 0u)), nsites = warp_sum(st.n_sites), al = warp_sum(st.n_albedo);
         if (lane_id == 0) {
             if (h) atomicAdd(&counters->n_evals_adjoint, (unsigned long long)h);
             if (nsites) atomicAdd(&counters->n_scatter_sites, (unsigned long long)nsites);
@@ -746,6 +747,8 @@ int enqueue_batch(sdfrt_ctx* ctx, const Sweep& sw, unsigned long long item0, int
 
 int run_sweeps(sdfrt_ctx* ctx, Sweep* sweeps, int ns, cudaStream_t st) {
     SDFRT_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ctx->sc.W.kind == WARP_CONV && ctx->sc.integrator == INTEGRATOR_PRB)
+        return fail(ctx, SDFRT_ERR_INVALID, "WarpFieldConvolution is implemented for the direct-illumination integrators only (not sdf_prb_reparam)");
     if (ctx->sc.E.data != nullptr && ctx->sc.integrator == INTEGRATOR_PRB)
         return fail(ctx, SDFRT_ERR_INVALID, "the envmap emitter is implemented for sdf_direct_reparam only (sdf_prb_reparam: constant emitter)");
     const SensorParams& S = ctx->sc.S;
@@ -1134,7 +1137,9 @@ int sdfrt_set_tracer(sdfrt_ctx* ctx, const sdfrt_tracer_params* p) {
 
 int sdfrt_set_warp(sdfrt_ctx* ctx, const sdfrt_warp_params* p) {
     if (!ctx || !p) return SDFRT_ERR_INVALID;
-    if (p->kind < SDFRT_WARP_NONE || p->kind > SDFRT_WARP_2D) return fail(ctx, SDFRT_ERR_INVALID, "unknown warp kind");
+    if (p->kind < SDFRT_WARP_NONE || p->kind > SDFRT_WARP_CONV) return fail(ctx, SDFRT_ERR_INVALID, "unknown warp kind");
+    if (p->kind == SDFRT_WARP_CONV && (p->n_aux_rays < 1 || p->n_aux_rays > kMaxAuxRays || !(p->kappa > 0.f) || !(p->power > 0.f)))
+        return fail(ctx, SDFRT_ERR_INVALID, "bad convolution warp parameters (need 1 <= n_aux_rays <= 64, kappa > 0, power > 0)");
     ctx->warp_pub = *p;
     ctx->sc.W = make_warp(*p);
     VS(ctx).adj_ready = false;
@@ -1416,7 +1421,10 @@ int sdfrt_adjoint_backprop(sdfrt_ctx* ctx, const float* film_accum, const float*
             k_prb_backward<2><<<(unsigned)blocks, kBlock, 0, st>>>(vsc, ps, VS(ctx).film_adj, L_rec, prim, recs, VS(ctx).rec_stride, tg, grad_p, ctx->counters);
     } else {
         LaunchScope ls(ctx, 6, st);
-        k_backward<<<(unsigned)blocks, kBlock, 0, st>>>(vsc, ps, VS(ctx).film_adj, VS(ctx).rec, VS(ctx).rec_stride, tg, grad_p, ctx->counters);
+        if (vsc.W.kind == WARP_CONV)   // WarpFieldConvolution: the auxiliary rays are marched inside the adjoint (python/warp_conv.py:185-282)
+            k_backward<true><<<(unsigned)blocks, kBlock, 0, st>>>(vsc, ps, VS(ctx).film_adj, VS(ctx).rec, VS(ctx).rec_stride, tg, grad_p, ctx->counters);
+        else
+            k_backward<false><<<(unsigned)blocks, kBlock, 0, st>>>(vsc, ps, VS(ctx).film_adj, VS(ctx).rec, VS(ctx).rec_stride, tg, grad_p, ctx->counters);
     }
     SDFRT_CUDA(ctx, cudaGetLastError());
     return SDFRT_OK;

@@ -13,7 +13,7 @@
 namespace sdfrt {
 
 enum { INTEGRATOR_SILHOUETTE = 0, INTEGRATOR_SIMPLE_SHADING = 1, INTEGRATOR_DIRECT = 2, INTEGRATOR_PRB = 3 };
-enum { WARP_NONE = 0, WARP_DUMMY = 1, WARP_2D = 2 };
+enum { WARP_NONE = 0, WARP_DUMMY = 1, WARP_2D = 2, WARP_CONV = 3 };
 
 struct PrbParams {  // props of SdfPrbReparamIntegrator (python/integrators/sdf_prb_reparam.py:35-48, reparam.py:14)
     int max_depth, rr_depth;
@@ -103,6 +103,10 @@ struct LaneStats {
 #define SDFRT_ATOMIC_ADD(ptr, val) (*(ptr) += (val))  // host builds (test harness): single-threaded unless overridden
 #endif
 
+// WarpFieldConvolution.ray_intersect: `reparam and (max_reparam_depth < 0 or depth <= max_reparam_depth)` (python/warp.py:142)
+SDFRT_HD bool conv_at_depth(const WarpParams& W, int depth) {
+    return W.kind == WARP_CONV && (W.max_reparam_depth < 0 || depth <= W.max_reparam_depth);
+}
 SDFRT_HD bool reparam_at_depth(const WarpParams& W, int depth) {
     return W.kind == WARP_2D && (W.max_reparam_depth < 0 || depth <= W.max_reparam_depth);
 }
@@ -176,7 +180,7 @@ SDFRT_HD void sh_frame(V3 n, V3& s, V3& t) {
     t = V3{n.y * s.z - n.z * s.y, n.z * s.x - n.x * s.z, n.x * s.y - n.y * s.x};
 }
 // warp::square_to_cosine_hemisphere through the concentric disk mapping.  S15
-SDFRT_HD V3 square_to_cosine_hemisphere(float u0, float u1) {
+SDFRT_HD void square_to_uniform_disk_concentric(float u0, float u1, float& px, float& py) {
     const float x = 2.f * u0 - 1.f, y = 2.f * u1 - 1.f;
     const bool is_zero = (x == 0.f) & (y == 0.f);
     const bool q13 = fabsf(x) < fabsf(y);
@@ -184,7 +188,11 @@ SDFRT_HD V3 square_to_cosine_hemisphere(float u0, float u1) {
     float phi = 0.25f * kPi * rp / (is_zero ? 1.f : r);
     if (q13) phi = 0.5f * kPi - phi;
     if (is_zero) phi = 0.f;
-    const float px = r * cosf(phi), py = r * sinf(phi);
+    px = r * cosf(phi); py = r * sinf(phi);
+}
+SDFRT_HD V3 square_to_cosine_hemisphere(float u0, float u1) {
+    float px, py;
+    square_to_uniform_disk_concentric(u0, u1, px, py);
     return V3{px, py, sqrtf(fmaxf(0.f, 1.f - (px * px + py * py)))};
 }
 // mitsuba.ad.integrators.common.mis_weight (power heuristic, 0 where undefined)
@@ -470,6 +478,124 @@ SDFRT_HD void push_site(SiteList& L, V3 x, float phi_hat, V3 g_hat) {
     ++L.n;
 }
 
+// ------------------------------------------------------------------------------------------------
+// WarpFieldConvolution (Bangaru et al. 2020; python/warp.py:126-176, python/warp_conv.py) -- the comparison baseline.
+// The reference's reparameterisation is a CustomOp whose primal returns (ray.d, 0): the auxiliary rays are only traced when
+// the AD graph is traversed, so ALL of it lives in the adjoint sweep.  conv_reparam_adjoint is that `backward`
+// (python/warp_conv.py:185-282) for one ray in closed form: pass 1 marches the auxiliary rays and accumulates the normalisation
+// Z and its direction derivative dZ, pass 2 pushes  dL/dV_direct = w * grad_V + d_w * grad_div_V_1  through
+// V_direct = normalize(detach(p) + (W - detach(W)) - o), W = -g phi / |g|^2 at the auxiliary hit point p: one B-spline site per
+// auxiliary hit (value adjoint only) and the adjoint of the ray origin o.  oracle/ref_semantics.md S19.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxAuxRays = 64;
+
+// mitsuba `coordinate_system` (Duff et al. 2017) as mi.Frame3f(n) builds it: both vectors from the closed form
+SDFRT_HD void coordinate_system(V3 n, V3& s, V3& t) {
+    const float sign = n.z >= 0.f ? 1.f : -1.f;
+    const float a = -1.f / (sign + n.z);
+    const float b = n.x * n.y * a;
+    s = V3{sign * n.x * n.x * a + 1.f, sign * b, -sign * n.x};
+    t = V3{b, sign + n.y * n.y * a, -n.y};
+}
+// One auxiliary direction: warp::square_to_von_mises_fisher (concentric-disk variant) in the frame of d, with the quantities
+// the harmonic weight needs, all from m = 1 - cos(theta) = -log(xi) / kappa so that nothing is lost to 1 - (1 - m) in fp32:
+// pdf = xi kappa / (2 pi (1 - e^{-2 kappa})),  D = exp(kappa - kappa d.omega) - 1 = 1 / xi - 1.
+struct AuxDir {
+    V3 omega, tang;   // direction; its component orthogonal to d (omega - d (d . omega))
+    float pdf, D;
+};
+SDFRT_HD AuxDir aux_direction(V3 d, V3 fs, V3 ft, float u0, float u1, float kappa) {
+    float px, py;
+    square_to_uniform_disk_concentric(u0, u1, px, py);
+    const float r2 = px * px + py * py;
+    const float sy = fmaxf(1.f - r2, 1e-6f);
+    const float e2k = expf(-2.f * kappa);
+    const float xi = sy + (1.f - sy) * e2k;
+    const float m = -logf(xi) / kappa;
+    const float sc = r2 > 0.f ? sqrtf(fmaxf(m * (2.f - m), 0.f) / r2) : 0.f;
+    AuxDir a;
+    a.tang = (px * sc) * fs + (py * sc) * ft;
+    a.omega = a.tang + (1.f - m) * d;
+    a.pdf = xi * kappa * (0.5f / kPi) / (1.f - e2k);
+    a.D = 1.f / xi - 1.f;
+    return a;
+}
+// harmonic weight w and the factor of its direction derivative (d_w = dwf * tang), both already divided by the pdf (python/warp_conv.py:50-66)
+SDFRT_HD void aux_weight(const AuxDir& a, float B, float kappa, float power, float& w, float& dwf) {
+    const float den = a.D + B;
+    const bool ok = den > 1e-7f;
+    const float ip = ok ? powf(den, -power) : 0.f;
+    w = ip / a.pdf;
+    const float tmp1 = (a.D + 1.f) * (ok ? ip / den : 0.f) * kappa * power;
+    dwf = fminf(fabsf(tmp1), 1e10f) / a.pdf;   // tmp1 >= 0
+}
+SDFRT_HD void rng_skip(Pcg32& rng, int n) {
+    for (int i = 0; i < n; ++i) (void)pcg_next_u32(rng);
+}
+// Adjoint of one reparameterised ray.  g_dir / g_div: adjoints of the returned direction and divergence.  Draws 2 n_aux_rays samples
+// from `rng` whatever happens.  Scatters into grad_sdf (may be null), accumulates dL/d(sdf.p) and returns dL/d(ray origin).
+SDFRT_HD V3 conv_reparam_adjoint(const SceneParams& sc, V3 o, V3 d, float maxt, Pcg32& rng, V3 g_dir, float g_div, float* grad_sdf,
+                                 V3& grad_p, LaneStats& st) {
+    const int N = sc.W.n_aux_rays < kMaxAuxRays ? sc.W.n_aux_rays : kMaxAuxRays;
+    const float kappa = sc.W.kappa, power = sc.W.power;
+    V3 o_hat = v3(0.f);
+    if (!((g_div != 0.f) | (g_dir.x != 0.f) | (g_dir.y != 0.f) | (g_dir.z != 0.f))) {
+        rng_skip(rng, 2 * N);
+        return o_hat;
+    }
+    V3 fs, ft;
+    coordinate_system(d, fs, ft);
+    float its[kMaxAuxRays];
+    Pcg32 rng2 = rng;
+    float Z = 0.f;
+    V3 dZ = v3(0.f);
+    for (int i = 0; i < N; ++i) {
+        const float u0 = pcg_next_f32(rng), u1 = pcg_next_f32(rng);
+        const AuxDir a = aux_direction(d, fs, ft, u0, u1, kappa);
+        int ns = 0, nv = 0;
+        its[i] = trace_non_diff(sc.G, sc.T, o, a.omega, maxt, true, ns, nv);
+        st.n_value += (unsigned)nv;
+        float B = 1.f;
+        if (isfinite(its[i])) {
+            float phi; V3 g; S3 H;
+            eval_sdf<1>(sc.G, o + its[i] * a.omega, phi, g, H);
+            st.n_grad += 1;
+            const float c = dot(g, a.omega);
+            B = c * c / dot(g, g);   // boundary test (n . -omega)^2
+        }
+        float w, dwf;
+        aux_weight(a, B, kappa, power, w, dwf);
+        Z += w;
+        dZ += dwf * a.tang;
+    }
+    Z = fmaxf(Z, 1e-8f);
+    const float iZ = 1.f / Z;
+    // direction = normalize(d + V_theta), divergence = (div_V_1 - V_theta . dZ) / Z at V_theta = 0 (python/warp_conv.py:226-236)
+    const V3 grad_V = ((g_dir - dot(d, g_dir) * d) - (g_div * iZ) * dZ) * iZ;
+    const float grad_div1 = g_div * iZ;
+    for (int i = 0; i < N; ++i) {
+        const float u0 = pcg_next_f32(rng2), u1 = pcg_next_f32(rng2);
+        if (!isfinite(its[i])) continue;   // the background does not move (:47)
+        const AuxDir a = aux_direction(d, fs, ft, u0, u1, kappa);
+        const V3 p = o + its[i] * a.omega;
+        float phi; V3 g; S3 H;
+        eval_sdf<1>(sc.G, p, phi, g, H);
+        st.n_grad += 1;
+        const float gg = dot(g, g), c = dot(g, a.omega);
+        float w, dwf;
+        aux_weight(a, c * c / gg, kappa, power, w, dwf);
+        const V3 V_hat = w * grad_V + (dwf * grad_div1) * a.tang;
+        const V3 q_hat = (V_hat - dot(a.omega, V_hat) * a.omega) / its[i];   // through normalize(p - o), |p - o| = its_t
+        const float phi_hat = -dot(g, q_hat) / gg;                           // W = -(g / |g|^2) phi(p)
+        if (!isfinite(phi_hat) | !isfinite(q_hat.x + q_hat.y + q_hat.z)) continue;
+        if (grad_sdf != nullptr) scatter_site(grad_sdf, sc.G, p, phi_hat, v3(0.f));
+        st.n_sites += 1;
+        grad_p = grad_p - phi_hat * g;
+        o_hat = o_hat - q_hat;
+    }
+    return o_hat;
+}
+
 struct BackwardTargets {
     float* grad_sdf;     // (rz, ry, rx), accumulated (by the caller, from the SiteList)
     float* grad_albedo;  // (rz, ry, rx, 3) or nullptr
@@ -479,6 +605,11 @@ struct BackwardTargets {
 // backward lane.  film_adj: (Hb, Wb, 4) = (dL/dV_rgb, dL/dWt) per film pixel (see k_film_adjoint).
 // Returns this lane's contribution to dL/d(sdf.p) in grad_p.
 // ------------------------------------------------------------------------------------------------
+// CONV: the warp field is a WarpFieldConvolution (kind WARP_CONV): no tracer records are read, the warp sites are replaced by
+// conv_reparam_adjoint, whose auxiliary samples continue the lane's sampler stream after its forward draws in the order the
+// reference's AD traversal visits the CustomOps: BSDF-sampled ray (every lane draws), shadow ray (lanes with an emitter sample),
+// camera ray (every lane).  oracle/ref_semantics.md S19
+template <bool CONV = false>
 SDFRT_HD void lane_backward(const SceneParams& sc, const PassParams& ps, unsigned long long lane, const float* film_adj,
                             const float* rec /* already offset to this lane's record */, unsigned long long rec_stride, const BackwardTargets& tg, V3& grad_p,
                             SiteList& sites, LaneStats& st) {
@@ -488,7 +619,7 @@ SDFRT_HD void lane_backward(const SceneParams& sc, const PassParams& ps, unsigne
     const bool hit = isfinite(its_t);
     // A sample that misses and has no valid warp site (warp_t = inf: weight below threshold, bbox miss, or a ray the
     // empty-space test skipped) carries no derivative at all: its only differentiable quantities are the warp outputs.
-    if (!hit && !(reparam_at_depth(sc.W, 0) && isfinite(r[REC_TAU * rec_stride]))) return;
+    if (!CONV && !hit && !(reparam_at_depth(sc.W, 0) && isfinite(r[REC_TAU * rec_stride]))) return;
     CameraSample cs = camera_sample(sc, ps, lane);
     const V3 o = cs.o, d0 = cs.d;
 
@@ -533,7 +664,7 @@ SDFRT_HD void lane_backward(const SceneParams& sc, const PassParams& ps, unsigne
         } else {
             nee = r[REC_S_STATE * rec_stride] != 0.f;
             bsdf_hit_env = mis && r[REC_B_STATE * rec_stride] != 0.f;
-            if (nee | bsdf_hit_env) {
+            if (nee | bsdf_hit_env | CONV) {   // (CONV: the sampler position after the forward draws matters for every lane)
                 const float u0 = pcg_next_f32(cs.rng), u1 = pcg_next_f32(cs.rng);
                 sr = sample_emitter_ray(sc, p, n, u0, u1, pdf_e);
                 cos_o = dot(n, sr.d);
@@ -553,6 +684,7 @@ SDFRT_HD void lane_backward(const SceneParams& sc, const PassParams& ps, unsigne
                     rgb = V3{rho.x * cos_o * K.x, rho.y * cos_o * K.y, rho.z * cos_o * K.z};
                 }
             }
+            if (CONV && mis && !bsdf_hit_env) rng_skip(cs.rng, 3);
             if (bsdf_hit_env) {
                 (void)pcg_next_f32(cs.rng);
                 const float b0 = pcg_next_f32(cs.rng), b1 = pcg_next_f32(cs.rng);
@@ -568,6 +700,17 @@ SDFRT_HD void lane_backward(const SceneParams& sc, const PassParams& ps, unsigne
                 rgb += rgb_b;
             }
         }
+    }
+
+    // ---- WarpFieldConvolution: where each reparameterised ray's auxiliary draws start in the lane's stream ------
+    Pcg32 rng_b = cs.rng, rng_s = cs.rng, rng_p = cs.rng;
+    if (CONV) {
+        const int n2 = 2 * (sc.W.n_aux_rays < kMaxAuxRays ? sc.W.n_aux_rays : kMaxAuxRays);
+        const bool direct = sc.integrator == INTEGRATOR_DIRECT;
+        if (direct && mis && conv_at_depth(sc.W, 1)) rng_skip(cs.rng, n2);                         // BSDF-sampled ray: active = True (:95)
+        rng_s = cs.rng;
+        if (direct && hit && pdf_e > 0.f && conv_at_depth(sc.W, 1)) rng_skip(cs.rng, n2);          // shadow ray: active_e (:42,52)
+        rng_p = cs.rng;
     }
 
     // ---- film adjoint: gather over the filter footprint ------------------------------------------
@@ -669,6 +812,10 @@ SDFRT_HD void lane_backward(const SceneParams& sc, const PassParams& ps, unsigne
             }
             // BSDF-sampled ray's warp site: spawned from the attached interaction (si.spawn_ray, :93), direction detached -- only its
             // divergence carries a derivative
+            if (CONV && bsdf_hit_env && conv_at_depth(sc.W, 1)) {
+                const V3 ob_hat = conv_reparam_adjoint(sc, br.o, br.d, INFINITY, rng_b, db_hat, dot(c_hat, rgb_b), tg.grad_sdf, grad_p, st);
+                p_hat += ob_hat;
+            }
             if (bsdf_hit_env && reparam_at_depth(sc.W, 1)) {
                 const V3 tau_d = V3{r[REC_B_TAU_DX * rec_stride], r[REC_B_TAU_DY * rec_stride], r[REC_B_TAU_DZ * rec_stride]};
                 const V3 om_d = V3{r[REC_B_OMEGA_DX * rec_stride], r[REC_B_OMEGA_DY * rec_stride], r[REC_B_OMEGA_DZ * rec_stride]};
@@ -685,6 +832,19 @@ SDFRT_HD void lane_backward(const SceneParams& sc, const PassParams& ps, unsigne
                         const V3 ob_hat = phi_hat * ws.g + mul(ws.H, g_hat);
                         grad_p = grad_p - ob_hat;
                         p_hat += ob_hat;
+                    }
+                }
+            }
+            if (CONV && nee && conv_at_depth(sc.W, 1)) {
+                const V3 os_hat = conv_reparam_adjoint(sc, sr.o, sr.d, sr.maxt, rng_s, ds_hat, div_s_hat, tg.grad_sdf, grad_p, st);
+                if (sc.Sh.shadow_origin == 0) {
+                    p_hat += os_hat;
+                } else if (sc.Sh.shadow_origin == 2) {
+                    const float phi0_hat = dot(os_hat, d0) / (-dot(g_p, d0));
+                    if (isfinite(phi0_hat)) {
+                        push_site(sites, p, phi0_hat, v3(0.f));
+                        st.n_sites += 1;
+                        grad_p = grad_p - phi0_hat * g_p;
                     }
                 }
             }
@@ -732,6 +892,7 @@ SDFRT_HD void lane_backward(const SceneParams& sc, const PassParams& ps, unsigne
     }
 
     // ---- primary warp site ---------------------------------------------------------------------------
+    if (CONV && conv_at_depth(sc.W, 0)) (void)conv_reparam_adjoint(sc, o, d0, cs.maxt, rng_p, d_hat, div_hat, tg.grad_sdf, grad_p, st);
     if (reparam_at_depth(sc.W, 0)) {
         const V3 tau_d = V3{r[REC_TAU_DX * rec_stride], r[REC_TAU_DY * rec_stride], r[REC_TAU_DZ * rec_stride]};
         const V3 om_d = V3{r[REC_OMEGA_DX * rec_stride], r[REC_OMEGA_DY * rec_stride], r[REC_OMEGA_DZ * rec_stride]};

@@ -30,6 +30,9 @@ inline void warp_defaults(sdfrt_warp_params* p) {  // python/configs.py:12-40 ("
     p->clamping_thresh = 0.05f;
     p->normalize_warp_field = 1;
     p->max_reparam_depth = -1;
+    p->n_aux_rays = 16;   // python/configs.py:123 ("ConvolutionWarp"); only read for SDFRT_WARP_CONV
+    p->kappa = 1e5f;
+    p->power = 3.f;
 }
 inline void sensor_defaults(sdfrt_sensor* s) {  // python/util.py:115-138, sensor 0 of a 6-camera rig is set by the caller
     std::memset(s, 0, sizeof(*s));
@@ -114,6 +117,7 @@ inline WarpParams make_warp(const sdfrt_warp_params& p) {
     w.kind = p.kind; w.edge_eps = p.edge_eps; w.weight_strategy = p.weight_strategy;
     w.clamping_thresh = p.clamping_thresh; w.normalize_warp_field = p.normalize_warp_field;
     w.max_reparam_depth = p.max_reparam_depth;
+    w.n_aux_rays = p.n_aux_rays; w.kappa = p.kappa; w.power = p.power;
     return w;
 }
 inline SensorParams make_sensor(const sdfrt_sensor& s) {

@@ -92,8 +92,9 @@ class Context:
         check(self.ctx, self.lib.sdfrt_set_tracer(self.ctx, C.byref(p)))
 
     def set_warp(self, kind=WARP_2D, edge_eps=0.01, weight_strategy=6, clamping_thresh=0.05, normalize_warp_field=True,
-                 max_reparam_depth=-1):
-        p = _capi.WarpParams(kind, edge_eps, weight_strategy, clamping_thresh, int(normalize_warp_field), max_reparam_depth)
+                 max_reparam_depth=-1, n_aux_rays=16, kappa=1e5, power=3.0):
+        p = _capi.WarpParams(kind, edge_eps, weight_strategy, clamping_thresh, int(normalize_warp_field), max_reparam_depth,
+                             int(n_aux_rays), kappa, power)
         check(self.ctx, self.lib.sdfrt_set_warp(self.ctx, C.byref(p)))
 
     def set_sensor(self, to_world, width, height, fov=39.0, near_clip=1e-2, far_clip=1e4, filter_radius=2.0,

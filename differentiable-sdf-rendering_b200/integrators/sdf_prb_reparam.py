@@ -1,5 +1,5 @@
 from .reparam import ReparamIntegrator, Properties
-from ..warp import DummyWarpField
+from ..warp import DummyWarpField, WarpFieldConvolution
 
 
 class SdfPrbReparamIntegrator(ReparamIntegrator):
@@ -17,7 +17,7 @@ class SdfPrbReparamIntegrator(ReparamIntegrator):
         self.reparam_max_depth = props.get('reparam_max_depth', self.max_depth)   # :37
         self.shade_gradient_max_depth = self.reparam_max_depth                    # :38
         self.rr_depth = props.get('rr_depth', 5)                                  # :41
-        # Bangaru-2020 convolution warp knobs (:43-45): accepted, unused (WarpFieldConvolution is out of scope)
+        # Bangaru-2020 convolution warp knobs (:43-45): accepted, unused (this integrator takes WarpField2D or no warp field)
         self.reparam_rays = props.get('reparam_rays', 16)
         self.reparam_kappa = props.get('reparam_kappa', 1e5)
         self.reparam_exp = props.get('reparam_exp', 3.0)
@@ -29,6 +29,8 @@ class SdfPrbReparamIntegrator(ReparamIntegrator):
         if isinstance(self.warp_field, DummyWarpField):
             # the reference calls warp_field.reparam (sdf_prb_reparam.py:181), which DummyWarpField lacks (python/warp.py:179-196)
             raise AttributeError("'DummyWarpField' object has no attribute 'reparam'")
+        if isinstance(self.warp_field, WarpFieldConvolution):
+            raise NotImplementedError("sdf_prb_reparam with WarpFieldConvolution: the convolution warp is built for the direct-illumination integrators")
         # max_depth = -1: the reference passes the prop through unchanged (python/integrators/reparam.py:14) -- unlike Mitsuba's own
         # prb there is no "-1 means unbounded" conversion.  `loop.set_max_iterations(-1)` wraps to a huge count, but
         # `active_next = (depth + 1 < self.max_depth)` (sdf_prb_reparam.py:307) is then false at the first vertex, so the path ends

@@ -27,6 +27,27 @@ class WarpField2D:
                     max_reparam_depth=int(self.max_reparam_depth))
 
 
+class WarpFieldConvolution:
+    """python/warp.py:126-136 (same constructor, same attributes): the Bangaru et al. 2020 convolution warp the reference compares
+    against (`configs.ConvolutionWarp*`).  All of its work happens in the adjoint sweep (`k_backward<CONV>`); sdf_prb_reparam
+    does not take it."""
+    is_dummy = False
+
+    def __init__(self, sdf, n_aux_rays=16):
+        self.sdf = sdf
+        self.n_aux_rays = n_aux_rays
+        self.max_reparam_depth = -1
+        self.kappa = 1e5
+        self.power = 3.0
+        self.return_aovs = False
+
+    def warp_params(self):
+        if self.return_aovs:
+            raise NotImplementedError("AOV outputs are not part of the hot path")
+        return dict(kind=_capi.WARP_CONV, max_reparam_depth=int(self.max_reparam_depth), n_aux_rays=int(self.n_aux_rays),
+                    kappa=float(self.kappa), power=float(self.power))
+
+
 class DummyWarpField:
     """python/warp.py:179-196."""
     is_dummy = True

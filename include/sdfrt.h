@@ -28,7 +28,7 @@ enum { SDFRT_OK = 0, SDFRT_ERR_INVALID = -1, SDFRT_ERR_CUDA = -2, SDFRT_ERR_STAT
 /* integrator plugins, python/integrators/{sdf_silhouette,sdf_simple_shading,sdf_direct,sdf_prb}_reparam.py */
 enum { SDFRT_INTEGRATOR_SILHOUETTE = 0, SDFRT_INTEGRATOR_SIMPLE_SHADING = 1, SDFRT_INTEGRATOR_DIRECT = 2, SDFRT_INTEGRATOR_PRB = 3 };
 /* warp field kinds, python/warp.py: None / DummyWarpField(:179) / WarpField2D(:7) */
-enum { SDFRT_WARP_NONE = 0, SDFRT_WARP_DUMMY = 1, SDFRT_WARP_2D = 2 };
+enum { SDFRT_WARP_NONE = 0, SDFRT_WARP_DUMMY = 1, SDFRT_WARP_2D = 2, SDFRT_WARP_CONV = 3 /* WarpFieldConvolution, python/warp.py:126-176 */ };
 
 /* SDFBase tracer knobs, python/shapes.py:28-41 (same defaults via sdfrt_tracer_defaults) */
 typedef struct sdfrt_tracer_params {
@@ -51,7 +51,11 @@ typedef struct sdfrt_warp_params {
     int32_t weight_strategy;    /* :14 */
     float clamping_thresh;      /* :16 */
     int32_t normalize_warp_field; /* :20 */
-    int32_t max_reparam_depth;  /* :11 */
+    int32_t max_reparam_depth;  /* :11 (WarpFieldConvolution: python/warp.py:132) */
+    /* SDFRT_WARP_CONV only -- WarpFieldConvolution (Bangaru et al. 2020, the comparison baseline), python/warp.py:129-136 */
+    int32_t n_aux_rays;         /* :131, 1..64 */
+    float kappa;                /* :134 von Mises-Fisher concentration, 1e5 */
+    float power;                /* :135 exponent of the harmonic weights, 3 */
 } sdfrt_warp_params;
 
 /* perspective sensor + hdrfilm + gaussian rfilter as built by python/util.py:115-138 */

@@ -110,17 +110,19 @@ class PCG32:
             self.state = self.state + initstate.astype(np.uint64)
             self.next_u32()
 
-    def next_u32(self):
+    def next_u32(self, mask=None):
+        """mask: lanes that advance (drjit `next_uint32(mask)`); the others keep their state and return garbage."""
         with np.errstate(over='ignore'):
             old = self.state
-            self.state = old * PCG32_MULT + self.inc
+            new = old * PCG32_MULT + self.inc
+            self.state = new if mask is None else np.where(mask, new, old)
             xorshifted = (((old >> np.uint64(18)) ^ old) >> np.uint64(27)) & _M32
             rot = (old >> np.uint64(59)) & _M32
             res = ((xorshifted >> rot) | (xorshifted << ((np.uint64(32) - rot) & np.uint64(31)))) & _M32
         return res.astype(np.uint32)
 
-    def next_f32(self):
-        u = self.next_u32()
+    def next_f32(self, mask=None):
+        u = self.next_u32(mask)
         bits = (u >> np.uint32(9)) | np.uint32(0x3F800000)
         return bits.view(np.float32) - np.float32(1.0)
 
@@ -134,12 +136,14 @@ class IndependentSampler:
         self.rng = PCG32(v0, v1)
         self.dtype = dtype
 
-    def next_1d(self):
-        return torch.from_numpy(self.rng.next_f32().copy()).to(self.dtype)
+    def next_1d(self, active=None):
+        """active: (N,) bool tensor / array; Mitsuba's samplers only advance the active lanes (`next_1d(active)`)."""
+        m = None if active is None else np.asarray(active, dtype=bool)
+        return torch.from_numpy(self.rng.next_f32(m).copy()).to(self.dtype)
 
-    def next_2d(self):
-        a = self.next_1d()
-        b = self.next_1d()
+    def next_2d(self, active=None):
+        a = self.next_1d(active)
+        b = self.next_1d(active)
         return torch.stack([a, b], -1)
 
 
@@ -584,6 +588,145 @@ class WarpField2D:
                                        warp_weight_d=warp_weight_d)
 
 
+def square_to_von_mises_fisher(u, kappa):
+    """mitsuba warp::square_to_von_mises_fisher (Mitsuba 3 include/mitsuba/core/warp.h, the low-distortion variant on the
+    concentric disk mapping; Jakob, "Numerically stable sampling of the von Mises Fisher distribution on S^2"):
+    p = concentric_disk(u), r2 = |p|^2, sy = max(1 - r2, 1e-6), cos_theta = 1 + log(sy + (1 - sy) exp(-2 kappa)) / kappa,
+    direction (p * sqrt((1 - cos_theta^2) / r2), cos_theta).  ref_semantics S19."""
+    t = square_to_uniform_disk_concentric(u)
+    r2 = (t * t).sum(-1)
+    sy = (1 - r2).clamp_min(1e-6)
+    cos_theta = 1 + torch.log(sy + (1 - sy) * math.exp(-2 * kappa)) / kappa
+    sc = torch.sqrt(((1 - cos_theta * cos_theta) / torch.where(r2 > 0, r2, torch.ones_like(r2))).clamp_min(0.0))
+    sc = torch.where(r2 > 0, sc, torch.zeros_like(sc))
+    return torch.stack([t[:, 0] * sc, t[:, 1] * sc, cos_theta], -1)
+
+
+def square_to_von_mises_fisher_pdf(v, kappa):
+    """exp(kappa (v.z - 1)) kappa / (2 pi (1 - exp(-2 kappa)))"""
+    return torch.exp(kappa * (v[:, 2] - 1)) * (kappa / (2 * math.pi)) / (1 - math.exp(-2 * kappa))
+
+
+class WarpFieldConvolution:
+    """python/warp.py:126-176 + python/warp_conv.py (Bangaru et al. 2020, the comparison baseline): the warp field is a convolution of
+    the SDF's own motion over `n_aux_rays` auxiliary rays drawn from a von Mises-Fisher lobe around the ray.
+
+    In the reference the reparameterisation is a dr.CustomOp: its `eval` returns (ray.d, 0) and draws NO samples; the auxiliary rays
+    are only traced when the AD graph is traversed (`backward`, python/warp_conv.py:185-282), with samples taken from the integrator's
+    sampler in the state it has THEN -- after every forward draw of the lane -- and the CustomOps are visited in reverse creation
+    order (BSDF-sampled ray, shadow ray, camera ray).  Restated here with placeholders: `ray_intersect` returns
+    d_att = normalize(d + ph_dir), div = 1 + ph_div with zero-valued leaf tensors and records the call; `conv_backward` (called by
+    render_backward after the loss has been differentiated w.r.t. the placeholders) replays the records in reverse, draws the
+    auxiliary samples, and differentiates  <g_dir, V_theta> + g_div * div_theta  (both zero-valued, python/warp_conv.py:230-236)
+    w.r.t. the SDF and -- through the attached ray origin -- the placeholders of earlier calls.  ref_semantics S19."""
+
+    def __init__(self, sdf, n_aux_rays=16):
+        self.sdf = sdf
+        self.n_aux_rays = n_aux_rays
+        self.max_reparam_depth = -1
+        self.kappa = 1e5
+        self.power = 3.0
+        self.pending = []
+
+    def ray_intersect(self, o, d, ray_maxt, depth=0, ray_test=False, reparam=True, active=None, sampler=None, lanes=None, draw_mask=None):
+        """lanes: indices of these rays in the sampler's wavefront (None: all of it, in order); draw_mask: the wavefront lanes whose
+        sampler advances when the auxiliary samples are drawn (the `active` mask the REFERENCE passes, which for the BSDF-sampled
+        ray is `True` for every lane, python/integrators/sdf_direct_reparam.py:95)."""
+        N = o.shape[0]
+        if active is None:
+            active = torch.ones(N, dtype=torch.bool)
+        reparam = reparam and ((self.max_reparam_depth < 0) or (depth <= self.max_reparam_depth))
+        its_t = self.sdf.ray_intersect_non_diff(o.detach(), d.detach(), ray_maxt, active)
+        div = torch.ones(N, dtype=o.dtype)
+        d_out = d
+        if reparam:
+            assert sampler is not None
+            ph_dir = torch.zeros(N, 3, dtype=o.dtype, requires_grad=True)
+            ph_div = torch.zeros(N, dtype=o.dtype, requires_grad=True)
+            act = active[:, None]
+            d_out = torch.where(act, normalize(d + ph_dir), d)          # direction = normalize(ray.d + V_theta) (:233); ray.d[active] = new_d
+            div = torch.where(active, div + ph_div, div)                # div = replace_grad(1, div) (python/warp.py:150)
+            self.pending.append(dict(o=o, d=d.detach(), maxt=ray_maxt, active=active.clone(), sampler=sampler, ph_dir=ph_dir, ph_div=ph_div,
+                                     lanes=lanes, draw_mask=draw_mask))
+        return its_t, d_out, div, {}
+
+    def _terms(self, op):
+        """(V_theta (N, 3), div_theta (N,)) of one recorded call -- python/warp_conv.py:12-68 per auxiliary ray, :226-236 normalisation."""
+        sdf, kappa, power = self.sdf, self.kappa, self.power
+        o, d, maxt, active, smp = op['o'], op['d'], op['maxt'], op['active'], op['sampler']
+        N, dt = o.shape[0], o.dtype
+        fs, ft = coordinate_system(d)                                    # mi.Frame3f(detach(ray.d))
+        Z = torch.zeros(N, dtype=dt); dZ = torch.zeros(N, 3, dtype=dt)
+        V = torch.zeros(N, 3, dtype=dt); div_lhs = torch.zeros(N, dtype=dt)
+        od = o.detach()
+        lanes, draw_mask = op['lanes'], op['draw_mask']
+        for _ in range(self.n_aux_rays):
+            if lanes is None:
+                u = smp.next_2d(active.numpy() if draw_mask is None else draw_mask)
+            else:
+                u = smp.next_2d(draw_mask)[lanes]
+            off = square_to_von_mises_fisher(u, kappa)
+            omega = fs * off[:, 0:1] + ft * off[:, 1:2] + d * off[:, 2:3]
+            pdf = square_to_von_mises_fisher_pdf(off, kappa)
+            its = sdf.ray_intersect_non_diff(od, omega, maxt, active)
+            hit = active & torch.isfinite(its)
+            D = torch.exp(kappa - kappa * dot(d, omega)) - 1.0
+            B = torch.ones(N, dtype=dt)
+            h = torch.nonzero(hit).squeeze(-1)
+            Vg = torch.zeros(N, 3, dtype=dt)                             # V_direct - detach(V_direct): zero valued
+            if h.numel() > 0:
+                p = od[h] + its[h][:, None] * omega[h]                    # detach(si.p)
+                val, g = sdf.eval_and_grad(p)
+                n_sq, _ = normalize_sqr(g.detach())
+                warp = -n_sq * val[:, None]                               # follows the surface along the normal (:41-43)
+                Vd = normalize(p + (warp - warp.detach()) - o[h])         # aux_ray.o = ray.o stays attached (:44)
+                Vg = Vg.index_add(0, h, Vd - Vd.detach())
+                n = normalize(g.detach())
+                B = B.index_copy(0, h, dot(n, -omega[h]) ** 2)            # boundary test (:52-53)
+            den = D + B
+            ok = den > 1e-7
+            den_s = torch.where(ok, den, torch.ones_like(den))
+            w = torch.where(ok, den_s ** (-power), torch.zeros_like(den)) / pdf
+            tmp1 = (D + 1.0) * torch.where(ok, den_s ** (-(power + 1.0)), torch.zeros_like(den)) * kappa * power
+            tmp2 = omega - d * dot(d, omega)[:, None]
+            dw = (dr_sign(tmp1) * tmp1.abs().clamp_max(1e10) / pdf)[:, None] * tmp2
+            w = torch.where(active, w, torch.zeros_like(w))
+            dw = torch.where(active[:, None], dw, torch.zeros_like(dw))
+            Z = Z + w
+            dZ = dZ + dw
+            V = V + w[:, None] * Vg
+            div_lhs = div_lhs + dot(dw, Vg)
+        Z = Z.clamp_min(1e-8)
+        V_theta = V / Z[:, None]
+        div_theta = (div_lhs - dot(V_theta, dZ)) / Z
+        return V_theta, div_theta
+
+    def conv_backward(self, loss, wrt):
+        """Gradients of `loss` w.r.t. the tensors `wrt` including everything that flows through the recorded reparameterisations."""
+        ops = self.pending
+        self.pending = []
+        phs = [t for op in ops for t in (op['ph_dir'], op['ph_div'])]
+        g = torch.autograd.grad(loss, list(wrt) + phs, allow_unused=True, retain_graph=True)
+        zero = lambda t, gi: torch.zeros_like(t) if gi is None else gi
+        acc = [zero(t, gi) for t, gi in zip(wrt, g[:len(wrt)])]
+        gph = [zero(t, gi) for t, gi in zip(phs, g[len(wrt):])]
+        for k in range(len(ops) - 1, -1, -1):
+            g_dir, g_div = gph[2 * k], gph[2 * k + 1]
+            V_theta, div_theta = self._terms(ops[k])
+            s = (g_dir.detach() * V_theta).sum() + (g_div.detach() * div_theta).sum()
+            if not s.requires_grad:
+                continue
+            earlier = phs[:2 * k]
+            gk = torch.autograd.grad(s, list(wrt) + earlier, allow_unused=True, retain_graph=True)
+            for i in range(len(wrt)):
+                if gk[i] is not None:
+                    acc[i] = acc[i] + gk[i]
+            for j in range(len(earlier)):
+                if gk[len(wrt) + j] is not None:
+                    gph[j] = gph[j] + gk[len(wrt) + j]
+        return acc
+
+
 class DummyWarpField:
     """python/warp.py:179-196: value-only trace, no reparameterisation."""
 
@@ -857,7 +1000,7 @@ def eval_albedo(scene, p):
 # --------------------------------------------------------------------------------------
 
 
-def _ray_intersect(scene, warp_field, o, d, maxt, depth, reparam, active=None):
+def _ray_intersect(scene, warp_field, o, d, maxt, depth, reparam, active=None, sampler=None, lanes=None, draw_mask=None):
     """ReparamIntegrator.ray_intersect without OptiX (python/integrators/reparam.py:201-232).
 
     With reparam=False only `its_t` is consumed; the reference still runs the differentiable
@@ -867,12 +1010,14 @@ def _ray_intersect(scene, warp_field, o, d, maxt, depth, reparam, active=None):
     wf = warp_field if warp_field is not None else DummyWarpField(scene.sdf)
     if isinstance(wf, WarpField2D) and not (reparam and (wf.max_reparam_depth < 0 or depth <= wf.max_reparam_depth)):
         wf = DummyWarpField(scene.sdf)
+    if isinstance(wf, WarpFieldConvolution):
+        return wf.ray_intersect(o, d, maxt, depth=depth, reparam=reparam, active=active, sampler=sampler, lanes=lanes, draw_mask=draw_mask)
     return wf.ray_intersect(o, d, maxt, depth=depth, reparam=reparam, active=active)
 
 
 def sample_silhouette(scene, warp_field, sampler, o, d, maxt, reparam_mode):
     """python/integrators/sdf_silhouette_reparam.py:16-29 (always reparameterises)."""
-    its_t, d_att, det, _ = _ray_intersect(scene, warp_field, o, d, maxt, 0, True)
+    its_t, d_att, det, _ = _ray_intersect(scene, warp_field, o, d, maxt, 0, True, sampler=sampler)
     valid = torch.isfinite(its_t)
     # (the reference also builds `si` here; its gradient does not reach `result`)
     result = torch.where(valid, torch.ones_like(det), torch.zeros_like(det)) * det
@@ -881,7 +1026,7 @@ def sample_silhouette(scene, warp_field, sampler, o, d, maxt, reparam_mode):
 
 def sample_simple_shading(scene, warp_field, sampler, o, d, maxt, reparam_mode):
     """python/integrators/sdf_simple_shading_reparam.py:16-28."""
-    its_t, d_att, det, _ = _ray_intersect(scene, warp_field, o, d, maxt, 0, True)
+    its_t, d_att, det, _ = _ray_intersect(scene, warp_field, o, d, maxt, 0, True, sampler=sampler)
     h = torch.nonzero(torch.isfinite(its_t)).squeeze(-1)
     result = torch.zeros(o.shape[0], dtype=o.dtype)
     if h.numel() > 0:
@@ -898,7 +1043,7 @@ def sample_direct(scene, warp_field, sampler, o, d, maxt, reparam_mode):
     dtype = o.dtype
     N = o.shape[0]
     reparametrize = reparam_mode
-    its_t, d_att, det, _ = _ray_intersect(scene, warp_field, o, d, maxt, 0, reparametrize)
+    its_t, d_att, det, _ = _ray_intersect(scene, warp_field, o, d, maxt, 0, reparametrize, sampler=sampler)
     valid = torch.isfinite(its_t)
     Le = torch.as_tensor(scene.env_radiance, dtype=dtype)
     env = scene.envmap
@@ -909,7 +1054,7 @@ def sample_direct(scene, warp_field, sampler, o, d, maxt, reparam_mode):
     result = det[:, None] * torch.where(miss_vis[:, None], Le_miss, torch.zeros(N, 3, dtype=dtype))
 
     # ---- emitter sampling (:36-84), on the lanes with a valid si ----
-    u = sampler.next_2d()
+    u = sampler.next_2d(valid.numpy())   # next_2d(active_e): only lanes with a valid interaction advance (:37-40)
     h = torch.nonzero(valid).squeeze(-1)
     if h.numel() == 0:
         return result, d_att, det
@@ -938,13 +1083,15 @@ def sample_direct(scene, warp_field, sampler, o, d, maxt, reparam_mode):
     dist = torch.linalg.norm(dvec, dim=-1)
     d_s = (dvec / dist[:, None]).detach()  # shadow_ray.d = detach(shadow_ray.d) (:51)
     maxt_s = (dist * (1 - SHADOW_EPSILON)).detach()
-    its_s, d_s_att, det_e, _ = _ray_intersect(scene, warp_field, o_s, d_s, maxt_s, 1, reparametrize)
+    pdf_ok = ds_pdf > 0                # active_e &= ds.pdf != 0 (:42)
+    dm = np.zeros(N, dtype=bool)
+    dm[h.numpy()[pdf_ok.numpy()]] = True
+    its_s, d_s_att, det_e, _ = _ray_intersect(scene, warp_field, o_s, d_s, maxt_s, 1, reparametrize, active=pdf_ok, sampler=sampler, lanes=h, draw_mask=dm)
     occluded = torch.isfinite(its_s)
     cos_o = dot(n, d_s_att)           # wo = si.to_local(shadow_ray.d); only z enters the diffuse BSDF
     cos_i = si['wi_z']
     # ds.emitter.eval(si_e) with si_e.wi = -shadow_ray.d (:61-68): for an envmap this follows the warped shadow direction; / ds.pdf (:74)
     Le_s = Le.expand(h.numel(), 3) if env is None else env.eval(d_s_att)
-    pdf_ok = ds_pdf > 0
     emitter_val = torch.where(pdf_ok[:, None], Le_s / torch.where(pdf_ok, ds_pdf, torch.ones_like(ds_pdf))[:, None], torch.zeros_like(Le_s))
     rho = eval_albedo(scene, p)
     gate = (~occluded) & (cos_i > 0) & (cos_o > 0) & pdf_ok
@@ -958,8 +1105,8 @@ def sample_direct(scene, warp_field, sampler, o, d, maxt, reparam_mode):
     result = result.index_add(0, h, contrib)
     if scene.use_mis:
         # ---- BSDF sampling (python/integrators/sdf_direct_reparam.py:87-107); not built in the CUDA path yet ----
-        u1 = sampler.next_1d()  # noqa: F841  component sample
-        u2 = sampler.next_2d()
+        u1 = sampler.next_1d(valid.numpy())  # noqa: F841  component sample; `active &= si.is_valid()` precedes the draws (:88-91)
+        u2 = sampler.next_2d(valid.numpy())
         with torch.no_grad():
             wo_l = square_to_cosine_hemisphere(u2[h])
             bs_pdf = wo_l[:, 2] / math.pi
@@ -968,7 +1115,8 @@ def sample_direct(scene, warp_field, sampler, o, d, maxt, reparam_mode):
             fs, ft = sh_frame(nd)
             wo_w = fs * wo_l[:, 0:1] + ft * wo_l[:, 1:2] + nd * wo_l[:, 2:3]   # si_d.to_world(bs.wo)
         o_b = _spawn_offset(p, n, wo_w)                              # si.spawn_ray (attached origin), d detached (:93-94)
-        its_b, d_b_att, det_b, _ = _ray_intersect(scene, warp_field, o_b, wo_w, torch.full_like(bs_pdf, INF), 1, reparametrize, active=act)
+        its_b, d_b_att, det_b, _ = _ray_intersect(scene, warp_field, o_b, wo_w, torch.full_like(bs_pdf, INF), 1, reparametrize, active=act,
+                                                  sampler=sampler, lanes=h, draw_mask=np.ones(N, dtype=bool))
         escaped = ~torch.isfinite(its_b)
         # bsdf.eval(ctx, si, bs.wo): local direction, so only rho(p) carries a derivative (:97)
         bsdf_val_b = torch.where(act[:, None], rho / math.pi * wo_l[:, 2:3], torch.zeros_like(rho))
@@ -1046,10 +1194,15 @@ def render_backward(scene, warp_field, integrator, grad_in, seed, spp, antitheti
     if alb0 is not None:
         scene.albedo_grid = alb0.detach().clone().requires_grad_(True)
     try:
+        if isinstance(warp_field, WarpFieldConvolution):
+            warp_field.pending = []
         image = render(scene, warp_field, integrator, seed, spp, mode_backward=True, antithetic=antithetic)
         loss = (image * grad_in).sum()
         wrt = [sdf.data, sdf.p] + ([scene.albedo_grid] if alb0 is not None else [])
-        grads = torch.autograd.grad(loss, wrt, allow_unused=True)
+        if isinstance(warp_field, WarpFieldConvolution):
+            grads = warp_field.conv_backward(loss, wrt)
+        else:
+            grads = torch.autograd.grad(loss, wrt, allow_unused=True)
         g_data = grads[0] if grads[0] is not None else torch.zeros_like(sdf.data)
         g_p = grads[1] if grads[1] is not None else torch.zeros_like(sdf.p)
         g_alb = None

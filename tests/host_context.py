@@ -27,7 +27,8 @@ class HostContext:
         self.to_world = None
         self.albedo = None
         self.tracer = {}
-        self.warp = dict(kind=2, edge_eps=0.01, weight_strategy=6, clamping_thresh=0.05, normalize_warp_field=True, max_reparam_depth=-1)
+        self.warp = dict(kind=2, edge_eps=0.01, weight_strategy=6, clamping_thresh=0.05, normalize_warp_field=True, max_reparam_depth=-1,
+                         n_aux_rays=16, kappa=1e5, power=3.0)
         self.sensor_args = None
         self.shading = dict(env_radiance=(1.0, 1.0, 1.0), env_dist=2.0 * 3.0 ** 0.5, albedo=(0.5, 0.5, 0.5), hide_emitters=False)
         self.integrator = 2
@@ -58,9 +59,11 @@ class HostContext:
     def set_tracer(self, **kw):
         self.tracer = dict(kw)
 
-    def set_warp(self, kind=2, edge_eps=0.01, weight_strategy=6, clamping_thresh=0.05, normalize_warp_field=True, max_reparam_depth=-1):
+    def set_warp(self, kind=2, edge_eps=0.01, weight_strategy=6, clamping_thresh=0.05, normalize_warp_field=True, max_reparam_depth=-1,
+                 n_aux_rays=16, kappa=1e5, power=3.0):
         self.warp = dict(kind=kind, edge_eps=edge_eps, weight_strategy=weight_strategy, clamping_thresh=clamping_thresh,
-                         normalize_warp_field=normalize_warp_field, max_reparam_depth=max_reparam_depth)
+                         normalize_warp_field=normalize_warp_field, max_reparam_depth=max_reparam_depth, n_aux_rays=n_aux_rays,
+                         kappa=kappa, power=power)
 
     def set_sensor(self, to_world, width, height, fov=39.0, near_clip=1e-2, far_clip=1e4, filter_radius=2.0, filter_stddev=0.5,
                    sample_border=True):
@@ -124,6 +127,7 @@ class HostContext:
         h.warp.clamping_thresh = self.warp['clamping_thresh']
         h.warp.normalize_warp_field = int(self.warp['normalize_warp_field'])
         h.warp.max_reparam_depth = self.warp['max_reparam_depth']
+        h.warp.n_aux_rays, h.warp.kappa, h.warp.power = self.warp.get('n_aux_rays', 16), self.warp.get('kappa', 1e5), self.warp.get('power', 3.0)
         h.sensor.fov_x_deg, h.sensor.near_clip, h.sensor.far_clip = fov, near, far
         h.sensor.filter_radius, h.sensor.filter_stddev, h.sensor.sample_border = frad, fstd, int(border)
         h.shading.env_radiance[:] = list(self.shading['env_radiance'])

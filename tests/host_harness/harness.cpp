@@ -179,7 +179,8 @@ int hh_backward(const hh_scene* h, unsigned seed, int spp, const float* film, co
         const unsigned long long lane = decode_item(ps, k).lane;
         if ((lane & ~kAntiBit) < g_win_lo || (lane & ~kAntiBit) >= g_win_hi) continue;
         SiteList sites;
-        lane_backward(sc, ps, lane, adj.data(), rec + k, n, tg, gp, sites, st);
+        if (sc.W.kind == WARP_CONV) lane_backward<true>(sc, ps, lane, adj.data(), rec + k, n, tg, gp, sites, st);
+        else lane_backward<false>(sc, ps, lane, adj.data(), rec + k, n, tg, gp, sites, st);
         for (int q = 0; q < sites.n; ++q) scatter_site(grad_sdf, sc.G, sites.s[q].x, sites.s[q].phi_hat, sites.s[q].g_hat);
     }
     if (grad_p) { grad_p[0] += gp.x; grad_p[1] += gp.y; grad_p[2] += gp.z; }

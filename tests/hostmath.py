@@ -23,7 +23,8 @@ class TracerParams(C.Structure):
 
 class WarpParams(C.Structure):
     _fields_ = [('kind', C.c_int32), ('edge_eps', C.c_float), ('weight_strategy', C.c_int32),
-                ('clamping_thresh', C.c_float), ('normalize_warp_field', C.c_int32), ('max_reparam_depth', C.c_int32)]
+                ('clamping_thresh', C.c_float), ('normalize_warp_field', C.c_int32), ('max_reparam_depth', C.c_int32),
+                ('n_aux_rays', C.c_int32), ('kappa', C.c_float), ('power', C.c_float)]
 
 
 class SensorParams(C.Structure):

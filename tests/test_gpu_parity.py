@@ -584,6 +584,36 @@ def test_envmap_emitter_against_oracle(sdfrt_mod, use_mis, albedo_res):
         sdf.ctx._envmap_key = None
 
 
+@pytest.mark.parametrize('integ_name,use_mis,n_aux', [('sdf_silhouette_reparam', False, 4), ('sdf_direct_reparam', False, 4), ('sdf_direct_reparam', True, 2)])
+def test_convolution_warp_against_oracle(sdfrt_mod, integ_name, use_mis, n_aux):
+    """WarpFieldConvolution (python/warp.py:126-176, python/warp_conv.py; oracle/ref_semantics.md S19) through `k_backward<CONV>`:
+    the images are those of a render without warp field, the gradient is the closed-form adjoint of the reference's CustomOp
+    `backward` with the auxiliary rays marched inside the adjoint sweep.  sdf_prb_reparam refuses the warp field."""
+    from oracle import sdf_oracle as O
+    sdfrt = sdfrt_mod
+    W, spp = 16, 4
+    osc = O.make_scene('knot', res=24, width=W, height=W)
+    osc.use_mis = use_mis
+    owf = O.WarpFieldConvolution(osc.sdf, n_aux_rays=n_aux)
+    sdf = sdfrt.Grid3d(osc.sdf.data.float().numpy(), device=0)
+    integ = sdfrt.integrators.create(integ_name, {'use_mis': use_mis}, sdf)
+    integ.warp_field = sdfrt.WarpFieldConvolution(sdf, n_aux_rays=n_aux)
+    scene = sdfrt.Scene(integ, [sdfrt.Sensor(osc.sensor.to_world, W, W)])
+    g_in = np.random.default_rng(7).uniform(-1, 1, size=(W, W, 3))
+    img_o, g_o, gp_o, _ = O.render_backward(osc, owf, integ_name, torch.from_numpy(g_in), seed=11, spp=spp)
+    sdf.data.requires_grad_(True)
+    img = sdfrt.render(scene, sensor=0, seed=11, spp=spp, seed_grad=11, spp_grad=spp)
+    assert (img.detach().cpu().double() - img_o).abs().max() < 2e-5
+    (img * torch.from_numpy(g_in).float().cuda()).sum().backward()
+    gs = sdf.data.grad[..., 0].cpu().double()
+    assert (gs - g_o).norm() < 2e-3 * g_o.norm() and (gs - g_o).abs().max() < 2e-2 * g_o.abs().max()
+    assert (sdf.p_grad.cpu().double() - gp_o).abs().max() < 2e-3 * gp_o.abs().max()
+    prb = sdfrt.integrators.create('sdf_prb_reparam', {}, sdf)
+    prb.warp_field = integ.warp_field
+    with pytest.raises(NotImplementedError):
+        sdfrt.render(sdfrt.Scene(prb, scene.sensors()), sensor=0, seed=1, spp=1)
+
+
 def test_deferred_differentiable_shadow_march_changes_nothing(sdfrt_mod):
     """Adjoint sweep 1 marches shadow segments with the value tracer first and only re-marches differentiably those whose |phi|
     stopped growing somewhere (the others provably end with an invalid warp record, python/shapes.py:195-201,278-283).

@@ -22,6 +22,11 @@ def make_pair(kind='sphere', R=32, W=24, integ='sdf_direct_reparam', albedo_res=
         wf.clamping_thresh = warp['clamping_thresh']
         wf.normalize_warp_field = warp['normalize']
         wf.max_reparam_depth = warp['max_depth']
+    elif warp['kind'] == 3:
+        wf = O.WarpFieldConvolution(sc.sdf, n_aux_rays=warp.get('n_aux_rays', 4))
+        wf.kappa, wf.power = warp.get('kappa', 1e5), warp.get('power', 3.0)
+        wf.max_reparam_depth = warp['max_depth']
+        hs.h.warp.n_aux_rays, hs.h.warp.kappa, hs.h.warp.power = wf.n_aux_rays, wf.kappa, wf.power
     elif warp['kind'] == 1:
         wf = O.DummyWarpField(sc.sdf)
     else:
@@ -386,3 +391,62 @@ def test_envmap_direction_derivative():
     assert np.linalg.norm(term) > 1e-2 * np.linalg.norm(g_att)
     assert np.linalg.norm(g_h - g_att) < 1e-3 * np.linalg.norm(g_att)
     assert np.linalg.norm((g_h - g_det) - term) < 2e-2 * np.linalg.norm(term)
+
+
+@pytest.mark.parametrize('integ,kind,mis,albedo_res,shadow_origin,max_depth,n_aux', [
+    ('sdf_silhouette_reparam', 'sphere', False, None, 0, -1, 4),
+    ('sdf_simple_shading_reparam', 'knot', False, None, 0, -1, 3),
+    ('sdf_direct_reparam', 'knot', False, 8, 0, -1, 4),
+    ('sdf_direct_reparam', 'sphere', True, None, 0, -1, 2),
+    ('sdf_direct_reparam', 'knot', False, None, 2, -1, 4),     # decouple_reparam: shadow origin on the detached interaction
+    ('sdf_direct_reparam', 'knot', False, None, 1, -1, 4),     # detach_indirect_si
+    ('sdf_direct_reparam', 'sphere', True, None, 0, 0, 4),     # max_reparam_depth = 0: camera ray only -- no auxiliary draws for the others
+])
+def test_convolution_warp_gradient_parity(integ, kind, mis, albedo_res, shadow_origin, max_depth, n_aux):
+    """WarpFieldConvolution (python/warp.py:126-176, python/warp_conv.py; oracle/ref_semantics.md S19): closed-form adjoint of the
+    reference's CustomOp `backward` in the kernel math vs torch autograd through the oracle's restatement, same auxiliary samples
+    (drawn after the lane's forward draws: BSDF-sampled, shadow, camera ray).  The images are those of a render without warp field."""
+    W, spp = 16, 4
+    sc, wf, hs = make_pair(kind, 24, W, integ, albedo_res=albedo_res, warp=dict(kind=3, n_aux_rays=n_aux, max_depth=max_depth))
+    sc.use_mis = mis
+    hs.h.use_mis = int(mis)
+    sc.detach_indirect_si, sc.decouple_reparam = shadow_origin == 1, shadow_origin == 2
+    hs.h.shadow_origin = shadow_origin
+    g_in = np.random.default_rng(7).uniform(-1, 1, size=(W, W, 3))
+    img_o, g_o, gp_o, ga_o = O.render_backward(sc, wf, integ, torch.from_numpy(g_in), seed=11, spp=spp)
+    with torch.no_grad():
+        img_none = O.render(sc, None, integ, seed=11, spp=spp)
+    assert (img_o - img_none).abs().max() < 1e-12                  # the primal of the reparameterisation is the identity
+    film, rec, _ = hs.forward(11, spp, True)
+    assert np.abs(hs.develop(film) - img_o.numpy()).max() < 2e-5
+    g_h, ga_h, gp_h, _ = hs.backward(11, spp, film, rec, g_in)
+    g_o = g_o.numpy()
+    # harmonic weights 1 / (D + B)^3 with B -> 0 at silhouettes: single auxiliary rays can be ill conditioned in fp32
+    assert np.linalg.norm(g_h - g_o) < 2e-3 * np.linalg.norm(g_o) and np.abs(g_h - g_o).max() < 2e-2 * np.abs(g_o).max()
+    assert np.abs(gp_h - gp_o.numpy()).max() < 2e-3 * np.abs(gp_o.numpy()).max()
+    if albedo_res is not None:
+        assert np.abs(ga_h - ga_o.numpy()).max() < 1e-3 * np.abs(ga_o.numpy()).max()
+    # and it is not the gradient without discontinuity handling
+    if integ != 'sdf_silhouette_reparam':      # (without a warp field the silhouette image has no derivative at all)
+        g_plain = O.render_backward(sc, None, integ, torch.from_numpy(g_in), seed=11, spp=spp)[1].numpy()
+        assert np.linalg.norm(g_plain - g_o) > 0.2 * np.linalg.norm(g_o)
+
+
+def test_convolution_warp_sampling_functions():
+    """von Mises-Fisher sampling as restated (S19): unit directions around +z, E[cos] = coth(kappa) - 1 / kappa, pdf integrates to 1
+    under its own samples' importance weights; mi.Frame3f basis orthonormal."""
+    u = torch.from_numpy(np.random.default_rng(0).uniform(0, 1, (200000, 2)))
+    for kappa in (5.0, 1e3):
+        v = O.square_to_von_mises_fisher(u, kappa)
+        assert (v.norm(dim=-1) - 1).abs().max() < 1e-9
+        assert abs(v[:, 2].mean().item() - (1 / np.tanh(kappa) - 1 / kappa)) < 5e-3 / np.sqrt(kappa)
+        c = 1 - 1.0 / kappa                                          # P(cos > c) = (e^k - e^{k c}) / (e^k - e^{-k})
+        want = (1 - np.exp(kappa * (c - 1))) / (1 - np.exp(-2 * kappa))
+        assert abs((v[:, 2] > c).double().mean().item() - want) < 5e-3
+        th = torch.linspace(0, np.pi, 200001, dtype=torch.float64)
+        vv = torch.stack([torch.sin(th), torch.zeros_like(th), torch.cos(th)], -1)
+        integral = torch.trapezoid(O.square_to_von_mises_fisher_pdf(vv, kappa) * 2 * np.pi * torch.sin(th), th).item()
+        assert abs(integral - 1.0) < 1e-4
+    n = O.normalize(torch.from_numpy(np.random.default_rng(1).normal(size=(100, 3))))
+    s, t = O.coordinate_system(n)
+    assert (O.dot(s, t).abs().max() < 1e-12) and (O.dot(s, n).abs().max() < 1e-12) and ((torch.linalg.cross(s, t) - n).abs().max() < 1e-12)

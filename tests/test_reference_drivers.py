@@ -96,6 +96,10 @@ def test_reference_configs_drive_the_mirror_objects(drivers):
     wp = configs.get_config('warpprimary').get_warpfield(sdf)
     assert wp.max_reparam_depth == 0
     assert isinstance(configs.get_config('onlyshadinggrad').get_warpfield(sdf), sdfrt.DummyWarpField)
+    for name, n in (('convolutionwarp', 16), ('convolutionwarp2', 2), ('convolutionwarp32', 32)):      # the Bangaru et al. baseline of figures/benchmark/benchmark.py:86-92
+        wc = configs.get_config(name).get_warpfield(sdf)
+        assert isinstance(wc, sdfrt.WarpFieldConvolution) and wc.n_aux_rays == n
+        assert wc.warp_params() == dict(kind=3, max_reparam_depth=-1, n_aux_rays=n, kappa=1e5, power=3.0)
     cfg, rest = opt_configs.get_opt_config('diffuse-12-hqq', {'sdf_res': '32', 'foo': 'bar'})
     assert rest == {'foo': 'bar'} and isinstance(cfg.variables[0], sdfrt.variables.SdfVariable) and len(cfg.variables) == 2
     assert cfg.variables[1].k == 'main-bsdf.reflectance.volume.data' and len(cfg.sensors) == 12
