@@ -35,12 +35,20 @@ METRIC = "primary+adjoint Mrays/s"
 # dram__bytes_read + dram__bytes_write of the k_march launches of ONE c3 step, from the committed ncu launch list
 NCU_DRAM_BYTES_PER_STEP = {'c3_blobs256_tex_512x512_64spp': (11.95e9, 'profiles/r1_launches_rows4_c3.csv')}
 # what binds each kernel, from the committed `ncu --set full` captures (profiles/): unit and its % of peak
-BINDING = {
-    'k_march<0,1,1> primary segments': {"unit": "issue + L1 (l1tex__throughput)", "pct": 76, "issue_active_pct": 56, "source": "profiles/r1_final_march.md"},
-    'k_march<0,1,1> shadow segments': {"unit": "L1 tag stage (l1tex__throughput), scattered 16 B gathers", "pct": 95, "issue_active_pct": 25, "source": "profiles/r1_final_march.md"},
-    'k_march<1,0,1> primary segments (differentiable)': {"unit": "issue (smsp__issue_active)", "pct": 77, "source": "profiles/r1_wavefront_march_diff_primary_vs_shadow.md"},
-    'k_march<1,1,1> shadow segments (differentiable)': {"unit": "L1 (l1tex__throughput)", "pct": 89, "source": "profiles/r1_wavefront_march_diff_primary_vs_shadow.md"},
-    'k_backward': {"unit": "RED queue (lg_throttle), grouped transposed scatter", "pct": None, "source": "profiles/r1_backward_direct_atomics.md"},
+BINDING = {   # round-2 captures of the shipped kernels (ncu --set full, one batch of a c3 step), summarised under profiles/r2_call*/
+    'k_march<0,1,8> primary segments (value, rows8)': {"unit": "L1 data stage (l1tex__throughput) + issue", "pct": 66, "issue_active_pct": 58,
+                                                        "top_stall": "long_scoreboard 1.8", "source": "profiles/r2_call3/r2_c3_value.md"},
+    'k_march<0,1,8> shadow segments (value, rows8)': {"unit": "L1 data stage (l1tex__throughput), one wavefront per 32 B sector of the scattered row loads", "pct": 67,
+                                                       "issue_active_pct": 44, "top_stall": "long_scoreboard 4.4", "source": "profiles/r2_call4/r2_c3_shadow_rows8.md"},
+    'k_march<1,0,8> primary segments (differentiable)': {"unit": "issue (smsp__issue_active)", "pct": 72, "source": "profiles/r2_call4/r2_c3_diff.md"},
+    'k_march<0,1,8,approach> shadow segments of adjoint sweep 1': {"unit": "L1 data stage + issue", "pct": 53, "issue_active_pct": 48, "source": "profiles/r2_call4/r2_c3_diff.md"},
+    'k_march<1,1,8> deferred differentiable march': {"unit": "issue (smsp__issue_active)", "pct": 57, "source": "profiles/r2_call4/r2_c3_deferred.md"},
+    'k_shade': {"unit": "L1 (l1tex__throughput)", "pct": 83, "issue_active_pct": 66, "source": "profiles/r2_call3/r2_c3_value.md"},
+    'k_gen_primary': {"unit": "issue (smsp__issue_active)", "pct": 86, "source": "profiles/r2_call3/r2_c3_value.md"},
+    'k_backward': {"unit": "latency: long_scoreboard 2.1 + no_instruction 1.8 stall cycles per issue (grouped transposed scatter)", "pct": None,
+                   "issue_active_pct": 34, "source": "profiles/r2_call3/r2_c3_backward.md"},
+    'k_prb_backward (c5)': {"unit": "instruction fetch: no_instruction 7.2 + long_scoreboard 5.5 stall cycles per issue", "pct": None, "issue_active_pct": 11,
+                            "source": "profiles/r2_call3/r2_c5_prb_bwd.md"},
 }
 
 

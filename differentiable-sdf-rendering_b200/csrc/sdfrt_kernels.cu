@@ -280,6 +280,36 @@ __global__ void __launch_bounds__(kBlock) k_prb_wf_emit(const __grid_constant__ 
     next_segs[idx] = stop.next_active ? make_seg(sc.T, stop.next_o, stop.next_d, INFINITY) : dead;
 }
 
+// Wavefront form, adjoint sweep 1 with the deferred differentiable march: the segments of one bounce were marched by the VALUE
+// tracer with APPROACH (hit distance in row 0 of their records; a miss whose |phi| stopped growing somewhere comes back as -inf).
+// Only segments that can end with a valid warp record go to the differentiable marcher: misses flagged -inf, and -- for
+// continuation segments, whose record the replay reads whatever they hit -- hits.  They are appended (warp-aggregated) to the
+// batch's list together with the offset of their record; every other segment gets warp_t = inf (rows 2..8 are then never used).
+template <bool CONT>
+__global__ void __launch_bounds__(256) k_prb_flag(const SegIn* __restrict__ segs, float* __restrict__ rec, unsigned long long stride, unsigned cnt,
+                                                   unsigned dest_base, SegIn* __restrict__ fsegs, unsigned* __restrict__ fdest, unsigned* __restrict__ fcount) {
+    const unsigned i = blockIdx.x * 256u + threadIdx.x;
+    const unsigned FULL = 0xffffffffu;
+    const int lane_id = threadIdx.x & 31;
+    bool take = false;
+    if (i < cnt) {
+        const float its = rec[i];
+        if (its == -INFINITY) { take = true; rec[i] = INFINITY; }
+        else if (CONT && isfinite(its)) take = true;
+        if (!take) rec[stride + i] = INFINITY;
+    }
+    const unsigned m = __ballot_sync(FULL, take);
+    if (m == 0u) return;
+    unsigned base = 0;
+    if (lane_id == (__ffs(m) - 1)) base = atomicAdd(fcount, (unsigned)__popc(m));
+    base = __shfl_sync(FULL, base, __ffs(m) - 1);
+    if (take) {
+        const unsigned slot = base + (unsigned)__popc(m & ((1u << lane_id) - 1u));
+        fsegs[slot] = segs[i];
+        fdest[slot] = dest_base + i;
+    }
+}
+
 template <int MIN_BLOCKS>  // resident blocks per SM the register allocation is tuned for (2: 255 registers, 3: 168)
 __global__ void __launch_bounds__(kBlock, MIN_BLOCKS) k_prb_backward(const __grid_constant__ SceneParams sc, const __grid_constant__ PassParams ps,
                                                           const float* __restrict__ film_adj, const float* __restrict__ L_rec,
@@ -536,6 +566,7 @@ struct MarchExtra {   // optional arguments of a k_march launch
     bool approach = false;                // value marcher: report misses whose |phi| stopped growing as -inf
     const unsigned* dest = nullptr;       // DIFF: record offset per segment
     const unsigned* n_slots_dev = nullptr;
+    bool keep_row0 = false;               // DIFF: leave row 0 (its_t) of the record alone
 };
 
 template <bool DIFF, int CACHE>
@@ -551,21 +582,21 @@ void launch_march(sdfrt_ctx* ctx, unsigned grid, cudaStream_t st, const SegIn* s
 #define SDFRT_MARCH_ARGS G, ctx->sc.T, segs, region_fill, n_slots, region, do_refine, ctx->min_live, out_its, rec_out, rec_stride, region_counter, ctx->counters, ctx->tmap
     if (ex.region_box != nullptr && CACHE != 2) {   // shadow segments with a staged SMEM box per region (TMA)
         const size_t smem = sizeof(BoxShared) + 128;
-        if (use8) k_march<DIFF, CACHE, 8, true><<<grid, kMarchBlock, smem, st>>>(SDFRT_MARCH_ARGS, ex.region_box, ex.dest, ex.n_slots_dev);
-        else k_march<DIFF, CACHE, 4, true><<<grid, kMarchBlock, smem, st>>>(SDFRT_MARCH_ARGS, ex.region_box, ex.dest, ex.n_slots_dev);
+        if (use8) k_march<DIFF, CACHE, 8, true><<<grid, kMarchBlock, smem, st>>>(SDFRT_MARCH_ARGS, ex.region_box, ex.dest, ex.n_slots_dev, ex.keep_row0);
+        else k_march<DIFF, CACHE, 4, true><<<grid, kMarchBlock, smem, st>>>(SDFRT_MARCH_ARGS, ex.region_box, ex.dest, ex.n_slots_dev, ex.keep_row0);
         return;
     }
     if constexpr (!DIFF && CACHE == 1) {
         if (ex.approach) {   // (only the register-cached value marcher is instantiated with APPROACH: the shadow role's mode)
-            if (use8) k_march<false, 1, 8, false, true><<<grid, kMarchBlock, 0, st>>>(SDFRT_MARCH_ARGS, nullptr, ex.dest, ex.n_slots_dev);
-            else if (use4) k_march<false, 1, 4, false, true><<<grid, kMarchBlock, 0, st>>>(SDFRT_MARCH_ARGS, nullptr, ex.dest, ex.n_slots_dev);
-            else k_march<false, 1, 0, false, true><<<grid, kMarchBlock, 0, st>>>(SDFRT_MARCH_ARGS, nullptr, ex.dest, ex.n_slots_dev);
+            if (use8) k_march<false, 1, 8, false, true><<<grid, kMarchBlock, 0, st>>>(SDFRT_MARCH_ARGS, nullptr, ex.dest, ex.n_slots_dev, ex.keep_row0);
+            else if (use4) k_march<false, 1, 4, false, true><<<grid, kMarchBlock, 0, st>>>(SDFRT_MARCH_ARGS, nullptr, ex.dest, ex.n_slots_dev, ex.keep_row0);
+            else k_march<false, 1, 0, false, true><<<grid, kMarchBlock, 0, st>>>(SDFRT_MARCH_ARGS, nullptr, ex.dest, ex.n_slots_dev, ex.keep_row0);
             return;
         }
     }
-    if (use8) k_march<DIFF, CACHE, 8><<<grid, kMarchBlock, 0, st>>>(SDFRT_MARCH_ARGS, nullptr, ex.dest, ex.n_slots_dev);
-    else if (use4) k_march<DIFF, CACHE, 4><<<grid, kMarchBlock, 0, st>>>(SDFRT_MARCH_ARGS, nullptr, ex.dest, ex.n_slots_dev);
-    else k_march<DIFF, CACHE, 0><<<grid, kMarchBlock, 0, st>>>(SDFRT_MARCH_ARGS, nullptr, ex.dest, ex.n_slots_dev);
+    if (use8) k_march<DIFF, CACHE, 8><<<grid, kMarchBlock, 0, st>>>(SDFRT_MARCH_ARGS, nullptr, ex.dest, ex.n_slots_dev, ex.keep_row0);
+    else if (use4) k_march<DIFF, CACHE, 4><<<grid, kMarchBlock, 0, st>>>(SDFRT_MARCH_ARGS, nullptr, ex.dest, ex.n_slots_dev, ex.keep_row0);
+    else k_march<DIFF, CACHE, 0><<<grid, kMarchBlock, 0, st>>>(SDFRT_MARCH_ARGS, nullptr, ex.dest, ex.n_slots_dev, ex.keep_row0);
 #undef SDFRT_MARCH_ARGS
 }
 template <bool DIFF>
@@ -658,23 +689,48 @@ int enqueue_batch(sdfrt_ctx* ctx, const Sweep& sw, unsigned long long item0, int
         SegIn* nsegs = reinterpret_cast<SegIn*>(sc.segs);
         SegIn* ssegs = reinterpret_cast<SegIn*>(sc.ssegs);
         float* rb = const_cast<float*>(prec.base);
+        // Deferred differentiable march (as for the direct integrator's shadow segments): value march with APPROACH first, then only
+        // the segments k_prb_flag selects go through the differentiable marcher, which fills rows 1..8 of their records in place.
+        const bool defer = DIFF && warp2d && ctx->defer_diff && !ctx->box_on && ctx->cache_mode[1] == 1 &&
+                           (unsigned long long)(max_depth * 2 * 9) * prec.stride + (unsigned long long)cnt <= 0xffffffffull;
+        SegIn* fsegs = reinterpret_cast<SegIn*>(sc.bsegs);
+        unsigned* fdest = reinterpret_cast<unsigned*>(sc.b_its);
+        auto remarch = [&](int role, int v, int s_idx, const SegIn* segs_in, bool cont) -> int {
+            float* rec_vs = rb + (size_t)((v * 2 + s_idx) * prec.rows) * prec.stride;
+            const unsigned dest_base = (unsigned)((unsigned long long)((v * 2 + s_idx) * 9) * prec.stride);
+            SDFRT_CUDA(ctx, cudaMemsetAsync(work + WQ_FLAG_COUNT, 0, 2 * sizeof(unsigned), bs));
+            { LaunchScope ls(ctx, 2, bs);
+              if (cont) k_prb_flag<true><<<(cnt + 255u) / 256u, 256, 0, bs>>>(segs_in, rec_vs, prec.stride, cnt, dest_base, fsegs, fdest, work + WQ_FLAG_COUNT);
+              else k_prb_flag<false><<<(cnt + 255u) / 256u, 256, 0, bs>>>(segs_in, rec_vs, prec.stride, cnt, dest_base, fsegs, fdest, work + WQ_FLAG_COUNT); }
+            MarchExtra ex;
+            ex.dest = fdest; ex.n_slots_dev = work + WQ_FLAG_COUNT; ex.keep_row0 = true;
+            LaunchScope ls(ctx, role == 3 ? 3 : 1, bs);
+            launch_march_mode<true>(ctx, role, need, bs, fsegs, nullptr, cnt, region, 0, nullptr, rb, prec.stride, work + WQ_FLAG_CHUNK, ex);
+            return SDFRT_OK;
+        };
         for (int k = 0; k < max_depth; ++k) {
             { LaunchScope ls(ctx, 2, bs);
               k_prb_wf_emit<<<(cnt + kBlock - 1) / kBlock, kBlock, 0, bs>>>(ctx->sc, ps, item0, cnt, k, prec, nsegs, ssegs); }
             float* srec = rb + (size_t)((k * 2 + 1) * prec.rows) * prec.stride;
             SDFRT_CUDA(ctx, cudaMemsetAsync(work, 0, WQ_COUNT * sizeof(unsigned), bs));
+            const bool shadow_diff = DIFF && warp2d && reparam_at_depth(ctx->sc.W, 1) && k <= rmd;
+            MarchExtra exa;
+            exa.approach = defer;
             { LaunchScope ls(ctx, 3, bs);
-              if (DIFF && warp2d && reparam_at_depth(ctx->sc.W, 1) && k <= rmd)
+              if (shadow_diff && !defer)
                   launch_march_mode<true>(ctx, 3, need, bs, ssegs, nullptr, cnt, region, 0, nullptr, srec, prec.stride, work + WQ_SHADOW_CHUNK);
               else
-                  launch_march_mode<false>(ctx, 1, need, bs, ssegs, nullptr, cnt, region, 0, srec, nullptr, 0, work + WQ_SHADOW_CHUNK); }
+                  launch_march_mode<false>(ctx, 1, need, bs, ssegs, nullptr, cnt, region, 0, srec, nullptr, 0, work + WQ_SHADOW_CHUNK, shadow_diff ? exa : MarchExtra()); }
+            if (shadow_diff && defer) { const int rr = remarch(3, k, 1, ssegs, false); if (rr) return rr; }
             if (k + 1 < max_depth) {
                 float* nrec = rb + (size_t)(((k + 1) * 2) * prec.rows) * prec.stride;
+                const bool next_diff = DIFF && warp2d && (k + 1) <= rmd;
                 { LaunchScope ls(ctx, 1, bs);
-                  if (DIFF && warp2d && (k + 1) <= rmd)
+                  if (next_diff && !defer)
                       launch_march_mode<true>(ctx, 2, need, bs, nsegs, nullptr, cnt, region, 1, nullptr, nrec, prec.stride, work + WQ_PRIMARY_CHUNK);
                   else
-                      launch_march_mode<false>(ctx, 0, need, bs, nsegs, nullptr, cnt, region, 1, nrec, nullptr, 0, work + WQ_PRIMARY_CHUNK); }
+                      launch_march_mode<false>(ctx, next_diff ? 1 : 0, need, bs, nsegs, nullptr, cnt, region, 1, nrec, nullptr, 0, work + WQ_PRIMARY_CHUNK, next_diff ? exa : MarchExtra()); }
+                if (next_diff && defer) { const int rr = remarch(2, k + 1, 0, nsegs, true); if (rr) return rr; }
             }
         }
         { LaunchScope ls(ctx, 4, bs);
@@ -813,6 +869,10 @@ int run_sweeps(sdfrt_ctx* ctx, Sweep* sweeps, int ns, cudaStream_t st) {
         if (any_value && (rc = ensure(ctx, &sc.its, &sc.its_n, (size_t)Bmax))) return rc;
         if (any_value && ctx->sc.integrator == INTEGRATOR_PRB && ctx->prb_wavefront &&
             (rc = ensure(ctx, &sc.prb_rec, &sc.prb_rec_n, (size_t)Bmax * 2 * (size_t)ctx->sc.prb.max_depth))) return rc;
+        if (any_diff && ctx->sc.integrator == INTEGRATOR_PRB && ctx->prb_wavefront && ctx->defer_diff) {   // list of the deferred differentiable march
+            if ((rc = ensure(ctx, &sc.bsegs, &sc.bsegs_n, (size_t)Bmax * 8))) return rc;
+            if ((rc = ensure(ctx, &sc.b_its, &sc.b_its_n, (size_t)Bmax))) return rc;
+        }
     }
     // Derived copies of the grid (row-expanded copies for the marchers, per-brick minima) are rebuilt when the grid was (re)bound
     // since they were built -- sdfrt_set_sdf is the `parameters_changed` of this boundary (python/shapes.py:477-479) and must follow

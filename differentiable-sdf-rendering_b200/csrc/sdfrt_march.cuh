@@ -30,7 +30,7 @@ constexpr unsigned kMaxRegion = 2048;  // segments per region (a power of two in
 constexpr int kMinActive = 24;         // leave the stepping loop when fewer slots are live
 
 // device work counters of one batch (zeroed before every batch)
-enum { WQ_PRIMARY_CHUNK = 0, WQ_SHADOW_CHUNK = 1, WQ_COUNT = 4 };
+enum { WQ_PRIMARY_CHUNK = 0, WQ_SHADOW_CHUNK = 1, WQ_FLAG_COUNT = 2, WQ_FLAG_CHUNK = 3, WQ_COUNT = 4 };
 
 // one ray segment ready to march: d normalised; maxt < 0 marks a segment that never enters the bounding box;
 // t0 == 0 <=> origin inside the box (python/shapes.py:141)
@@ -402,6 +402,7 @@ enum { SLOT_IDLE = 0, SLOT_MARCH = 1, SLOT_REFINE = 2, SLOT_DONE = 3 };
 //   adjoint sweep 1: 9 in 10).
 // dest (DIFF, optional): record of segment `item` goes to rec_out + dest[item] instead of rec_out + item.
 // n_slots_dev (optional): the number of valid slots is read from device memory (a list filled by earlier kernels of the stream).
+// keep_row0 (DIFF): rows 1..8 of the record are written, row 0 (its_t) is left as the earlier value march of the same segment wrote it.
 template <bool DIFF, int CACHE, int ROWS, bool BOX = false, bool APPROACH = false>
 __global__ void __launch_bounds__(kMarchBlock, BOX ? 3 : (DIFF ? (CACHE == 1 ? 3 : 4) : (CACHE == 1 ? 4 : 7))) k_march(const GridView G, const TracerParams T, const SegIn* __restrict__ segs,
                                                         const unsigned* __restrict__ region_count, unsigned n_slots, unsigned region, int do_refine, int min_live,
@@ -409,7 +410,7 @@ __global__ void __launch_bounds__(kMarchBlock, BOX ? 3 : (DIFF ? (CACHE == 1 ? 3
                                                         unsigned long long rec_stride, unsigned* __restrict__ region_counter,
                                                         Counters* __restrict__ counters, const __grid_constant__ TmaMap tmap,
                                                         const int4* __restrict__ region_box, const unsigned* __restrict__ dest = nullptr,
-                                                        const unsigned* __restrict__ n_slots_dev = nullptr) {
+                                                        const unsigned* __restrict__ n_slots_dev = nullptr, bool keep_row0 = false) {
     if (n_slots_dev != nullptr) n_slots = *n_slots_dev;
     __shared__ unsigned long long s_word;
     extern __shared__ unsigned char s_dyn[];   // BOX: one BoxShared (128-byte aligned by the launch)
@@ -455,7 +456,7 @@ __global__ void __launch_bounds__(kMarchBlock, BOX ? 3 : (DIFF ? (CACHE == 1 ? 3
             TraceOut tr;
             diff_finalize(seg, acc, T, tr);
             float* r = rec_out + (dest != nullptr ? dest[item] : item);
-            r[0 * rec_stride] = tr.its_t;
+            if (!keep_row0) r[0 * rec_stride] = tr.its_t;   // (keep_row0: the hit distance of an earlier value march stays)
             r[1 * rec_stride] = tr.warp_t;
             r[2 * rec_stride] = tr.warp_t_d.x; r[3 * rec_stride] = tr.warp_t_d.y; r[4 * rec_stride] = tr.warp_t_d.z;
             r[5 * rec_stride] = tr.warp_weight;

@@ -626,7 +626,7 @@ def test_deferred_differentiable_shadow_march_changes_nothing(sdfrt_mod):
     cam = sdfrt.get_regular_cameras(ns, resx=W, resy=W)[0]
     G = torch.from_numpy(np.random.default_rng(2).uniform(-1, 1, (W, W, 3))).float().cuda()
 
-    def run(defer, mis):
+    def run(defer, mis, integrator='sdf_direct_reparam', spp=spp):
         old = os.environ.get('SDFRT_DEFER')
         os.environ['SDFRT_DEFER'] = '1' if defer else '0'
         try:
@@ -639,9 +639,10 @@ def test_deferred_differentiable_shadow_march_changes_nothing(sdfrt_mod):
         ctx.set_sdf(sdf)
         ctx.set_sensor(cam.to_world, W, W)
         ctx.set_shading()
-        ctx.set_integrator('sdf_direct_reparam')
+        ctx.set_integrator(integrator)
         ctx.set_use_mis(mis)
         ctx.set_warp()
+        ctx.set_prb(3, 5)
         ctx.stats(reset=True)
         fa = ctx.adjoint_accumulate(18, spp)
         g = torch.zeros_like(sdf)
@@ -655,3 +656,11 @@ def test_deferred_differentiable_shadow_march_changes_nothing(sdfrt_mod):
         assert g0.abs().max() > 0 and (g0 - g1).abs().max() < 1e-4 * g0.abs().max(), (mis, ((g0 - g1).abs().max() / g0.abs().max()).item())
         assert s1['n_evals_hess'] < 0.8 * s0['n_evals_hess'], (s0, s1)
         assert abs(s1['n_scatter_sites'] - s0['n_scatter_sites']) <= 1e-3 * s0['n_scatter_sites'], (s0, s1)
+    # sdf_prb_reparam (wavefront form): shadow AND continuation segments of every bounce take the same route -- value march with the
+    # approach flag, then only hits (continuation) and flagged misses go through the differentiable marcher (k_prb_flag)
+    f0, g0, s0 = run(False, False, 'sdf_prb_reparam', 4)
+    f1, g1, s1 = run(True, False, 'sdf_prb_reparam', 4)
+    assert (f0 - f1).abs().max() < 2e-5 * f0.abs().max()
+    assert g0.abs().max() > 0 and (g0 - g1).norm() < 2e-4 * g0.norm(), ((g0 - g1).norm() / g0.norm()).item()
+    assert s1['n_evals_hess'] < 0.8 * s0['n_evals_hess'], (s0, s1)
+    assert abs(s1['n_scatter_sites'] - s0['n_scatter_sites']) <= 2e-3 * s0['n_scatter_sites'], (s0, s1)
