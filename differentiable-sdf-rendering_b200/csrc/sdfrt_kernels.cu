@@ -17,6 +17,7 @@
 #include <cstring>
 #include <algorithm>
 #include <string>
+#include <type_traits>
 #include <utility>
 #include <vector>
 
@@ -53,6 +54,40 @@ struct RowStore {
     __device__ __forceinline__ void operator()(int t, float v) const { row[t] = v; }
 };
 
+// One round of the grouped transposed scatter: every lane of the warp brings at most one site.  Each publishes its 64 tap values in
+// shared memory ([lane][65], conflict free); lanes with equal 4x4x4 block are grouped (ballot on the block key), the group's values
+// are summed "transposed" (tap t by lane t mod 32) and ONE red.global.add.f32 per tap and group is issued.  Convergent: all 32 lanes.
+__device__ __forceinline__ void grouped_scatter_round(const GridView& G, bool has, V3 x, float phi_hat, V3 g_hat, float (*vals)[65], float* grad_sdf) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane_id = threadIdx.x & 31;
+    unsigned rem = __ballot_sync(FULL, has);
+    if (rem == 0u) return;
+    int bx = 0, by = 0, bz = 0, key = -1;
+    if (has) {
+        site_tap_values(G, x, phi_hat, g_hat, bx, by, bz, RowStore{vals[lane_id]});
+        key = (bz * G.ry + by) * G.rx + bx;
+    }
+    __syncwarp();
+    while (rem) {
+        const int leader = __ffs(rem) - 1;
+        const int lkey = __shfl_sync(FULL, key, leader);
+        const unsigned members = __ballot_sync(FULL, has && key == lkey);
+        const int lbx = __shfl_sync(FULL, bx, leader), lby = __shfl_sync(FULL, by, leader), lbz = __shfl_sync(FULL, bz, leader);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int t = lane_id + 32 * h;
+            float acc = 0.f;
+            for (unsigned m = members; m; m &= m - 1) acc += vals[__ffs(m) - 1][t];
+            if (acc != 0.f && grad_sdf != nullptr) {
+                const int i = t & 3, j = (t >> 2) & 3, k = t >> 4;
+                atomicAdd(grad_sdf + ((size_t)(lbz + k) * G.ry + (lby + j)) * (size_t)G.rx + (lbx + i), acc);
+            }
+        }
+        rem &= ~members;
+    }
+    __syncwarp();
+}
+
 template <bool CONV>
 __global__ void __launch_bounds__(kBlock) k_backward(const __grid_constant__ SceneParams sc, const __grid_constant__ PassParams ps,
                                                       const float* __restrict__ film_adj, const float* __restrict__ rec,
@@ -75,32 +110,8 @@ __global__ void __launch_bounds__(kBlock) k_backward(const __grid_constant__ Sce
     }
     for (int q = 0; q < 5; ++q) {
         const bool has = q < sites.n;
-        unsigned rem = __ballot_sync(FULL, has);
-        if (rem == 0u) break;
-        int bx = 0, by = 0, bz = 0, key = -1;
-        if (has) {
-            site_tap_values(sc.G, sites.s[q].x, sites.s[q].phi_hat, sites.s[q].g_hat, bx, by, bz, RowStore{vals[lane_id]});
-            key = (bz * sc.G.ry + by) * sc.G.rx + bx;
-        }
-        __syncwarp();
-        while (rem) {
-            const int leader = __ffs(rem) - 1;
-            const int lkey = __shfl_sync(FULL, key, leader);
-            const unsigned members = __ballot_sync(FULL, has && key == lkey);
-            const int lbx = __shfl_sync(FULL, bx, leader), lby = __shfl_sync(FULL, by, leader), lbz = __shfl_sync(FULL, bz, leader);
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int t = lane_id + 32 * h;
-                float acc = 0.f;
-                for (unsigned m = members; m; m &= m - 1) acc += vals[__ffs(m) - 1][t];
-                if (acc != 0.f && tg.grad_sdf != nullptr) {
-                    const int i = t & 3, j = (t >> 2) & 3, k = t >> 4;
-                    atomicAdd(tg.grad_sdf + ((size_t)(lbz + k) * sc.G.ry + (lby + j)) * (size_t)sc.G.rx + (lbx + i), acc);
-                }
-            }
-            rem &= ~members;
-        }
-        __syncwarp();
+        if (__ballot_sync(FULL, has) == 0u) break;
+        grouped_scatter_round(sc.G, has, sites.s[q].x, sites.s[q].phi_hat, sites.s[q].g_hat, vals, tg.grad_sdf);
     }
     {   // the adjoint sweep's evaluations are counted separately from the marchers'
         const unsigned h = warp_sum(st.n_hess + (CONV ? st.n_value + st.n_grad : 0u)), nsites = warp_sum(st.n_sites), al = warp_sum(st.n_albedo);
@@ -280,6 +291,62 @@ __global__ void __launch_bounds__(kBlock) k_prb_wf_emit(const __grid_constant__ 
     next_segs[idx] = stop.next_active ? make_seg(sc.T, stop.next_o, stop.next_d, INFINITY) : dead;
 }
 
+// Site queue of the replay.  k_prb_backward used to scatter every B-spline site where the walker produced it: 64 red.global.add by ONE
+// thread of a divergent warp, 22 of the kernel's 35 ms at c5 (scripts/prb_timing.py: 15 ms with the scatter switched off).  The walker
+// now only appends the site (position, value adjoint, gradient adjoint: 32 B) to a queue -- opportunistically warp-aggregated, one
+// atomic per converged group -- and k_scatter_sites drains the queue with full warps through the grouped transposed scatter of
+// k_backward.  A site that does not fit into the queue is scattered on the spot, so the capacity is a tuning knob, not a limit.
+struct SiteQueue {
+    float4* a;          // (x, phi_hat)
+    float4* b;          // (g_hat, unused)
+    unsigned* count;    // appended so far (may exceed capacity: the excess was scattered directly)
+    unsigned capacity;
+};
+struct QueueEmit {
+    float* grad_sdf;
+    float* grad_albedo;
+    GridView G;
+    SiteQueue q;
+    __device__ void site(V3 x, float phi_hat, V3 g_hat) {
+        if (grad_sdf == nullptr) return;
+        const unsigned m = __activemask();
+        const int lane_id = threadIdx.x & 31, leader = __ffs(m) - 1;
+        unsigned base = 0;
+        if (lane_id == leader) base = atomicAdd(q.count, (unsigned)__popc(m));
+        base = __shfl_sync(m, base, leader);
+        const unsigned slot = base + (unsigned)__popc(m & ((1u << lane_id) - 1u));
+        if (slot < q.capacity) {
+            q.a[slot] = make_float4(x.x, x.y, x.z, phi_hat);
+            q.b[slot] = make_float4(g_hat.x, g_hat.y, g_hat.z, 0.f);
+        } else {
+            prb_scatter_site(grad_sdf, G, x, phi_hat, g_hat);
+        }
+    }
+    __device__ void albedo(const AlbedoTaps& taps, V3 rho_hat) {
+        if (grad_albedo == nullptr) return;
+        for (int k = 0; k < 8; ++k) {
+            float* t = grad_albedo + (size_t)taps.idx[k] * 3;
+            atomicAdd(t + 0, taps.w[k] * rho_hat.x);
+            atomicAdd(t + 1, taps.w[k] * rho_hat.y);
+            atomicAdd(t + 2, taps.w[k] * rho_hat.z);
+        }
+    }
+};
+__global__ void __launch_bounds__(kBlock) k_scatter_sites(const GridView G, SiteQueue q, float* __restrict__ grad_sdf) {
+    __shared__ float s_vals[kBlock / 32][32][65];
+    float(*vals)[65] = s_vals[threadIdx.x >> 5];
+    const unsigned n = min(*q.count, q.capacity);
+    const unsigned warps = gridDim.x * (kBlock / 32);
+    const unsigned lane_id = threadIdx.x & 31;
+    for (unsigned w = blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5); (unsigned long long)w * 32ull < n; w += warps) {
+        const unsigned i = w * 32u + lane_id;
+        const bool has = i < n;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+        if (has) { a = q.a[i]; b = q.b[i]; }
+        grouped_scatter_round(G, has, V3{a.x, a.y, a.z}, a.w, V3{b.x, b.y, b.z}, vals, grad_sdf);
+    }
+}
+
 // Wavefront form, adjoint sweep 1 with the deferred differentiable march: the segments of one bounce were marched by the VALUE
 // tracer with APPROACH (hit distance in row 0 of their records; a miss whose |phi| stopped growing somewhere comes back as -inf).
 // Only segments that can end with a valid warp record go to the differentiable marcher: misses flagged -inf, and -- for
@@ -310,12 +377,13 @@ __global__ void __launch_bounds__(256) k_prb_flag(const SegIn* __restrict__ segs
     }
 }
 
-template <int MIN_BLOCKS>  // resident blocks per SM the register allocation is tuned for (2: 255 registers, 3: 168)
+template <int MIN_BLOCKS, bool QUEUE>  // MIN_BLOCKS: resident blocks per SM the register allocation is tuned for (2: 255 registers, 3: 168)
 __global__ void __launch_bounds__(kBlock, MIN_BLOCKS) k_prb_backward(const __grid_constant__ SceneParams sc, const __grid_constant__ PassParams ps,
                                                           const float* __restrict__ film_adj, const float* __restrict__ L_rec,
                                                           const float* __restrict__ prim_rec /* rows REC_ITS_T.. of the lane records, or nullptr */,
                                                           PrbRecords recs /* wavefront form: no marching in the replay */,
-                                                          unsigned long long rec_stride, BackwardTargets tg, float* grad_p, Counters* counters) {
+                                                          unsigned long long rec_stride, BackwardTargets tg, float* grad_p, Counters* counters,
+                                                          SiteQueue queue) {
     const int lane_id = threadIdx.x & 31;
     const unsigned long long item = (unsigned long long)blockIdx.x * kBlock + threadIdx.x;
     LaneStats st = {0, 0, 0, 0, 0, 0, 0};
@@ -323,7 +391,8 @@ __global__ void __launch_bounds__(kBlock, MIN_BLOCKS) k_prb_backward(const __gri
     if (item < ps.n_items && (decode_item(ps, item).lane & ~kAntiBit) >= ps.win_lo && (decode_item(ps, item).lane & ~kAntiBit) < ps.win_hi) {
         const WorkItem w = decode_item(ps, item);
         const V3 L = V3{L_rec[item], L_rec[item + rec_stride], L_rec[item + 2 * rec_stride]};
-        DirectEmit em{tg.grad_sdf, tg.grad_albedo, sc.G};
+        typename std::conditional<QUEUE, QueueEmit, DirectEmit>::type em{tg.grad_sdf, tg.grad_albedo, sc.G};
+        if constexpr (QUEUE) em.q = queue;
         PrbPrimary pre;
         if (prim_rec) {
             const float* r = prim_rec + item;
@@ -400,6 +469,9 @@ struct sdfrt_ctx {
         size_t film_adj_capacity = 0;
         float* prb_rec = nullptr;     // sdf_prb_reparam, DIFF sweep: per-vertex march records [max_depth * 18][n_items]
         size_t prb_rec_n = 0;
+        float *siteq_a = nullptr, *siteq_b = nullptr;        // site queue of k_prb_backward (one per view: backprops of views in flight overlap)
+        size_t siteq_a_n = 0, siteq_b_n = 0;
+        unsigned* siteq_count = nullptr;
         float *flag_segs = nullptr, *flag_dest = nullptr;   // deferred differentiable march: segments + record offsets, and
         size_t flag_segs_n = 0, flag_dest_n = 0;           // [0] their count, [1] the marcher's region counter
         unsigned* flag_count = nullptr;
@@ -464,6 +536,9 @@ struct sdfrt_ctx {
     bool prb_wavefront = true;               // sdf_prb_reparam bounce by bounce through k_march (SDFRT_PRB_WAVEFRONT=0: per-lane walker)
     bool prb_primary_wavefront = true;       // camera rays of sdf_prb_reparam through k_march (SDFRT_PRB_PRIMARY=0: per lane)
     int prb_min_blocks = 2;                  // register-allocation variant of k_prb_backward (SDFRT_PRB_OCC)
+    unsigned long long site_queue_cap = 1ull << 27;   // entries (SDFRT_SITEQ_CAP); sites beyond it are scattered in place
+    bool site_queue = true;                  // k_prb_backward appends its scatter sites to a queue drained by k_scatter_sites (SDFRT_SITEQ=0: scatter in place)
+
     int cache_mode[4] = {1, 1, 0, 1};        // tap-cache mode of [value primary, value shadow, diff primary, diff shadow]
     // buffers of the host entry point
     float *h_sdf = nullptr, *h_film = nullptr, *h_film2 = nullptr, *h_image = nullptr, *h_gimg = nullptr, *h_grad = nullptr;
@@ -1102,6 +1177,8 @@ sdfrt_ctx* sdfrt_create(int device, int* status) {
     if (const char* e = std::getenv("SDFRT_SLOTS")) ctx->max_slots = std::max(1, std::min(kSlots, std::atoi(e)));          // developer overrides
     if (const char* e = std::getenv("SDFRT_MIN_LIVE")) ctx->min_live = std::max(1, std::min(32, std::atoi(e)));
     if (const char* e = std::getenv("SDFRT_PRB_OCC")) ctx->prb_min_blocks = std::atoi(e);
+    if (const char* e = std::getenv("SDFRT_SITEQ")) ctx->site_queue = std::atoi(e) != 0;
+    if (const char* e = std::getenv("SDFRT_SITEQ_CAP")) ctx->site_queue_cap = std::max(1ll, std::atoll(e));
     if (const char* e = std::getenv("SDFRT_PRB_WAVEFRONT")) ctx->prb_wavefront = std::atoi(e) != 0;
     if (const char* e = std::getenv("SDFRT_PRB_PRIMARY")) ctx->prb_primary_wavefront = std::atoi(e) != 0;
     if (const char* e = std::getenv("SDFRT_DEFER")) ctx->defer_diff = std::atoi(e) != 0;
@@ -1137,7 +1214,7 @@ void sdfrt_destroy(sdfrt_ctx* ctx) {
     cudaSetDevice(ctx->device);
     for (auto& t : ctx->timed) { cudaEventDestroy(t.second.first); cudaEventDestroy(t.second.second); }
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
-    for (auto& v : ctx->view) { cudaFree(v.rec); cudaFree(v.film_adj); cudaFree(v.prb_rec); cudaFree(v.brick_a); cudaFree(v.brick_b); cudaFree(v.pix_mask); cudaFree(v.flag_segs); cudaFree(v.flag_dest); cudaFree(v.flag_count); }
+    for (auto& v : ctx->view) { cudaFree(v.rec); cudaFree(v.film_adj); cudaFree(v.prb_rec); cudaFree(v.brick_a); cudaFree(v.brick_b); cudaFree(v.pix_mask); cudaFree(v.flag_segs); cudaFree(v.flag_dest); cudaFree(v.flag_count); cudaFree(v.siteq_a); cudaFree(v.siteq_b); cudaFree(v.siteq_count); }
     cudaFree(ctx->counters);
     cudaFree(ctx->work);
     cudaFree(ctx->rows4); cudaFree(ctx->rows8); cudaFree(ctx->brick_raw); cudaFree(ctx->env_buf);
@@ -1475,10 +1552,25 @@ int sdfrt_adjoint_backprop(sdfrt_ctx* ctx, const float* film_accum, const float*
         const float* L_rec = VS(ctx).rec + (size_t)REC_S_STATE * VS(ctx).rec_stride;   // rows 9..11: L of the re-render
         const float* prim = (ctx->prb_primary_wavefront && !ctx->prb_wavefront) ? VS(ctx).rec : nullptr;  // rows 0..8: camera ray's march by k_march
         const PrbRecords recs = ctx->prb_wavefront ? PrbRecords{VS(ctx).prb_rec, ps.n_items, 9} : PrbRecords{nullptr, 0, 9};
-        if (ctx->prb_min_blocks >= 3)
-            k_prb_backward<3><<<(unsigned)blocks, kBlock, 0, st>>>(vsc, ps, VS(ctx).film_adj, L_rec, prim, recs, VS(ctx).rec_stride, tg, grad_p, ctx->counters);
-        else
-            k_prb_backward<2><<<(unsigned)blocks, kBlock, 0, st>>>(vsc, ps, VS(ctx).film_adj, L_rec, prim, recs, VS(ctx).rec_stride, tg, grad_p, ctx->counters);
+        SiteQueue queue{nullptr, nullptr, nullptr, 0u};
+        if (ctx->site_queue && tg.grad_sdf != nullptr) {   // sites go through a queue and the grouped scatter (k_scatter_sites)
+            const size_t cap = (size_t)std::min<unsigned long long>(n, ctx->site_queue_cap);
+            if ((rc = ensure(ctx, &VS(ctx).siteq_a, &VS(ctx).siteq_a_n, cap * 4))) return rc;
+            if ((rc = ensure(ctx, &VS(ctx).siteq_b, &VS(ctx).siteq_b_n, cap * 4))) return rc;
+            if (!VS(ctx).siteq_count) SDFRT_CUDA(ctx, cudaMalloc((void**)&VS(ctx).siteq_count, sizeof(unsigned)));
+            SDFRT_CUDA(ctx, cudaMemsetAsync(VS(ctx).siteq_count, 0, sizeof(unsigned), st));
+            queue = SiteQueue{reinterpret_cast<float4*>(VS(ctx).siteq_a), reinterpret_cast<float4*>(VS(ctx).siteq_b), VS(ctx).siteq_count, (unsigned)cap};
+        }
+#define SDFRT_PRB_BWD_ARGS vsc, ps, VS(ctx).film_adj, L_rec, prim, recs, VS(ctx).rec_stride, tg, grad_p, ctx->counters, queue
+        if (queue.a != nullptr) {
+            if (ctx->prb_min_blocks >= 3) k_prb_backward<3, true><<<(unsigned)blocks, kBlock, 0, st>>>(SDFRT_PRB_BWD_ARGS);
+            else k_prb_backward<2, true><<<(unsigned)blocks, kBlock, 0, st>>>(SDFRT_PRB_BWD_ARGS);
+            k_scatter_sites<<<(unsigned)ctx->num_sms * 8u, kBlock, 0, st>>>(vsc.G, queue, tg.grad_sdf);
+        } else {
+            if (ctx->prb_min_blocks >= 3) k_prb_backward<3, false><<<(unsigned)blocks, kBlock, 0, st>>>(SDFRT_PRB_BWD_ARGS);
+            else k_prb_backward<2, false><<<(unsigned)blocks, kBlock, 0, st>>>(SDFRT_PRB_BWD_ARGS);
+        }
+#undef SDFRT_PRB_BWD_ARGS
     } else {
         LaunchScope ls(ctx, 6, st);
         if (vsc.W.kind == WARP_CONV)   // WarpFieldConvolution: the auxiliary rays are marched inside the adjoint (python/warp_conv.py:185-282)

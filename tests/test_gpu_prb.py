@@ -127,3 +127,34 @@ def test_convex_object_expectation_at_baseline_film_size(sdfrt_mod):
     assert abs(float(img[inside].mean()) - 0.5) < 5e-3
     assert float((img - want).abs().mean()) < 0.02
     assert torch.isfinite(img).all()
+
+
+@pytest.mark.parametrize('env', [{'SDFRT_SITEQ': '0'}, {'SDFRT_SITEQ_CAP': '64'}])
+def test_site_queue_changes_nothing(sdfrt_mod, env):
+    """The replay appends its B-spline sites to a queue that k_scatter_sites drains through the grouped transposed scatter; sites that do
+    not fit are scattered where they arise.  Queue off, and a queue far too small (almost everything takes the overflow path), give the
+    gradient of the default configuration."""
+    from golden import make_golden as MG
+    kind, R, W, spp, ar, max_depth, rr_depth, mrd = MG.PRB_CASES['blobs_tex_prb']
+
+    def grad(extra_env):
+        old = {k: os.environ.get(k) for k in extra_env}
+        os.environ.update(extra_env)
+        try:
+            scene, _ = build_scene(sdfrt_mod, kind, R, W, ar, max_depth, rr_depth, mrd)
+        finally:
+            for k, v in old.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+        sdf = scene.integrator().sdf
+        sdf.data.requires_grad_(True)
+        img = sdfrt_mod.render(scene, sensor=0, seed=MG.SEED, spp=spp, seed_grad=MG.SEED_GRAD, spp_grad=spp)
+        (img * torch.from_numpy(MG.grad_image(W)).float().cuda()).sum().backward()
+        return sdf.data.grad[..., 0].cpu().double(), sdf.ctx.stats(reset=True)
+
+    g0, s0 = grad({})
+    g1, s1 = grad(env)
+    assert g0.abs().max() > 0 and (g0 - g1).norm() < 1e-5 * g0.norm()          # (atomics order only)
+    assert s0['n_scatter_sites'] == s1['n_scatter_sites'] > 256
