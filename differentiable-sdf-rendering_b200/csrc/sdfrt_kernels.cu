@@ -274,6 +274,16 @@ __global__ void __launch_bounds__(kBlock) k_prb_wf_emit(const __grid_constant__ 
                                                          SegIn* __restrict__ next_segs, SegIn* __restrict__ shadow_segs) {
     const unsigned idx = blockIdx.x * kBlock + threadIdx.x;
     if (idx >= cnt) return;
+    SegIn dead;
+    dead.a = make_float4(0.f, 0.f, 0.f, 0.f);
+    dead.b = make_float4(0.f, 0.f, 1.f, -1.f);
+    // a path emits at vertex k only if the segment that ends there hit the surface (three camera samples in four do not even reach
+    // vertex 0): its record decides before anything of the path is re-walked
+    if (!isfinite(recs.base[(size_t)((k * 2) * recs.rows) * recs.stride + idx])) {
+        shadow_segs[idx] = dead;
+        next_segs[idx] = dead;
+        return;
+    }
     const WorkItem w = decode_item(ps, item0 + idx);
     PrbStop stop;
     stop.stop_at = k; stop.shadow_active = false; stop.next_active = false;
@@ -284,9 +294,6 @@ __global__ void __launch_bounds__(kBlock) k_prb_wf_emit(const __grid_constant__ 
     PrbRecords my = recs;
     my.base += idx;
     (void)lane_prb<false>(sc, ps, w.lane, nullptr, v3(0.f), ne, gp, st, nullptr, my, &stop);
-    SegIn dead;
-    dead.a = make_float4(0.f, 0.f, 0.f, 0.f);
-    dead.b = make_float4(0.f, 0.f, 1.f, -1.f);
     shadow_segs[idx] = stop.shadow_active ? make_seg(sc.T, stop.shadow_o, stop.shadow_d, stop.shadow_maxt) : dead;
     next_segs[idx] = stop.next_active ? make_seg(sc.T, stop.next_o, stop.next_d, INFINITY) : dead;
 }
