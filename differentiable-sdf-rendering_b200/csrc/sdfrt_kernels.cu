@@ -538,6 +538,7 @@ struct sdfrt_ctx {
     size_t rows8_n = 0;
     int rows8_roles = 15;                    // role mask (SDFRT_ROWS8; 0 = off): measured best at c3 with every role on the 8x copy
     bool rows8_on = false;
+    bool shade_rows8 = true;   // k_shade's lookup from the 8x row copy (SDFRT_SHADE_ROWS8=0: plain grid)
     int rows4_roles = -1, march_role = 0;
     bool rows4_on = false;
     bool prb_wavefront = true;               // sdf_prb_reparam bounce by bounce through k_march (SDFRT_PRB_WAVEFRONT=0: per-lane walker)
@@ -787,7 +788,7 @@ int enqueue_batch(sdfrt_ctx* ctx, const Sweep& sw, unsigned long long item0, int
             MarchExtra ex;
             ex.dest = fdest; ex.n_slots_dev = work + WQ_FLAG_COUNT; ex.keep_row0 = true;
             LaunchScope ls(ctx, role == 3 ? 3 : 1, bs);
-            launch_march_mode<true>(ctx, role, need, bs, fsegs, nullptr, cnt, region, 0, nullptr, rb, prec.stride, work + WQ_FLAG_CHUNK, ex);
+            launch_march_mode<true>(ctx, role, need, bs, fsegs, nullptr, cnt, 256u /* short lists: small work units */, 0, nullptr, rb, prec.stride, work + WQ_FLAG_CHUNK, ex);
             return SDFRT_OK;
         };
         for (int k = 0; k < max_depth; ++k) {
@@ -832,9 +833,15 @@ int enqueue_batch(sdfrt_ctx* ctx, const Sweep& sw, unsigned long long item0, int
         return SDFRT_OK;
     }
     { LaunchScope ls(ctx, 2, bs);
-      k_shade<DIFF><<<regions, 256, 0, bs>>>(ctx->sc, ps, item0, cnt, region, reinterpret_cast<const SegIn*>(sc.segs), its, q, qb, film,
-                                             DIFF ? rec_b + REC_S_STATE * VS(ctx).rec_stride : nullptr,
-                                             (DIFF && mis) ? rec_b + REC_B_STATE * VS(ctx).rec_stride : nullptr, ctx->counters); }
+      float* rs = DIFF ? rec_b + REC_S_STATE * VS(ctx).rec_stride : nullptr;
+      float* rbs = (DIFF && mis) ? rec_b + REC_B_STATE * VS(ctx).rec_stride : nullptr;
+      if (ctx->rows8_on && ctx->shade_rows8) {
+          SceneParams scs = ctx->sc;
+          scs.G.rows8 = ctx->rows8;
+          k_shade<DIFF, true><<<regions, 256, 0, bs>>>(scs, ps, item0, cnt, region, reinterpret_cast<const SegIn*>(sc.segs), its, q, qb, film, rs, rbs, ctx->counters);
+      } else {
+          k_shade<DIFF, false><<<regions, 256, 0, bs>>>(ctx->sc, ps, item0, cnt, region, reinterpret_cast<const SegIn*>(sc.segs), its, q, qb, film, rs, rbs, ctx->counters);
+      } }
     if (ctx->sc.integrator == INTEGRATOR_DIRECT) {
         // shadow march over the region-compacted queue.  The differentiable tracer is only needed if shadow rays are
         // reparameterised (python/warp.py:103: max_reparam_depth); otherwise the value tracer's its_t is all the pass uses.
@@ -1185,6 +1192,7 @@ sdfrt_ctx* sdfrt_create(int device, int* status) {
     if (const char* e = std::getenv("SDFRT_MIN_LIVE")) ctx->min_live = std::max(1, std::min(32, std::atoi(e)));
     if (const char* e = std::getenv("SDFRT_PRB_OCC")) ctx->prb_min_blocks = std::atoi(e);
     if (const char* e = std::getenv("SDFRT_SITEQ")) ctx->site_queue = std::atoi(e) != 0;
+    if (const char* e = std::getenv("SDFRT_SHADE_ROWS8")) ctx->shade_rows8 = std::atoi(e) != 0;
     if (const char* e = std::getenv("SDFRT_SITEQ_CAP")) ctx->site_queue_cap = std::max(1ll, std::atoll(e));
     if (const char* e = std::getenv("SDFRT_PRB_WAVEFRONT")) ctx->prb_wavefront = std::atoi(e) != 0;
     if (const char* e = std::getenv("SDFRT_PRB_PRIMARY")) ctx->prb_primary_wavefront = std::atoi(e) != 0;

@@ -604,7 +604,9 @@ struct ShadowQueue {
     int4* box;        // [n_regions] or nullptr: origin (block-base texel coordinates) of the SMEM box of the region's shadow rays, w = valid
 };
 
-template <bool DIFF>
+// R8: the order-1 lookup at the hit point reads the marchers' 8x row copy (8 x 256-bit loads instead of 64 scalar ones; same taps,
+// same reduction, bit-identical result) -- the kernel is bound by the L1 data stage (ncu: l1tex__throughput 83 %).
+template <bool DIFF, bool R8 = false>
 __global__ void __launch_bounds__(256, 3) k_shade(const __grid_constant__ SceneParams sc, const __grid_constant__ PassParams ps,
                                                 unsigned long long item0, unsigned n, unsigned region, const SegIn* __restrict__ psegs,
                                                 const float* __restrict__ its, ShadowQueue q, ShadowQueue qb /* use_mis: BSDF-sampled rays */,
@@ -652,7 +654,15 @@ __global__ void __launch_bounds__(256, 3) k_shade(const __grid_constant__ SceneP
             } else {
                 const V3 p = r.o + its_t * r.d;
                 float phi; V3 g; S3 H;
-                eval_sdf<1>(sc.G, p, phi, g, H);
+                if constexpr (R8) {
+                    CellSetup<1> cs;
+                    cell_setup<1>(sc.G, p, cs);
+                    float f[64];
+                    load_taps<8>(sc.G, cs.bx, cs.by, cs.bz, f);
+                    reduce_taps<1>(f, cs, sc.G, phi, g, H);
+                } else {
+                    eval_sdf<1>(sc.G, p, phi, g, H);
+                }
                 ++n_grad;
                 const V3 nrm = normalize(g);
                 if (sc.integrator == INTEGRATOR_SIMPLE_SHADING) {

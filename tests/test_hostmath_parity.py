@@ -450,3 +450,19 @@ def test_convolution_warp_sampling_functions():
     n = O.normalize(torch.from_numpy(np.random.default_rng(1).normal(size=(100, 3))))
     s, t = O.coordinate_system(n)
     assert (O.dot(s, t).abs().max() < 1e-12) and (O.dot(s, n).abs().max() < 1e-12) and ((torch.linalg.cross(s, t) - n).abs().max() < 1e-12)
+
+
+def test_convolution_warp_with_antithetic_sampling():
+    """antithetic_sampling + WarpFieldConvolution: the mirrored sample runs on a CLONE of the sampler taken after the jitter draw
+    (python/integrators/reparam.py:171-178), so its auxiliary draws continue the same stream positions as the first sample's."""
+    W, spp = 12, 2
+    sc, wf, hs = make_pair('sphere', 24, W, 'sdf_direct_reparam', warp=dict(kind=3, n_aux_rays=3))
+    hs.h.antithetic = 1
+    g_in = np.random.default_rng(5).uniform(-1, 1, size=(W, W, 3))
+    img_o, g_o, gp_o, _ = O.render_backward(sc, wf, 'sdf_direct_reparam', torch.from_numpy(g_in), seed=11, spp=spp, antithetic=True)
+    film, rec, _ = hs.forward(11, spp, True)
+    assert np.abs(hs.develop(film) - img_o.numpy()).max() < 2e-5
+    g_h, _, gp_h, _ = hs.backward(11, spp, film, rec, g_in)
+    g_o = g_o.numpy()
+    assert np.linalg.norm(g_h - g_o) < 2e-3 * np.linalg.norm(g_o)
+    assert np.abs(gp_h - gp_o.numpy()).max() < 2e-3 * np.abs(gp_o.numpy()).max()
