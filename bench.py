@@ -47,8 +47,10 @@ BINDING = {   # round-2 captures of the shipped kernels (ncu --set full, one bat
     'k_gen_primary': {"unit": "issue (smsp__issue_active)", "pct": 86, "source": "profiles/r2_call3/r2_c3_value.md"},
     'k_backward': {"unit": "latency: long_scoreboard 2.1 + no_instruction 1.8 stall cycles per issue (grouped transposed scatter)", "pct": None,
                    "issue_active_pct": 34, "source": "profiles/r2_call3/r2_c3_backward.md"},
-    'k_prb_backward (c5)': {"unit": "instruction fetch: no_instruction 7.2 + long_scoreboard 5.5 stall cycles per issue", "pct": None, "issue_active_pct": 11,
-                            "source": "profiles/r2_call3/r2_c5_prb_bwd.md"},
+    'k_prb_backward (c5, sites queued)': {"unit": "latency at 8 resident warps per SM (255 registers): long_scoreboard 3.1 + no_instruction 2.2 stall cycles per issue",
+                                          "pct": None, "issue_active_pct": 20, "source": "profiles/r2_call15/r2_c5_prb_bwd_queue.md"},
+    'k_scatter_sites (c5)': {"unit": "shared-memory transpose (short_scoreboard 3.0) + RED", "pct": None, "issue_active_pct": 50,
+                             "source": "profiles/r2_call15/r2_c5_prb_bwd_queue.md"},
 }
 
 

@@ -303,12 +303,7 @@ __global__ void __launch_bounds__(kBlock) k_prb_wf_emit(const __grid_constant__ 
 // now only appends the site (position, value adjoint, gradient adjoint: 32 B) to a queue -- opportunistically warp-aggregated, one
 // atomic per converged group -- and k_scatter_sites drains the queue with full warps through the grouped transposed scatter of
 // k_backward.  A site that does not fit into the queue is scattered on the spot, so the capacity is a tuning knob, not a limit.
-struct SiteQueue {
-    float4* a;          // (x, phi_hat)
-    float4* b;          // (g_hat, unused)
-    unsigned* count;    // appended so far (may exceed capacity: the excess was scattered directly)
-    unsigned capacity;
-};
+// (struct SiteQueue: sdfrt_lane.cuh -- the convolution warp's adjoint appends to the same kind of queue.)
 struct QueueEmit {
     float* grad_sdf;
     float* grad_albedo;
@@ -538,7 +533,7 @@ struct sdfrt_ctx {
     size_t rows8_n = 0;
     int rows8_roles = 15;                    // role mask (SDFRT_ROWS8; 0 = off): measured best at c3 with every role on the 8x copy
     bool rows8_on = false;
-    bool shade_rows8 = true;   // k_shade's lookup from the 8x row copy (SDFRT_SHADE_ROWS8=0: plain grid)
+    bool shade_rows8 = false;  // k_shade's lookup from the 8x row copy (SDFRT_SHADE_ROWS8=1): measured 2755 vs 2757 Mrays/s at c3 -- no gain, off
     int rows4_roles = -1, march_role = 0;
     bool rows4_on = false;
     bool prb_wavefront = true;               // sdf_prb_reparam bounce by bounce through k_march (SDFRT_PRB_WAVEFRONT=0: per-lane walker)
@@ -1561,21 +1556,25 @@ int sdfrt_adjoint_backprop(sdfrt_ctx* ctx, const float* film_accum, const float*
     BackwardTargets tg;
     tg.grad_sdf = grad_sdf;
     tg.grad_albedo = grad_albedo;
+    tg.queue = SiteQueue{nullptr, nullptr, nullptr, 0u};
     const unsigned long long blocks = (n + kBlock - 1) / kBlock;
+    auto make_queue = [&](SiteQueue& q) -> int {   // per-view site queue (views in flight run their adjoints concurrently)
+        const size_t cap = (size_t)std::min<unsigned long long>(n, ctx->site_queue_cap);
+        int r;
+        if ((r = ensure(ctx, &VS(ctx).siteq_a, &VS(ctx).siteq_a_n, cap * 4))) return r;
+        if ((r = ensure(ctx, &VS(ctx).siteq_b, &VS(ctx).siteq_b_n, cap * 4))) return r;
+        if (!VS(ctx).siteq_count) SDFRT_CUDA(ctx, cudaMalloc((void**)&VS(ctx).siteq_count, sizeof(unsigned)));
+        SDFRT_CUDA(ctx, cudaMemsetAsync(VS(ctx).siteq_count, 0, sizeof(unsigned), st));
+        q = SiteQueue{reinterpret_cast<float4*>(VS(ctx).siteq_a), reinterpret_cast<float4*>(VS(ctx).siteq_b), VS(ctx).siteq_count, (unsigned)cap};
+        return SDFRT_OK;
+    };
     if (vsc.integrator == INTEGRATOR_PRB) {
         LaunchScope ls(ctx, 6, st);
         const float* L_rec = VS(ctx).rec + (size_t)REC_S_STATE * VS(ctx).rec_stride;   // rows 9..11: L of the re-render
         const float* prim = (ctx->prb_primary_wavefront && !ctx->prb_wavefront) ? VS(ctx).rec : nullptr;  // rows 0..8: camera ray's march by k_march
         const PrbRecords recs = ctx->prb_wavefront ? PrbRecords{VS(ctx).prb_rec, ps.n_items, 9} : PrbRecords{nullptr, 0, 9};
         SiteQueue queue{nullptr, nullptr, nullptr, 0u};
-        if (ctx->site_queue && tg.grad_sdf != nullptr) {   // sites go through a queue and the grouped scatter (k_scatter_sites)
-            const size_t cap = (size_t)std::min<unsigned long long>(n, ctx->site_queue_cap);
-            if ((rc = ensure(ctx, &VS(ctx).siteq_a, &VS(ctx).siteq_a_n, cap * 4))) return rc;
-            if ((rc = ensure(ctx, &VS(ctx).siteq_b, &VS(ctx).siteq_b_n, cap * 4))) return rc;
-            if (!VS(ctx).siteq_count) SDFRT_CUDA(ctx, cudaMalloc((void**)&VS(ctx).siteq_count, sizeof(unsigned)));
-            SDFRT_CUDA(ctx, cudaMemsetAsync(VS(ctx).siteq_count, 0, sizeof(unsigned), st));
-            queue = SiteQueue{reinterpret_cast<float4*>(VS(ctx).siteq_a), reinterpret_cast<float4*>(VS(ctx).siteq_b), VS(ctx).siteq_count, (unsigned)cap};
-        }
+        if (ctx->site_queue && tg.grad_sdf != nullptr && (rc = make_queue(queue))) return rc;   // sites go through a queue and the grouped scatter (k_scatter_sites)
 #define SDFRT_PRB_BWD_ARGS vsc, ps, VS(ctx).film_adj, L_rec, prim, recs, VS(ctx).rec_stride, tg, grad_p, ctx->counters, queue
         if (queue.a != nullptr) {
             if (ctx->prb_min_blocks >= 3) k_prb_backward<3, true><<<(unsigned)blocks, kBlock, 0, st>>>(SDFRT_PRB_BWD_ARGS);
@@ -1588,9 +1587,11 @@ int sdfrt_adjoint_backprop(sdfrt_ctx* ctx, const float* film_accum, const float*
 #undef SDFRT_PRB_BWD_ARGS
     } else {
         LaunchScope ls(ctx, 6, st);
-        if (vsc.W.kind == WARP_CONV)   // WarpFieldConvolution: the auxiliary rays are marched inside the adjoint (python/warp_conv.py:185-282)
+        if (vsc.W.kind == WARP_CONV) {   // WarpFieldConvolution: the auxiliary rays are marched inside the adjoint (python/warp_conv.py:185-282)
+            if (ctx->site_queue && tg.grad_sdf != nullptr && (rc = make_queue(tg.queue))) return rc;   // one site per auxiliary hit: queued like the replay's
             k_backward<true><<<(unsigned)blocks, kBlock, 0, st>>>(vsc, ps, VS(ctx).film_adj, VS(ctx).rec, VS(ctx).rec_stride, tg, grad_p, ctx->counters);
-        else
+            if (tg.queue.a != nullptr) k_scatter_sites<<<(unsigned)ctx->num_sms * 8u, kBlock, 0, st>>>(vsc.G, tg.queue, tg.grad_sdf);
+        } else
             k_backward<false><<<(unsigned)blocks, kBlock, 0, st>>>(vsc, ps, VS(ctx).film_adj, VS(ctx).rec, VS(ctx).rec_stride, tg, grad_p, ctx->counters);
     }
     SDFRT_CUDA(ctx, cudaGetLastError());

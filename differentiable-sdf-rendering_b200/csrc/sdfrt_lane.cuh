@@ -478,6 +478,40 @@ SDFRT_HD void push_site(SiteList& L, V3 x, float phi_hat, V3 g_hat) {
     ++L.n;
 }
 
+// Queue of scatter sites (device): producers append (position, value adjoint, gradient adjoint), k_scatter_sites drains it with full
+// warps through the grouped transposed scatter.  a == nullptr: no queue, sites are scattered where they arise.
+struct SiteQueue {
+    float4* a;          // (x, phi_hat)
+    float4* b;          // (g_hat, unused)
+    unsigned* count;    // appended so far (may exceed capacity: the excess was scattered directly)
+    unsigned capacity;
+};
+struct BackwardTargets {
+    float* grad_sdf;     // (rz, ry, rx), accumulated (by the caller, from the SiteList)
+    float* grad_albedo;  // (rz, ry, rx, 3) or nullptr
+    SiteQueue queue;     // sites produced inside the lane code (convolution warp: one per auxiliary hit)
+};
+// value-only site of the convolution warp's adjoint: into the queue if there is one (opportunistic warp aggregation), else in place
+SDFRT_HD void emit_value_site(const BackwardTargets& tg, const GridView& G, V3 x, float phi_hat) {
+    if (tg.grad_sdf == nullptr) return;
+#if defined(__CUDA_ARCH__)
+    if (tg.queue.a != nullptr) {
+        const unsigned m = __activemask();
+        const int lane_id = threadIdx.x & 31, leader = __ffs(m) - 1;
+        unsigned base = 0;
+        if (lane_id == leader) base = atomicAdd(tg.queue.count, (unsigned)__popc(m));
+        base = __shfl_sync(m, base, leader);
+        const unsigned slot = base + (unsigned)__popc(m & ((1u << lane_id) - 1u));
+        if (slot < tg.queue.capacity) {
+            tg.queue.a[slot] = float4{x.x, x.y, x.z, phi_hat};
+            tg.queue.b[slot] = float4{0.f, 0.f, 0.f, 0.f};
+            return;
+        }
+    }
+#endif
+    scatter_site(tg.grad_sdf, G, x, phi_hat, v3(0.f));
+}
+
 // ------------------------------------------------------------------------------------------------
 // WarpFieldConvolution (Bangaru et al. 2020; python/warp.py:126-176, python/warp_conv.py) -- the comparison baseline.
 // The reference's reparameterisation is a CustomOp whose primal returns (ray.d, 0): the auxiliary rays are only traced when
@@ -533,8 +567,9 @@ SDFRT_HD void rng_skip(Pcg32& rng, int n) {
     for (int i = 0; i < n; ++i) (void)pcg_next_u32(rng);
 }
 // Adjoint of one reparameterised ray.  g_dir / g_div: adjoints of the returned direction and divergence.  Draws 2 n_aux_rays samples
-// from `rng` whatever happens.  Scatters into grad_sdf (may be null), accumulates dL/d(sdf.p) and returns dL/d(ray origin).
-SDFRT_HD V3 conv_reparam_adjoint(const SceneParams& sc, V3 o, V3 d, float maxt, Pcg32& rng, V3 g_dir, float g_div, float* grad_sdf,
+// from `rng` whatever happens.  Emits one value-only site per auxiliary hit (tg.grad_sdf may be null), accumulates dL/d(sdf.p) and
+// returns dL/d(ray origin).
+SDFRT_HD V3 conv_reparam_adjoint(const SceneParams& sc, V3 o, V3 d, float maxt, Pcg32& rng, V3 g_dir, float g_div, const BackwardTargets& tg,
                                  V3& grad_p, LaneStats& st) {
     const int N = sc.W.n_aux_rays < kMaxAuxRays ? sc.W.n_aux_rays : kMaxAuxRays;
     const float kappa = sc.W.kappa, power = sc.W.power;
@@ -588,7 +623,7 @@ SDFRT_HD V3 conv_reparam_adjoint(const SceneParams& sc, V3 o, V3 d, float maxt, 
         const V3 q_hat = (V_hat - dot(a.omega, V_hat) * a.omega) / its[i];   // through normalize(p - o), |p - o| = its_t
         const float phi_hat = -dot(g, q_hat) / gg;                           // W = -(g / |g|^2) phi(p)
         if (!isfinite(phi_hat) | !isfinite(q_hat.x + q_hat.y + q_hat.z)) continue;
-        if (grad_sdf != nullptr) scatter_site(grad_sdf, sc.G, p, phi_hat, v3(0.f));
+        emit_value_site(tg, sc.G, p, phi_hat);
         st.n_sites += 1;
         grad_p = grad_p - phi_hat * g;
         o_hat = o_hat - q_hat;
@@ -596,10 +631,6 @@ SDFRT_HD V3 conv_reparam_adjoint(const SceneParams& sc, V3 o, V3 d, float maxt, 
     return o_hat;
 }
 
-struct BackwardTargets {
-    float* grad_sdf;     // (rz, ry, rx), accumulated (by the caller, from the SiteList)
-    float* grad_albedo;  // (rz, ry, rx, 3) or nullptr
-};
 
 // ------------------------------------------------------------------------------------------------
 // backward lane.  film_adj: (Hb, Wb, 4) = (dL/dV_rgb, dL/dWt) per film pixel (see k_film_adjoint).
@@ -813,7 +844,7 @@ SDFRT_HD void lane_backward(const SceneParams& sc, const PassParams& ps, unsigne
             // BSDF-sampled ray's warp site: spawned from the attached interaction (si.spawn_ray, :93), direction detached -- only its
             // divergence carries a derivative
             if (CONV && bsdf_hit_env && conv_at_depth(sc.W, 1)) {
-                const V3 ob_hat = conv_reparam_adjoint(sc, br.o, br.d, INFINITY, rng_b, db_hat, dot(c_hat, rgb_b), tg.grad_sdf, grad_p, st);
+                const V3 ob_hat = conv_reparam_adjoint(sc, br.o, br.d, INFINITY, rng_b, db_hat, dot(c_hat, rgb_b), tg, grad_p, st);
                 p_hat += ob_hat;
             }
             if (bsdf_hit_env && reparam_at_depth(sc.W, 1)) {
@@ -836,7 +867,7 @@ SDFRT_HD void lane_backward(const SceneParams& sc, const PassParams& ps, unsigne
                 }
             }
             if (CONV && nee && conv_at_depth(sc.W, 1)) {
-                const V3 os_hat = conv_reparam_adjoint(sc, sr.o, sr.d, sr.maxt, rng_s, ds_hat, div_s_hat, tg.grad_sdf, grad_p, st);
+                const V3 os_hat = conv_reparam_adjoint(sc, sr.o, sr.d, sr.maxt, rng_s, ds_hat, div_s_hat, tg, grad_p, st);
                 if (sc.Sh.shadow_origin == 0) {
                     p_hat += os_hat;
                 } else if (sc.Sh.shadow_origin == 2) {
@@ -892,7 +923,7 @@ SDFRT_HD void lane_backward(const SceneParams& sc, const PassParams& ps, unsigne
     }
 
     // ---- primary warp site ---------------------------------------------------------------------------
-    if (CONV && conv_at_depth(sc.W, 0)) (void)conv_reparam_adjoint(sc, o, d0, cs.maxt, rng_p, d_hat, div_hat, tg.grad_sdf, grad_p, st);
+    if (CONV && conv_at_depth(sc.W, 0)) (void)conv_reparam_adjoint(sc, o, d0, cs.maxt, rng_p, d_hat, div_hat, tg, grad_p, st);
     if (reparam_at_depth(sc.W, 0)) {
         const V3 tau_d = V3{r[REC_TAU_DX * rec_stride], r[REC_TAU_DY * rec_stride], r[REC_TAU_DZ * rec_stride]};
         const V3 om_d = V3{r[REC_OMEGA_DX * rec_stride], r[REC_OMEGA_DY * rec_stride], r[REC_OMEGA_DZ * rec_stride]};

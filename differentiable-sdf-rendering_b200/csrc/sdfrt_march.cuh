@@ -605,7 +605,8 @@ struct ShadowQueue {
 };
 
 // R8: the order-1 lookup at the hit point reads the marchers' 8x row copy (8 x 256-bit loads instead of 64 scalar ones; same taps,
-// same reduction, bit-identical result) -- the kernel is bound by the L1 data stage (ncu: l1tex__throughput 83 %).
+// same reduction, bit-identical result).  Measured at c3: 30.92 vs 30.90 ms per step -- the lookup is not what binds the kernel's L1
+// data stage (the reflectance gather and the splat are); kept as an option (SDFRT_SHADE_ROWS8=1), off by default.
 template <bool DIFF, bool R8 = false>
 __global__ void __launch_bounds__(256, 3) k_shade(const __grid_constant__ SceneParams sc, const __grid_constant__ PassParams ps,
                                                 unsigned long long item0, unsigned n, unsigned region, const SegIn* __restrict__ psegs,

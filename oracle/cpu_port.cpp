@@ -144,7 +144,7 @@ int cp_time_sample(const cp_scene* h, unsigned seed, int spp_primal, int spp_adj
         o[0] = o[1] = o[2] = iw;
         o[3] = -(a[0] + a[1] + a[2]) * iw * iw;
     }
-    BackwardTargets tg; tg.grad_sdf = grad_sdf; tg.grad_albedo = nullptr;
+    BackwardTargets tg; tg.grad_sdf = grad_sdf; tg.grad_albedo = nullptr; tg.queue = SiteQueue{nullptr, nullptr, nullptr, 0u};
 #pragma omp parallel for schedule(dynamic, 64) reduction(+ : nh)
     for (long long k = 0; k < n_adjoint; ++k) {
         const long long l = k;

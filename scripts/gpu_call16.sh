@@ -1,6 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q -k "prb or deferred or golden or parity" > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest.log
+timeout 900 python -m pytest tests -m gpu -q -k "prb or deferred or golden or parity or convolution" > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest.log
+timeout 600 python scripts/conv_timing.py > gpurun_out/conv_timing.log 2>&1; echo "conv rc=$?"; tail -7 gpurun_out/conv_timing.log
 timeout 600 python scripts/prb_timing.py > gpurun_out/prb_timing.log 2>&1; echo "prb rc=$?"; grep "_ms" gpurun_out/prb_timing.log | tail -4
 for v in 1 0; do
 SDFRT_SHADE_ROWS8=$v timeout 600 python bench.py --steps 12 --warmup 3 --no-secondary --no-e2e --no-grad-check --no-cpu-baseline > gpurun_out/bench_c3_shade$v.json 2> gpurun_out/bench_c3_shade$v.err; echo "c3 shade_rows8=$v rc=$?"

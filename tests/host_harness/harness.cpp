@@ -171,7 +171,7 @@ int hh_backward(const hh_scene* h, unsigned seed, int spp, const float* film, co
             o[0] = g[0] * iw; o[1] = g[1] * iw; o[2] = g[2] * iw;
             o[3] = -(g[0] * a[0] + g[1] * a[1] + g[2] * a[2]) * iw * iw;
         }
-    BackwardTargets tg; tg.grad_sdf = grad_sdf; tg.grad_albedo = grad_albedo;
+    BackwardTargets tg; tg.grad_sdf = grad_sdf; tg.grad_albedo = grad_albedo; tg.queue = SiteQueue{nullptr, nullptr, nullptr, 0u};
     LaneStats st = {0, 0, 0, 0, 0, 0, 0};
     V3 gp = v3(0.f);
     const unsigned long long n = ps.n_items;
