@@ -66,6 +66,8 @@ def parse():
     ap.add_argument('--no-grad-check', action='store_true', help='skip the lane-subsample gradient check against the oracle')
     ap.add_argument('--no-e2e', action='store_true', help='profiling runs: skip the host-buffer leg')
     ap.add_argument('--views-in-flight', type=int, default=2, help='independent views (steps) enqueued concurrently on separate streams / view slots')
+    ap.add_argument('--partition-rows', type=int, default=8, choices=[1, 2, 4, 8], help='film rows per unit of the interleaved row partition')
+    ap.add_argument('--partition-rank', type=int, default=0, help='tuning: which rank of --partition-of to emulate')
     ap.add_argument('--partition-of', type=int, default=0, help='tuning: render rank 0 of a partition into this many ranks on one GPU (no collectives)')
     return ap.parse_args()
 
@@ -231,7 +233,7 @@ def run_reference(args):
 class Job:
     """One workload bound to a context: buffers + the step function (device buffers resident; one optimisation-loop view)."""
 
-    def __init__(self, wl, local, rank, world, inflight=2, partition_of=0):
+    def __init__(self, wl, local, rank, world, inflight=2, partition_of=0, partition_rank=0, partition_rows=8):
         import torch
         import sdfrt
         from sdfrt import synthetic as syn
@@ -255,10 +257,11 @@ class Job:
         else:
             ctx.set_integrator('sdf_direct_reparam')
         ctx.set_warp()
+        self.partition_rows = partition_rows
         if partition_of > 1:
-            ctx.set_partition(0, partition_of)
+            ctx.set_partition(partition_rank, partition_of, partition_rows)
         else:
-            ctx.set_partition(rank, world)
+            ctx.set_partition(rank, world, partition_rows)
         Hb, Wb, b = ctx.film_dims()
         self.n_primal, self.n_adj = Hb * Wb * spp * mult, Hb * Wb * spp
         self.rays_per_step = self.n_primal + self.n_adj
@@ -270,9 +273,13 @@ class Job:
         self.inflight = max(1, min(inflight, ctx.num_view_slots()))
         self.lanes = []
         for k in range(self.inflight):
-            self.lanes.append(dict(stream=self.stream if self.inflight == 1 else torch.cuda.Stream(dev), film_p=ctx.new_film(), film_a=ctx.new_film(),
-                                   image=torch.empty((H, W, 3), device=dev), grad_sdf=torch.zeros_like(self.sdf),
-                                   grad_alb=None if self.alb is None else torch.zeros_like(self.alb)))
+            # the two film accumulators and the two gradient grids of a view live in one allocation each: one collective per pair
+            films = torch.empty((2, Hb, Wb, 4), device=dev)
+            nv, na = self.sdf.numel(), 0 if self.alb is None else self.alb.numel()
+            grads = torch.zeros(nv + na, device=dev)
+            self.lanes.append(dict(stream=self.stream if self.inflight == 1 else torch.cuda.Stream(dev), films=films, film_p=films[0], film_a=films[1],
+                                   image=torch.empty((H, W, 3), device=dev), grads=grads, grad_sdf=grads[:nv].view(self.sdf.shape),
+                                   grad_alb=None if self.alb is None else grads[nv:].view(self.alb.shape)))
         self.grad_sdf, self.grad_alb = self.lanes[0]['grad_sdf'], self.lanes[0]['grad_alb']
         self.n_step = 0
 
@@ -290,19 +297,14 @@ class Job:
             ctx.set_view_slot(k)
             ctx.render_view(seed, self.spp * self.mult, seed + 1 + self.nsens, self.spp, L['film_p'], L['film_a'])
             if world > 1:
-                dist.all_reduce(L['film_p'])
-                dist.all_reduce(L['film_a'])
+                dist.all_reduce(L['films'])     # primal film + film of adjoint sweep 1
             ctx.develop(L['film_p'], L['image'])
             if ev:
                 ev[1].record()
-            L['grad_sdf'].zero_()
-            if L['grad_alb'] is not None:
-                L['grad_alb'].zero_()
+            L['grads'].zero_()
             ctx.adjoint_backprop(L['film_a'], self.grad_image, L['grad_sdf'], L['grad_alb'])
             if world > 1:
-                dist.all_reduce(L['grad_sdf'])
-                if L['grad_alb'] is not None:
-                    dist.all_reduce(L['grad_alb'])
+                dist.all_reduce(L['grads'])     # dL/d(sdf) + dL/d(reflectance grid): the one large collective per backward
             if ev:
                 ev[2].record()
 
@@ -443,7 +445,7 @@ def grad_check(job, n_lanes=16384):
     ga = None if job.alb is None else torch.zeros_like(job.alb)
     ctx.adjoint_backprop(film, torch.from_numpy(G).to(job.dev), g, ga)
     ctx.set_lane_window(0, 0)
-    ctx.set_partition(job.rank, job.world)
+    ctx.set_partition(job.rank, job.world, job.partition_rows)
     _, g_o, ga_o = WC.window_gradient(osc, owf, 'sdf_direct_reparam', film.cpu().numpy(), G, seed_grad, job.spp, (lo, hi))
     out = {"vs": "fp64 oracle (oracle/sdf_oracle.py, torch autograd) on the same lanes", "lanes": [lo, hi],
            "grad_image": "uniform(-1,1), seed 4", "sdf": WC.gradient_errors(g.cpu().numpy(), g_o.numpy())}
@@ -624,7 +626,7 @@ def run_gpu(args):
     peak = float(peaks.get('hbm_gbs', 6650.0))
     peak_src = 'measured (MEASURED_PEAKS.json, burst copy)' if 'hbm_gbs' in peaks else 'fallback (B200_PROFILING.md)'
 
-    job = Job(args.workload, local, rank, world, args.views_in_flight, args.partition_of)
+    job = Job(args.workload, local, rank, world, args.views_in_flight, args.partition_of, args.partition_rank, args.partition_rows)
     ms, stats, passes, clocks = job.timed(args.steps, args.warmup, clocks=True)
     value = job.rays_per_step * args.steps / (ms * 1e-3) / 1e6
     n_cam = stats['n_rays'] + 0   # camera samples this rank shaded (marched or culled)
@@ -635,7 +637,7 @@ def run_gpu(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "sdf_res": job.R, "albedo_res": job.AR, "film": [job.W, job.H],
                        "spp_primal": job.spp * job.mult, "spp_adjoint": job.spp, "rays_per_step": job.rays_per_step,
-                       "partition": f"interleaved 8-row film bands x{world}" + (f" (tuning: rank 0 of {args.partition_of} on one GPU, no collectives)" if args.partition_of > 1 else ""),
+                       "partition": f"interleaved {args.partition_rows}-row film sub-bands x{world}, walked in 8-row tiles" + (f" (tuning: rank {args.partition_rank} of {args.partition_of} on one GPU, no collectives)" if args.partition_of > 1 else ""),
                        "views_in_flight": job.inflight,
                        **({"integrator": "sdf_prb_reparam", **job.prb} if job.prb else {}),
                        "l2": "inputs (sdf+albedo+grads+lane records > 1 GB) exceed L2; no explicit flush"},

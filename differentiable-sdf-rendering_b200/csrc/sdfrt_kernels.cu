@@ -451,6 +451,7 @@ struct sdfrt_ctx {
     float to_world[16];      // Grid3d's transform (row-major) when has_xf
     bool has_xf = false;
     int shadow_origin = 0;   // sdf_direct_reparam props detach_indirect_si (1) / decouple_reparam (2)
+    int assign_rows = kBandRows;   // granularity of the row partition (sdfrt_set_partition_rows)
     int use_mis = 0;         // ReparamIntegrator prop use_mis (python/integrators/reparam.py:17)
     float* env_buf = nullptr;   // `envmap` emitter: bitmap + sampling tables in one allocation (sc.E points into it)
     int antithetic = 0;  // ReparamIntegrator.antithetic_sampling (python/integrators/reparam.py:19); not used by sdf_prb_reparam
@@ -1400,14 +1401,17 @@ int sdfrt_set_prb(sdfrt_ctx* ctx, const sdfrt_prb_params* p) {
     return SDFRT_OK;
 }
 
-int sdfrt_set_partition(sdfrt_ctx* ctx, int rank, int world) {
+int sdfrt_set_partition_rows(sdfrt_ctx* ctx, int rank, int world, int rows) {
     if (!ctx) return SDFRT_ERR_INVALID;
     if (world < 1 || rank < 0 || rank >= world) return fail(ctx, SDFRT_ERR_INVALID, "bad partition");
+    if (rows != 1 && rows != 2 && rows != 4 && rows != 8) return fail(ctx, SDFRT_ERR_INVALID, "partition granularity must be 1, 2, 4 or 8 film rows");
     ctx->rank = rank;
     ctx->world = world;
+    ctx->assign_rows = rows;
     VS(ctx).adj_ready = false;
     return SDFRT_OK;
 }
+int sdfrt_set_partition(sdfrt_ctx* ctx, int rank, int world) { return sdfrt_set_partition_rows(ctx, rank, world, kBandRows); }
 
 int sdfrt_set_lane_window(sdfrt_ctx* ctx, uint64_t lane_lo, uint64_t lane_hi) {
     if (!ctx) return SDFRT_ERR_INVALID;
@@ -1455,10 +1459,10 @@ int sdfrt_render_primal(sdfrt_ctx* ctx, uint32_t seed, int spp, float* film_accu
     if (!film_accum) return fail(ctx, SDFRT_ERR_INVALID, "film_accum is null");
     const bool prb = ctx->sc.integrator == INTEGRATOR_PRB;
     if (prb && !ctx->prb_primary_wavefront && !ctx->prb_wavefront)
-        return run_prb_sweep(ctx, make_pass(ctx->sc.S, seed, spp, ctx->rank, ctx->world), film_accum, nullptr, 0, (cudaStream_t)stream);
+        return run_prb_sweep(ctx, make_pass(ctx->sc.S, seed, spp, ctx->rank, ctx->world, 0, ctx->assign_rows), film_accum, nullptr, 0, (cudaStream_t)stream);
     Sweep sw;
     sw.diff = false;
-    sw.ps = make_pass(ctx->sc.S, seed, spp, ctx->rank, ctx->world, prb ? 0 : ctx->antithetic);
+    sw.ps = make_pass(ctx->sc.S, seed, spp, ctx->rank, ctx->world, prb ? 0 : ctx->antithetic, ctx->assign_rows);
     sw.film = film_accum;
     return run_sweeps(ctx, &sw, 1, (cudaStream_t)stream);
 }
@@ -1480,7 +1484,7 @@ int sdfrt_adjoint_accumulate(sdfrt_ctx* ctx, uint32_t seed_grad, int spp_grad, f
     SDFRT_CUDA(ctx, cudaSetDevice(ctx->device));
     Sweep sw;
     sw.diff = true;
-    sw.ps = make_pass(ctx->sc.S, seed_grad, spp_grad, ctx->rank, ctx->world, ctx->sc.integrator == INTEGRATOR_PRB ? 0 : ctx->antithetic);
+    sw.ps = make_pass(ctx->sc.S, seed_grad, spp_grad, ctx->rank, ctx->world, ctx->sc.integrator == INTEGRATOR_PRB ? 0 : ctx->antithetic, ctx->assign_rows);
     sw.film = film_accum;
     rc = ensure(ctx, &VS(ctx).rec, &VS(ctx).rec_capacity, (size_t)sw.ps.n_items * (size_t)rec_rows(ctx) + 1);
     if (rc) return rc;
@@ -1509,10 +1513,10 @@ int sdfrt_render_view(sdfrt_ctx* ctx, uint32_t seed, int spp, float* film_primal
     Sweep sw[2];
     sw[0].diff = false;
     const int anti = ctx->sc.integrator == INTEGRATOR_PRB ? 0 : ctx->antithetic;  // sdf_prb_reparam.sample_rays has no antithetic mode
-    sw[0].ps = make_pass(ctx->sc.S, seed, spp, ctx->rank, ctx->world, anti);
+    sw[0].ps = make_pass(ctx->sc.S, seed, spp, ctx->rank, ctx->world, anti, ctx->assign_rows);
     sw[0].film = film_primal;
     sw[1].diff = true;
-    sw[1].ps = make_pass(ctx->sc.S, seed_grad, spp_grad, ctx->rank, ctx->world, anti);
+    sw[1].ps = make_pass(ctx->sc.S, seed_grad, spp_grad, ctx->rank, ctx->world, anti, ctx->assign_rows);
     sw[1].film = film_adjoint;
     rc = ensure(ctx, &VS(ctx).rec, &VS(ctx).rec_capacity, (size_t)sw[1].ps.n_items * (size_t)rec_rows(ctx) + 1);
     if (rc) return rc;

@@ -35,9 +35,11 @@ struct PassParams {
     uint32_t seed;
     int spp;
     int log2_spp;               // >= 0 if spp is a power of two (python/integrators/reparam.py:144-148)
-    // Multi-GPU partition: the film rows are cut into bands of kBandRows rows; rank r owns the bands r, r + world, ...
-    // (interleaved, so that every rank sees a similar mix of object and background).  `n_items` = camera samples of this rank.
+    // Multi-GPU partition: the film rows are cut into sub-bands of `assign_rows` rows (1, 2, 4 or 8); rank r owns the sub-bands
+    // r, r + world, ... (interleaved, so that every rank sees a similar mix of object and background), `rows_local` rows in all.
+    // A rank walks ITS rows in tiles of kBandRows rows, whatever the assignment granularity.  `n_items` = camera samples of this rank.
     int rank, world;
+    int assign_rows, rows_local;
     int Wb, Hb;                 // film size incl. border
     unsigned long long n_items;
     // antithetic_sampling (python/integrators/reparam.py:19,167-178): every wavefront lane is evaluated twice, the second time
@@ -51,7 +53,7 @@ constexpr unsigned long long kAntiBit = 1ull << 63;  // WorkItem::lane carries t
 
 constexpr int kBandRows = 8;
 
-// Work item k of this rank -> pixel and wavefront lane.  Items walk the rank's bands in order, each band column by column
+// Work item k of this rank -> pixel and wavefront lane.  Items walk the rank's rows in tiles of kBandRows rows, each tile column by column
 // (8 rows x spp samples per column), so neighbouring items are neighbouring samples; lane indices -- and with them the
 // sampler streams -- stay the reference's scanline wavefront indices (python/integrators/reparam.py:141-155).
 struct WorkItem {
@@ -62,21 +64,24 @@ SDFRT_HD WorkItem decode_item(const PassParams& ps, unsigned long long k) {
     const unsigned long long anti = ps.antithetic ? (k & 1ull) : 0ull;
     if (ps.antithetic) k >>= 1;
     const unsigned Wb = (unsigned)ps.Wb;
-    const unsigned long long per_band = (unsigned long long)kBandRows * Wb * (unsigned)ps.spp;  // < 2^32 (checked on the host)
-    const unsigned bl = (unsigned)(k / per_band);
-    const unsigned r = (unsigned)(k - (unsigned long long)bl * per_band);
-    const unsigned g = bl * (unsigned)ps.world + (unsigned)ps.rank;  // global band
-    const unsigned row0 = g * (unsigned)kBandRows;
-    const unsigned left = (unsigned)ps.Hb - row0;
+    const unsigned long long per_tile = (unsigned long long)kBandRows * Wb * (unsigned)ps.spp;  // < 2^32 (checked on the host)
+    const unsigned bl = (unsigned)(k / per_tile);
+    const unsigned r = (unsigned)(k - (unsigned long long)bl * per_tile);
+    const unsigned row_l0 = bl * (unsigned)kBandRows;                  // first local row of the tile
+    const unsigned left = (unsigned)ps.rows_local - row_l0;
     const unsigned rows_here = left < (unsigned)kBandRows ? left : (unsigned)kBandRows;
     const unsigned per_col = rows_here * (unsigned)ps.spp;
     const unsigned x = r / per_col;
     const unsigned rr = r - x * per_col;
     const unsigned y_in = ps.log2_spp >= 0 ? (rr >> ps.log2_spp) : (rr / (unsigned)ps.spp);
     const unsigned sidx = rr - y_in * (unsigned)ps.spp;
+    // local row -> film row: sub-band (j / A) of this rank is the global sub-band (j / A) * world + rank
+    const unsigned j = row_l0 + y_in, A = (unsigned)ps.assign_rows;
+    const unsigned sb = j / A;
+    const unsigned row = (sb * (unsigned)ps.world + (unsigned)ps.rank) * A + (j - sb * A);
     WorkItem w;
     w.px = (int)x;
-    w.py = (int)(row0 + y_in);
+    w.py = (int)row;
     w.lane = (((unsigned long long)w.py * Wb + x) * (unsigned)ps.spp + sidx) | (anti ? kAntiBit : 0ull);
     return w;
 }

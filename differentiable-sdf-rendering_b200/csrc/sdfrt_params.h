@@ -191,7 +191,7 @@ inline bool build_envmap(const float* rgb, int w, int h, float scale, EnvTables&
     }
     return true;
 }
-inline PassParams make_pass(const SensorParams& S, uint32_t seed, int spp, int rank, int world, int antithetic = 0) {
+inline PassParams make_pass(const SensorParams& S, uint32_t seed, int spp, int rank, int world, int antithetic = 0, int assign_rows = kBandRows) {
     PassParams p;
     p.seed = seed;
     p.spp = spp;
@@ -202,10 +202,12 @@ inline PassParams make_pass(const SensorParams& S, uint32_t seed, int spp, int r
     p.world = world;
     p.Wb = S.W + 2 * S.border;
     p.Hb = S.H + 2 * S.border;
-    // bands rank, rank + world, ... of kBandRows film rows each (the last band of the film may be shorter)
-    const int nbands = (p.Hb + kBandRows - 1) / kBandRows;
+    // sub-bands rank, rank + world, ... of assign_rows film rows each (the last sub-band of the film may be shorter)
+    p.assign_rows = (assign_rows == 1 || assign_rows == 2 || assign_rows == 4) ? assign_rows : kBandRows;
+    const int nsub = (p.Hb + p.assign_rows - 1) / p.assign_rows;
     unsigned long long rows = 0;
-    for (int g = rank; g < nbands; g += world) rows += (unsigned long long)std::min(kBandRows, p.Hb - g * kBandRows);
+    for (int g = rank; g < nsub; g += world) rows += (unsigned long long)std::min(p.assign_rows, p.Hb - g * p.assign_rows);
+    p.rows_local = (int)rows;
     p.antithetic = antithetic ? 1 : 0;
     p.n_items = rows * (unsigned long long)p.Wb * (unsigned long long)spp * (unsigned long long)(1 + p.antithetic);
     p.win_lo = 0ull;

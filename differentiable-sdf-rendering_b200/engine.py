@@ -142,8 +142,9 @@ class Context:
         p = _capi.PrbParams(int(max_depth), int(rr_depth))
         check(self.ctx, self.lib.sdfrt_set_prb(self.ctx, C.byref(p)))
 
-    def set_partition(self, rank, world):
-        check(self.ctx, self.lib.sdfrt_set_partition(self.ctx, rank, world))
+    def set_partition(self, rank, world, rows=8):
+        """Rank `rank` of `world` renders the sub-bands rank, rank + world, ... of `rows` film rows (1, 2, 4 or 8)."""
+        check(self.ctx, self.lib.sdfrt_set_partition_rows(self.ctx, rank, world, rows))
 
     def set_lane_window(self, lane_lo=0, lane_hi=0):
         """Validation hook: adjoint_backprop only back-propagates wavefront lanes [lane_lo, lane_hi); (0, 0) = all."""

@@ -92,8 +92,9 @@ class HostContext:
     def set_prb(self, max_depth=4, rr_depth=5):
         self.prb = dict(max_depth=int(max_depth), rr_depth=int(rr_depth))
 
-    def set_partition(self, rank, world):
+    def set_partition(self, rank, world, rows=8):
         self.rank, self.world = rank, world
+        HM.lib().hh_set_assign_rows(int(rows))
 
     def set_view_slot(self, slot):
         self.slot = int(slot)

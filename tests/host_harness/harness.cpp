@@ -51,7 +51,11 @@ static SceneParams build(const hh_scene* h) {
     return sc;
 }
 
+static int g_assign_rows = kBandRows;   // granularity of the row partition (sdfrt_set_partition_rows)
+
 extern "C" {
+
+void hh_set_assign_rows(int rows) { g_assign_rows = rows; }
 
 // `envmap` emitter tables (the same builder sdfrt_set_envmap_host uses)
 void* hh_envmap_create(const float* rgb, int w, int h, float scale) {
@@ -120,7 +124,7 @@ int hh_trace(const hh_scene* h, const float* o, const float* d, const float* max
 // forward pass over the whole wavefront; film: (Hb, Wb, 4) zeroed here; rec: REC_COUNT * n floats (diff only)
 int hh_forward(const hh_scene* h, unsigned seed, int spp, int diff, float* film, float* rec, unsigned long long* stats, int rank, int world) {
     SceneParams sc = build(h);
-    PassParams ps = make_pass(sc.S, seed, spp, rank, world, h->antithetic);
+    PassParams ps = make_pass(sc.S, seed, spp, rank, world, h->antithetic, g_assign_rows);
     const size_t nf = (size_t)(sc.S.W + 2 * sc.S.border) * (sc.S.H + 2 * sc.S.border) * 4;
     std::memset(film, 0, nf * sizeof(float));
     LaneStats st = {0, 0, 0, 0, 0, 0, 0};
@@ -155,7 +159,7 @@ void hh_set_lane_window(unsigned long long lo, unsigned long long hi) {
 int hh_backward(const hh_scene* h, unsigned seed, int spp, const float* film, const float* rec, const float* grad_image,
                 float* grad_sdf, float* grad_albedo, float* grad_p, unsigned long long* stats, int rank, int world) {
     SceneParams sc = build(h);
-    PassParams ps = make_pass(sc.S, seed, spp, rank, world, h->antithetic);
+    PassParams ps = make_pass(sc.S, seed, spp, rank, world, h->antithetic, g_assign_rows);
     const SensorParams& S = sc.S;
     const int Wb = S.W + 2 * S.border, Hb = S.H + 2 * S.border;
     std::vector<float> adj((size_t)Wb * Hb * 4, 0.f);
@@ -191,7 +195,7 @@ int hh_backward(const hh_scene* h, unsigned seed, int spp, const float* film, co
 // sdf_prb_reparam: primal sweep (film zeroed here; L_rec: 3 * n floats, may be null)
 int hh_prb_forward(const hh_scene* h, unsigned seed, int spp, float* film, float* L_rec, int rank, int world) {
     SceneParams sc = build(h);
-    PassParams ps = make_pass(sc.S, seed, spp, rank, world);
+    PassParams ps = make_pass(sc.S, seed, spp, rank, world, 0, g_assign_rows);
     const int Wb = sc.S.W + 2 * sc.S.border, Hb = sc.S.H + 2 * sc.S.border;
     std::memset(film, 0, (size_t)Wb * Hb * 4 * sizeof(float));
     LaneStats st = {0, 0, 0, 0, 0, 0, 0};
@@ -224,7 +228,7 @@ int hh_prb_forward(const hh_scene* h, unsigned seed, int spp, float* film, float
 int hh_prb_backward(const hh_scene* h, unsigned seed, int spp, const float* film, const float* L_rec, const float* grad_image,
                     float* grad_sdf, float* grad_albedo, float* grad_p, unsigned long long* stats, int rank, int world) {
     SceneParams sc = build(h);
-    PassParams ps = make_pass(sc.S, seed, spp, rank, world);
+    PassParams ps = make_pass(sc.S, seed, spp, rank, world, 0, g_assign_rows);
     const SensorParams& S = sc.S;
     const int Wb = S.W + 2 * S.border, Hb = S.H + 2 * S.border;
     std::vector<float> adj((size_t)Wb * Hb * 4, 0.f);
@@ -272,7 +276,7 @@ static void hh_march_into(const SceneParams& sc, V3 o, V3 d, float maxt, bool re
 
 int hh_prb_wf_forward(const hh_scene* h, unsigned seed, int spp, int diff, float* film, float* L_rec, float* recs, int rank, int world) {
     SceneParams sc = build(h);
-    PassParams ps = make_pass(sc.S, seed, spp, rank, world);
+    PassParams ps = make_pass(sc.S, seed, spp, rank, world, 0, g_assign_rows);
     const int Wb = sc.S.W + 2 * sc.S.border, Hb = sc.S.H + 2 * sc.S.border;
     std::memset(film, 0, (size_t)Wb * Hb * 4 * sizeof(float));
     const unsigned long long n = ps.n_items;
@@ -330,7 +334,7 @@ int hh_prb_wf_forward(const hh_scene* h, unsigned seed, int spp, int diff, float
 int hh_prb_wf_backward(const hh_scene* h, unsigned seed, int spp, const float* film, const float* L_rec, const float* recs,
                        const float* grad_image, float* grad_sdf, float* grad_albedo, float* grad_p, int rank, int world) {
     SceneParams sc = build(h);
-    PassParams ps = make_pass(sc.S, seed, spp, rank, world);
+    PassParams ps = make_pass(sc.S, seed, spp, rank, world, 0, g_assign_rows);
     const SensorParams& S = sc.S;
     const int Wb = S.W + 2 * S.border, Hb = S.H + 2 * S.border;
     std::vector<float> adj((size_t)Wb * Hb * 4, 0.f);
@@ -362,7 +366,7 @@ int hh_prb_wf_backward(const hh_scene* h, unsigned seed, int spp, const float* f
 int hh_rec_count() { return REC_COUNT_MIS; }
 unsigned long long hh_local_lanes(const hh_scene* h, int spp, int rank, int world) {
     SensorParams S = make_sensor(h->sensor);
-    PassParams ps = make_pass(S, 0, spp, rank, world, h->antithetic);
+    PassParams ps = make_pass(S, 0, spp, rank, world, h->antithetic, g_assign_rows);
     return ps.n_items;
 }
 }

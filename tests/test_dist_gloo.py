@@ -27,8 +27,10 @@ class HostBackend:
         self.hs.h.prb.max_depth = 3
         self.rank, self.world = 0, 1
 
-    def set_partition(self, rank, world):
+    def set_partition(self, rank, world, rows=8):
+        import hostmath as HM
         self.rank, self.world = rank, world
+        HM.lib().hh_set_assign_rows(int(rows))
 
     def render_primal(self, seed, spp):
         if self.prb:

@@ -466,3 +466,31 @@ def test_convolution_warp_with_antithetic_sampling():
     g_o = g_o.numpy()
     assert np.linalg.norm(g_h - g_o) < 2e-3 * np.linalg.norm(g_o)
     assert np.abs(gp_h - gp_o.numpy()).max() < 2e-3 * np.abs(gp_o.numpy()).max()
+
+
+@pytest.mark.parametrize('rows', [1, 2, 4])
+def test_row_partition_granularity(rows):
+    """sdfrt_set_partition_rows: ranks own interleaved sub-bands of 1 / 2 / 4 film rows and walk their own rows in 8-row tiles; every
+    camera sample belongs to exactly one rank (lane counts add up, films and gradients add up to the single-rank result), also when the
+    film height is not a multiple of anything (15 + 2 * 2 = 19 rows)."""
+    W, spp = 15, 2
+    sc, wf, hs = make_pair('sphere', 24, W, 'sdf_direct_reparam')
+    g_in = np.random.default_rng(3).uniform(-1, 1, size=(W, W, 3))
+    whole, rec, _ = hs.forward(7, spp, True)
+    g_whole = hs.backward(7, spp, whole, rec, g_in)[0]
+    try:
+        HM.lib().hh_set_assign_rows(rows)
+        for world in (2, 3, 8):
+            assert sum(hs.local_lanes(spp, r, world) for r in range(world)) == hs.wavefront(spp)
+            films, g = [], np.zeros_like(g_whole)
+            for r in range(world):
+                f, rec_r, _ = hs.forward(7, spp, True, r, world)
+                films.append(f)
+            total = sum(films)
+            assert np.abs(total - whole).max() < 2e-5
+            for r in range(world):
+                _, rec_r, _ = hs.forward(7, spp, True, r, world)
+                g += hs.backward(7, spp, total, rec_r, g_in, r, world)[0]
+            assert np.abs(g - g_whole).max() < 1e-4 * np.abs(g_whole).max()
+    finally:
+        HM.lib().hh_set_assign_rows(8)
