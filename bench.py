@@ -33,7 +33,10 @@ PRB_WORKLOADS = {'c5_prb_blobs256_512x512_128spp': dict(max_depth=3, rr_depth=5)
 SECONDARY = ('c4_blobs512_512x512_64spp', 'c5_prb_blobs256_512x512_128spp')
 METRIC = "primary+adjoint Mrays/s"
 # dram__bytes_read + dram__bytes_write of the k_march launches of ONE c3 step, from the committed ncu launch list
-NCU_DRAM_BYTES_PER_STEP = {'c3_blobs256_tex_512x512_64spp': (11.95e9, 'profiles/r1_launches_rows4_c3.csv')}
+NCU_DRAM_BYTES_PER_STEP = {'c3_blobs256_tex_512x512_64spp': (16.80e9, 'profiles/r2_final_launches_c3.csv')}
+# the same launch list, serialised by ncu (cold caches, no overlap): per step 44.0 ms of kernels, 34.1 ms of them k_march (22 launches)
+NCU_SERIALISED = {'c3_blobs256_tex_512x512_64spp': {"step_kernel_ms": 44.04, "k_march_ms": 34.07, "k_march_share": 0.774, "k_march_launches": 22,
+                                                    "source": "profiles/r2_final_launches_c3.csv"}}
 # what binds each kernel, from the committed `ncu --set full` captures (profiles/): unit and its % of peak
 BINDING = {   # round-2 captures of the shipped kernels (ncu --set full, one batch of a c3 step), summarised under profiles/r2_call*/
     'k_march<0,1,8> primary segments (value, rows8)': {"unit": "L1 data stage (l1tex__throughput) + issue", "pct": 66, "issue_active_pct": 58,
@@ -407,7 +410,7 @@ def march_roofline(job, kt, stats, steps, peak, peak_src, loop_ms):
     launches = sum(v[1] for k, v in kt.items() if k != 'march_all') / steps
     return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": traffic[0] if traffic else None, "traffic_source": traffic[1] if traffic else None, "peak_source": peak_src,
-            "kernel": "k_march: all launches of one step",
+            "kernel": "k_march: all launches of one step", "ncu_serialised": NCU_SERIALISED.get(job.wl),
             "kernel_ms": march_ms, "kernel_ms_how": "union of the k_march launch intervals (CUDA events recorded by the library around every "
                                                     "launch), steps run as in the timed region with overlapping batches",
             "profiled_loop_ms_per_step": loop_ms,
