@@ -69,6 +69,7 @@ def parse():
     ap.add_argument('--no-grad-check', action='store_true', help='skip the lane-subsample gradient check against the oracle')
     ap.add_argument('--no-e2e', action='store_true', help='profiling runs: skip the host-buffer leg')
     ap.add_argument('--views-in-flight', type=int, default=2, help='independent views (steps) enqueued concurrently on separate streams / view slots')
+    ap.add_argument('--e2e-contexts', type=int, default=3, help='N = 1: contexts (host threads) of the host-buffer leg')
     ap.add_argument('--partition-rows', type=int, default=8, choices=[1, 2, 4, 8], help='film rows per unit of the interleaved row partition')
     ap.add_argument('--partition-rank', type=int, default=0, help='tuning: which rank of --partition-of to emulate')
     ap.add_argument('--partition-of', type=int, default=0, help='tuning: render rank 0 of a partition into this many ranks on one GPU (no collectives)')
@@ -261,6 +262,7 @@ class Job:
             ctx.set_integrator('sdf_direct_reparam')
         ctx.set_warp()
         self.partition_rows = partition_rows
+        self.e2e_contexts = 3
         if partition_of > 1:
             ctx.set_partition(partition_rank, partition_of, partition_rows)
         else:
@@ -475,10 +477,11 @@ def e2e_leg(job, steps):
     ga_h = None if job.alb is None else torch.empty(tuple(job.alb.shape)).pin_memory()
     nsens, spp, mult = job.nsens, job.spp, job.mult
     if job.world == 1:
-        # Views in flight on the host API too: `inflight` contexts, one host thread each (the C call releases the GIL), every one with
-        # its own pinned host buffers; the copies of one view overlap the kernels of the other (PCIe is full duplex).
+        # Views in flight on the host API too: several contexts, one host thread each (the C call releases the GIL), every one with its own
+        # pinned host buffers.  A context's view is upload -> kernels -> download in sequence, so with THREE contexts the copies of one view
+        # run while two others keep the SMs busy (PCIe is full duplex); with two, the kernels of one view ran alone a third of the time.
         import threading
-        nctx = job.inflight
+        nctx = max(1, job.e2e_contexts)
         ctxs = [job.ctx] + [sdfrt.Context(job.dev.index) for _ in range(nctx - 1)]
         for c in ctxs[1:]:
             c.set_sensor(job.sensor.to_world, job.W, job.H)
@@ -518,8 +521,18 @@ def e2e_leg(job, steps):
         # copies are double-buffered around it: the grids of view v+1 are uploaded on a copy stream into the other pair of device
         # buffers while view v renders, and rank 0's downloads of view v run on the copy stream behind the next view's kernels.
         copy_s = torch.cuda.Stream(job.dev)
-        sdf_d = [job.sdf, torch.empty_like(job.sdf)]
-        alb_d = [job.alb, None if job.alb is None else torch.empty_like(job.alb)]
+        # ONE rank reads the host buffers: rank 0 uploads SDF + reflectance grid (one pinned allocation, one copy) and broadcasts them over
+        # NVLink on a communicator of its own, so that the broadcast of view v+1 queues behind nothing of view v.  (Every rank uploading its
+        # own replica was bound by the host side at 8 GPUs: 2.1 GB per step through shared PCIe uplinks, 12 ms per step against 5.9 of kernels.)
+        bgroup = dist.new_group(backend='nccl')
+        nv, na = job.sdf.numel(), 0 if job.alb is None else job.alb.numel()
+        grid_h = torch.empty(nv + na).pin_memory()
+        grid_h[:nv].copy_(sdf_h.reshape(-1))
+        if na:
+            grid_h[nv:].copy_(alb_h.reshape(-1))
+        grid_d = [torch.empty(nv + na, device=job.dev) for _ in range(2)]
+        sdf_d = [g[:nv].view(job.sdf.shape) for g in grid_d]
+        alb_d = [None if job.alb is None else g[nv:].view(job.alb.shape) for g in grid_d]
         gs_d = [job.grad_sdf, torch.empty_like(job.grad_sdf)]
         ga_d = [job.grad_alb, None if job.grad_alb is None else torch.empty_like(job.grad_alb)]
         outs = [(img_h, g_h, ga_h), (torch.empty_like(img_h).pin_memory(), torch.empty_like(g_h).pin_memory(),
@@ -532,9 +545,9 @@ def e2e_leg(job, steps):
         def upload(k):
             with torch.cuda.stream(copy_s):
                 copy_s.wait_event(free[k])
-                sdf_d[k].copy_(sdf_h, non_blocking=True)
-                if alb_h is not None:
-                    alb_d[k].copy_(alb_h, non_blocking=True)
+                if job.rank == 0:
+                    grid_d[k].copy_(grid_h, non_blocking=True)
+                dist.broadcast(grid_d[k], src=0, group=bgroup)
                 up_done[k].record(copy_s)
 
         def view(k, seed):
@@ -580,8 +593,8 @@ def e2e_leg(job, steps):
         tw = twt.item()
         job.ctx.set_sdf(job.sdf)
         job.ctx.set_albedo(job.alb)
-        api = "sdfrt.dist.render_view (uploads / downloads double-buffered on a copy stream)"
-    h2d = (sdf_h.numel() + (alb_h.numel() if alb_h is not None else 0)) * 4 * job.world
+        api = "sdfrt.dist.render_view (rank 0 uploads, NVLink broadcast of the grids; uploads / downloads double-buffered on a copy stream)"
+    h2d = (sdf_h.numel() + (alb_h.numel() if alb_h is not None else 0)) * 4 * (job.world if job.world == 1 else 1)
     d2h = (img_h.numel() + g_h.numel() + (ga_h.numel() if ga_h is not None else 0)) * 4
     return {"value": job.rays_per_step * e_steps / tw / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
             "steps": e_steps, "api": api}
@@ -630,6 +643,7 @@ def run_gpu(args):
     peak_src = 'measured (MEASURED_PEAKS.json, burst copy)' if 'hbm_gbs' in peaks else 'fallback (B200_PROFILING.md)'
 
     job = Job(args.workload, local, rank, world, args.views_in_flight, args.partition_of, args.partition_rank, args.partition_rows)
+    job.e2e_contexts = args.e2e_contexts
     ms, stats, passes, clocks = job.timed(args.steps, args.warmup, clocks=True)
     value = job.rays_per_step * args.steps / (ms * 1e-3) / 1e6
     n_cam = stats['n_rays'] + 0   # camera samples this rank shaded (marched or culled)
