@@ -540,6 +540,17 @@ def e2e_leg(job, steps):
         up_done = [torch.cuda.Event(), torch.cuda.Event()]
         free = [torch.cuda.Event(), torch.cuda.Event()]      # device buffers k may be overwritten (their view's kernels are done)
         main = torch.cuda.current_stream(job.dev)
+        # Two views in flight here too: view v runs on context v % 2 and on that context's stream (one host thread, so every rank issues
+        # its collectives in the same order).  Two CONTEXTS rather than two view slots of one, because each view binds its own upload of
+        # the grid and the derived copies (rows8, brick minima) belong to the context.
+        ctxs = [job.ctx, sdfrt.Context(job.dev.index)]
+        ctxs[1].set_sensor(job.sensor.to_world, job.W, job.H)
+        ctxs[1].set_shading()
+        ctxs[1].set_integrator('sdf_prb_reparam' if job.prb else 'sdf_direct_reparam')
+        if job.prb:
+            ctxs[1].set_prb(**job.prb)
+        ctxs[1].set_warp()
+        lanes = [torch.cuda.Stream(job.dev), torch.cuda.Stream(job.dev)]
         job.ctx.set_view_slot(0)
 
         def upload(k):
@@ -551,15 +562,16 @@ def e2e_leg(job, steps):
                 up_done[k].record(copy_s)
 
         def view(k, seed):
-            main.wait_event(up_done[k])
-            job.ctx.set_sdf(sdf_d[k])
-            job.ctx.set_albedo(alb_d[k])
-            gs_d[k].zero_()
-            if ga_d[k] is not None:
-                ga_d[k].zero_()
-            img = sdfrt.dist.render_view(job.ctx, seed, spp * mult, seed + 1 + nsens, spp, lambda im: job.grad_image, gs_d[k], ga_d[k], buffers_are_zero=True)
             done = torch.cuda.Event()
-            done.record(main)
+            with torch.cuda.stream(lanes[k]):
+                lanes[k].wait_event(up_done[k])
+                ctxs[k].set_sdf(sdf_d[k])
+                ctxs[k].set_albedo(alb_d[k])
+                gs_d[k].zero_()
+                if ga_d[k] is not None:
+                    ga_d[k].zero_()
+                img = sdfrt.dist.render_view(ctxs[k], seed, spp * mult, seed + 1 + nsens, spp, lambda im: job.grad_image, gs_d[k], ga_d[k], buffers_are_zero=True)
+                done.record(lanes[k])
             if job.rank == 0:
                 with torch.cuda.stream(copy_s):
                     copy_s.wait_event(done)
@@ -570,7 +582,7 @@ def e2e_leg(job, steps):
                     img.record_stream(copy_s)
                     free[k].record(copy_s)
             else:
-                free[k].record(main)
+                free[k].record(lanes[k])
 
         def run(n_steps, seed0):
             for k in range(2):
@@ -593,7 +605,8 @@ def e2e_leg(job, steps):
         tw = twt.item()
         job.ctx.set_sdf(job.sdf)
         job.ctx.set_albedo(job.alb)
-        api = "sdfrt.dist.render_view (rank 0 uploads, NVLink broadcast of the grids; uploads / downloads double-buffered on a copy stream)"
+        del ctxs
+        api = "sdfrt.dist.render_view (rank 0 uploads, NVLink broadcast of the grids; two views in flight on two contexts, uploads / downloads on a copy stream)"
     h2d = (sdf_h.numel() + (alb_h.numel() if alb_h is not None else 0)) * 4 * (job.world if job.world == 1 else 1)
     d2h = (img_h.numel() + g_h.numel() + (ga_h.numel() if ga_h is not None else 0)) * 4
     return {"value": job.rays_per_step * e_steps / tw / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
