@@ -69,7 +69,7 @@ def parse():
     ap.add_argument('--no-grad-check', action='store_true', help='skip the lane-subsample gradient check against the oracle')
     ap.add_argument('--no-e2e', action='store_true', help='profiling runs: skip the host-buffer leg')
     ap.add_argument('--views-in-flight', type=int, default=2, help='independent views (steps) enqueued concurrently on separate streams / view slots')
-    ap.add_argument('--e2e-contexts', type=int, default=3, help='N = 1: contexts (host threads) of the host-buffer leg')
+    ap.add_argument('--e2e-contexts', type=int, default=4, help='N = 1: contexts (host threads) of the host-buffer leg')
     ap.add_argument('--partition-rows', type=int, default=8, choices=[1, 2, 4, 8], help='film rows per unit of the interleaved row partition')
     ap.add_argument('--partition-rank', type=int, default=0, help='tuning: which rank of --partition-of to emulate')
     ap.add_argument('--partition-of', type=int, default=0, help='tuning: render rank 0 of a partition into this many ranks on one GPU (no collectives)')
@@ -262,7 +262,7 @@ class Job:
             ctx.set_integrator('sdf_direct_reparam')
         ctx.set_warp()
         self.partition_rows = partition_rows
-        self.e2e_contexts = 3
+        self.e2e_contexts = 4
         if partition_of > 1:
             ctx.set_partition(partition_rank, partition_of, partition_rows)
         else:
@@ -478,7 +478,7 @@ def e2e_leg(job, steps):
     nsens, spp, mult = job.nsens, job.spp, job.mult
     if job.world == 1:
         # Views in flight on the host API too: several contexts, one host thread each (the C call releases the GIL), every one with its own
-        # pinned host buffers.  A context's view is upload -> kernels -> download in sequence, so with THREE contexts the copies of one view
+        # pinned host buffers.  A context's view is upload -> kernels -> download in sequence, so with several contexts (default 4: 2406 / 2586 / 2644 Mrays/s with 2 / 3 / 4) the copies of one view
         # run while two others keep the SMs busy (PCIe is full duplex); with two, the kernels of one view ran alone a third of the time.
         import threading
         nctx = max(1, job.e2e_contexts)

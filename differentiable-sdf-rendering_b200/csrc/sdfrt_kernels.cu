@@ -475,6 +475,9 @@ struct sdfrt_ctx {
         float *siteq_a = nullptr, *siteq_b = nullptr;        // site queue of k_prb_backward (one per view: backprops of views in flight overlap)
         size_t siteq_a_n = 0, siteq_b_n = 0;
         unsigned* siteq_count = nullptr;
+        cudaStream_t defer_stream = nullptr;                 // the deferred differentiable march of this view runs beside the caller's stream:
+        cudaEvent_t defer_ready = nullptr, defer_done = nullptr;   // only the adjoint (and whoever reuses the records) waits for it
+        bool defer_pending = false;
         float *flag_segs = nullptr, *flag_dest = nullptr;   // deferred differentiable march: segments + record offsets, and
         size_t flag_segs_n = 0, flag_dest_n = 0;           // [0] their count, [1] the marcher's region counter
         unsigned* flag_count = nullptr;
@@ -507,6 +510,8 @@ struct sdfrt_ctx {
     float* brick_raw = nullptr;   // per-brick SDF minima (undilated; rebuilt when the grid changes)
     size_t brick_raw_n = 0;
     bool skip_empty = true;
+    bool defer_side_stream = false;  // ... on a stream of its own beside the caller's (SDFRT_DEFER_SIDE=1).  Measured: 4.88 vs 4.92 ms for one rank of
+                                     // eight, 31.25 vs 30.92 ms at N = 1 -- nothing gained, so the march stays on the caller's stream
     bool defer_diff = true;     // deferred differentiable march of the shadow segments (SDFRT_DEFER=0: march them differentiably per batch)
     int min_live = kMinActive;  // slots that must be stepping for a warp to stay in the stepping loop
     int max_slots = 6;
@@ -886,8 +891,14 @@ int enqueue_batch(sdfrt_ctx* ctx, const Sweep& sw, unsigned long long item0, int
     return SDFRT_OK;
 }
 
+int wait_deferred(sdfrt_ctx* ctx, cudaStream_t st, int slot);
+
 int run_sweeps(sdfrt_ctx* ctx, Sweep* sweeps, int ns, cudaStream_t st) {
     SDFRT_CUDA(ctx, cudaSetDevice(ctx->device));
+    {   // a deferred march still in flight reads this view slot's records and flag list, and -- any slot's -- the derived grid copies
+        const int rcw = wait_deferred(ctx, st, ctx->grid_dirty ? -1 : ctx->cur_view);
+        if (rcw) return rcw;
+    }
     if (ctx->sc.W.kind == WARP_CONV && ctx->sc.integrator == INTEGRATOR_PRB)
         return fail(ctx, SDFRT_ERR_INVALID, "WarpFieldConvolution is implemented for the direct-illumination integrators only (not sdf_prb_reparam)");
     if (ctx->sc.E.data != nullptr && ctx->sc.integrator == INTEGRATOR_PRB)
@@ -1091,10 +1102,40 @@ int run_sweeps(sdfrt_ctx* ctx, Sweep* sweeps, int ns, cudaStream_t st) {
         ex.dest = sw.flag.dest;
         ex.n_slots_dev = sw.flag.count;
         const unsigned region = 256u;
-        LaunchScope ls(ctx, 3, st);
-        launch_march_mode<true>(ctx, 3, 0xffffffffu, st, sw.flag.segs, nullptr, sw.flag.capacity, region, 0, nullptr, VS(ctx).rec, VS(ctx).rec_stride,
-                                sw.flag.count + 1, ex);
+        // The films of the sweep are complete at this point; what is still missing are warp records of the flagged segments, which only
+        // adjoint sweep 2 reads.  The march is a few thousand long grazing rays -- latency, not throughput (2.3 ms for one rank of eight
+        // against 3.3 ms for the whole film).  Optionally (SDFRT_DEFER_SIDE=1) it goes to a stream of its own so that the caller's stream
+        // (film all-reduce, develop, the next view) does not queue behind it; sdfrt_adjoint_backprop and every reuse of the records then
+        // wait for `defer_done`.  With two views in flight that bought nothing, so it is off by default.
+        sdfrt_ctx::ViewSlot& V = VS(ctx);
+        cudaStream_t ds = st;
+        if (ctx->defer_side_stream) {
+            if (!V.defer_stream) {
+                SDFRT_CUDA(ctx, cudaStreamCreateWithFlags(&V.defer_stream, cudaStreamNonBlocking));
+                SDFRT_CUDA(ctx, cudaEventCreateWithFlags(&V.defer_ready, cudaEventDisableTiming));
+                SDFRT_CUDA(ctx, cudaEventCreateWithFlags(&V.defer_done, cudaEventDisableTiming));
+            }
+            ds = V.defer_stream;
+            SDFRT_CUDA(ctx, cudaEventRecord(V.defer_ready, st));
+            SDFRT_CUDA(ctx, cudaStreamWaitEvent(ds, V.defer_ready, 0));
+        }
+        { LaunchScope ls(ctx, 3, ds);
+          launch_march_mode<true>(ctx, 3, 0xffffffffu, ds, sw.flag.segs, nullptr, sw.flag.capacity, region, 0, nullptr, V.rec, V.rec_stride,
+                                  sw.flag.count + 1, ex); }
         SDFRT_CUDA(ctx, cudaGetLastError());
+        if (ds != st) {
+            SDFRT_CUDA(ctx, cudaEventRecord(V.defer_done, ds));
+            V.defer_pending = true;
+        }
+    }
+    return SDFRT_OK;
+}
+// make `st` wait for the deferred march of one view slot (or of all of them)
+int wait_deferred(sdfrt_ctx* ctx, cudaStream_t st, int slot /* -1: every slot */) {
+    for (int i = 0; i < kViewSlots; ++i) {
+        if (slot >= 0 && i != slot) continue;
+        sdfrt_ctx::ViewSlot& V = ctx->view[i];
+        if (V.defer_pending) SDFRT_CUDA(ctx, cudaStreamWaitEvent(st, V.defer_done, 0));
     }
     return SDFRT_OK;
 }
@@ -1188,6 +1229,7 @@ sdfrt_ctx* sdfrt_create(int device, int* status) {
     if (const char* e = std::getenv("SDFRT_MIN_LIVE")) ctx->min_live = std::max(1, std::min(32, std::atoi(e)));
     if (const char* e = std::getenv("SDFRT_PRB_OCC")) ctx->prb_min_blocks = std::atoi(e);
     if (const char* e = std::getenv("SDFRT_SITEQ")) ctx->site_queue = std::atoi(e) != 0;
+    if (const char* e = std::getenv("SDFRT_DEFER_SIDE")) ctx->defer_side_stream = std::atoi(e) != 0;
     if (const char* e = std::getenv("SDFRT_SHADE_ROWS8")) ctx->shade_rows8 = std::atoi(e) != 0;
     if (const char* e = std::getenv("SDFRT_SITEQ_CAP")) ctx->site_queue_cap = std::max(1ll, std::atoll(e));
     if (const char* e = std::getenv("SDFRT_PRB_WAVEFRONT")) ctx->prb_wavefront = std::atoi(e) != 0;
@@ -1225,6 +1267,7 @@ void sdfrt_destroy(sdfrt_ctx* ctx) {
     cudaSetDevice(ctx->device);
     for (auto& t : ctx->timed) { cudaEventDestroy(t.second.first); cudaEventDestroy(t.second.second); }
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
+    for (auto& v : ctx->view) { if (v.defer_stream) cudaStreamDestroy(v.defer_stream); if (v.defer_ready) cudaEventDestroy(v.defer_ready); if (v.defer_done) cudaEventDestroy(v.defer_done); }
     for (auto& v : ctx->view) { cudaFree(v.rec); cudaFree(v.film_adj); cudaFree(v.prb_rec); cudaFree(v.brick_a); cudaFree(v.brick_b); cudaFree(v.pix_mask); cudaFree(v.flag_segs); cudaFree(v.flag_dest); cudaFree(v.flag_count); cudaFree(v.siteq_a); cudaFree(v.siteq_b); cudaFree(v.siteq_count); }
     cudaFree(ctx->counters);
     cudaFree(ctx->work);
@@ -1545,6 +1588,7 @@ int sdfrt_adjoint_backprop(sdfrt_ctx* ctx, const float* film_accum, const float*
     if (!grad_sdf && !grad_albedo && !grad_p) return fail(ctx, SDFRT_ERR_INVALID, "no gradient target");
     SDFRT_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
+    { const int rcw = wait_deferred(ctx, st, ctx->cur_view); if (rcw) return rcw; }   // the warp records of the flagged segments
     const SceneParams& vsc = VS(ctx).sc;   // the scene adjoint sweep 1 of this view was rendered with
     const SensorParams& S = vsc.S;
     int rc = ensure(ctx, &VS(ctx).film_adj, &VS(ctx).film_adj_capacity, (size_t)(S.W + 2 * S.border) * (size_t)(S.H + 2 * S.border) * 4);
@@ -1606,6 +1650,7 @@ int sdfrt_get_stats(sdfrt_ctx* ctx, sdfrt_stats* out, int reset, void* stream) {
     if (!ctx || !out) return SDFRT_ERR_INVALID;
     SDFRT_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
+    { const int rcw = wait_deferred(ctx, st, -1); if (rcw) return rcw; }
     Counters c;
     SDFRT_CUDA(ctx, cudaMemcpyAsync(&c, ctx->counters, sizeof(c), cudaMemcpyDeviceToHost, st));
     SDFRT_CUDA(ctx, cudaStreamSynchronize(st));

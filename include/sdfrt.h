@@ -202,7 +202,10 @@ int sdfrt_develop(sdfrt_ctx* ctx, const float* film_accum, float* image, void* s
  *  backprop:   given the (all-reduced) film_accum of that re-render and grad_image =
  *              dLoss/dImage (H, W, 3), ADDS dLoss/d(sdf.data) into grad_sdf (rz, ry, rx),
  *              dLoss/d(albedo) into grad_albedo (or NULL) and dLoss/d(sdf.p) into grad_p[3]
- *              (device pointer, or NULL). */
+ *              (device pointer, or NULL).
+ * The SDF tensor must stay unchanged until the view's backprop has been enqueued (with SDFRT_DEFER_SIDE=1 the warp records of the few
+ * shadow segments that need the differentiable march are still being filled on a stream of the context when accumulate returns;
+ * backprop and every later sweep of the view slot wait for them). */
 int sdfrt_adjoint_accumulate(sdfrt_ctx* ctx, uint32_t seed_grad, int spp_grad, float* film_accum, void* stream);
 /* Primal render at (seed, spp) and adjoint sweep 1 at (seed_grad, spp_grad) in ONE pipelined call: the two sweeps do not
  * depend on each other (the re-render of render_backward does not need the loss, python/integrators/reparam.py:187-189),
