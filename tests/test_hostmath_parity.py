@@ -494,3 +494,27 @@ def test_row_partition_granularity(rows):
             assert np.abs(g - g_whole).max() < 1e-4 * np.abs(g_whole).max()
     finally:
         HM.lib().hh_set_assign_rows(8)
+
+
+def test_partition_with_envmap_and_convolution_warp():
+    """The row partition with the round-2 additions: an envmap-lit scene rendered by two ranks, and the convolution warp's adjoint
+    (auxiliary samples continue each lane's own sampler stream, so they do not depend on which rank owns the lane) over three ranks,
+    add up to the single-rank film and gradient."""
+    W, spp = 14, 2
+    g_in = np.random.default_rng(2).uniform(-1, 1, size=(W, W, 3))
+    for warp, env, world in ((dict(kind=2), True, 2), (dict(kind=3, n_aux_rays=3), False, 3)):
+        sc, wf, hs = make_pair('sphere', 24, W, 'sdf_direct_reparam', warp=warp)
+        if env:
+            hs.set_envmap(_envmap_bitmap())
+        whole, rec, _ = hs.forward(9, spp, True)
+        g_whole = hs.backward(9, spp, whole, rec, g_in)[0]
+        g, total = np.zeros_like(g_whole), np.zeros_like(whole)
+        recs = []
+        for r in range(world):
+            f, rec_r, _ = hs.forward(9, spp, True, r, world)
+            total += f
+            recs.append(rec_r)
+        assert np.abs(total - whole).max() < 2e-5
+        for r in range(world):
+            g += hs.backward(9, spp, total, recs[r], g_in, r, world)[0]
+        assert np.abs(g_whole).max() > 0 and np.abs(g - g_whole).max() < 1e-4 * np.abs(g_whole).max()
