@@ -75,6 +75,7 @@ SIGNATURES = {
     'sdfrt_set_use_mis': (C.c_int, [_P, C.c_int]),
     'sdfrt_set_partition_rows': (C.c_int, [_P, C.c_int, C.c_int, C.c_int]),
     'sdfrt_set_envmap_host': (C.c_int, [_P, C.c_void_p, C.c_int, C.c_int, C.c_float]),
+    'sdfrt_set_envmap_transform': (C.c_int, [_P, C.c_void_p]),
     'sdfrt_set_shadow_origin': (C.c_int, [_P, C.c_int]),
     'sdfrt_prb_defaults': (None, [C.POINTER(PrbParams)]),
     'sdfrt_set_prb': (C.c_int, [_P, C.POINTER(PrbParams)]),

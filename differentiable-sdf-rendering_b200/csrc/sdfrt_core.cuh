@@ -149,6 +149,8 @@ struct EnvView {
     const float* cond_cdf;   // [(H - 1) * (W1 - 1)] inclusive CDF inside each row
     const float* cell_prob;  // [(H - 1) * (W1 - 1)]
     int W1, H;
+    int has_rot;    // to_world is not the identity
+    float R[9];     // to_world rotation, row-major: d_world = R d_local, d_local = R^T d_world
 };
 struct Counters {  // device work counters (unsigned long long for atomicAdd)
     unsigned long long n_rays, n_evals_value, n_evals_grad, n_evals_hess, n_scatter_sites, n_albedo_lookups,
@@ -811,6 +813,15 @@ SDFRT_HD V3 square_to_uniform_sphere(float u0, float u1) {
 // ------------------------------------------------------------------------------------
 // envmap emitter: lookup (+ derivative w.r.t. the direction), importance sampling, pdf
 // ------------------------------------------------------------------------------------
+SDFRT_HD V3 env_to_local(const EnvView& E, V3 d) {
+    if (!E.has_rot) return d;
+    return V3{E.R[0] * d.x + E.R[3] * d.y + E.R[6] * d.z, E.R[1] * d.x + E.R[4] * d.y + E.R[7] * d.z, E.R[2] * d.x + E.R[5] * d.y + E.R[8] * d.z};
+}
+SDFRT_HD V3 env_to_world(const EnvView& E, V3 d) {
+    if (!E.has_rot) return d;
+    return V3{E.R[0] * d.x + E.R[1] * d.y + E.R[2] * d.z, E.R[3] * d.x + E.R[4] * d.y + E.R[5] * d.z, E.R[6] * d.x + E.R[7] * d.y + E.R[8] * d.z};
+}
+// (d: direction in the emitter's local frame)
 SDFRT_HD void env_coord(const EnvView& E, V3 d, float& cx, float& cy) {
     float u = atan2f(d.x, -d.z) * (0.5f / kPi) - 0.5f / (float)(E.W1 - 1);
     float v = acosf(fminf(fmaxf(d.y, -1.f), 1.f)) * (1.f / kPi);
@@ -821,6 +832,7 @@ SDFRT_HD void env_coord(const EnvView& E, V3 d, float& cx, float& cy) {
 }
 // radiance from the unit direction d; dLe (optional): dLe[c] = gradient of channel c w.r.t. d
 SDFRT_HD V3 env_eval(const EnvView& E, V3 d, V3* dLe) {
+    d = env_to_local(E, d);   // v = to_world^-1 (-si.wi)
     float cx, cy;
     env_coord(E, d, cx, cy);
     const int ix = min_i((int)floorf(cx), E.W1 - 2), iy = min_i((int)floorf(cy), E.H - 2);
@@ -838,13 +850,14 @@ SDFRT_HD V3 env_eval(const EnvView& E, V3 d, V3* dLe) {
         const float s2 = 1.f - d.y * d.y;
         const float ky = s2 > 0.f ? -(float)(E.H - 1) * (1.f / kPi) / sqrtf(s2) : 0.f;
         const V3 gy = V3{0.f, ky, 0.f};                         // grad cy
-        dLe[0] = dcx.x * gx + dcy.x * gy;
-        dLe[1] = dcx.y * gx + dcy.y * gy;
-        dLe[2] = dcx.z * gx + dcy.z * gy;
+        dLe[0] = env_to_world(E, dcx.x * gx + dcy.x * gy);   // d/d(d_world) = R d/d(d_local)
+        dLe[1] = env_to_world(E, dcx.y * gx + dcy.y * gy);
+        dLe[2] = env_to_world(E, dcx.z * gx + dcy.z * gy);
     }
     return Le;
 }
 SDFRT_HD float env_pdf(const EnvView& E, V3 d) {
+    d = env_to_local(E, d);
     float cx, cy;
     env_coord(E, d, cx, cy);
     const int ix = min_i((int)floorf(cx), E.W1 - 2), iy = min_i((int)floorf(cy), E.H - 2);
@@ -874,9 +887,9 @@ SDFRT_HD V3 env_sample(const EnvView& E, float u0, float u1, float& pdf) {
     const float vv = ((float)iy + fy) / (float)ny;
     const float theta = vv * kPi, phi = uu * 2.f * kPi;
     const float st = sinf(theta);
-    const V3 d = V3{sinf(phi) * st, cosf(theta), -cosf(phi) * st};
-    pdf = env_pdf(E, d);
-    return d;
+    // pdf from the sampled cell and sin(theta) themselves (re-deriving them from the rotated direction loses digits near the poles)
+    pdf = st > 0.f ? E.cell_prob[(size_t)iy * nx + ix] * (float)(nx * ny) / (2.f * kPi * kPi * st) : 0.f;
+    return env_to_world(E, V3{sinf(phi) * st, cosf(theta), -cosf(phi) * st});
 }
 
 // diffuse reflectance: constant or trilinear gridvolume on [0,1]^3 (clamp); optional gradient wrt p

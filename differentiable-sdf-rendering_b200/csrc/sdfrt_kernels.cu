@@ -454,6 +454,8 @@ struct sdfrt_ctx {
     int assign_rows = kBandRows;   // granularity of the row partition (sdfrt_set_partition_rows)
     int use_mis = 0;         // ReparamIntegrator prop use_mis (python/integrators/reparam.py:17)
     float* env_buf = nullptr;   // `envmap` emitter: bitmap + sampling tables in one allocation (sc.E points into it)
+    int env_has_rot = 0;        // to_world of the emitter (sdfrt_set_envmap_transform), kept across sdfrt_set_envmap_host
+    float env_R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     int antithetic = 0;  // ReparamIntegrator.antithetic_sampling (python/integrators/reparam.py:19); not used by sdf_prb_reparam
     bool have_sdf = false;
     // Adjoint state of a VIEW: the lane records of adjoint sweep 1, the scene it was rendered with and the per-view scratch of the
@@ -1410,6 +1412,8 @@ int sdfrt_set_envmap_host(sdfrt_ctx* ctx, const float* rgb_host, int width, int 
     cudaFree(ctx->env_buf);
     ctx->env_buf = nullptr;
     std::memset(&ctx->sc.E, 0, sizeof(ctx->sc.E));
+    ctx->sc.E.has_rot = ctx->env_has_rot;
+    for (int i = 0; i < 9; ++i) ctx->sc.E.R[i] = ctx->env_R[i];
     for (auto& v : ctx->view) v.adj_ready = false;
     if (rgb_host == nullptr) return SDFRT_OK;
     EnvTables t;
@@ -1425,6 +1429,32 @@ int sdfrt_set_envmap_host(sdfrt_ctx* ctx, const float* rgb_host, int width, int 
     SDFRT_CUDA(ctx, cudaMemcpy(d + n_data + n_m + n_c, t.cell_prob.data(), n_c * sizeof(float), cudaMemcpyHostToDevice));
     ctx->sc.E.data = d; ctx->sc.E.marg_cdf = d + n_data; ctx->sc.E.cond_cdf = d + n_data + n_m; ctx->sc.E.cell_prob = d + n_data + n_m + n_c;
     ctx->sc.E.W1 = t.W1; ctx->sc.E.H = t.H;
+    return SDFRT_OK;
+}
+
+int sdfrt_set_envmap_transform(sdfrt_ctx* ctx, const float* to_world) {
+    if (!ctx) return SDFRT_ERR_INVALID;
+    float R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    int has = 0;
+    if (to_world != nullptr) {
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) R[i * 3 + j] = to_world[i * 4 + j];
+        double err = 0.0;   // a rotation: R R^T = I, det = +1 (the emitter is at infinity: translation is ignored, scale is not allowed)
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                double v = 0.0;
+                for (int k = 0; k < 3; ++k) v += (double)R[i * 3 + k] * (double)R[j * 3 + k];
+                err = std::max(err, std::fabs(v - (i == j ? 1.0 : 0.0)));
+            }
+        const double det = (double)R[0] * ((double)R[4] * R[8] - (double)R[5] * R[7]) - (double)R[1] * ((double)R[3] * R[8] - (double)R[5] * R[6]) +
+                           (double)R[2] * ((double)R[3] * R[7] - (double)R[4] * R[6]);
+        if (err > 1e-4 || det < 0.0) return fail(ctx, SDFRT_ERR_INVALID, "the envmap's to_world must be a rotation");
+        has = !(R[0] == 1.f && R[4] == 1.f && R[8] == 1.f);
+    }
+    ctx->env_has_rot = has;
+    for (int i = 0; i < 9; ++i) { ctx->env_R[i] = R[i]; ctx->sc.E.R[i] = R[i]; }
+    ctx->sc.E.has_rot = has;
+    for (auto& v : ctx->view) v.adj_ready = false;
     return SDFRT_OK;
 }
 

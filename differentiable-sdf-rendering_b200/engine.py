@@ -124,9 +124,18 @@ class Context:
     def set_use_mis(self, enable):
         check(self.ctx, self.lib.sdfrt_set_use_mis(self.ctx, int(bool(enable))))
 
-    def set_envmap(self, rgb=None, scale=1.0):
+    def set_envmap(self, rgb=None, scale=1.0, to_world=None):
         """`envmap` emitter from an (H, W, 3) lat-long bitmap (numpy / CPU tensor; row 0 = +y pole), or None for the constant emitter
-        of set_shading.  sdf_direct_reparam only.  Copies the bitmap; synchronises the device."""
+        of set_shading.  to_world: 4x4 (or 3x3) rotation of the emitter, None = identity.  sdf_direct_reparam only.  Copies the
+        bitmap; synchronises the device."""
+        if to_world is None:
+            check(self.ctx, self.lib.sdfrt_set_envmap_transform(self.ctx, None))
+        else:
+            m = np.asarray(to_world, dtype=np.float64)
+            m4 = np.eye(4)
+            m4[:3, :3] = m[:3, :3]
+            m4 = np.ascontiguousarray(m4, dtype=np.float32)
+            check(self.ctx, self.lib.sdfrt_set_envmap_transform(self.ctx, m4.ctypes.data_as(C.c_void_p)))
         if rgb is None:
             check(self.ctx, self.lib.sdfrt_set_envmap_host(self.ctx, None, 0, 0, 1.0))
             return

@@ -61,7 +61,7 @@ class ReparamIntegrator:
         ctx.set_albedo(scene.albedo_grid)
         env_key = (id(scene), getattr(scene, 'envmap_version', 0)) if getattr(scene, 'envmap', None) is not None else None
         if getattr(ctx, '_envmap_key', None) != env_key:   # the bitmap is uploaded once per scene / change, not per view
-            ctx.set_envmap(None if env_key is None else scene.envmap, getattr(scene, 'envmap_scale', 1.0))
+            ctx.set_envmap(None if env_key is None else scene.envmap, getattr(scene, 'envmap_scale', 1.0), getattr(scene, 'envmap_to_world', None))
             ctx._envmap_key = env_key
         ctx.set_integrator(self.integrator_name)
         ctx.set_antithetic(self.antithetic_sampling)

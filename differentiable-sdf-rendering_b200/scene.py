@@ -71,12 +71,12 @@ class Scene:
         self._integrator = integrator
         self._sensors = list(sensors)
         self.env_radiance, self.albedo, self.albedo_grid, self.env_dist = env_radiance, albedo, albedo_grid, env_dist
-        self.envmap, self.envmap_scale, self.envmap_version = None, 1.0, 0
+        self.envmap, self.envmap_scale, self.envmap_version, self.envmap_to_world = None, 1.0, 0, None
 
-    def set_envmap(self, rgb, scale=1.0):
+    def set_envmap(self, rgb, scale=1.0, to_world=None):
         """Light the scene with an `envmap` emitter ((H, W, 3) lat-long bitmap, what the reference's scene files load from an .exr)
         instead of the constant one; None switches back.  Call again after changing the array."""
-        self.envmap, self.envmap_scale = rgb, scale
+        self.envmap, self.envmap_scale, self.envmap_to_world = rgb, scale, to_world
         self.envmap_version += 1
 
     def integrator(self):

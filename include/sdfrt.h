@@ -162,6 +162,10 @@ int sdfrt_set_use_mis(sdfrt_ctx* ctx, int enable);
  * Mitsuba's hierarchical sample warp is not restated; the estimator is unbiased either way).  sdf_direct_reparam only: a render with
  * sdf_prb_reparam fails with SDFRT_ERR_INVALID while an envmap is bound.  Synchronises the device. */
 int sdfrt_set_envmap_host(sdfrt_ctx* ctx, const float* rgb_host, int width, int height, float scale);
+/* `to_world` of the envmap emitter (<transform name="to_world"> of the scene file): row-major 4x4 in HOST memory, or NULL for the
+ * identity.  Must be a rotation (the emitter is at infinity: a translation is ignored, anything else is refused).  Lookup direction
+ * = to_world^-1 d, sampled directions are mapped with to_world (Mitsuba's envmap.cpp).  Kept across sdfrt_set_envmap_host. */
+int sdfrt_set_envmap_transform(sdfrt_ctx* ctx, const float* to_world);
 void sdfrt_prb_defaults(sdfrt_prb_params* p);
 int sdfrt_set_prb(sdfrt_ctx* ctx, const sdfrt_prb_params* p);      /* used when the integrator is SDFRT_INTEGRATOR_PRB */
 /* multi-GPU ray partition: the film rows (border included) are cut into bands of 8 rows; this context renders the

@@ -892,7 +892,10 @@ class EnvMap:
     cell, a different sample warp (deliberate deviation, the reference's estimator is unbiased either way).
     pdf over solid angle = cell probability * (res.x - 1)(res.y - 1) / (2 pi^2 sin theta)."""
 
-    def __init__(self, rgb, scale=1.0):
+    def __init__(self, rgb, scale=1.0, to_world=None):
+        """to_world: 3x3 rotation of the emitter (Mitsuba: `v = to_world.inverse() * (-si.wi)` before the lookup, sampled directions
+        are mapped with to_world); None = identity."""
+        self.R = None if to_world is None else torch.as_tensor(to_world, dtype=torch.float64).reshape(3, 3)
         rgb = torch.as_tensor(rgb, dtype=torch.float64) * scale          # (H, W, 3)
         self.data = torch.cat([rgb, rgb[:, :1]], 1).contiguous()       # (H, W + 1, 3)
         self.H, self.W1 = self.data.shape[0], self.data.shape[1]
@@ -907,6 +910,8 @@ class EnvMap:
 
     def _coord(self, d):
         """direction (unit) -> lookup coordinate c in [0, W) x [0, H - 1]."""
+        if self.R is not None:
+            d = d @ self.R.to(d.dtype)                                   # to_world^-1 d = R^T d  (row vectors: d R)
         u = torch.atan2(d[:, 0], -d[:, 2]) * (0.5 / math.pi)
         v = torch.acos(d[:, 1].clamp(-1.0, 1.0)) * (1.0 / math.pi)
         u = u - 0.5 / (self.W1 - 1)
@@ -929,7 +934,8 @@ class EnvMap:
         cx, cy = self._coord(d.detach())
         ix = torch.minimum(torch.floor(cx), torch.full_like(cx, self.W1 - 2)).long()
         iy = torch.minimum(torch.floor(cy), torch.full_like(cy, self.H - 2)).long()
-        sin_t = torch.sqrt((1 - d[:, 1].detach() ** 2).clamp_min(0.0))
+        dl = d.detach() if self.R is None else d.detach() @ self.R.to(d.dtype)
+        sin_t = torch.sqrt((1 - dl[:, 1] ** 2).clamp_min(0.0))
         p = self.cell_prob.to(d.dtype)[iy, ix] * ((self.W1 - 1) * (self.H - 1)) / (2 * math.pi ** 2 * sin_t.clamp_min(1e-30))
         return torch.where(sin_t > 0, p, torch.zeros_like(p))
 
@@ -950,6 +956,8 @@ class EnvMap:
         theta, phi = vv * math.pi, uu * 2 * math.pi
         st = torch.sin(theta)
         d = torch.stack([torch.sin(phi) * st, torch.cos(theta), -torch.cos(phi) * st], -1)
+        if self.R is not None:
+            d = d @ self.R.to(dt).T                                      # to_world d_local
         return d, self.pdf(d)
 
 

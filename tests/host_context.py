@@ -86,8 +86,8 @@ class HostContext:
     def set_shadow_origin(self, mode):
         self.shadow_origin = int(mode)
 
-    def set_envmap(self, rgb=None, scale=1.0):
-        self.envmap = None if rgb is None else (np.array(rgb.detach().cpu().numpy() if torch.is_tensor(rgb) else rgb, dtype=np.float32), float(scale))
+    def set_envmap(self, rgb=None, scale=1.0, to_world=None):
+        self.envmap = None if rgb is None else (np.array(rgb.detach().cpu().numpy() if torch.is_tensor(rgb) else rgb, dtype=np.float32), float(scale), to_world)
 
     def set_prb(self, max_depth=4, rr_depth=5):
         self.prb = dict(max_depth=int(max_depth), rr_depth=int(rr_depth))

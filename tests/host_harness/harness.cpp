@@ -25,6 +25,8 @@ struct hh_scene {
     int shadow_origin;   // sdf_direct_reparam: 0 si, 1 detach_indirect_si, 2 decouple_reparam
     int use_mis;         // ReparamIntegrator prop use_mis (sdf_direct_reparam's BSDF-sampling branch)
     const void* envmap;  // hh_envmap_create handle or NULL (constant emitter)
+    int env_has_rot;     // to_world rotation of the envmap (row-major 3x3)
+    float env_R[9];
 };
 
 static SceneParams build(const hh_scene* h) {
@@ -47,6 +49,8 @@ static SceneParams build(const hh_scene* h) {
         const EnvTables* t = (const EnvTables*)h->envmap;
         sc.E.data = t->data.data(); sc.E.marg_cdf = t->marg_cdf.data(); sc.E.cond_cdf = t->cond_cdf.data();
         sc.E.cell_prob = t->cell_prob.data(); sc.E.W1 = t->W1; sc.E.H = t->H;
+        sc.E.has_rot = h->env_has_rot;
+        for (int i = 0; i < 9; ++i) sc.E.R[i] = h->env_R[i];
     }
     return sc;
 }
@@ -65,9 +69,11 @@ void* hh_envmap_create(const float* rgb, int w, int h, float scale) {
 }
 void hh_envmap_destroy(void* t) { delete (EnvTables*)t; }
 // lookup / sampling of the emitter alone: out (n, 8) = Le rgb, pdf(d), sampled direction, its pdf
-int hh_envmap_query(const void* e, const float* d, const float* u, int n, float* out) {
+int hh_envmap_query(const void* e, const float* R /* 9 floats or NULL */, const float* d, const float* u, int n, float* out) {
     const EnvTables* t = (const EnvTables*)e;
     EnvView E;
+    E.has_rot = R != nullptr;
+    for (int i = 0; i < 9; ++i) E.R[i] = R ? R[i] : (i % 4 == 0 ? 1.f : 0.f);
     E.data = t->data.data(); E.marg_cdf = t->marg_cdf.data(); E.cond_cdf = t->cond_cdf.data(); E.cell_prob = t->cell_prob.data();
     E.W1 = t->W1; E.H = t->H;
     for (int i = 0; i < n; ++i) {

@@ -47,7 +47,7 @@ class HHScene(C.Structure):
                 ('albedo', C.c_void_p), ('ax', C.c_int), ('ay', C.c_int), ('az', C.c_int),
                 ('tracer', TracerParams), ('warp', WarpParams), ('sensor', SensorParams), ('shading', ShadingParams),
                 ('integrator', C.c_int), ('prb', PrbParams), ('antithetic', C.c_int), ('has_transform', C.c_int),
-                ('to_world', C.c_float * 16), ('shadow_origin', C.c_int), ('use_mis', C.c_int), ('envmap', C.c_void_p)]
+                ('to_world', C.c_float * 16), ('shadow_origin', C.c_int), ('use_mis', C.c_int), ('envmap', C.c_void_p), ('env_has_rot', C.c_int), ('env_R', C.c_float * 9)]
 
 
 def build():
@@ -99,8 +99,12 @@ class HostScene:
         self.border = 2
         self._env = None
 
-    def set_envmap(self, rgb, scale=1.0):
-        """`envmap` emitter from an (H, W, 3) bitmap (None: back to the constant emitter)."""
+    def set_envmap(self, rgb, scale=1.0, to_world=None):
+        """`envmap` emitter from an (H, W, 3) bitmap (None: back to the constant emitter); to_world: 3x3 rotation or None."""
+        self.h.env_has_rot = 0 if to_world is None else 1
+        self._env_R = None if to_world is None else np.ascontiguousarray(np.asarray(to_world, dtype=np.float64)[:3, :3], dtype=np.float32)
+        if to_world is not None:
+            self.h.env_R[:] = [float(v) for v in self._env_R.reshape(-1)]
         L = lib()
         L.hh_envmap_create.restype = C.c_void_p
         if self._env is not None:
@@ -117,7 +121,8 @@ class HostScene:
         d = np.ascontiguousarray(d, dtype=np.float32)
         u = np.ascontiguousarray(u, dtype=np.float32)
         out = np.zeros((d.shape[0], 8), np.float32)
-        lib().hh_envmap_query(C.c_void_p(self._env), fptr(d), fptr(u), d.shape[0], fptr(out))
+        R = getattr(self, '_env_R', None)
+        lib().hh_envmap_query(C.c_void_p(self._env), None if R is None else fptr(R), fptr(d), fptr(u), d.shape[0], fptr(out))
         return dict(Le=out[:, :3], pdf=out[:, 3], d=out[:, 4:7], d_pdf=out[:, 7])
 
     @property

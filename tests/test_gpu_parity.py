@@ -545,7 +545,13 @@ def test_envmap_emitter_against_oracle(sdfrt_mod, use_mis, albedo_res):
     W, spp = 20, 4
     osc = O.make_scene('knot', res=32, width=W, height=W, albedo_grid_res=albedo_res)
     bm = np.random.default_rng(1).uniform(0.05, 4.0, size=(24, 48, 3)).astype(np.float32)
-    osc.envmap = O.EnvMap(bm.astype(np.float64))
+    R = None
+    if use_mis:                       # the second case also rotates the emitter (<transform name="to_world"> of the scene file)
+        R, rr = np.linalg.qr(np.random.default_rng(5).normal(size=(3, 3)))
+        R = R * np.sign(np.diag(rr))
+        if np.linalg.det(R) < 0:
+            R[:, 0] = -R[:, 0]
+    osc.envmap = O.EnvMap(bm.astype(np.float64), to_world=R)
     osc.use_mis = use_mis
     owf = O.WarpField2D(osc.sdf, weight_strategy=6, edge_eps=0.01)
     owf.clamping_thresh = 0.05
@@ -556,7 +562,7 @@ def test_envmap_emitter_against_oracle(sdfrt_mod, use_mis, albedo_res):
     integ.warp_field = wf
     alb = None if albedo_res is None else osc.albedo_grid.float().cuda().contiguous().requires_grad_(True)
     scene = sdfrt.Scene(integ, [sdfrt.Sensor(osc.sensor.to_world, W, W)], albedo_grid=alb)
-    scene.set_envmap(bm)
+    scene.set_envmap(bm, to_world=R)
     g_in = np.random.default_rng(7).uniform(-1, 1, size=(W, W, 3))
     img_o, g_o, _, ga_o = O.render_backward(osc, owf, 'sdf_direct_reparam', torch.from_numpy(g_in), seed=11, spp=spp)
     with torch.no_grad():
@@ -576,7 +582,7 @@ def test_envmap_emitter_against_oracle(sdfrt_mod, use_mis, albedo_res):
         prb = sdfrt.integrators.create('sdf_prb_reparam', {}, sdf)
         prb.warp_field = wf
         scene2 = sdfrt.Scene(prb, scene.sensors())
-        scene2.set_envmap(bm)
+        scene2.set_envmap(bm, to_world=R)
         with pytest.raises(RuntimeError, match='envmap'):
             sdfrt.render(scene2, sensor=0, seed=1, spp=1)
     finally:

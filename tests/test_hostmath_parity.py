@@ -316,12 +316,24 @@ def _envmap_bitmap(h=8, w=16, seed=0):
     return (base + 4.0 * lobe[..., None] * np.array([1.0, 0.9, 0.7])).astype(np.float32)
 
 
-def test_envmap_lookup_sampling_pdf():
-    """`envmap` emitter (oracle/ref_semantics.md S18): lookup, sampled directions and pdf of the kernel math against the oracle."""
+def _rotation(seed=5):
+    """A general rotation matrix (to_world of an envmap emitter)."""
+    q, r = np.linalg.qr(np.random.default_rng(seed).normal(size=(3, 3)))
+    q = q * np.sign(np.diag(r))
+    if np.linalg.det(q) < 0:
+        q[:, 0] = -q[:, 0]
+    return q
+
+
+@pytest.mark.parametrize('rotated', [False, True])
+def test_envmap_lookup_sampling_pdf(rotated):
+    """`envmap` emitter (oracle/ref_semantics.md S18): lookup, sampled directions and pdf of the kernel math against the oracle,
+    without and with a to_world rotation of the emitter."""
     bm = _envmap_bitmap()
-    env = O.EnvMap(bm.astype(np.float64))
+    R = _rotation() if rotated else None
+    env = O.EnvMap(bm.astype(np.float64), to_world=R)
     _, _, hs = make_pair('sphere', 16, 8)
-    hs.set_envmap(bm)
+    hs.set_envmap(bm, to_world=R)
     rng = np.random.default_rng(3)
     d = rng.normal(size=(4000, 3))
     d /= np.linalg.norm(d, axis=-1, keepdims=True)
@@ -329,23 +341,25 @@ def test_envmap_lookup_sampling_pdf():
     got = hs.envmap_query(d, u)
     dd = torch.from_numpy(d.astype(np.float32).astype(np.float64))
     assert np.abs(got['Le'] - env.eval(dd).numpy()).max() < 2e-4          # cell coordinates in fp32: ~1e-5 of a cell
-    assert np.abs(got['pdf'] - env.pdf(dd).numpy()).max() < 1e-4 * env.pdf(dd).numpy().max()
+    pdf_o = env.pdf(dd).numpy()      # cell probability / sin(theta): near the (rotated) poles the fp32 direction limits sin(theta)
+    assert np.quantile(np.abs(got['pdf'] - pdf_o), 0.995) < 1e-4 * pdf_o.max() and (np.abs(got['pdf'] - pdf_o) < 5e-3 * pdf_o + 1e-6).all()
     ds, ps = env.sample(torch.from_numpy(u.astype(np.float32).astype(np.float64)))
     same = np.abs(got['d'] - ds.numpy()).max(-1) < 1e-3                    # a sample on a CDF boundary may pick the neighbouring cell
     assert same.mean() > 0.995
     assert np.abs(got['d_pdf'][same] - ps.numpy()[same]).max() < 1e-3 * ps.numpy().max()
 
 
-@pytest.mark.parametrize('use_mis,albedo_res', [(False, None), (True, 8)])
-def test_envmap_image_and_gradient_parity(use_mis, albedo_res):
+@pytest.mark.parametrize('use_mis,albedo_res,rotated', [(False, None, False), (True, 8, True)])
+def test_envmap_image_and_gradient_parity(use_mis, albedo_res, rotated):
     """sdf_direct_reparam lit by an `envmap` emitter: escaped camera rays, the importance-sampled emitter direction (emitter_val /
     ds.pdf) and the MIS branch's escaped BSDF rays all look the bitmap up with the ATTACHED directions
     (python/integrators/sdf_direct_reparam.py:31,62-70,105), so dLe/dd flows into the three warp sites."""
     W, spp = 20, 4
     sc, wf, hs = make_pair('knot', 32, W, 'sdf_direct_reparam', albedo_res=albedo_res)
     bm = _envmap_bitmap()
-    sc.envmap = O.EnvMap(bm.astype(np.float64))
-    hs.set_envmap(bm)
+    R = _rotation() if rotated else None
+    sc.envmap = O.EnvMap(bm.astype(np.float64), to_world=R)
+    hs.set_envmap(bm, to_world=R)
     sc.use_mis = use_mis
     hs.h.use_mis = int(use_mis)
     g_in = np.random.default_rng(7).uniform(-1, 1, size=(W, W, 3))
@@ -375,8 +389,9 @@ def test_envmap_direction_derivative():
     W, spp = 20, 4
     sc, wf, hs = make_pair('knot', 32, W, 'sdf_direct_reparam')
     bm = np.random.default_rng(1).uniform(0.05, 4.0, size=(48, 96, 3)).astype(np.float32)
-    sc.envmap = O.EnvMap(bm.astype(np.float64))
-    hs.set_envmap(bm)
+    R = _rotation(9)                  # (with a rotated emitter: d/d(d_world) = R d/d(d_local))
+    sc.envmap = O.EnvMap(bm.astype(np.float64), to_world=R)
+    hs.set_envmap(bm, to_world=R)
     g_in = np.random.default_rng(7).uniform(-1, 1, size=(W, W, 3))
     g_att = O.render_backward(sc, wf, 'sdf_direct_reparam', torch.from_numpy(g_in), seed=11, spp=spp)[1].numpy()
     ev = O.EnvMap.eval

@@ -20,7 +20,7 @@ def test_scene_envmap_reaches_the_context_once_per_change(monkeypatch, built):
     scene = sdfrt.Scene(integ, sensors)
     calls = []
     orig = sdf.ctx.set_envmap
-    monkeypatch.setattr(sdf.ctx, 'set_envmap', lambda rgb=None, scale=1.0: (calls.append(rgb is not None), orig(rgb, scale)))
+    monkeypatch.setattr(sdf.ctx, 'set_envmap', lambda rgb=None, scale=1.0, to_world=None: (calls.append(rgb is not None), orig(rgb, scale, to_world)))
     img_const = sdfrt.render(scene, sensor=0, seed=3, spp=spp)
     assert calls == []                                     # constant emitter: nothing to upload
     bm = np.random.default_rng(0).uniform(0.1, 2.0, size=(6, 12, 3)).astype(np.float32)
