@@ -68,7 +68,7 @@ void* hh_envmap_create(const float* rgb, int w, int h, float scale) {
     return t;
 }
 void hh_envmap_destroy(void* t) { delete (EnvTables*)t; }
-// lookup / sampling of the emitter alone: out (n, 8) = Le rgb, pdf(d), sampled direction, its pdf
+// lookup / sampling of the emitter alone: out (n, 17) = Le rgb, pdf(d), sampled direction, its pdf, dLe_c / dd (3 x 3, row c)
 int hh_envmap_query(const void* e, const float* R /* 9 floats or NULL */, const float* d, const float* u, int n, float* out) {
     const EnvTables* t = (const EnvTables*)e;
     EnvView E;
@@ -78,11 +78,13 @@ int hh_envmap_query(const void* e, const float* R /* 9 floats or NULL */, const 
     E.W1 = t->W1; E.H = t->H;
     for (int i = 0; i < n; ++i) {
         const V3 di = V3{d[3 * i], d[3 * i + 1], d[3 * i + 2]};
-        const V3 Le = env_eval(E, di, nullptr);
+        V3 dLe[3];
+        const V3 Le = env_eval(E, di, dLe);
         float pdf;
         const V3 s = env_sample(E, u[2 * i], u[2 * i + 1], pdf);
-        float* o = out + (size_t)i * 8;
+        float* o = out + (size_t)i * 17;
         o[0] = Le.x; o[1] = Le.y; o[2] = Le.z; o[3] = env_pdf(E, di); o[4] = s.x; o[5] = s.y; o[6] = s.z; o[7] = pdf;
+        for (int c = 0; c < 3; ++c) { o[8 + 3 * c] = dLe[c].x; o[9 + 3 * c] = dLe[c].y; o[10 + 3 * c] = dLe[c].z; }
     }
     return 0;
 }

@@ -120,10 +120,10 @@ class HostScene:
     def envmap_query(self, d, u):
         d = np.ascontiguousarray(d, dtype=np.float32)
         u = np.ascontiguousarray(u, dtype=np.float32)
-        out = np.zeros((d.shape[0], 8), np.float32)
+        out = np.zeros((d.shape[0], 17), np.float32)
         R = getattr(self, '_env_R', None)
         lib().hh_envmap_query(C.c_void_p(self._env), None if R is None else fptr(R), fptr(d), fptr(u), d.shape[0], fptr(out))
-        return dict(Le=out[:, :3], pdf=out[:, 3], d=out[:, 4:7], d_pdf=out[:, 7])
+        return dict(Le=out[:, :3], pdf=out[:, 3], d=out[:, 4:7], d_pdf=out[:, 7], dLe=out[:, 8:17].reshape(-1, 3, 3))
 
     @property
     def film_shape(self):

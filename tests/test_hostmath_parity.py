@@ -343,6 +343,14 @@ def test_envmap_lookup_sampling_pdf(rotated):
     assert np.abs(got['Le'] - env.eval(dd).numpy()).max() < 2e-4          # cell coordinates in fp32: ~1e-5 of a cell
     pdf_o = env.pdf(dd).numpy()      # cell probability / sin(theta): near the (rotated) poles the fp32 direction limits sin(theta)
     assert np.quantile(np.abs(got['pdf'] - pdf_o), 0.995) < 1e-4 * pdf_o.max() and (np.abs(got['pdf'] - pdf_o) < 5e-3 * pdf_o + 1e-6).all()
+    # closed-form dLe_c/dd of the kernel math (what the adjoint pushes into the warp sites) against autograd through the oracle's lookup
+    dg = dd[:500].clone().requires_grad_(True)
+    Le_o = env.eval(dg)
+    for c in range(3):
+        jac = torch.autograd.grad(Le_o[:, c].sum(), dg, retain_graph=True)[0].numpy()
+        scale = max(1.0, np.abs(jac).max())
+        # (cells are bilinear: the derivative jumps across cell borders, where fp32 may sit on the other side)
+        assert np.quantile(np.abs(got['dLe'][:500, c] - jac).max(-1), 0.98) < 2e-3 * scale
     ds, ps = env.sample(torch.from_numpy(u.astype(np.float32).astype(np.float64)))
     same = np.abs(got['d'] - ds.numpy()).max(-1) < 1e-3                    # a sample on a CDF boundary may pick the neighbouring cell
     assert same.mean() > 0.995
